@@ -1,0 +1,108 @@
+"""ctypes binding of libbgm_b200.so (include/bgm_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, the product path
+raises.  torch tensors are used only as device-memory containers; the library sees
+raw pointers and a raw cudaStream_t.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbgm_b200.so")
+
+_lib = None
+
+
+class BgmError(RuntimeError):
+    """A C-ABI call returned a negative bgm_status."""
+
+    def __init__(self, fn, code, msg):
+        super().__init__("%s failed (%d): %s" % (fn, code, msg))
+        self.code = code
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("dims", C.POINTER(C.c_int)), ("params", C.POINTER(C.c_float))]
+
+
+class MhArgs(C.Structure):
+    _fields_ = [
+        ("x_dev", C.c_void_p), ("y_dev", C.c_void_p), ("v_dev", C.c_void_p),
+        ("ldv", C.c_int), ("n", C.c_int),
+        ("z_state_dev", C.c_void_p), ("lp_state_dev", C.c_void_p),
+        ("init_mode", C.c_int), ("t_begin", C.c_int), ("t_end", C.c_int), ("burn_in", C.c_int),
+        ("q_sd_dev", C.c_void_p), ("eps_dev", C.c_void_p), ("u_dev", C.c_void_p),
+        ("seed", C.c_uint64), ("row_offset", C.c_int64),
+        ("out_samples_dev", C.c_void_p), ("accept_count_dev", C.c_void_p),
+        ("accept_mask_dev", C.c_void_p), ("lp_trace_dev", C.c_void_p),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/bgm_b200.h declares
+SYMBOLS = {
+    "bgm_last_error": (C.c_char_p, []),
+    "bgm_version": (C.c_int, []),
+    "bgm_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "bgm_causal_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int,
+                                    C.c_float, C.c_float, C.c_float,
+                                    C.POINTER(NetDesc), C.POINTER(NetDesc), C.POINTER(NetDesc)]),
+    "bgm_causal_destroy": (None, [C.c_void_p]),
+    "bgm_causal_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                  C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    "bgm_causal_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "bgm_causal_mh": (C.c_int, [C.c_void_p, C.POINTER(MhArgs), C.c_void_p]),
+    "bgm_mh_adapt_qsd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float,
+                                   C.c_void_p, C.c_void_p]),
+    "bgm_mh_noise": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_causal_effect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                    C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "bgm_fp32_peak_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
+}
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "bayesgm_b200: %s is missing.  Build it with `python -m bayesgm_b200._build` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the .so disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(fn_name, rc):
+    if rc != 0:
+        msg = load().bgm_last_error()
+        raise BgmError(fn_name, rc, msg.decode() if msg else "?")
+
+
+def call(fn_name, *args):
+    check(fn_name, getattr(load(), fn_name)(*args))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bayesgm_b200 needs a CUDA device (sm_100a); there is no CPU fallback.")
+    return torch
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,389 @@
+"""CausalBGM with the posterior-sampling path on B200 (sm_100a) kernels.
+
+Drop-in for the method surface of `bayesgm.models.causalbgm.CausalBGM`
+(`src/bayesgm/models/causalbgm/base.py`): same constructor, same method names,
+kwargs, return types and error behaviour for the path this package accelerates --
+`get_log_posterior` (:765), `metropolis_hastings_sampler` (:820),
+`infer_from_latent_posterior` (:671) and `predict` (:573).  Inputs and outputs are
+host NumPy arrays like the reference's; underneath every method calls the C ABI of
+libbgm_b200.so (include/bgm_b200.h) on device buffers.  There is no CPU fallback.
+
+Deterministic networks only (`use_bnn=False`): the Bayesian (DenseFlipout) nets are
+stochastic per call and batch-coupled and are not built yet.
+"""
+import ctypes as C
+import datetime
+import os
+
+import numpy as np
+
+from . import _lib
+from .datasets import Gaussian_sampler
+from .nets import DenseNet
+
+_DEFAULTS = dict(use_bnn=True, g_units=[64] * 5, e_units=[64] * 5, f_units=[64, 32, 8],
+                 h_units=[64, 32, 8], dz_units=[64, 32, 8], lr=0.0002, lr_theta=0.0001,
+                 lr_z=0.0001, g_d_freq=5, save_model=False, save_res=True, kl_weight=0.0001,
+                 use_z_rec=True)
+
+
+def _quantile_dim0(torch, a, q):
+    """np.quantile(a, q, axis=0) (linear interpolation) on the device, without
+    torch.quantile's input-size limit."""
+    srt = torch.sort(a, dim=0).values
+    pos = q * (a.shape[0] - 1)
+    lo = int(np.floor(pos))
+    hi = min(lo + 1, a.shape[0] - 1)
+    frac = float(pos - lo)
+    return srt[lo] + (srt[hi] - srt[lo]) * frac
+
+
+class CausalBGM(object):
+    """See the reference docstring, causalbgm/base.py:12-54, for `params`."""
+
+    def __init__(self, params, timestamp=None, random_seed=None):
+        self.params = params
+        self.timestamp = timestamp
+        p = dict(_DEFAULTS)
+        p.update(params)
+        self._p = p
+        if p['use_bnn']:
+            raise NotImplementedError(
+                "bayesgm_b200: use_bnn=True (DenseFlipout + training-mode BatchNorm, networks/bnn.py) "
+                "is not built; pass use_bnn=False (deterministic nets, networks/base.py).")
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        zd = sum(p['z_dims'])
+        z0, z1, z2, _ = p['z_dims']
+        rng = np.random.RandomState(random_seed) if random_seed is not None else np.random
+        self.g_net = DenseNet(zd, p['v_dim'] + 1, 'g_net', p['g_units'], rng)          # :74
+        self.e_net = DenseNet(p['v_dim'], zd, 'e_net', p['e_units'], rng)              # :76
+        self.f_net = DenseNet(z0 + z1 + 1, 2, 'f_net', p['f_units'], rng)              # :78
+        self.h_net = DenseNet(z0 + z2, 2, 'h_net', p['h_units'], rng)                  # :80
+        self.z_sampler = Gaussian_sampler(mean=np.zeros(zd), sd=1.0)                  # :88 (reseeds to 1024)
+        if self.timestamp is None:
+            self.timestamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
+        self.checkpoint_path = "{}/checkpoints/{}/{}".format(p['output_dir'], p['dataset'], self.timestamp)
+        if p['save_model'] and not os.path.exists(self.checkpoint_path):
+            os.makedirs(self.checkpoint_path)
+        self.save_dir = "{}/results/{}/{}".format(p['output_dir'], p['dataset'], self.timestamp)
+        if p['save_res'] and not os.path.exists(self.save_dir):
+            os.makedirs(self.save_dir)
+        self._handle = None
+        self.last_acceptance_rate = None
+        self.last_q_sd = None
+
+    # ------------------------------------------------------------------ plumbing
+    def get_config(self):
+        return {"params": self.params}
+
+    def initialize_nets(self, print_summary=False):
+        if print_summary:
+            for net in (self.g_net, self.f_net, self.h_net):
+                print(net.model_name, net.dims)
+
+    def set_weights(self, g=None, e=None, f=None, h=None):
+        """Load Keras-layout weights ([kernel, bias, ...] per net), e.g. exported from a
+        trained reference model with `net.get_weights()`."""
+        for net, w in ((self.g_net, g), (self.e_net, e), (self.f_net, f), (self.h_net, h)):
+            if w is not None:
+                net.set_weights(w)
+        self._drop_handle()
+
+    def _drop_handle(self):
+        if self._handle is not None:
+            _lib.load().bgm_causal_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._drop_handle()
+        except Exception:
+            pass
+
+    def _device_model(self):
+        """Packs g/f/h for the kernels (once per weight change)."""
+        if self._handle is None:
+            _lib.require_cuda()
+            p = self._p
+            zd4 = (C.c_int * 4)(*[int(d) for d in p['z_dims']])
+            gd, gk = self.g_net.desc()
+            fd, fk = self.f_net.desc()
+            hd, hk = self.h_net.desc()
+            h = C.c_void_p()
+            sig = [float(p[k]) if k in p else -1.0 for k in ('sigma_v', 'sigma_x', 'sigma_y')]
+            _lib.call("bgm_causal_create", C.byref(h), zd4, int(p['v_dim']), int(bool(p['binary_treatment'])),
+                      sig[0], sig[1], sig[2], C.byref(gd), C.byref(fd), C.byref(hd))
+            self._handle = h
+        return self._handle
+
+    def kernel_info(self):
+        smem, warps, nops = C.c_int(), C.c_int(), C.c_int()
+        macs, issued = C.c_longlong(), C.c_longlong()
+        _lib.call("bgm_causal_info", self._device_model(), C.byref(smem), C.byref(warps), C.byref(nops),
+                  C.byref(macs), C.byref(issued))
+        return dict(smem_bytes=smem.value, warps_per_cta=warps.value, n_ops=nops.value,
+                    macs_per_row=macs.value, issued_macs_per_row=issued.value)
+
+    @staticmethod
+    def _to_device(a, torch, cols=None):
+        """Host array (NumPy or torch CPU, possibly pinned) -> contiguous float32 device
+        tensor; `cols` pads the row length with zeros (the kernels need ldv % 4 == 0)."""
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        if t.dtype != torch.float32:
+            t = t.float()
+        if t.is_cuda:
+            d = t.contiguous()
+        else:
+            d = t.contiguous().to('cuda', non_blocking=True)
+        if cols is not None and d.shape[1] != cols:
+            pad = torch.zeros((d.shape[0], cols), dtype=torch.float32, device='cuda')
+            pad[:, :d.shape[1]] = d
+            d = pad
+        return d
+
+    def _stage(self, data):
+        torch = _lib.require_cuda()
+        data_x, data_y, data_v = data
+        n = len(data_x)
+        p = self._p['v_dim']
+        if data_v.shape[1] != p:
+            raise ValueError("data_v has %d columns, params['v_dim'] is %d" % (data_v.shape[1], p))
+        ldv = (p + 3) // 4 * 4
+        x = self._to_device(data_x, torch).reshape(-1)
+        y = self._to_device(data_y, torch).reshape(-1)
+        v = self._to_device(data_v, torch, cols=ldv)
+        assert x.numel() == n and y.numel() == n and v.shape[0] == n
+        return torch, x, y, v, ldv, n
+
+    # --------------------------------------------------------------- hot path
+    def get_log_posterior(self, data_x, data_y, data_v, data_z, eps=1e-6):
+        """causalbgm/base.py:765-817 -> (n,) float32 NumPy array."""
+        torch, x, y, v, ldv, n = self._stage((data_x, data_y, data_v))
+        z = self._to_device(data_z, torch)
+        zd = sum(self._p['z_dims'])
+        if z.shape != (n, zd):
+            raise ValueError("data_z must have shape (%d, %d)" % (n, zd))
+        out = torch.empty(n, dtype=torch.float32, device='cuda')
+        _lib.call("bgm_causal_logpost", self._device_model(), _lib.ptr(x), _lib.ptr(y), _lib.ptr(v), ldv,
+                  _lib.ptr(z), n, _lib.ptr(out), _lib.stream_ptr())
+        return out.cpu().numpy()
+
+    def _mh_device(self, x, y, v, ldv, n, burn_in, n_keep, q_sd, adaptive_sd, initial_q_sd,
+                   target_acceptance_rate, tolerance, adjustment_interval, window_size,
+                   seed, row_offset, noise=None, trace=False, keep_samples=True):
+        """Runs the sampler on staged device buffers; returns a dict of device tensors."""
+        torch = _lib.require_cuda()
+        zd = sum(self._p['z_dims'])
+        T = burn_in + n_keep
+        m = self._device_model()
+        dev = 'cuda'
+        z_state = torch.empty((n, zd), dtype=torch.float32, device=dev)
+        lp_state = torch.empty(n, dtype=torch.float32, device=dev)
+        samples = torch.empty((n_keep, n, zd), dtype=torch.float32, device=dev) if keep_samples else None
+        acc_count = torch.zeros(T, dtype=torch.int32, device=dev)
+        q = torch.tensor([initial_q_sd if adaptive_sd else q_sd], dtype=torch.float32, device=dev)
+        a = _lib.MhArgs()
+        a.x_dev, a.y_dev, a.v_dev = x.data_ptr(), y.data_ptr(), v.data_ptr()
+        a.ldv, a.n = ldv, n
+        a.z_state_dev, a.lp_state_dev = z_state.data_ptr(), lp_state.data_ptr()
+        a.burn_in = burn_in
+        a.q_sd_dev = q.data_ptr()
+        a.seed, a.row_offset = int(seed) & (2 ** 64 - 1), int(row_offset)
+        a.out_samples_dev = samples.data_ptr() if keep_samples else None
+        a.accept_count_dev = acc_count.data_ptr()
+        keep = []
+        if noise is not None:
+            z0 = self._to_device(noise['z0'], torch)
+            eps = self._to_device(noise['eps'], torch)
+            u = torch.from_numpy(np.ascontiguousarray(noise['u'], dtype=np.float64)).to(dev)
+            assert z0.shape == (n, zd) and eps.shape == (T, n, zd) and u.shape == (T, n)
+            z_state.copy_(z0)
+            a.eps_dev, a.u_dev = eps.data_ptr(), u.data_ptr()
+            a.init_mode = 1
+            keep += [eps, u]
+        else:
+            a.init_mode = 2
+        out = dict(samples=samples, z_state=z_state, lp_state=lp_state, accept_count=acc_count, q_sd=q)
+        if trace:
+            out['accept_mask'] = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+            out['lp_trace'] = torch.zeros((T, n), dtype=torch.float32, device=dev)
+            a.accept_mask_dev = out['accept_mask'].data_ptr()
+            a.lp_trace_dev = out['lp_trace'].data_ptr()
+        st = _lib.stream_ptr()
+        if not adaptive_sd:
+            a.t_begin, a.t_end = 0, T
+            _lib.call("bgm_causal_mh", m, C.byref(a), st)
+        else:
+            # q_sd changes after iterations 50, 100, ... < burn_in (:880): one launch per
+            # constant-q_sd stretch, the rule itself runs on the device in between.
+            cuts = [c for c in range(adjustment_interval, burn_in, adjustment_interval)]
+            begin = 0
+            for c in cuts + [None]:
+                end = T if c is None else c + 1
+                a.t_begin, a.t_end = begin, end
+                _lib.call("bgm_causal_mh", m, C.byref(a), st)
+                a.init_mode = 0
+                if c is not None:
+                    _lib.call("bgm_mh_adapt_qsd", C.c_void_p(acc_count.data_ptr()), c, window_size, n,
+                              float(target_acceptance_rate), float(tolerance), C.c_void_p(q.data_ptr()), st)
+                begin = end
+        out['_keep'] = keep
+        return out
+
+    def metropolis_hastings_sampler(self, data, initial_q_sd=1.0, q_sd=None, burn_in=5000, n_keep=3000,
+                                    target_acceptance_rate=0.25, tolerance=0.05, adjustment_interval=50,
+                                    adaptive_sd=None, window_size=100, *, seed=None, noise=None,
+                                    return_trace=False, verbose=1):
+        """causalbgm/base.py:820-904 -> np.ndarray (n_keep, n, zd).
+
+        Noise: by default an in-kernel Philox4x32-10 stream keyed by `seed` (drawn from
+        NumPy's global generator when None, so `np.random.seed` still makes runs
+        repeatable).  `noise=dict(z0, eps, u)` injects pre-drawn N(0,1) / U(0,1) values
+        (shapes (n,zd), (T,n,zd), (T,n)) for state-for-state parity tests.
+        """
+        torch, x, y, v, ldv, n = self._stage(data)
+        if adaptive_sd is None:                                                   # :852-853
+            adaptive_sd = (q_sd is None or q_sd <= 0)
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+        r = self._mh_device(x, y, v, ldv, n, int(burn_in), int(n_keep), q_sd, adaptive_sd, initial_q_sd,
+                            target_acceptance_rate, tolerance, adjustment_interval, window_size,
+                            seed, 0, noise=noise, trace=return_trace)
+        samples = r['samples'].cpu().numpy()
+        counts = r['accept_count'].cpu().numpy()
+        T = burn_in + n_keep
+        w = min(window_size, T)
+        self.last_acceptance_rate = float(counts[T - w:].sum()) / (w * n)         # :901
+        self.last_q_sd = float(r['q_sd'].cpu()[0])
+        if verbose:
+            print(f"Final MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
+        if return_trace:
+            tr = dict(accept=r['accept_mask'].cpu().numpy().astype(bool), lp_prop=r['lp_trace'].cpu().numpy(),
+                      accept_count=counts, q_sd_final=self.last_q_sd,
+                      z_final=r['z_state'].cpu().numpy(), lp_final=r['lp_state'].cpu().numpy())
+            return samples, tr
+        return samples
+
+    def _effect_device(self, z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=None):
+        torch = _lib.require_cuda()
+        m = self._device_model()
+        if self._p['binary_treatment']:
+            ite = torch.empty((n_keep, n), dtype=torch.float32, device='cuda')
+            nz = self._to_device(noise, torch) if noise is not None else None
+            _lib.call("bgm_causal_effect", m, _lib.ptr(z_samples), n_keep, n, None, 2, int(bool(sample_y)),
+                      int(seed) & (2 ** 64 - 1), int(row_offset), _lib.ptr(nz), None, _lib.ptr(ite),
+                      _lib.stream_ptr())
+            return ite
+        xv = torch.tensor(np.asarray(x_values, dtype=np.float32), device='cuda')
+        sums = torch.zeros((len(x_values), n_keep), dtype=torch.float64, device='cuda')
+        nz = self._to_device(noise, torch) if noise is not None else None
+        _lib.call("bgm_causal_effect", m, _lib.ptr(z_samples), n_keep, n, _lib.ptr(xv), len(x_values),
+                  int(bool(sample_y)), int(seed) & (2 ** 64 - 1), int(row_offset), _lib.ptr(nz),
+                  _lib.ptr(sums), None, _lib.stream_ptr())
+        return sums
+
+    def infer_from_latent_posterior(self, data_posterior_z, x_values=None, sample_y=True, eps=1e-6, *,
+                                    seed=None, noise=None):
+        """causalbgm/base.py:671-763.  Binary: ITE (n_keep, n); continuous: ADRF draws
+        (len(x_values), n_keep).  `noise` injects the N(0,1) draws of :704/:725/:753
+        (binary (2,n_keep,n): x=1 then x=0; continuous (len(x_values), n_keep, n))."""
+        torch = _lib.require_cuda()
+        zs = self._to_device(data_posterior_z, torch)
+        n_keep, n, zd = zs.shape
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1))
+        if self._p['binary_treatment']:
+            return self._effect_device(zs, n_keep, n, None, sample_y, seed, 0, noise).cpu().numpy()
+        x_values = np.atleast_1d(np.asarray(x_values, dtype=float))
+        sums = self._effect_device(zs, n_keep, n, x_values, sample_y, seed, 0, noise)
+        return (sums / float(n)).float().cpu().numpy()
+
+    def predict(self, data, alpha=0.01, n_mcmc=3000, burn_in=5000, x_values=None, q_sd=1.0, sample_y=True,
+                bs=10000, *, seed=None, group=None, row_offset=0, verbose=1):
+        """causalbgm/base.py:573-668 -> (effect, posterior interval).
+
+        The kept states never leave the device: each `bs` slice is sampled and reduced
+        to ITE draws / ADRF partial sums on the GPU.  Under torch.distributed pass
+        `group` (and this rank's global `row_offset`): every rank processes its own
+        shard of rows and the ADRF sums are all-reduced once at the end (no collective
+        inside the sampling loop).
+        """
+        assert 0 < alpha < 1, "The significance level 'alpha' must be greater than 0 and less than 1."
+        if not self._p['binary_treatment']:
+            if x_values is None:
+                raise ValueError("For continuous treatment, 'x_values' must not be None. "
+                                 "Provide a list or a single treatment value.")
+        if x_values is not None:
+            x_values = np.array([x_values], dtype=float) if np.isscalar(x_values) else np.array(x_values, dtype=float)
+        torch = _lib.require_cuda()
+        data_x, data_y, data_v = data
+        n_test = len(data_x)
+        bs = max(1, int(bs))
+        if seed is None:
+            seed = int(np.random.randint(0, 2 ** 31 - 1)) * (2 ** 31) + int(np.random.randint(0, 2 ** 31 - 1))
+        if verbose:
+            print('MCMC Latent Variable Sampling ...')
+        adaptive = (q_sd is None or q_sd <= 0)
+        binary = self._p['binary_treatment']
+        if binary:
+            ite_mean = np.zeros(n_test, dtype=np.float32)
+            upper = np.zeros(n_test, dtype=np.float32)
+            lower = np.zeros(n_test, dtype=np.float32)
+        else:
+            sums = torch.zeros((len(x_values), n_mcmc), dtype=torch.float64, device='cuda')
+            n_seen = 0
+        for start in range(0, n_test, bs):
+            end = min(start + bs, n_test)
+            _, x, y, v, ldv, n = self._stage((data_x[start:end], data_y[start:end], data_v[start:end]))
+            r = self._mh_device(x, y, v, ldv, n, int(burn_in), int(n_mcmc), q_sd, adaptive, 1.0, 0.25, 0.05,
+                                50, 100, seed, row_offset + start)
+            eff = self._effect_device(r['samples'], int(n_mcmc), n, x_values, sample_y, seed,
+                                      row_offset + start)
+            if binary:                                                            # :640-642
+                ite_mean[start:end] = eff.mean(dim=0).cpu().numpy()
+                lower[start:end] = _quantile_dim0(torch, eff, alpha / 2).cpu().numpy()
+                upper[start:end] = _quantile_dim0(torch, eff, 1 - alpha / 2).cpu().numpy()
+            else:                                                                 # :660-661
+                sums += eff
+                n_seen += n
+        if binary:
+            return ite_mean, np.stack([lower, upper], axis=1)
+        if group is not None:
+            import torch.distributed as dist
+            cnt = torch.tensor([float(n_seen)], dtype=torch.float64, device='cuda')
+            dist.all_reduce(sums, group=group)
+            dist.all_reduce(cnt, group=group)
+            n_seen = float(cnt.item())
+        ce = (sums / float(n_seen)).float().cpu().numpy()                         # :663-667
+        ADRF = np.mean(ce, axis=1)
+        up = np.quantile(ce, 1 - alpha / 2, axis=1)
+        lo = np.quantile(ce, alpha / 2, axis=1)
+        return ADRF, np.stack([lo, up], axis=1)
+
+    def philox_noise(self, seed, n, T, row_offset=0):
+        """The exact noise `metropolis_hastings_sampler(seed=...)` draws in-kernel, as
+        host arrays dict(z0, eps, u) -- lets a Philox run be replayed through any other
+        implementation of the algorithm (used by the parity tests)."""
+        torch = _lib.require_cuda()
+        zd = sum(self._p['z_dims'])
+        z0 = torch.empty((n, zd), dtype=torch.float32, device='cuda')
+        eps = torch.empty((T, n, zd), dtype=torch.float32, device='cuda')
+        u = torch.empty((T, n), dtype=torch.float64, device='cuda')
+        _lib.call("bgm_mh_noise", int(seed) & (2 ** 64 - 1), int(row_offset), n, zd, 0, T, _lib.ptr(z0),
+                  _lib.ptr(eps), _lib.ptr(u), _lib.stream_ptr())
+        return dict(z0=z0.cpu().numpy(), eps=eps.cpu().numpy(), u=u.cpu().numpy())
+
+    # ------------------------------------------------- not on the hot path yet
+    def fit(self, data, epochs=100, epochs_per_eval=5, batch_size=32, startoff=0, use_egm_init=True,
+            egm_n_iter=30000, egm_batches_per_eval=500, save_format='txt', verbose=1):
+        raise NotImplementedError(
+            "bayesgm_b200: the training path (egm_init / iterative updates, causalbgm/base.py:156-532) "
+            "has no sm_100a kernels yet; load trained weights with set_weights().")
+
+    def egm_init(self, data, egm_n_iter=30000, batch_size=32, egm_batches_per_eval=500, verbose=1):
+        raise NotImplementedError(
+            "bayesgm_b200: EGM initialisation (causalbgm/base.py:305-431) has no sm_100a kernels yet.")

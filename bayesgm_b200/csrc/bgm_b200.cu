@@ -1,0 +1,441 @@
+// libbgm_b200.so -- C ABI (include/bgm_b200.h) over the sm_100a kernels.
+// Host code here only packs weights, validates arguments and launches.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "causal.cuh"
+
+namespace bgm {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ----------------------------------------------------------- weight packer --
+// A Dense layer W[K][N] (+bias) whose K input rows have already been mapped onto
+// rows of the source buffer (`krows`), cut into column tiles [kp][NT] | bias[NT].
+struct Packer {
+  std::vector<float> image;
+  std::vector<TileOp> ops;
+  long long macs = 0, issued = 0;
+
+  // Wm: dense [krows][N] row-major (krows = rows of the source buffer actually used)
+  void add_tile(const std::vector<float>& Wm, const std::vector<float>& b, int krows, int N,
+                int col_begin, int ncols, int ctype, int src, int epi, int c0) {
+    static const int NTS[3] = {64, 32, 8};
+    const int NT = NTS[ctype];
+    const int kp = round_up(krows, 4);
+    TileOp op;
+    memset(&op, 0, sizeof(op));
+    op.w_off = (int)image.size();
+    image.resize(image.size() + (size_t)kp * NT, 0.f);
+    for (int k = 0; k < krows; ++k)
+      for (int c = 0; c < ncols; ++c)
+        image[op.w_off + (size_t)k * NT + c] = Wm[(size_t)k * N + col_begin + c];
+    op.b_off = (int)image.size();
+    image.resize(image.size() + NT, 0.f);
+    for (int c = 0; c < ncols; ++c) image[op.b_off + c] = b[col_begin + c];
+    op.kp = (short)kp;
+    op.ctype = (unsigned char)ctype;
+    op.src = (unsigned char)src;
+    op.epi = (unsigned char)epi;
+    op.c0 = (short)c0;
+    op.nvalid = (short)ncols;
+    ops.push_back(op);
+    issued += (long long)kp * NT;
+  }
+
+  // hidden layer: one tile, LeakyReLU, output to the activation buffer
+  int add_hidden(const std::vector<float>& Wm, const std::vector<float>& b, int krows, int N,
+                 int src, int epi = EPI_ACT) {
+    if (N > 64) return -1;
+    const int ctype = N > 32 ? 0 : (N > 8 ? 1 : 2);
+    add_tile(Wm, b, krows, N, 0, N, ctype, src, epi, 0);
+    return 0;
+  }
+
+  // output columns [col_begin, col_begin+ncols) of a final layer, cut by issue cost
+  // (per k: NT=64 costs 68 slots, NT=32 35, NT=8 11)
+  void add_final(const std::vector<float>& Wm, const std::vector<float>& b, int krows, int N,
+                 int col_begin, int ncols, int src, int epi, int c0) {
+    int done = 0;
+    while (done < ncols) {
+      const int rem = ncols - done;
+      int ctype, take;
+      if (rem > 48) { ctype = 0; take = std::min(rem, 64); }
+      else if (rem > 24) { ctype = 1; take = std::min(rem, 32); }
+      else { ctype = 2; take = std::min(rem, 8); }
+      add_tile(Wm, b, krows, N, col_begin + done, take, ctype, src, epi, c0 + done);
+      done += take;
+    }
+  }
+};
+
+struct HostNet {
+  int L;
+  std::vector<int> dims;
+  std::vector<std::vector<float>> W, b;
+};
+static int read_net(const bgm_net_desc* d, HostNet& n, const char* name) {
+  if (!d || d->n_layers < 1 || !d->dims || !d->params)
+    return fail(BGM_ERR_ARG, std::string(name) + ": null / empty net description");
+  n.L = d->n_layers;
+  n.dims.assign(d->dims, d->dims + n.L + 1);
+  const float* p = d->params;
+  for (int l = 0; l < n.L; ++l) {
+    const int K = n.dims[l], N = n.dims[l + 1];
+    if (K < 1 || N < 1) return fail(BGM_ERR_ARG, std::string(name) + ": non-positive layer size");
+    n.W.emplace_back(p, p + (size_t)K * N);
+    p += (size_t)K * N;
+    n.b.emplace_back(p, p + N);
+    p += N;
+  }
+  return 0;
+}
+
+}  // namespace bgm
+
+using namespace bgm;
+
+struct bgm_causal {
+  CausalProgram prog;
+  float* image_dev = nullptr;
+  int warps = 0;
+  int smem_bytes = 0;
+  int effect_warps = 0;
+  int effect_smem_bytes = 0;
+  int sm_count = 0;
+  long long macs = 0, issued = 0;
+};
+
+static int check_data(const char* fn, const float* x, const float* y, const float* v, int ldv, int n,
+                      int p) {
+  if (!x || !y || !v) return fail(BGM_ERR_ARG, std::string(fn) + ": null data pointer");
+  if (n < 1) return fail(BGM_ERR_ARG, std::string(fn) + ": n must be >= 1");
+  if (ldv < p || ldv % 4 != 0)
+    return fail(BGM_ERR_ARG, std::string(fn) + ": ldv must be >= v_dim and a multiple of 4");
+  if (reinterpret_cast<uintptr_t>(v) % 16 != 0)
+    return fail(BGM_ERR_ARG, std::string(fn) + ": v_dev must be 16-byte aligned");
+  return 0;
+}
+
+template <int ZMAX>
+static int launch_mh_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream_t st) {
+  auto k = causal_mh_kernel<ZMAX>;
+  BGM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes));
+  k<<<grid, m->warps * 32, m->smem_bytes, st>>>(m->prog, m->image_dev, D);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static int launch_mh(const bgm_causal* m, const MhDev& D, cudaStream_t st) {
+  const int ntiles = (D.a.n + TILE_ROWS - 1) / TILE_ROWS;
+  const int grid = std::max(1, std::min((ntiles + m->warps - 1) / m->warps, m->sm_count));
+  const int zd = m->prog.zd;
+  if (zd <= 8) return launch_mh_t<8>(m, D, grid, st);
+  if (zd <= 16) return launch_mh_t<16>(m, D, grid, st);
+  return launch_mh_t<32>(m, D, grid, st);
+}
+
+extern "C" {
+
+const char* bgm_last_error(void) { return g_last_error.c_str(); }
+int bgm_version(void) { return 100; }
+
+int bgm_device_info(int* sm_count, int* smem_optin_bytes, int* clock_khz) {
+  int dev = 0;
+  BGM_CUDA_OK(cudaGetDevice(&dev));
+  if (sm_count) BGM_CUDA_OK(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+  if (smem_optin_bytes)
+    BGM_CUDA_OK(cudaDeviceGetAttribute(smem_optin_bytes, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  if (clock_khz) BGM_CUDA_OK(cudaDeviceGetAttribute(clock_khz, cudaDevAttrClockRate, dev));
+  return 0;
+}
+
+int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int binary_treatment,
+                      float sigma_v, float sigma_x, float sigma_y, const bgm_net_desc* g_net,
+                      const bgm_net_desc* f_net, const bgm_net_desc* h_net) {
+  if (!out || !z_dims) return fail(BGM_ERR_ARG, "bgm_causal_create: null argument");
+  *out = nullptr;
+  const int d0 = z_dims[0], d1 = z_dims[1], d2 = z_dims[2], d3 = z_dims[3];
+  if (d0 < 0 || d1 < 0 || d2 < 0 || d3 < 0) return fail(BGM_ERR_ARG, "z_dims must be >= 0");
+  const int zd = d0 + d1 + d2 + d3;
+  if (zd < 1 || zd > 32) return fail(BGM_ERR_UNSUPPORTED, "sum(z_dims) must be in [1, 32]");
+  if (v_dim < 1) return fail(BGM_ERR_ARG, "v_dim must be >= 1");
+  HostNet g, f, h;
+  int rc;
+  if ((rc = read_net(g_net, g, "g_net"))) return rc;
+  if ((rc = read_net(f_net, f, "f_net"))) return rc;
+  if ((rc = read_net(h_net, h, "h_net"))) return rc;
+  if (g.dims[0] != zd || g.dims[g.L] != v_dim + 1)
+    return fail(BGM_ERR_ARG, "g_net must map sum(z_dims) -> v_dim+1 (causalbgm/base.py:74)");
+  if (f.dims[0] != d0 + d1 + 1 || f.dims[f.L] != 2)
+    return fail(BGM_ERR_ARG, "f_net must map z0+z1+1 -> 2 (causalbgm/base.py:78)");
+  if (h.dims[0] != d0 + d2 || h.dims[h.L] != 2)
+    return fail(BGM_ERR_ARG, "h_net must map z0+z2 -> 2 (causalbgm/base.py:80)");
+  if (g.L < 2 || f.L < 2 || h.L < 2)
+    return fail(BGM_ERR_UNSUPPORTED, "each net needs at least one hidden layer");
+
+  const int kin = round_up(zd + 1, 4);
+  Packer pk;
+  CausalProgram P;
+  memset(&P, 0, sizeof(P));
+
+  // maps each net's first-layer input rows onto rows of the shared input buffer
+  // zin = [z (zd rows), x (row zd), zero pad]
+  auto remap_first = [&](const HostNet& net, const std::vector<int>& rows) {
+    const int N = net.dims[1];
+    std::vector<float> Wm((size_t)(zd + 1) * N, 0.f);
+    for (size_t k = 0; k < rows.size(); ++k)
+      for (int c = 0; c < N; ++c) Wm[(size_t)rows[k] * N + c] = net.W[0][k * N + c];
+    return Wm;
+  };
+  auto add_net = [&](const HostNet& net, const std::vector<int>& rows, int kind) -> int {
+    // kind 0: g (SSE over v_dim columns + sigma head), 1: f / h (mu, sigma -> scratch)
+    for (int l = 0; l < net.L; ++l) {
+      const int K = net.dims[l], N = net.dims[l + 1];
+      pk.macs += (long long)K * N;
+      const bool last = l == net.L - 1;
+      const int src = l == 0 ? 0 : 1;
+      const std::vector<float>& Wm = l == 0 ? remap_first(net, rows) : net.W[l];
+      const int krows = l == 0 ? zd + 1 : K;
+      if (l > 0 && K > ACT_ROWS) return -1;
+      if (!last) {
+        if (pk.add_hidden(Wm, net.b[l], krows, N, src)) return -1;
+      } else if (kind == 0) {
+        pk.add_final(Wm, net.b[l], krows, N, 0, v_dim, src, EPI_SSE, 0);
+        if (sigma_v < 0.f) pk.add_final(Wm, net.b[l], krows, N, v_dim, 1, src, EPI_OUT, 1);
+      } else {
+        pk.add_final(Wm, net.b[l], krows, N, 0, 2, src, EPI_OUT, 0);
+      }
+    }
+    return 0;
+  };
+  std::vector<int> g_rows, f_rows, h_rows;
+  for (int k = 0; k < zd; ++k) g_rows.push_back(k);
+  for (int k = 0; k < d0 + d1; ++k) f_rows.push_back(k);
+  f_rows.push_back(zd);  // x
+  for (int k = 0; k < d0; ++k) h_rows.push_back(k);
+  for (int k = 0; k < d2; ++k) h_rows.push_back(d0 + d1 + k);
+  const char* wide = "hidden layers wider than 64 units are not supported by the sm_100a sampler kernel";
+  if (add_net(g, g_rows, 0)) return fail(BGM_ERR_UNSUPPORTED, wide);
+  P.g_end = (int)pk.ops.size();
+  P.f_img_begin = (int)pk.image.size();
+  if (add_net(f, f_rows, 1)) return fail(BGM_ERR_UNSUPPORTED, wide);
+  P.f_end = (int)pk.ops.size();
+  P.f_img_end = (int)pk.image.size();
+  if (add_net(h, h_rows, 1)) return fail(BGM_ERR_UNSUPPORTED, wide);
+  P.h_end = (int)pk.ops.size();
+  P.n_ops = P.h_end;
+  if (P.n_ops > MAX_OPS) return fail(BGM_ERR_UNSUPPORTED, "too many column tiles (v_dim too large)");
+  for (int i = 0; i < P.n_ops; ++i) P.ops[i] = pk.ops[i];
+  P.zd = zd;
+  P.kin = kin;
+  P.p = v_dim;
+  P.binary = binary_treatment ? 1 : 0;
+  P.s2v = sigma_v >= 0.f ? sigma_v * sigma_v : -1.f;
+  P.s2x = sigma_x >= 0.f ? sigma_x * sigma_x : -1.f;
+  P.s2y = sigma_y >= 0.f ? sigma_y * sigma_y : -1.f;
+  pk.image.resize(pk.image.size() + IMG_PAD, 0.f);
+  P.image_floats = (int)pk.image.size();
+  P.per_warp_floats = (ACT_ROWS + kin + SCR_SLOTS) * TILE_ROWS;
+
+  int dev = 0, smem_max = 0, sms = 0;
+  BGM_CUDA_OK(cudaGetDevice(&dev));
+  BGM_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  BGM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int static_smem = 64;  // mbarrier + alignment slack
+  auto fit = [&](int img_floats) {
+    int w = (smem_max - static_smem - img_floats * 4) / (P.per_warp_floats * 4);
+    return std::min(w, MAX_WARPS);
+  };
+  bgm_causal* m = new bgm_causal();
+  m->warps = fit(P.image_floats);
+  if (m->warps < 1) {
+    delete m;
+    return fail(BGM_ERR_NOMEM, "packed nets do not fit in shared memory");
+  }
+  if (m->warps > 8) m->warps = (m->warps / 4) * 4;  // keep the 4 SM sub-partitions balanced
+  m->smem_bytes = (P.image_floats + m->warps * P.per_warp_floats) * 4;
+  const int f_floats = P.f_img_end - P.f_img_begin + IMG_PAD;
+  m->effect_warps = std::min(fit(f_floats), MAX_WARPS);
+  m->effect_smem_bytes = (f_floats + m->effect_warps * P.per_warp_floats) * 4;
+  m->sm_count = sms;
+  m->prog = P;
+  m->macs = pk.macs;
+  m->issued = pk.issued;
+  cudaError_t e = cudaMalloc(&m->image_dev, pk.image.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->image_dev, pk.image.data(), pk.image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (m->image_dev) cudaFree(m->image_dev);
+    delete m;
+    return fail(BGM_ERR_CUDA, std::string("uploading weight image: ") + cudaGetErrorString(e));
+  }
+  *out = m;
+  return 0;
+}
+
+void bgm_causal_destroy(bgm_causal* m) {
+  if (!m) return;
+  if (m->image_dev) cudaFree(m->image_dev);
+  delete m;
+}
+
+int bgm_causal_info(const bgm_causal* m, int* smem_bytes, int* warps_per_cta, int* n_ops,
+                    long long* macs_per_row, long long* issued_macs_per_row) {
+  if (!m) return fail(BGM_ERR_ARG, "null model");
+  if (smem_bytes) *smem_bytes = m->smem_bytes;
+  if (warps_per_cta) *warps_per_cta = m->warps;
+  if (n_ops) *n_ops = m->prog.n_ops;
+  if (macs_per_row) *macs_per_row = m->macs;
+  if (issued_macs_per_row) *issued_macs_per_row = m->issued;
+  return 0;
+}
+
+int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_dev,
+                       const float* v_dev, int ldv, const float* z_dev, int n, float* out_logp_dev,
+                       void* stream) {
+  if (!m) return fail(BGM_ERR_ARG, "bgm_causal_logpost: null model");
+  int rc = check_data("bgm_causal_logpost", x_dev, y_dev, v_dev, ldv, n, m->prog.p);
+  if (rc) return rc;
+  if (!z_dev || !out_logp_dev) return fail(BGM_ERR_ARG, "bgm_causal_logpost: null z / out pointer");
+  MhDev D;
+  memset(&D, 0, sizeof(D));
+  D.a.x_dev = x_dev; D.a.y_dev = y_dev; D.a.v_dev = v_dev; D.a.ldv = ldv; D.a.n = n;
+  D.a.z_state_dev = const_cast<float*>(z_dev);
+  D.a.lp_state_dev = out_logp_dev;
+  D.a.init_mode = 1;
+  D.mode = 1;
+  return launch_mh(m, D, (cudaStream_t)stream);
+}
+
+int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* a, void* stream) {
+  if (!m || !a) return fail(BGM_ERR_ARG, "bgm_causal_mh: null model / args");
+  int rc = check_data("bgm_causal_mh", a->x_dev, a->y_dev, a->v_dev, a->ldv, a->n, m->prog.p);
+  if (rc) return rc;
+  if (!a->z_state_dev || !a->lp_state_dev)
+    return fail(BGM_ERR_ARG, "bgm_causal_mh: z_state_dev and lp_state_dev are required");
+  if (a->init_mode < 0 || a->init_mode > 2) return fail(BGM_ERR_ARG, "bgm_causal_mh: init_mode must be 0, 1 or 2");
+  if (a->t_begin < 0 || a->t_end < a->t_begin) return fail(BGM_ERR_ARG, "bgm_causal_mh: bad iteration range");
+  if ((a->eps_dev == nullptr) != (a->u_dev == nullptr))
+    return fail(BGM_ERR_ARG, "bgm_causal_mh: eps_dev and u_dev must be given together");
+  if (a->init_mode == 2 && a->eps_dev)
+    return fail(BGM_ERR_ARG, "bgm_causal_mh: init_mode 2 draws from Philox; pass z_state with injected noise");
+  if (!a->q_sd_dev) return fail(BGM_ERR_ARG, "bgm_causal_mh: q_sd_dev is required");
+  MhDev D;
+  D.a = *a;
+  D.mode = 0;
+  return launch_mh(m, D, (cudaStream_t)stream);
+}
+
+int bgm_mh_adapt_qsd(const int* accept_count_dev, int t, int window, long long n_total, float target,
+                     float tolerance, float* q_sd_dev, void* stream) {
+  if (!accept_count_dev || !q_sd_dev) return fail(BGM_ERR_ARG, "bgm_mh_adapt_qsd: null pointer");
+  if (t < 0 || window < 1 || n_total < 1) return fail(BGM_ERR_ARG, "bgm_mh_adapt_qsd: bad t / window / n");
+  mh_adapt_qsd_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(accept_count_dev, t, window, n_total, target,
+                                                        tolerance, q_sd_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_mh_noise(uint64_t seed, int64_t row_offset, int n, int zd, int t_begin, int t_end,
+                 float* z0_dev, float* eps_dev, double* u_dev, void* stream) {
+  if (n < 1 || zd < 1 || t_end < t_begin) return fail(BGM_ERR_ARG, "bgm_mh_noise: bad sizes");
+  const long long total = (long long)(t_end - t_begin + 1) * n;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  mh_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n, zd, t_begin, t_end,
+                                                         z0_dev, eps_dev, u_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_keep, int n,
+                      const float* x_values_dev, int n_x, int sample_y, uint64_t seed,
+                      int64_t row_offset, const float* noise_dev, double* adrf_sum_dev, float* ite_dev,
+                      void* stream) {
+  if (!m || !z_samples_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect: null model / samples");
+  if (n_keep < 1 || n < 1) return fail(BGM_ERR_ARG, "bgm_causal_effect: n_keep and n must be >= 1");
+  EffectDev E;
+  memset(&E, 0, sizeof(E));
+  if (m->prog.binary) {
+    if (!ite_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect: binary treatment needs ite_dev");
+    E.x_values = nullptr;
+    E.n_x = 2;
+  } else {
+    if (!x_values_dev || n_x < 1 || !adrf_sum_dev)
+      return fail(BGM_ERR_ARG, "bgm_causal_effect: continuous treatment needs x_values_dev, n_x >= 1 and adrf_sum_dev");
+    E.x_values = x_values_dev;
+    E.n_x = n_x;
+  }
+  E.z_samples = z_samples_dev; E.n_keep = n_keep; E.n = n; E.sample_y = sample_y ? 1 : 0;
+  E.seed = seed; E.row_offset = row_offset; E.noise = noise_dev; E.adrf_sum = adrf_sum_dev; E.ite = ite_dev;
+  const long long ntiles = (long long)((n + TILE_ROWS - 1) / TILE_ROWS) * n_keep;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((ntiles + m->effect_warps - 1) / m->effect_warps, m->sm_count));
+  BGM_CUDA_OK(cudaFuncSetAttribute(causal_effect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   m->effect_smem_bytes));
+  causal_effect_kernel<<<grid, m->effect_warps * 32, m->effect_smem_bytes, (cudaStream_t)stream>>>(
+      m->prog, m->image_dev, E);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------- fp32 peak ----
+}  // extern "C"
+
+namespace bgm {
+// 16 independent FFMA chains per thread, operands in registers: the issue-bound
+// ceiling of the fp32 pipe that the sampler's inner loop runs on.
+__global__ void __launch_bounds__(256) fp32_peak_kernel(float* out, int iters, float a, float b) {
+  float x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = threadIdx.x * 1e-3f + i;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += x[i];
+  if (s == 123.456f) out[0] = s;  // never true; keeps the chain alive
+}
+}  // namespace bgm
+
+extern "C" int bgm_fp32_peak_tflops(double* tflops, void* stream) {
+  if (!tflops) return fail(BGM_ERR_ARG, "bgm_fp32_peak_tflops: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0, sms = 0;
+  BGM_CUDA_OK(cudaGetDevice(&dev));
+  BGM_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  float* out = nullptr;
+  BGM_CUDA_OK(cudaMalloc(&out, 4));
+  cudaEvent_t e0, e1;
+  BGM_CUDA_OK(cudaEventCreate(&e0));
+  BGM_CUDA_OK(cudaEventCreate(&e1));
+  const int iters = 4096, grid = sms * 8, block = 256;
+  double best = 0.0;
+  for (int rep = 0; rep < 6; ++rep) {
+    BGM_CUDA_OK(cudaEventRecord(e0, st));
+    bgm::fp32_peak_kernel<<<grid, block, 0, st>>>(out, iters, 0.999f, 1e-3f);
+    BGM_CUDA_OK(cudaEventRecord(e1, st));
+    BGM_CUDA_OK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    BGM_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    const double flop = 2.0 * 16 * 8 * (double)iters * grid * block;
+    if (rep > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  *tflops = best;
+  return 0;
+}

@@ -1,0 +1,449 @@
+// CausalBGM hot path: packed g/f/h nets, log-posterior, persistent random-walk MH
+// sampler and the effect (ITE / ADRF) kernel.
+//
+// Replaces causalbgm/base.py:765-817 (get_log_posterior), :820-904
+// (metropolis_hastings_sampler) and :671-763 (infer_from_latent_posterior) of the
+// reference.  One warp carries 32 observations (rows) through all T iterations; the
+// weight image of the three nets sits in shared memory for the whole launch, the
+// activations in the warp's private shared-memory slice, the chain state in
+// registers (one row per lane); the covariate rows are re-read from L2 once per
+// iteration.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace bgm {
+
+constexpr int MAX_OPS = 48;
+constexpr int MAX_WARPS = 12;
+constexpr int SCR_SLOTS = 2;  // reused per net: [sse | mu] and [sigma raw]
+constexpr int ACT_ROWS = 64;  // widest hidden layer
+constexpr int IMG_PAD = 64;   // floats after the image that the last prefetch may touch
+
+struct CausalProgram {
+  int n_ops;
+  int g_end, f_end, h_end;     // op ranges: g [0,g_end) f [g_end,f_end) h [f_end,h_end)
+  int f_img_begin, f_img_end;  // float range of the f-net tiles in the image
+  int zd, kin, p, binary;
+  float s2v, s2x, s2y;         // fixed variances, < 0 = learned head
+  int image_floats;            // padded by IMG_PAD
+  int per_warp_floats;
+  TileOp ops[MAX_OPS];
+};
+
+// Shared-memory slice of one warp (floats): act[64][32] | zin[kin][32] | scr[2][32]
+struct WarpSmem {
+  float* act;
+  float* zin;
+  float* scr;
+};
+__device__ __forceinline__ WarpSmem warp_smem(float* base, const CausalProgram& P) {
+  WarpSmem s;
+  s.act = base;
+  s.zin = s.act + ACT_ROWS * TILE_ROWS;
+  s.scr = s.zin + P.kin * TILE_ROWS;
+  return s;
+}
+
+// Runs one column tile: init accumulators (bias, or bias - data for the SSE
+// epilogue), MAC over k, then the epilogue.
+template <int C>
+__device__ __forceinline__ void run_tile(const TileOp& op, const float* __restrict__ wimg,
+                                         const WarpSmem& S, const float* __restrict__ v, int ldv,
+                                         int p, int row0, int n, int rg, int cg,
+                                         float (&sse)[RPT]) {
+  const float* in = op.src ? S.act : S.zin;
+  const float* w = wimg + op.w_off;
+  const float* bias = wimg + op.b_off;
+  float acc[RPT][C];
+#pragma unroll
+  for (int j = 0; j < C; ++j) {
+    float bj = bias[ColMap<C>::col(cg, j)];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i][j] = bj;
+  }
+  if (op.epi == EPI_SSE) {
+    // acc starts at bias - v so that after the MAC it holds mu - v.
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+      int r = row0 + row_of(rg, i);
+      r = r < n ? r : n - 1;
+      const float* vr = v + (size_t)r * ldv + op.c0;
+      if constexpr (C == 1) {
+        int c = op.c0 + cg;
+        float t = (c < p) ? __ldg(vr + cg) : 0.f;
+        acc[i][0] -= t;
+      } else {
+#pragma unroll
+        for (int h = 0; h < C / 4; ++h) {
+          int cl = h * 32 + cg * 4;  // tile-local first column of this float4
+          int c = op.c0 + cl;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < p) t = __ldg(reinterpret_cast<const float4*>(vr + cl));
+          acc[i][h * 4 + 0] -= t.x;
+          acc[i][h * 4 + 1] -= (c + 1 < p) ? t.y : 0.f;
+          acc[i][h * 4 + 2] -= (c + 2 < p) ? t.z : 0.f;
+          acc[i][h * 4 + 3] -= (c + 3 < p) ? t.w : 0.f;
+        }
+      }
+    }
+  }
+  tile_mac<C>(in, w, op.kp, rg, cg, acc);
+  if (op.epi == EPI_ACT || op.epi == EPI_LIN) {
+    __syncwarp();  // every lane is done reading the buffer we overwrite
+    const bool act = op.epi == EPI_ACT;
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int c = ColMap<C>::col(cg, j);
+      float4 lo, hi;
+      lo.x = act ? leaky(acc[0][j]) : acc[0][j];
+      lo.y = act ? leaky(acc[1][j]) : acc[1][j];
+      lo.z = act ? leaky(acc[2][j]) : acc[2][j];
+      lo.w = act ? leaky(acc[3][j]) : acc[3][j];
+      hi.x = act ? leaky(acc[4][j]) : acc[4][j];
+      hi.y = act ? leaky(acc[5][j]) : acc[5][j];
+      hi.z = act ? leaky(acc[6][j]) : acc[6][j];
+      hi.w = act ? leaky(acc[7][j]) : acc[7][j];
+      *reinterpret_cast<float4*>(S.act + c * TILE_ROWS + rg * 4) = lo;
+      *reinterpret_cast<float4*>(S.act + c * TILE_ROWS + 16 + rg * 4) = hi;
+    }
+    __syncwarp();
+  } else if (op.epi == EPI_SSE) {
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+      for (int j = 0; j < C; ++j) sse[i] = fmaf(acc[i][j], acc[i][j], sse[i]);
+  } else {  // EPI_OUT: raw outputs to scratch slots c0 + col
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+      int c = ColMap<C>::col(cg, j);
+      if (c < op.nvalid) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) S.scr[(op.c0 + c) * TILE_ROWS + row_of(rg, i)] = acc[i][j];
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void run_ops(const CausalProgram& P, int o_begin, int o_end,
+                                        const float* __restrict__ wimg, const WarpSmem& S,
+                                        const float* __restrict__ v, int ldv, int row0, int n,
+                                        int rg, int cg, float (&sse)[RPT]) {
+  for (int o = o_begin; o < o_end; ++o) {
+    const TileOp& op = P.ops[o];
+    if (op.ctype == 0) run_tile<8>(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
+    else if (op.ctype == 1) run_tile<4>(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
+    else run_tile<1>(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
+  }
+}
+
+// Log-posterior of the 32 rows whose z (and x) sit in S.zin; returns the value of
+// this lane's row.  causalbgm/base.py:779-816.  The three losses are assembled as
+// each net finishes so that two scratch rows suffice.
+__device__ __forceinline__ float eval_logpost(const CausalProgram& P, const float* __restrict__ wimg,
+                                              const WarpSmem& S, const float* __restrict__ v,
+                                              int ldv, int row0, int n, int lane, float x_l,
+                                              float y_l) {
+  const int rg = lane >> 3, cg = lane & 7;
+  float sse[RPT];
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) sse[i] = 0.f;
+  // ---- g-net: sum_j (v_j - mu_j)^2 and the sigma_v head ----
+  run_ops(P, 0, P.g_end, wimg, S, v, ldv, row0, n, rg, cg, sse);
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    float s = sse[i];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (cg == 0) S.scr[row_of(rg, i)] = s;
+  }
+  __syncwarp();
+  const float sse_l = S.scr[lane];
+  const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+  const float loss_pv = sse_l / (2.f * s2v) + ((float)P.p * logf(s2v)) / 2.f;    // :800-801
+  __syncwarp();
+  // ---- f-net: outcome model ----
+  run_ops(P, P.g_end, P.f_end, wimg, S, v, ldv, row0, n, rg, cg, sse);
+  __syncwarp();
+  const float mu_y = S.scr[lane];
+  const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+  const float dy = y_l - mu_y;
+  const float loss_py = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;              // :809-810
+  __syncwarp();
+  // ---- h-net: treatment model ----
+  run_ops(P, P.f_end, P.h_end, wimg, S, v, ldv, row0, n, rg, cg, sse);
+  __syncwarp();
+  const float mu_x = S.scr[lane];
+  float loss_px;
+  if (P.binary) {                                                               // :804
+    loss_px = fmaxf(mu_x, 0.f) - mu_x * x_l + log1pf(expf(-fabsf(mu_x)));
+  } else {                                                                      // :806-807
+    const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+    const float d = x_l - mu_x;
+    loss_px = (d * d) / (2.f * s2x) + logf(s2x) / 2.f;
+  }
+  float prior = 0.f;
+  for (int d = 0; d < P.zd; ++d) {
+    const float z = S.zin[d * TILE_ROWS + lane];
+    prior = fmaf(z, z, prior);
+  }
+  prior *= 0.5f;                                                                // :812
+  __syncwarp();
+  return -(((loss_pv + loss_px) + loss_py) + prior);                            // :814-816
+}
+
+struct MhDev {
+  bgm_mh_args a;
+  int mode;  // 0: MH, 1: log-posterior of z_state only (out -> lp_state)
+};
+
+// ZMAX: compile-time bound on zd; the chain state z_cur[ZMAX] of the lane's row is
+// held in registers.
+template <int ZMAX>
+__global__ void __launch_bounds__(MAX_WARPS * 32, 1)
+causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restrict__ image,
+                 const __grid_constant__ MhDev D) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar;
+  bulk_load_to_smem(smem, image, (uint32_t)P.image_floats * 4u, &bar);
+  const float* wimg = smem;
+
+  const bgm_mh_args& A = D.a;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const WarpSmem S = warp_smem(smem + P.image_floats + warp * P.per_warp_floats, P);
+  const int n = A.n, zd = P.zd;
+  const int ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
+  const float q_sd = A.q_sd_dev ? *A.q_sd_dev : 1.f;
+
+  for (int tile = blockIdx.x * warps + warp; tile < ntiles; tile += gridDim.x * warps) {
+    const int row0 = tile * TILE_ROWS;
+    const int row = row0 + lane;
+    const bool valid = row < n;
+    const int lrow = valid ? row : n - 1;
+    const int nvalid_rows = min(TILE_ROWS, n - row0);
+    const float x_l = A.x_dev[lrow], y_l = A.y_dev[lrow];
+    const int64_t grow = A.row_offset + lrow;
+    float zc[ZMAX];
+    // input buffer: rows [0,zd) proposal, row zd = x, remaining pad rows zero
+    for (int k = zd; k < P.kin; ++k) S.zin[k * TILE_ROWS + lane] = (k == zd) ? x_l : 0.f;
+    // ---- initial state (:842) ----
+    if (A.init_mode == 2) {
+#pragma unroll
+      for (int g = 0; g < ZMAX / 4; ++g) {
+        if (g * 4 < zd) {
+          float e[4];
+          normal4(A.seed, grow, T_INIT, NOISE_PROPOSAL, g, e);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) zc[g * 4 + q] = e[q];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) zc[d] = A.z_state_dev[(size_t)lrow * zd + d];
+    }
+    float lp_cur;
+    if (A.init_mode == 0 && D.mode == 0) {
+      lp_cur = A.lp_state_dev[lrow];
+    } else {
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) S.zin[d * TILE_ROWS + lane] = zc[d];
+      __syncwarp();
+      lp_cur = eval_logpost(P, wimg, S, A.v_dev, A.ldv, row0, n, lane, x_l, y_l);
+    }
+    if (D.mode == 1) {
+      if (valid) A.lp_state_dev[row] = lp_cur;
+      continue;
+    }
+    // ---- iterations (:860-898) ----
+    for (int t = A.t_begin; t < A.t_end; ++t) {
+      // proposal z' = z + q_sd * eps (:862); product and sum rounded separately like
+      // NumPy's normal(0, q_sd).astype(float32) followed by the add.
+      if (A.eps_dev) {
+        const float* e = A.eps_dev + ((size_t)t * n + lrow) * zd;
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) S.zin[d * TILE_ROWS + lane] = __fadd_rn(zc[d], __fmul_rn(q_sd, e[d]));
+      } else {
+#pragma unroll
+        for (int g = 0; g < ZMAX / 4; ++g) {
+          if (g * 4 < zd) {
+            float e[4];
+            normal4(A.seed, grow, (uint32_t)t, NOISE_PROPOSAL, g, e);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (g * 4 + q < zd)
+                S.zin[(g * 4 + q) * TILE_ROWS + lane] = __fadd_rn(zc[g * 4 + q], __fmul_rn(q_sd, e[q]));
+          }
+        }
+      }
+      __syncwarp();
+      const float lp_prop = eval_logpost(P, wimg, S, A.v_dev, A.ldv, row0, n, lane, x_l, y_l);
+      // accept: u < exp(min(lp' - lp, 0))  (:868-870); a NaN ratio never accepts
+      const float dlp = lp_prop - lp_cur;
+      const float ratio = (dlp < 0.f) ? expf(dlp) : ((dlp >= 0.f) ? 1.f : __int_as_float(0x7fc00000));
+      bool acc;
+      if (A.u_dev) acc = A.u_dev[(size_t)t * n + lrow] < (double)ratio;
+      else acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT) < ratio;
+      if (acc) {                                                                 // :871
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) zc[d] = S.zin[d * TILE_ROWS + lane];
+        lp_cur = lp_prop;
+      }
+      if (A.accept_mask_dev && valid) A.accept_mask_dev[(size_t)t * n + row] = acc ? 1 : 0;
+      if (A.lp_trace_dev && valid) A.lp_trace_dev[(size_t)t * n + row] = lp_prop;
+      if (A.accept_count_dev) {
+        const unsigned b = __ballot_sync(0xffffffffu, acc && valid);
+        if (lane == 0 && b) atomicAdd(A.accept_count_dev + t, __popc(b));
+      }
+      if (t >= A.burn_in && A.out_samples_dev) {                                 // :895-896
+        // stage through the (idle) activation buffer so that the warp writes its
+        // contiguous (rows x zd) block with full 128-byte lines
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) S.act[d * TILE_ROWS + lane] = zc[d];
+        __syncwarp();
+        float* dst = A.out_samples_dev + ((size_t)(t - A.burn_in) * n + row0) * zd;
+        for (int idx = lane; idx < nvalid_rows * zd; idx += 32) {
+          const int r = idx / zd, d = idx - r * zd;
+          dst[idx] = S.act[d * TILE_ROWS + r];
+        }
+      }
+      __syncwarp();
+    }
+    // ---- save state ----
+    if (valid) {
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) A.z_state_dev[(size_t)row * zd + d] = zc[d];
+      A.lp_state_dev[row] = lp_cur;
+    }
+    __syncwarp();
+  }
+}
+
+// Effect kernel: f-net on kept states for each dose.  One warp tile = 32 rows of
+// one kept sample.  infer_from_latent_posterior, causalbgm/base.py:671-763.
+struct EffectDev {
+  const float* z_samples;  // (n_keep, n, zd)
+  int n_keep, n;
+  const float* x_values;   // (n_x) ; binary: NULL -> {1, 0}
+  int n_x;
+  int sample_y;
+  uint64_t seed;
+  int64_t row_offset;
+  const float* noise;      // optional injected N(0,1): (n_x, n_keep, n)
+  double* adrf_sum;        // (n_x, n_keep)
+  float* ite;              // (n_keep, n)
+};
+
+__global__ void __launch_bounds__(MAX_WARPS * 32, 1)
+causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __restrict__ image,
+                     const __grid_constant__ EffectDev E) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar;
+  const int img_floats = P.f_img_end - P.f_img_begin;
+  bulk_load_to_smem(smem, image + P.f_img_begin, (uint32_t)img_floats * 4u, &bar);
+  // tile ops carry offsets into the full image; rebase them onto the f-net copy
+  const float* wimg = smem;
+  const int rebase = P.f_img_begin;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warps = blockDim.x >> 5;
+  const int rg = lane >> 3, cg = lane & 7;
+  const WarpSmem S = warp_smem(smem + img_floats + IMG_PAD + warp * P.per_warp_floats, P);
+  const int n = E.n, zd = P.zd;
+  const int tiles_per_s = (n + TILE_ROWS - 1) / TILE_ROWS;
+  const long long ntiles = (long long)tiles_per_s * E.n_keep;
+  for (int k = zd; k < P.kin; ++k) S.zin[k * TILE_ROWS + lane] = 0.f;
+  for (long long tile = (long long)blockIdx.x * warps + warp; tile < ntiles;
+       tile += (long long)gridDim.x * warps) {
+    const int s = (int)(tile / tiles_per_s);
+    const int row0 = (int)(tile - (long long)s * tiles_per_s) * TILE_ROWS;
+    const int row = row0 + lane;
+    const bool valid = row < n;
+    const int lrow = valid ? row : n - 1;
+    const int64_t grow = E.row_offset + lrow;
+    const float* zs = E.z_samples + ((size_t)s * n + lrow) * zd;
+    for (int d = 0; d < zd; ++d) S.zin[d * TILE_ROWS + lane] = zs[d];
+    float y_prev = 0.f;
+    for (int j = 0; j < E.n_x; ++j) {
+      const float xv = E.x_values ? E.x_values[j] : (j == 0 ? 1.f : 0.f);
+      S.zin[zd * TILE_ROWS + lane] = xv;
+      __syncwarp();
+      float sse[RPT];
+      for (int o = P.g_end; o < P.f_end; ++o) {
+        TileOp op = P.ops[o];
+        op.w_off -= rebase;
+        op.b_off -= rebase;
+        if (op.ctype == 0) run_tile<8>(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
+        else if (op.ctype == 1) run_tile<4>(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
+        else run_tile<1>(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
+      }
+      __syncwarp();
+      float y = S.scr[lane];                                                     // mu_y
+      if (E.sample_y) {                                                          // :703-708
+        const float s2 = P.s2y >= 0.f ? P.s2y : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+        const float e = E.noise ? E.noise[((size_t)j * E.n_keep + s) * n + lrow]
+                                : normal1(E.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)j);
+        y = fmaf(sqrtf(s2), e, y);
+      }
+      __syncwarp();
+      if (P.binary) {                                                            // :731
+        if (j == 0) y_prev = y;
+        else if (valid) E.ite[(size_t)s * n + row] = y_prev - y;
+      } else {                                                                   // :759
+        float part = valid ? y : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) atomicAdd(E.adrf_sum + (size_t)j * E.n_keep + s, (double)part);
+      }
+    }
+  }
+}
+
+// 1-thread kernel: the q_sd adaptation rule, causalbgm/base.py:880-890.
+__global__ void mh_adapt_qsd_kernel(const int* __restrict__ accept_count, int t, int window,
+                                    long long n_total, float target, float tol, float* q_sd) {
+  int lo = t - window + 1;
+  if (lo < 0) lo = 0;
+  long long s = 0;
+  for (int i = lo; i <= t; ++i) s += accept_count[i];
+  const double rate = (double)s / ((double)(t - lo + 1) * (double)n_total);
+  float q = *q_sd;
+  if (rate < (double)target - (double)tol) q *= 0.9f;
+  else if (rate > (double)target + (double)tol) q *= 1.1f;
+  *q_sd = q;
+}
+
+__global__ void mh_noise_kernel(uint64_t seed, int64_t row_offset, int n, int zd, int t_begin,
+                                int t_end, float* z0, float* eps, double* u) {
+  const int T = t_end - t_begin;
+  const long long total = (long long)(T + 1) * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ti = (int)(i / n);
+    const int row = (int)(i - (long long)ti * n);
+    const int64_t grow = row_offset + row;
+    const bool init = ti == T;
+    const uint32_t t = init ? T_INIT : (uint32_t)(t_begin + ti);
+    float* dst = init ? (z0 ? z0 + (size_t)row * zd : nullptr)
+                      : (eps ? eps + ((size_t)ti * n + row) * zd : nullptr);
+    if (dst) {
+      for (int g = 0; g * 4 < zd; ++g) {
+        float e[4];
+        normal4(seed, grow, t, NOISE_PROPOSAL, g, e);
+        for (int q = 0; q < 4; ++q)
+          if (g * 4 + q < zd) dst[g * 4 + q] = e[q];
+      }
+    }
+    if (!init && u) u[(size_t)ti * n + row] = (double)uniform1(seed, grow, t, NOISE_ACCEPT);
+  }
+}
+
+}  // namespace bgm

@@ -1,0 +1,139 @@
+/*
+ * bgm_b200.h -- C ABI of the B200-native bayesgm hot path (libbgm_b200.so).
+ *
+ * The reference (liuq-lab/bayesgm @ 85350a1) has no FFI / plugin layer: its seam is
+ * the Python method surface of `CausalBGM` / `BGM`.  Each
+ * entry point below replaces the device-side work of one of those methods; the
+ * Python host (bayesgm_b200/causalbgm.py, bgm.py) keeps the reference's method
+ * names and kwargs and binds these symbols with ctypes.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Pointers named *_dev are
+ * caller-owned DEVICE memory on the current CUDA device; `stream` is a cudaStream_t
+ * passed as void* (NULL = default stream).  Every function returns 0 on success or
+ * a negative bgm_status; bgm_last_error() gives the message (thread-local).  No
+ * hidden device allocation happens outside the *_create functions.  All arithmetic
+ * is IEEE fp32 on the CUDA cores (no TF32 / fast-math), row-major layouts.
+ */
+#ifndef BGM_B200_H
+#define BGM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  BGM_OK = 0,
+  BGM_ERR_ARG = -1,      /* bad argument (message says which) */
+  BGM_ERR_UNSUPPORTED = -2, /* layer width / dimension outside what the kernels cover */
+  BGM_ERR_CUDA = -3,     /* CUDA runtime error (message carries cudaGetErrorString) */
+  BGM_ERR_NOMEM = -4     /* packed model does not fit in shared memory */
+} bgm_status;
+
+const char* bgm_last_error(void);
+int bgm_version(void);
+/* SM count, opt-in shared memory per block, SM clock (kHz) of the current device. */
+int bgm_device_info(int* sm_count, int* smem_optin_bytes, int* clock_khz);
+
+/* ---------------------------------------------------------------- networks -- */
+/* A Dense stack as the reference builds it (networks/base.py:17-26): n_layers
+ * layers, dims[n_layers+1] = [in, units..., out]; `params` (HOST memory) is the
+ * concatenation, layer by layer, of the Keras arrays kernel[in][out] (row-major)
+ * then bias[out].  LeakyReLU(0.2) after every layer but the last (:38-51). */
+typedef struct {
+  int n_layers;
+  const int* dims;
+  const float* params;
+} bgm_net_desc;
+
+/* ------------------------------------------------------- CausalBGM sampler -- */
+typedef struct bgm_causal bgm_causal; /* opaque: g/f/h nets packed for the kernels */
+
+/* Replaces the construction-time state get_log_posterior reads
+ * (causalbgm/base.py:74-81, :765-798).  z_dims = [z0,z1,z2,z3]; sigma_* < 0 means
+ * "learned head" (softplus(last output)+1e-6), >= 0 is the fixed `sigma_*` of the
+ * params dict (variance = sigma^2, :781-798).  g: sum(z_dims) -> v_dim+1,
+ * f: z0+z1+1 -> 2, h: z0+z2 -> 2.  Hidden widths up to 64 are supported. */
+int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int binary_treatment,
+                      float sigma_v, float sigma_x, float sigma_y,
+                      const bgm_net_desc* g_net, const bgm_net_desc* f_net,
+                      const bgm_net_desc* h_net);
+void bgm_causal_destroy(bgm_causal* m);
+/* Packed-model facts: shared-memory bytes per CTA, warps per CTA, tile ops per
+ * log-posterior evaluation, algorithmic FMAs per row per evaluation (unpadded). */
+int bgm_causal_info(const bgm_causal* m, int* smem_bytes, int* warps_per_cta, int* n_ops,
+                    long long* macs_per_row, long long* issued_macs_per_row);
+
+/* CausalBGM.get_log_posterior (causalbgm/base.py:765-817).
+ * x_dev,y_dev: (n) ; v_dev: (n, ldv) with ldv >= v_dim, ldv % 4 == 0, 16-byte
+ * aligned base; z_dev: (n, sum z_dims); out_logp_dev: (n). */
+int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_dev,
+                       const float* v_dev, int ldv, const float* z_dev, int n,
+                       float* out_logp_dev, void* stream);
+
+/* CausalBGM.metropolis_hastings_sampler (causalbgm/base.py:820-904): iterations
+ * [t_begin, t_end) of n independent random-walk MH chains in ONE persistent launch.
+ * The chain state lives in z_state_dev / lp_state_dev between launches so that the
+ * adaptive-q_sd path (:880-892) can run as a sequence of launches with
+ * bgm_mh_adapt_qsd in between, all on `stream`, without host synchronisation. */
+typedef struct {
+  const float* x_dev;       /* (n)    treatment                                   */
+  const float* y_dev;       /* (n)    outcome                                     */
+  const float* v_dev;       /* (n,ldv) covariates                                 */
+  int ldv;
+  int n;
+  float* z_state_dev;       /* (n,zd) current state: in (init_mode 0/1) and out   */
+  float* lp_state_dev;      /* (n)    cached log-posterior of the current state   */
+  int init_mode;            /* 0: continue (lp_state valid); 1: z_state given,
+                               evaluate its log-posterior first; 2: draw
+                               z0 ~ N(0,1) from the Philox stream (:842), then 1  */
+  int t_begin, t_end;       /* iteration range of this launch                     */
+  int burn_in;              /* samples of iterations t >= burn_in are kept (:895) */
+  const float* q_sd_dev;    /* (1) proposal sd, read once at launch               */
+  /* noise: injected (both non-NULL; test / exact-parity mode) or Philox4x32-10  */
+  const float* eps_dev;     /* (T,n,zd) UNIT normals, scaled by q_sd in-kernel    */
+  const double* u_dev;      /* (T,n)  uniforms, compared as float64 like :870     */
+  uint64_t seed;            /* Philox key                                         */
+  int64_t row_offset;       /* global index of row 0 (multi-GPU shards)           */
+  /* outputs, each may be NULL */
+  float* out_samples_dev;   /* (t_end_total-burn_in, n, zd) kept states           */
+  int* accept_count_dev;    /* (T) accepted proposals per iteration (atomicAdd)   */
+  uint8_t* accept_mask_dev; /* (T,n) per-row accept decisions (trace)             */
+  float* lp_trace_dev;      /* (T,n) proposed log-posteriors (trace)              */
+} bgm_mh_args;
+
+int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* args, void* stream);
+
+/* The windowed acceptance-rate rule of causalbgm/base.py:880-890, evaluated on the
+ * device after iteration `t`: rate over iterations (t-window, t] (clipped at 0) of
+ * accept_count / (len * n_total); q_sd *= 0.9 / 1.1 outside target +- tolerance. */
+int bgm_mh_adapt_qsd(const int* accept_count_dev, int t, int window, long long n_total,
+                     float target, float tolerance, float* q_sd_dev, void* stream);
+
+/* Writes exactly the noise bgm_causal_mh would draw from Philox for rows
+ * [0,n) + row_offset: z0 (n,zd), eps (t_end-t_begin,n,zd) unit normals, u (.,n)
+ * as float64.  Used by the parity tests to replay Philox runs through the oracle. */
+int bgm_mh_noise(uint64_t seed, int64_t row_offset, int n, int zd, int t_begin, int t_end,
+                 float* z0_dev, float* eps_dev, double* u_dev, void* stream);
+
+/* CausalBGM.infer_from_latent_posterior (causalbgm/base.py:671-763) on kept states.
+ * z_samples_dev: (n_keep, n, zd).  Continuous: for each x_values[j] and sample s,
+ * adrf_sum_dev[j*n_keep+s] += sum over rows of y(s,row,j) (float64 accumulators,
+ * caller zeroes them and divides by n; shards add into the same layout).
+ * Binary: ite_dev[s*n+row] = y(z,1) - y(z,0).  sample_y != 0 adds
+ * sqrt(sigma_y^2)*N(0,1) from Philox (seed,row_offset); noise_dev, if non-NULL,
+ * replaces those draws (continuous: (n_x,n_keep,n); binary: (2,n_keep,n)). */
+int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_keep, int n,
+                      const float* x_values_dev, int n_x, int sample_y, uint64_t seed,
+                      int64_t row_offset, const float* noise_dev, double* adrf_sum_dev,
+                      float* ite_dev, void* stream);
+
+/* Dependent-FFMA micro-benchmark: measured fp32 FMA peak of the device in TFLOP/s
+ * (the roofline denominator for the SIMT kernels; MEASURED_PEAKS.json has none). */
+int bgm_fp32_peak_tflops(double* tflops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BGM_B200_H */

@@ -1,0 +1,73 @@
+"""Shared builders for the parity tests: one synthetic case = params dict + oracle
+nets (Keras-layout arrays) + data, and the same weights loaded into the product model."""
+import numpy as np
+
+from oracle import nets as onets
+
+
+def causal_params(v_dim, z_dims, binary=False, g_units=(64,) * 5, f_units=(64, 32, 8),
+                  h_units=(64, 32, 8), e_units=(64,) * 5, **extra):
+    p = dict(dataset='test', output_dir='/tmp/bgm_b200_test', save_res=False, save_model=False,
+             binary_treatment=binary, use_bnn=False, z_dims=list(z_dims), v_dim=v_dim,
+             lr_theta=1e-4, lr_z=1e-4, g_units=list(g_units), f_units=list(f_units),
+             h_units=list(h_units), e_units=list(e_units), dz_units=[64, 32, 8], lr=2e-4,
+             g_d_freq=5, use_z_rec=True, kl_weight=1e-4)
+    p.update(extra)
+    return p
+
+
+def causal_nets(params, seed=123, bias_scale=0.1):
+    rs = np.random.RandomState(seed)
+    zd = sum(params['z_dims'])
+    d0, d1, d2, _ = params['z_dims']
+    return dict(
+        g=onets.init_mlp(rs, [zd] + list(params['g_units']) + [params['v_dim'] + 1], bias_scale),
+        e=onets.init_mlp(rs, [params['v_dim']] + list(params['e_units']) + [zd], bias_scale),
+        f=onets.init_mlp(rs, [d0 + d1 + 1] + list(params['f_units']) + [2], bias_scale),
+        h=onets.init_mlp(rs, [d0 + d2] + list(params['h_units']) + [2], bias_scale))
+
+
+def causal_data(n, v_dim, binary=False, seed=0):
+    rs = np.random.RandomState(seed)
+    v = rs.standard_normal((n, v_dim)).astype(np.float32)
+    if binary:
+        x = (rs.uniform(size=(n, 1)) < 0.5).astype(np.float32)
+    else:
+        x = rs.exponential(size=(n, 1)).astype(np.float32)
+    y = (x + 0.5 * v[:, :1] + rs.standard_normal((n, 1))).astype(np.float32)
+    return x, y, v
+
+
+def product_model(params, nets):
+    from bayesgm_b200 import CausalBGM
+    m = CausalBGM(params=params, random_seed=None)
+    flat = lambda layers: [a for W, b in layers for a in (W, b)]
+    m.set_weights(g=flat(nets['g']), e=flat(nets['e']), f=flat(nets['f']), h=flat(nets['h']))
+    return m
+
+
+def injected_noise(n, zd, T, seed=7):
+    rs = np.random.RandomState(seed)
+    return dict(z0=rs.standard_normal((n, zd)).astype(np.float32),
+                eps=rs.standard_normal((T, n, zd)).astype(np.float32),
+                u=rs.uniform(size=(T, n)))
+
+
+# ---- NumPy restatement of the library's Philox4x32-10 noise (csrc/common.cuh) ----
+M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(c, k):
+    """c: (...,4) uint32 counters, k: (2,) key -> (...,4) uint32."""
+    c = [c[..., i].astype(np.uint64) for i in range(4)]
+    k0, k1 = np.uint64(k[0]), np.uint64(k[1])
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = np.uint64(M0) * c[0]
+        p1 = np.uint64(M1) * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & mask
+        hi1, lo1 = p1 >> np.uint64(32), p1 & mask
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(W0)) & mask
+        k1 = (k1 + np.uint64(W1)) & mask
+    return np.stack(c, axis=-1).astype(np.uint32)
