@@ -52,7 +52,7 @@ SYMBOLS = {
     "bgm_causal_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_causal_mh": (C.c_int, [C.c_void_p, C.POINTER(MhArgs), C.c_void_p]),
-    "bgm_mh_adapt_qsd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float,
+    "bgm_mh_adapt_qsd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_double, C.c_double,
                                    C.c_void_p, C.c_void_p]),
     "bgm_mh_noise": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

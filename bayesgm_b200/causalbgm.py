@@ -185,7 +185,7 @@ class CausalBGM(object):
         lp_state = torch.empty(n, dtype=torch.float32, device=dev)
         samples = torch.empty((n_keep, n, zd), dtype=torch.float32, device=dev) if keep_samples else None
         acc_count = torch.zeros(T, dtype=torch.int32, device=dev)
-        q = torch.tensor([initial_q_sd if adaptive_sd else q_sd], dtype=torch.float32, device=dev)
+        q = torch.tensor([initial_q_sd if adaptive_sd else q_sd], dtype=torch.float64, device=dev)
         a = _lib.MhArgs()
         a.x_dev, a.y_dev, a.v_dev = x.data_ptr(), y.data_ptr(), v.data_ptr()
         a.ldv, a.n = ldv, n

@@ -226,12 +226,15 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   for (int k = 0; k < d2; ++k) h_rows.push_back(d0 + d1 + k);
   const char* wide = "hidden layers wider than 64 units are not supported by the sm_100a sampler kernel";
   if (add_net(g, g_rows, 0)) return fail(BGM_ERR_UNSUPPORTED, wide);
+  pk.ops.back().post = POST_G;
   P.g_end = (int)pk.ops.size();
   P.f_img_begin = (int)pk.image.size();
   if (add_net(f, f_rows, 1)) return fail(BGM_ERR_UNSUPPORTED, wide);
+  pk.ops.back().post = POST_F;
   P.f_end = (int)pk.ops.size();
   P.f_img_end = (int)pk.image.size();
   if (add_net(h, h_rows, 1)) return fail(BGM_ERR_UNSUPPORTED, wide);
+  pk.ops.back().post = POST_H;
   P.h_end = (int)pk.ops.size();
   P.n_ops = P.h_end;
   if (P.n_ops > MAX_OPS) return fail(BGM_ERR_UNSUPPORTED, "too many column tiles (v_dim too large)");
@@ -336,8 +339,8 @@ int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* a, void* stream) {
   return launch_mh(m, D, (cudaStream_t)stream);
 }
 
-int bgm_mh_adapt_qsd(const int* accept_count_dev, int t, int window, long long n_total, float target,
-                     float tolerance, float* q_sd_dev, void* stream) {
+int bgm_mh_adapt_qsd(const int* accept_count_dev, int t, int window, long long n_total, double target,
+                     double tolerance, double* q_sd_dev, void* stream) {
   if (!accept_count_dev || !q_sd_dev) return fail(BGM_ERR_ARG, "bgm_mh_adapt_qsd: null pointer");
   if (t < 0 || window < 1 || n_total < 1) return fail(BGM_ERR_ARG, "bgm_mh_adapt_qsd: bad t / window / n");
   mh_adapt_qsd_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(accept_count_dev, t, window, n_total, target,

@@ -16,7 +16,7 @@
 namespace bgm {
 
 constexpr int MAX_OPS = 48;
-constexpr int MAX_WARPS = 12;
+constexpr int MAX_WARPS = 8;
 constexpr int SCR_SLOTS = 2;  // reused per net: [sse | mu] and [sigma raw]
 constexpr int ACT_ROWS = 64;  // widest hidden layer
 constexpr int IMG_PAD = 64;   // floats after the image that the last prefetch may touch
@@ -95,7 +95,8 @@ __device__ __forceinline__ void run_tile(const TileOp& op, const float* __restri
     const bool act = op.epi == EPI_ACT;
 #pragma unroll
     for (int j = 0; j < C; ++j) {
-      int c = ColMap<C>::col(cg, j);
+      const int c = ColMap<C>::col(cg, j);
+      const int chunk = (rg ^ act_swz(c)) << 2;
       float4 lo, hi;
       lo.x = act ? leaky(acc[0][j]) : acc[0][j];
       lo.y = act ? leaky(acc[1][j]) : acc[1][j];
@@ -105,8 +106,8 @@ __device__ __forceinline__ void run_tile(const TileOp& op, const float* __restri
       hi.y = act ? leaky(acc[5][j]) : acc[5][j];
       hi.z = act ? leaky(acc[6][j]) : acc[6][j];
       hi.w = act ? leaky(acc[7][j]) : acc[7][j];
-      *reinterpret_cast<float4*>(S.act + c * TILE_ROWS + rg * 4) = lo;
-      *reinterpret_cast<float4*>(S.act + c * TILE_ROWS + 16 + rg * 4) = hi;
+      *reinterpret_cast<float4*>(S.act + c * TILE_ROWS + chunk) = lo;
+      *reinterpret_cast<float4*>(S.act + c * TILE_ROWS + (chunk ^ 16)) = hi;
     }
     __syncwarp();
   } else if (op.epi == EPI_SSE) {
@@ -126,21 +127,18 @@ __device__ __forceinline__ void run_tile(const TileOp& op, const float* __restri
   }
 }
 
-__device__ __forceinline__ void run_ops(const CausalProgram& P, int o_begin, int o_end,
-                                        const float* __restrict__ wimg, const WarpSmem& S,
-                                        const float* __restrict__ v, int ldv, int row0, int n,
-                                        int rg, int cg, float (&sse)[RPT]) {
-  for (int o = o_begin; o < o_end; ++o) {
-    const TileOp& op = P.ops[o];
-    if (op.ctype == 0) run_tile<8>(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
-    else if (op.ctype == 1) run_tile<4>(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
-    else run_tile<1>(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
-  }
+__device__ __forceinline__ void run_one(const TileOp& op, const float* __restrict__ wimg,
+                                        const WarpSmem& S, const float* __restrict__ v, int ldv,
+                                        int p, int row0, int n, int rg, int cg, float (&sse)[RPT]) {
+  if (op.ctype == 0) run_tile<8>(op, wimg, S, v, ldv, p, row0, n, rg, cg, sse);
+  else if (op.ctype == 1) run_tile<4>(op, wimg, S, v, ldv, p, row0, n, rg, cg, sse);
+  else run_tile<1>(op, wimg, S, v, ldv, p, row0, n, rg, cg, sse);
 }
 
 // Log-posterior of the 32 rows whose z (and x) sit in S.zin; returns the value of
-// this lane's row.  causalbgm/base.py:779-816.  The three losses are assembled as
-// each net finishes so that two scratch rows suffice.
+// this lane's row.  causalbgm/base.py:779-816.  ONE loop over the tile program (so
+// each tile routine exists once in the instruction stream); the three losses are
+// assembled as each net's last tile finishes, so two scratch rows suffice.
 __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const float* __restrict__ wimg,
                                               const WarpSmem& S, const float* __restrict__ v,
                                               int ldv, int row0, int n, int lane, float x_l,
@@ -149,49 +147,54 @@ __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const floa
   float sse[RPT];
 #pragma unroll
   for (int i = 0; i < RPT; ++i) sse[i] = 0.f;
-  // ---- g-net: sum_j (v_j - mu_j)^2 and the sigma_v head ----
-  run_ops(P, 0, P.g_end, wimg, S, v, ldv, row0, n, rg, cg, sse);
+  float loss = 0.f;  // loss_pv, then + loss_py after the f-net; loss_px joins at the end
+  float result = 0.f;
+#pragma unroll 1
+  for (int o = 0; o < P.n_ops; ++o) {
+    const TileOp& op = P.ops[o];
+    run_one(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
+    if (op.post == POST_NONE) continue;
+    if (op.post == POST_G) {  // sum_j (v_j - mu_j)^2 and the sigma_v head
 #pragma unroll
-  for (int i = 0; i < RPT; ++i) {
-    float s = sse[i];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (cg == 0) S.scr[row_of(rg, i)] = s;
+      for (int i = 0; i < RPT; ++i) {
+        float s = sse[i];
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (cg == 0) S.scr[row_of(rg, i)] = s;
+      }
+      __syncwarp();
+      const float sse_l = S.scr[lane];
+      const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+      loss = sse_l / (2.f * s2v) + ((float)P.p * logf(s2v)) / 2.f;                 // :800-801
+    } else if (op.post == POST_F) {  // outcome model
+      __syncwarp();
+      const float mu_y = S.scr[lane];
+      const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+      const float dy = y_l - mu_y;
+      result = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;                         // :809-810
+    } else {  // POST_H: treatment model, prior, total
+      __syncwarp();
+      const float mu_x = S.scr[lane];
+      float loss_px;
+      if (P.binary) {                                                             // :804
+        loss_px = fmaxf(mu_x, 0.f) - mu_x * x_l + log1pf(expf(-fabsf(mu_x)));
+      } else {                                                                    // :806-807
+        const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
+        const float d = x_l - mu_x;
+        loss_px = (d * d) / (2.f * s2x) + logf(s2x) / 2.f;
+      }
+      float prior = 0.f;
+      for (int d = 0; d < P.zd; ++d) {
+        const float z = S.zin[act_idx(d, lane)];
+        prior = fmaf(z, z, prior);
+      }
+      prior *= 0.5f;                                                              // :812
+      result = -(((loss + loss_px) + result) + prior);                            // :814-816
+    }
+    __syncwarp();  // scratch rows are reused by the next net
   }
-  __syncwarp();
-  const float sse_l = S.scr[lane];
-  const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
-  const float loss_pv = sse_l / (2.f * s2v) + ((float)P.p * logf(s2v)) / 2.f;    // :800-801
-  __syncwarp();
-  // ---- f-net: outcome model ----
-  run_ops(P, P.g_end, P.f_end, wimg, S, v, ldv, row0, n, rg, cg, sse);
-  __syncwarp();
-  const float mu_y = S.scr[lane];
-  const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
-  const float dy = y_l - mu_y;
-  const float loss_py = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;              // :809-810
-  __syncwarp();
-  // ---- h-net: treatment model ----
-  run_ops(P, P.f_end, P.h_end, wimg, S, v, ldv, row0, n, rg, cg, sse);
-  __syncwarp();
-  const float mu_x = S.scr[lane];
-  float loss_px;
-  if (P.binary) {                                                               // :804
-    loss_px = fmaxf(mu_x, 0.f) - mu_x * x_l + log1pf(expf(-fabsf(mu_x)));
-  } else {                                                                      // :806-807
-    const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
-    const float d = x_l - mu_x;
-    loss_px = (d * d) / (2.f * s2x) + logf(s2x) / 2.f;
-  }
-  float prior = 0.f;
-  for (int d = 0; d < P.zd; ++d) {
-    const float z = S.zin[d * TILE_ROWS + lane];
-    prior = fmaf(z, z, prior);
-  }
-  prior *= 0.5f;                                                                // :812
-  __syncwarp();
-  return -(((loss_pv + loss_px) + loss_py) + prior);                            // :814-816
+  return result;
 }
 
 struct MhDev {
@@ -216,7 +219,11 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
   const WarpSmem S = warp_smem(smem + P.image_floats + warp * P.per_warp_floats, P);
   const int n = A.n, zd = P.zd;
   const int ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
-  const float q_sd = A.q_sd_dev ? *A.q_sd_dev : 1.f;
+  const double q_sd = A.q_sd_dev ? *A.q_sd_dev : 1.0;
+  // the log-posterior of the initial state is evaluated as pseudo-iteration t_begin-1
+  const bool need_init = !(A.init_mode == 0 && D.mode == 0);
+  const int t_first = need_init ? A.t_begin - 1 : A.t_begin;
+  const int t_last = D.mode == 1 ? A.t_begin : A.t_end;
 
   for (int tile = blockIdx.x * warps + warp; tile < ntiles; tile += gridDim.x * warps) {
     const int row0 = tile * TILE_ROWS;
@@ -228,7 +235,7 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
     const int64_t grow = A.row_offset + lrow;
     float zc[ZMAX];
     // input buffer: rows [0,zd) proposal, row zd = x, remaining pad rows zero
-    for (int k = zd; k < P.kin; ++k) S.zin[k * TILE_ROWS + lane] = (k == zd) ? x_l : 0.f;
+    for (int k = zd; k < P.kin; ++k) S.zin[act_idx(k, lane)] = (k == zd) ? x_l : 0.f;
     // ---- initial state (:842) ----
     if (A.init_mode == 2) {
 #pragma unroll
@@ -245,29 +252,22 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
       for (int d = 0; d < ZMAX; ++d)
         if (d < zd) zc[d] = A.z_state_dev[(size_t)lrow * zd + d];
     }
-    float lp_cur;
-    if (A.init_mode == 0 && D.mode == 0) {
-      lp_cur = A.lp_state_dev[lrow];
-    } else {
-#pragma unroll
-      for (int d = 0; d < ZMAX; ++d)
-        if (d < zd) S.zin[d * TILE_ROWS + lane] = zc[d];
-      __syncwarp();
-      lp_cur = eval_logpost(P, wimg, S, A.v_dev, A.ldv, row0, n, lane, x_l, y_l);
-    }
-    if (D.mode == 1) {
-      if (valid) A.lp_state_dev[row] = lp_cur;
-      continue;
-    }
+    float lp_cur = need_init ? 0.f : A.lp_state_dev[lrow];
     // ---- iterations (:860-898) ----
-    for (int t = A.t_begin; t < A.t_end; ++t) {
-      // proposal z' = z + q_sd * eps (:862); product and sum rounded separately like
-      // NumPy's normal(0, q_sd).astype(float32) followed by the add.
-      if (A.eps_dev) {
+#pragma unroll 1
+    for (int t = t_first; t < t_last; ++t) {
+      const bool init_pass = t < A.t_begin;
+      if (init_pass) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) S.zin[act_idx(d, lane)] = zc[d];
+      } else if (A.eps_dev) {
+        // proposal z' = z + float32(q_sd * eps) (:862): NumPy scales the unit normal by
+        // q_sd in float64, .astype(float32) rounds once, then the float32 add.
         const float* e = A.eps_dev + ((size_t)t * n + lrow) * zd;
 #pragma unroll
         for (int d = 0; d < ZMAX; ++d)
-          if (d < zd) S.zin[d * TILE_ROWS + lane] = __fadd_rn(zc[d], __fmul_rn(q_sd, e[d]));
+          if (d < zd) S.zin[act_idx(d, lane)] = __fadd_rn(zc[d], (float)(q_sd * (double)e[d]));
       } else {
 #pragma unroll
         for (int g = 0; g < ZMAX / 4; ++g) {
@@ -277,12 +277,16 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
 #pragma unroll
             for (int q = 0; q < 4; ++q)
               if (g * 4 + q < zd)
-                S.zin[(g * 4 + q) * TILE_ROWS + lane] = __fadd_rn(zc[g * 4 + q], __fmul_rn(q_sd, e[q]));
+                S.zin[act_idx(g * 4 + q, lane)] = __fadd_rn(zc[g * 4 + q], (float)(q_sd * (double)e[q]));
           }
         }
       }
       __syncwarp();
       const float lp_prop = eval_logpost(P, wimg, S, A.v_dev, A.ldv, row0, n, lane, x_l, y_l);
+      if (init_pass) {
+        lp_cur = lp_prop;
+        continue;
+      }
       // accept: u < exp(min(lp' - lp, 0))  (:868-870); a NaN ratio never accepts
       const float dlp = lp_prop - lp_cur;
       const float ratio = (dlp < 0.f) ? expf(dlp) : ((dlp >= 0.f) ? 1.f : __int_as_float(0x7fc00000));
@@ -292,7 +296,7 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
       if (acc) {                                                                 // :871
 #pragma unroll
         for (int d = 0; d < ZMAX; ++d)
-          if (d < zd) zc[d] = S.zin[d * TILE_ROWS + lane];
+          if (d < zd) zc[d] = S.zin[act_idx(d, lane)];
         lp_cur = lp_prop;
       }
       if (A.accept_mask_dev && valid) A.accept_mask_dev[(size_t)t * n + row] = acc ? 1 : 0;
@@ -318,9 +322,11 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
     }
     // ---- save state ----
     if (valid) {
+      if (D.mode == 0) {
 #pragma unroll
-      for (int d = 0; d < ZMAX; ++d)
-        if (d < zd) A.z_state_dev[(size_t)row * zd + d] = zc[d];
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) A.z_state_dev[(size_t)row * zd + d] = zc[d];
+      }
       A.lp_state_dev[row] = lp_cur;
     }
     __syncwarp();
@@ -360,7 +366,7 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
   const int n = E.n, zd = P.zd;
   const int tiles_per_s = (n + TILE_ROWS - 1) / TILE_ROWS;
   const long long ntiles = (long long)tiles_per_s * E.n_keep;
-  for (int k = zd; k < P.kin; ++k) S.zin[k * TILE_ROWS + lane] = 0.f;
+  for (int k = zd; k < P.kin; ++k) S.zin[act_idx(k, lane)] = 0.f;
   for (long long tile = (long long)blockIdx.x * warps + warp; tile < ntiles;
        tile += (long long)gridDim.x * warps) {
     const int s = (int)(tile / tiles_per_s);
@@ -370,20 +376,19 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
     const int lrow = valid ? row : n - 1;
     const int64_t grow = E.row_offset + lrow;
     const float* zs = E.z_samples + ((size_t)s * n + lrow) * zd;
-    for (int d = 0; d < zd; ++d) S.zin[d * TILE_ROWS + lane] = zs[d];
+    for (int d = 0; d < zd; ++d) S.zin[act_idx(d, lane)] = zs[d];
     float y_prev = 0.f;
     for (int j = 0; j < E.n_x; ++j) {
       const float xv = E.x_values ? E.x_values[j] : (j == 0 ? 1.f : 0.f);
-      S.zin[zd * TILE_ROWS + lane] = xv;
+      S.zin[act_idx(zd, lane)] = xv;
       __syncwarp();
-      float sse[RPT];
+      float sse[RPT] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
       for (int o = P.g_end; o < P.f_end; ++o) {
         TileOp op = P.ops[o];
         op.w_off -= rebase;
         op.b_off -= rebase;
-        if (op.ctype == 0) run_tile<8>(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
-        else if (op.ctype == 1) run_tile<4>(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
-        else run_tile<1>(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
+        run_one(op, wimg, S, nullptr, 0, P.p, row0, n, rg, cg, sse);
       }
       __syncwarp();
       float y = S.scr[lane];                                                     // mu_y
@@ -409,15 +414,15 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
 
 // 1-thread kernel: the q_sd adaptation rule, causalbgm/base.py:880-890.
 __global__ void mh_adapt_qsd_kernel(const int* __restrict__ accept_count, int t, int window,
-                                    long long n_total, float target, float tol, float* q_sd) {
+                                    long long n_total, double target, double tol, double* q_sd) {
   int lo = t - window + 1;
   if (lo < 0) lo = 0;
   long long s = 0;
   for (int i = lo; i <= t; ++i) s += accept_count[i];
   const double rate = (double)s / ((double)(t - lo + 1) * (double)n_total);
-  float q = *q_sd;
-  if (rate < (double)target - (double)tol) q *= 0.9f;
-  else if (rate > (double)target + (double)tol) q *= 1.1f;
+  double q = *q_sd;
+  if (rate < target - tol) q *= 0.9;
+  else if (rate > target + tol) q *= 1.1;
   *q_sd = q;
 }
 

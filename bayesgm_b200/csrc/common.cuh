@@ -119,9 +119,22 @@ template <> struct ColMap<1> {
   static __device__ __forceinline__ int col(int cg, int) { return cg; }
 };
 
-__device__ __forceinline__ void lds_rows(const float* in, int rg, float (&a)[RPT]) {
-  float4 lo = *reinterpret_cast<const float4*>(in + rg * 4);
-  float4 hi = *reinterpret_cast<const float4*>(in + 16 + rg * 4);
+// Activation buffers are XOR-swizzled: element (k, row) lives at
+//   k*32 + (((row>>2) ^ ((k>>2)&7)) << 2 | (row&3)),
+// i.e. the 16-byte chunk index of the row is XORed with bits 2..4 of k.  A lane's
+// loads are unaffected (all 8 lanes of a quarter-warp read the same chunk), while the
+// epilogue's STS.128 of 8 lanes (8 different k = output columns, same row chunk) land
+// in 8 different bank groups instead of one.
+__device__ __forceinline__ int act_swz(int k) { return (k >> 2) & 7; }
+__device__ __forceinline__ int act_idx(int k, int row) {
+  return k * TILE_ROWS + ((((row >> 2) ^ act_swz(k)) << 2) | (row & 3));
+}
+
+// a[0..3] = rows rg*4.., a[4..7] = rows 16+rg*4.. of activation row k; `chunk` is the
+// swizzled chunk offset (rg ^ swz(k)) << 2 in floats.
+__device__ __forceinline__ void lds_rows(const float* in_k, int chunk, float (&a)[RPT]) {
+  float4 lo = *reinterpret_cast<const float4*>(in_k + chunk);
+  float4 hi = *reinterpret_cast<const float4*>(in_k + (chunk ^ 16));
   a[0] = lo.x; a[1] = lo.y; a[2] = lo.z; a[3] = lo.w;
   a[4] = hi.x; a[5] = hi.y; a[6] = hi.z; a[7] = hi.w;
 }
@@ -149,21 +162,27 @@ __device__ __forceinline__ void tile_mac(const float* __restrict__ in, const flo
                                          int kp, int rg, int cg, float (&acc)[RPT][C]) {
   constexpr int NT = ColMap<C>::NT;
   float a[RPT], b[C];
-  lds_rows(in, rg, a);
+  lds_rows(in, rg << 2, a);
   lds_cols<C>(w, cg, b);
-#pragma unroll 4
-  for (int k = 0; k < kp; ++k) {
-    float an[RPT], bn[C];
-    lds_rows(in + (k + 1) * TILE_ROWS, rg, an);
-    lds_cols<C>(w + (k + 1) * NT, cg, bn);
+#pragma unroll 1
+  for (int k0 = 0; k0 < kp; k0 += 4) {
+    const int ch_cur = (rg ^ act_swz(k0)) << 2;
+    const int ch_nxt = (rg ^ act_swz(k0 + 4)) << 2;
 #pragma unroll
-    for (int i = 0; i < RPT; ++i)
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = k0 + kk;
+      float an[RPT], bn[C];
+      lds_rows(in + (k + 1) * TILE_ROWS, kk == 3 ? ch_nxt : ch_cur, an);
+      lds_cols<C>(w + (k + 1) * NT, cg, bn);
 #pragma unroll
-      for (int j = 0; j < C; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < RPT; ++i)
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) a[i] = an[i];
+        for (int j = 0; j < C; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
 #pragma unroll
-    for (int j = 0; j < C; ++j) b[j] = bn[j];
+      for (int i = 0; i < RPT; ++i) a[i] = an[i];
+#pragma unroll
+      for (int j = 0; j < C; ++j) b[j] = bn[j];
+    }
   }
 }
 
@@ -175,11 +194,12 @@ struct TileOp {
   unsigned char ctype;  // 0: C=8 (NT 64), 1: C=4 (NT 32), 2: C=1 (NT 8)
   unsigned char src;    // 0: input buffer (zin), 1: activation buffer
   unsigned char epi;    // EPI_*
-  unsigned char pad_;
+  unsigned char post;   // POST_*: what to assemble after this tile (last tile of a net)
   short c0;             // EPI_SSE: first data column; EPI_OUT: first scratch slot
   short nvalid;         // valid columns in this tile
 };
 enum : unsigned char { EPI_ACT = 0, EPI_SSE = 1, EPI_OUT = 2, EPI_LIN = 3 };
+enum : unsigned char { POST_NONE = 0, POST_G = 1, POST_F = 2, POST_H = 3 };
 
 // ------------------------------------------------------- bulk smem loader ---
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -90,9 +90,11 @@ typedef struct {
                                z0 ~ N(0,1) from the Philox stream (:842), then 1  */
   int t_begin, t_end;       /* iteration range of this launch                     */
   int burn_in;              /* samples of iterations t >= burn_in are kept (:895) */
-  const float* q_sd_dev;    /* (1) proposal sd, read once at launch               */
+  const double* q_sd_dev;   /* (1) proposal sd (float64 like the reference's Python
+                               float), read once at launch                        */
   /* noise: injected (both non-NULL; test / exact-parity mode) or Philox4x32-10  */
-  const float* eps_dev;     /* (T,n,zd) UNIT normals, scaled by q_sd in-kernel    */
+  const float* eps_dev;     /* (T,n,zd) UNIT normals; proposal step = float32(q_sd*eps)
+                               computed in float64 like normal(0,q_sd).astype(f32)  */
   const double* u_dev;      /* (T,n)  uniforms, compared as float64 like :870     */
   uint64_t seed;            /* Philox key                                         */
   int64_t row_offset;       /* global index of row 0 (multi-GPU shards)           */
@@ -109,7 +111,7 @@ int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* args, void* stream);
  * device after iteration `t`: rate over iterations (t-window, t] (clipped at 0) of
  * accept_count / (len * n_total); q_sd *= 0.9 / 1.1 outside target +- tolerance. */
 int bgm_mh_adapt_qsd(const int* accept_count_dev, int t, int window, long long n_total,
-                     float target, float tolerance, float* q_sd_dev, void* stream);
+                     double target, double tolerance, double* q_sd_dev, void* stream);
 
 /* Writes exactly the noise bgm_causal_mh would draw from Philox for rows
  * [0,n) + row_offset: z0 (n,zd), eps (t_end-t_begin,n,zd) unit normals, u (.,n)

@@ -76,7 +76,8 @@ class InjectedNoise(object):
         return self.z0.astype(np.float32).copy()
 
     def proposal(self, q_sd, n, zd):
-        return (np.float32(q_sd) * self.eps[self.t]).astype(np.float32)
+        # normal(0, q_sd) scales the unit draw in float64; .astype('float32') rounds once (:862)
+        return (np.float64(q_sd) * self.eps[self.t].astype(np.float64)).astype(np.float32)
 
     def uniform(self, n):
         u = self.u[self.t]
