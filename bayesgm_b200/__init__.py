@@ -7,6 +7,7 @@ infer_from_latent_posterior`, `BGM.predict / tfp_mcmc_sampler`).  See DESIGN.md.
 __version__ = "0.1.0"
 
 from .causalbgm import CausalBGM  # noqa: F401
+from .bgm import BGM  # noqa: F401
 from . import datasets  # noqa: F401
 
-__all__ = ["CausalBGM", "datasets"]
+__all__ = ["CausalBGM", "BGM", "datasets"]

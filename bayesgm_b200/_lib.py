@@ -38,6 +38,26 @@ class MhArgs(C.Structure):
     ]
 
 
+class VarNetDesc(C.Structure):
+    _fields_ = [("z_dim", C.c_int), ("x_dim", C.c_int), ("n_hidden", C.c_int),
+                ("units", C.POINTER(C.c_int)), ("bn", C.POINTER(C.c_float)),
+                ("hidden_params", C.POINTER(C.c_float)), ("mean_params", C.POINTER(C.c_float)),
+                ("var_params", C.POINTER(C.c_float))]
+
+
+class HmcArgs(C.Structure):
+    _fields_ = [
+        ("x_dev", C.c_void_p), ("ldx", C.c_int), ("n", C.c_int),
+        ("z_state_dev", C.c_void_p), ("g_state_dev", C.c_void_p), ("lp_state_dev", C.c_void_p),
+        ("init_mode", C.c_int), ("t_begin", C.c_int), ("t_end", C.c_int), ("burn_in", C.c_int),
+        ("num_leapfrog", C.c_int),
+        ("step_dev", C.c_void_p), ("mom_dev", C.c_void_p), ("logu_dev", C.c_void_p),
+        ("seed", C.c_uint64), ("row_offset", C.c_int64),
+        ("out_samples_dev", C.c_void_p), ("accept_stat_dev", C.c_void_p), ("accept_count_dev", C.c_void_p),
+        ("accept_mask_dev", C.c_void_p), ("log_accept_dev", C.c_void_p),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/bgm_b200.h declares
 SYMBOLS = {
     "bgm_last_error": (C.c_char_p, []),
@@ -60,6 +80,18 @@ SYMBOLS = {
                                     C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "bgm_fp32_peak_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
+    "bgm_hmc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VarNetDesc)]),
+    "bgm_hmc_destroy": (None, [C.c_void_p]),
+    "bgm_hmc_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong),
+                               C.POINTER(C.c_longlong)]),
+    "bgm_hmc_logpost_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "bgm_hmc_run": (C.c_int, [C.c_void_p, C.POINTER(HmcArgs), C.c_void_p]),
+    "bgm_hmc_adapt": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    "bgm_hmc_noise": (C.c_int, [C.c_uint64, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_hmc_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

@@ -1,0 +1,406 @@
+"""BGM with the HMC posterior-sampling path on B200 (sm_100a) kernels.
+
+Drop-in for the method surface of `bayesgm.models.bgm.BGM`
+(`src/bayesgm/models/bgm/base.py`): same constructor, method names, kwargs, return
+shapes and error behaviour for the path this package accelerates --
+`get_log_posterior` (:665), `tfp_mcmc_sampler` (:709), `predict_on_posteriors` (:511),
+`predict` (:527) and `generate` (:483).  The HMC integrator / accept step / shared
+step-size adaptation the reference delegates to TFP 0.18 runs in `hmc_kernel`
+(csrc/hmc.cuh); inputs and outputs are host NumPy arrays like the reference's.
+There is no CPU fallback.  Deterministic generator only (`use_bnn=False`).
+"""
+import ctypes as C
+import datetime
+import os
+
+import numpy as np
+
+from . import _lib
+from .datasets import Gaussian_sampler
+from .nets import DenseNet, VariationalNet
+
+_DEFAULTS = dict(use_bnn=False, g_units=[64] * 5, e_units=[64] * 5, dz_units=[64, 32, 8],
+                 dx_units=[64, 32, 8], lr=0.001, lr_theta=0.005, lr_z=0.005, gamma=0.0, alpha=0.0,
+                 g_d_freq=1, save_model=True, save_res=True, kl_weight=0.00005)
+
+
+def quantile_dim0(torch, a, q):
+    """np.quantile(a, q, axis=0) (linear interpolation) on the device."""
+    srt = torch.sort(a, dim=0).values
+    pos = q * (a.shape[0] - 1)
+    lo = int(np.floor(pos))
+    hi = min(lo + 1, a.shape[0] - 1)
+    return srt[lo] + (srt[hi] - srt[lo]) * float(pos - lo)
+
+
+def nan_coded(data, ind_x1, n, x_dim):
+    """The dense equivalent of tfp_mcmc_sampler's `ind_x1` forms (bgm/base.py:741-775):
+    a copy of `data` with NaN at every entry that is NOT listed as observed."""
+    data = np.array(data, dtype=np.float32, copy=True)
+    if ind_x1 is None:
+        return data
+    obs = np.zeros((n, x_dim), dtype=bool)
+    if isinstance(ind_x1, (list, tuple)) and len(ind_x1) > 0 and isinstance(ind_x1[0], (list, tuple)):
+        assert len(ind_x1) == n, "len(ind_x1)=%d != n_samples=%d" % (len(ind_x1), n)
+        assert max(len(r) for r in ind_x1) > 0, "No observed features"
+        for i, row in enumerate(ind_x1):
+            if len(set(row)) != len(row):
+                raise NotImplementedError("bayesgm_b200: duplicate feature indices in ind_x1 are not supported")
+            obs[i, np.asarray(row, dtype=np.int64)] = True
+    else:
+        ind = np.asarray(ind_x1, dtype=np.int64)
+        if ind.ndim == 1:
+            ind = np.broadcast_to(ind[None, :], (n, ind.shape[0]))
+        elif ind.ndim != 2:
+            raise ValueError("ind_x1 must be rank 1 or 2 if tensor-like.")
+        for i in range(n):
+            if len(np.unique(ind[i])) != ind.shape[1]:
+                raise NotImplementedError("bayesgm_b200: duplicate feature indices in ind_x1 are not supported")
+        np.put_along_axis(obs, ind, True, axis=1)
+    data[~obs] = np.nan
+    return data
+
+
+class BGM(object):
+    """See the reference docstring, bgm/base.py:19-57, for `params`."""
+
+    def __init__(self, params, timestamp=None, random_seed=None):
+        self.params = params
+        self.timestamp = timestamp
+        p = dict(_DEFAULTS)
+        p.update(params)
+        self._p = p
+        if p['use_bnn']:
+            raise NotImplementedError(
+                "bayesgm_b200: use_bnn=True (BayesianVariationalNet, networks/bnn.py) is not built; "
+                "pass use_bnn=False (BaseVariationalNet, networks/base.py).")
+        rng = np.random.RandomState(random_seed) if random_seed is not None else np.random
+        self.g_net = VariationalNet(p['z_dim'], p['x_dim'], 'g_net', p['g_units'], rng)      # :70
+        self.e_net = DenseNet(p['x_dim'], p['z_dim'], 'e_net', p['e_units'], rng)             # :73
+        self.z_sampler = Gaussian_sampler(mean=np.zeros(p['z_dim']), sd=1.0)                 # :85
+        if self.timestamp is None:
+            self.timestamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
+        self.checkpoint_path = "{}/checkpoints/{}/{}".format(p['output_dir'], p['dataset'], self.timestamp)
+        if p['save_model'] and not os.path.exists(self.checkpoint_path):
+            os.makedirs(self.checkpoint_path)
+        self.save_dir = "{}/results/{}/{}".format(p['output_dir'], p['dataset'], self.timestamp)
+        if p['save_res'] and not os.path.exists(self.save_dir):
+            os.makedirs(self.save_dir)
+        self._handle = None
+        self.last_acceptance_rate = None
+        self.last_step_size = None
+
+    # ------------------------------------------------------------------ plumbing
+    def get_config(self):
+        return {"params": self.params}
+
+    def initialize_nets(self, print_summary=False):
+        if print_summary:
+            print(self.g_net.model_name, [self.g_net.input_dim] + self.g_net.nb_units + [self.g_net.output_dim])
+
+    def set_weights(self, g=None, e=None):
+        """Keras-layout weights (`net.get_weights()` of a trained reference model)."""
+        if g is not None:
+            self.g_net.set_weights(g)
+        if e is not None:
+            self.e_net.set_weights(e)
+        self._drop_handle()
+
+    def _drop_handle(self):
+        if self._handle is not None:
+            _lib.load().bgm_hmc_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._drop_handle()
+        except Exception:
+            pass
+
+    def _device_model(self):
+        if self._handle is None:
+            _lib.require_cuda()
+            d, keep = self.g_net.desc()
+            h = C.c_void_p()
+            _lib.call("bgm_hmc_create", C.byref(h), C.byref(d))
+            self._handle = h
+        return self._handle
+
+    def kernel_info(self):
+        smem, nops = C.c_int(), C.c_int()
+        macs, issued = C.c_longlong(), C.c_longlong()
+        _lib.call("bgm_hmc_info", self._device_model(), C.byref(smem), C.byref(nops), C.byref(macs),
+                  C.byref(issued))
+        return dict(smem_bytes=smem.value, n_ops=nops.value, macs_per_grad=macs.value,
+                    issued_macs_per_grad=issued.value)
+
+    def _stage_x(self, data, torch):
+        """Host (n,x_dim) array with NaN = missing -> device (n,ldx), ldx % 4 == 0,
+        pad columns NaN (= not observed)."""
+        xd = self._p['x_dim']
+        if isinstance(data, torch.Tensor):
+            t = data.float()
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+        if t.ndim != 2 or t.shape[1] != xd:
+            raise ValueError("data must have shape (n, %d)" % xd)
+        ldx = (xd + 3) // 4 * 4
+        d = t.contiguous() if t.is_cuda else t.contiguous().to('cuda', non_blocking=True)
+        if ldx != xd:
+            pad = torch.full((d.shape[0], ldx), float('nan'), dtype=torch.float32, device='cuda')
+            pad[:, :xd] = d
+            d = pad
+        return d, ldx, d.shape[0]
+
+    @staticmethod
+    def _dev(a, torch, dtype=None):
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous().to('cuda', non_blocking=True) if not t.is_cuda else t.contiguous()
+
+    # --------------------------------------------------------------- hot path
+    def get_log_posterior(self, data_z, data_x, ind_x1=None, obs_mask=None, *, return_grad=False):
+        """bgm/base.py:665-705 -> (n,) float32.  Missing observations: either NaN entries in
+        `data_x` or the reference's (`ind_x1`, `obs_mask`) padded-gather form (:689-700).
+        `return_grad=True` also returns d log p / d z, the quantity TFP's HMC differentiates for."""
+        torch = _lib.require_cuda()
+        data_x = np.asarray(data_x, dtype=np.float32)
+        n, xd = data_x.shape
+        if ind_x1 is not None:
+            ind = np.asarray(ind_x1, dtype=np.int64)
+            msk = np.ones(ind.shape, bool) if obs_mask is None else np.asarray(obs_mask) > 0
+            lists = [ind[i][msk[i]].tolist() for i in range(n)]
+            data_x = nan_coded(data_x, lists, n, xd)
+        x, ldx, n = self._stage_x(data_x, torch)
+        z = self._dev(data_z, torch, torch.float32)
+        if z.shape != (n, self._p['z_dim']):
+            raise ValueError("data_z must have shape (%d, %d)" % (n, self._p['z_dim']))
+        lp = torch.empty(n, dtype=torch.float32, device='cuda')
+        g = torch.empty((n, self._p['z_dim']), dtype=torch.float32, device='cuda') if return_grad else None
+        _lib.call("bgm_hmc_logpost_grad", self._device_model(), _lib.ptr(x), ldx, _lib.ptr(z), n, _lib.ptr(lp),
+                  _lib.ptr(g), _lib.stream_ptr())
+        if return_grad:
+            return lp.cpu().numpy(), g.cpu().numpy()
+        return lp.cpu().numpy()
+
+    def _hmc_device(self, x, ldx, n, n_mcmc, burn_in, step_size, num_leapfrog_steps, seed, row_offset=0,
+                    noise=None, trace=False, group=None, n_total=None, keep_samples=True,
+                    adaptation_rate=0.01, target_accept=0.75):
+        """Runs the sampler on a staged device buffer; returns a dict of device tensors."""
+        torch = _lib.require_cuda()
+        zd = self._p['z_dim']
+        T = int(burn_in) + int(n_mcmc)
+        n_adapt = int(burn_in * 0.8)                                              # :807
+        m = self._device_model()
+        dev = 'cuda'
+        z_state = torch.empty((n, zd), dtype=torch.float32, device=dev)
+        g_state = torch.empty((n, zd), dtype=torch.float32, device=dev)
+        lp_state = torch.empty(n, dtype=torch.float32, device=dev)
+        samples = torch.empty((n_mcmc, n, zd), dtype=torch.float32, device=dev) if keep_samples else None
+        stat = torch.zeros(max(T, 1), dtype=torch.float64, device=dev)
+        count = torch.zeros(max(T, 1), dtype=torch.int32, device=dev)
+        step = torch.tensor([step_size], dtype=torch.float32, device=dev)
+        a = _lib.HmcArgs()
+        a.x_dev, a.ldx, a.n = x.data_ptr(), ldx, n
+        a.z_state_dev, a.g_state_dev, a.lp_state_dev = z_state.data_ptr(), g_state.data_ptr(), lp_state.data_ptr()
+        a.burn_in, a.num_leapfrog = int(burn_in), int(num_leapfrog_steps)
+        a.step_dev = step.data_ptr()
+        a.seed, a.row_offset = int(seed) & (2 ** 64 - 1), int(row_offset)
+        a.out_samples_dev = samples.data_ptr() if keep_samples else None
+        a.accept_stat_dev, a.accept_count_dev = stat.data_ptr(), count.data_ptr()
+        keep = []
+        if noise is not None:
+            z0 = self._dev(noise['z0'], torch, torch.float32)
+            mom = self._dev(noise['momentum'], torch, torch.float32)
+            logu = self._dev(noise['log_u'], torch, torch.float32)
+            assert z0.shape == (n, zd) and mom.shape == (T, n, zd) and logu.shape == (T, n)
+            z_state.copy_(z0)
+            a.mom_dev, a.logu_dev = mom.data_ptr(), logu.data_ptr()
+            a.init_mode = 1
+            keep += [mom, logu]
+        else:
+            a.init_mode = 2
+        out = dict(samples=samples, z_state=z_state, g_state=g_state, lp_state=lp_state, accept_stat=stat,
+                   accept_count=count, step=step, _keep=keep)
+        if trace:
+            out['accept_mask'] = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+            out['log_accept'] = torch.zeros((T, n), dtype=torch.float32, device=dev)
+            out['step_trace'] = torch.zeros(T, dtype=torch.float32, device=dev)
+            a.accept_mask_dev, a.log_accept_dev = out['accept_mask'].data_ptr(), out['log_accept'].data_ptr()
+        st = _lib.stream_ptr()
+        n_total = int(n_total) if n_total is not None else n
+        # one launch per step while the shared step size adapts (:805-809), then one launch
+        t = 0
+        while t < min(n_adapt, T):
+            a.t_begin, a.t_end = t, t + 1
+            if trace:
+                out['step_trace'][t] = step[0]
+            _lib.call("bgm_hmc_run", m, C.byref(a), st)
+            a.init_mode = 0
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(stat[t:t + 1], group=group)
+            _lib.call("bgm_hmc_adapt", C.c_void_p(stat.data_ptr()), t, n_total, float(target_accept),
+                      float(adaptation_rate), C.c_void_p(step.data_ptr()), st)
+            t += 1
+        if t < T or a.init_mode != 0:
+            a.t_begin, a.t_end = t, T
+            if trace and t < T:
+                out['step_trace'][t:] = step[0]
+            _lib.call("bgm_hmc_run", m, C.byref(a), st)
+        return out
+
+    def tfp_mcmc_sampler(self, data, ind_x1=None, n_mcmc=3000, burn_in=5000, step_size=0.01,
+                         num_leapfrog_steps=10, seed=42, *, noise=None, return_trace=False, verbose=1):
+        """bgm/base.py:709-830 -> np.ndarray (n_mcmc, n, z_dim).
+
+        `data` may carry NaN for missing entries (as BGM.predict receives it) and/or
+        `ind_x1` may list the observed features per row (list of lists, (n,K) or (K,)
+        indices).  Noise: in-kernel Philox4x32-10 keyed by `seed`, or
+        `noise=dict(z0, momentum, log_u)` of shapes (n,zd), (T,n,zd), (T,n) for
+        state-for-state parity tests.
+        """
+        torch = _lib.require_cuda()
+        data = np.asarray(data, dtype=np.float32)
+        n, xd = data.shape
+        x, ldx, n = self._stage_x(nan_coded(data, ind_x1, n, xd), torch)
+        r = self._hmc_device(x, ldx, n, int(n_mcmc), int(burn_in), float(step_size), int(num_leapfrog_steps),
+                             seed, noise=noise, trace=return_trace)
+        T = int(burn_in) + int(n_mcmc)
+        counts = r['accept_count'].cpu().numpy()[:T]
+        self.last_acceptance_rate = float(counts[int(burn_in):].sum()) / max(1, int(n_mcmc) * n)   # :825
+        self.last_step_size = float(r['step'].cpu()[0])
+        if verbose:
+            print(f"TFP MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
+        samples = r['samples'].cpu().numpy()
+        if return_trace:
+            tr = dict(accept=r['accept_mask'].cpu().numpy().astype(bool), log_accept=r['log_accept'].cpu().numpy(),
+                      step=r['step_trace'].cpu().numpy(), step_final=self.last_step_size, accept_count=counts,
+                      z_final=r['z_state'].cpu().numpy(), lp_final=r['lp_state'].cpu().numpy(),
+                      g_final=r['g_state'].cpu().numpy())
+            return samples, tr
+        return samples
+
+    def philox_noise(self, seed, n, T, row_offset=0):
+        """The exact noise `tfp_mcmc_sampler(seed=...)` draws in-kernel."""
+        torch = _lib.require_cuda()
+        zd = self._p['z_dim']
+        z0 = torch.empty((n, zd), dtype=torch.float32, device='cuda')
+        mom = torch.empty((T, n, zd), dtype=torch.float32, device='cuda')
+        logu = torch.empty((T, n), dtype=torch.float32, device='cuda')
+        _lib.call("bgm_hmc_noise", int(seed) & (2 ** 64 - 1), int(row_offset), n, zd, 0, T, _lib.ptr(z0),
+                  _lib.ptr(mom), _lib.ptr(logu), _lib.stream_ptr())
+        return dict(z0=z0.cpu().numpy(), momentum=mom.cpu().numpy(), log_u=logu.cpu().numpy())
+
+    def _predict_device(self, zs, n_keep, n, seed, row_offset=0, noise=None, sample0=0):
+        torch = _lib.require_cuda()
+        out = torch.empty((n_keep, n, self._p['x_dim']), dtype=torch.float32, device='cuda')
+        nz = self._dev(noise, torch, torch.float32) if noise is not None else None
+        _lib.call("bgm_hmc_predict", self._device_model(), _lib.ptr(zs), n_keep, n, int(sample0),
+                  int(seed) & (2 ** 64 - 1), int(row_offset), _lib.ptr(nz), _lib.ptr(out), _lib.stream_ptr())
+        return out
+
+    def predict_on_posteriors(self, data_posterior_z, *, seed=0, noise=None):
+        """bgm/base.py:511-525 -> (n_mcmc, n, x_dim) posterior-predictive draws.
+        `noise` (n_mcmc, n, x_dim) injects the N(0,1) draws of `reparameterize` (:113-117)."""
+        torch = _lib.require_cuda()
+        zs = self._dev(data_posterior_z, torch, torch.float32)
+        n_keep, n, _ = zs.shape
+        return self._predict_device(zs, n_keep, n, seed, noise=noise).cpu().numpy()
+
+    def generate(self, nb_samples=1000, use_x_sd=True, *, seed=0):
+        """bgm/base.py:483-509: z ~ N(0,I) through the generator -> (x, sigma^2)."""
+        torch = _lib.require_cuda()
+        z = torch.from_numpy(np.random.RandomState(seed).standard_normal((nb_samples, self._p['z_dim']))
+                             .astype(np.float32)).cuda()
+        zeros = torch.zeros((1, nb_samples, self._p['x_dim']), dtype=torch.float32, device='cuda')
+        mu = self._predict_device(z[None], 1, nb_samples, seed, noise=zeros)[0]
+        draw = self._predict_device(z[None], 1, nb_samples, seed)[0]
+        ones = torch.ones_like(zeros)
+        sd = self._predict_device(z[None], 1, nb_samples, seed, noise=ones)[0] - mu
+        return (draw if use_x_sd else mu).cpu().numpy(), (sd * sd).cpu().numpy()
+
+    def predict(self, data, alpha=0.05, return_samples=False, bs=100, n_mcmc=5000, burn_in=5000, step_size=0.01,
+                num_leapfrog_steps=10, seed=42, *, group=None, row_offset=0, n_total=None, verbose=1):
+        """bgm/base.py:527-663 -> (imputed data | posterior-predictive samples, intervals).
+
+        The chain states and the predictive draws stay on the device; each `bs` slice of
+        rows is reduced there (mean over samples, quantiles on the missing dims) and only
+        the results come back.  Under torch.distributed pass `group`, this rank's global
+        `row_offset` and the global row count `n_total`: rows are sharded, the only
+        collective is the scalar all-reduce of the shared step-size statistic while TFP's
+        SimpleStepSizeAdaptation is active.
+        """
+        assert 0 < alpha < 1, "The significance level 'alpha' must be greater than 0 and less than 1."
+        torch = _lib.require_cuda()
+        data_np = np.asarray(data, dtype=np.float32)
+        n, xd = data_np.shape
+        miss = np.isnan(data_np)
+        x, ldx, n = self._stage_x(data_np, torch)
+        r = self._hmc_device(x, ldx, n, int(n_mcmc), int(burn_in), float(step_size), int(num_leapfrog_steps),
+                             seed, row_offset=row_offset, group=group, n_total=n_total)
+        T = int(burn_in) + int(n_mcmc)
+        counts = r['accept_count'][int(burn_in):T].sum()
+        self.last_step_size = float(r['step'].cpu()[0])
+        self.last_acceptance_rate = float(counts.item()) / max(1, int(n_mcmc) * n)
+        if verbose:
+            print(f"TFP MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
+        zs = r['samples']
+        same_pattern = bool(np.all(miss == miss[0]))                               # :622-623
+        miss_idx = np.where(miss[0])[0]
+        bs = max(1, int(bs))
+        imputed = np.empty((n, xd), np.float32)
+        all_draws = [] if return_samples else None
+        lowers, uppers = [], []
+        miss_dev = torch.from_numpy(miss).cuda()
+        for i in range(0, n, bs):                                                  # :607-612
+            j = min(i + bs, n)
+            zb = zs[:, i:j, :].contiguous()
+            draws = self._predict_device(zb, int(n_mcmc), j - i, seed, row_offset=row_offset + i)
+            if return_samples:
+                all_draws.append(draws.cpu().numpy())
+            imputed[i:j] = draws.mean(dim=0).cpu().numpy()                         # :660
+            if same_pattern:
+                if miss_idx.size:
+                    dim = draws[:, :, torch.from_numpy(miss_idx).cuda()]
+                    lowers.append(quantile_dim0(torch, dim, alpha / 2.0).cpu().numpy())
+                    uppers.append(quantile_dim0(torch, dim, 1.0 - alpha / 2.0).cpu().numpy())
+            else:
+                lo = quantile_dim0(torch, draws, alpha / 2.0).cpu().numpy()
+                up = quantile_dim0(torch, draws, 1.0 - alpha / 2.0).cpu().numpy()
+                lowers.append(lo)
+                uppers.append(up)
+        if same_pattern:
+            if miss_idx.size == 0:
+                pred_interval = np.zeros((n, 0, 2), dtype=np.float32)
+            else:
+                pred_interval = np.stack([np.concatenate(lowers, 0), np.concatenate(uppers, 0)], axis=-1)
+        else:
+            lo, up = np.concatenate(lowers, 0), np.concatenate(uppers, 0)
+            pred_interval = []
+            for i in range(n):                                                     # :637-649
+                idx = np.where(miss[i])[0]
+                if idx.size == 0:
+                    pred_interval.append(np.zeros((0, 2), dtype=np.float32))
+                else:
+                    pred_interval.append(np.stack([lo[i, idx], up[i, idx]], axis=-1))
+        del miss_dev
+        if return_samples:
+            return np.concatenate(all_draws, axis=1), pred_interval
+        obs_mask = 1.0 - miss.astype(np.float32)
+        data_imputed = miss.astype(np.float32) * imputed + obs_mask * np.nan_to_num(data_np, nan=0.0)  # :662
+        return data_imputed, pred_interval
+
+    # ------------------------------------------------- not on the hot path yet
+    def fit(self, data, batch_size=32, epochs=100, epochs_per_eval=5, use_egm_init=True, egm_n_iter=20000,
+            egm_batches_per_eval=500, verbose=1):
+        raise NotImplementedError(
+            "bayesgm_b200: the BGM training path (bgm/base.py:145-442) has no sm_100a kernels yet; "
+            "load trained weights with set_weights().")
+
+    def egm_init(self, data, egm_n_iter=10000, batch_size=32, egm_batches_per_eval=500, verbose=1):
+        raise NotImplementedError("bayesgm_b200: BGM EGM initialisation (bgm/base.py:190-340) is not built yet.")

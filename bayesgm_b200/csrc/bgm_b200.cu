@@ -442,3 +442,5 @@ extern "C" int bgm_fp32_peak_tflops(double* tflops, void* stream) {
   *tflops = best;
   return 0;
 }
+
+#include "hmc_api.cuh"

@@ -1,0 +1,310 @@
+// Host side of the BGM / HMC entry points (include/bgm_b200.h): cuts the generator's
+// Keras arrays into the streamed tile program of hmc.cuh, validates, launches.
+// Included by bgm_b200.cu.
+#pragma once
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "hmc.cuh"
+
+struct bgm_hmc {
+  bgm::HmcProgram prog;      // forward + backward (one gradient evaluation)
+  bgm::HmcProgram prog_fwd;  // forward only (posterior-predictive draws)
+  float* image_dev = nullptr;
+  int sm_count = 0;
+  int smem_max = 0;
+  long long macs = 0, issued = 0;
+};
+
+namespace bgm {
+
+constexpr int HMC_SMEM_RESERVE = 1024;  // static shared memory (barriers) + alignment slack
+
+struct HmcPacker {
+  std::vector<float> image;
+  long long issued = 0;
+  // appends a tile [kp][NT] | bias[NT]; `fill(k, c)` gives W, `bias(c)` the bias
+  template <class FW, class FB>
+  HmcOp add(int kp, int NT, unsigned char kind, int layer, int c0, int flags, FW fill, FB bias) {
+    HmcOp op;
+    memset(&op, 0, sizeof(op));
+    op.g_off = (int)image.size();
+    image.resize(image.size() + (size_t)kp * NT + NT, 0.f);
+    for (int k = 0; k < kp; ++k)
+      for (int c = 0; c < NT; ++c) image[op.g_off + (size_t)k * NT + c] = fill(k, c);
+    for (int c = 0; c < NT; ++c) image[op.g_off + (size_t)kp * NT + c] = bias(c);
+    op.bytes = (kp * NT + NT) * 4;
+    op.kp = (short)kp;
+    op.kind = kind;
+    op.layer = (unsigned char)layer;
+    op.c0 = (short)c0;
+    op.flags = (short)flags;
+    issued += (long long)kp * NT;
+    return op;
+  }
+};
+
+static int hmc_pick_ncons(const bgm_hmc* m, int n_rows) {
+  const HmcProgram& P = m->prog;
+  const int per_warp = (P.kin * TILE_ROWS + 2 * HMC_BUF + 3 * P.zd * TILE_ROWS) * 4;
+  const int ring = HMC_STAGES * HMC_STAGE_FLOATS * 4;
+  int fit = (m->smem_max - HMC_SMEM_RESERVE - ring) / per_warp;
+  int ncons = fit >= 8 ? 8 : (fit >= 4 ? 4 : (fit >= 2 ? 2 : (fit >= 1 ? 1 : 0)));
+  // small problems: spread the 32-row tiles over more CTAs instead of more warps per CTA
+  const int ntiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+  while (ncons > 1 && (ntiles + ncons - 1) / ncons < m->sm_count) ncons >>= 1;
+  return ncons;
+}
+
+static int hmc_launch(const bgm_hmc* m, const HmcProgram& P, HmcDev& D, int n_rows, cudaStream_t st) {
+  const int ncons = hmc_pick_ncons(m, n_rows);
+  if (ncons < 1) return fail(BGM_ERR_NOMEM, "bgm_hmc: per-warp buffers do not fit in shared memory");
+  D.ncons = ncons;
+  const int per_warp = P.kin * TILE_ROWS + 2 * HMC_BUF + 3 * P.zd * TILE_ROWS;
+  const int smem = (HMC_STAGES * HMC_STAGE_FLOATS + ncons * per_warp) * 4;
+  const int ntiles = (n_rows + TILE_ROWS - 1) / TILE_ROWS;
+  const int nblocks = (ntiles + ncons - 1) / ncons;
+  const int grid = std::max(1, std::min(nblocks, m->sm_count));
+  BGM_CUDA_OK(cudaFuncSetAttribute(hmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_max - HMC_SMEM_RESERVE));
+  hmc_kernel<<<grid, ncons * 32, smem, st>>>(P, m->image_dev, D);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bgm
+
+extern "C" {
+
+int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
+  using namespace bgm;
+  if (!out || !g) return fail(BGM_ERR_ARG, "bgm_hmc_create: null argument");
+  *out = nullptr;
+  if (!g->units || !g->bn || !g->hidden_params || !g->mean_params || !g->var_params)
+    return fail(BGM_ERR_ARG, "bgm_hmc_create: null array in the net description");
+  const int zd = g->z_dim, xd = g->x_dim, nh = g->n_hidden;
+  if (zd < 1 || zd > HMC_MAXZ) return fail(BGM_ERR_UNSUPPORTED, "bgm_hmc_create: z_dim must be in [1, 16]");
+  if (xd < 1) return fail(BGM_ERR_ARG, "bgm_hmc_create: x_dim must be >= 1");
+  if (nh < 1 || nh > HMC_MAXL) return fail(BGM_ERR_UNSUPPORTED, "bgm_hmc_create: 1..6 hidden layers are supported");
+  for (int l = 0; l < nh; ++l)
+    if (g->units[l] < 1 || g->units[l] > 64)
+      return fail(BGM_ERR_UNSUPPORTED, "bgm_hmc_create: hidden widths must be in [1, 64]");
+  const int ntile = (xd + 31) / 32, ndz = (zd + 7) / 8;
+  if (nh + 2 * ntile + (nh - 1) + ndz > HMC_MAX_OPS)
+    return fail(BGM_ERR_UNSUPPORTED, "bgm_hmc_create: x_dim too large for the tile program");
+
+  // unpack the Keras arrays
+  std::vector<int> dims(nh + 1);
+  dims[0] = zd;
+  for (int l = 0; l < nh; ++l) dims[l + 1] = g->units[l];
+  std::vector<const float*> Wl(nh), bl(nh);
+  const float* p = g->hidden_params;
+  long long macs = 0;
+  for (int l = 0; l < nh; ++l) {
+    Wl[l] = p;
+    p += (size_t)dims[l] * dims[l + 1];
+    bl[l] = p;
+    p += dims[l + 1];
+    macs += (long long)dims[l] * dims[l + 1];
+  }
+  const int last = dims[nh];
+  const float *Wm = g->mean_params, *bm = g->mean_params + (size_t)last * xd;
+  const float *Wv = g->var_params, *bv = g->var_params + (size_t)last * xd;
+  macs += 2LL * last * xd;
+  macs *= 2;  // forward + gradient w.r.t. the inputs
+
+  bgm_hmc* m = new bgm_hmc();
+  HmcProgram& P = m->prog;
+  memset(&P, 0, sizeof(P));
+  P.zd = zd;
+  P.kin = (zd + 3) / 4 * 4;
+  P.x_dim = xd;
+  P.nh = nh;
+  for (int d = 0; d < zd; ++d) {   // Keras BN inference: gamma*(z-mean)/sqrt(var+1e-3)+beta
+    const float gamma = g->bn[d], beta = g->bn[zd + d], mean = g->bn[2 * zd + d], var = g->bn[3 * zd + d];
+    P.bn_mean[d] = mean;
+    P.bn_inv[d] = gamma / sqrtf(var + 1e-3f);
+    P.bn_beta[d] = beta;
+  }
+  HmcPacker pk;
+  std::vector<HmcOp> ops, fops;
+  auto zero = [](int) { return 0.f; };
+  auto r4 = [](int a) { return (a + 3) / 4 * 4; };
+  for (int l = 0; l < nh; ++l) {  // forward hidden layers
+    const int K = dims[l], N = dims[l + 1];
+    const int kp = l == 0 ? P.kin : r4(K);
+    ops.push_back(pk.add(kp, 64, HK_FWD, l, 0, 0,
+                         [&](int k, int c) { return (k < K && c < N) ? Wl[l][(size_t)k * N + c] : 0.f; },
+                         [&](int c) { return c < N ? bl[l][c] : 0.f; }));
+    fops.push_back(ops.back());
+  }
+  for (int t = 0; t < ntile; ++t) {  // fused head tiles: 32 data columns, [mean | var]
+    const int c0 = t * 32;
+    auto col = [&](int c) { return c0 + (c & 31); };
+    ops.push_back(pk.add(r4(last), 64, HK_HEADF, 0, c0, 0,
+                         [&](int k, int c) {
+                           if (k >= last || col(c) >= xd) return 0.f;
+                           return (c < 32 ? Wm : Wv)[(size_t)k * xd + col(c)];
+                         },
+                         [&](int c) { return col(c) < xd ? (c < 32 ? bm : bv)[col(c)] : 0.f; }));
+    fops.push_back(ops.back());
+    const int flags = (t == 0 ? 1 : 0) | (t == ntile - 1 ? 2 : 0);
+    ops.push_back(pk.add(64, 64, HK_HEADB, nh - 1, c0, flags,
+                         [&](int c, int k) {   // row = tile column c, output = hidden unit k
+                           if (k >= last || col(c) >= xd) return 0.f;
+                           return (c < 32 ? Wm : Wv)[(size_t)k * xd + col(c)];
+                         },
+                         zero));
+  }
+  for (int l = nh - 1; l >= 1; --l) {  // backward hidden layers: d/d(output of layer l-1)
+    const int K = dims[l], N = dims[l + 1];
+    ops.push_back(pk.add(r4(N), 64, HK_BWD, l - 1, 0, 0,
+                         [&](int j, int i) { return (j < N && i < K) ? Wl[l][(size_t)i * N + j] : 0.f; }, zero));
+  }
+  for (int t = 0; t < ndz; ++t) {  // backward of layer 0: d/d BN(z)
+    const int N = dims[1];
+    ops.push_back(pk.add(r4(N), 8, HK_DZ, 0, t * 8, 0,
+                         [&](int j, int c) { return (j < N && t * 8 + c < zd) ? Wl[0][(size_t)(t * 8 + c) * N + j] : 0.f; },
+                         zero));
+  }
+  P.n_ops = (int)ops.size();
+  for (int i = 0; i < P.n_ops; ++i) P.ops[i] = ops[i];
+  m->prog_fwd = P;
+  m->prog_fwd.n_ops = (int)fops.size();
+  for (size_t i = 0; i < fops.size(); ++i) m->prog_fwd.ops[i] = fops[i];
+  m->macs = macs;
+  m->issued = pk.issued;
+
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e == cudaSuccess) e = cudaMalloc(&m->image_dev, pk.image.size() * sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaMemcpy(m->image_dev, pk.image.data(), pk.image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (m->image_dev) cudaFree(m->image_dev);
+    delete m;
+    return fail(BGM_ERR_CUDA, std::string("bgm_hmc_create: ") + cudaGetErrorString(e));
+  }
+  if (hmc_pick_ncons(m, 1 << 30) < 1) {
+    cudaFree(m->image_dev);
+    delete m;
+    return fail(BGM_ERR_NOMEM, "bgm_hmc_create: per-warp buffers do not fit in shared memory");
+  }
+  *out = m;
+  return 0;
+}
+
+void bgm_hmc_destroy(bgm_hmc* m) {
+  if (!m) return;
+  if (m->image_dev) cudaFree(m->image_dev);
+  delete m;
+}
+
+int bgm_hmc_info(const bgm_hmc* m, int* smem_bytes, int* n_ops, long long* macs_per_grad,
+                 long long* issued_macs_per_grad) {
+  using namespace bgm;
+  if (!m) return fail(BGM_ERR_ARG, "bgm_hmc_info: null model");
+  const HmcProgram& P = m->prog;
+  const int ncons = hmc_pick_ncons(m, 1 << 30);
+  if (smem_bytes)
+    *smem_bytes = (HMC_STAGES * HMC_STAGE_FLOATS + ncons * (P.kin * TILE_ROWS + 2 * HMC_BUF + 3 * P.zd * TILE_ROWS)) * 4;
+  if (n_ops) *n_ops = P.n_ops;
+  if (macs_per_grad) *macs_per_grad = m->macs;
+  if (issued_macs_per_grad) *issued_macs_per_grad = m->issued;
+  return 0;
+}
+
+static int hmc_check_x(const char* fn, const float* x, int ldx, int n, int x_dim) {
+  using namespace bgm;
+  if (!x) return fail(BGM_ERR_ARG, std::string(fn) + ": null x_dev");
+  if (n < 1) return fail(BGM_ERR_ARG, std::string(fn) + ": n must be >= 1");
+  if (ldx < x_dim || ldx % 4 != 0) return fail(BGM_ERR_ARG, std::string(fn) + ": ldx must be >= x_dim and a multiple of 4");
+  if (reinterpret_cast<uintptr_t>(x) % 16 != 0) return fail(BGM_ERR_ARG, std::string(fn) + ": x_dev must be 16-byte aligned");
+  return 0;
+}
+
+int bgm_hmc_logpost_grad(const bgm_hmc* m, const float* x_dev, int ldx, const float* z_dev, int n,
+                         float* out_logp_dev, float* out_grad_dev, void* stream) {
+  using namespace bgm;
+  if (!m) return fail(BGM_ERR_ARG, "bgm_hmc_logpost_grad: null model");
+  int rc = hmc_check_x("bgm_hmc_logpost_grad", x_dev, ldx, n, m->prog.x_dim);
+  if (rc) return rc;
+  if (!z_dev || !out_logp_dev) return fail(BGM_ERR_ARG, "bgm_hmc_logpost_grad: null z / out pointer");
+  HmcDev D;
+  memset(&D, 0, sizeof(D));
+  D.a.x_dev = x_dev; D.a.ldx = ldx; D.a.n = n; D.a.lp_state_dev = out_logp_dev;
+  D.mode = HMC_EVAL;
+  D.z_in = z_dev;
+  D.out_grad = out_grad_dev;
+  return hmc_launch(m, m->prog, D, n, (cudaStream_t)stream);
+}
+
+int bgm_hmc_run(const bgm_hmc* m, const bgm_hmc_args* a, void* stream) {
+  using namespace bgm;
+  if (!m || !a) return fail(BGM_ERR_ARG, "bgm_hmc_run: null model / args");
+  int rc = hmc_check_x("bgm_hmc_run", a->x_dev, a->ldx, a->n, m->prog.x_dim);
+  if (rc) return rc;
+  if (!a->z_state_dev || !a->g_state_dev || !a->lp_state_dev)
+    return fail(BGM_ERR_ARG, "bgm_hmc_run: z_state_dev, g_state_dev and lp_state_dev are required");
+  if (a->init_mode < 0 || a->init_mode > 2) return fail(BGM_ERR_ARG, "bgm_hmc_run: init_mode must be 0, 1 or 2");
+  if (a->t_begin < 0 || a->t_end < a->t_begin) return fail(BGM_ERR_ARG, "bgm_hmc_run: bad step range");
+  if (a->num_leapfrog < 1) return fail(BGM_ERR_ARG, "bgm_hmc_run: num_leapfrog must be >= 1");
+  if (!a->step_dev) return fail(BGM_ERR_ARG, "bgm_hmc_run: step_dev is required");
+  if ((a->mom_dev == nullptr) != (a->logu_dev == nullptr))
+    return fail(BGM_ERR_ARG, "bgm_hmc_run: mom_dev and logu_dev must be given together");
+  if (a->init_mode == 2 && a->mom_dev)
+    return fail(BGM_ERR_ARG, "bgm_hmc_run: init_mode 2 draws from Philox; pass z_state with injected noise");
+  HmcDev D;
+  memset(&D, 0, sizeof(D));
+  D.a = *a;
+  D.mode = HMC_RUN;
+  return hmc_launch(m, m->prog, D, a->n, (cudaStream_t)stream);
+}
+
+int bgm_hmc_adapt(const double* accept_stat_dev, int t, long long n_total, float target, float rate,
+                  float* step_dev, void* stream) {
+  using namespace bgm;
+  if (!accept_stat_dev || !step_dev) return fail(BGM_ERR_ARG, "bgm_hmc_adapt: null pointer");
+  if (t < 0 || n_total < 1) return fail(BGM_ERR_ARG, "bgm_hmc_adapt: bad t / n_total");
+  hmc_adapt_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(accept_stat_dev, t, n_total, target, rate, step_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_hmc_noise(uint64_t seed, int64_t row_offset, int n, int z_dim, int t_begin, int t_end,
+                  float* z0_dev, float* mom_dev, float* logu_dev, void* stream) {
+  using namespace bgm;
+  if (n < 1 || z_dim < 1 || t_end < t_begin) return fail(BGM_ERR_ARG, "bgm_hmc_noise: bad sizes");
+  const long long total = (long long)(t_end - t_begin + 1) * n;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  hmc_noise_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(seed, row_offset, n, z_dim, t_begin, t_end, z0_dev,
+                                                          mom_dev, logu_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, int n, int sample0,
+                    uint64_t seed, int64_t row_offset, const float* noise_dev, float* out_x_dev,
+                    void* stream) {
+  using namespace bgm;
+  if (!m || !z_samples_dev || !out_x_dev) return fail(BGM_ERR_ARG, "bgm_hmc_predict: null model / pointer");
+  if (n_keep < 1 || n < 1) return fail(BGM_ERR_ARG, "bgm_hmc_predict: n_keep and n must be >= 1");
+  if ((long long)n_keep * n > 0x7fffffffLL) return fail(BGM_ERR_ARG, "bgm_hmc_predict: n_keep*n exceeds 2^31-1; call per chunk of samples");
+  HmcDev D;
+  memset(&D, 0, sizeof(D));
+  D.a.n = n_keep * n;
+  D.a.ldx = 0;
+  D.a.seed = seed;
+  D.a.row_offset = row_offset;
+  D.mode = HMC_PREDICT;
+  D.z_in = z_samples_dev;
+  D.out_x = out_x_dev;
+  D.noise_x = noise_dev;
+  D.n_per_sample = n;
+  D.sample0 = sample0;
+  return hmc_launch(m, m->prog_fwd, D, n_keep * n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -61,3 +61,62 @@ class DenseNet(object):
 
     def as_oracle_layers(self):
         return [(W, b) for W, b in self.layers]
+
+
+class VariationalNet(object):
+    """`BaseVariationalNet` (networks/base.py:53-117): BatchNormalization on the input,
+    Dense+LeakyReLU(0.2) hidden layers, a mean head and a softplus(+eps) variance head.
+    Keras defaults: BN gamma 1, beta 0, moving mean 0, moving variance 1, eps 1e-3."""
+
+    def __init__(self, input_dim, output_dim, model_name, nb_units, rng=None):
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.model_name = model_name
+        self.nb_units = [int(u) for u in nb_units]
+        rng = rng if rng is not None else np.random
+        self.bn = dict(gamma=np.ones(self.input_dim, np.float32), beta=np.zeros(self.input_dim, np.float32),
+                       mean=np.zeros(self.input_dim, np.float32), var=np.ones(self.input_dim, np.float32))
+        dims = [self.input_dim] + self.nb_units
+
+        def dense(fi, fo):
+            lim = np.sqrt(6.0 / (fi + fo))
+            return [rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32), np.zeros(fo, np.float32)]
+        self.hidden = [dense(dims[i], dims[i + 1]) for i in range(len(self.nb_units))]
+        self.mean = dense(dims[-1], self.output_dim)
+        self.var = dense(dims[-1], self.output_dim)
+
+    # Keras order: BN [gamma, beta, moving_mean, moving_variance], hidden kernel/bias..., mean, var
+    def get_weights(self):
+        out = [self.bn[k].copy() for k in ('gamma', 'beta', 'mean', 'var')]
+        for W, b in self.hidden + [self.mean, self.var]:
+            out += [W.copy(), b.copy()]
+        return out
+
+    def set_weights(self, weights):
+        assert len(weights) == 4 + 2 * (len(self.hidden) + 2), "expected BN(4) + kernel/bias per Dense layer"
+        for k, w in zip(('gamma', 'beta', 'mean', 'var'), weights[:4]):
+            w = np.asarray(w, np.float32)
+            assert w.shape == (self.input_dim,)
+            self.bn[k] = w.copy()
+        layers = self.hidden + [self.mean, self.var]
+        for i, layer in enumerate(layers):
+            W = np.asarray(weights[4 + 2 * i], np.float32)
+            b = np.asarray(weights[5 + 2 * i], np.float32)
+            assert W.shape == layer[0].shape and b.shape == layer[1].shape, \
+                "%s layer %d: shape mismatch" % (self.model_name, i)
+            layer[0], layer[1] = W.copy(), b.copy()
+
+    def desc(self):
+        """(bgm_varnet_desc, keep-alive tuple) for the C ABI."""
+        units = (C.c_int * len(self.nb_units))(*self.nb_units)
+        bn = np.ascontiguousarray(np.concatenate([self.bn[k] for k in ('gamma', 'beta', 'mean', 'var')]), np.float32)
+        flat = lambda layers: np.ascontiguousarray(
+            np.concatenate([np.concatenate([W.ravel(), b.ravel()]) for W, b in layers]).astype(np.float32))
+        hp, mp, vp = flat(self.hidden), flat([self.mean]), flat([self.var])
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        d = _lib.VarNetDesc(self.input_dim, self.output_dim, len(self.nb_units),
+                            C.cast(units, C.POINTER(C.c_int)), fp(bn), fp(hp), fp(mp), fp(vp))
+        return d, (units, bn, hp, mp, vp)
+
+    def as_oracle_params(self):
+        return dict(bn=dict(self.bn), hidden=[(W, b) for W, b in self.hidden],
+                    mean=(self.mean[0], self.mean[1]), var=(self.var[0], self.var[1]))

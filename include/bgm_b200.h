@@ -131,6 +131,91 @@ int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_kee
                       int64_t row_offset, const float* noise_dev, double* adrf_sum_dev,
                       float* ite_dev, void* stream);
 
+/* --------------------------------------------------------------- BGM / HMC -- */
+/* The generator of BGM, `BaseVariationalNet` (networks/base.py:53-117), in
+ * inference mode as bgm/base.py:679 calls it: BatchNormalization on z with its
+ * moving statistics, n_hidden Dense+LeakyReLU(0.2) layers, a mean head and a
+ * softplus(+1e-6) variance head.  All arrays are HOST memory in Keras layout:
+ *   bn            4*z_dim floats: gamma, beta, moving_mean, moving_variance (eps 1e-3)
+ *   hidden_params per layer kernel[in][out] then bias[out], concatenated
+ *   mean_params   kernel[units[-1]][x_dim] then bias[x_dim]; var_params likewise.
+ * Supported: z_dim <= 16, hidden widths <= 64, n_hidden <= 6, any x_dim <= 2600. */
+typedef struct {
+  int z_dim, x_dim, n_hidden;
+  const int* units;
+  const float* bn;
+  const float* hidden_params;
+  const float* mean_params;
+  const float* var_params;
+} bgm_varnet_desc;
+
+typedef struct bgm_hmc bgm_hmc; /* opaque: g_net tiles (forward + transposed) in device memory */
+
+int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g_net);
+void bgm_hmc_destroy(bgm_hmc* m);
+/* shared-memory bytes per CTA at 8 consumer warps, tile ops per gradient evaluation,
+ * algorithmic and issued FMAs per row per gradient evaluation (forward + d/dz). */
+int bgm_hmc_info(const bgm_hmc* m, int* smem_bytes, int* n_ops, long long* macs_per_grad,
+                 long long* issued_macs_per_grad);
+
+/* BGM.get_log_posterior (bgm/base.py:665-705) and its gradient w.r.t. z (what TFP's
+ * HMC obtains by autodiff).  x_dev: (n, ldx), ldx % 4 == 0, 16-byte aligned; a NaN
+ * entry is a MISSING observation (the input convention of BGM.predict, :527-545) and
+ * contributes nothing -- the dense equivalent of the reference's ind_x1 / obs_mask
+ * gather (:689-700).  z_dev: (n,z_dim); out_logp_dev: (n); out_grad_dev: (n,z_dim) or NULL. */
+int bgm_hmc_logpost_grad(const bgm_hmc* m, const float* x_dev, int ldx, const float* z_dev, int n,
+                         float* out_logp_dev, float* out_grad_dev, void* stream);
+
+/* BGM.tfp_mcmc_sampler (bgm/base.py:709-830): HMC steps [t_begin, t_end) of n chains
+ * that share ONE step size (read from step_dev at launch), num_leapfrog leapfrog steps
+ * each, in one persistent launch.  While TFP's SimpleStepSizeAdaptation is active (the
+ * first int(0.8*burn_in) steps, :805-809) the host launches one step at a time with
+ * bgm_hmc_adapt in between on the same stream; afterwards a single launch runs the rest. */
+typedef struct {
+  const float* x_dev;        /* (n,ldx) data, NaN = missing                          */
+  int ldx;
+  int n;
+  float* z_state_dev;        /* (n,z_dim) current state, in/out                      */
+  float* g_state_dev;        /* (n,z_dim) gradient of log p at the current state     */
+  float* lp_state_dev;       /* (n)       log p at the current state                 */
+  int init_mode;             /* 0: continue; 1: z_state given, evaluate log p / grad
+                                first; 2: z0 ~ N(0,1) from Philox (:778), then 1     */
+  int t_begin, t_end;
+  int burn_in;               /* states of steps t >= burn_in are kept                */
+  int num_leapfrog;
+  const float* step_dev;     /* (1) shared step size (float32 like TFP's state dtype)*/
+  const float* mom_dev;      /* (T,n,z_dim) injected momenta N(0,1), or NULL: Philox */
+  const float* logu_dev;     /* (T,n) injected log-uniforms, or NULL: Philox         */
+  uint64_t seed;
+  int64_t row_offset;
+  float* out_samples_dev;    /* (n_mcmc,n,z_dim) or NULL                             */
+  double* accept_stat_dev;   /* (T) += sum over rows of exp(min(log_accept,0)), or NULL */
+  int* accept_count_dev;     /* (T) accepted chains per step, or NULL                */
+  uint8_t* accept_mask_dev;  /* (T,n) trace, or NULL                                 */
+  float* log_accept_dev;     /* (T,n) trace, or NULL                                 */
+} bgm_hmc_args;
+
+int bgm_hmc_run(const bgm_hmc* m, const bgm_hmc_args* args, void* stream);
+
+/* TFP SimpleStepSizeAdaptation after step t (adaptation_rate `rate`, float32):
+ * step *= (1+rate) if accept_stat[t]/n_total > target else step /= (1+rate).
+ * Multi-GPU: all-reduce accept_stat_dev[t] over the shards before this call. */
+int bgm_hmc_adapt(const double* accept_stat_dev, int t, long long n_total, float target, float rate,
+                  float* step_dev, void* stream);
+
+/* The Philox noise bgm_hmc_run draws: z0 (n,z_dim), momenta (t_end-t_begin,n,z_dim),
+ * log-uniforms (.,n); any pointer may be NULL.  Test hook (oracle replay). */
+int bgm_hmc_noise(uint64_t seed, int64_t row_offset, int n, int z_dim, int t_begin, int t_end,
+                  float* z0_dev, float* mom_dev, float* logu_dev, void* stream);
+
+/* BGM.predict_on_posteriors (bgm/base.py:511-525): x = mu(z) + sqrt(sigma^2(z)) * N(0,1)
+ * for z_samples_dev (n_keep, n, z_dim) -> out_x_dev (n_keep, n, x_dim).  The N(0,1)
+ * draws come from Philox keyed by (seed, row_offset+row, sample0+s, column) or from
+ * noise_dev (n_keep, n, x_dim) if non-NULL. */
+int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, int n, int sample0,
+                    uint64_t seed, int64_t row_offset, const float* noise_dev, float* out_x_dev,
+                    void* stream);
+
 /* Dependent-FFMA micro-benchmark: measured fp32 FMA peak of the device in TFLOP/s
  * (the roofline denominator for the SIMT kernels; MEASURED_PEAKS.json has none). */
 int bgm_fp32_peak_tflops(double* tflops, void* stream);

@@ -71,3 +71,55 @@ def philox4x32_10(c, k):
         k0 = (k0 + np.uint64(W0)) & mask
         k1 = (k1 + np.uint64(W1)) & mask
     return np.stack(c, axis=-1).astype(np.uint32)
+
+
+def philox_normal4(seed, rows, t, kind, j):
+    """NumPy restatement of csrc/common.cuh `normal4`: 4 unit normals per (row, t, kind, j)
+    from one Philox block via Box-Muller.  rows: int64 array -> (len(rows), 4) float32."""
+    rows = np.asarray(rows, np.int64)
+    c = np.stack([np.full(rows.shape, t & 0xFFFFFFFF, np.uint64), (rows & 0xFFFFFFFF).astype(np.uint64),
+                  ((rows >> 32) & 0xFFFFFFFF).astype(np.uint64),
+                  np.full(rows.shape, ((kind << 24) | j) & 0xFFFFFFFF, np.uint64)], axis=-1).astype(np.uint32)
+    r = philox4x32_10(c, np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], np.uint64))
+
+    def bm(a, b):
+        u0 = (a.astype(np.float64) * 2.3283064365386963e-10 + 1.1641532182693481e-10).astype(np.float32)
+        u1 = ((b >> np.uint32(8)).astype(np.float32) * np.float32(5.9604644775390625e-08))
+        rad = np.sqrt(np.float32(-2.0) * np.log(u0)).astype(np.float32)
+        ang = (2.0 * np.pi * u1.astype(np.float64))
+        return (rad * np.cos(ang)).astype(np.float32), (rad * np.sin(ang)).astype(np.float32)
+    n0, n1 = bm(r[..., 0], r[..., 1])
+    n2, n3 = bm(r[..., 2], r[..., 3])
+    return np.stack([n0, n1, n2, n3], axis=-1)
+
+
+def bgm_params(x_dim, z_dim, g_units=(64,) * 5, **extra):
+    p = dict(dataset='test', output_dir='/tmp/bgm_b200_test', save_res=False, save_model=False,
+             use_bnn=False, x_dim=x_dim, z_dim=z_dim, g_units=list(g_units), e_units=[64] * 5,
+             dz_units=[64, 32, 8], dx_units=[64, 32, 8], lr=1e-3, lr_theta=5e-3, lr_z=5e-3, gamma=0.0,
+             alpha=0.0, g_d_freq=1, kl_weight=5e-5)
+    p.update(extra)
+    return p
+
+
+def bgm_oracle_net(params, seed=21, bn_random=True):
+    rs = np.random.RandomState(seed)
+    return onets.init_variational(rs, params['z_dim'], params['x_dim'], list(params['g_units']),
+                                  bias_scale=0.1, bn_random=bn_random)
+
+
+def bgm_product_model(params, p):
+    from bayesgm_b200 import BGM
+    m = BGM(params=params, random_seed=None)
+    w = [p['bn']['gamma'], p['bn']['beta'], p['bn']['mean'], p['bn']['var']]
+    for W, b in p['hidden'] + [p['mean'], p['var']]:
+        w += [W, b]
+    m.set_weights(g=w)
+    return m
+
+
+def hmc_noise(n, zd, T, seed=9):
+    rs = np.random.RandomState(seed)
+    return dict(z0=rs.standard_normal((n, zd)).astype(np.float32),
+                momentum=rs.standard_normal((T, n, zd)).astype(np.float32),
+                log_u=np.log(rs.uniform(size=(T, n))).astype(np.float32))

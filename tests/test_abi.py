@@ -29,12 +29,22 @@ def test_mh_args_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.MhArgs) == 24 + 8 + 16 + 16 + 24 + 16 + 32
 
 
+def test_hmc_args_struct_layout_matches_header():
+    # x,ldx,n | z,g,lp | 5 ints (+4 pad) | step,mom,logu | seed,row_offset | 5 pointers
+    assert ctypes.sizeof(_lib.HmcArgs) == 16 + 24 + 24 + 24 + 16 + 40
+    assert _lib.HmcArgs.step_dev.offset == 64 and _lib.HmcArgs.seed.offset == 88
+
+
 def test_bad_arguments_fail_loudly_without_gpu():
     lib = _lib.load()
     h = ctypes.c_void_p()
     rc = lib.bgm_causal_create(ctypes.byref(h), None, 10, 0, -1.0, -1.0, -1.0, None, None, None)
     assert rc < 0 and b"null" in lib.bgm_last_error()
     assert lib.bgm_causal_logpost(None, None, None, None, 0, None, 0, None, None) < 0
+    assert lib.bgm_hmc_create(ctypes.byref(h), None) < 0 and b"null" in lib.bgm_last_error()
+    assert lib.bgm_hmc_run(None, None, None) < 0
+    d = _lib.VarNetDesc(40, 10, 1, None, None, None, None, None)
+    assert lib.bgm_hmc_create(ctypes.byref(h), ctypes.byref(d)) < 0
 
 
 def test_product_never_imports_oracle():
