@@ -20,6 +20,7 @@ import numpy as np
 from . import _lib
 from .datasets import Gaussian_sampler
 from .nets import DenseNet
+from .shard import merge_adrf, finish_adrf
 
 _DEFAULTS = dict(use_bnn=True, g_units=[64] * 5, e_units=[64] * 5, f_units=[64, 32, 8],
                  h_units=[64, 32, 8], dz_units=[64, 32, 8], lr=0.0002, lr_theta=0.0001,
@@ -352,17 +353,9 @@ class CausalBGM(object):
                 n_seen += n
         if binary:
             return ite_mean, np.stack([lower, upper], axis=1)
-        if group is not None:
-            import torch.distributed as dist
-            cnt = torch.tensor([float(n_seen)], dtype=torch.float64, device='cuda')
-            dist.all_reduce(sums, group=group)
-            dist.all_reduce(cnt, group=group)
-            n_seen = float(cnt.item())
-        ce = (sums / float(n_seen)).float().cpu().numpy()                         # :663-667
-        ADRF = np.mean(ce, axis=1)
-        up = np.quantile(ce, 1 - alpha / 2, axis=1)
-        lo = np.quantile(ce, alpha / 2, axis=1)
-        return ADRF, np.stack([lo, up], axis=1)
+        ce = merge_adrf(sums, n_seen, group) if group is not None else \
+            (sums / float(n_seen)).float().cpu().numpy()                          # :663
+        return finish_adrf(ce, alpha)                                             # :665-667
 
     def philox_noise(self, seed, n, T, row_offset=0):
         """The exact noise `metropolis_hastings_sampler(seed=...)` draws in-kernel, as
