@@ -29,6 +29,7 @@ class MhArgs(C.Structure):
     _fields_ = [
         ("x_dev", C.c_void_p), ("y_dev", C.c_void_p), ("v_dev", C.c_void_p),
         ("ldv", C.c_int), ("n", C.c_int),
+        ("vproj_dev", C.c_void_p), ("r0_dev", C.c_void_p), ("ldvproj", C.c_int), ("sched_dev", C.c_void_p),
         ("z_state_dev", C.c_void_p), ("lp_state_dev", C.c_void_p),
         ("init_mode", C.c_int), ("t_begin", C.c_int), ("t_end", C.c_int), ("burn_in", C.c_int),
         ("q_sd_dev", C.c_void_p), ("eps_dev", C.c_void_p), ("u_dev", C.c_void_p),
@@ -68,9 +69,12 @@ SYMBOLS = {
                                     C.POINTER(NetDesc), C.POINTER(NetDesc), C.POINTER(NetDesc)]),
     "bgm_causal_destroy": (None, [C.c_void_p]),
     "bgm_causal_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
-                                  C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+                                  C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "bgm_causal_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
     "bgm_causal_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
-                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+                                     C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]),
     "bgm_causal_mh": (C.c_int, [C.c_void_p, C.POINTER(MhArgs), C.c_void_p]),
     "bgm_mh_adapt_qsd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_double, C.c_double,
                                    C.c_void_p, C.c_void_p]),

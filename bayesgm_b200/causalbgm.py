@@ -119,12 +119,28 @@ class CausalBGM(object):
         return self._handle
 
     def kernel_info(self):
-        smem, warps, nops = C.c_int(), C.c_int(), C.c_int()
+        smem, warps, nops, proj = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         macs, issued = C.c_longlong(), C.c_longlong()
         _lib.call("bgm_causal_info", self._device_model(), C.byref(smem), C.byref(warps), C.byref(nops),
-                  C.byref(macs), C.byref(issued))
+                  C.byref(macs), C.byref(issued), C.byref(proj))
         return dict(smem_bytes=smem.value, warps_per_cta=warps.value, n_ops=nops.value,
-                    macs_per_row=macs.value, issued_macs_per_row=issued.value)
+                    macs_per_row=macs.value, issued_macs_per_row=issued.value, proj_dim=proj.value)
+
+    def _aux(self, v, ldv, n):
+        """Per-data-set device buffers: the projected covariates (models with proj_dim > 0,
+        see bgm_causal_project) and the scratch of the in-kernel work scheduler."""
+        torch = _lib.require_cuda()
+        sched = torch.empty((n + 31) // 32 + 1, dtype=torch.int32, device='cuda')
+        if not hasattr(self, '_proj_dim') or self._handle is None:
+            self._proj_dim = self.kernel_info()['proj_dim']
+        if not self._proj_dim:
+            return dict(vproj=None, r0=None, ldvproj=0, sched=sched)
+        ldp = (self._proj_dim + 3) // 4 * 4
+        vproj = torch.empty((n, ldp), dtype=torch.float32, device='cuda')
+        r0 = torch.empty(n, dtype=torch.float32, device='cuda')
+        _lib.call("bgm_causal_project", self._device_model(), _lib.ptr(v), ldv, n, _lib.ptr(vproj), ldp,
+                  _lib.ptr(r0), _lib.stream_ptr())
+        return dict(vproj=vproj, r0=r0, ldvproj=ldp, sched=sched)
 
     @staticmethod
     def _to_device(a, torch, cols=None):
@@ -169,15 +185,18 @@ class CausalBGM(object):
         if z.shape != (n, zd):
             raise ValueError("data_z must have shape (%d, %d)" % (n, zd))
         out = torch.empty(n, dtype=torch.float32, device='cuda')
+        aux = self._aux(v, ldv, n)
         _lib.call("bgm_causal_logpost", self._device_model(), _lib.ptr(x), _lib.ptr(y), _lib.ptr(v), ldv,
-                  _lib.ptr(z), n, _lib.ptr(out), _lib.stream_ptr())
+                  _lib.ptr(aux['vproj']), aux['ldvproj'], _lib.ptr(aux['r0']), _lib.ptr(z), n, _lib.ptr(out),
+                  _lib.ptr(aux['sched']), _lib.stream_ptr())
         return out.cpu().numpy()
 
     def _mh_device(self, x, y, v, ldv, n, burn_in, n_keep, q_sd, adaptive_sd, initial_q_sd,
                    target_acceptance_rate, tolerance, adjustment_interval, window_size,
-                   seed, row_offset, noise=None, trace=False, keep_samples=True):
+                   seed, row_offset, noise=None, trace=False, keep_samples=True, aux=None):
         """Runs the sampler on staged device buffers; returns a dict of device tensors."""
         torch = _lib.require_cuda()
+        aux = aux if aux is not None else self._aux(v, ldv, n)
         zd = sum(self._p['z_dims'])
         T = burn_in + n_keep
         m = self._device_model()
@@ -190,13 +209,16 @@ class CausalBGM(object):
         a = _lib.MhArgs()
         a.x_dev, a.y_dev, a.v_dev = x.data_ptr(), y.data_ptr(), v.data_ptr()
         a.ldv, a.n = ldv, n
+        if aux['vproj'] is not None:
+            a.vproj_dev, a.r0_dev, a.ldvproj = aux['vproj'].data_ptr(), aux['r0'].data_ptr(), aux['ldvproj']
+        a.sched_dev = aux['sched'].data_ptr()
         a.z_state_dev, a.lp_state_dev = z_state.data_ptr(), lp_state.data_ptr()
         a.burn_in = burn_in
         a.q_sd_dev = q.data_ptr()
         a.seed, a.row_offset = int(seed) & (2 ** 64 - 1), int(row_offset)
         a.out_samples_dev = samples.data_ptr() if keep_samples else None
         a.accept_count_dev = acc_count.data_ptr()
-        keep = []
+        keep = [aux]
         if noise is not None:
             z0 = self._to_device(noise['z0'], torch)
             eps = self._to_device(noise['eps'], torch)

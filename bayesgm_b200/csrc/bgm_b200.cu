@@ -79,6 +79,35 @@ struct Packer {
   }
 };
 
+// Thin QR of A (rows x cols, rows >= cols, row-major, float64) by modified Gram-Schmidt
+// with one re-orthogonalisation pass: A = Q R, Q rows x cols with orthonormal (or zero,
+// if A is rank deficient) columns, R cols x cols upper triangular.
+static void thin_qr(const std::vector<double>& A, int rows, int cols, std::vector<double>& Q,
+                    std::vector<double>& R) {
+  Q.assign((size_t)rows * cols, 0.0);
+  R.assign((size_t)cols * cols, 0.0);
+  std::vector<double> u(rows);
+  double scale = 0.0;
+  for (double a : A) scale = std::max(scale, std::fabs(a));
+  for (int j = 0; j < cols; ++j) {
+    for (int r = 0; r < rows; ++r) u[r] = A[(size_t)r * cols + j];
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < j; ++i) {
+        double d = 0.0;
+        for (int r = 0; r < rows; ++r) d += u[r] * Q[(size_t)r * cols + i];
+        R[(size_t)i * cols + j] += d;
+        for (int r = 0; r < rows; ++r) u[r] -= d * Q[(size_t)r * cols + i];
+      }
+    double nrm = 0.0;
+    for (int r = 0; r < rows; ++r) nrm += u[r] * u[r];
+    nrm = std::sqrt(nrm);
+    if (nrm > 1e-12 * std::max(scale, 1e-300) * std::sqrt((double)rows)) {
+      R[(size_t)j * cols + j] = nrm;
+      for (int r = 0; r < rows; ++r) Q[(size_t)r * cols + j] = u[r] / nrm;
+    }
+  }
+}
+
 struct HostNet {
   int L;
   std::vector<int> dims;
@@ -108,6 +137,8 @@ using namespace bgm;
 struct bgm_causal {
   CausalProgram prog;
   float* image_dev = nullptr;
+  float* proj_dev = nullptr;   // U [p][HP] | b [p] of the covariate projection (proj_dim > 0)
+  int proj_dim = 0, proj_hp = 0;
   int warps = 0;
   int smem_bytes = 0;
   int effect_warps = 0;
@@ -116,11 +147,21 @@ struct bgm_causal {
   long long macs = 0, issued = 0;
 };
 
-static int check_data(const char* fn, const float* x, const float* y, const float* v, int ldv, int n,
-                      int p) {
-  if (!x || !y || !v) return fail(BGM_ERR_ARG, std::string(fn) + ": null data pointer");
+static int check_data(const char* fn, const bgm_causal* m, const float* x, const float* y, const float* v,
+                      int ldv, const float* vproj, int ldvproj, const float* r0, const int* sched, int n) {
+  if (!x || !y) return fail(BGM_ERR_ARG, std::string(fn) + ": null data pointer");
   if (n < 1) return fail(BGM_ERR_ARG, std::string(fn) + ": n must be >= 1");
-  if (ldv < p || ldv % 4 != 0)
+  if (!sched) return fail(BGM_ERR_ARG, std::string(fn) + ": sched_dev is required");
+  if (m->proj_dim) {
+    if (!vproj || !r0)
+      return fail(BGM_ERR_ARG, std::string(fn) + ": this model projects the covariates: vproj_dev and r0_dev "
+                                                 "(bgm_causal_project) are required");
+    if (ldvproj < m->proj_dim || ldvproj % 4 != 0 || reinterpret_cast<uintptr_t>(vproj) % 16 != 0)
+      return fail(BGM_ERR_ARG, std::string(fn) + ": vproj_dev must be 16-byte aligned, ldvproj >= proj_dim, % 4 == 0");
+    return 0;
+  }
+  if (!v) return fail(BGM_ERR_ARG, std::string(fn) + ": null data pointer");
+  if (ldv < m->prog.p || ldv % 4 != 0)
     return fail(BGM_ERR_ARG, std::string(fn) + ": ldv must be >= v_dim and a multiple of 4");
   if (reinterpret_cast<uintptr_t>(v) % 16 != 0)
     return fail(BGM_ERR_ARG, std::string(fn) + ": v_dev must be 16-byte aligned");
@@ -135,10 +176,15 @@ static int launch_mh_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
-static int launch_mh(const bgm_causal* m, const MhDev& D, cudaStream_t st) {
+static int launch_mh(const bgm_causal* m, MhDev& D, cudaStream_t st) {
   const int ntiles = (D.a.n + TILE_ROWS - 1) / TILE_ROWS;
   const int grid = std::max(1, std::min((ntiles + m->warps - 1) / m->warps, m->sm_count));
   const int zd = m->prog.zd;
+  // iteration chunks of ~16 per work unit, fewer when there are many tiles per warp anyway
+  const bool need_init = !(D.a.init_mode == 0 && D.mode == 0);
+  const int n_iter = (D.mode == 1 ? 0 : D.a.t_end - D.a.t_begin) + (need_init ? 1 : 0);
+  D.nchunks = std::max(1, (n_iter + 15) / 16);
+  BGM_CUDA_OK(cudaMemsetAsync(D.a.sched_dev, 0, sizeof(int) * (size_t)(ntiles + 1), st));
   if (zd <= 8) return launch_mh_t<8>(m, D, grid, st);
   if (zd <= 16) return launch_mh_t<16>(m, D, grid, st);
   return launch_mh_t<32>(m, D, grid, st);
@@ -188,6 +234,8 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   CausalProgram P;
   memset(&P, 0, sizeof(P));
 
+  int proj_dim = 0, proj_hp = 0;
+  std::vector<float> proj_host;
   // maps each net's first-layer input rows onto rows of the shared input buffer
   // zin = [z (zd rows), x (row zd), zero pad]
   auto remap_first = [&](const HostNet& net, const std::vector<int>& rows) {
@@ -210,7 +258,28 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
       if (!last) {
         if (pk.add_hidden(Wm, net.b[l], krows, N, src)) return -1;
       } else if (kind == 0) {
-        pk.add_final(Wm, net.b[l], krows, N, 0, v_dim, src, EPI_SSE, 0);
+        const int H = K;
+        if (l > 0 && v_dim > H + 8) {
+          // covariate likelihood through the row space of this layer (bgm_causal_project):
+          // M^T = U R; the SSE tiles see R^T (H x H, zero bias) and the projected data.
+          std::vector<double> A((size_t)v_dim * H), Q, R;
+          for (int k = 0; k < H; ++k)
+            for (int c = 0; c < v_dim; ++c) A[(size_t)c * H + k] = Wm[(size_t)k * N + c];
+          thin_qr(A, v_dim, H, Q, R);
+          std::vector<float> RT((size_t)H * H), zb(H, 0.f);
+          for (int j = 0; j < H; ++j)
+            for (int i = 0; i < H; ++i) RT[(size_t)j * H + i] = (float)R[(size_t)i * H + j];
+          pk.add_final(RT, zb, H, H, 0, H, src, EPI_SSE, 0);
+          proj_dim = H;
+          proj_hp = H > 32 ? 64 : 32;
+          proj_host.assign((size_t)v_dim * proj_hp + v_dim, 0.f);
+          for (int c = 0; c < v_dim; ++c) {
+            for (int i = 0; i < H; ++i) proj_host[(size_t)c * proj_hp + i] = (float)Q[(size_t)c * H + i];
+            proj_host[(size_t)v_dim * proj_hp + c] = net.b[l][c];
+          }
+        } else {
+          pk.add_final(Wm, net.b[l], krows, N, 0, v_dim, src, EPI_SSE, 0);
+        }
         if (sigma_v < 0.f) pk.add_final(Wm, net.b[l], krows, N, v_dim, 1, src, EPI_OUT, 1);
       } else {
         pk.add_final(Wm, net.b[l], krows, N, 0, 2, src, EPI_OUT, 0);
@@ -242,6 +311,8 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   P.zd = zd;
   P.kin = kin;
   P.p = v_dim;
+  P.p_data = proj_dim ? proj_dim : v_dim;
+  P.proj = proj_dim ? 1 : 0;
   P.binary = binary_treatment ? 1 : 0;
   P.s2v = sigma_v >= 0.f ? sigma_v * sigma_v : -1.f;
   P.s2x = sigma_x >= 0.f ? sigma_x * sigma_x : -1.f;
@@ -274,10 +345,18 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   m->prog = P;
   m->macs = pk.macs;
   m->issued = pk.issued;
+  m->proj_dim = proj_dim;
+  m->proj_hp = proj_hp;
   cudaError_t e = cudaMalloc(&m->image_dev, pk.image.size() * sizeof(float));
   if (e == cudaSuccess)
     e = cudaMemcpy(m->image_dev, pk.image.data(), pk.image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && proj_dim) {
+    e = cudaMalloc(&m->proj_dev, proj_host.size() * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->proj_dev, proj_host.data(), proj_host.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
+    if (m->proj_dev) cudaFree(m->proj_dev);
     if (m->image_dev) cudaFree(m->image_dev);
     delete m;
     return fail(BGM_ERR_CUDA, std::string("uploading weight image: ") + cudaGetErrorString(e));
@@ -289,30 +368,52 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
 void bgm_causal_destroy(bgm_causal* m) {
   if (!m) return;
   if (m->image_dev) cudaFree(m->image_dev);
+  if (m->proj_dev) cudaFree(m->proj_dev);
   delete m;
 }
 
 int bgm_causal_info(const bgm_causal* m, int* smem_bytes, int* warps_per_cta, int* n_ops,
-                    long long* macs_per_row, long long* issued_macs_per_row) {
+                    long long* macs_per_row, long long* issued_macs_per_row, int* proj_dim) {
   if (!m) return fail(BGM_ERR_ARG, "null model");
   if (smem_bytes) *smem_bytes = m->smem_bytes;
   if (warps_per_cta) *warps_per_cta = m->warps;
   if (n_ops) *n_ops = m->prog.n_ops;
   if (macs_per_row) *macs_per_row = m->macs;
   if (issued_macs_per_row) *issued_macs_per_row = m->issued;
+  if (proj_dim) *proj_dim = m->proj_dim;
+  return 0;
+}
+
+int bgm_causal_project(const bgm_causal* m, const float* v_dev, int ldv, int n, float* vproj_dev,
+                       int ldvproj, float* r0_dev, void* stream) {
+  if (!m) return fail(BGM_ERR_ARG, "bgm_causal_project: null model");
+  if (!m->proj_dim) return fail(BGM_ERR_ARG, "bgm_causal_project: this model does not project (proj_dim == 0)");
+  if (!v_dev || !vproj_dev || !r0_dev) return fail(BGM_ERR_ARG, "bgm_causal_project: null pointer");
+  if (n < 1 || ldv < m->prog.p) return fail(BGM_ERR_ARG, "bgm_causal_project: bad n / ldv");
+  if (ldvproj < m->proj_dim || ldvproj % 4 != 0)
+    return fail(BGM_ERR_ARG, "bgm_causal_project: ldvproj must be >= proj_dim and a multiple of 4");
+  const int p = m->prog.p, HP = m->proj_hp;
+  const int smem = (p * HP + p) * 4;
+  BGM_CUDA_OK(cudaFuncSetAttribute(causal_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const int grid = std::max(1, std::min((n + 7) / 8, m->sm_count * 2));
+  causal_project_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(v_dev, ldv, n, p, HP, m->proj_dev, vproj_dev,
+                                                                   ldvproj, r0_dev);
+  BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_dev,
-                       const float* v_dev, int ldv, const float* z_dev, int n, float* out_logp_dev,
-                       void* stream) {
+                       const float* v_dev, int ldv, const float* vproj_dev, int ldvproj,
+                       const float* r0_dev, const float* z_dev, int n, float* out_logp_dev,
+                       int* sched_dev, void* stream) {
   if (!m) return fail(BGM_ERR_ARG, "bgm_causal_logpost: null model");
-  int rc = check_data("bgm_causal_logpost", x_dev, y_dev, v_dev, ldv, n, m->prog.p);
+  int rc = check_data("bgm_causal_logpost", m, x_dev, y_dev, v_dev, ldv, vproj_dev, ldvproj, r0_dev, sched_dev, n);
   if (rc) return rc;
   if (!z_dev || !out_logp_dev) return fail(BGM_ERR_ARG, "bgm_causal_logpost: null z / out pointer");
   MhDev D;
   memset(&D, 0, sizeof(D));
   D.a.x_dev = x_dev; D.a.y_dev = y_dev; D.a.v_dev = v_dev; D.a.ldv = ldv; D.a.n = n;
+  D.a.vproj_dev = vproj_dev; D.a.ldvproj = ldvproj; D.a.r0_dev = r0_dev; D.a.sched_dev = sched_dev;
   D.a.z_state_dev = const_cast<float*>(z_dev);
   D.a.lp_state_dev = out_logp_dev;
   D.a.init_mode = 1;
@@ -322,7 +423,8 @@ int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_d
 
 int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* a, void* stream) {
   if (!m || !a) return fail(BGM_ERR_ARG, "bgm_causal_mh: null model / args");
-  int rc = check_data("bgm_causal_mh", a->x_dev, a->y_dev, a->v_dev, a->ldv, a->n, m->prog.p);
+  int rc = check_data("bgm_causal_mh", m, a->x_dev, a->y_dev, a->v_dev, a->ldv, a->vproj_dev, a->ldvproj,
+                      a->r0_dev, a->sched_dev, a->n);
   if (rc) return rc;
   if (!a->z_state_dev || !a->lp_state_dev)
     return fail(BGM_ERR_ARG, "bgm_causal_mh: z_state_dev and lp_state_dev are required");

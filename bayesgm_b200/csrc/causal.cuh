@@ -26,6 +26,8 @@ struct CausalProgram {
   int g_end, f_end, h_end;     // op ranges: g [0,g_end) f [g_end,f_end) h [f_end,h_end)
   int f_img_begin, f_img_end;  // float range of the f-net tiles in the image
   int zd, kin, p, binary;
+  int p_data;                  // columns of the data the SSE tiles read: p, or the projected width
+  int proj;                    // 1: covariate likelihood through the QR projection (see bgm_b200.cu)
   float s2v, s2x, s2y;         // fixed variances, < 0 = learned head
   int image_floats;            // padded by IMG_PAD
   int per_warp_floats;
@@ -142,7 +144,7 @@ __device__ __forceinline__ void run_one(const TileOp& op, const float* __restric
 __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const float* __restrict__ wimg,
                                               const WarpSmem& S, const float* __restrict__ v,
                                               int ldv, int row0, int n, int lane, float x_l,
-                                              float y_l) {
+                                              float y_l, float r0_l) {
   const int rg = lane >> 3, cg = lane & 7;
   float sse[RPT];
 #pragma unroll
@@ -152,7 +154,7 @@ __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const floa
 #pragma unroll 1
   for (int o = 0; o < P.n_ops; ++o) {
     const TileOp& op = P.ops[o];
-    run_one(op, wimg, S, v, ldv, P.p, row0, n, rg, cg, sse);
+    run_one(op, wimg, S, v, ldv, P.p_data, row0, n, rg, cg, sse);
     if (op.post == POST_NONE) continue;
     if (op.post == POST_G) {  // sum_j (v_j - mu_j)^2 and the sigma_v head
 #pragma unroll
@@ -164,7 +166,7 @@ __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const floa
         if (cg == 0) S.scr[row_of(rg, i)] = s;
       }
       __syncwarp();
-      const float sse_l = S.scr[lane];
+      const float sse_l = S.scr[lane] + r0_l;   // r0: part of v outside the last layer's row space
       const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
       loss = sse_l / (2.f * s2v) + ((float)P.p * logf(s2v)) / 2.f;                 // :800-801
     } else if (op.post == POST_F) {  // outcome model
@@ -199,7 +201,8 @@ __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const floa
 
 struct MhDev {
   bgm_mh_args a;
-  int mode;  // 0: MH, 1: log-posterior of z_state only (out -> lp_state)
+  int mode;     // 0: MH, 1: log-posterior of z_state only (out -> lp_state)
+  int nchunks;  // iteration chunks per tile (dynamic scheduling granularity)
 };
 
 // ZMAX: compile-time bound on zd; the chain state z_cur[ZMAX] of the lane's row is
@@ -225,19 +228,47 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
   const int t_first = need_init ? A.t_begin - 1 : A.t_begin;
   const int t_last = D.mode == 1 ? A.t_begin : A.t_end;
 
-  for (int tile = blockIdx.x * warps + warp; tile < ntiles; tile += gridDim.x * warps) {
+  // Work units are (32-row tile, chunk of iterations), handed out by a global counter in
+  // chunk-major order; chunk c of a tile waits for chunk c-1 of the same tile (progress
+  // flag).  All CTAs are co-resident (grid <= #SMs) and units are claimed in increasing
+  // order, so the unit a warp waits for is always owned by a running warp.
+  const float* vdat = P.proj ? A.vproj_dev : A.v_dev;
+  const int ldd = P.proj ? A.ldvproj : A.ldv;
+  int* sched = A.sched_dev;
+  const int n_iter = t_last - t_first;
+  const int nchunks = D.nchunks;
+  const int chunk_len = (n_iter + nchunks - 1) / nchunks;
+  const long long total_units = (long long)ntiles * nchunks;
+  for (;;) {
+    long long u = 0;
+    if (lane == 0) u = atomicAdd(reinterpret_cast<unsigned int*>(sched), 1u);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= total_units) break;
+    const int chunk = (int)(u / ntiles);
+    const int tile = (int)(u - (long long)chunk * ntiles);
+    const int ta = t_first + chunk * chunk_len;
+    const int tb = min(ta + chunk_len, t_last);
+    if (chunk > 0) {
+      if (lane == 0) {
+        const volatile int* flag = sched + 1 + tile;
+        while (*flag < chunk) __nanosleep(200);
+        __threadfence();
+      }
+      __syncwarp();
+    }
     const int row0 = tile * TILE_ROWS;
     const int row = row0 + lane;
     const bool valid = row < n;
     const int lrow = valid ? row : n - 1;
     const int nvalid_rows = min(TILE_ROWS, n - row0);
     const float x_l = A.x_dev[lrow], y_l = A.y_dev[lrow];
+    const float r0_l = P.proj ? A.r0_dev[lrow] : 0.f;
     const int64_t grow = A.row_offset + lrow;
     float zc[ZMAX];
     // input buffer: rows [0,zd) proposal, row zd = x, remaining pad rows zero
     for (int k = zd; k < P.kin; ++k) S.zin[act_idx(k, lane)] = (k == zd) ? x_l : 0.f;
     // ---- initial state (:842) ----
-    if (A.init_mode == 2) {
+    if (chunk == 0 && A.init_mode == 2) {
 #pragma unroll
       for (int g = 0; g < ZMAX / 4; ++g) {
         if (g * 4 < zd) {
@@ -250,12 +281,12 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
     } else {
 #pragma unroll
       for (int d = 0; d < ZMAX; ++d)
-        if (d < zd) zc[d] = A.z_state_dev[(size_t)lrow * zd + d];
+        if (d < zd) zc[d] = __ldcg(A.z_state_dev + (size_t)lrow * zd + d);
     }
-    float lp_cur = need_init ? 0.f : A.lp_state_dev[lrow];
+    float lp_cur = (need_init && chunk == 0) ? 0.f : __ldcg(A.lp_state_dev + lrow);
     // ---- iterations (:860-898) ----
 #pragma unroll 1
-    for (int t = t_first; t < t_last; ++t) {
+    for (int t = ta; t < tb; ++t) {
       const bool init_pass = t < A.t_begin;
       if (init_pass) {
 #pragma unroll
@@ -282,7 +313,7 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
         }
       }
       __syncwarp();
-      const float lp_prop = eval_logpost(P, wimg, S, A.v_dev, A.ldv, row0, n, lane, x_l, y_l);
+      const float lp_prop = eval_logpost(P, wimg, S, vdat, ldd, row0, n, lane, x_l, y_l, r0_l);
       if (init_pass) {
         lp_cur = lp_prop;
         continue;
@@ -320,7 +351,7 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
       }
       __syncwarp();
     }
-    // ---- save state ----
+    // ---- save state, publish the chunk ----
     if (valid) {
       if (D.mode == 0) {
 #pragma unroll
@@ -329,7 +360,9 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
       }
       A.lp_state_dev[row] = lp_cur;
     }
+    __threadfence();
     __syncwarp();
+    if (lane == 0) *reinterpret_cast<volatile int*>(sched + 1 + tile) = chunk + 1;
   }
 }
 
@@ -424,6 +457,48 @@ __global__ void mh_adapt_qsd_kernel(const int* __restrict__ accept_count, int t,
   if (rate < target - tol) q *= 0.9;
   else if (rate > target + tol) q *= 1.1;
   *q_sd = q;
+}
+
+// Projection of the covariates onto the row space of g_net's last layer (see
+// bgm_b200.cu): t = (v - b) U  (n x H) and r0 = |v - b|^2 - |t|^2.  One warp per row,
+// U (p x HP) and b in shared memory.
+__global__ void __launch_bounds__(256)
+causal_project_kernel(const float* __restrict__ v, int ldv, int n, int p, int HP,
+                      const float* __restrict__ Ub, float* __restrict__ t, int ldt,
+                      float* __restrict__ r0) {
+  extern __shared__ __align__(16) float psm[];
+  float* U = psm;            // [p][HP]
+  float* b = psm + p * HP;   // [p]
+  for (int i = threadIdx.x; i < p * HP + p; i += blockDim.x) psm[i] = Ub[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  for (int row = blockIdx.x * warps + warp; row < n; row += gridDim.x * warps) {
+    const float* vr = v + (size_t)row * ldv;
+    float t0 = 0.f, t1 = 0.f;
+    double nv = 0.0;
+    for (int k0 = 0; k0 < p; k0 += 32) {
+      const int kk = k0 + lane;
+      const float mine = kk < p ? vr[kk] - b[kk] : 0.f;
+      nv += (double)mine * (double)mine;
+      const int lim = min(32, p - k0);
+      for (int j = 0; j < lim; ++j) {
+        const float vk = __shfl_sync(0xffffffffu, mine, j);
+        const float* u = U + (k0 + j) * HP;
+        t0 = fmaf(vk, u[lane], t0);
+        if (HP > 32) t1 = fmaf(vk, u[32 + lane], t1);
+      }
+    }
+    double nt = (double)t0 * (double)t0 + (double)t1 * (double)t1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      nv += __shfl_xor_sync(0xffffffffu, nv, o);
+      nt += __shfl_xor_sync(0xffffffffu, nt, o);
+    }
+    float* tr = t + (size_t)row * ldt;
+    if (lane < HP) tr[lane] = t0;
+    if (32 + lane < HP) tr[32 + lane] = t1;
+    if (lane == 0) r0[row] = (float)fmax(nv - nt, 0.0);
+  }
 }
 
 __global__ void mh_noise_kernel(uint64_t seed, int64_t row_offset, int n, int zd, int t_begin,

@@ -244,6 +244,7 @@ def run_ours(args):
         fp32_peak = tf.value
         flop_per_launch = 2.0 * info['macs_per_row'] * n * (T + 1)
         achieved_tflops = flop_per_launch / (kern_ms_mean * 1e-3) / 1e12
+        issued_tflops = 2.0 * info['issued_macs_per_row'] * n * (T + 1) / (kern_ms_mean * 1e-3) / 1e12
         bytes_per_launch = 4.0 * n * (V_DIM + 2) + 4.0 * N_MCMC * n * sum(Z_DIMS) + 8.0 * n * (sum(Z_DIMS) + 1)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -269,8 +270,12 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tflops / fp32_peak, "traffic": traffic,
                          "peak_source": "bgm_fp32_peak_tflops (dependent-FFMA micro-benchmark, measured live)",
-                         "note": "compute-bound SIMT kernel: 2*%d FLOP per row-iteration, weights resident in smem"
-                                 % info['macs_per_row']},
+                         "issued": issued_tflops, "issued_frac": issued_tflops / fp32_peak,
+                         "note": "compute-bound SIMT kernel. achieved = ALGORITHMIC 2*%d FLOP per row-iteration "
+                                 "(the reference's log-posterior, evaluated once per iteration); the kernel ISSUES "
+                                 "2*%d: the v_dim-wide last layer of g_net is evaluated in its %d-dim row space "
+                                 "(exact QR identity, DESIGN.md 4.1)"
+                                 % (info['macs_per_row'], info['issued_macs_per_row'], info['proj_dim'])},
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9 / peaks["hbm_gbs"],

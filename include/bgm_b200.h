@@ -61,16 +61,33 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
                       const bgm_net_desc* h_net);
 void bgm_causal_destroy(bgm_causal* m);
 /* Packed-model facts: shared-memory bytes per CTA, warps per CTA, tile ops per
- * log-posterior evaluation, algorithmic FMAs per row per evaluation (unpadded). */
+ * log-posterior evaluation, algorithmic FMAs per row per evaluation (the reference's
+ * formula, unpadded), FMAs the kernel issues per row per evaluation, and proj_dim:
+ * 0, or the width H of the projected covariates (see bgm_causal_project). */
 int bgm_causal_info(const bgm_causal* m, int* smem_bytes, int* warps_per_cta, int* n_ops,
-                    long long* macs_per_row, long long* issued_macs_per_row);
+                    long long* macs_per_row, long long* issued_macs_per_row, int* proj_dim);
+
+/* Covariate projection.  With mu_v = h M + b (M: H x v_dim, the last layer of g_net,
+ * H <= 64 < v_dim) and M^T = U R (thin QR, computed at create time in float64),
+ *   sum_j (v_j - mu_v,j)^2 = | (v-b) U - h R^T |^2 + ( |v-b|^2 - |(v-b) U|^2 ),
+ * an exact identity: the likelihood term of causalbgm/base.py:800 only sees h through
+ * the H-dimensional row space of M.  The data-dependent parts t = (v-b) U (n,H) and
+ * r0 = |v-b|^2 - |t|^2 (n) do not depend on z, so they are computed ONCE per data set
+ * by this call and every log-posterior evaluation then costs H*H instead of H*v_dim
+ * FMAs for that layer.  Models with proj_dim == 0 (v_dim <= H + 8) do not use it.
+ * vproj_dev: (n, ldvproj), ldvproj >= proj_dim, ldvproj % 4 == 0; r0_dev: (n). */
+int bgm_causal_project(const bgm_causal* m, const float* v_dev, int ldv, int n, float* vproj_dev,
+                       int ldvproj, float* r0_dev, void* stream);
 
 /* CausalBGM.get_log_posterior (causalbgm/base.py:765-817).
  * x_dev,y_dev: (n) ; v_dev: (n, ldv) with ldv >= v_dim, ldv % 4 == 0, 16-byte
- * aligned base; z_dev: (n, sum z_dims); out_logp_dev: (n). */
+ * aligned base; z_dev: (n, sum z_dims); out_logp_dev: (n).  Models with proj_dim > 0
+ * read vproj_dev / r0_dev (from bgm_causal_project) instead of v_dev, which may then
+ * be NULL.  sched_dev: see bgm_mh_args. */
 int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_dev,
-                       const float* v_dev, int ldv, const float* z_dev, int n,
-                       float* out_logp_dev, void* stream);
+                       const float* v_dev, int ldv, const float* vproj_dev, int ldvproj,
+                       const float* r0_dev, const float* z_dev, int n, float* out_logp_dev,
+                       int* sched_dev, void* stream);
 
 /* CausalBGM.metropolis_hastings_sampler (causalbgm/base.py:820-904): iterations
  * [t_begin, t_end) of n independent random-walk MH chains in ONE persistent launch.
@@ -80,9 +97,14 @@ int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_d
 typedef struct {
   const float* x_dev;       /* (n)    treatment                                   */
   const float* y_dev;       /* (n)    outcome                                     */
-  const float* v_dev;       /* (n,ldv) covariates                                 */
+  const float* v_dev;       /* (n,ldv) covariates (unused if the model projects)  */
   int ldv;
   int n;
+  const float* vproj_dev;   /* (n,ldvproj) projected covariates, bgm_causal_project */
+  const float* r0_dev;      /* (n)                                                */
+  int ldvproj;
+  int* sched_dev;           /* 4*(ceil(n/32)+1) bytes of scratch for the in-kernel
+                               work scheduler; zeroed by the call                 */
   float* z_state_dev;       /* (n,zd) current state: in (init_mode 0/1) and out   */
   float* lp_state_dev;      /* (n)    cached log-posterior of the current state   */
   int init_mode;            /* 0: continue (lp_state valid); 1: z_state given,

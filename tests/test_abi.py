@@ -25,8 +25,10 @@ def test_library_loads_and_exports_header_symbols():
 
 
 def test_mh_args_struct_layout_matches_header():
-    # pointers 8 bytes, ints 4, natural alignment: 3*8 + 2*4 + 2*8 + 4*4 + 3*8 + 2*8 + 4*8
-    assert ctypes.sizeof(_lib.MhArgs) == 24 + 8 + 16 + 16 + 24 + 16 + 32
+    # pointers 8 bytes, ints 4, natural alignment:
+    # x,y,v | ldv,n | vproj,r0 | ldvproj(+pad) | sched | z,lp | 4 ints | q_sd,eps,u | seed,row_offset | 4 ptrs
+    assert ctypes.sizeof(_lib.MhArgs) == 24 + 8 + 16 + 8 + 8 + 16 + 16 + 24 + 16 + 32
+    assert _lib.MhArgs.sched_dev.offset == 56 and _lib.MhArgs.q_sd_dev.offset == 96
 
 
 def test_hmc_args_struct_layout_matches_header():
@@ -40,7 +42,7 @@ def test_bad_arguments_fail_loudly_without_gpu():
     h = ctypes.c_void_p()
     rc = lib.bgm_causal_create(ctypes.byref(h), None, 10, 0, -1.0, -1.0, -1.0, None, None, None)
     assert rc < 0 and b"null" in lib.bgm_last_error()
-    assert lib.bgm_causal_logpost(None, None, None, None, 0, None, 0, None, None) < 0
+    assert lib.bgm_causal_logpost(None, None, None, None, 0, None, 0, None, None, 0, None, None, None) < 0
     assert lib.bgm_hmc_create(ctypes.byref(h), None) < 0 and b"null" in lib.bgm_last_error()
     assert lib.bgm_hmc_run(None, None, None) < 0
     d = _lib.VarNetDesc(40, 10, 1, None, None, None, None, None)
