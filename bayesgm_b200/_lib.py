@@ -46,6 +46,10 @@ class VarNetDesc(C.Structure):
                 ("var_params", C.POINTER(C.c_float))]
 
 
+class DiscDesc(C.Structure):
+    _fields_ = [("n_hidden", C.c_int), ("dims", C.POINTER(C.c_int)), ("params", C.POINTER(C.c_float))]
+
+
 class HmcArgs(C.Structure):
     _fields_ = [
         ("x_dev", C.c_void_p), ("ldx", C.c_int), ("n", C.c_int),
@@ -84,6 +88,20 @@ SYMBOLS = {
                                     C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     "bgm_fp32_peak_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
+    "bgm_trainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(NetDesc), C.POINTER(NetDesc), C.POINTER(NetDesc),
+                                     C.POINTER(NetDesc), C.POINTER(DiscDesc), C.c_float, C.c_float, C.c_float]),
+    "bgm_trainer_destroy": (None, [C.c_void_p]),
+    "bgm_trainer_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p),
+                                      C.POINTER(C.c_void_p)]),
+    "bgm_trainer_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bgm_trainer_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bgm_train_disc_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                      C.c_void_p, C.c_void_p]),
+    "bgm_train_gen_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_void_p, C.c_void_p]),
+    "bgm_train_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "bgm_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_hmc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VarNetDesc)]),
     "bgm_hmc_destroy": (None, [C.c_void_p]),
     "bgm_hmc_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong),

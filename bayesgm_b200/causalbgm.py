@@ -19,7 +19,7 @@ import numpy as np
 
 from . import _lib
 from .datasets import Gaussian_sampler
-from .nets import DenseNet
+from .nets import DenseNet, DiscNet
 from .shard import merge_adrf, finish_adrf
 
 _DEFAULTS = dict(use_bnn=True, g_units=[64] * 5, e_units=[64] * 5, f_units=[64, 32, 8],
@@ -61,7 +61,11 @@ class CausalBGM(object):
         self.e_net = DenseNet(p['v_dim'], zd, 'e_net', p['e_units'], rng)              # :76
         self.f_net = DenseNet(z0 + z1 + 1, 2, 'f_net', p['f_units'], rng)              # :78
         self.h_net = DenseNet(z0 + z2, 2, 'h_net', p['h_units'], rng)                  # :80
+        self.dz_net = DiscNet(zd, 'dz_net', p['dz_units'], rng)                        # :83
         self.z_sampler = Gaussian_sampler(mean=np.zeros(zd), sd=1.0)                  # :88 (reseeds to 1024)
+        self._trainer = None
+        self._trainer_dirty = False      # device parameters newer than the host arrays
+        self._eps_rng = np.random.RandomState(0 if random_seed is None else random_seed)
         if self.timestamp is None:
             self.timestamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
         self.checkpoint_path = "{}/checkpoints/{}/{}".format(p['output_dir'], p['dataset'], self.timestamp)
@@ -83,13 +87,58 @@ class CausalBGM(object):
             for net in (self.g_net, self.f_net, self.h_net):
                 print(net.model_name, net.dims)
 
-    def set_weights(self, g=None, e=None, f=None, h=None):
-        """Load Keras-layout weights ([kernel, bias, ...] per net), e.g. exported from a
-        trained reference model with `net.get_weights()`."""
+    def set_weights(self, g=None, e=None, f=None, h=None, dz=None):
+        """Load Keras-layout weights ([kernel, bias, ...] per net; dz: the Discriminator's
+        trainable_variables), e.g. exported from a trained reference model."""
+        self._sync_from_trainer()
         for net, w in ((self.g_net, g), (self.e_net, e), (self.f_net, f), (self.h_net, h)):
             if w is not None:
                 net.set_weights(w)
+        if dz is not None:
+            self.dz_net.set_trainable(dz)
         self._drop_handle()
+        self._drop_trainer()
+
+    def _drop_trainer(self):
+        if self._trainer is not None:
+            _lib.load().bgm_trainer_destroy(self._trainer)
+            self._trainer = None
+            self._trainer_dirty = False
+
+    def _sync_from_trainer(self):
+        """Pull the trained parameters back into the host arrays (and invalidate the packed
+        sampler model) -- done lazily, when something reads the weights."""
+        if self._trainer is None or not self._trainer_dirty:
+            return
+        n = C.c_int()
+        for group in (0, 1):
+            _lib.call("bgm_trainer_buffers", self._trainer, group, C.byref(n), None, None)
+            flat = np.empty(n.value, np.float32)
+            _lib.call("bgm_trainer_get_params", self._trainer, group, flat.ctypes.data_as(C.c_void_p))
+            if group == 0:
+                o = 0
+                for net in (self.g_net, self.e_net, self.f_net, self.h_net):
+                    k = net.flat_params().size
+                    net.load_flat(flat[o:o + k])
+                    o += k
+            else:
+                self.dz_net.load_flat(flat)
+        self._trainer_dirty = False
+        self._drop_handle()
+
+    def _device_trainer(self):
+        if self._trainer is None:
+            _lib.require_cuda()
+            p = self._p
+            zd4 = (C.c_int * 4)(*[int(d) for d in p['z_dims']])
+            descs = [net.desc() for net in (self.g_net, self.e_net, self.f_net, self.h_net)]
+            dd, dk = self.dz_net.desc()
+            h = C.c_void_p()
+            _lib.call("bgm_trainer_create", C.byref(h), zd4, int(p['v_dim']), int(bool(p['binary_treatment'])),
+                      int(bool(p['use_z_rec'])), C.byref(descs[0][0]), C.byref(descs[1][0]),
+                      C.byref(descs[2][0]), C.byref(descs[3][0]), C.byref(dd), float(p['lr']), 0.9, 0.99)
+            self._trainer = h
+        return self._trainer
 
     def _drop_handle(self):
         if self._handle is not None:
@@ -99,11 +148,13 @@ class CausalBGM(object):
     def __del__(self):
         try:
             self._drop_handle()
+            self._drop_trainer()
         except Exception:
             pass
 
     def _device_model(self):
         """Packs g/f/h for the kernels (once per weight change)."""
+        self._sync_from_trainer()
         if self._handle is None:
             _lib.require_cuda()
             p = self._p
@@ -399,6 +450,144 @@ class CausalBGM(object):
             "bayesgm_b200: the training path (egm_init / iterative updates, causalbgm/base.py:156-532) "
             "has no sm_100a kernels yet; load trained weights with set_weights().")
 
-    def egm_init(self, data, egm_n_iter=30000, batch_size=32, egm_batches_per_eval=500, verbose=1):
-        raise NotImplementedError(
-            "bayesgm_b200: EGM initialisation (causalbgm/base.py:305-431) has no sm_100a kernels yet.")
+    # ------------------------------------------------------------ EGM training
+    def _grad_tensor(self, group):
+        """torch view (no copy) of the trainer's flat gradient buffer, for all-reduce."""
+        torch = _lib.require_cuda()
+        n, ptr = C.c_int(), C.c_void_p()
+        _lib.call("bgm_trainer_buffers", self._device_trainer(), group, C.byref(n), None, C.byref(ptr))
+
+        class _View(object):
+            __cuda_array_interface__ = dict(shape=(n.value,), typestr='<f4', data=(ptr.value, False), version=2)
+        return torch.as_tensor(_View(), device='cuda')
+
+    def _apply(self, group_id, dist_group):
+        scale = 1.0
+        if dist_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._grad_tensor(group_id), group=dist_group)
+            scale = 1.0 / dist.get_world_size(dist_group)
+        _lib.call("bgm_train_adam", self._device_trainer(), group_id, float(scale), _lib.stream_ptr())
+        self._trainer_dirty = True
+
+    def gradients(self, which, data_z, data_v, data_x=None, data_y=None, epsilon=0.5):
+        """(losses, flat gradient) of one step WITHOUT the optimizer update; `which` is
+        'disc' (dz_net, Keras trainable_variables order) or 'gen' (g|e|f|h).  Test hook."""
+        torch = _lib.require_cuda()
+        z = self._to_device(data_z, torch)
+        v = self._to_device(data_v, torch)
+        if which == 'disc':
+            losses = torch.empty(2, dtype=torch.float32, device='cuda')
+            _lib.call("bgm_train_disc_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), z.shape[0],
+                      float(epsilon), 10.0, _lib.ptr(losses), _lib.stream_ptr())
+            return losses.cpu().numpy(), self._grad_tensor(1).cpu().numpy()
+        x = self._to_device(data_x, torch).reshape(-1)
+        y = self._to_device(data_y, torch).reshape(-1)
+        losses = torch.empty(6, dtype=torch.float32, device='cuda')
+        _lib.call("bgm_train_gen_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), _lib.ptr(x), _lib.ptr(y),
+                  z.shape[0], _lib.ptr(losses), _lib.stream_ptr())
+        return losses.cpu().numpy(), self._grad_tensor(0).cpu().numpy()
+
+    def get_weights(self):
+        """dict of Keras-layout weight lists of g, e, f, h and dz (trainable_variables order)."""
+        self._sync_from_trainer()
+        return dict(g=self.g_net.get_weights(), e=self.e_net.get_weights(), f=self.f_net.get_weights(),
+                    h=self.h_net.get_weights(), dz=[a.copy() for a in self.dz_net.trainable_list()])
+
+    def train_disc_step(self, data_z, data_v, *, epsilon=None, group=None):
+        """causalbgm/base.py:305-330 -> (dz_loss, d_loss).  `epsilon` is the U(0,1) draw of
+        :307 (TensorFlow's stream in the reference; here a private RandomState unless given).
+        Under torch.distributed pass `group`: gradients are averaged over the ranks."""
+        torch = _lib.require_cuda()
+        z = self._to_device(data_z, torch)
+        v = self._to_device(data_v, torch)
+        bs = z.shape[0]
+        if epsilon is None:
+            epsilon = float(self._eps_rng.uniform())
+        losses = torch.empty(2, dtype=torch.float32, device='cuda')
+        _lib.call("bgm_train_disc_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), bs, float(epsilon), 10.0,
+                  _lib.ptr(losses), _lib.stream_ptr())
+        self._apply(1, group)
+        l = losses.cpu().numpy()
+        return float(l[0]), float(l[1])
+
+    def train_gen_step(self, data_z, data_v, data_x, data_y, *, group=None):
+        """causalbgm/base.py:332-377 -> (e_loss_adv, l2_loss_v, l2_loss_z, l2_loss_x, l2_loss_y, g_e_loss)."""
+        torch = _lib.require_cuda()
+        z = self._to_device(data_z, torch)
+        v = self._to_device(data_v, torch)
+        x = self._to_device(data_x, torch).reshape(-1)
+        y = self._to_device(data_y, torch).reshape(-1)
+        losses = torch.empty(6, dtype=torch.float32, device='cuda')
+        _lib.call("bgm_train_gen_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), _lib.ptr(x), _lib.ptr(y),
+                  z.shape[0], _lib.ptr(losses), _lib.stream_ptr())
+        self._apply(0, group)
+        return tuple(float(a) for a in losses.cpu().numpy())
+
+    def egm_init(self, data, egm_n_iter=30000, batch_size=32, egm_batches_per_eval=500, verbose=1, *,
+                 group=None, chunk=64):
+        """causalbgm/base.py:380-431.  The data set stays on the device; mini-batch indices
+        and prior draws come from NumPy's global generator in the reference's exact call
+        order (g_d_freq x [choice, get_batch], then [get_batch, choice]) -- bit-exact index
+        streams -- generated `chunk` iterations ahead and uploaded in one copy; the batches
+        are gathered on the device.  Returns the last (dz_loss, d_loss) and generator losses.
+        The periodic evaluate()/save_data of :418-430 is not run."""
+        torch = _lib.require_cuda()
+        data_x, data_y, data_v = data
+        n = len(data_x)
+        p, zd = self._p['v_dim'], sum(self._p['z_dims'])
+        freq = int(self._p['g_d_freq'])
+        bs = int(batch_size)
+        xd = self._to_device(data_x, torch).reshape(-1).contiguous()
+        yd = self._to_device(data_y, torch).reshape(-1).contiguous()
+        vd = self._to_device(data_v, torch).contiguous()
+        tr = self._device_trainer()
+        st = _lib.stream_ptr()
+        dloss = torch.zeros(2, dtype=torch.float32, device='cuda')
+        gloss = torch.zeros(6, dtype=torch.float32, device='cuda')
+        bz = torch.empty((bs, zd), dtype=torch.float32, device='cuda')
+        bv = torch.empty((bs, p), dtype=torch.float32, device='cuda')
+        bx = torch.empty(bs, dtype=torch.float32, device='cuda')
+        by = torch.empty(bs, dtype=torch.float32, device='cuda')
+        if verbose:
+            print('EGM Initialization Starts ...')
+        total = int(egm_n_iter) + 1
+        it = 0
+        while it < total:
+            cnt = min(int(chunk), total - it)
+            idx = np.empty((cnt, freq + 1, bs), np.int32)
+            zz = np.empty((cnt, freq + 1, bs, zd), np.float32)
+            eps = np.empty((cnt, freq), np.float32)
+            for c in range(cnt):                                                  # host RNG, reference order
+                for k in range(freq):
+                    idx[c, k] = np.random.choice(n, bs, replace=False)            # :406
+                    zz[c, k] = self.z_sampler.get_batch(bs)                       # :407
+                    eps[c, k] = self._eps_rng.uniform()
+                zz[c, freq] = self.z_sampler.get_batch(bs)                        # :412
+                idx[c, freq] = np.random.choice(n, bs, replace=False)             # :413
+            idx_d = torch.from_numpy(idx).cuda()
+            zz_d = torch.from_numpy(zz).cuda()
+            for c in range(cnt):
+                for k in range(freq):
+                    ip = C.c_void_p(idx_d[c, k].data_ptr())
+                    _lib.call("bgm_gather_rows", _lib.ptr(vd), p, ip, bs, p, _lib.ptr(bv), st)
+                    _lib.call("bgm_train_disc_grad", tr, C.c_void_p(zz_d[c, k].data_ptr()), _lib.ptr(bv), bs,
+                              float(eps[c, k]), 10.0, _lib.ptr(dloss), st)
+                    self._apply(1, group)
+                ip = C.c_void_p(idx_d[c, freq].data_ptr())
+                _lib.call("bgm_gather_rows", _lib.ptr(vd), p, ip, bs, p, _lib.ptr(bv), st)
+                _lib.call("bgm_gather_rows", _lib.ptr(xd), 1, ip, bs, 1, _lib.ptr(bx), st)
+                _lib.call("bgm_gather_rows", _lib.ptr(yd), 1, ip, bs, 1, _lib.ptr(by), st)
+                _lib.call("bgm_train_gen_grad", tr, C.c_void_p(zz_d[c, freq].data_ptr()), _lib.ptr(bv), _lib.ptr(bx),
+                          _lib.ptr(by), bs, _lib.ptr(gloss), st)
+                self._apply(0, group)
+                if verbose and (it + c) % egm_batches_per_eval == 0:
+                    d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
+                    print('EGM Initialization Iter [%d] : e_loss_adv [%.4f], l2_loss_v [%.4f], l2_loss_z [%.4f], '
+                          'l2_loss_x [%.4f], l2_loss_y [%.4f], g_e_loss [%.4f], dz_loss [%.4f], d_loss [%.4f]'
+                          % (it + c, g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1]))
+            it += cnt
+        if verbose:
+            print('EGM Initialization Ends.')
+        d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
+        return (float(d[0]), float(d[1])), tuple(float(a) for a in g)

@@ -546,3 +546,4 @@ extern "C" int bgm_fp32_peak_tflops(double* tflops, void* stream) {
 }
 
 #include "hmc_api.cuh"
+#include "train_api.cuh"

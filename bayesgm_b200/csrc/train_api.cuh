@@ -1,0 +1,244 @@
+// Host side of the EGM training entry points (include/bgm_b200.h).  Included by bgm_b200.cu.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "train.cuh"
+
+struct bgm_trainer {
+  bgm::tr::Net g, e, f, h;
+  bgm::tr::Disc dz;
+  int z_dims[4];
+  int zd = 0, p = 0, binary = 0;
+  float use_z_rec = 1.f;
+  int n_gen = 0, n_disc = 0;
+  float *theta[2] = {nullptr, nullptr}, *grad[2] = {nullptr, nullptr};   // group 0: g|e|f|h ; group 1: dz
+  float *m[2] = {nullptr, nullptr}, *v[2] = {nullptr, nullptr};
+  float* tape = nullptr;
+  int tape_floats = 0;
+  long long step[2] = {0, 0};
+  double lr = 0, b1 = 0.9, b2 = 0.99;
+  int wm = 0, smem_gen = 0, smem_disc = 0, sm_count = 0;
+};
+
+namespace bgm {
+
+static int tr_fill_net(const bgm_net_desc* d, tr::Net& n, int& off, const char* name) {
+  if (!d || d->n_layers < 2 || d->n_layers > tr::MAXL || !d->dims || !d->params)
+    return fail(BGM_ERR_ARG, std::string(name) + ": need 2.." + std::to_string(tr::MAXL) + " Dense layers");
+  n.L = d->n_layers;
+  for (int l = 0; l <= n.L; ++l) n.dims[l] = d->dims[l];
+  for (int l = 0; l < n.L; ++l) {
+    if (n.dims[l] < 1 || n.dims[l + 1] < 1) return fail(BGM_ERR_ARG, std::string(name) + ": non-positive layer size");
+    n.w_off[l] = off;
+    off += n.dims[l] * n.dims[l + 1];
+    n.b_off[l] = off;
+    off += n.dims[l + 1];
+  }
+  return 0;
+}
+static int tr_net_params(const bgm_net_desc* d) {
+  int t = 0;
+  for (int l = 0; l < d->n_layers; ++l) t += d->dims[l] * d->dims[l + 1] + d->dims[l + 1];
+  return t;
+}
+
+}  // namespace bgm
+
+extern "C" {
+
+int bgm_trainer_create(bgm_trainer** out, const int z_dims[4], int v_dim, int binary_treatment, int use_z_rec,
+                       const bgm_net_desc* g_net, const bgm_net_desc* e_net, const bgm_net_desc* f_net,
+                       const bgm_net_desc* h_net, const bgm_disc_desc* dz_net, float lr, float beta_1,
+                       float beta_2) {
+  using namespace bgm;
+  if (!out || !z_dims || !dz_net) return fail(BGM_ERR_ARG, "bgm_trainer_create: null argument");
+  *out = nullptr;
+  bgm_trainer* t = new bgm_trainer();
+  int off = 0, rc;
+  if ((rc = tr_fill_net(g_net, t->g, off, "g_net")) || (rc = tr_fill_net(e_net, t->e, off, "e_net")) ||
+      (rc = tr_fill_net(f_net, t->f, off, "f_net")) || (rc = tr_fill_net(h_net, t->h, off, "h_net"))) {
+    delete t;
+    return rc;
+  }
+  t->n_gen = off;
+  const int zd = z_dims[0] + z_dims[1] + z_dims[2] + z_dims[3];
+  for (int i = 0; i < 4; ++i) t->z_dims[i] = z_dims[i];
+  t->zd = zd;
+  t->p = v_dim;
+  t->binary = binary_treatment ? 1 : 0;
+  t->use_z_rec = use_z_rec ? 1.f : 0.f;
+  bool ok = t->g.dims[0] == zd && t->g.dims[t->g.L] == v_dim + 1 && t->e.dims[0] == v_dim &&
+            t->e.dims[t->e.L] == zd && t->f.dims[0] == z_dims[0] + z_dims[1] + 1 && t->f.dims[t->f.L] == 2 &&
+            t->h.dims[0] == z_dims[0] + z_dims[2] && t->h.dims[t->h.L] == 2;
+  if (!ok) { delete t; return fail(BGM_ERR_ARG, "bgm_trainer_create: net shapes do not match z_dims / v_dim (causalbgm/base.py:74-81)"); }
+  // discriminator
+  if (dz_net->n_hidden < 1 || dz_net->n_hidden >= tr::MAXL || !dz_net->dims || !dz_net->params ||
+      dz_net->dims[0] != zd || dz_net->dims[dz_net->n_hidden + 1] != 1) {
+    delete t;
+    return fail(BGM_ERR_ARG, "bgm_trainer_create: dz_net must map sum(z_dims) -> 1 with 1..7 hidden blocks");
+  }
+  tr::Disc& D = t->dz;
+  D.L = dz_net->n_hidden;
+  int doff = 0;
+  for (int l = 0; l <= D.L + 1; ++l) D.dims[l] = dz_net->dims[l];
+  for (int l = 0; l <= D.L; ++l) {
+    D.w_off[l] = doff; doff += D.dims[l] * D.dims[l + 1];
+    D.b_off[l] = doff; doff += D.dims[l + 1];
+    if (l < D.L) {
+      D.g_off[l] = doff; doff += D.dims[l + 1];
+      D.be_off[l] = doff; doff += D.dims[l + 1];
+    }
+  }
+  D.n_params = doff;
+  t->n_disc = doff;
+  t->lr = lr; t->b1 = beta_1; t->b2 = beta_2;
+  int maxw = v_dim + 1;
+  for (const tr::Net* n : {&t->g, &t->e, &t->f, &t->h})
+    for (int l = 0; l <= n->L; ++l) maxw = std::max(maxw, n->dims[l]);
+  t->wm = (maxw + 3) / 4 * 4;
+  const int gen_floats = 4 * t->wm * tr::LD + 2 * zd * tr::LD + 2 * tr::LD + (zd + 1) * tr::LD + 16 +
+                         tr::disc_smem_floats(D, false);
+  const int disc_floats = 2 * t->wm * tr::LD + 3 * zd * tr::LD + tr::disc_smem_floats(D, true);
+  t->smem_gen = gen_floats * 4 + 64;
+  t->smem_disc = disc_floats * 4 + 64;
+  int dev = 0, smem_max = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) { delete t; return fail(BGM_ERR_CUDA, std::string("bgm_trainer_create: ") + cudaGetErrorString(e)); }
+  if (t->smem_gen > smem_max - 1024 || t->smem_disc > smem_max - 1024) {
+    delete t;
+    return fail(BGM_ERR_NOMEM, "bgm_trainer_create: v_dim / layer widths too large for the single-CTA training kernels");
+  }
+  t->tape_floats = 2 * tr::net_tape_floats(t->g) + 2 * tr::net_tape_floats(t->e) + tr::net_tape_floats(t->f) +
+                   tr::net_tape_floats(t->h) + (v_dim + zd) * tr::LD + 64;
+  const int n[2] = {t->n_gen, t->n_disc};
+  for (int gidx = 0; gidx < 2 && e == cudaSuccess; ++gidx) {
+    const size_t bytes = sizeof(float) * (size_t)n[gidx];
+    float** arrs[4] = {&t->theta[gidx], &t->grad[gidx], &t->m[gidx], &t->v[gidx]};
+    for (float** a : arrs) {
+      if (e == cudaSuccess) e = cudaMalloc(a, bytes);
+      if (e == cudaSuccess) e = cudaMemset(*a, 0, bytes);
+    }
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&t->tape, sizeof(float) * (size_t)t->tape_floats);
+  // initial parameters
+  if (e == cudaSuccess) {
+    std::vector<float> host(t->n_gen);
+    size_t o = 0;
+    for (const bgm_net_desc* d : {g_net, e_net, f_net, h_net}) {
+      const int cnt = tr_net_params(d);
+      memcpy(host.data() + o, d->params, sizeof(float) * cnt);
+      o += cnt;
+    }
+    e = cudaMemcpy(t->theta[0], host.data(), sizeof(float) * t->n_gen, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(t->theta[1], dz_net->params, sizeof(float) * t->n_disc, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    bgm_trainer_destroy(t);
+    return fail(BGM_ERR_CUDA, std::string("bgm_trainer_create: ") + cudaGetErrorString(e));
+  }
+  *out = t;
+  return 0;
+}
+
+void bgm_trainer_destroy(bgm_trainer* t) {
+  if (!t) return;
+  for (int g = 0; g < 2; ++g) {
+    if (t->theta[g]) cudaFree(t->theta[g]);
+    if (t->grad[g]) cudaFree(t->grad[g]);
+    if (t->m[g]) cudaFree(t->m[g]);
+    if (t->v[g]) cudaFree(t->v[g]);
+  }
+  if (t->tape) cudaFree(t->tape);
+  delete t;
+}
+
+int bgm_trainer_buffers(bgm_trainer* t, int group, int* n_params, float** theta_dev, float** grad_dev) {
+  using namespace bgm;
+  if (!t || group < 0 || group > 1) return fail(BGM_ERR_ARG, "bgm_trainer_buffers: bad trainer / group");
+  if (n_params) *n_params = group == 0 ? t->n_gen : t->n_disc;
+  if (theta_dev) *theta_dev = t->theta[group];
+  if (grad_dev) *grad_dev = t->grad[group];
+  return 0;
+}
+
+int bgm_trainer_get_params(bgm_trainer* t, int group, float* host_out) {
+  using namespace bgm;
+  if (!t || group < 0 || group > 1 || !host_out) return fail(BGM_ERR_ARG, "bgm_trainer_get_params: bad argument");
+  BGM_CUDA_OK(cudaMemcpy(host_out, t->theta[group], sizeof(float) * (group == 0 ? t->n_gen : t->n_disc),
+                         cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bgm_trainer_set_params(bgm_trainer* t, int group, const float* host_in) {
+  using namespace bgm;
+  if (!t || group < 0 || group > 1 || !host_in) return fail(BGM_ERR_ARG, "bgm_trainer_set_params: bad argument");
+  BGM_CUDA_OK(cudaMemcpy(t->theta[group], host_in, sizeof(float) * (group == 0 ? t->n_gen : t->n_disc),
+                         cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, int bs, float epsilon,
+                        float gp_weight, float* losses_dev, void* stream) {
+  using namespace bgm;
+  if (!t || !z_dev || !v_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_train_disc_grad: null argument");
+  if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_train_disc_grad: batch size must be in [2, 32]");
+  tr::DiscArgs A;
+  memset(&A, 0, sizeof(A));
+  A.e = t->e; A.dz = t->dz; A.zd = t->zd; A.p = t->p; A.bs = bs;
+  A.theta = t->theta[0]; A.theta_d = t->theta[1]; A.grad_d = t->grad[1];
+  A.z = z_dev; A.v = v_dev; A.epsilon = epsilon; A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm;
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::disc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_disc));
+  tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, (cudaStream_t)stream>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, const float* x_dev,
+                       const float* y_dev, int bs, float* losses_dev, void* stream) {
+  using namespace bgm;
+  if (!t || !z_dev || !v_dev || !x_dev || !y_dev || !losses_dev)
+    return fail(BGM_ERR_ARG, "bgm_train_gen_grad: null argument");
+  if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_train_gen_grad: batch size must be in [2, 32]");
+  tr::GenArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = t->g; A.e = t->e; A.f = t->f; A.h = t->h; A.dz = t->dz;
+  for (int i = 0; i < 4; ++i) A.z_dims[i] = t->z_dims[i];
+  A.zd = t->zd; A.p = t->p; A.binary = t->binary; A.use_z_rec = t->use_z_rec; A.bs = bs;
+  A.theta = t->theta[0]; A.theta_d = t->theta[1]; A.grad = t->grad[0]; A.tape = t->tape;
+  A.tape_floats = t->tape_floats;
+  A.z = z_dev; A.v = v_dev; A.x = x_dev; A.y = y_dev; A.losses = losses_dev; A.wm = t->wm;
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::gen_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_gen));
+  tr::gen_grad_kernel<<<1, tr::NTH, t->smem_gen, (cudaStream_t)stream>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_train_adam(bgm_trainer* t, int group, float grad_scale, void* stream) {
+  using namespace bgm;
+  if (!t || group < 0 || group > 1) return fail(BGM_ERR_ARG, "bgm_train_adam: bad trainer / group");
+  const int n = group == 0 ? t->n_gen : t->n_disc;
+  t->step[group] += 1;
+  const double k = (double)t->step[group];
+  const float lr_t = (float)(t->lr * std::sqrt(1.0 - std::pow(t->b2, k)) / (1.0 - std::pow(t->b1, k)));
+  const int grid = std::max(1, std::min((n + 255) / 256, t->sm_count * 4));
+  tr::adam_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t->theta[group], t->grad[group], t->m[group], t->v[group],
+                                                          n, lr_t, (float)t->b1, (float)t->b2, 1e-7f, grad_scale);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_gather_rows(const float* src_dev, int ld, const int* idx_dev, int bs, int dim, float* dst_dev, void* stream) {
+  using namespace bgm;
+  if (!src_dev || !idx_dev || !dst_dev || bs < 1 || dim < 1 || ld < dim)
+    return fail(BGM_ERR_ARG, "bgm_gather_rows: bad argument");
+  const int grid = std::max(1, std::min((bs * dim + 255) / 256, 148));
+  tr::gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_dev, ld, idx_dev, bs, dim, dst_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -62,6 +62,15 @@ class DenseNet(object):
     def as_oracle_layers(self):
         return [(W, b) for W, b in self.layers]
 
+    def load_flat(self, flat):
+        """Inverse of flat_params()."""
+        o = 0
+        for layer in self.layers:
+            for i in (0, 1):
+                a = layer[i]
+                layer[i] = np.array(flat[o:o + a.size], np.float32).reshape(a.shape)
+                o += a.size
+
 
 class VariationalNet(object):
     """`BaseVariationalNet` (networks/base.py:53-117): BatchNormalization on the input,
@@ -120,3 +129,53 @@ class VariationalNet(object):
     def as_oracle_params(self):
         return dict(bn=dict(self.bn), hidden=[(W, b) for W, b in self.hidden],
                     mean=(self.mean[0], self.mean[1]), var=(self.var[0], self.var[1]))
+
+
+class DiscNet(object):
+    """`Discriminator` (networks/base.py:338-385): Dense -> BatchNormalization (batch
+    statistics) -> tanh blocks, then Dense(1).  Keras defaults: glorot-uniform kernels, zero
+    biases, gamma 1, beta 0."""
+
+    def __init__(self, input_dim, model_name, nb_units, rng=None):
+        self.input_dim = int(input_dim)
+        self.model_name = model_name
+        self.nb_units = [int(u) for u in nb_units]
+        self.dims = [self.input_dim] + self.nb_units + [1]
+        rng = rng if rng is not None else np.random
+        self.layers, self.bns = [], []
+        for i in range(len(self.dims) - 1):
+            fi, fo = self.dims[i], self.dims[i + 1]
+            lim = np.sqrt(6.0 / (fi + fo))
+            self.layers.append([rng.uniform(-lim, lim, size=(fi, fo)).astype(np.float32), np.zeros(fo, np.float32)])
+            if i < len(self.nb_units):
+                self.bns.append([np.ones(fo, np.float32), np.zeros(fo, np.float32)])
+
+    def trainable_list(self):
+        """Keras trainable_variables order: per block kernel, bias, gamma, beta; then output kernel, bias."""
+        out = []
+        for (W, b), (g, be) in zip(self.layers[:-1], self.bns):
+            out += [W, b, g, be]
+        return out + list(self.layers[-1])
+
+    def flat_params(self):
+        return np.ascontiguousarray(np.concatenate([a.ravel() for a in self.trainable_list()]).astype(np.float32))
+
+    def load_flat(self, flat):
+        o = 0
+        for a in self.trainable_list():
+            a[...] = flat[o:o + a.size].reshape(a.shape)
+            o += a.size
+
+    def set_trainable(self, arrays):
+        for a, src in zip(self.trainable_list(), arrays):
+            a[...] = np.asarray(src, np.float32).reshape(a.shape)
+
+    def desc(self):
+        dims = (C.c_int * len(self.dims))(*self.dims)
+        flat = self.flat_params()
+        d = _lib.DiscDesc(len(self.nb_units), C.cast(dims, C.POINTER(C.c_int)), flat.ctypes.data_as(C.POINTER(C.c_float)))
+        return d, (dims, flat)
+
+    def as_oracle_params(self):
+        return dict(layers=[(W, b) for W, b in self.layers],
+                    bns=[dict(gamma=g, beta=be) for g, be in self.bns])

@@ -238,6 +238,55 @@ int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, in
                     uint64_t seed, int64_t row_offset, const float* noise_dev, float* out_x_dev,
                     void* stream);
 
+/* ------------------------------------------------------- EGM training steps -- */
+/* The Discriminator of networks/base.py:338-385: n_hidden blocks of
+ * Dense -> BatchNormalization (batch statistics in every call, eps 1e-3) -> tanh, then
+ * Dense(1).  dims[n_hidden+2] = [in, units..., 1]; `params` (HOST) in the order of
+ * Keras' trainable_variables: per block kernel[in][out], bias, gamma, beta; then the
+ * output kernel, bias.  (The BN moving statistics are never read by the reference's
+ * training path and are not kept.) */
+typedef struct {
+  int n_hidden;
+  const int* dims;
+  const float* params;
+} bgm_disc_desc;
+
+typedef struct bgm_trainer bgm_trainer; /* opaque: parameters, gradients, Adam moments on the device */
+
+/* State of CausalBGM's EGM phase (causalbgm/base.py:74-87): nets g,e,f,h (parameter
+ * group 0, flat in the order g|e|f|h, each net kernel,bias per layer = the order
+ * train_gen_step concatenates trainable_variables, :370) and dz_net (group 1), each
+ * group with its own Keras Adam(lr, beta_1, beta_2, eps=1e-7) (:86-87). */
+int bgm_trainer_create(bgm_trainer** out, const int z_dims[4], int v_dim, int binary_treatment, int use_z_rec,
+                       const bgm_net_desc* g_net, const bgm_net_desc* e_net, const bgm_net_desc* f_net,
+                       const bgm_net_desc* h_net, const bgm_disc_desc* dz_net, float lr, float beta_1,
+                       float beta_2);
+void bgm_trainer_destroy(bgm_trainer* t);
+/* Device pointers of a group's flat parameter / gradient buffers (for the data-parallel
+ * gradient all-reduce, the only collective of the training path) and their length. */
+int bgm_trainer_buffers(bgm_trainer* t, int group, int* n_params, float** theta_dev, float** grad_dev);
+int bgm_trainer_get_params(bgm_trainer* t, int group, float* host_out);
+int bgm_trainer_set_params(bgm_trainer* t, int group, const float* host_in);
+
+/* Gradients of train_disc_step (causalbgm/base.py:305-323) w.r.t. dz_net into the
+ * group-1 gradient buffer: e_net forward, three discriminator passes, WGAN-GP term
+ * gp_weight * mean((|d D(z_hat)/d z_hat| - 1)^2) with its double backward.  z_dev: (bs,zd)
+ * prior draws, v_dev: (bs,v_dim) covariate rows, 2 <= bs <= 32; epsilon: the U(0,1)
+ * draw of :307; losses_dev[2] = dz_loss, d_loss. */
+int bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, int bs, float epsilon,
+                        float gp_weight, float* losses_dev, void* stream);
+/* Gradients of train_gen_step (causalbgm/base.py:332-370) w.r.t. g,e,f,h into the
+ * group-0 gradient buffer; losses_dev[6] = e_loss_adv, l2_loss_v, l2_loss_z, l2_loss_x,
+ * l2_loss_y, g_e_loss (:377).  x_dev, y_dev: (bs). */
+int bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, const float* x_dev,
+                       const float* y_dev, int bs, float* losses_dev, void* stream);
+/* One Keras-Adam step of the group on (grad_scale * gradient buffer); grad_scale is
+ * 1/world_size after a summing all-reduce, 1 on a single GPU. */
+int bgm_train_adam(bgm_trainer* t, int group, float grad_scale, void* stream);
+/* dst[r][:] = src[idx[r]][:dim] -- mini-batch gather from device-resident data (:406-416). */
+int bgm_gather_rows(const float* src_dev, int ld, const int* idx_dev, int bs, int dim, float* dst_dev,
+                    void* stream);
+
 /* Dependent-FFMA micro-benchmark: measured fp32 FMA peak of the device in TFLOP/s
  * (the roofline denominator for the SIMT kernels; MEASURED_PEAKS.json has none). */
 int bgm_fp32_peak_tflops(double* tflops, void* stream);

@@ -1,0 +1,160 @@
+"""GPU parity tests of the EGM training steps: CUDA (hand-derived backward and double
+backward, through the C ABI) vs the torch-autograd oracle on the same batches.
+
+Tolerances (fp32): losses rtol 2e-4; every parameter-gradient tensor
+|d| <= 2e-3 * max|grad of that tensor| + 1e-7 (different summation orders through ~10
+layers and a double backward; + 2e-6 * the largest gradient of the step); after k optimizer steps parameters within 5e-4 absolute
+(Adam normalises the update to ~lr per step regardless of the gradient scale, so a
+sign-level disagreement on a near-zero gradient moves a parameter by at most k*lr).
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from oracle import train, nets as onets
+from helpers import causal_params, causal_nets, causal_data, product_model
+
+pytestmark = pytest.mark.gpu
+
+
+def make(v_dim=200, z_dims=(1, 1, 1, 2), binary=False, bs=32, seed=0, **extra):
+    params = causal_params(v_dim, list(z_dims), binary, **extra)
+    nets = causal_nets(params, seed=11)
+    rs = np.random.RandomState(seed)
+    zd = sum(z_dims)
+    dz = onets.init_discriminator(rs, zd, params['dz_units'])
+    for bn in dz['bns']:
+        bn['gamma'] = (1 + 0.1 * rs.standard_normal(bn['gamma'].shape)).astype(np.float32)
+        bn['beta'] = (0.1 * rs.standard_normal(bn['beta'].shape)).astype(np.float32)
+    for i, (W, b) in enumerate(dz['layers']):
+        dz['layers'][i] = (W, (0.1 * rs.standard_normal(b.shape)).astype(np.float32))
+    x, y, v = causal_data(bs, v_dim, binary, seed=seed + 1)
+    z = rs.standard_normal((bs, zd)).astype(np.float32)
+    m = product_model(params, nets)
+    m.set_weights(dz=train.disc_flat_params(dz))
+    return params, nets, dz, m, z, v, x, y
+
+
+def split_like(flat, arrays):
+    out, o = [], 0
+    for a in arrays:
+        out.append(flat[o:o + a.size].reshape(a.shape))
+        o += a.size
+    assert o == flat.size
+    return out
+
+
+def check_grads(got_list, want_list, names=None):
+    # a Dense bias in front of a batch-statistics BatchNorm has a mathematically ZERO gradient:
+    # both sides then hold rounding noise, so the absolute floor scales with the largest gradient
+    gmax = max(float(np.abs(w).max()) for w in want_list)
+    for i, (g, w) in enumerate(zip(got_list, want_list)):
+        tol = 2e-3 * np.abs(w).max() + 2e-6 * gmax + 1e-7
+        err = np.abs(g - w).max()
+        assert err <= tol, "tensor %d (%s): err %.3g > tol %.3g (max |g| %.3g)" % (
+            i, names[i] if names else "?", err, tol, np.abs(w).max())
+
+
+GEN_CASES = [
+    dict(),                                                       # cfg-3 shape, batch 32
+    dict(v_dim=100, z_dims=(3, 6, 3, 6), binary=True),            # cfg-2 shape, binary treatment
+    dict(v_dim=177, z_dims=(2, 1, 1, 1), bs=20),                  # ragged batch, odd v_dim
+    dict(v_dim=10, z_dims=(1, 1, 1, 0), g_units=[8, 8], e_units=[8, 8], f_units=[8, 8], h_units=[8, 8],
+         dz_units=[8, 8]),                                        # the R tests' tiny nets
+    dict(use_z_rec=False),
+]
+
+
+@pytest.mark.parametrize("kw", GEN_CASES)
+def test_gen_step_gradients(kw):
+    params, nets, dz, m, z, v, x, y = make(**kw)
+    want_losses, want = train.gen_step(params, nets, dz, z, v, x, y)
+    losses, flat = m.gradients('gen', z, v, x, y)
+    np.testing.assert_allclose(losses, want_losses, rtol=2e-4, atol=1e-6)
+    want_list = want['g'] + want['e'] + want['f'] + want['h']
+    check_grads(split_like(flat, want_list), want_list)
+
+
+DISC_CASES = [dict(), dict(v_dim=100, z_dims=(3, 6, 3, 6)), dict(v_dim=40, z_dims=(1, 1, 1, 1), bs=9),
+              dict(v_dim=12, z_dims=(1, 1, 1, 2), dz_units=[16, 16, 16, 4])]
+
+
+@pytest.mark.parametrize("kw", DISC_CASES)
+def test_disc_step_gradients_including_the_gradient_penalty(kw):
+    params, nets, dz, m, z, v, x, y = make(**kw)
+    for eps in (0.3, 0.9):
+        dz_loss, d_loss, want = train.disc_step(params, nets, dz, z, v, eps)
+        losses, flat = m.gradients('disc', z, v, epsilon=eps)
+        np.testing.assert_allclose(losses, [dz_loss, d_loss], rtol=2e-4, atol=2e-6)
+        check_grads(split_like(flat, want), want)
+
+
+def test_optimizer_steps_track_the_oracle():
+    params, nets, dz, m, z, v, x, y = make(v_dim=60, z_dims=(1, 2, 1, 2), lr=1e-3)
+    tr = train.EgmTrainer(params, copy.deepcopy(nets), copy.deepcopy(dz))
+    rs = np.random.RandomState(5)
+    for k in range(4):
+        zz = rs.standard_normal(z.shape).astype(np.float32)
+        eps = float(rs.uniform())
+        a = tr.train_disc_step(zz, v, eps)
+        b = m.train_disc_step(zz, v, epsilon=eps)
+        np.testing.assert_allclose(b, a, rtol=1e-3, atol=1e-5)
+        a = tr.train_gen_step(zz, v, x, y)
+        b = m.train_gen_step(zz, v, x, y)
+        np.testing.assert_allclose(b, a, rtol=1e-3, atol=1e-5)
+    w = m.get_weights()
+    for name in ('g', 'e', 'f', 'h'):
+        for got, want in zip(w[name], train.flat_params(tr.nets[name])):
+            assert np.abs(got - want).max() <= 5e-4
+    for i, (got, want) in enumerate(zip(w['dz'], train.disc_flat_params(tr.dz))):
+        if i % 4 == 1 and i < len(w['dz']) - 2:
+            # Dense bias in front of a batch-statistics BN: zero true gradient, Adam turns the
+            # rounding noise into +-lr steps on both sides; the value never reaches the output
+            assert np.abs(got - want).max() <= 2 * 4 * 1e-3 + 1e-6
+            continue
+        assert np.abs(got - want).max() <= 5e-4, i
+    # ... and the discriminators agree as functions
+    zt = rs.standard_normal(z.shape).astype(np.float32)
+    dz_got = dict(layers=[(w['dz'][4 * b], w['dz'][4 * b + 1]) for b in range(3)] + [(w['dz'][-2], w['dz'][-1])],
+                  bns=[dict(gamma=w['dz'][4 * b + 2], beta=w['dz'][4 * b + 3]) for b in range(3)])
+    np.testing.assert_allclose(onets.discriminator_forward(dz_got, zt), onets.discriminator_forward(tr.dz, zt),
+                               rtol=0, atol=5e-3)
+    # the sampler picks up the trained weights
+    from oracle import causal
+    lp = m.get_log_posterior(x, y, v, zz)
+    want_lp = causal.log_posterior(params, {k: [(W, b) for W, b in zip(w[k][0::2], w[k][1::2])] for k in 'gefh'},
+                                   x, y, v, zz)
+    assert (np.abs(lp - want_lp) / np.maximum(1, np.abs(want_lp))).max() <= 1e-4
+
+
+def test_egm_init_follows_the_reference_index_stream():
+    """Same NumPy seed on both sides: mini-batch indices and prior draws are bit-identical
+    (host RNG, reference call order), so after a few iterations the parameters agree."""
+    params = causal_params(30, [1, 1, 1, 2], lr=1e-3, g_d_freq=2)
+    nets = causal_nets(params, seed=11)
+    data = causal_data(500, 30)
+    m = product_model(params, nets)
+    dz0 = m.dz_net.as_oracle_params()
+    tr = train.EgmTrainer(params, copy.deepcopy(nets), copy.deepcopy(dz0))
+    eps_stream = np.random.RandomState(77).uniform(size=100).astype(np.float32)
+    it = iter(eps_stream)
+    np.random.seed(123)
+    tr.egm_init(data, 3, 16, m.z_sampler, lambda: float(next(it)))
+    after_oracle = np.random.get_state()[1][:5].copy()
+
+    class Eps(object):
+        def __init__(self):
+            self.i = 0
+
+        def uniform(self):
+            self.i += 1
+            return eps_stream[self.i - 1]
+    m._eps_rng = Eps()
+    np.random.seed(123)
+    m.egm_init(data, egm_n_iter=3, batch_size=16, egm_batches_per_eval=2, verbose=0)
+    np.testing.assert_array_equal(np.random.get_state()[1][:5], after_oracle)   # same number of draws
+    w = m.get_weights()
+    for name in ('g', 'e', 'f', 'h'):
+        for got, want in zip(w[name], train.flat_params(tr.nets[name])):
+            assert np.abs(got - want).max() <= 1e-3
