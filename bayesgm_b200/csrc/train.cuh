@@ -338,7 +338,8 @@ __device__ void disc_forward(const Disc& dz, const float* th, const DiscBufs& B,
 //   gacc != NULL: accumulate scale * parameter gradients into gacc (disc group layout)
 //   keeps H, U, Q, m2 in B for the double backward.  U[0] = d(loss)/d(input).
 __device__ void disc_backward(const Disc& dz, const float* th, const DiscBufs& B, int bs, float seed,
-                              float* gacc, float scale) {
+                              float* gacc, float scale, const float* seedv = nullptr) {
+  // seedv != NULL: per-row seeds d(loss)/d(out[r]) (shared memory, 32 floats) instead of `seed`
   const float inv_bs = 1.f / (float)bs;
   const int L = dz.L;
   {  // output layer
@@ -349,15 +350,19 @@ __device__ void disc_backward(const Disc& dz, const float* th, const DiscBufs& B
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 x4 = ld4(B.X[L] + j * LD + q * 4);
-        float4 u;
-        u.x = rowmask(q * 4, bs) * seed * w; u.y = rowmask(q * 4 + 1, bs) * seed * w;
-        u.z = rowmask(q * 4 + 2, bs) * seed * w; u.w = rowmask(q * 4 + 3, bs) * seed * w;
-        st4(B.U[L] + j * LD + q * 4, u);
-        sx += x4.x + x4.y + x4.z + x4.w;       // rows >= bs of X are zero
+        float sd[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sd[c] = rowmask(q * 4 + c, bs) * (seedv ? seedv[q * 4 + c] : seed);
+        st4(B.U[L] + j * LD + q * 4, make_float4(sd[0] * w, sd[1] * w, sd[2] * w, sd[3] * w));
+        sx += sd[0] * x4.x + sd[1] * x4.y + sd[2] * x4.z + sd[3] * x4.w;
       }
-      if (gacc) gacc[dz.w_off[L] + j] += scale * seed * sx;
+      if (gacc) gacc[dz.w_off[L] + j] += scale * sx;
     }
-    if (gacc && threadIdx.x == 0) gacc[dz.b_off[L]] += scale * seed * (float)bs;
+    if (gacc && threadIdx.x == 0) {
+      float sb = 0.f;
+      for (int r = 0; r < bs; ++r) sb += seedv ? seedv[r] : seed;
+      gacc[dz.b_off[L]] += scale * sb;
+    }
     __syncthreads();
   }
   for (int l = L; l >= 1; --l) {
@@ -399,7 +404,7 @@ __device__ void disc_backward(const Disc& dz, const float* th, const DiscBufs& B
           dbias += hh[c];
         }
         st4(B.H[l - 1] + j * LD + q * 4, make_float4(hh[0], hh[1], hh[2], hh[3]));
-        st4(B.Q[l - 1] + j * LD + q * 4, make_float4(q_[q * 4], q_[q * 4 + 1], q_[q * 4 + 2], q_[q * 4 + 3]));
+        if (B.Q[l - 1]) st4(B.Q[l - 1] + j * LD + q * 4, make_float4(q_[q * 4], q_[q * 4 + 1], q_[q * 4 + 2], q_[q * 4 + 3]));
       }
       if (gacc) {
         gacc[dz.g_off[l - 1] + j] += scale * dgam;
@@ -654,25 +659,32 @@ __device__ __host__ inline int disc_maxd(const Disc& dz) {
   for (int l = 0; l <= dz.L; ++l) m = dz.dims[l] > m ? dz.dims[l] : m;
   return m;
 }
-// floats of shared memory the discriminator machinery needs
-__device__ __host__ inline int disc_smem_floats(const Disc& dz, bool with_double) {
+// floats of shared memory the discriminator machinery needs.  with_double: keep what the
+// double backward reads (Q) and its scratch; ext_x0: the input matrix X[0] lives elsewhere.
+__device__ __host__ inline int disc_smem_floats(const Disc& dz, bool with_double, bool ext_x0 = false) {
   const int ft = disc_feat_total(dz), md = disc_maxd(dz);
   int hid = 0;
   for (int l = 1; l <= dz.L; ++l) hid += dz.dims[l];
-  // X (ft) + U (ft) + N,H,Q (3*hid) matrices ; double backward: XB,NB (2*hid) + 3*maxd
-  return (2 * ft + 3 * hid + (with_double ? 2 * hid + 3 * md : 0)) * LD + 3 * ft + 64 + dz.n_params * 2;
+  const int mats = (ext_x0 ? hid : ft) + ft + 2 * hid + (with_double ? hid + 2 * hid + 3 * md : 0);
+  return mats * LD + 3 * ft + 64 + dz.n_params * 2;
 }
 
 __device__ void disc_carve(const Disc& dz, float* base, bool with_double, DiscBufs& B, float*& scr, float*& sbar,
-                           float*& outv, float*& th_s, float*& gacc) {
+                           float*& outv, float*& th_s, float*& gacc, float* x0_ext = nullptr) {
   float* p = base;
   int f = 0;
-  for (int l = 0; l <= dz.L; ++l) { B.X[l] = p; p += dz.dims[l] * LD; B.foff[l] = f; f += dz.dims[l]; }
+  for (int l = 0; l <= dz.L; ++l) {
+    if (l == 0 && x0_ext) B.X[0] = x0_ext;
+    else { B.X[l] = p; p += dz.dims[l] * LD; }
+    B.foff[l] = f;
+    f += dz.dims[l];
+  }
   for (int l = 0; l <= dz.L; ++l) { B.U[l] = p; p += dz.dims[l] * LD; }
   for (int l = 1; l <= dz.L; ++l) {
     B.N[l - 1] = p; p += dz.dims[l] * LD;
     B.H[l - 1] = p; p += dz.dims[l] * LD;
-    B.Q[l - 1] = p; p += dz.dims[l] * LD;
+    if (with_double) { B.Q[l - 1] = p; p += dz.dims[l] * LD; }
+    else B.Q[l - 1] = nullptr;
   }
   int hid = 0;
   for (int l = 1; l <= dz.L; ++l) hid += dz.dims[l];

@@ -148,7 +148,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = N_ROWS * iters * args.steps / dt
     sample = "%d MH iterations per step over all n=%d rows (of T=%d)" % (iters, N_ROWS, BURN_IN + N_MCMC)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -156,7 +156,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement (oracle/) of causalbgm/base.py:820-904; TF 2.10/TFP 0.18 not installable here",
-    }))
+    })
 
 
 def run_ours(args):
@@ -286,12 +286,25 @@ def run_ours(args):
                                        % (cpu_iters, n, cpu_dt)},
             "clocks": clk,
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(obj):
+    """The ONE JSON line on the real stdout (see main(): fd 1 is pointed at stderr while the
+    benchmark runs so that library chatter -- e.g. NCCL's version banner -- cannot precede it)."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
