@@ -101,6 +101,14 @@ SYMBOLS = {
     "bgm_train_gen_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]),
     "bgm_train_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "bgm_bgmtrainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VarNetDesc), C.POINTER(NetDesc),
+                                        C.POINTER(DiscDesc), C.POINTER(DiscDesc), C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_float]),
+    "bgm_trainer_bn_moving": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "bgm_bgm_train_disc_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_bgm_train_gen_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
     "bgm_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_hmc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VarNetDesc)]),
     "bgm_hmc_destroy": (None, [C.c_void_p]),

@@ -17,7 +17,8 @@ import numpy as np
 
 from . import _lib
 from .datasets import Gaussian_sampler
-from .nets import DenseNet, VariationalNet
+from .nets import DenseNet, VariationalNet, DiscNet
+from .datasets import Base_sampler
 
 _DEFAULTS = dict(use_bnn=False, g_units=[64] * 5, e_units=[64] * 5, dz_units=[64, 32, 8],
                  dx_units=[64, 32, 8], lr=0.001, lr_theta=0.005, lr_z=0.005, gamma=0.0, alpha=0.0,
@@ -77,7 +78,12 @@ class BGM(object):
         rng = np.random.RandomState(random_seed) if random_seed is not None else np.random
         self.g_net = VariationalNet(p['z_dim'], p['x_dim'], 'g_net', p['g_units'], rng)      # :70
         self.e_net = DenseNet(p['x_dim'], p['z_dim'], 'e_net', p['e_units'], rng)             # :73
+        self.dz_net = DiscNet(p['z_dim'], 'dz_net', p['dz_units'], rng)                       # :76
+        self.dx_net = DiscNet(p['x_dim'], 'dx_net', p['dx_units'], rng)                       # :78
         self.z_sampler = Gaussian_sampler(mean=np.zeros(p['z_dim']), sd=1.0)                 # :85
+        self._trainer = None
+        self._trainer_dirty = False
+        self._noise_rng = np.random.RandomState(0 if random_seed is None else random_seed)
         if self.timestamp is None:
             self.timestamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
         self.checkpoint_path = "{}/checkpoints/{}/{}".format(p['output_dir'], p['dataset'], self.timestamp)
@@ -98,12 +104,83 @@ class BGM(object):
         if print_summary:
             print(self.g_net.model_name, [self.g_net.input_dim] + self.g_net.nb_units + [self.g_net.output_dim])
 
-    def set_weights(self, g=None, e=None):
-        """Keras-layout weights (`net.get_weights()` of a trained reference model)."""
+    def set_weights(self, g=None, e=None, dz=None, dx=None):
+        """Keras-layout weights (`net.get_weights()` of a trained reference model; dz / dx: the
+        Discriminators' trainable_variables)."""
+        self._sync_from_trainer()
         if g is not None:
             self.g_net.set_weights(g)
         if e is not None:
             self.e_net.set_weights(e)
+        if dz is not None:
+            self.dz_net.set_trainable(dz)
+        if dx is not None:
+            self.dx_net.set_trainable(dx)
+        self._drop_handle()
+        self._drop_trainer()
+
+    def get_weights(self):
+        self._sync_from_trainer()
+        return dict(g=self.g_net.get_weights(), e=self.e_net.get_weights(),
+                    dz=[a.copy() for a in self.dz_net.trainable_list()],
+                    dx=[a.copy() for a in self.dx_net.trainable_list()])
+
+    def _drop_trainer(self):
+        if self._trainer is not None:
+            _lib.load().bgm_trainer_destroy(self._trainer)
+            self._trainer = None
+            self._trainer_dirty = False
+
+    def _device_trainer(self):
+        if self._trainer is None:
+            _lib.require_cuda()
+            p = self._p
+            gd, gk = self.g_net.desc()
+            ed, ek = self.e_net.desc()
+            zd_, zk = self.dz_net.desc()
+            xd_, xk = self.dx_net.desc()
+            h = C.c_void_p()
+            _lib.call("bgm_bgmtrainer_create", C.byref(h), C.byref(gd), C.byref(ed), C.byref(zd_), C.byref(xd_),
+                      float(p['lr']), 0.5, 0.9, float(p['alpha']), float(p['gamma']))          # Adam betas :83-85
+            self._trainer = h
+        return self._trainer
+
+    def _sync_from_trainer(self):
+        """Pull trained parameters (device layout: gamma | beta | hidden | [W_mean|W_var] | [b_mean|b_var] | e)
+        and the BN moving statistics back into the Keras-layout host arrays."""
+        if self._trainer is None or not self._trainer_dirty:
+            return
+        n = C.c_int()
+        zd, xd = self._p['z_dim'], self._p['x_dim']
+        _lib.call("bgm_trainer_buffers", self._trainer, 0, C.byref(n), None, None)
+        flat = np.empty(n.value, np.float32)
+        _lib.call("bgm_trainer_get_params", self._trainer, 0, flat.ctypes.data_as(C.c_void_p))
+        g = self.g_net
+        g.bn['gamma'], g.bn['beta'] = flat[:zd].copy(), flat[zd:2 * zd].copy()
+        o = 2 * zd
+        for layer in g.hidden:
+            for i in (0, 1):
+                a = layer[i]
+                layer[i] = flat[o:o + a.size].reshape(a.shape).copy()
+                o += a.size
+        last = g.nb_units[-1]
+        wcat = flat[o:o + last * 2 * xd].reshape(last, 2 * xd)
+        o += last * 2 * xd
+        bcat = flat[o:o + 2 * xd]
+        o += 2 * xd
+        g.mean = [wcat[:, :xd].copy(), bcat[:xd].copy()]
+        g.var = [wcat[:, xd:].copy(), bcat[xd:].copy()]
+        self.e_net.load_flat(flat[o:])
+        mv = np.empty(2 * zd, np.float32)
+        _lib.call("bgm_trainer_bn_moving", self._trainer, mv.ctypes.data_as(C.c_void_p), 0)
+        g.bn['mean'], g.bn['var'] = mv[:zd].copy(), mv[zd:].copy()
+        _lib.call("bgm_trainer_buffers", self._trainer, 1, C.byref(n), None, None)
+        flat = np.empty(n.value, np.float32)
+        _lib.call("bgm_trainer_get_params", self._trainer, 1, flat.ctypes.data_as(C.c_void_p))
+        k = self.dz_net.flat_params().size
+        self.dz_net.load_flat(flat[:k])
+        self.dx_net.load_flat(flat[k:])
+        self._trainer_dirty = False
         self._drop_handle()
 
     def _drop_handle(self):
@@ -114,10 +191,12 @@ class BGM(object):
     def __del__(self):
         try:
             self._drop_handle()
+            self._drop_trainer()
         except Exception:
             pass
 
     def _device_model(self):
+        self._sync_from_trainer()
         if self._handle is None:
             _lib.require_cuda()
             d, keep = self.g_net.desc()
@@ -402,5 +481,109 @@ class BGM(object):
             "bayesgm_b200: the BGM training path (bgm/base.py:145-442) has no sm_100a kernels yet; "
             "load trained weights with set_weights().")
 
-    def egm_init(self, data, egm_n_iter=10000, batch_size=32, egm_batches_per_eval=500, verbose=1):
-        raise NotImplementedError("bayesgm_b200: BGM EGM initialisation (bgm/base.py:190-340) is not built yet.")
+    # ------------------------------------------------------------ EGM training
+    def _grad_tensor(self, group):
+        torch = _lib.require_cuda()
+        n, ptr = C.c_int(), C.c_void_p()
+        _lib.call("bgm_trainer_buffers", self._device_trainer(), group, C.byref(n), None, C.byref(ptr))
+
+        class _View(object):
+            __cuda_array_interface__ = dict(shape=(n.value,), typestr='<f4', data=(ptr.value, False), version=2)
+        return torch.as_tensor(_View(), device='cuda')
+
+    def _apply(self, group_id, dist_group):
+        scale = 1.0
+        if dist_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self._grad_tensor(group_id), group=dist_group)
+            scale = 1.0 / dist.get_world_size(dist_group)
+        _lib.call("bgm_train_adam", self._device_trainer(), group_id, float(scale), _lib.stream_ptr())
+        self._trainer_dirty = True
+
+    def _disc_call(self, z, x, eps_z, eps_x, noise, losses):
+        _lib.call("bgm_bgm_train_disc_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(x), z.shape[0],
+                  float(eps_z), float(eps_x), _lib.ptr(noise), _lib.ptr(losses), _lib.stream_ptr())
+
+    def _gen_call(self, z, x, n1, n2, losses):
+        _lib.call("bgm_bgm_train_gen_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(x), z.shape[0],
+                  _lib.ptr(n1), _lib.ptr(n2), _lib.ptr(losses), _lib.stream_ptr())
+
+    def gradients(self, which, data_z, data_x, *, eps_z=0.5, eps_x=0.5, noise=None, noise2=None):
+        """(losses, flat gradient in DEVICE layout) of one step without the optimizer update
+        (test hook).  'disc': group 1 = [dz | dx]; 'gen': group 0 (see bgm_bgmtrainer_create)."""
+        torch = _lib.require_cuda()
+        z = self._dev(data_z, torch, torch.float32)
+        x = self._dev(data_x, torch, torch.float32)
+        n1 = self._dev(noise, torch, torch.float32)
+        if which == 'disc':
+            losses = torch.empty(3, dtype=torch.float32, device='cuda')
+            self._disc_call(z, x, eps_z, eps_x, n1, losses)
+            return losses.cpu().numpy(), self._grad_tensor(1).cpu().numpy()
+        n2 = self._dev(noise2, torch, torch.float32)
+        losses = torch.empty(6, dtype=torch.float32, device='cuda')
+        self._gen_call(z, x, n1, n2, losses)
+        return losses.cpu().numpy(), self._grad_tensor(0).cpu().numpy()
+
+    def train_disc_step(self, data_z, data_x, *, eps_z=None, eps_x=None, noise=None, group=None):
+        """bgm/base.py:190-245 -> (dz_loss, dx_loss, d_loss).  The U(0,1) draws of :199-200 and the
+        N(0,1) draws of reparameterize (:208) come from a private RandomState unless given."""
+        torch = _lib.require_cuda()
+        z = self._dev(data_z, torch, torch.float32)
+        x = self._dev(data_x, torch, torch.float32)
+        rs = self._noise_rng
+        eps_z = float(rs.uniform()) if eps_z is None else eps_z
+        eps_x = float(rs.uniform()) if eps_x is None else eps_x
+        noise = rs.standard_normal(tuple(x.shape)).astype(np.float32) if noise is None else noise
+        losses = torch.empty(3, dtype=torch.float32, device='cuda')
+        self._disc_call(z, x, eps_z, eps_x, self._dev(noise, torch, torch.float32), losses)
+        self._apply(1, group)
+        return tuple(float(a) for a in losses.cpu().numpy())
+
+    def train_gen_step(self, data_z, data_x, *, noise1=None, noise2=None, group=None):
+        """bgm/base.py:247-291 -> (g_loss_adv, e_loss_adv, l2_loss_z, l2_loss_x, reg_loss, g_e_loss)."""
+        torch = _lib.require_cuda()
+        z = self._dev(data_z, torch, torch.float32)
+        x = self._dev(data_x, torch, torch.float32)
+        rs = self._noise_rng
+        noise1 = rs.standard_normal(tuple(x.shape)).astype(np.float32) if noise1 is None else noise1
+        noise2 = rs.standard_normal(tuple(x.shape)).astype(np.float32) if noise2 is None else noise2
+        losses = torch.empty(6, dtype=torch.float32, device='cuda')
+        self._gen_call(z, x, self._dev(noise1, torch, torch.float32), self._dev(noise2, torch, torch.float32), losses)
+        self._apply(0, group)
+        return tuple(float(a) for a in losses.cpu().numpy())
+
+    def egm_init(self, data, egm_n_iter=10000, batch_size=32, egm_batches_per_eval=500, verbose=1, *, group=None):
+        """bgm/base.py:294-340: mini-batches from `Base_sampler` (its shuffled index stream is
+        NumPy's legacy generator, bit-exact), prior draws from `z_sampler.get_batch`.  The
+        periodic generate()/evaluate()/np.savez of :317-339 is not run."""
+        torch = _lib.require_cuda()
+        data = np.asarray(data, dtype=np.float32)
+        self.data_sampler = Base_sampler(x=data, y=data, v=data, batch_size=batch_size, normalize=False)   # :295
+        dloss = torch.zeros(3, dtype=torch.float32, device='cuda')
+        gloss = torch.zeros(6, dtype=torch.float32, device='cuda')
+        rs = self._noise_rng
+        if verbose:
+            print('EGM Initialization Starts ...')
+        for it in range(int(egm_n_iter) + 1):
+            for _ in range(int(self._p['g_d_freq'])):
+                bx, _, _ = self.data_sampler.next_batch()                                    # :300
+                bz = self.z_sampler.get_batch(batch_size)                                   # :301
+                x, z = self._dev(bx, torch, torch.float32), self._dev(bz, torch, torch.float32)
+                nz = self._dev(rs.standard_normal(bx.shape).astype(np.float32), torch, torch.float32)
+                self._disc_call(z, x, rs.uniform(), rs.uniform(), nz, dloss)
+                self._apply(1, group)
+            bx, _, _ = self.data_sampler.next_batch()                                        # :304
+            bz = self.z_sampler.get_batch(batch_size)                                       # :305
+            x, z = self._dev(bx, torch, torch.float32), self._dev(bz, torch, torch.float32)
+            n1 = self._dev(rs.standard_normal(bx.shape).astype(np.float32), torch, torch.float32)
+            n2 = self._dev(rs.standard_normal(bx.shape).astype(np.float32), torch, torch.float32)
+            self._gen_call(z, x, n1, n2, gloss)
+            self._apply(0, group)
+            if verbose and it % egm_batches_per_eval == 0:
+                d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
+                print('EGM Initialization Iter [%d] : g_loss_adv[%.4f], e_loss_adv [%.4f], l2_loss_z [%.4f], '
+                      'l2_loss_x [%.4f], sd^2_loss[%.4f], g_e_loss [%.4f], dz_loss [%.4f], dx_loss[%.4f], d_loss [%.4f]'
+                      % (it, g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1], d[2]))
+        if verbose:
+            print('EGM Initialization Ends.')
+        return tuple(float(a) for a in dloss.cpu().numpy()), tuple(float(a) for a in gloss.cpu().numpy())

@@ -666,11 +666,14 @@ __device__ __host__ inline int disc_smem_floats(const Disc& dz, bool with_double
   int hid = 0;
   for (int l = 1; l <= dz.L; ++l) hid += dz.dims[l];
   const int mats = (ext_x0 ? hid : ft) + ft + 2 * hid + (with_double ? hid + 2 * hid + 3 * md : 0);
-  return mats * LD + 3 * ft + 64 + dz.n_params * 2;
+  return mats * LD + 3 * ft + 64 + 16;
 }
 
+// Parameters are read from global memory (L1-cached) and gradients accumulate straight into
+// the global gradient buffer (each parameter is owned by one thread per phase; phases are
+// separated by __syncthreads), so neither takes shared memory.
 __device__ void disc_carve(const Disc& dz, float* base, bool with_double, DiscBufs& B, float*& scr, float*& sbar,
-                           float*& outv, float*& th_s, float*& gacc, float* x0_ext = nullptr) {
+                           float*& outv, float* x0_ext = nullptr) {
   float* p = base;
   int f = 0;
   for (int l = 0; l <= dz.L; ++l) {
@@ -693,8 +696,6 @@ __device__ void disc_carve(const Disc& dz, float* base, bool with_double, DiscBu
   B.m2 = p; p += f;
   sbar = p; p += f;
   outv = p; p += 64;
-  th_s = p; p += dz.n_params;
-  gacc = p; p += dz.n_params;
 }
 
 // ================================ kernels ======================================
@@ -709,9 +710,11 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
   float* zenc = zmat + A.zd * LD;           // e(v)   [zd][LD]
   float* zhat = zenc + A.zd * LD;
   DiscBufs B;
-  float *scr, *sbar, *outv, *th_s, *gacc;
-  disc_carve(dz, zhat + A.zd * LD, true, B, scr, sbar, outv, th_s, gacc);
-  for (int i = threadIdx.x; i < dz.n_params; i += NTH) { th_s[i] = A.theta_d[i]; gacc[i] = 0.f; }
+  float *scr, *sbar, *outv;
+  disc_carve(dz, zhat + A.zd * LD, true, B, scr, sbar, outv);
+  const float* th_s = A.theta_d;
+  float* gacc = A.grad_d;
+  for (int i = threadIdx.x; i < dz.n_params; i += NTH) gacc[i] = 0.f;
   load_cols(A.v, A.p, 0, A.p, bs, bufA);
   load_cols(A.z, A.zd, 0, A.zd, bs, zmat);
   __syncthreads();
@@ -768,7 +771,6 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
   __syncthreads();
   disc_double_backward(dz, th_s, B, bs, UB0, scr, sbar, gacc, A.gp_weight, disc_maxd(dz));
   __syncthreads();
-  for (int i = threadIdx.x; i < dz.n_params; i += NTH) A.grad_d[i] = gacc[i];
   if (threadIdx.x == 0) {
     const float dz_loss = -mean_d + mean_d_;               // :316
     A.losses[0] = dz_loss;
@@ -791,9 +793,9 @@ __global__ void __launch_bounds__(NTH, 1) gen_grad_kernel(const __grid_constant_
   float* fin = xy + 2 * LD;                // f / h inputs   [zd+1][LD]
   float* red = fin + (zd + 1) * LD;        // [16] loss accumulators
   DiscBufs B;
-  float *scr, *sbar, *outv, *th_s, *gacc;
-  disc_carve(A.dz, red + 16, false, B, scr, sbar, outv, th_s, gacc);
-  for (int i = threadIdx.x; i < A.dz.n_params; i += NTH) th_s[i] = A.theta_d[i];
+  float *scr, *sbar, *outv;
+  disc_carve(A.dz, red + 16, false, B, scr, sbar, outv);
+  const float* th_s = A.theta_d;
   if (threadIdx.x < 16) red[threadIdx.x] = 0.f;
   // tape layout
   float* T_g1 = A.tape;

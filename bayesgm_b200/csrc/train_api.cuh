@@ -4,7 +4,7 @@
 #include <cstring>
 #include <vector>
 
-#include "train.cuh"
+#include "train_bgm.cuh"
 
 struct bgm_trainer {
   bgm::tr::Net g, e, f, h;
@@ -20,6 +20,14 @@ struct bgm_trainer {
   long long step[2] = {0, 0};
   double lr = 0, b1 = 0.9, b2 = 0.99;
   int wm = 0, smem_gen = 0, smem_disc = 0, sm_count = 0;
+  // BGM flavour (kind == 1): variational generator, two discriminators
+  int kind = 0;
+  bgm::tr::VarNet vg;
+  bgm::tr::Disc dx;
+  int dx_base = 0, xd = 0;
+  float alpha = 0.f, gamma = 0.f;
+  float* moving = nullptr;     // [2*zd] BN moving mean | variance of the generator input
+  int disc_floats = 0;
 };
 
 namespace bgm {
@@ -44,9 +52,176 @@ static int tr_net_params(const bgm_net_desc* d) {
   return t;
 }
 
+static int tr_fill_disc(const bgm_disc_desc* d, tr::Disc& D, int in_dim, const char* name) {
+  if (!d || d->n_hidden < 1 || d->n_hidden >= tr::MAXL || !d->dims || !d->params || d->dims[0] != in_dim ||
+      d->dims[d->n_hidden + 1] != 1)
+    return fail(BGM_ERR_ARG, std::string(name) + ": discriminator must map its input -> 1 with 1..7 hidden blocks");
+  D.L = d->n_hidden;
+  int doff = 0;
+  for (int l = 0; l <= D.L + 1; ++l) D.dims[l] = d->dims[l];
+  for (int l = 0; l <= D.L; ++l) {
+    D.w_off[l] = doff; doff += D.dims[l] * D.dims[l + 1];
+    D.b_off[l] = doff; doff += D.dims[l + 1];
+    if (l < D.L) {
+      D.g_off[l] = doff; doff += D.dims[l + 1];
+      D.be_off[l] = doff; doff += D.dims[l + 1];
+    }
+  }
+  D.n_params = doff;
+  return 0;
+}
+
 }  // namespace bgm
 
 extern "C" {
+
+void bgm_trainer_destroy(bgm_trainer* t);
+
+int bgm_bgmtrainer_create(bgm_trainer** out, const bgm_varnet_desc* g, const bgm_net_desc* e_net,
+                          const bgm_disc_desc* dz_net, const bgm_disc_desc* dx_net, float lr, float beta_1,
+                          float beta_2, float alpha, float gamma) {
+  using namespace bgm;
+  if (!out || !g || !e_net || !dz_net || !dx_net) return fail(BGM_ERR_ARG, "bgm_bgmtrainer_create: null argument");
+  *out = nullptr;
+  if (!g->units || !g->bn || !g->hidden_params || !g->mean_params || !g->var_params || g->n_hidden < 1 ||
+      g->n_hidden + 1 > tr::MAXL)
+    return fail(BGM_ERR_ARG, "bgm_bgmtrainer_create: bad generator description");
+  const int zd = g->z_dim, xd = g->x_dim, nh = g->n_hidden;
+  bgm_trainer* t = new bgm_trainer();
+  t->kind = 1;
+  t->zd = zd; t->xd = xd; t->p = xd;
+  t->alpha = alpha; t->gamma = gamma;
+  int off = 0;
+  t->vg.zd = zd; t->vg.xd = xd;
+  t->vg.gamma_off = off; off += zd;
+  t->vg.beta_off = off; off += zd;
+  tr::Net& G = t->vg.mlp;
+  G.L = nh + 1;
+  G.dims[0] = zd;
+  for (int l = 0; l < nh; ++l) G.dims[l + 1] = g->units[l];
+  G.dims[nh + 1] = 2 * xd;
+  for (int l = 0; l < G.L; ++l) {
+    G.w_off[l] = off; off += G.dims[l] * G.dims[l + 1];
+    G.b_off[l] = off; off += G.dims[l + 1];
+  }
+  const int g_params = off;
+  int rc;
+  if ((rc = tr_fill_net(e_net, t->e, off, "e_net"))) { delete t; return rc; }
+  if (t->e.dims[0] != xd || t->e.dims[t->e.L] != zd) { delete t; return fail(BGM_ERR_ARG, "bgm_bgmtrainer_create: e_net must map x_dim -> z_dim"); }
+  t->n_gen = off;
+  if ((rc = tr_fill_disc(dz_net, t->dz, zd, "dz_net")) || (rc = tr_fill_disc(dx_net, t->dx, xd, "dx_net"))) { delete t; return rc; }
+  t->dx_base = t->dz.n_params;
+  t->n_disc = t->dz.n_params + t->dx.n_params;
+  t->lr = lr; t->b1 = beta_1; t->b2 = beta_2;
+  int maxw = 2 * xd;
+  for (int l = 0; l <= G.L; ++l) maxw = std::max(maxw, G.dims[l]);
+  for (int l = 0; l <= t->e.L; ++l) maxw = std::max(maxw, t->e.dims[l]);
+  t->wm = (maxw + 3) / 4 * 4;
+  const bool gp_on = gamma != 0.f;
+  const int dgen = std::max(tr::disc_smem_floats(t->dz, false, true), tr::disc_smem_floats(t->dx, false, true));
+  const int ddis = std::max(tr::disc_smem_floats(t->dz, gp_on, true), tr::disc_smem_floats(t->dx, gp_on, true));
+  t->smem_gen = (4 * t->wm * tr::LD + 7 * zd * tr::LD + 2 * zd + 8 + 16 + 32 + dgen) * 4 + 64;
+  t->smem_disc = (2 * t->wm * tr::LD + 3 * xd * tr::LD + 5 * zd * tr::LD + zd + 4 + 32 + 4 + ddis) * 4 + 64;
+  int dev = 0, smem_max = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) { delete t; return fail(BGM_ERR_CUDA, std::string("bgm_bgmtrainer_create: ") + cudaGetErrorString(e)); }
+  if (t->smem_gen > smem_max - 1024 || t->smem_disc > smem_max - 1024) {
+    delete t;
+    return fail(BGM_ERR_NOMEM, "bgm_bgmtrainer_create: x_dim (with this gamma) too large for the single-CTA training kernels");
+  }
+  t->tape_floats = 2 * tr::net_tape_floats(G) + 2 * tr::net_tape_floats(t->e) + (2 * xd + 2 * zd) * tr::LD + 64;
+  const int n[2] = {t->n_gen, t->n_disc};
+  for (int gi = 0; gi < 2 && e == cudaSuccess; ++gi) {
+    const size_t bytes = sizeof(float) * (size_t)n[gi];
+    float** arrs[4] = {&t->theta[gi], &t->grad[gi], &t->m[gi], &t->v[gi]};
+    for (float** a : arrs) {
+      if (e == cudaSuccess) e = cudaMalloc(a, bytes);
+      if (e == cudaSuccess) e = cudaMemset(*a, 0, bytes);
+    }
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&t->tape, sizeof(float) * (size_t)t->tape_floats);
+  if (e == cudaSuccess) e = cudaMalloc(&t->moving, sizeof(float) * 2 * zd);
+  if (e == cudaSuccess) {
+    // pack group 0: gamma, beta, hidden..., [W_mean | W_var], [b_mean | b_var], then e
+    std::vector<float> host(t->n_gen, 0.f);
+    memcpy(host.data() + t->vg.gamma_off, g->bn, sizeof(float) * zd);
+    memcpy(host.data() + t->vg.beta_off, g->bn + zd, sizeof(float) * zd);
+    const float* p = g->hidden_params;
+    for (int l = 0; l < nh; ++l) {
+      const int cnt = G.dims[l] * G.dims[l + 1] + G.dims[l + 1];
+      memcpy(host.data() + G.w_off[l], p, sizeof(float) * cnt);
+      p += cnt;
+    }
+    const int last = G.dims[nh];
+    for (int k = 0; k < last; ++k)
+      for (int c = 0; c < xd; ++c) {
+        host[G.w_off[nh] + (size_t)k * 2 * xd + c] = g->mean_params[(size_t)k * xd + c];
+        host[G.w_off[nh] + (size_t)k * 2 * xd + xd + c] = g->var_params[(size_t)k * xd + c];
+      }
+    for (int c = 0; c < xd; ++c) {
+      host[G.b_off[nh] + c] = g->mean_params[(size_t)last * xd + c];
+      host[G.b_off[nh] + xd + c] = g->var_params[(size_t)last * xd + c];
+    }
+    memcpy(host.data() + g_params, e_net->params, sizeof(float) * tr_net_params(e_net));
+    e = cudaMemcpy(t->theta[0], host.data(), sizeof(float) * t->n_gen, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t->moving, g->bn + 2 * zd, sizeof(float) * 2 * zd, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(t->theta[1], dz_net->params, sizeof(float) * t->dz.n_params, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess)
+    e = cudaMemcpy(t->theta[1] + t->dx_base, dx_net->params, sizeof(float) * t->dx.n_params, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    bgm_trainer_destroy(t);
+    return fail(BGM_ERR_CUDA, std::string("bgm_bgmtrainer_create: ") + cudaGetErrorString(e));
+  }
+  *out = t;
+  return 0;
+}
+
+int bgm_trainer_bn_moving(bgm_trainer* t, float* host_inout, int set) {
+  using namespace bgm;
+  if (!t || t->kind != 1 || !host_inout) return fail(BGM_ERR_ARG, "bgm_trainer_bn_moving: needs a BGM trainer and a buffer");
+  if (set) BGM_CUDA_OK(cudaMemcpy(t->moving, host_inout, sizeof(float) * 2 * t->zd, cudaMemcpyHostToDevice));
+  else BGM_CUDA_OK(cudaMemcpy(host_inout, t->moving, sizeof(float) * 2 * t->zd, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int bgm_bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* x_dev, int bs, float eps_z, float eps_x,
+                            const float* noise_dev, float* losses_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 1 || !z_dev || !x_dev || !noise_dev || !losses_dev)
+    return fail(BGM_ERR_ARG, "bgm_bgm_train_disc_grad: null argument / not a BGM trainer");
+  if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_bgm_train_disc_grad: batch size must be in [2, 32]");
+  tr::BgmDiscArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = t->vg; A.e = t->e; A.dz = t->dz; A.dx = t->dx; A.dx_base = t->dx_base;
+  A.zd = t->zd; A.xd = t->xd; A.bs = bs; A.gamma = t->gamma; A.eps_z = eps_z; A.eps_x = eps_x;
+  A.theta = t->theta[0]; A.theta_d = t->theta[1]; A.grad_d = t->grad[1]; A.moving = t->moving;
+  A.z = z_dev; A.x = x_dev; A.noise = noise_dev; A.losses = losses_dev; A.wm = t->wm;
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::bgm_disc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_disc));
+  tr::bgm_disc_grad_kernel<<<1, tr::NTH, t->smem_disc, (cudaStream_t)stream>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* x_dev, int bs, const float* noise1_dev,
+                           const float* noise2_dev, float* losses_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 1 || !z_dev || !x_dev || !noise1_dev || !noise2_dev || !losses_dev)
+    return fail(BGM_ERR_ARG, "bgm_bgm_train_gen_grad: null argument / not a BGM trainer");
+  if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_bgm_train_gen_grad: batch size must be in [2, 32]");
+  tr::BgmGenArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = t->vg; A.e = t->e; A.dz = t->dz; A.dx = t->dx; A.dx_base = t->dx_base;
+  A.zd = t->zd; A.xd = t->xd; A.bs = bs; A.alpha = t->alpha;
+  A.theta = t->theta[0]; A.theta_d = t->theta[1]; A.grad = t->grad[0]; A.tape = t->tape; A.moving = t->moving;
+  A.z = z_dev; A.x = x_dev; A.noise1 = noise1_dev; A.noise2 = noise2_dev; A.losses = losses_dev; A.wm = t->wm;
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::bgm_gen_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_gen));
+  tr::bgm_gen_grad_kernel<<<1, tr::NTH, t->smem_gen, (cudaStream_t)stream>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 
 int bgm_trainer_create(bgm_trainer** out, const int z_dims[4], int v_dim, int binary_treatment, int use_z_rec,
                        const bgm_net_desc* g_net, const bgm_net_desc* e_net, const bgm_net_desc* f_net,
@@ -74,25 +249,9 @@ int bgm_trainer_create(bgm_trainer** out, const int z_dims[4], int v_dim, int bi
             t->h.dims[0] == z_dims[0] + z_dims[2] && t->h.dims[t->h.L] == 2;
   if (!ok) { delete t; return fail(BGM_ERR_ARG, "bgm_trainer_create: net shapes do not match z_dims / v_dim (causalbgm/base.py:74-81)"); }
   // discriminator
-  if (dz_net->n_hidden < 1 || dz_net->n_hidden >= tr::MAXL || !dz_net->dims || !dz_net->params ||
-      dz_net->dims[0] != zd || dz_net->dims[dz_net->n_hidden + 1] != 1) {
-    delete t;
-    return fail(BGM_ERR_ARG, "bgm_trainer_create: dz_net must map sum(z_dims) -> 1 with 1..7 hidden blocks");
-  }
+  if ((rc = tr_fill_disc(dz_net, t->dz, zd, "dz_net"))) { delete t; return rc; }
   tr::Disc& D = t->dz;
-  D.L = dz_net->n_hidden;
-  int doff = 0;
-  for (int l = 0; l <= D.L + 1; ++l) D.dims[l] = dz_net->dims[l];
-  for (int l = 0; l <= D.L; ++l) {
-    D.w_off[l] = doff; doff += D.dims[l] * D.dims[l + 1];
-    D.b_off[l] = doff; doff += D.dims[l + 1];
-    if (l < D.L) {
-      D.g_off[l] = doff; doff += D.dims[l + 1];
-      D.be_off[l] = doff; doff += D.dims[l + 1];
-    }
-  }
-  D.n_params = doff;
-  t->n_disc = doff;
+  t->n_disc = D.n_params;
   t->lr = lr; t->b1 = beta_1; t->b2 = beta_2;
   int maxw = v_dim + 1;
   for (const tr::Net* n : {&t->g, &t->e, &t->f, &t->h})
@@ -153,6 +312,7 @@ void bgm_trainer_destroy(bgm_trainer* t) {
     if (t->v[g]) cudaFree(t->v[g]);
   }
   if (t->tape) cudaFree(t->tape);
+  if (t->moving) cudaFree(t->moving);
   delete t;
 }
 
@@ -184,7 +344,7 @@ int bgm_trainer_set_params(bgm_trainer* t, int group, const float* host_in) {
 int bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, int bs, float epsilon,
                         float gp_weight, float* losses_dev, void* stream) {
   using namespace bgm;
-  if (!t || !z_dev || !v_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_train_disc_grad: null argument");
+  if (!t || t->kind != 0 || !z_dev || !v_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_train_disc_grad: null argument / not a CausalBGM trainer");
   if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_train_disc_grad: batch size must be in [2, 32]");
   tr::DiscArgs A;
   memset(&A, 0, sizeof(A));
@@ -200,8 +360,8 @@ int bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, 
 int bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, const float* x_dev,
                        const float* y_dev, int bs, float* losses_dev, void* stream) {
   using namespace bgm;
-  if (!t || !z_dev || !v_dev || !x_dev || !y_dev || !losses_dev)
-    return fail(BGM_ERR_ARG, "bgm_train_gen_grad: null argument");
+  if (!t || t->kind != 0 || !z_dev || !v_dev || !x_dev || !y_dev || !losses_dev)
+    return fail(BGM_ERR_ARG, "bgm_train_gen_grad: null argument / not a CausalBGM trainer");
   if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_train_gen_grad: batch size must be in [2, 32]");
   tr::GenArgs A;
   memset(&A, 0, sizeof(A));

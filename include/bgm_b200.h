@@ -280,6 +280,29 @@ int bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, 
  * l2_loss_y, g_e_loss (:377).  x_dev, y_dev: (bs). */
 int bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, const float* x_dev,
                        const float* y_dev, int bs, float* losses_dev, void* stream);
+/* ---- BGM flavour of the EGM steps (bgm/base.py:190-291) ---- */
+/* Generator = BaseVariationalNet in TRAINING mode (input BatchNormalization on batch
+ * statistics, moving statistics updated with momentum .99 on every call), encoder e_net,
+ * discriminators dz_net (latent) and dx_net (data); LSGAN targets .9/.1; reg weight `alpha`
+ * (:279), gradient-penalty weight `gamma` (:236; 0 skips that path).  Parameter group 0 on
+ * the device: g = [gamma | beta | hidden kernel,bias ... | [W_mean|W_var] | [b_mean|b_var]],
+ * then e; group 1 = [dz | dx].  Adam of the reference: beta = (.5, .9) (bgm/base.py:83-85). */
+int bgm_bgmtrainer_create(bgm_trainer** out, const bgm_varnet_desc* g_net, const bgm_net_desc* e_net,
+                          const bgm_disc_desc* dz_net, const bgm_disc_desc* dx_net, float lr, float beta_1,
+                          float beta_2, float alpha, float gamma);
+/* BN moving mean | variance (2*z_dim floats, HOST): read (set == 0) or overwrite. */
+int bgm_trainer_bn_moving(bgm_trainer* t, float* host_inout, int set);
+/* BGM.train_disc_step gradients (:190-240) into group 1.  noise_dev: (bs,x_dim) N(0,1)
+ * draws of reparameterize (:208); eps_z / eps_x: the U(0,1) draws of :199-200;
+ * losses_dev[3] = dz_loss, dx_loss, d_loss. */
+int bgm_bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* x_dev, int bs, float eps_z, float eps_x,
+                            const float* noise_dev, float* losses_dev, void* stream);
+/* BGM.train_gen_step gradients (:247-285) into group 0.  noise1/2_dev: the N(0,1) draws of the
+ * two reparameterize calls (:259, :267); losses_dev[6] = g_loss_adv, e_loss_adv, l2_loss_z,
+ * l2_loss_x, reg_loss, g_e_loss (:291). */
+int bgm_bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* x_dev, int bs, const float* noise1_dev,
+                           const float* noise2_dev, float* losses_dev, void* stream);
+
 /* One Keras-Adam step of the group on (grad_scale * gradient buffer); grad_scale is
  * 1/world_size after a summing all-reduce, 1 on a single GPU. */
 int bgm_train_adam(bgm_trainer* t, int group, float grad_scale, void* stream);

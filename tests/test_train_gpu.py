@@ -158,3 +158,110 @@ def test_egm_init_follows_the_reference_index_stream():
     for name in ('g', 'e', 'f', 'h'):
         for got, want in zip(w[name], train.flat_params(tr.nets[name])):
             assert np.abs(got - want).max() <= 1e-3
+
+
+# ------------------------------------------------------------------ BGM (a14) --
+from oracle import train_bgm
+from helpers import bgm_params, bgm_oracle_net, bgm_product_model
+
+
+def make_bgm(x_dim=100, z_dim=10, bs=32, seed=0, **extra):
+    params = bgm_params(x_dim, z_dim, **extra)
+    g = bgm_oracle_net(params, seed=31, bn_random=True)
+    rs = np.random.RandomState(seed)
+    e = onets.init_mlp(rs, [x_dim] + params['e_units'] + [z_dim], 0.1)
+    dz = onets.init_discriminator(rs, z_dim, params['dz_units'])
+    dx = onets.init_discriminator(rs, x_dim, params['dx_units'])
+    for d in (dz, dx):
+        for bn in d['bns']:
+            bn['gamma'] = (1 + 0.1 * rs.standard_normal(bn['gamma'].shape)).astype(np.float32)
+            bn['beta'] = (0.1 * rs.standard_normal(bn['beta'].shape)).astype(np.float32)
+    m = bgm_product_model(params, g)
+    m.set_weights(e=[a for W, b in e for a in (W, b)], dz=train.disc_flat_params(dz), dx=train.disc_flat_params(dx))
+    z = rs.standard_normal((bs, z_dim)).astype(np.float32)
+    x = rs.standard_normal((bs, x_dim)).astype(np.float32)
+    n1 = rs.standard_normal((bs, x_dim)).astype(np.float32)
+    n2 = rs.standard_normal((bs, x_dim)).astype(np.float32)
+    return params, g, e, dz, dx, m, z, x, n1, n2
+
+
+def bgm_gen_device_layout(grads, g, x_dim):
+    """oracle (Keras order) gradient list -> tensors in the device layout of group 0."""
+    nh = len(g['hidden'])
+    gl = grads[:2 + 2 * nh + 4]
+    el = grads[2 + 2 * nh + 4:]
+    out = gl[:2 + 2 * nh]
+    wm, bm, wv, bv = gl[2 + 2 * nh:]
+    out += [np.concatenate([wm, wv], axis=1), np.concatenate([bm, bv])]
+    return out + el
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(x_dim=10, z_dim=3, bs=17), dict(x_dim=4, z_dim=2, alpha=0.1),
+                                dict(x_dim=33, z_dim=5, g_units=(16, 16), e_units=[16, 16], alpha=0.5)])
+def test_bgm_gen_step_gradients(kw):
+    params, g, e, dz, dx, m, z, x, n1, n2 = make_bgm(**kw)
+    want_losses, want, stats = train_bgm.gen_step(params, g, e, dz, dx, z, x, n1, n2)
+    losses, flat = m.gradients('gen', z, x, noise=n1, noise2=n2)
+    np.testing.assert_allclose(losses, want_losses, rtol=2e-4, atol=1e-6)
+    want_dev = bgm_gen_device_layout(want, g, params['x_dim'])
+    check_grads(split_like(flat, want_dev), want_dev)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(x_dim=10, z_dim=3, bs=17), dict(x_dim=20, z_dim=4, gamma=1.0),
+                                dict(x_dim=4, z_dim=2, gamma=0.5, bs=12)])
+def test_bgm_disc_step_gradients(kw):
+    params, g, e, dz, dx, m, z, x, n1, n2 = make_bgm(**kw)
+    want_losses, want, stats = train_bgm.disc_step(params, g, e, dz, dx, z, x, 0.3, 0.7, n1)
+    losses, flat = m.gradients('disc', z, x, eps_z=0.3, eps_x=0.7, noise=n1)
+    np.testing.assert_allclose(losses, want_losses, rtol=2e-4, atol=2e-6)
+    check_grads(split_like(flat, want), want)
+
+
+def test_bgm_steps_update_weights_and_moving_statistics():
+    params, g, e, dz, dx, m, z, x, n1, n2 = make_bgm(x_dim=12, z_dim=3, lr=1e-3)
+    import copy
+    g0 = copy.deepcopy(g)
+    gen_opt, d_opt = train.Adam(1e-3, 0.5, 0.9), train.Adam(1e-3, 0.5, 0.9)
+    for k in range(3):
+        _, grads, stats = train_bgm.disc_step(params, g, e, dz, dx, z, x, 0.3, 0.7, n1)
+        d_opt.apply(train.disc_flat_params(dz) + train.disc_flat_params(dx), grads)
+        train_bgm.update_moving(g, stats)
+        m.train_disc_step(z, x, eps_z=0.3, eps_x=0.7, noise=n1)
+        _, grads, stats = train_bgm.gen_step(params, g, e, dz, dx, z, x, n1, n2)
+        gen_opt.apply(train_bgm.g_flat_params(g) + train.flat_params(e), grads)
+        train_bgm.update_moving(g, stats)
+        m.train_gen_step(z, x, noise1=n1, noise2=n2)
+    w = m.get_weights()
+    # Keras order of g: gamma, beta, moving_mean, moving_var, hidden..., mean, var
+    np.testing.assert_allclose(w['g'][2], g['bn']['mean'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(w['g'][3], g['bn']['var'], rtol=1e-4, atol=1e-5)
+    assert not np.allclose(w['g'][2], g0['bn']['mean'])
+    want_g = [g['bn']['gamma'], g['bn']['beta']] + [a for W, b in g['hidden'] for a in (W, b)] + \
+        list(g['mean']) + list(g['var'])
+    got_g = w['g'][:2] + w['g'][4:]
+    for a, b in zip(got_g, want_g):
+        assert np.abs(a - b).max() <= 6 * 1e-3 * 0.5     # k*lr bound; most entries agree to 1e-5
+        assert np.median(np.abs(a - b)) <= 2e-5
+    for a, b in zip(w['e'], train.flat_params(e)):
+        assert np.median(np.abs(a - b)) <= 2e-5
+
+
+def test_bgm_egm_init_runs_and_keeps_the_reference_batch_stream():
+    params = bgm_params(8, 2, lr=1e-3)
+    g = bgm_oracle_net(params, seed=31)
+    m = bgm_product_model(params, g)
+    data = np.random.RandomState(3).standard_normal((200, 8)).astype(np.float32)
+    from bayesgm_b200.datasets import Base_sampler
+    np.random.seed(5)
+    dl, gl = m.egm_init(data, egm_n_iter=4, batch_size=16, egm_batches_per_eval=2, verbose=0)
+    after = np.random.get_state()[1][:4].copy()
+    assert np.isfinite(dl).all() and np.isfinite(gl).all()
+    # the same host-RNG consumption as the reference loop: Base_sampler ctor, then per iteration
+    # (g_d_freq + 1) x (next_batch, get_batch)
+    np.random.seed(5)
+    s = Base_sampler(x=data, y=data, v=data, batch_size=16, normalize=False)
+    for it in range(5):
+        for _ in range(params['g_d_freq'] + 1):
+            s.next_batch()
+            m.z_sampler.get_batch(16)
+    np.testing.assert_array_equal(np.random.get_state()[1][:4], after)
