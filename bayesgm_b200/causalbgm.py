@@ -443,12 +443,123 @@ class CausalBGM(object):
                   _lib.ptr(eps), _lib.ptr(u), _lib.stream_ptr())
         return dict(z0=z0.cpu().numpy(), eps=eps.cpu().numpy(), u=u.cpu().numpy())
 
-    # ------------------------------------------------- not on the hot path yet
+    # ------------------------------------------------- fit: EGM + iterative phase
+    @staticmethod
+    def _save_data(fname, data, delimiter='\t'):
+        """utils/data_io.py:8-31."""
+        if fname.endswith('.npy'):
+            np.save(fname, data)
+        elif fname.endswith('.txt') or fname.endswith('.csv'):
+            np.savetxt(fname, data, fmt='%.6f', delimiter=delimiter)
+        else:
+            raise ValueError("Wrong saving format, please specify either .npy, .txt, or .csv")
+
+    @property
+    def data_z(self):
+        """The latent table of `fit` (:484) as a host array."""
+        z = getattr(self, '_data_z', None)
+        return None if z is None else z.cpu().numpy()
+
+    def _sigmas(self):
+        return [float(self._p[k]) if k in self._p else -1.0 for k in ('sigma_v', 'sigma_x', 'sigma_y')]
+
+    def evaluate(self, data, data_z=None, nb_intervals=200):
+        """causalbgm/base.py:534-570 -> (causal_pre, mse_x, mse_y, mse_v): ITE (n,1) for a binary
+        treatment, else the ADRF on `nb_intervals` doses between the 5th and 95th percentile of x."""
+        torch, x, y, v, ldv, n = self._stage(data)
+        p, zd = self._p['v_dim'], sum(self._p['z_dims'])
+        vc = v[:, :p].contiguous() if ldv != p else v
+        tr = self._device_trainer()
+        sums = torch.zeros(3, dtype=torch.float64, device='cuda')
+        if data_z is None:
+            z = torch.empty((n, zd), dtype=torch.float32, device='cuda')
+            _lib.call("bgm_causal_evaluate", tr, None, _lib.ptr(x), _lib.ptr(y), _lib.ptr(vc), n, _lib.ptr(sums),
+                      _lib.ptr(z), _lib.stream_ptr())
+        else:
+            z = self._to_device(data_z, torch)
+            _lib.call("bgm_causal_evaluate", tr, _lib.ptr(z), _lib.ptr(x), _lib.ptr(y), _lib.ptr(vc), n,
+                      _lib.ptr(sums), None, _lib.stream_ptr())
+        s = sums.cpu().numpy()
+        mse_v, mse_x, mse_y = np.float32(s[0] / (n * p)), np.float32(s[1] / n), np.float32(s[2] / n)
+        zs = z.reshape(1, n, zd)
+        if self._p['binary_treatment']:
+            ite = self._effect_device(zs, 1, n, None, False, 0, 0)
+            return ite.reshape(n, 1).cpu().numpy(), mse_x, mse_y, mse_v
+        xs = np.sort(np.asarray(x.cpu().numpy()).ravel())                       # tfp.stats.percentile, 'nearest'
+        x_min = xs[int(np.round((n - 1) * 0.05))]
+        x_max = xs[int(np.round((n - 1) * 0.95))]
+        x_values = np.linspace(x_min, x_max, nb_intervals).astype(np.float32)
+        adrf = self._effect_device(zs, 1, n, x_values, False, 0, 0)
+        return (adrf[:, 0] / float(n)).float().cpu().numpy(), mse_x, mse_y, mse_v
+
     def fit(self, data, epochs=100, epochs_per_eval=5, batch_size=32, startoff=0, use_egm_init=True,
             egm_n_iter=30000, egm_batches_per_eval=500, save_format='txt', verbose=1):
-        raise NotImplementedError(
-            "bayesgm_b200: the training path (egm_init / iterative updates, causalbgm/base.py:156-532) "
-            "has no sm_100a kernels yet; load trained weights with set_weights().")
+        """causalbgm/base.py:434-532: optional EGM warm-start, latent table from e(V) (or N(0,1)),
+        then `epochs+1` epochs of mini-batch updates of g, h, f and of the latent rows (dense
+        Keras-Adam sweep), evaluating every `epochs_per_eval` epochs.  Data, latent table and all
+        optimizer state stay on the device; the epoch permutation comes from NumPy's global
+        generator (`np.random.choice(n, n, replace=False)`, :489) -- bit-exact index stream."""
+        torch = _lib.require_cuda()
+        data_x, data_y, data_v = data
+        n = len(data_x)
+        p, zd = self._p['v_dim'], sum(self._p['z_dims'])
+        bs = int(batch_size)
+        if bs > 32:
+            raise NotImplementedError("bayesgm_b200: the training kernels take mini-batches of at most 32 rows")
+        if self._p['save_res']:
+            with open('{}/params.txt'.format(self.save_dir), 'w') as f_params:
+                f_params.write(str(self.params))
+        xd = self._to_device(data_x, torch).reshape(-1).contiguous()
+        yd = self._to_device(data_y, torch).reshape(-1).contiguous()
+        vd = self._to_device(data_v, torch).contiguous()
+        tr = self._device_trainer()
+        st = _lib.stream_ptr()
+        if use_egm_init:
+            self.egm_init(data, egm_n_iter=egm_n_iter, egm_batches_per_eval=egm_batches_per_eval,
+                          batch_size=batch_size, verbose=verbose)
+            if verbose:
+                print('Initialize latent variables Z with e(V)...')
+            z = torch.empty((n, zd), dtype=torch.float32, device='cuda')                    # :479
+            sums = torch.zeros(3, dtype=torch.float64, device='cuda')
+            _lib.call("bgm_causal_evaluate", tr, None, _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), n, _lib.ptr(sums),
+                      _lib.ptr(z), st)
+        else:
+            if verbose:
+                print('Random initialization of latent variables Z...')
+            z = torch.from_numpy(np.random.normal(0, 1, size=(n, zd)).astype('float32')).cuda()   # :482
+        self._data_z = z
+        m_z, v_z = torch.zeros_like(z), torch.zeros_like(z)
+        slot = torch.full((n,), -1, dtype=torch.int32, device='cuda')
+        sig = self._sigmas()
+        _lib.call("bgm_trainer_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']), sig[0], sig[1], sig[2])
+        nl = torch.zeros(6, dtype=torch.float32, device='cuda')
+        zl = torch.zeros(1, dtype=torch.float32, device='cuda')
+        best_loss = np.inf
+        if verbose:
+            print('Iterative Updating Starts ...')
+        for epoch in range(int(epochs) + 1):
+            sample_idx = np.random.choice(n, n, replace=False)                               # :489
+            idx_d = torch.from_numpy(sample_idx.astype(np.int32)).cuda()
+            base = idx_d.data_ptr()
+            for i in range(0, n, bs):
+                b = min(bs, n - i)
+                ip = C.c_void_p(base + 4 * i)
+                _lib.call("bgm_train_iter_nets", tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, 1,
+                          1.0, _lib.ptr(nl), st)                                             # :500-502
+                _lib.call("bgm_train_iter_latent", tr, _lib.ptr(z), _lib.ptr(m_z), _lib.ptr(v_z), _lib.ptr(slot), n,
+                          _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, _lib.ptr(zl), st)     # :505
+            self._trainer_dirty = True
+            if epoch % epochs_per_eval == 0:                                                 # :517-532
+                causal_pre, mse_x, mse_y, mse_v = self.evaluate(data=(xd, yd, vd), data_z=z)
+                if verbose:
+                    print('Epoch [%d/%d]: MSE_x: %.4f, MSE_y: %.4f, MSE_v: %.4f\n' % (epoch, epochs, mse_x, mse_y, mse_v))
+                if epoch >= startoff and mse_y < best_loss:
+                    best_loss = mse_y
+                    self.best_causal_pre = causal_pre
+                    self.best_epoch = epoch
+                if self._p['save_res']:
+                    self._save_data('{}/causal_pre_at_{}.{}'.format(self.save_dir, epoch, save_format), causal_pre)
+        self.last_iter_losses = tuple(float(a) for a in nl.cpu().numpy()) + (float(zl.cpu()[0]),)
 
     # ------------------------------------------------------------ EGM training
     def _grad_tensor(self, group):

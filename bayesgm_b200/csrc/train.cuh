@@ -995,3 +995,327 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int ld, const 
 
 }  // namespace tr
 }  // namespace bgm
+
+// ======================= iterative phase of CausalBGM.fit (N2) ====================
+namespace bgm {
+namespace tr {
+
+struct IterArgs {
+  Net g, f, h;
+  int z_dims[4];
+  int zd, p, binary, bs;
+  float s2v, s2x, s2y;        // fixed variances (sigma_* keys), < 0: learned softplus head
+  const float* theta;
+  float* grad;                // gen-group layout; g, f, h ranges are written
+  float* tape;
+  const float* zt;            // latent table (n, zd)
+  const float *x, *y, *v;     // full data (n), (n), (n, p)
+  const int* idx;             // (bs) rows of this mini-batch
+  float* losses;              // NET step: [6] loss_v, mse_v, loss_x, mse_x, loss_y, mse_y ; LATENT step: [1]
+  float* gz_out;              // LATENT step: (bs, zd) d loss_postrior_z / d z rows
+  int wm;
+};
+
+// gather rows idx[r] of a row-major (n, dim) array into a [dim][LD] column matrix
+__device__ void gather_cols(const float* __restrict__ src, int ld, const int* __restrict__ idx, int ncols, int bs,
+                            float* dst) {
+  for (int i = threadIdx.x; i < ncols * 32; i += NTH) {
+    const int r = i / ncols, c = i - r * ncols;
+    dst[c * LD + r] = r < bs ? src[(size_t)idx[r] * ld + c] : 0.f;
+  }
+}
+
+// Gaussian negative log-likelihood head (causalbgm/base.py:166-169 and the like):
+// out rows [0,nd) = mu, row nd = raw variance head; tgt [nd][LD].  Writes the seeds
+// d mean_r(loss_r) / d out in place; returns (thread 0 .. all threads via shared) nothing --
+// partial sums go to red[slot] (loss) and red[slot+1] (sum of squared errors).
+__device__ void nll_seed(float* out, const float* tgt, int nd, int bs, float s2_fixed, float* red, int slot,
+                         float* rowbuf) {
+  const float inv_bs = 1.f / (float)bs;
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    float sse = 0.f;
+    if (r < bs)
+      for (int c = 0; c < nd; ++c) { const float d = tgt[c * LD + r] - out[c * LD + r]; sse = fmaf(d, d, sse); }
+    const float raw = out[nd * LD + r];
+    const float s2 = s2_fixed >= 0.f ? s2_fixed : softplus_f(raw) + 1e-6f;
+    float loss = r < bs ? sse / (2.f * s2) + (float)nd * logf(s2) / 2.f : 0.f;
+    rowbuf[r] = r < bs ? 1.f / s2 : 0.f;                         // 1/s2 per row for the mu seeds
+    const float draw = (r < bs && s2_fixed < 0.f)
+                           ? (-sse / (2.f * s2 * s2) + (float)nd / (2.f * s2)) * sigmoid_f(raw) * inv_bs : 0.f;
+    out[nd * LD + r] = draw;
+    float sl = loss, ss = sse;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sl += __shfl_xor_sync(0xffffffffu, sl, o);
+      ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (r == 0) { red[slot] = sl; red[slot + 1] = ss; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nd * 32; i += NTH) {
+    const int c = i >> 5, r = i & 31;
+    out[c * LD + r] = r < bs ? -(tgt[c * LD + r] - out[c * LD + r]) * rowbuf[r] * inv_bs : 0.f;
+  }
+  __syncthreads();
+}
+// sigmoid cross-entropy head (:196): out row 0 = logit; row 1 (unused head) gets a zero seed
+__device__ void bce_seed(float* out, const float* tgt, int bs, float* red, int slot) {
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    const float lg = out[r], xv = tgt[r];
+    float l = r < bs ? fmaxf(lg, 0.f) - lg * xv + log1pf(expf(-fabsf(lg))) : 0.f;
+    out[r] = r < bs ? (sigmoid_f(lg) - xv) / (float)bs : 0.f;
+    out[LD + r] = 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if (r == 0) { red[slot] = l; red[slot + 1] = l; }
+  }
+  __syncthreads();
+}
+
+// update_g_net / update_h_net / update_f_net gradients (:156-243), one launch.
+// mode 0: parameter gradients of the three nets.  mode 1: update_latent_variable_sgd
+// (:246-295): gradient of mean_r(loss_pv + loss_px + loss_py + |z|^2/2) w.r.t. the batch rows of z.
+template <int MODE>
+__global__ void __launch_bounds__(NTH, 1) iter_grad_kernel(const __grid_constant__ IterArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  const int bs = A.bs, p = A.p, zd = A.zd;
+  const float inv_bs = 1.f / (float)bs;
+  float* bufA = sm;
+  float* bufB = bufA + A.wm * LD;
+  float* bufC = bufB + A.wm * LD;
+  float* bufD = bufC + A.wm * LD;
+  float* zmat = bufD + A.wm * LD;       // [zd][LD]
+  float* gz = zmat + zd * LD;           // [zd][LD]
+  float* xy = gz + zd * LD;             // [2][LD]
+  float* fin = xy + 2 * LD;             // [zd+1][LD]
+  float* red = fin + (zd + 1) * LD;     // [16]
+  float* rowbuf = red + 16;             // [32]
+  const float* th = A.theta;
+  float* T_g = A.tape;
+  float* T_f = T_g + net_tape_floats(A.g);
+  float* T_h = T_f + net_tape_floats(A.f);
+  float* T_v = T_h + net_tape_floats(A.h);
+  const int d0 = A.z_dims[0], d1 = A.z_dims[1], d2 = A.z_dims[2];
+  gather_cols(A.zt, zd, A.idx, zd, bs, zmat);
+  gather_cols(A.x, 1, A.idx, 1, bs, xy);
+  gather_cols(A.y, 1, A.idx, 1, bs, xy + LD);
+  gather_cols(A.v, p, A.idx, p, bs, bufC);
+  if (threadIdx.x < 16) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  copy_mat(bufC, T_v, p);
+  for (int i = threadIdx.x; i < zd * (LD / 4); i += NTH) st4(gz + i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+  // ---- g: covariates ----
+  {
+    float* go = mlp_forward(A.g, th, zmat, bufA, bufB, T_g);
+    nll_seed(go, bufC, p, bs, A.s2v, red, 0, rowbuf);
+    float* other = go == bufA ? bufB : bufA;
+    if (MODE == 0) mlp_backward(A.g, th, A.grad, zmat, T_g, go, other, go, bufD, nullptr, false);
+    else {
+      // input gradient only: reuse mlp_backward's structure without the parameter part
+      int toff[MAXL]; int t = 0;
+      for (int l = 0; l < A.g.L; ++l) { toff[l] = t; t += A.g.dims[l + 1] * LD; }
+      float* g = go;
+      for (int l = A.g.L - 1; l >= 0; --l) {
+        float* o = l == 0 ? bufD : (g == other ? go : other);
+        const float* xprev = l == 0 ? nullptr : T_g + toff[l - 1];
+        if (xprev) { copy_mat(xprev, bufC, A.g.dims[l]); __syncthreads(); }
+        dense_bwd_x(th + A.g.w_off[l], A.g.dims[l], A.g.dims[l + 1], g, o, xprev ? bufC : nullptr, false);
+        g = o;
+      }
+      for (int i = threadIdx.x; i < zd * 32; i += NTH) gz[(i >> 5) * LD + (i & 31)] += bufD[(i >> 5) * LD + (i & 31)];
+      __syncthreads();
+    }
+  }
+  auto input_grad = [&](const Net& n, const float* tape, float* seed, float* other, float* out) {
+    int toff[MAXL]; int t = 0;
+    for (int l = 0; l < n.L; ++l) { toff[l] = t; t += n.dims[l + 1] * LD; }
+    float* g = seed;
+    for (int l = n.L - 1; l >= 0; --l) {
+      float* o = l == 0 ? out : (g == other ? seed : other);
+      const float* xprev = l == 0 ? nullptr : tape + toff[l - 1];
+      if (xprev) { copy_mat(xprev, bufC, n.dims[l]); __syncthreads(); }
+      dense_bwd_x(th + n.w_off[l], n.dims[l], n.dims[l + 1], g, o, xprev ? bufC : nullptr, false);
+      g = o;
+    }
+  };
+  // ---- h: treatment ([z0, z2]) ----
+  {
+    copy_mat(zmat, fin, d0);
+    copy_mat(zmat + (d0 + d1) * LD, fin + d0 * LD, d2);
+    __syncthreads();
+    float* ho = mlp_forward(A.h, th, fin, bufA, bufB, T_h);
+    if (A.binary) bce_seed(ho, xy, bs, red, 2);
+    else nll_seed(ho, xy, 1, bs, A.s2x, red, 2, rowbuf);
+    float* other = ho == bufA ? bufB : bufA;
+    if (MODE == 0) mlp_backward(A.h, th, A.grad, fin, T_h, ho, other, ho, bufC, nullptr, false);
+    else {
+      input_grad(A.h, T_h, ho, other, bufD);
+      for (int i = threadIdx.x; i < d0 * 32; i += NTH) gz[(i >> 5) * LD + (i & 31)] += bufD[(i >> 5) * LD + (i & 31)];
+      for (int i = threadIdx.x; i < d2 * 32; i += NTH)
+        gz[(d0 + d1 + (i >> 5)) * LD + (i & 31)] += bufD[(d0 + (i >> 5)) * LD + (i & 31)];
+      __syncthreads();
+    }
+  }
+  // ---- f: outcome ([z0, z1, x]) ----
+  {
+    copy_mat(zmat, fin, d0 + d1);
+    copy_mat(xy, fin + (d0 + d1) * LD, 1);
+    __syncthreads();
+    float* fo = mlp_forward(A.f, th, fin, bufA, bufB, T_f);
+    nll_seed(fo, xy + LD, 1, bs, A.s2y, red, 4, rowbuf);
+    float* other = fo == bufA ? bufB : bufA;
+    if (MODE == 0) mlp_backward(A.f, th, A.grad, fin, T_f, fo, other, fo, bufC, nullptr, false);
+    else {
+      input_grad(A.f, T_f, fo, other, bufD);
+      for (int i = threadIdx.x; i < (d0 + d1) * 32; i += NTH) gz[(i >> 5) * LD + (i & 31)] += bufD[(i >> 5) * LD + (i & 31)];
+      __syncthreads();
+    }
+  }
+  if (MODE == 0) {
+    if (threadIdx.x == 0) {
+      A.losses[0] = red[0] * inv_bs; A.losses[1] = red[1] / (float)(bs * p);
+      A.losses[2] = red[2] * inv_bs; A.losses[3] = red[3] * inv_bs;
+      A.losses[4] = red[4] * inv_bs; A.losses[5] = red[5] * inv_bs;
+    }
+  } else {
+    // prior |z|^2/2 (:288-289): gradient z / bs ; write the batch-row gradients
+    float pr = 0.f;
+    for (int i = threadIdx.x; i < zd * 32; i += NTH) {
+      const int d = i >> 5, r = i & 31;
+      if (r < bs) {
+        const float z = zmat[d * LD + r];
+        pr = fmaf(z, z, pr);
+        A.gz_out[(size_t)r * zd + d] = gz[d * LD + r] + z * inv_bs;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(red + 6, pr);
+    __syncthreads();
+    if (threadIdx.x == 0) A.losses[0] = (red[0] + red[2] + red[4] + 0.5f * red[6]) * inv_bs;   // :291
+  }
+}
+
+// Keras Adam on a tf.gather'ed variable (TF 2.10 optimizer_v2 _resource_apply_sparse, SURVEY
+// A.4): m and v of the WHOLE table decay, the batch rows receive (1-beta) g / (1-beta) g^2,
+// and every row moves by lr_t * m / (sqrt(v) + eps).  slot[row] = position of the row in
+// this mini-batch or -1 (set by latent_mark_kernel, reset here).  HBM-bound: 6 floats of
+// traffic per table element.
+__global__ void latent_mark_kernel(const int* __restrict__ idx, int bs, int* __restrict__ slot) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < bs) slot[idx[r]] = r;
+}
+__global__ void latent_adam_sweep_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
+                                         int* __restrict__ slot, const float* __restrict__ gz, long long n, int zd,
+                                         float lr_t, float b1, float b2, float eps) {
+  const long long total = n * zd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / zd;
+    const int d = (int)(i - row * zd);
+    const int s = slot[row];
+    float mi = m[i] * b1, vi = v[i] * b2;
+    if (s >= 0) {
+      const float g = gz[(size_t)s * zd + d];
+      mi += (1.f - b1) * g;
+      vi += (1.f - b2) * g * g;
+    }
+    m[i] = mi;
+    v[i] = vi;
+    z[i] -= lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+__global__ void latent_unmark_kernel(const int* __restrict__ idx, int bs, int* __restrict__ slot) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < bs) slot[idx[r]] = -1;
+}
+
+// evaluate (:534-556): sums of squared errors of the three models over all rows, and
+// e_net / any Dense stack applied to many rows.  One CTA per 32 rows.
+struct EvalArgs {
+  Net g, f, h, e;
+  int z_dims[4];
+  int zd, p, binary, n;
+  const float* theta;
+  const float* zt;            // (n, zd) latent table, or NULL: z = e_net(v)
+  const float *x, *y, *v;
+  double* sums;               // [3] sum (v-v^)^2, sum (x-x^)^2, sum (y-y^)^2
+  float* z_out;               // optional (n, zd): the z that was used
+  int wm;
+};
+__global__ void __launch_bounds__(NTH) eval_kernel(const __grid_constant__ EvalArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  const int p = A.p, zd = A.zd;
+  float* bufA = sm;
+  float* bufB = bufA + A.wm * LD;
+  float* bufC = bufB + A.wm * LD;
+  float* zmat = bufC + A.wm * LD;
+  float* xy = zmat + zd * LD;
+  float* fin = xy + 2 * LD;
+  __shared__ float red[3];
+  const int d0 = A.z_dims[0], d1 = A.z_dims[1], d2 = A.z_dims[2];
+  for (int blk = blockIdx.x; blk * 32 < A.n; blk += gridDim.x) {
+    const int r0 = blk * 32, bs = min(32, A.n - r0);
+    if (threadIdx.x < 3) red[threadIdx.x] = 0.f;
+    load_cols(A.v + (size_t)r0 * p, p, 0, p, bs, bufC);
+    load_cols(A.x + r0, 1, 0, 1, bs, xy);
+    load_cols(A.y + r0, 1, 0, 1, bs, xy + LD);
+    __syncthreads();
+    if (A.zt) {
+      load_cols(A.zt + (size_t)r0 * zd, zd, 0, zd, bs, zmat);
+      __syncthreads();
+    } else {
+      float* ze = mlp_forward(A.e, A.theta, bufC, bufA, bufB, nullptr);
+      copy_mat(ze, zmat, zd);
+      __syncthreads();
+    }
+    if (A.z_out)
+      for (int i = threadIdx.x; i < zd * 32; i += NTH)
+        if ((i & 31) < bs) A.z_out[(size_t)(r0 + (i & 31)) * zd + (i >> 5)] = zmat[(i >> 5) * LD + (i & 31)];
+    auto acc = [&](float v, int slot) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((threadIdx.x & 31) == 0) atomicAdd(red + slot, v);
+    };
+    {
+      float* go = mlp_forward(A.g, A.theta, zmat, bufA, bufB, nullptr);
+      float s = 0.f;
+      for (int i = threadIdx.x; i < p * 32; i += NTH) {
+        const int c = i >> 5, r = i & 31;
+        if (r < bs) { const float d = bufC[c * LD + r] - go[c * LD + r]; s = fmaf(d, d, s); }
+      }
+      acc(s, 0);
+    }
+    {
+      copy_mat(zmat, fin, d0);
+      copy_mat(zmat + (d0 + d1) * LD, fin + d0 * LD, d2);
+      __syncthreads();
+      float* ho = mlp_forward(A.h, A.theta, fin, bufA, bufB, nullptr);
+      float s = 0.f;
+      if (threadIdx.x < bs) {
+        float xh = ho[threadIdx.x];
+        if (A.binary) xh = sigmoid_f(xh);                         // :549-550
+        const float d = xy[threadIdx.x] - xh;
+        s = d * d;
+      }
+      acc(s, 1);
+    }
+    {
+      copy_mat(zmat, fin, d0 + d1);
+      copy_mat(xy, fin + (d0 + d1) * LD, 1);
+      __syncthreads();
+      float* fo = mlp_forward(A.f, A.theta, fin, bufA, bufB, nullptr);
+      float s = 0.f;
+      if (threadIdx.x < bs) { const float d = xy[LD + threadIdx.x] - fo[threadIdx.x]; s = d * d; }
+      acc(s, 2);
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) atomicAdd(A.sums + threadIdx.x, (double)red[threadIdx.x]);
+    __syncthreads();
+  }
+}
+
+}  // namespace tr
+}  // namespace bgm

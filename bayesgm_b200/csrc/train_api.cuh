@@ -28,6 +28,12 @@ struct bgm_trainer {
   float alpha = 0.f, gamma = 0.f;
   float* moving = nullptr;     // [2*zd] BN moving mean | variance of the generator input
   int disc_floats = 0;
+  // iterative phase of CausalBGM.fit (bgm_trainer_set_iter)
+  float *m_it = nullptr, *v_it = nullptr, *gz = nullptr;
+  double lr_theta = 0, lr_z = 0;
+  float s2v = -1.f, s2x = -1.f, s2y = -1.f;
+  long long step_it = 0, step_z = 0;
+  int smem_iter = 0, smem_eval = 0;
 };
 
 namespace bgm {
@@ -313,6 +319,9 @@ void bgm_trainer_destroy(bgm_trainer* t) {
   }
   if (t->tape) cudaFree(t->tape);
   if (t->moving) cudaFree(t->moving);
+  if (t->m_it) cudaFree(t->m_it);
+  if (t->v_it) cudaFree(t->v_it);
+  if (t->gz) cudaFree(t->gz);
   delete t;
 }
 
@@ -397,6 +406,122 @@ int bgm_gather_rows(const float* src_dev, int ld, const int* idx_dev, int bs, in
     return fail(BGM_ERR_ARG, "bgm_gather_rows: bad argument");
   const int grid = std::max(1, std::min((bs * dim + 255) / 256, 148));
   tr::gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_dev, ld, idx_dev, bs, dim, dst_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+
+// ---------------------------------------------- iterative phase of CausalBGM.fit ----
+int bgm_trainer_set_iter(bgm_trainer* t, float lr_theta, float lr_z, float sigma_v, float sigma_x, float sigma_y) {
+  using namespace bgm;
+  if (!t || t->kind != 0) return fail(BGM_ERR_ARG, "bgm_trainer_set_iter: needs a CausalBGM trainer");
+  t->lr_theta = lr_theta; t->lr_z = lr_z;
+  t->s2v = sigma_v >= 0.f ? sigma_v * sigma_v : -1.f;
+  t->s2x = sigma_x >= 0.f ? sigma_x * sigma_x : -1.f;
+  t->s2y = sigma_y >= 0.f ? sigma_y * sigma_y : -1.f;
+  if (!t->m_it) {
+    const size_t bytes = sizeof(float) * (size_t)t->n_gen;
+    BGM_CUDA_OK(cudaMalloc(&t->m_it, bytes));
+    BGM_CUDA_OK(cudaMalloc(&t->v_it, bytes));
+    BGM_CUDA_OK(cudaMalloc(&t->gz, sizeof(float) * 32 * t->zd));
+  }
+  BGM_CUDA_OK(cudaMemset(t->m_it, 0, sizeof(float) * (size_t)t->n_gen));
+  BGM_CUDA_OK(cudaMemset(t->v_it, 0, sizeof(float) * (size_t)t->n_gen));
+  t->step_it = t->step_z = 0;
+  t->smem_iter = (4 * t->wm * tr::LD + 2 * t->zd * tr::LD + 2 * tr::LD + (t->zd + 1) * tr::LD + 16 + 32) * 4 + 64;
+  t->smem_eval = (3 * t->wm * tr::LD + t->zd * tr::LD + 2 * tr::LD + (t->zd + 1) * tr::LD) * 4 + 64;
+  return 0;
+}
+
+static void iter_fill(const bgm_trainer* t, bgm::tr::IterArgs& A, const float* zt, const float* x, const float* y,
+                      const float* v, const int* idx, int bs) {
+  memset(&A, 0, sizeof(A));
+  A.g = t->g; A.f = t->f; A.h = t->h;
+  for (int i = 0; i < 4; ++i) A.z_dims[i] = t->z_dims[i];
+  A.zd = t->zd; A.p = t->p; A.binary = t->binary; A.bs = bs;
+  A.s2v = t->s2v; A.s2x = t->s2x; A.s2y = t->s2y;
+  A.theta = t->theta[0]; A.grad = t->grad[0]; A.tape = t->tape;
+  A.zt = zt; A.x = x; A.y = y; A.v = v; A.idx = idx; A.wm = t->wm;
+}
+
+int bgm_train_iter_nets(bgm_trainer* t, const float* zt_dev, const float* x_dev, const float* y_dev,
+                        const float* v_dev, const int* idx_dev, int bs, int apply, float grad_scale,
+                        float* losses_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 0 || !t->m_it) return fail(BGM_ERR_ARG, "bgm_train_iter_nets: call bgm_trainer_set_iter first");
+  if (!zt_dev || !x_dev || !y_dev || !v_dev || !idx_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_train_iter_nets: null argument");
+  if (bs < 1 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_train_iter_nets: batch size must be in [1, 32]");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (apply != 2) {
+    tr::IterArgs A;
+    iter_fill(t, A, zt_dev, x_dev, y_dev, v_dev, idx_dev, bs);
+    A.losses = losses_dev;
+    BGM_CUDA_OK(cudaFuncSetAttribute(tr::iter_grad_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_iter));
+    tr::iter_grad_kernel<0><<<1, tr::NTH, t->smem_iter, st>>>(A);
+    BGM_CUDA_OK(cudaGetLastError());
+  }
+  if (apply) {   // g_optimizer, h_optimizer, f_optimizer (:89-91): same hyper-parameters, same step count
+    t->step_it += 1;
+    const double k = (double)t->step_it;
+    const float lr_t = (float)(t->lr_theta * std::sqrt(1.0 - std::pow(0.99, k)) / (1.0 - std::pow(0.9, k)));
+    const int ranges[2][2] = {{t->g.w_off[0], t->e.w_off[0]}, {t->f.w_off[0], t->n_gen}};
+    for (auto& r : ranges) {
+      const int n = r[1] - r[0];
+      const int grid = std::max(1, std::min((n + 255) / 256, t->sm_count * 4));
+      tr::adam_kernel<<<grid, 256, 0, st>>>(t->theta[0] + r[0], t->grad[0] + r[0], t->m_it + r[0], t->v_it + r[0], n,
+                                            lr_t, 0.9f, 0.99f, 1e-7f, grad_scale);
+      BGM_CUDA_OK(cudaGetLastError());
+    }
+  }
+  return 0;
+}
+
+int bgm_train_iter_latent(bgm_trainer* t, float* zt_dev, float* m_dev, float* v_dev_adam, int* slot_dev,
+                          long long n, const float* x_dev, const float* y_dev, const float* v_dev,
+                          const int* idx_dev, int bs, float* loss_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 0 || !t->m_it) return fail(BGM_ERR_ARG, "bgm_train_iter_latent: call bgm_trainer_set_iter first");
+  if (!zt_dev || !m_dev || !v_dev_adam || !slot_dev || !x_dev || !y_dev || !v_dev || !idx_dev || !loss_dev)
+    return fail(BGM_ERR_ARG, "bgm_train_iter_latent: null argument");
+  if (bs < 1 || bs > 32 || n < bs) return fail(BGM_ERR_UNSUPPORTED, "bgm_train_iter_latent: batch size must be in [1, 32]");
+  cudaStream_t st = (cudaStream_t)stream;
+  tr::IterArgs A;
+  iter_fill(t, A, zt_dev, x_dev, y_dev, v_dev, idx_dev, bs);
+  A.losses = loss_dev;
+  A.gz_out = t->gz;
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::iter_grad_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_iter));
+  tr::iter_grad_kernel<1><<<1, tr::NTH, t->smem_iter, st>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  t->step_z += 1;
+  const double k = (double)t->step_z;
+  const float lr_t = (float)(t->lr_z * std::sqrt(1.0 - std::pow(0.99, k)) / (1.0 - std::pow(0.9, k)));
+  tr::latent_mark_kernel<<<1, 32, 0, st>>>(idx_dev, bs, slot_dev);
+  const long long total = n * t->zd;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)t->sm_count * 8));
+  tr::latent_adam_sweep_kernel<<<grid, 256, 0, st>>>(zt_dev, m_dev, v_dev_adam, slot_dev, t->gz, n, t->zd, lr_t, 0.9f,
+                                                     0.99f, 1e-7f);
+  tr::latent_unmark_kernel<<<1, 32, 0, st>>>(idx_dev, bs, slot_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_causal_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, const float* y_dev,
+                        const float* v_dev, int n, double* sums_dev, float* z_out_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 0) return fail(BGM_ERR_ARG, "bgm_causal_evaluate: needs a CausalBGM trainer");
+  if (!x_dev || !y_dev || !v_dev || !sums_dev || n < 1) return fail(BGM_ERR_ARG, "bgm_causal_evaluate: bad argument");
+  if (!t->smem_eval) t->smem_eval = (3 * t->wm * tr::LD + t->zd * tr::LD + 2 * tr::LD + (t->zd + 1) * tr::LD) * 4 + 64;
+  tr::EvalArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = t->g; A.f = t->f; A.h = t->h; A.e = t->e;
+  for (int i = 0; i < 4; ++i) A.z_dims[i] = t->z_dims[i];
+  A.zd = t->zd; A.p = t->p; A.binary = t->binary; A.n = n;
+  A.theta = t->theta[0]; A.zt = zt_dev; A.x = x_dev; A.y = y_dev; A.v = v_dev; A.sums = sums_dev; A.z_out = z_out_dev;
+  A.wm = t->wm;
+  BGM_CUDA_OK(cudaMemsetAsync(sums_dev, 0, 3 * sizeof(double), (cudaStream_t)stream));
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_eval));
+  const int grid = std::max(1, std::min((n + 31) / 32, t->sm_count * 2));
+  tr::eval_kernel<<<grid, tr::NTH, t->smem_eval, (cudaStream_t)stream>>>(A);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }

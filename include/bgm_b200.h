@@ -306,6 +306,33 @@ int bgm_bgm_train_gen_grad(bgm_trainer* t, const float* z_dev, const float* x_de
 /* One Keras-Adam step of the group on (grad_scale * gradient buffer); grad_scale is
  * 1/world_size after a summing all-reduce, 1 on a single GPU. */
 int bgm_train_adam(bgm_trainer* t, int group, float grad_scale, void* stream);
+/* ---- iterative phase of CausalBGM.fit (causalbgm/base.py:156-302, :488-514) ---- */
+/* Learning rates of g/h/f_optimizer (lr_theta) and posterior_optimizer (lr_z), all Adam
+ * beta=(.9,.99) (:89-92); sigma_* >= 0 are the fixed `sigma_*` keys of the params dict,
+ * < 0 = learned softplus head.  Resets the Adam state of this phase. */
+int bgm_trainer_set_iter(bgm_trainer* t, float lr_theta, float lr_z, float sigma_v, float sigma_x, float sigma_y);
+/* update_g_net, update_h_net, update_f_net (:156-243) on the mini-batch rows idx_dev[0..bs)
+ * of the device-resident data and latent table zt_dev (n, zd): gradients (apply 0 or 1) and
+ * the three Adam updates (apply 1; apply 2 = only the update, after an all-reduce of the
+ * group-0 gradient buffer, with grad_scale = 1/world).  losses_dev[6] = loss_v, loss_mse_v,
+ * loss_x, loss_mse_x, loss_y, loss_mse_y.  1 <= bs <= 32. */
+int bgm_train_iter_nets(bgm_trainer* t, const float* zt_dev, const float* x_dev, const float* y_dev,
+                        const float* v_dev, const int* idx_dev, int bs, int apply, float grad_scale,
+                        float* losses_dev, void* stream);
+/* update_latent_variable_sgd (:246-302): gradient of loss_postrior_z w.r.t. the batch rows
+ * of the latent table, then Keras Adam on a gathered variable = a DENSE sweep (m, v decay
+ * and every one of the n rows moves).  m_dev, v_dev_adam: (n, zd) Adam moments;
+ * slot_dev: (n) int32 scratch initialised to -1.  loss_dev[1] = loss_postrior_z. */
+int bgm_train_iter_latent(bgm_trainer* t, float* zt_dev, float* m_dev, float* v_dev_adam, int* slot_dev,
+                          long long n, const float* x_dev, const float* y_dev, const float* v_dev,
+                          const int* idx_dev, int bs, float* loss_dev, void* stream);
+/* CausalBGM.evaluate (:534-556), the part that touches every row: sums_dev[3] = sum (v-v^)^2,
+ * sum (x-x^)^2, sum (y-y^)^2 (float64) with z = zt_dev rows, or z = e_net(v) if zt_dev is
+ * NULL; z_out_dev (n, zd), if non-NULL, receives the z used (the `data_z_init = e_net(data_v)`
+ * of :479). */
+int bgm_causal_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, const float* y_dev,
+                        const float* v_dev, int n, double* sums_dev, float* z_out_dev, void* stream);
+
 /* dst[r][:] = src[idx[r]][:dim] -- mini-batch gather from device-resident data (:406-416). */
 int bgm_gather_rows(const float* src_dev, int ld, const int* idx_dev, int bs, int dim, float* dst_dev,
                     void* stream);

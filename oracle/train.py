@@ -244,4 +244,86 @@ def update_net_grads(params, nets, which, batch_z, batch_x, batch_y, batch_v, ep
             mse = ((tgt - mu) ** 2).mean()
             loss = (((tgt - mu) ** 2).sum(dim=1) / (2 * s2) + torch.log(torch.as_tensor(s2)) / 2).mean()
     grads = torch.autograd.grad(loss, mlp_param_list(net))
-    return float(loss), float(mse), [a.numpy() for a in grads]
+    return float(loss.detach()), float(mse.detach()), [a.numpy() for a in grads]
+
+
+def latent_grad(params, nets, batch_z, batch_x, batch_y, batch_v, eps=1e-6):
+    """update_latent_variable_sgd (:246-295): (loss_postrior_z, gradient w.r.t. the batch rows)."""
+    p = params['v_dim']
+    sp = torch.nn.functional.softplus
+    g, f, h = [to_t(nets[k]) for k in ('g', 'f', 'h')]
+    z = torch.tensor(batch_z, dtype=torch.float32, requires_grad=True)
+    x = torch.tensor(batch_x, dtype=torch.float32)
+    y = torch.tensor(batch_y, dtype=torch.float32)
+    v = torch.tensor(batch_v, dtype=torch.float32)
+    z0, z1, z2 = _split_z(params, z)
+    go = mlp(g, z)
+    s2v = params['sigma_v'] ** 2 if 'sigma_v' in params else sp(go[:, -1]) + eps
+    loss_v = (((v - go[:, :p]) ** 2).sum(dim=1) / (2 * s2v) + p * torch.log(torch.as_tensor(s2v)) / 2).mean()
+    ho = mlp(h, torch.cat([z0, z2], dim=-1))
+    if params['binary_treatment']:
+        loss_x = torch.nn.functional.binary_cross_entropy_with_logits(ho[:, :1], x, reduction='mean')
+    else:
+        s2x = params['sigma_x'] ** 2 if 'sigma_x' in params else sp(ho[:, -1]) + eps
+        loss_x = (((x - ho[:, :1]) ** 2).sum(dim=1) / (2 * s2x) + torch.log(torch.as_tensor(s2x)) / 2).mean()
+    fo = mlp(f, torch.cat([z0, z1, x], dim=-1))
+    s2y = params['sigma_y'] ** 2 if 'sigma_y' in params else sp(fo[:, -1]) + eps
+    loss_y = (((y - fo[:, :1]) ** 2).sum(dim=1) / (2 * s2y) + torch.log(torch.as_tensor(s2y)) / 2).mean()
+    prior = ((z ** 2).sum(dim=1) / 2).mean()
+    loss = loss_v + loss_x + loss_y + prior
+    gz = torch.autograd.grad(loss, z)[0]
+    return float(loss.detach()), gz.numpy()
+
+
+class SparseAdam(object):
+    """Keras Adam applied to tf.gather'ed rows of a variable (TF 2.10 optimizer_v2
+    `_resource_apply_sparse`): m, v of the WHOLE variable decay, the gathered
+    rows receive the scaled gradient, and the WHOLE variable moves."""
+
+    def __init__(self, lr, shape, beta_1=0.9, beta_2=0.99, epsilon=1e-7):
+        self.lr, self.b1, self.b2, self.eps, self.t = lr, beta_1, beta_2, epsilon, 0
+        self.m = np.zeros(shape, np.float32)
+        self.v = np.zeros(shape, np.float32)
+
+    def apply(self, table, idx, grad_rows):
+        f32 = np.float32
+        self.t += 1
+        lr_t = f32(self.lr * np.sqrt(1.0 - self.b2 ** self.t) / (1.0 - self.b1 ** self.t))
+        self.m *= f32(self.b1)
+        self.v *= f32(self.b2)
+        self.m[idx] += f32(1 - self.b1) * grad_rows
+        self.v[idx] += f32(1 - self.b2) * grad_rows * grad_rows
+        table -= lr_t * self.m / (np.sqrt(self.v) + f32(self.eps))
+
+
+class IterTrainer(object):
+    """The iterative phase of CausalBGM.fit (:488-514) on host arrays."""
+
+    def __init__(self, params, nets, data_z):
+        self.params, self.nets = params, nets
+        for k in ('g', 'f', 'h'):
+            nets[k] = [(np.array(W, np.float32), np.array(b, np.float32)) for W, b in nets[k]]
+        self.data_z = np.array(data_z, np.float32)
+        self.opt = {k: Adam(params['lr_theta'], 0.9, 0.99) for k in ('g', 'h', 'f')}
+        self.z_opt = SparseAdam(params['lr_z'], self.data_z.shape)
+
+    def step(self, data, batch_idx):
+        data_x, data_y, data_v = data
+        bz = self.data_z[batch_idx]
+        bx, by, bv = data_x[batch_idx], data_y[batch_idx], data_v[batch_idx]
+        out = []
+        for k in ('g', 'h', 'f'):                                          # :500-502
+            loss, mse, grads = update_net_grads(self.params, self.nets, k, bz, bx, by, bv)
+            self.opt[k].apply(flat_params(self.nets[k]), grads)
+            out += [loss, mse]
+        lz, gz = latent_grad(self.params, self.nets, bz, bx, by, bv)       # :505 (updated nets)
+        self.z_opt.apply(self.data_z, batch_idx, gz)
+        return out, lz
+
+    def epoch(self, data, batch_size):
+        n = len(data[0])
+        sample_idx = np.random.choice(n, n, replace=False)                 # :489
+        last = None
+        for i in range(0, n, batch_size):
+            last = self.step(data, sample_idx[i:i + batch_size])
+        return last

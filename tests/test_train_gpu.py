@@ -265,3 +265,58 @@ def test_bgm_egm_init_runs_and_keeps_the_reference_batch_stream():
             s.next_batch()
             m.z_sampler.get_batch(16)
     np.testing.assert_array_equal(np.random.get_state()[1][:4], after)
+
+
+# --------------------------------------------------- iterative phase of fit (N2) --
+def test_fit_iterative_phase_tracks_the_oracle():
+    """fit(use_egm_init=False): same NumPy seed on both sides -> same random latent table and
+    epoch permutations (bit-exact host streams); g/h/f updates, the latent gradient and the
+    DENSE Keras-Adam sweep over the whole table then agree with the oracle loop."""
+    from oracle import causal
+    params = causal_params(20, [1, 2, 1, 1], lr_theta=1e-3, lr_z=1e-3)
+    nets = causal_nets(params, seed=11)
+    n, bs = 70, 16                                   # 70 = 4 batches of 16 + a ragged 6
+    data = causal_data(n, 20)
+    m = product_model(params, nets)
+    np.random.seed(42)
+    m.fit(data, epochs=1, epochs_per_eval=1, batch_size=bs, use_egm_init=False, verbose=0)
+    np.random.seed(42)
+    z0 = np.random.normal(0, 1, size=(n, 5)).astype('float32')
+    tr = train.IterTrainer(params, copy.deepcopy(nets), z0)
+    for epoch in range(2):
+        last = tr.epoch(data, bs)
+    # every row of the table moved (dense Adam), and it moved like the oracle's
+    assert (np.abs(m.data_z - z0) > 0).all()
+    np.testing.assert_allclose(m.data_z, tr.data_z, rtol=0, atol=2e-4)
+    w = m.get_weights()
+    for name in ('g', 'f', 'h'):
+        for got, want in zip(w[name], train.flat_params(tr.nets[name])):
+            assert np.median(np.abs(got - want)) <= 2e-5 and np.abs(got - want).max() <= 3e-3
+    for got, want in zip(w['e'], train.flat_params(nets['e'])):
+        np.testing.assert_array_equal(got, want)                 # e_net is not trained in this phase
+    np.testing.assert_allclose(m.last_iter_losses[:6], last[0], rtol=2e-3, atol=1e-5)
+    np.testing.assert_allclose(m.last_iter_losses[6], last[1], rtol=2e-3)
+    # evaluate (:534-570) on the trained state
+    got = m.evaluate(data, data_z=m.data_z)
+    onets_now = {k: [(W, b) for W, b in zip(w[k][0::2], w[k][1::2])] for k in 'gefh'}
+    want = causal.evaluate(params, onets_now, data, data_z=m.data_z)
+    np.testing.assert_allclose(got[0], want[0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got[1:], want[1:], rtol=1e-4)
+    assert m.best_causal_pre.shape == (200,) and m.best_epoch in (0, 1)
+    got2 = m.evaluate(data)                                      # data_z=None -> z = e_net(v)
+    want2 = causal.evaluate(params, onets_now, data)
+    np.testing.assert_allclose(got2[0], want2[0], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got2[1:], want2[1:], rtol=1e-4)
+
+
+def test_fit_with_egm_init_binary_end_to_end():
+    params = causal_params(12, [1, 1, 1, 1], binary=True, lr=1e-3, lr_theta=1e-3, lr_z=1e-3, g_d_freq=1)
+    nets = causal_nets(params, seed=11)
+    data = causal_data(64, 12, binary=True)
+    m = product_model(params, nets)
+    np.random.seed(1)
+    m.fit(data, epochs=0, epochs_per_eval=1, batch_size=32, use_egm_init=True, egm_n_iter=3, verbose=0)
+    assert m.data_z.shape == (64, 4) and np.isfinite(m.data_z).all()
+    assert m.best_causal_pre.shape == (64, 1)                    # ITE per subject (:559-563)
+    ite, interval = m.predict(data, n_mcmc=10, burn_in=10, q_sd=0.5, verbose=0)
+    assert ite.shape == (64,) and np.isfinite(ite).all()
