@@ -74,6 +74,9 @@ SYMBOLS = {
     "bgm_causal_destroy": (None, [C.c_void_p]),
     "bgm_causal_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                   C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_int)]),
+    "bgm_causal_set_sampler": (C.c_int, [C.c_void_p, C.c_int]),
+    "bgm_causal_sampler_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                          C.POINTER(C.c_longlong)]),
     "bgm_causal_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]),
     "bgm_causal_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -167,7 +167,28 @@ class CausalBGM(object):
             _lib.call("bgm_causal_create", C.byref(h), zd4, int(p['v_dim']), int(bool(p['binary_treatment'])),
                       sig[0], sig[1], sig[2], C.byref(gd), C.byref(fd), C.byref(hd))
             self._handle = h
+            kind = {'auto': 0, 'simt': 1, 'tensor': 2}[getattr(self, 'sampler_engine', 'auto')]
+            if kind:
+                _lib.call("bgm_causal_set_sampler", h, kind)
         return self._handle
+
+    def set_sampler_engine(self, engine='auto'):
+        """'auto' (tensor-core engine when the net shape allows it), 'simt' (fp32 FMA-pipe
+        engine) or 'tensor' (raises if unavailable).  Both run the same algorithm on the
+        same Philox streams; see DESIGN.md 4.1 / 4.1b."""
+        if engine not in ('auto', 'simt', 'tensor'):
+            raise ValueError("engine must be 'auto', 'simt' or 'tensor'")
+        self.sampler_engine = engine
+        if self._handle is not None:
+            _lib.call("bgm_causal_set_sampler", self._handle, {'auto': 0, 'simt': 1, 'tensor': 2}[engine])
+
+    def sampler_info(self):
+        kind, avail, smem = C.c_int(), C.c_int(), C.c_int()
+        issued = C.c_longlong()
+        _lib.call("bgm_causal_sampler_info", self._device_model(), C.byref(kind), C.byref(avail), C.byref(smem),
+                  C.byref(issued))
+        return dict(engine={1: 'simt', 2: 'tensor'}[kind.value], tensor_available=bool(avail.value),
+                    tensor_smem_bytes=smem.value, tensor_issued_macs_per_row=issued.value)
 
     def kernel_info(self):
         smem, warps, nops, proj = C.c_int(), C.c_int(), C.c_int(), C.c_int()

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "causal.cuh"
+#include "causal_tc.cuh"
 
 namespace bgm {
 
@@ -130,6 +131,57 @@ static int read_net(const bgm_net_desc* d, HostNet& n, const char* name) {
   return 0;
 }
 
+// ---- tensor-core engine image (causal_tc.cuh) ----
+static void split_tf32_host(float w, float& hi, float& lo) {
+  uint32_t b;
+  memcpy(&b, &w, 4);
+  uint32_t h = (b + 0x1000u) & 0xffffe000u;
+  memcpy(&hi, &h, 4);
+  const float l = w - hi;
+  memcpy(&b, &l, 4);
+  b = (b + 0x1000u) & 0xffffe000u;
+  memcpy(&lo, &b, 4);
+}
+// Wm [64][64] (Keras [in][out]) -> two [16][64][4] blocks (umma.cuh layout), returns the hi offset
+static void pack_mma64(std::vector<float>& img, const std::vector<float>& Wm, int& off_hi, int& off_lo) {
+  off_hi = (int)img.size();
+  img.resize(img.size() + 4096, 0.f);
+  off_lo = (int)img.size();
+  img.resize(img.size() + 4096, 0.f);
+  for (int k = 0; k < 64; ++k)
+    for (int n = 0; n < 64; ++n) {
+      float hi, lo;
+      split_tf32_host(Wm[(size_t)k * 64 + n], hi, lo);
+      const int idx = (k >> 2) * 256 + n * 4 + (k & 3);
+      img[off_hi + idx] = hi;
+      img[off_lo + idx] = lo;
+    }
+}
+static int push_floats(std::vector<float>& img, const float* p, size_t count) {
+  while (img.size() % 4) img.push_back(0.f);   // float4 loads
+  const int off = (int)img.size();
+  img.insert(img.end(), p, p + count);
+  return off;
+}
+static bool small_net_shape(const HostNet& n) {
+  return n.L == 4 && n.dims[1] == 64 && n.dims[2] == 32 && n.dims[3] == 8 && n.dims[4] == 2;
+}
+// first-layer rows remapped onto [z.., x] -> transposed [64][kin4]
+static void pack_small_net(std::vector<float>& img, const HostNet& net, const std::vector<int>& rows, int kin4,
+                           SmallNet& o) {
+  std::vector<float> w1t((size_t)64 * kin4, 0.f);
+  for (size_t r = 0; r < rows.size(); ++r)
+    for (int k = 0; k < 64; ++k) w1t[(size_t)k * kin4 + rows[r]] = net.W[0][r * 64 + k];
+  o.W1t = push_floats(img, w1t.data(), w1t.size());
+  o.b1 = push_floats(img, net.b[0].data(), 64);
+  o.W2 = push_floats(img, net.W[1].data(), 64 * 32);
+  o.b2 = push_floats(img, net.b[1].data(), 32);
+  o.W3 = push_floats(img, net.W[2].data(), 32 * 8);
+  o.b3 = push_floats(img, net.b[2].data(), 8);
+  o.W4 = push_floats(img, net.W[3].data(), 8 * 2);
+  o.b4 = push_floats(img, net.b[3].data(), 2);
+}
+
 }  // namespace bgm
 
 using namespace bgm;
@@ -145,6 +197,12 @@ struct bgm_causal {
   int effect_smem_bytes = 0;
   int sm_count = 0;
   long long macs = 0, issued = 0;
+  // tensor-core engine (causal_tc.cuh); tc.enabled == 0 when the net shape is outside it
+  TcProgram tc;
+  float* tc_image_dev = nullptr;
+  int tc_smem_bytes = 0;
+  long long tc_issued = 0;     // FMA-equivalents per row per evaluation (tensor + FMA pipe)
+  int sampler = 0;             // 0: auto, 1: SIMT engine, 2: tensor-core engine
 };
 
 static int check_data(const char* fn, const bgm_causal* m, const float* x, const float* y, const float* v,
@@ -176,7 +234,29 @@ static int launch_mh_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
+template <int ZMAX>
+static int launch_mh_tc_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream_t st) {
+  auto k = causal_mh_tc_kernel<ZMAX>;
+  BGM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tc_smem_bytes));
+  k<<<grid, 256, m->tc_smem_bytes, st>>>(m->tc, m->tc_image_dev, D);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+static bool use_tc(const bgm_causal* m) { return m->tc.enabled && m->sampler != 1; }
 static int launch_mh(const bgm_causal* m, MhDev& D, cudaStream_t st) {
+  if (use_tc(m)) {
+    // 128-row tiles, two warpgroups per CTA
+    const int nt = (D.a.n + TC_ROWS - 1) / TC_ROWS;
+    const int grid = std::max(1, std::min((nt + 1) / 2, m->sm_count));
+    const bool need_init = !(D.a.init_mode == 0 && D.mode == 0);
+    const int n_iter = (D.mode == 1 ? 0 : D.a.t_end - D.a.t_begin) + (need_init ? 1 : 0);
+    D.nchunks = std::max(1, (n_iter + 15) / 16);
+    BGM_CUDA_OK(cudaMemsetAsync(D.a.sched_dev, 0, sizeof(int) * (size_t)(nt + 1), st));
+    const int zd = m->prog.zd;
+    if (zd <= 8) return launch_mh_tc_t<8>(m, D, grid, st);
+    if (zd <= 16) return launch_mh_tc_t<16>(m, D, grid, st);
+    return launch_mh_tc_t<32>(m, D, grid, st);
+  }
   const int ntiles = (D.a.n + TILE_ROWS - 1) / TILE_ROWS;
   const int grid = std::max(1, std::min((ntiles + m->warps - 1) / m->warps, m->sm_count));
   const int zd = m->prog.zd;
@@ -235,7 +315,7 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   memset(&P, 0, sizeof(P));
 
   int proj_dim = 0, proj_hp = 0;
-  std::vector<float> proj_host;
+  std::vector<float> proj_host, proj_RT;
   // maps each net's first-layer input rows onto rows of the shared input buffer
   // zin = [z (zd rows), x (row zd), zero pad]
   auto remap_first = [&](const HostNet& net, const std::vector<int>& rows) {
@@ -270,6 +350,7 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
           for (int j = 0; j < H; ++j)
             for (int i = 0; i < H; ++i) RT[(size_t)j * H + i] = (float)R[(size_t)i * H + j];
           pk.add_final(RT, zb, H, H, 0, H, src, EPI_SSE, 0);
+          proj_RT = RT;
           proj_dim = H;
           proj_hp = H > 32 ? 64 : 32;
           proj_host.assign((size_t)v_dim * proj_hp + v_dim, 0.f);
@@ -321,6 +402,41 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   P.image_floats = (int)pk.image.size();
   P.per_warp_floats = (ACT_ROWS + kin + SCR_SLOTS) * TILE_ROWS;
 
+  // ---- tensor-core engine: g hidden layers 64 wide, projected likelihood, standard f / h ----
+  TcProgram T;
+  memset(&T, 0, sizeof(T));
+  std::vector<float> tc_image;
+  long long tc_issued = 0;
+  {
+    bool ok = proj_dim == 64 && g.L >= 3 && g.L - 1 <= TC_MAX_MMA && small_net_shape(f) && small_net_shape(h);
+    for (int l = 1; l < g.L; ++l) ok = ok && g.dims[l] == 64;
+    if (ok) {
+      T.zd = zd; T.kin4 = kin; T.p = v_dim; T.binary = P.binary;
+      T.s2v = P.s2v; T.s2x = P.s2x; T.s2y = P.s2y;
+      T.n_mma = g.L - 1;
+      for (int m = 0; m < T.n_mma; ++m) {
+        const bool last = m == T.n_mma - 1;
+        pack_mma64(tc_image, last ? proj_RT : g.W[m + 1], T.w_hi[m], T.w_lo[m]);
+      }
+      for (int m = 0; m + 1 < T.n_mma; ++m) T.gb[m] = push_floats(tc_image, g.b[m + 1].data(), 64);
+      T.gW1 = push_floats(tc_image, g.W[0].data(), (size_t)zd * 64);
+      T.gb1 = push_floats(tc_image, g.b[0].data(), 64);
+      std::vector<float> wsig(64);
+      const int NL = v_dim + 1;
+      for (int k = 0; k < 64; ++k) wsig[k] = g.W[g.L - 1][(size_t)k * NL + v_dim];
+      T.wsig = push_floats(tc_image, wsig.data(), 64);
+      T.bsig = push_floats(tc_image, &g.b[g.L - 1][v_dim], 1);
+      pack_small_net(tc_image, f, f_rows, kin, T.f);
+      pack_small_net(tc_image, h, h_rows, kin, T.h);
+      while (tc_image.size() % 4) tc_image.push_back(0.f);
+      T.image_floats = (int)tc_image.size();
+      T.enabled = 1;
+      // tensor pipe: 3 TF32 products per FMA of the 64x64 layers; FMA pipe: the narrow layers
+      tc_issued = 3LL * 4096 * T.n_mma + (long long)zd * 64 + 64 +
+                  2LL * ((long long)kin * 64 + 64 * 32 + 32 * 8 + 8 * 2);
+    }
+  }
+
   int dev = 0, smem_max = 0, sms = 0;
   BGM_CUDA_OK(cudaGetDevice(&dev));
   BGM_CUDA_OK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -355,7 +471,17 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
     if (e == cudaSuccess)
       e = cudaMemcpy(m->proj_dev, proj_host.data(), proj_host.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
+  m->tc = T;
+  m->tc_issued = tc_issued;
+  m->tc_smem_bytes = T.image_floats * 4;
+  if (T.enabled && m->tc_smem_bytes + 256 > smem_max) m->tc.enabled = 0;
+  if (e == cudaSuccess && m->tc.enabled) {
+    e = cudaMalloc(&m->tc_image_dev, tc_image.size() * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->tc_image_dev, tc_image.data(), tc_image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
+    if (m->tc_image_dev) cudaFree(m->tc_image_dev);
     if (m->proj_dev) cudaFree(m->proj_dev);
     if (m->image_dev) cudaFree(m->image_dev);
     delete m;
@@ -369,6 +495,7 @@ void bgm_causal_destroy(bgm_causal* m) {
   if (!m) return;
   if (m->image_dev) cudaFree(m->image_dev);
   if (m->proj_dev) cudaFree(m->proj_dev);
+  if (m->tc_image_dev) cudaFree(m->tc_image_dev);
   delete m;
 }
 
@@ -381,6 +508,26 @@ int bgm_causal_info(const bgm_causal* m, int* smem_bytes, int* warps_per_cta, in
   if (macs_per_row) *macs_per_row = m->macs;
   if (issued_macs_per_row) *issued_macs_per_row = m->issued;
   if (proj_dim) *proj_dim = m->proj_dim;
+  return 0;
+}
+
+int bgm_causal_set_sampler(bgm_causal* m, int kind) {
+  if (!m) return fail(BGM_ERR_ARG, "bgm_causal_set_sampler: null model");
+  if (kind < 0 || kind > 2) return fail(BGM_ERR_ARG, "bgm_causal_set_sampler: kind must be 0 (auto), 1 (SIMT) or 2 (tensor)");
+  if (kind == 2 && !m->tc.enabled)
+    return fail(BGM_ERR_UNSUPPORTED, "bgm_causal_set_sampler: the tensor-core engine needs g hidden layers of 64 "
+                                     "units, v_dim > 72 and f/h units [64,32,8]");
+  m->sampler = kind;
+  return 0;
+}
+
+int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_available, int* tensor_smem_bytes,
+                            long long* tensor_issued_macs_per_row) {
+  if (!m) return fail(BGM_ERR_ARG, "bgm_causal_sampler_info: null model");
+  if (active_kind) *active_kind = use_tc(m) ? 2 : 1;
+  if (tensor_available) *tensor_available = m->tc.enabled;
+  if (tensor_smem_bytes) *tensor_smem_bytes = m->tc_smem_bytes;
+  if (tensor_issued_macs_per_row) *tensor_issued_macs_per_row = m->tc_issued;
   return 0;
 }
 

@@ -1,0 +1,447 @@
+// CausalBGM random-walk MH sampler, tensor-core engine (tcgen05 / TMEM).
+//
+// Same contract as causal_mh_kernel (causal.cuh): causalbgm/base.py:765-817
+// (get_log_posterior) inside :820-904 (metropolis_hastings_sampler), same Philox streams,
+// same scheduling, same arguments -- a different execution plan for the standard net shape
+// (g: zd -> 64 x (L-1) -> v_dim+1 with the covariate likelihood projected to 64 columns,
+// f / h: in -> 64 -> 32 -> 8 -> 2):
+//
+//  * a warpgroup (4 warps, 128 threads) owns a 128-row tile; THREAD = ROW = TMEM LANE.  The
+//    chain state, the proposal, the per-row losses and the accept decision never leave the
+//    thread; there is no shuffle and no shared-memory activation buffer.
+//  * the 64x64 layers of g_net (hidden layers 2.. and the projected output layer) run on the
+//    tensor cores as 3xTF32 (umma.cuh): the thread writes its activation row, split into
+//    hi/lo, into TMEM (tcgen05.st), one elected thread issues 24 tcgen05.mma (A from TMEM,
+//    weights from the shared-memory image), the accumulator row comes back with tcgen05.ld
+//    for bias + LeakyReLU + split.  fp32-level error.
+//  * the narrow nets (g's first layer, f_net, h_net) stay on the fp32 FMA pipe, one row per
+//    thread with warp-uniform (broadcast) weight loads, in the same k order as the SIMT
+//    engine; f_net / h_net are evaluated while the thread's MMAs are in flight.
+//  * two warpgroups per CTA (one CTA per SM, 512 TMEM columns = 2 x [A_hi 64 | A_lo 64 | D 64 | -])
+//    work on different tiles, so one tile's epilogue overlaps the other's MMAs.
+#pragma once
+#include "causal.cuh"
+#include "umma.cuh"
+
+namespace bgm {
+
+constexpr int TC_ROWS = 128;
+constexpr int TC_MAX_MMA = 8;
+
+struct SmallNet {      // in -> 64 -> 32 -> 8 -> 2; float offsets into the image
+  int W1t, b1;         // [64][kin4]: first layer transposed over the padded input [z.., x, 0..]
+  int W2, b2;          // [64][32]
+  int W3, b3;          // [32][8]
+  int W4, b4;          // [8][2]
+};
+
+struct TcProgram {
+  int enabled;
+  int zd, kin4, p, binary;
+  float s2v, s2x, s2y;
+  int n_mma;                                  // g_net layers on the tensor cores (g.L - 1)
+  int w_hi[TC_MAX_MMA], w_lo[TC_MAX_MMA];     // [16][64][4] tf32 images (hi / lo)
+  int gb[TC_MAX_MMA];                         // bias added after MMA layer m (m < n_mma-1)
+  int gW1, gb1;                               // g first layer [zd][64], bias[64]
+  int wsig, bsig;                             // sigma_v head: column v_dim of g's last layer
+  SmallNet f, h;
+  int image_floats;
+};
+
+__device__ __forceinline__ void wg_sync(int wg) {
+  if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+// f_net / h_net for the thread's row.  `in` = [z (zd), x, 0 pad] (kin4 entries used).
+template <int KINMAX>
+__device__ __forceinline__ void small_net(const float* __restrict__ w, const SmallNet& o, int kin4,
+                                          const float (&in)[KINMAX], float& out0, float& out1) {
+  float acc2[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(w + o.b2 + q * 4);
+    acc2[q * 4 + 0] = b.x; acc2[q * 4 + 1] = b.y; acc2[q * 4 + 2] = b.z; acc2[q * 4 + 3] = b.w;
+  }
+  const float* W1t = w + o.W1t;
+  const float* b1 = w + o.b1;
+  const float* W2 = w + o.W2;
+#pragma unroll 2
+  for (int k = 0; k < 64; ++k) {
+    float a = b1[k];
+    const float* w1 = W1t + k * kin4;
+#pragma unroll
+    for (int q = 0; q < KINMAX / 4; ++q) {
+      if (q * 4 < kin4) {
+        const float4 ww = *reinterpret_cast<const float4*>(w1 + q * 4);
+        a = fmaf(in[q * 4 + 0], ww.x, a);
+        a = fmaf(in[q * 4 + 1], ww.y, a);
+        a = fmaf(in[q * 4 + 2], ww.z, a);
+        a = fmaf(in[q * 4 + 3], ww.w, a);
+      }
+    }
+    a = leaky(a);
+    const float4* w2 = reinterpret_cast<const float4*>(W2 + k * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 ww = w2[q];
+      acc2[q * 4 + 0] = fmaf(a, ww.x, acc2[q * 4 + 0]);
+      acc2[q * 4 + 1] = fmaf(a, ww.y, acc2[q * 4 + 1]);
+      acc2[q * 4 + 2] = fmaf(a, ww.z, acc2[q * 4 + 2]);
+      acc2[q * 4 + 3] = fmaf(a, ww.w, acc2[q * 4 + 3]);
+    }
+  }
+  float acc3[8];
+  {
+    const float4 ba = *reinterpret_cast<const float4*>(w + o.b3);
+    const float4 bb = *reinterpret_cast<const float4*>(w + o.b3 + 4);
+    acc3[0] = ba.x; acc3[1] = ba.y; acc3[2] = ba.z; acc3[3] = ba.w;
+    acc3[4] = bb.x; acc3[5] = bb.y; acc3[6] = bb.z; acc3[7] = bb.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    const float a = leaky(acc2[k]);
+    const float4 wa = *reinterpret_cast<const float4*>(w + o.W3 + k * 8);
+    const float4 wb = *reinterpret_cast<const float4*>(w + o.W3 + k * 8 + 4);
+    acc3[0] = fmaf(a, wa.x, acc3[0]); acc3[1] = fmaf(a, wa.y, acc3[1]);
+    acc3[2] = fmaf(a, wa.z, acc3[2]); acc3[3] = fmaf(a, wa.w, acc3[3]);
+    acc3[4] = fmaf(a, wb.x, acc3[4]); acc3[5] = fmaf(a, wb.y, acc3[5]);
+    acc3[6] = fmaf(a, wb.z, acc3[6]); acc3[7] = fmaf(a, wb.w, acc3[7]);
+  }
+  float o0 = w[o.b4], o1 = w[o.b4 + 1];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float a = leaky(acc3[k]);
+    const float2 ww = *reinterpret_cast<const float2*>(w + o.W4 + k * 2);
+    o0 = fmaf(a, ww.x, o0);
+    o1 = fmaf(a, ww.y, o1);
+  }
+  out0 = o0;
+  out1 = o1;
+}
+
+// bias + LeakyReLU + hi/lo split of 32 accumulator columns, back into the A slots.
+template <bool SIG>
+__device__ __forceinline__ void act_block32(uint32_t (&r)[32], const float* __restrict__ bias,
+                                            const float* __restrict__ wsig, float& sig, uint32_t tA_hi,
+                                            uint32_t tA_lo) {
+  uint32_t lo[32];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    float ws[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (SIG) {
+      const float4 s4 = *reinterpret_cast<const float4*>(wsig + q * 4);
+      ws[0] = s4.x; ws[1] = s4.y; ws[2] = s4.z; ws[3] = s4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = leaky(__uint_as_float(r[q * 4 + i]) + bb[i]);
+      if constexpr (SIG) sig = fmaf(a, ws[i], sig);
+      umma::split_tf32(a, r[q * 4 + i], lo[q * 4 + i]);
+    }
+  }
+  umma::st32(tA_hi, r);
+  umma::st32(tA_lo, lo);
+}
+
+template <int ZMAX>
+__global__ void __launch_bounds__(256, 1)
+causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict__ image,
+                    const __grid_constant__ MhDev D) {
+  constexpr int KINMAX = ZMAX + 4;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar_img;
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ long long unit_s[2];
+  bulk_load_to_smem(smem, image, (uint32_t)P.image_floats * 4u, &bar_img);
+  const float* wimg = smem;
+  const uint32_t wimg_s = umma::smem_addr(smem);
+
+  const bgm_mh_args& A = D.a;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2, wtid = tid & 127;
+  if (tid == 0) {
+    umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
+    umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc512(&tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem0 = tmem_slot;
+  const uint32_t tbase = tmem0 + (uint32_t)wg * 256u;             // MMA operand addresses (lane 0)
+  const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes
+  const uint32_t tA_hi = 0, tA_lo = 64, tD = 128;                 // column offsets
+  const uint32_t bar = umma::smem_addr(&bar_mma[wg]);
+  uint32_t parity = 0;
+
+  const int n = A.n, zd = P.zd;
+  const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
+  const double q_sd = A.q_sd_dev ? *A.q_sd_dev : 1.0;
+  const bool need_init = !(A.init_mode == 0 && D.mode == 0);
+  const int t_first = need_init ? A.t_begin - 1 : A.t_begin;
+  const int t_last = D.mode == 1 ? A.t_begin : A.t_end;
+  int* sched = A.sched_dev;
+  const int n_iter = t_last - t_first;
+  const int nchunks = D.nchunks;
+  const int chunk_len = (n_iter + nchunks - 1) / nchunks;
+  const long long total_units = (long long)ntiles * nchunks;
+  const int n_mma = P.n_mma;
+
+  // One MMA layer: publish the A rows written by the 128 threads, one thread issues.
+  auto stage_issue = [&](int m) {
+    umma::wait_st();
+    umma::fence_before_sync();
+    wg_sync(wg);
+    if (wtid == 0) {
+      umma::fence_after_sync();
+      umma::issue_layer_k64<64>(tbase + tD, tbase + tA_hi, tbase + tA_lo, wimg_s + 4u * (uint32_t)P.w_hi[m],
+                                wimg_s + 4u * (uint32_t)P.w_lo[m]);
+      umma::mma_commit(bar);
+    }
+  };
+  auto stage_wait = [&]() {
+    umma::mbar_wait(bar, parity);
+    parity ^= 1u;
+    umma::fence_after_sync();
+  };
+
+  for (;;) {
+    if (wtid == 0) {
+      const long long u = atomicAdd(reinterpret_cast<unsigned int*>(sched), 1u);
+      if (u < total_units) {
+        const int chunk = (int)(u / ntiles);
+        const int tile = (int)(u - (long long)chunk * ntiles);
+        if (chunk > 0) {
+          const volatile int* flag = sched + 1 + tile;
+          while (*flag < chunk) __nanosleep(200);
+          __threadfence();
+        }
+      }
+      unit_s[wg] = u;
+    }
+    wg_sync(wg);
+    const long long u = unit_s[wg];
+    if (u >= total_units) break;
+    const int chunk = (int)(u / ntiles);
+    const int tile = (int)(u - (long long)chunk * ntiles);
+    const int ta = t_first + chunk * chunk_len;
+    const int tb = min(ta + chunk_len, t_last);
+    const int row = tile * TC_ROWS + wtid;
+    const bool valid = row < n;
+    const int lrow = valid ? row : n - 1;
+    const float x_l = A.x_dev[lrow], y_l = A.y_dev[lrow];
+    const float r0_l = A.r0_dev[lrow];
+    const float4* trow_g = reinterpret_cast<const float4*>(A.vproj_dev + (size_t)lrow * A.ldvproj);
+    const int64_t grow = A.row_offset + lrow;
+    float zc[ZMAX];
+    // ---- initial state (:842) ----
+    if (chunk == 0 && A.init_mode == 2) {
+#pragma unroll
+      for (int g = 0; g < ZMAX / 4; ++g) {
+        if (g * 4 < zd) {
+          float e[4];
+          normal4(A.seed, grow, T_INIT, NOISE_PROPOSAL, g, e);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) zc[g * 4 + q] = e[q];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d) zc[d] = (d < zd) ? __ldcg(A.z_state_dev + (size_t)lrow * zd + d) : 0.f;
+    }
+    float lp_cur = (need_init && chunk == 0) ? 0.f : __ldcg(A.lp_state_dev + lrow);
+    // ---- iterations (:860-898) ----
+#pragma unroll 1
+    for (int t = ta; t < tb; ++t) {
+      const bool init_pass = t < A.t_begin;
+      float in[KINMAX];   // [proposal z' (zd), x, 0 pad]
+#pragma unroll
+      for (int d = 0; d < KINMAX; ++d) in[d] = 0.f;
+      if (init_pass) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) in[d] = zc[d];
+      } else if (A.eps_dev) {
+        // z' = z + float32(q_sd * eps) (:862): float64 scale, one rounding, then the fp32 add
+        const float* e = A.eps_dev + ((size_t)t * n + lrow) * zd;
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)e[d]));
+      } else {
+#pragma unroll
+        for (int g = 0; g < ZMAX / 4; ++g) {
+          if (g * 4 < zd) {
+            float e[4];
+            normal4(A.seed, grow, (uint32_t)t, NOISE_PROPOSAL, g, e);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (g * 4 + q < zd) in[g * 4 + q] = __fadd_rn(zc[g * 4 + q], (float)(q_sd * (double)e[q]));
+          }
+        }
+      }
+      // prior on the proposal (:812), before x joins the input vector
+      float prior = 0.f;
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) prior = fmaf(in[d], in[d], prior);
+      prior *= 0.5f;
+#pragma unroll
+      for (int d = 0; d < KINMAX; ++d)
+        if (d == zd) in[d] = x_l;
+
+      // ---- g_net layer 1 on the FMA pipe, straight into the A slots ----
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float acc[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(wimg + P.gb1 + c * 16 + q * 4);
+          acc[q * 4 + 0] = b.x; acc[q * 4 + 1] = b.y; acc[q * 4 + 2] = b.z; acc[q * 4 + 3] = b.w;
+        }
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d) {
+          if (d < zd) {
+            const float zv = in[d];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 ww = *reinterpret_cast<const float4*>(wimg + P.gW1 + d * 64 + c * 16 + q * 4);
+              acc[q * 4 + 0] = fmaf(zv, ww.x, acc[q * 4 + 0]);
+              acc[q * 4 + 1] = fmaf(zv, ww.y, acc[q * 4 + 1]);
+              acc[q * 4 + 2] = fmaf(zv, ww.z, acc[q * 4 + 2]);
+              acc[q * 4 + 3] = fmaf(zv, ww.w, acc[q * 4 + 3]);
+            }
+          }
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) umma::split_tf32(leaky(acc[j]), hi[j], lo[j]);
+        umma::st16(trow + tA_hi + c * 16, hi);
+        umma::st16(trow + tA_lo + c * 16, lo);
+      }
+      stage_issue(0);
+      // ---- outcome model while the MMAs run (:809-810) ----
+      float mu_y, raw_y;
+      small_net<KINMAX>(wimg, P.f, P.kin4, in, mu_y, raw_y);
+      const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(raw_y) + 1e-6f;
+      const float dy = y_l - mu_y;
+      const float loss_py = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;
+      float loss_px = 0.f;
+      float sig = wimg[P.bsig];
+      float4 tq[16];
+      stage_wait();
+#pragma unroll 1
+      for (int m = 1; m < n_mma; ++m) {
+        // epilogue of MMA layer m-1 (a hidden layer of g_net)
+        {
+          uint32_t r0[32], r1[32];
+          umma::ld32(trow + tD, r0);
+          umma::ld32(trow + tD + 32, r1);
+          umma::wait_ld();
+          const float* bias = wimg + P.gb[m - 1];
+          if (m == n_mma - 1) {
+            act_block32<true>(r0, bias, wimg + P.wsig, sig, trow + tA_hi, trow + tA_lo);
+            act_block32<true>(r1, bias + 32, wimg + P.wsig + 32, sig, trow + tA_hi + 32, trow + tA_lo + 32);
+          } else {
+            act_block32<false>(r0, bias, nullptr, sig, trow + tA_hi, trow + tA_lo);
+            act_block32<false>(r1, bias + 32, nullptr, sig, trow + tA_hi + 32, trow + tA_lo + 32);
+          }
+        }
+        stage_issue(m);
+        if (m == 1) {
+          // ---- treatment model (:803-807) ----
+          float mu_x, raw_x;
+          small_net<KINMAX>(wimg, P.h, P.kin4, in, mu_x, raw_x);
+          if (P.binary) {
+            loss_px = fmaxf(mu_x, 0.f) - mu_x * x_l + log1pf(expf(-fabsf(mu_x)));
+          } else {
+            const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(raw_x) + 1e-6f;
+            const float dx = x_l - mu_x;
+            loss_px = (dx * dx) / (2.f * s2x) + logf(s2x) / 2.f;
+          }
+        }
+        if (m == n_mma - 1) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q) tq[q] = __ldg(trow_g + q);   // projected covariates of the row
+        }
+        stage_wait();
+      }
+      // ---- covariate likelihood in the row space of g's last layer (:800-801) ----
+      float sse = 0.f;
+      {
+        uint32_t r0[32], r1[32];
+        umma::ld32(trow + tD, r0);
+        umma::ld32(trow + tD + 32, r1);
+        umma::wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float d0 = __uint_as_float(r0[q * 4 + 0]) - tq[q].x;
+          const float d1 = __uint_as_float(r0[q * 4 + 1]) - tq[q].y;
+          const float d2 = __uint_as_float(r0[q * 4 + 2]) - tq[q].z;
+          const float d3 = __uint_as_float(r0[q * 4 + 3]) - tq[q].w;
+          sse = fmaf(d0, d0, sse); sse = fmaf(d1, d1, sse); sse = fmaf(d2, d2, sse); sse = fmaf(d3, d3, sse);
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float d0 = __uint_as_float(r1[q * 4 + 0]) - tq[8 + q].x;
+          const float d1 = __uint_as_float(r1[q * 4 + 1]) - tq[8 + q].y;
+          const float d2 = __uint_as_float(r1[q * 4 + 2]) - tq[8 + q].z;
+          const float d3 = __uint_as_float(r1[q * 4 + 3]) - tq[8 + q].w;
+          sse = fmaf(d0, d0, sse); sse = fmaf(d1, d1, sse); sse = fmaf(d2, d2, sse); sse = fmaf(d3, d3, sse);
+        }
+      }
+      const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(sig) + 1e-6f;
+      const float loss_pv = (sse + r0_l) / (2.f * s2v) + ((float)P.p * logf(s2v)) / 2.f;
+      const float lp_prop = -(((loss_pv + loss_px) + loss_py) + prior);              // :814-816
+      if (init_pass) {
+        lp_cur = lp_prop;
+        continue;
+      }
+      // accept: u < exp(min(lp' - lp, 0))  (:868-870); a NaN ratio never accepts
+      const float dlp = lp_prop - lp_cur;
+      const float ratio = (dlp < 0.f) ? expf(dlp) : ((dlp >= 0.f) ? 1.f : __int_as_float(0x7fc00000));
+      bool acc;
+      if (A.u_dev) acc = A.u_dev[(size_t)t * n + lrow] < (double)ratio;
+      else acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT) < ratio;
+      if (acc) {                                                                     // :871
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) zc[d] = in[d];
+        lp_cur = lp_prop;
+      }
+      if (A.accept_mask_dev && valid) A.accept_mask_dev[(size_t)t * n + row] = acc ? 1 : 0;
+      if (A.lp_trace_dev && valid) A.lp_trace_dev[(size_t)t * n + row] = lp_prop;
+      if (A.accept_count_dev) {
+        const unsigned b = __ballot_sync(0xffffffffu, acc && valid);
+        if (lane == 0 && b) atomicAdd(A.accept_count_dev + t, __popc(b));
+      }
+      if (t >= A.burn_in && A.out_samples_dev && valid) {                            // :895-896
+        float* dst = A.out_samples_dev + ((size_t)(t - A.burn_in) * n + row) * zd;
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) dst[d] = zc[d];
+      }
+    }
+    // ---- save state, publish the chunk ----
+    if (valid) {
+      if (D.mode == 0) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) A.z_state_dev[(size_t)row * zd + d] = zc[d];
+      }
+      A.lp_state_dev[row] = lp_cur;
+    }
+    __threadfence();
+    wg_sync(wg);
+    if (wtid == 0) *reinterpret_cast<volatile int*>(sched + 1 + tile) = chunk + 1;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc512(tmem0);
+}
+
+}  // namespace bgm

@@ -12,7 +12,9 @@
  * passed as void* (NULL = default stream).  Every function returns 0 on success or
  * a negative bgm_status; bgm_last_error() gives the message (thread-local).  No
  * hidden device allocation happens outside the *_create functions.  All arithmetic
- * is IEEE fp32 on the CUDA cores (no TF32 / fast-math), row-major layouts.
+ * is IEEE fp32 (no fast-math, no plain-TF32 rounding): on the CUDA cores, or -- the
+ * sampler's tensor engine, see bgm_causal_set_sampler -- as error-compensated 3xTF32
+ * products with fp32 accumulation on the tensor cores.  Row-major layouts.
  */
 #ifndef BGM_B200_H
 #define BGM_B200_H
@@ -66,6 +68,21 @@ void bgm_causal_destroy(bgm_causal* m);
  * 0, or the width H of the projected covariates (see bgm_causal_project). */
 int bgm_causal_info(const bgm_causal* m, int* smem_bytes, int* warps_per_cta, int* n_ops,
                     long long* macs_per_row, long long* issued_macs_per_row, int* proj_dim);
+
+/* Sampler engines.  Two execution plans of the SAME algorithm (same arguments, same
+ * Philox streams) serve bgm_causal_logpost / bgm_causal_mh:
+ *   1  SIMT   : every layer on the fp32 FMA pipe (causal.cuh), any net shape;
+ *   2  tensor : the 64x64 layers of g_net on the 5th-gen tensor cores (tcgen05, accumulators
+ *               and activations in TMEM) as error-compensated 3xTF32 products (fp32-level
+ *               error, no plain-TF32 rounding anywhere), everything else on the FMA pipe
+ *               (causal_tc.cuh).  Needs g hidden layers of 64 units (>= 2 of them), v_dim > 72
+ *               (projected likelihood) and f / h units [64, 32, 8].
+ * kind 0 = auto (tensor when available).  bgm_causal_sampler_info reports the engine the
+ * next launch will use, whether the tensor engine exists for this model, its shared-memory
+ * bytes and the multiply-adds it issues per row per evaluation (tensor + FMA pipe). */
+int bgm_causal_set_sampler(bgm_causal* m, int kind);
+int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_available,
+                            int* tensor_smem_bytes, long long* tensor_issued_macs_per_row);
 
 /* Covariate projection.  With mu_v = h M + b (M: H x v_dim, the last layer of g_net,
  * H <= 64 < v_dim) and M^T = U R (thin QR, computed at create time in float64),

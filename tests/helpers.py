@@ -38,9 +38,12 @@ def causal_data(n, v_dim, binary=False, seed=0):
     return x, y, v
 
 
-def product_model(params, nets):
+def product_model(params, nets, engine=None):
+    """engine: None / 'auto', 'simt' or 'tensor' (CausalBGM.set_sampler_engine)."""
     from bayesgm_b200 import CausalBGM
     m = CausalBGM(params=params, random_seed=None)
+    if engine:
+        m.set_sampler_engine(engine)
     flat = lambda layers: [a for W, b in layers for a in (W, b)]
     m.set_weights(g=flat(nets['g']), e=flat(nets['e']), f=flat(nets['f']), h=flat(nets['h']))
     return m

@@ -37,16 +37,33 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("n,v_dim,z_dims,binary,extra", CASES)
-def test_log_posterior_parity(n, v_dim, z_dims, binary, extra):
+# every case on the fp32 FMA-pipe engine; the standard net shapes (CASES[:4]) also on the
+# tensor-core engine (3xTF32) -- same tolerances for both
+ENGINE_CASES = [c + ('simt',) for c in CASES] + [c + ('tensor',) for c in CASES[:4]]
+
+
+@pytest.mark.parametrize("n,v_dim,z_dims,binary,extra,engine", ENGINE_CASES)
+def test_log_posterior_parity(n, v_dim, z_dims, binary, extra, engine):
     params = causal_params(v_dim, z_dims, binary, **extra)
     nets = causal_nets(params)
     x, y, v = causal_data(n, v_dim, binary)
     z = np.random.RandomState(11).standard_normal((n, sum(z_dims))).astype(np.float32)
     want = causal.log_posterior(params, nets, x, y, v, z)
-    got = product_model(params, nets).get_log_posterior(x, y, v, z)
+    m = product_model(params, nets, engine)
+    got = m.get_log_posterior(x, y, v, z)
+    assert m.sampler_info()['engine'] == engine
     assert got.shape == (n,) and got.dtype == np.float32
     lp_close(got, want)
+
+
+def test_auto_engine_selection():
+    std = product_model(causal_params(200, [1, 1, 1, 2]), causal_nets(causal_params(200, [1, 1, 1, 2])))
+    assert std.sampler_info()['engine'] == 'tensor' and std.sampler_info()['tensor_available']
+    p = causal_params(10, [1, 1, 1, 0], g_units=[8, 8], f_units=[8, 8], h_units=[8, 8])
+    small = product_model(p, causal_nets(p))
+    assert small.sampler_info()['engine'] == 'simt' and not small.sampler_info()['tensor_available']
+    with pytest.raises(Exception):
+        small.set_sampler_engine('tensor')
 
 
 def compare_chains(samples_g, tr_g, samples_o, tr_o, u, burn_in):
@@ -77,8 +94,12 @@ def compare_chains(samples_g, tr_g, samples_o, tr_o, u, burn_in):
     return clean.mean()
 
 
-@pytest.mark.parametrize("n,v_dim,z_dims,binary,extra", CASES[:4] + CASES[5:])
-def test_mh_injected_noise_state_for_state(n, v_dim, z_dims, binary, extra):
+MH_CASES = ([c + ('simt',) for c in CASES[:4] + CASES[5:]] + [c + ('tensor',) for c in CASES[:4]] +
+            [(300, 200, [1, 1, 1, 2], False, {}, 'tensor')])   # 3 row tiles of 128, ragged last one
+
+
+@pytest.mark.parametrize("n,v_dim,z_dims,binary,extra,engine", MH_CASES)
+def test_mh_injected_noise_state_for_state(n, v_dim, z_dims, binary, extra, engine):
     params = causal_params(v_dim, z_dims, binary, **extra)
     nets = causal_nets(params)
     data = causal_data(n, v_dim, binary)
@@ -86,7 +107,7 @@ def test_mh_injected_noise_state_for_state(n, v_dim, z_dims, binary, extra):
     nz = injected_noise(n, sum(z_dims), burn_in + n_keep)
     so, tro = causal.mh_sampler(params, nets, data, q_sd=0.3, burn_in=burn_in, n_keep=n_keep,
                                 noise=causal.InjectedNoise(**nz), return_trace=True)
-    m = product_model(params, nets)
+    m = product_model(params, nets, engine)
     sg, trg = m.metropolis_hastings_sampler(data, q_sd=0.3, burn_in=burn_in, n_keep=n_keep, noise=nz,
                                             return_trace=True, verbose=0)
     assert sg.shape == so.shape == (n_keep, n, sum(z_dims)) and sg.dtype == np.float32
@@ -97,14 +118,15 @@ def test_mh_injected_noise_state_for_state(n, v_dim, z_dims, binary, extra):
     assert 0.0 < trg['accept'].mean() < 1.0
 
 
-def test_mh_philox_run_replayed_through_oracle():
+@pytest.mark.parametrize("engine", ['simt', 'tensor'])
+def test_mh_philox_run_replayed_through_oracle(engine):
     """The production noise path: sample with the in-kernel Philox stream, dump the
     very same stream, replay it through the oracle."""
     params = causal_params(200, [1, 1, 1, 2])
     nets = causal_nets(params)
     data = causal_data(200, 200)
     burn_in, n_keep, seed = 20, 20, 20261017
-    m = product_model(params, nets)
+    m = product_model(params, nets, engine)
     sg, trg = m.metropolis_hastings_sampler(data, q_sd=0.5, burn_in=burn_in, n_keep=n_keep, seed=seed,
                                             return_trace=True, verbose=0)
     nz = m.philox_noise(seed, 200, burn_in + n_keep)
