@@ -142,17 +142,17 @@ static void split_tf32_host(float w, float& hi, float& lo) {
   b = (b + 0x1000u) & 0xffffe000u;
   memcpy(&lo, &b, 4);
 }
-// Wm [64][64] (Keras [in][out]) -> two [16][64][4] blocks (umma.cuh layout), returns the hi offset
-static void pack_mma64(std::vector<float>& img, const std::vector<float>& Wm, int& off_hi, int& off_lo) {
+// Wm [64][N] (Keras [in][out]) -> two [16][N][4] blocks (umma.cuh layout), hi and lo
+static void pack_mma_k64(std::vector<float>& img, const std::vector<float>& Wm, int N, int& off_hi, int& off_lo) {
   off_hi = (int)img.size();
-  img.resize(img.size() + 4096, 0.f);
+  img.resize(img.size() + (size_t)64 * N, 0.f);
   off_lo = (int)img.size();
-  img.resize(img.size() + 4096, 0.f);
+  img.resize(img.size() + (size_t)64 * N, 0.f);
   for (int k = 0; k < 64; ++k)
-    for (int n = 0; n < 64; ++n) {
+    for (int n = 0; n < N; ++n) {
       float hi, lo;
-      split_tf32_host(Wm[(size_t)k * 64 + n], hi, lo);
-      const int idx = (k >> 2) * 256 + n * 4 + (k & 3);
+      split_tf32_host(Wm[(size_t)k * N + n], hi, lo);
+      const int idx = (k >> 2) * (N * 4) + n * 4 + (k & 3);
       img[off_hi + idx] = hi;
       img[off_lo + idx] = lo;
     }
@@ -166,20 +166,16 @@ static int push_floats(std::vector<float>& img, const float* p, size_t count) {
 static bool small_net_shape(const HostNet& n) {
   return n.L == 4 && n.dims[1] == 64 && n.dims[2] == 32 && n.dims[3] == 8 && n.dims[4] == 2;
 }
-// first-layer rows remapped onto [z.., x] -> transposed [64][kin4]
-static void pack_small_net(std::vector<float>& img, const HostNet& net, const std::vector<int>& rows, int kin4,
-                           SmallNet& o) {
-  std::vector<float> w1t((size_t)64 * kin4, 0.f);
-  for (size_t r = 0; r < rows.size(); ++r)
-    for (int k = 0; k < 64; ++k) w1t[(size_t)k * kin4 + rows[r]] = net.W[0][r * 64 + k];
-  o.W1t = push_floats(img, w1t.data(), w1t.size());
-  o.b1 = push_floats(img, net.b[0].data(), 64);
-  o.W2 = push_floats(img, net.W[1].data(), 64 * 32);
-  o.b2 = push_floats(img, net.b[1].data(), 32);
-  o.W3 = push_floats(img, net.W[2].data(), 32 * 8);
-  o.b3 = push_floats(img, net.b[2].data(), 8);
-  o.W4 = push_floats(img, net.W[3].data(), 8 * 2);
-  o.b4 = push_floats(img, net.b[3].data(), 2);
+// first layer [in][64] with its rows remapped onto the input vector [z.., x] -> [zd+1][64]
+static int pack_first_layer(std::vector<float>& img, const HostNet& net, const std::vector<int>& rows, int zd,
+                            unsigned long long& mask) {
+  std::vector<float> w((size_t)(zd + 1) * 64, 0.f);
+  mask = 0;
+  for (size_t r = 0; r < rows.size(); ++r) {
+    mask |= 1ull << rows[r];
+    for (int k = 0; k < 64; ++k) w[(size_t)rows[r] * 64 + k] = net.W[0][r * 64 + k];
+  }
+  return push_floats(img, w.data(), w.size());
 }
 
 }  // namespace bgm
@@ -411,12 +407,26 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
     bool ok = proj_dim == 64 && g.L >= 3 && g.L - 1 <= TC_MAX_MMA && small_net_shape(f) && small_net_shape(h);
     for (int l = 1; l < g.L; ++l) ok = ok && g.dims[l] == 64;
     if (ok) {
-      T.zd = zd; T.kin4 = kin; T.p = v_dim; T.binary = P.binary;
+      T.zd = zd; T.p = v_dim; T.binary = P.binary;
       T.s2v = P.s2v; T.s2x = P.s2x; T.s2y = P.s2y;
       T.n_mma = g.L - 1;
       for (int m = 0; m < T.n_mma; ++m) {
         const bool last = m == T.n_mma - 1;
-        pack_mma64(tc_image, last ? proj_RT : g.W[m + 1], T.w_hi[m], T.w_lo[m]);
+        pack_mma_k64(tc_image, last ? proj_RT : g.W[m + 1], 64, T.w_hi[m], T.w_lo[m]);
+      }
+      pack_mma_k64(tc_image, f.W[1], 32, T.f2_hi, T.f2_lo);
+      pack_mma_k64(tc_image, h.W[1], 32, T.h2_hi, T.h2_lo);
+      {
+        // [f_h2 | h_h2] (64) -> [f_h3 (8) | h_h3 (8)], block diagonal
+        std::vector<float> w3((size_t)64 * 16, 0.f), b3(16);
+        for (int k = 0; k < 32; ++k)
+          for (int c = 0; c < 8; ++c) {
+            w3[(size_t)k * 16 + c] = f.W[2][(size_t)k * 8 + c];
+            w3[(size_t)(32 + k) * 16 + 8 + c] = h.W[2][(size_t)k * 8 + c];
+          }
+        for (int c = 0; c < 8; ++c) { b3[c] = f.b[2][c]; b3[8 + c] = h.b[2][c]; }
+        pack_mma_k64(tc_image, w3, 16, T.w3_hi, T.w3_lo);
+        T.b3 = push_floats(tc_image, b3.data(), 16);
       }
       for (int m = 0; m + 1 < T.n_mma; ++m) T.gb[m] = push_floats(tc_image, g.b[m + 1].data(), 64);
       T.gW1 = push_floats(tc_image, g.W[0].data(), (size_t)zd * 64);
@@ -426,14 +436,22 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
       for (int k = 0; k < 64; ++k) wsig[k] = g.W[g.L - 1][(size_t)k * NL + v_dim];
       T.wsig = push_floats(tc_image, wsig.data(), 64);
       T.bsig = push_floats(tc_image, &g.b[g.L - 1][v_dim], 1);
-      pack_small_net(tc_image, f, f_rows, kin, T.f);
-      pack_small_net(tc_image, h, h_rows, kin, T.h);
+      T.fW1 = pack_first_layer(tc_image, f, f_rows, zd, T.fmask);
+      T.fb1 = push_floats(tc_image, f.b[0].data(), 64);
+      T.hW1 = pack_first_layer(tc_image, h, h_rows, zd, T.hmask);
+      T.hb1 = push_floats(tc_image, h.b[0].data(), 64);
+      T.fb2 = push_floats(tc_image, f.b[1].data(), 32);
+      T.hb2 = push_floats(tc_image, h.b[1].data(), 32);
+      T.fW4 = push_floats(tc_image, f.W[3].data(), 16);
+      T.fb4 = push_floats(tc_image, f.b[3].data(), 2);
+      T.hW4 = push_floats(tc_image, h.W[3].data(), 16);
+      T.hb4 = push_floats(tc_image, h.b[3].data(), 2);
       while (tc_image.size() % 4) tc_image.push_back(0.f);
       T.image_floats = (int)tc_image.size();
       T.enabled = 1;
       // tensor pipe: 3 TF32 products per FMA of the 64x64 layers; FMA pipe: the narrow layers
-      tc_issued = 3LL * 4096 * T.n_mma + (long long)zd * 64 + 64 +
-                  2LL * ((long long)kin * 64 + 64 * 32 + 32 * 8 + 8 * 2);
+      tc_issued = 3LL * (4096LL * T.n_mma + 2 * 64 * 32 + 64 * 16) + (long long)zd * 64 + 64 +
+                  (long long)(f.dims[0] + h.dims[0]) * 64 + 2 * 16;
     }
   }
 

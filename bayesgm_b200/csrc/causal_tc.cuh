@@ -14,10 +14,11 @@
 //    hi/lo, into TMEM (tcgen05.st), one elected thread issues 24 tcgen05.mma (A from TMEM,
 //    weights from the shared-memory image), the accumulator row comes back with tcgen05.ld
 //    for bias + LeakyReLU + split.  fp32-level error.
-//  * the narrow nets (g's first layer, f_net, h_net) stay on the fp32 FMA pipe, one row per
-//    thread with warp-uniform (broadcast) weight loads, in the same k order as the SIMT
-//    engine; f_net / h_net are evaluated while the thread's MMAs are in flight.
-//  * two warpgroups per CTA (one CTA per SM, 512 TMEM columns = 2 x [A_hi 64 | A_lo 64 | D 64 | -])
+//  * f_net / h_net: their 64->32 layers and (as one block-diagonal 64->16 product) their 32->8
+//    layers run the same way; only the first layers (a handful of inputs) and the 8->2 heads
+//    stay on the fp32 FMA pipe, one row per thread with warp-uniform (broadcast) weight loads,
+//    scheduled while the thread's MMAs are in flight.  Per iteration: 3 + (g.L-1) MMA stages.
+//  * two warpgroups per CTA (one CTA per SM, 512 TMEM columns = 2 x [A_hi 64 | A_lo 64 | D 64 | P 64])
 //    work on different tiles, so one tile's epilogue overlaps the other's MMAs.
 #pragma once
 #include "causal.cuh"
@@ -28,23 +29,26 @@ namespace bgm {
 constexpr int TC_ROWS = 128;
 constexpr int TC_MAX_MMA = 8;
 
-struct SmallNet {      // in -> 64 -> 32 -> 8 -> 2; float offsets into the image
-  int W1t, b1;         // [64][kin4]: first layer transposed over the padded input [z.., x, 0..]
-  int W2, b2;          // [64][32]
-  int W3, b3;          // [32][8]
-  int W4, b4;          // [8][2]
-};
+// TMEM columns of one warpgroup (256 of the CTA's 512)
+constexpr uint32_t TC_A_HI = 0, TC_A_LO = 64, TC_D = 128, TC_P = 192;
 
 struct TcProgram {
   int enabled;
-  int zd, kin4, p, binary;
+  int zd, p, binary;
   float s2v, s2x, s2y;
   int n_mma;                                  // g_net layers on the tensor cores (g.L - 1)
-  int w_hi[TC_MAX_MMA], w_lo[TC_MAX_MMA];     // [16][64][4] tf32 images (hi / lo)
-  int gb[TC_MAX_MMA];                         // bias added after MMA layer m (m < n_mma-1)
+  int w_hi[TC_MAX_MMA], w_lo[TC_MAX_MMA];     // g: [16][64][4] tf32 images (hi / lo), float offsets
+  int gb[TC_MAX_MMA];                         // bias added after g MMA layer m (m < n_mma-1)
   int gW1, gb1;                               // g first layer [zd][64], bias[64]
   int wsig, bsig;                             // sigma_v head: column v_dim of g's last layer
-  SmallNet f, h;
+  // f / h: in -> 64 -> 32 -> 8 -> 2
+  int fW1, fb1, hW1, hb1;                     // first layers over the input vector [z.., x]: [zd+1][64]
+  unsigned long long fmask, hmask;            // input rows each net really uses
+  int f2_hi, f2_lo, h2_hi, h2_lo;             // second layers, [16][32][4] images
+  int fb2, hb2;
+  int w3_hi, w3_lo, b3;                       // third layers of f and h as one block-diagonal
+                                              // [f_h2 | h_h2] (64) -> [f 8 | h 8]: [16][16][4]
+  int fW4, fb4, hW4, hb4;                     // [8][2], [2]
   int image_floats;
 };
 
@@ -52,72 +56,60 @@ __device__ __forceinline__ void wg_sync(int wg) {
   if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
+__device__ __forceinline__ float leaky_mx(float v) { return fmaxf(v, 0.2f * v); }  // == leaky(v)
 
-// f_net / h_net for the thread's row.  `in` = [z (zd), x, 0 pad] (kin4 entries used).
+// First layer of a net on the FMA pipe for the thread's row: out = LeakyReLU(b + in W), 64 wide,
+// rows of W (inputs) taken in ascending order like the SIMT engine; `mask` skips the rows
+// whose weights are structurally zero for this net.
 template <int KINMAX>
-__device__ __forceinline__ void small_net(const float* __restrict__ w, const SmallNet& o, int kin4,
-                                          const float (&in)[KINMAX], float& out0, float& out1) {
-  float acc2[32];
+__device__ __forceinline__ void first_layer(const float* __restrict__ W, const float* __restrict__ b,
+                                            unsigned long long mask, int nin, const float (&in)[KINMAX],
+                                            float (&out)[64]) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 b = *reinterpret_cast<const float4*>(w + o.b2 + q * 4);
-    acc2[q * 4 + 0] = b.x; acc2[q * 4 + 1] = b.y; acc2[q * 4 + 2] = b.z; acc2[q * 4 + 3] = b.w;
+  for (int q = 0; q < 16; ++q) {
+    const float4 bb = *reinterpret_cast<const float4*>(b + q * 4);
+    out[q * 4 + 0] = bb.x; out[q * 4 + 1] = bb.y; out[q * 4 + 2] = bb.z; out[q * 4 + 3] = bb.w;
   }
-  const float* W1t = w + o.W1t;
-  const float* b1 = w + o.b1;
-  const float* W2 = w + o.W2;
-#pragma unroll 2
-  for (int k = 0; k < 64; ++k) {
-    float a = b1[k];
-    const float* w1 = W1t + k * kin4;
 #pragma unroll
-    for (int q = 0; q < KINMAX / 4; ++q) {
-      if (q * 4 < kin4) {
-        const float4 ww = *reinterpret_cast<const float4*>(w1 + q * 4);
-        a = fmaf(in[q * 4 + 0], ww.x, a);
-        a = fmaf(in[q * 4 + 1], ww.y, a);
-        a = fmaf(in[q * 4 + 2], ww.z, a);
-        a = fmaf(in[q * 4 + 3], ww.w, a);
+  for (int d = 0; d < KINMAX; ++d) {
+    if (d < nin && ((mask >> d) & 1ull)) {
+      const float zv = in[d];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 ww = *reinterpret_cast<const float4*>(W + d * 64 + q * 4);
+        out[q * 4 + 0] = fmaf(zv, ww.x, out[q * 4 + 0]);
+        out[q * 4 + 1] = fmaf(zv, ww.y, out[q * 4 + 1]);
+        out[q * 4 + 2] = fmaf(zv, ww.z, out[q * 4 + 2]);
+        out[q * 4 + 3] = fmaf(zv, ww.w, out[q * 4 + 3]);
       }
     }
-    a = leaky(a);
-    const float4* w2 = reinterpret_cast<const float4*>(W2 + k * 32);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 ww = w2[q];
-      acc2[q * 4 + 0] = fmaf(a, ww.x, acc2[q * 4 + 0]);
-      acc2[q * 4 + 1] = fmaf(a, ww.y, acc2[q * 4 + 1]);
-      acc2[q * 4 + 2] = fmaf(a, ww.z, acc2[q * 4 + 2]);
-      acc2[q * 4 + 3] = fmaf(a, ww.w, acc2[q * 4 + 3]);
-    }
-  }
-  float acc3[8];
-  {
-    const float4 ba = *reinterpret_cast<const float4*>(w + o.b3);
-    const float4 bb = *reinterpret_cast<const float4*>(w + o.b3 + 4);
-    acc3[0] = ba.x; acc3[1] = ba.y; acc3[2] = ba.z; acc3[3] = ba.w;
-    acc3[4] = bb.x; acc3[5] = bb.y; acc3[6] = bb.z; acc3[7] = bb.w;
   }
 #pragma unroll
-  for (int k = 0; k < 32; ++k) {
-    const float a = leaky(acc2[k]);
-    const float4 wa = *reinterpret_cast<const float4*>(w + o.W3 + k * 8);
-    const float4 wb = *reinterpret_cast<const float4*>(w + o.W3 + k * 8 + 4);
-    acc3[0] = fmaf(a, wa.x, acc3[0]); acc3[1] = fmaf(a, wa.y, acc3[1]);
-    acc3[2] = fmaf(a, wa.z, acc3[2]); acc3[3] = fmaf(a, wa.w, acc3[3]);
-    acc3[4] = fmaf(a, wb.x, acc3[4]); acc3[5] = fmaf(a, wb.y, acc3[5]);
-    acc3[6] = fmaf(a, wb.z, acc3[6]); acc3[7] = fmaf(a, wb.w, acc3[7]);
-  }
-  float o0 = w[o.b4], o1 = w[o.b4 + 1];
+  for (int j = 0; j < 64; ++j) out[j] = leaky_mx(out[j]);
+}
+
+// activation row (fp32, 64 wide) -> hi / lo halves in the A slots of the thread's TMEM lane
+__device__ __forceinline__ void split_store64(const float (&a)[64], uint32_t tA_hi, uint32_t tA_lo) {
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const float a = leaky(acc3[k]);
-    const float2 ww = *reinterpret_cast<const float2*>(w + o.W4 + k * 2);
-    o0 = fmaf(a, ww.x, o0);
-    o1 = fmaf(a, ww.y, o1);
+  for (int c = 0; c < 2; ++c) {
+    uint32_t hi[32], lo[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) umma::split_tf32(a[c * 32 + j], hi[j], lo[j]);
+    umma::st32(tA_hi + c * 32, hi);
+    umma::st32(tA_lo + c * 32, lo);
   }
-  out0 = o0;
-  out1 = o1;
+}
+
+// r (32 raw accumulator columns) -> LeakyReLU(r + bias) as floats
+__device__ __forceinline__ void bias_act32(const uint32_t (&r)[32], const float* __restrict__ bias, float* out) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + q * 4);
+    out[q * 4 + 0] = leaky_mx(__uint_as_float(r[q * 4 + 0]) + b.x);
+    out[q * 4 + 1] = leaky_mx(__uint_as_float(r[q * 4 + 1]) + b.y);
+    out[q * 4 + 2] = leaky_mx(__uint_as_float(r[q * 4 + 2]) + b.z);
+    out[q * 4 + 3] = leaky_mx(__uint_as_float(r[q * 4 + 3]) + b.w);
+  }
 }
 
 // bias + LeakyReLU + hi/lo split of 32 accumulator columns, back into the A slots.
@@ -137,7 +129,7 @@ __device__ __forceinline__ void act_block32(uint32_t (&r)[32], const float* __re
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const float a = leaky(__uint_as_float(r[q * 4 + i]) + bb[i]);
+      const float a = leaky_mx(__uint_as_float(r[q * 4 + i]) + bb[i]);
       if constexpr (SIG) sig = fmaf(a, ws[i], sig);
       umma::split_tf32(a, r[q * 4 + i], lo[q * 4 + i]);
     }
@@ -150,7 +142,7 @@ template <int ZMAX>
 __global__ void __launch_bounds__(256, 1)
 causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict__ image,
                     const __grid_constant__ MhDev D) {
-  constexpr int KINMAX = ZMAX + 4;
+  constexpr int KINMAX = ZMAX + 1;
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar_img;
   __shared__ uint64_t bar_mma[2];
@@ -173,9 +165,8 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem0 = tmem_slot;
-  const uint32_t tbase = tmem0 + (uint32_t)wg * 256u;             // MMA operand addresses (lane 0)
-  const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 lanes
-  const uint32_t tA_hi = 0, tA_lo = 64, tD = 128;                 // column offsets
+  const uint32_t tbase = tmem0 + (uint32_t)wg * 256u;                  // MMA operand addresses (lane 0)
+  const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes
   const uint32_t bar = umma::smem_addr(&bar_mma[wg]);
   uint32_t parity = 0;
 
@@ -192,17 +183,11 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
   const long long total_units = (long long)ntiles * nchunks;
   const int n_mma = P.n_mma;
 
-  // One MMA layer: publish the A rows written by the 128 threads, one thread issues.
-  auto stage_issue = [&](int m) {
+  // One MMA stage: publish the A rows written by the 128 threads; one thread issues + commits.
+  auto publish = [&]() {
     umma::wait_st();
     umma::fence_before_sync();
     wg_sync(wg);
-    if (wtid == 0) {
-      umma::fence_after_sync();
-      umma::issue_layer_k64<64>(tbase + tD, tbase + tA_hi, tbase + tA_lo, wimg_s + 4u * (uint32_t)P.w_hi[m],
-                                wimg_s + 4u * (uint32_t)P.w_lo[m]);
-      umma::mma_commit(bar);
-    }
   };
   auto stage_wait = [&]() {
     umma::mbar_wait(bar, parity);
@@ -259,7 +244,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
 #pragma unroll 1
     for (int t = ta; t < tb; ++t) {
       const bool init_pass = t < A.t_begin;
-      float in[KINMAX];   // [proposal z' (zd), x, 0 pad]
+      float in[KINMAX];   // [proposal z' (zd), x]
 #pragma unroll
       for (int d = 0; d < KINMAX; ++d) in[d] = 0.f;
       if (init_pass) {
@@ -294,75 +279,119 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       for (int d = 0; d < KINMAX; ++d)
         if (d == zd) in[d] = x_l;
 
-      // ---- g_net layer 1 on the FMA pipe, straight into the A slots ----
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float acc[16];
+      // ---- f_net layer 1 (FMA pipe) -> A; stage F2: f layer 2 on the tensor cores ----
+      {
+        float a1[64];
+        first_layer<KINMAX>(wimg + P.fW1, wimg + P.fb1, P.fmask, zd + 1, in, a1);
+        split_store64(a1, trow + TC_A_HI, trow + TC_A_LO);
+      }
+      publish();
+      if (wtid == 0) {
+        umma::fence_after_sync();
+        umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.f2_hi,
+                                  wimg_s + 4u * (uint32_t)P.f2_lo);
+        umma::mma_commit(bar);
+      }
+      float h2[64];   // [f_h2 (32) | h_h2 (32)], post-activation
+      {
+        // h_net layer 1 while f's MMAs run
+        float a1[64];
+        first_layer<KINMAX>(wimg + P.hW1, wimg + P.hb1, P.hmask, zd + 1, in, a1);
+        stage_wait();
+        uint32_t r[32];
+        umma::ld32(trow + TC_P, r);
+        umma::wait_ld();
+        bias_act32(r, wimg + P.fb2, h2);
+        split_store64(a1, trow + TC_A_HI, trow + TC_A_LO);
+      }
+      publish();
+      if (wtid == 0) {
+        umma::fence_after_sync();
+        umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.h2_hi,
+                                  wimg_s + 4u * (uint32_t)P.h2_lo);
+        umma::mma_commit(bar);
+      }
+      float g1[64];   // g_net layer 1 while h's MMAs run
+      first_layer<KINMAX>(wimg + P.gW1, wimg + P.gb1, ~0ull, zd, in, g1);
+      stage_wait();
+      {
+        uint32_t r[32];
+        umma::ld32(trow + TC_P, r);
+        umma::wait_ld();
+        bias_act32(r, wimg + P.hb2, h2 + 32);
+        split_store64(h2, trow + TC_A_HI, trow + TC_A_LO);
+      }
+      publish();
+      if (wtid == 0) {
+        umma::fence_after_sync();
+        umma::issue_layer_k64<16>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w3_hi,
+                                  wimg_s + 4u * (uint32_t)P.w3_lo);
+        umma::mma_commit(bar);
+      }
+      stage_wait();
+      float loss_py, loss_px;
+      {
+        uint32_t r[16];
+        umma::ld16(trow + TC_P, r);
+        umma::wait_ld();
+        float h3[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 b = *reinterpret_cast<const float4*>(wimg + P.gb1 + c * 16 + q * 4);
-          acc[q * 4 + 0] = b.x; acc[q * 4 + 1] = b.y; acc[q * 4 + 2] = b.z; acc[q * 4 + 3] = b.w;
+          const float4 b = *reinterpret_cast<const float4*>(wimg + P.b3 + q * 4);
+          h3[q * 4 + 0] = leaky_mx(__uint_as_float(r[q * 4 + 0]) + b.x);
+          h3[q * 4 + 1] = leaky_mx(__uint_as_float(r[q * 4 + 1]) + b.y);
+          h3[q * 4 + 2] = leaky_mx(__uint_as_float(r[q * 4 + 2]) + b.z);
+          h3[q * 4 + 3] = leaky_mx(__uint_as_float(r[q * 4 + 3]) + b.w);
         }
+        float mu_y = wimg[P.fb4], raw_y = wimg[P.fb4 + 1], mu_x = wimg[P.hb4], raw_x = wimg[P.hb4 + 1];
 #pragma unroll
-        for (int d = 0; d < ZMAX; ++d) {
-          if (d < zd) {
-            const float zv = in[d];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 ww = *reinterpret_cast<const float4*>(wimg + P.gW1 + d * 64 + c * 16 + q * 4);
-              acc[q * 4 + 0] = fmaf(zv, ww.x, acc[q * 4 + 0]);
-              acc[q * 4 + 1] = fmaf(zv, ww.y, acc[q * 4 + 1]);
-              acc[q * 4 + 2] = fmaf(zv, ww.z, acc[q * 4 + 2]);
-              acc[q * 4 + 3] = fmaf(zv, ww.w, acc[q * 4 + 3]);
-            }
-          }
+        for (int k = 0; k < 8; ++k) {
+          const float2 wf = *reinterpret_cast<const float2*>(wimg + P.fW4 + k * 2);
+          const float2 wh = *reinterpret_cast<const float2*>(wimg + P.hW4 + k * 2);
+          mu_y = fmaf(h3[k], wf.x, mu_y);
+          raw_y = fmaf(h3[k], wf.y, raw_y);
+          mu_x = fmaf(h3[8 + k], wh.x, mu_x);
+          raw_x = fmaf(h3[8 + k], wh.y, raw_x);
         }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) umma::split_tf32(leaky(acc[j]), hi[j], lo[j]);
-        umma::st16(trow + tA_hi + c * 16, hi);
-        umma::st16(trow + tA_lo + c * 16, lo);
+        // outcome model (:809-810), treatment model (:803-807)
+        const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(raw_y) + 1e-6f;
+        const float dy = y_l - mu_y;
+        loss_py = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;
+        if (P.binary) {
+          loss_px = fmaxf(mu_x, 0.f) - mu_x * x_l + log1pf(expf(-fabsf(mu_x)));
+        } else {
+          const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(raw_x) + 1e-6f;
+          const float dx = x_l - mu_x;
+          loss_px = (dx * dx) / (2.f * s2x) + logf(s2x) / 2.f;
+        }
       }
-      stage_issue(0);
-      // ---- outcome model while the MMAs run (:809-810) ----
-      float mu_y, raw_y;
-      small_net<KINMAX>(wimg, P.f, P.kin4, in, mu_y, raw_y);
-      const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(raw_y) + 1e-6f;
-      const float dy = y_l - mu_y;
-      const float loss_py = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;
-      float loss_px = 0.f;
+      // ---- g_net: layers 2.. and the projected output layer on the tensor cores ----
+      split_store64(g1, trow + TC_A_HI, trow + TC_A_LO);
       float sig = wimg[P.bsig];
       float4 tq[16];
-      stage_wait();
 #pragma unroll 1
-      for (int m = 1; m < n_mma; ++m) {
-        // epilogue of MMA layer m-1 (a hidden layer of g_net)
-        {
+      for (int m = 0; m < n_mma; ++m) {
+        if (m > 0) {
+          // epilogue of MMA layer m-1 (a hidden layer of g_net)
           uint32_t r0[32], r1[32];
-          umma::ld32(trow + tD, r0);
-          umma::ld32(trow + tD + 32, r1);
+          umma::ld32(trow + TC_D, r0);
+          umma::ld32(trow + TC_D + 32, r1);
           umma::wait_ld();
           const float* bias = wimg + P.gb[m - 1];
           if (m == n_mma - 1) {
-            act_block32<true>(r0, bias, wimg + P.wsig, sig, trow + tA_hi, trow + tA_lo);
-            act_block32<true>(r1, bias + 32, wimg + P.wsig + 32, sig, trow + tA_hi + 32, trow + tA_lo + 32);
+            act_block32<true>(r0, bias, wimg + P.wsig, sig, trow + TC_A_HI, trow + TC_A_LO);
+            act_block32<true>(r1, bias + 32, wimg + P.wsig + 32, sig, trow + TC_A_HI + 32, trow + TC_A_LO + 32);
           } else {
-            act_block32<false>(r0, bias, nullptr, sig, trow + tA_hi, trow + tA_lo);
-            act_block32<false>(r1, bias + 32, nullptr, sig, trow + tA_hi + 32, trow + tA_lo + 32);
+            act_block32<false>(r0, bias, nullptr, sig, trow + TC_A_HI, trow + TC_A_LO);
+            act_block32<false>(r1, bias + 32, nullptr, sig, trow + TC_A_HI + 32, trow + TC_A_LO + 32);
           }
         }
-        stage_issue(m);
-        if (m == 1) {
-          // ---- treatment model (:803-807) ----
-          float mu_x, raw_x;
-          small_net<KINMAX>(wimg, P.h, P.kin4, in, mu_x, raw_x);
-          if (P.binary) {
-            loss_px = fmaxf(mu_x, 0.f) - mu_x * x_l + log1pf(expf(-fabsf(mu_x)));
-          } else {
-            const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(raw_x) + 1e-6f;
-            const float dx = x_l - mu_x;
-            loss_px = (dx * dx) / (2.f * s2x) + logf(s2x) / 2.f;
-          }
+        publish();
+        if (wtid == 0) {
+          umma::fence_after_sync();
+          umma::issue_layer_k64<64>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w_hi[m],
+                                    wimg_s + 4u * (uint32_t)P.w_lo[m]);
+          umma::mma_commit(bar);
         }
         if (m == n_mma - 1) {
 #pragma unroll
@@ -374,8 +403,8 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       float sse = 0.f;
       {
         uint32_t r0[32], r1[32];
-        umma::ld32(trow + tD, r0);
-        umma::ld32(trow + tD + 32, r1);
+        umma::ld32(trow + TC_D, r0);
+        umma::ld32(trow + TC_D + 32, r1);
         umma::wait_ld();
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
