@@ -153,8 +153,11 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
   const uint32_t wimg_s = umma::smem_addr(smem);
 
   const bgm_mh_args& A = D.a;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // warp-uniform by construction (shfl), so that role branches and MMA operands are uniform
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wg = warp >> 2, wtid = tid & 127;
+  const bool issuer_warp = (warp & 3) == 0;
   if (tid == 0) {
     umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
     umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
@@ -164,7 +167,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
-  const uint32_t tmem0 = tmem_slot;
+  const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_slot, 0);
   const uint32_t tbase = tmem0 + (uint32_t)wg * 256u;                  // MMA operand addresses (lane 0)
   const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);   // this warp's 32 lanes
   const uint32_t bar = umma::smem_addr(&bar_mma[wg]);
@@ -286,11 +289,14 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
         split_store64(a1, trow + TC_A_HI, trow + TC_A_LO);
       }
       publish();
-      if (wtid == 0) {
-        umma::fence_after_sync();
-        umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.f2_hi,
-                                  wimg_s + 4u * (uint32_t)P.f2_lo);
-        umma::mma_commit(bar);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          umma::fence_after_sync();
+          umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.f2_hi,
+                                    wimg_s + 4u * (uint32_t)P.f2_lo);
+          umma::mma_commit(bar);
+        }
+        __syncwarp();
       }
       float h2[64];   // [f_h2 (32) | h_h2 (32)], post-activation
       {
@@ -305,11 +311,14 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
         split_store64(a1, trow + TC_A_HI, trow + TC_A_LO);
       }
       publish();
-      if (wtid == 0) {
-        umma::fence_after_sync();
-        umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.h2_hi,
-                                  wimg_s + 4u * (uint32_t)P.h2_lo);
-        umma::mma_commit(bar);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          umma::fence_after_sync();
+          umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.h2_hi,
+                                    wimg_s + 4u * (uint32_t)P.h2_lo);
+          umma::mma_commit(bar);
+        }
+        __syncwarp();
       }
       float g1[64];   // g_net layer 1 while h's MMAs run
       first_layer<KINMAX>(wimg + P.gW1, wimg + P.gb1, ~0ull, zd, in, g1);
@@ -322,11 +331,14 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
         split_store64(h2, trow + TC_A_HI, trow + TC_A_LO);
       }
       publish();
-      if (wtid == 0) {
-        umma::fence_after_sync();
-        umma::issue_layer_k64<16>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w3_hi,
-                                  wimg_s + 4u * (uint32_t)P.w3_lo);
-        umma::mma_commit(bar);
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          umma::fence_after_sync();
+          umma::issue_layer_k64<16>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w3_hi,
+                                    wimg_s + 4u * (uint32_t)P.w3_lo);
+          umma::mma_commit(bar);
+        }
+        __syncwarp();
       }
       stage_wait();
       float loss_py, loss_px;
@@ -387,11 +399,14 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
           }
         }
         publish();
-        if (wtid == 0) {
-          umma::fence_after_sync();
-          umma::issue_layer_k64<64>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w_hi[m],
-                                    wimg_s + 4u * (uint32_t)P.w_lo[m]);
-          umma::mma_commit(bar);
+        if (issuer_warp) {
+          if (umma::elect_one()) {
+            umma::fence_after_sync();
+            umma::issue_layer_k64<64>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO,
+                                      wimg_s + 4u * (uint32_t)P.w_hi[m], wimg_s + 4u * (uint32_t)P.w_lo[m]);
+            umma::mma_commit(bar);
+          }
+          __syncwarp();
         }
         if (m == n_mma - 1) {
 #pragma unroll

@@ -22,6 +22,17 @@ namespace umma {
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync): used with warp-uniform operands so that the
+// tcgen05.mma / commit operands stay in uniform registers (a divergent `if (tid == 0)` makes
+// the compiler wrap every MMA in an ELECT / R2UR waterfall loop, ~60 cycles per issue).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM allocation (one warp, all 512 columns: the kernels run one CTA per SM) ----
 __device__ __forceinline__ void tmem_alloc512(uint32_t* slot_in_smem) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_addr(slot_in_smem)) : "memory");
