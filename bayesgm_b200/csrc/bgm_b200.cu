@@ -142,13 +142,14 @@ static void split_tf32_host(float w, float& hi, float& lo) {
   b = (b + 0x1000u) & 0xffffe000u;
   memcpy(&lo, &b, 4);
 }
-// Wm [64][N] (Keras [in][out]) -> two [16][N][4] blocks (umma.cuh layout), hi and lo
-static void pack_mma_k64(std::vector<float>& img, const std::vector<float>& Wm, int N, int& off_hi, int& off_lo) {
+// Wm [K][N] (Keras [in][out]) -> two [K/4][N][4] blocks (umma.cuh layout), hi and lo
+static void pack_mma_k64(std::vector<float>& img, const std::vector<float>& Wm, int N, int& off_hi, int& off_lo,
+                         int K = 64) {
   off_hi = (int)img.size();
-  img.resize(img.size() + (size_t)64 * N, 0.f);
+  img.resize(img.size() + (size_t)K * N, 0.f);
   off_lo = (int)img.size();
-  img.resize(img.size() + (size_t)64 * N, 0.f);
-  for (int k = 0; k < 64; ++k)
+  img.resize(img.size() + (size_t)K * N, 0.f);
+  for (int k = 0; k < K; ++k)
     for (int n = 0; n < N; ++n) {
       float hi, lo;
       split_tf32_host(Wm[(size_t)k * N + n], hi, lo);
@@ -427,6 +428,12 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
         for (int c = 0; c < 8; ++c) { b3[c] = f.b[2][c]; b3[8 + c] = h.b[2][c]; }
         pack_mma_k64(tc_image, w3, 16, T.w3_hi, T.w3_lo);
         T.b3 = push_floats(tc_image, b3.data(), 16);
+        // the effect kernel runs f alone: f_h2 (32) -> [f_h3 (8) | 0 (8)]
+        std::vector<float> f3((size_t)32 * 16, 0.f);
+        for (int k = 0; k < 32; ++k)
+          for (int c = 0; c < 8; ++c) f3[(size_t)k * 16 + c] = f.W[2][(size_t)k * 8 + c];
+        pack_mma_k64(tc_image, f3, 16, T.f3_hi, T.f3_lo, 32);
+        T.fb3 = push_floats(tc_image, f.b[2].data(), 8);
       }
       for (int m = 0; m + 1 < T.n_mma; ++m) T.gb[m] = push_floats(tc_image, g.b[m + 1].data(), 64);
       T.gW1 = push_floats(tc_image, g.W[0].data(), (size_t)zd * 64);
@@ -647,6 +654,20 @@ int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_kee
   }
   E.z_samples = z_samples_dev; E.n_keep = n_keep; E.n = n; E.sample_y = sample_y ? 1 : 0;
   E.seed = seed; E.row_offset = row_offset; E.noise = noise_dev; E.adrf_sum = adrf_sum_dev; E.ite = ite_dev;
+  if (use_tc(m)) {
+    const long long nt = (long long)((n + TC_ROWS - 1) / TC_ROWS) * n_keep;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((nt + 1) / 2, m->sm_count));
+    const int zd = m->prog.zd;
+    auto launch = [&](auto kern) -> int {
+      BGM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tc_smem_bytes));
+      kern<<<grid, 256, m->tc_smem_bytes, (cudaStream_t)stream>>>(m->tc, m->tc_image_dev, E);
+      BGM_CUDA_OK(cudaGetLastError());
+      return 0;
+    };
+    if (zd <= 8) return launch(causal_effect_tc_kernel<8>);
+    if (zd <= 16) return launch(causal_effect_tc_kernel<16>);
+    return launch(causal_effect_tc_kernel<32>);
+  }
   const long long ntiles = (long long)((n + TILE_ROWS - 1) / TILE_ROWS) * n_keep;
   const int grid = (int)std::max<long long>(1, std::min<long long>((ntiles + m->effect_warps - 1) / m->effect_warps, m->sm_count));
   BGM_CUDA_OK(cudaFuncSetAttribute(causal_effect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

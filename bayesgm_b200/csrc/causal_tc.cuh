@@ -49,6 +49,7 @@ struct TcProgram {
   int w3_hi, w3_lo, b3;                       // third layers of f and h as one block-diagonal
                                               // [f_h2 | h_h2] (64) -> [f 8 | h 8]: [16][16][4]
   int fW4, fb4, hW4, hb4;                     // [8][2], [2]
+  int f3_hi, f3_lo, fb3;                      // effect kernel: f third layer alone, [8][16][4] (cols 8.. zero)
   int image_floats;
 };
 
@@ -482,6 +483,182 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
     __threadfence();
     wg_sync(wg);
     if (wtid == 0) *reinterpret_cast<volatile int*>(sched + 1 + tile) = chunk + 1;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc512(tmem0);
+}
+
+// ---------------------------------------------------------------------------------------
+// Effect kernel, tensor-core engine: f_net on kept states for every dose
+// (infer_from_latent_posterior, causalbgm/base.py:671-763; same contract and the same Philox
+// stream as causal_effect_kernel).  Thread = (kept state, row) = TMEM lane.  The z part of the
+// first layer is computed once per tile; per dose the thread adds x*w_x, and the 64->32 and
+// 32->8 layers run on the tensor cores, software-pipelined over doses: MMA stage j carries
+// layer 2 of dose j and layer 3 of dose j-1.
+constexpr uint32_t EF_A2_HI = 0, EF_A2_LO = 64, EF_D2 = 128, EF_A3_HI = 160, EF_A3_LO = 192, EF_D3 = 224;
+
+template <int ZMAX>
+__global__ void __launch_bounds__(256, 1)
+causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict__ image,
+                        const __grid_constant__ EffectDev E) {
+  constexpr int KINMAX = ZMAX + 1;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar_img;
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_slot;
+  bulk_load_to_smem(smem, image, (uint32_t)P.image_floats * 4u, &bar_img);
+  const float* wimg = smem;
+  const uint32_t wimg_s = umma::smem_addr(smem);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int wg = warp >> 2, wtid = tid & 127;
+  const bool issuer_warp = (warp & 3) == 0;
+  if (tid == 0) {
+    umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
+    umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc512(&tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  const uint32_t tbase = tmem0 + (uint32_t)wg * 256u;
+  const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t bar = umma::smem_addr(&bar_mma[wg]);
+  uint32_t parity = 0;
+
+  const int n = E.n, zd = P.zd, n_x = E.n_x;
+  const int tiles_per_s = (n + TC_ROWS - 1) / TC_ROWS;
+  const long long ntiles = (long long)tiles_per_s * E.n_keep;
+  const float* wx = wimg + P.fW1 + zd * 64;   // first-layer weights of the treatment input
+  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < ntiles; tile += (long long)gridDim.x * 2) {
+    const int s = (int)(tile / tiles_per_s);
+    const int row = (int)(tile - (long long)s * tiles_per_s) * TC_ROWS + wtid;
+    const bool valid = row < n;
+    const int lrow = valid ? row : n - 1;
+    const int64_t grow = E.row_offset + lrow;
+    // z part of f's first layer: base = b1 + [z0, z1] W1 (ascending rows, like the SIMT engine)
+    float base[64];
+    {
+      float in[KINMAX];
+      const float* zs = E.z_samples + ((size_t)s * n + lrow) * zd;
+#pragma unroll
+      for (int d = 0; d < KINMAX; ++d) in[d] = (d < zd) ? zs[d] : 0.f;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const float4 bb = *reinterpret_cast<const float4*>(wimg + P.fb1 + q * 4);
+        base[q * 4 + 0] = bb.x; base[q * 4 + 1] = bb.y; base[q * 4 + 2] = bb.z; base[q * 4 + 3] = bb.w;
+      }
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d) {
+        if (d < zd && ((P.fmask >> d) & 1ull)) {
+          const float zv = in[d];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const float4 ww = *reinterpret_cast<const float4*>(wimg + P.fW1 + d * 64 + q * 4);
+            base[q * 4 + 0] = fmaf(zv, ww.x, base[q * 4 + 0]);
+            base[q * 4 + 1] = fmaf(zv, ww.y, base[q * 4 + 1]);
+            base[q * 4 + 2] = fmaf(zv, ww.z, base[q * 4 + 2]);
+            base[q * 4 + 3] = fmaf(zv, ww.w, base[q * 4 + 3]);
+          }
+        }
+      }
+    }
+    float y_prev = 0.f;
+#pragma unroll 1
+    for (int j = 0; j < n_x + 2; ++j) {
+      if (j < n_x) {
+        // layer 1 of dose j -> A2
+        const float xv = E.x_values ? E.x_values[j] : (j == 0 ? 1.f : 0.f);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t hi[32], lo[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 ww = *reinterpret_cast<const float4*>(wx + c * 32 + q * 4);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.x, base[c * 32 + q * 4 + 0])), hi[q * 4 + 0], lo[q * 4 + 0]);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.y, base[c * 32 + q * 4 + 1])), hi[q * 4 + 1], lo[q * 4 + 1]);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.z, base[c * 32 + q * 4 + 2])), hi[q * 4 + 2], lo[q * 4 + 2]);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.w, base[c * 32 + q * 4 + 3])), hi[q * 4 + 3], lo[q * 4 + 3]);
+          }
+          umma::st32(trow + EF_A2_HI + c * 32, hi);
+          umma::st32(trow + EF_A2_LO + c * 32, lo);
+        }
+      }
+      uint32_t r3[16];
+      if (j >= 2) umma::ld16(trow + EF_D3, r3);            // layer-3 output of dose j-2
+      if (j >= 1 && j <= n_x) {
+        // layer-2 output of dose j-1 -> bias, LeakyReLU, split -> A3
+        uint32_t r[32], lo[32];
+        umma::ld32(trow + EF_D2, r);
+        umma::wait_ld();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 b = *reinterpret_cast<const float4*>(wimg + P.fb2 + q * 4);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 0]) + b.x), r[q * 4 + 0], lo[q * 4 + 0]);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 1]) + b.y), r[q * 4 + 1], lo[q * 4 + 1]);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 2]) + b.z), r[q * 4 + 2], lo[q * 4 + 2]);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 3]) + b.w), r[q * 4 + 3], lo[q * 4 + 3]);
+        }
+        umma::st32(trow + EF_A3_HI, r);
+        umma::st32(trow + EF_A3_LO, lo);
+      } else {
+        umma::wait_ld();
+      }
+      if (j <= n_x) {
+        umma::wait_st();
+        umma::fence_before_sync();
+        wg_sync(wg);
+        if (issuer_warp) {
+          if (umma::elect_one()) {
+            umma::fence_after_sync();
+            if (j < n_x)
+              umma::issue_layer<32, 8>(tbase + EF_D2, tbase + EF_A2_HI, tbase + EF_A2_LO,
+                                       wimg_s + 4u * (uint32_t)P.f2_hi, wimg_s + 4u * (uint32_t)P.f2_lo);
+            if (j >= 1)
+              umma::issue_layer<16, 4>(tbase + EF_D3, tbase + EF_A3_HI, tbase + EF_A3_LO,
+                                       wimg_s + 4u * (uint32_t)P.f3_hi, wimg_s + 4u * (uint32_t)P.f3_lo);
+            umma::mma_commit(bar);
+          }
+          __syncwarp();
+        }
+      }
+      if (j >= 2) {
+        // dose j-2: layer 4 (8 -> 2), optional y ~ N(mu, sigma^2) (:703-708), reduction
+        const int jd = j - 2;
+        float mu = wimg[P.fb4], raw = wimg[P.fb4 + 1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float a = leaky_mx(__uint_as_float(r3[k]) + wimg[P.fb3 + k]);
+          const float2 wf = *reinterpret_cast<const float2*>(wimg + P.fW4 + k * 2);
+          mu = fmaf(a, wf.x, mu);
+          raw = fmaf(a, wf.y, raw);
+        }
+        float y = mu;
+        if (E.sample_y) {
+          const float s2 = P.s2y >= 0.f ? P.s2y : softplus_f(raw) + 1e-6f;
+          const float e = E.noise ? E.noise[((size_t)jd * E.n_keep + s) * n + lrow]
+                                  : normal1(E.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)jd);
+          y = fmaf(sqrtf(s2), e, y);
+        }
+        if (P.binary) {                                                            // :731
+          if (jd == 0) y_prev = y;
+          else if (valid) E.ite[(size_t)s * n + row] = y_prev - y;
+        } else {                                                                   // :759
+          float part = valid ? y : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          if (lane == 0) atomicAdd(E.adrf_sum + (size_t)jd * E.n_keep + s, (double)part);
+        }
+      }
+      if (j <= n_x) {
+        umma::mbar_wait(bar, parity);
+        parity ^= 1u;
+        umma::fence_after_sync();
+      }
+    }
   }
   umma::fence_before_sync();
   __syncthreads();

@@ -128,21 +128,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar_saddr, uint32_t parity) {
   }
 }
 
-// One Dense layer with K = 64 inputs as 3xTF32: 8 k-steps of (hi*hi, lo*hi, hi*lo).
-// b_hi / b_lo: shared-memory byte addresses of the [16][N][4] images.
-template <int N>
-__device__ __forceinline__ void issue_layer_k64(uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, uint32_t b_hi,
-                                                uint32_t b_lo) {
+// One Dense layer with K = 8*KSTEPS inputs as 3xTF32: per k-step (hi*hi, lo*hi, hi*lo).
+// b_hi / b_lo: shared-memory byte addresses of the [K/4][N][4] images.
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_layer(uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, uint32_t b_hi,
+                                            uint32_t b_lo) {
   constexpr uint32_t idesc = idesc_tf32_m128(N);
   uint64_t dh = smem_desc(b_hi, N * 16, 128), dl = smem_desc(b_lo, N * 16, 128);
 #pragma unroll
-  for (int ks = 0; ks < 8; ++ks) {
+  for (int ks = 0; ks < KSTEPS; ++ks) {
     mma_tf32_ts(tD, tA_hi + ks * 8, dh, idesc, ks > 0);
     mma_tf32_ts(tD, tA_lo + ks * 8, dh, idesc, 1);
     mma_tf32_ts(tD, tA_hi + ks * 8, dl, idesc, 1);
     dh += (N * 32) >> 4;   // next 8 k: 2 core-matrix columns of N*16 bytes
     dl += (N * 32) >> 4;
   }
+}
+template <int N>
+__device__ __forceinline__ void issue_layer_k64(uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, uint32_t b_hi,
+                                                uint32_t b_lo) {
+  issue_layer<N, 8>(tD, tA_hi, tA_lo, b_hi, b_lo);
 }
 
 }  // namespace umma

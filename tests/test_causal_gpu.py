@@ -185,6 +185,38 @@ def test_effect_parity(binary):
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("binary,engine", [(False, 'tensor'), (True, 'tensor'), (False, 'simt'), (True, 'simt')])
+def test_effect_parity_standard_nets(binary, engine):
+    """The effect kernel on the standard net shape (tensor-core engine available): 3 row tiles of
+    128 per kept state with a ragged last one, 1..5 doses (pipeline fill / drain), both engines."""
+    z_dims = [3, 6, 3, 6] if binary else [1, 1, 1, 2]
+    v_dim = 100 if binary else 200
+    params = causal_params(v_dim, z_dims, binary)
+    nets = causal_nets(params)
+    n, n_keep = 300, 3
+    rs = np.random.RandomState(4)
+    zs = rs.standard_normal((n_keep, n, sum(z_dims))).astype(np.float32)
+    m = product_model(params, nets, engine)
+    assert m.sampler_info()['engine'] == engine
+    for xv in ([None] if binary else [[0.3], [0.0, 1.5], [0.0, 0.7, 3.0, 1.1, 2.2]]):
+        want = causal.infer_from_latent_posterior(params, nets, zs, xv, sample_y=False)
+        got = m.infer_from_latent_posterior(zs, x_values=xv, sample_y=False)
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-5)
+        k = 2 if binary else len(xv)
+        noise = rs.standard_normal((k, n_keep, n)).astype(np.float32)
+        it = iter(noise)
+        want = causal.infer_from_latent_posterior(params, nets, zs, xv, sample_y=True,
+                                                  normal_fn=lambda shape: next(it))
+        got = m.infer_from_latent_posterior(zs, x_values=xv, sample_y=True, noise=noise)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4)
+    if not binary:   # the Philox draws are keyed by (row, kept state, dose): engines agree
+        a = m.infer_from_latent_posterior(zs, x_values=[0.5, 2.0], sample_y=True, seed=11)
+        m2 = product_model(params, nets, 'simt' if engine == 'tensor' else 'tensor')
+        b = m2.infer_from_latent_posterior(zs, x_values=[0.5, 2.0], sample_y=True, seed=11)
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
+
+
 def test_effect_sample_y_philox_is_distributionally_right():
     params = causal_params(16, [1, 1, 1, 1])
     nets = causal_nets(params)
