@@ -18,7 +18,7 @@
 //    layers run the same way; only the first layers (a handful of inputs) and the 8->2 heads
 //    stay on the fp32 FMA pipe, one row per thread with warp-uniform (broadcast) weight loads,
 //    scheduled while the thread's MMAs are in flight.  Per iteration: 3 + (g.L-1) MMA stages.
-//  * two warpgroups per CTA (one CTA per SM, 512 TMEM columns = 2 x [A_hi 64 | A_lo 64 | D 64 | P 64])
+//  * two warpgroups per CTA (one CTA per SM, 512 TMEM columns = 2 x [A_hi 64 | A_lo 64 | D 64 | t 64])
 //    work on different tiles, so one tile's epilogue overlaps the other's MMAs.
 #pragma once
 #include "causal.cuh"
@@ -225,8 +225,24 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
     const int lrow = valid ? row : n - 1;
     const float x_l = A.x_dev[lrow], y_l = A.y_dev[lrow];
     const float r0_l = A.r0_dev[lrow];
-    const float4* trow_g = reinterpret_cast<const float4*>(A.vproj_dev + (size_t)lrow * A.ldvproj);
     const int64_t grow = A.row_offset + lrow;
+    // the row's projected covariates t (64 floats) stay in the thread's TMEM lane (columns
+    // TC_P..) for the whole unit: one uncoalesced read per ~16 iterations instead of one each
+    {
+      const float4* tg = reinterpret_cast<const float4*>(A.vproj_dev + (size_t)lrow * A.ldvproj);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t tr[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 v4 = __ldg(tg + c * 8 + q);
+          tr[q * 4 + 0] = __float_as_uint(v4.x); tr[q * 4 + 1] = __float_as_uint(v4.y);
+          tr[q * 4 + 2] = __float_as_uint(v4.z); tr[q * 4 + 3] = __float_as_uint(v4.w);
+        }
+        umma::st32(trow + TC_P + c * 32, tr);
+      }
+      umma::wait_st();
+    }
     float zc[ZMAX];
     // ---- initial state (:842) ----
     if (chunk == 0 && A.init_mode == 2) {
@@ -244,6 +260,23 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       for (int d = 0; d < ZMAX; ++d) zc[d] = (d < zd) ? __ldcg(A.z_state_dev + (size_t)lrow * zd + d) : 0.f;
     }
     float lp_cur = (need_init && chunk == 0) ? 0.f : __ldcg(A.lp_state_dev + lrow);
+    // unit normals of the current iteration's proposal (Philox mode): drawn here for the first
+    // iteration of the unit, afterwards under the previous iteration's MMA waits
+    float en[ZMAX];
+    float u_acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < ZMAX; ++d) en[d] = 0.f;
+    if (!A.eps_dev && ta < tb) {
+#pragma unroll
+      for (int g = 0; g < ZMAX / 4; ++g) {
+        if (g * 4 < zd) {
+          float e[4];
+          normal4(A.seed, grow, (uint32_t)ta, NOISE_PROPOSAL, g, e);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) en[g * 4 + q] = e[q];
+        }
+      }
+    }
     // ---- iterations (:860-898) ----
 #pragma unroll 1
     for (int t = ta; t < tb; ++t) {
@@ -263,15 +296,8 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
           if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)e[d]));
       } else {
 #pragma unroll
-        for (int g = 0; g < ZMAX / 4; ++g) {
-          if (g * 4 < zd) {
-            float e[4];
-            normal4(A.seed, grow, (uint32_t)t, NOISE_PROPOSAL, g, e);
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (g * 4 + q < zd) in[g * 4 + q] = __fadd_rn(zc[g * 4 + q], (float)(q_sd * (double)e[q]));
-          }
-        }
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)en[d]));
       }
       // prior on the proposal (:812), before x joins the input vector
       float prior = 0.f;
@@ -293,7 +319,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       if (issuer_warp) {
         if (umma::elect_one()) {
           umma::fence_after_sync();
-          umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.f2_hi,
+          umma::issue_layer_k64<32>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.f2_hi,
                                     wimg_s + 4u * (uint32_t)P.f2_lo);
           umma::mma_commit(bar);
         }
@@ -306,7 +332,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
         first_layer<KINMAX>(wimg + P.hW1, wimg + P.hb1, P.hmask, zd + 1, in, a1);
         stage_wait();
         uint32_t r[32];
-        umma::ld32(trow + TC_P, r);
+        umma::ld32(trow + TC_D, r);
         umma::wait_ld();
         bias_act32(r, wimg + P.fb2, h2);
         split_store64(a1, trow + TC_A_HI, trow + TC_A_LO);
@@ -315,7 +341,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       if (issuer_warp) {
         if (umma::elect_one()) {
           umma::fence_after_sync();
-          umma::issue_layer_k64<32>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.h2_hi,
+          umma::issue_layer_k64<32>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.h2_hi,
                                     wimg_s + 4u * (uint32_t)P.h2_lo);
           umma::mma_commit(bar);
         }
@@ -326,7 +352,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       stage_wait();
       {
         uint32_t r[32];
-        umma::ld32(trow + TC_P, r);
+        umma::ld32(trow + TC_D, r);
         umma::wait_ld();
         bias_act32(r, wimg + P.hb2, h2 + 32);
         split_store64(h2, trow + TC_A_HI, trow + TC_A_LO);
@@ -335,7 +361,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       if (issuer_warp) {
         if (umma::elect_one()) {
           umma::fence_after_sync();
-          umma::issue_layer_k64<16>(tbase + TC_P, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w3_hi,
+          umma::issue_layer_k64<16>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.w3_hi,
                                     wimg_s + 4u * (uint32_t)P.w3_lo);
           umma::mma_commit(bar);
         }
@@ -345,7 +371,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       float loss_py, loss_px;
       {
         uint32_t r[16];
-        umma::ld16(trow + TC_P, r);
+        umma::ld16(trow + TC_D, r);
         umma::wait_ld();
         float h3[16];
 #pragma unroll
@@ -381,7 +407,6 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       // ---- g_net: layers 2.. and the projected output layer on the tensor cores ----
       split_store64(g1, trow + TC_A_HI, trow + TC_A_LO);
       float sig = wimg[P.bsig];
-      float4 tq[16];
 #pragma unroll 1
       for (int m = 0; m < n_mma; ++m) {
         if (m > 0) {
@@ -409,34 +434,37 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
           }
           __syncwarp();
         }
-        if (m == n_mma - 1) {
+        // independent work under the MMA waits: noise of the next iteration, this iteration's uniform
+        if (!A.eps_dev) {
+          if (m == 0 && t + 1 < tb) {
 #pragma unroll
-          for (int q = 0; q < 16; ++q) tq[q] = __ldg(trow_g + q);   // projected covariates of the row
+            for (int g = 0; g < ZMAX / 4; ++g) {
+              if (g * 4 < zd) {
+                float e[4];
+                normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, g, e);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) en[g * 4 + q] = e[q];
+              }
+            }
+          }
+          if (m == 1 && !init_pass) u_acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT);
         }
         stage_wait();
       }
       // ---- covariate likelihood in the row space of g's last layer (:800-801) ----
       float sse = 0.f;
       {
-        uint32_t r0[32], r1[32];
-        umma::ld32(trow + TC_D, r0);
-        umma::ld32(trow + TC_D + 32, r1);
-        umma::wait_ld();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float d0 = __uint_as_float(r0[q * 4 + 0]) - tq[q].x;
-          const float d1 = __uint_as_float(r0[q * 4 + 1]) - tq[q].y;
-          const float d2 = __uint_as_float(r0[q * 4 + 2]) - tq[q].z;
-          const float d3 = __uint_as_float(r0[q * 4 + 3]) - tq[q].w;
-          sse = fmaf(d0, d0, sse); sse = fmaf(d1, d1, sse); sse = fmaf(d2, d2, sse); sse = fmaf(d3, d3, sse);
-        }
+        for (int c = 0; c < 2; ++c) {
+          uint32_t r[32], tt[32];
+          umma::ld32(trow + TC_D + c * 32, r);
+          umma::ld32(trow + TC_P + c * 32, tt);
+          umma::wait_ld();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float d0 = __uint_as_float(r1[q * 4 + 0]) - tq[8 + q].x;
-          const float d1 = __uint_as_float(r1[q * 4 + 1]) - tq[8 + q].y;
-          const float d2 = __uint_as_float(r1[q * 4 + 2]) - tq[8 + q].z;
-          const float d3 = __uint_as_float(r1[q * 4 + 3]) - tq[8 + q].w;
-          sse = fmaf(d0, d0, sse); sse = fmaf(d1, d1, sse); sse = fmaf(d2, d2, sse); sse = fmaf(d3, d3, sse);
+          for (int j = 0; j < 32; ++j) {
+            const float dd = __uint_as_float(r[j]) - __uint_as_float(tt[j]);
+            sse = fmaf(dd, dd, sse);
+          }
         }
       }
       const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(sig) + 1e-6f;
@@ -451,7 +479,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
       const float ratio = (dlp < 0.f) ? expf(dlp) : ((dlp >= 0.f) ? 1.f : __int_as_float(0x7fc00000));
       bool acc;
       if (A.u_dev) acc = A.u_dev[(size_t)t * n + lrow] < (double)ratio;
-      else acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT) < ratio;
+      else acc = u_acc < ratio;
       if (acc) {                                                                     // :871
 #pragma unroll
         for (int d = 0; d < ZMAX; ++d)
