@@ -660,7 +660,7 @@ int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_kee
     const int zd = m->prog.zd;
     auto launch = [&](auto kern) -> int {
       BGM_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, m->tc_smem_bytes));
-      kern<<<grid, 256, m->tc_smem_bytes, (cudaStream_t)stream>>>(m->tc, m->tc_image_dev, E);
+      kern<<<grid, 512, m->tc_smem_bytes, (cudaStream_t)stream>>>(m->tc, m->tc_image_dev, E);
       BGM_CUDA_OK(cudaGetLastError());
       return 0;
     };

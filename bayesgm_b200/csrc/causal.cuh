@@ -411,6 +411,7 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
     const float* zs = E.z_samples + ((size_t)s * n + lrow) * zd;
     for (int d = 0; d < zd; ++d) S.zin[act_idx(d, lane)] = zs[d];
     float y_prev = 0.f;
+    float nz4[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < E.n_x; ++j) {
       const float xv = E.x_values ? E.x_values[j] : (j == 0 ? 1.f : 0.f);
       S.zin[act_idx(zd, lane)] = xv;
@@ -427,8 +428,15 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
       float y = S.scr[lane];                                                     // mu_y
       if (E.sample_y) {                                                          // :703-708
         const float s2 = P.s2y >= 0.f ? P.s2y : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
-        const float e = E.noise ? E.noise[((size_t)j * E.n_keep + s) * n + lrow]
-                                : normal1(E.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)j);
+        float e;
+        if (E.noise) {
+          e = E.noise[((size_t)j * E.n_keep + s) * n + lrow];
+        } else {
+          // doses 4g..4g+3 share one Philox block: component j & 3 of normal4(.., g)
+          if ((j & 3) == 0) normal4(E.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)(j >> 2), nz4);
+          const int k4 = j & 3;
+          e = k4 == 0 ? nz4[0] : (k4 == 1 ? nz4[1] : (k4 == 2 ? nz4[2] : nz4[3]));
+        }
         y = fmaf(sqrtf(s2), e, y);
       }
       __syncwarp();

@@ -520,17 +520,25 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
 // ---------------------------------------------------------------------------------------
 // Effect kernel, tensor-core engine: f_net on kept states for every dose
 // (infer_from_latent_posterior, causalbgm/base.py:671-763; same contract and the same Philox
-// stream as causal_effect_kernel).  Thread = (kept state, row) = TMEM lane.  The z part of the
-// first layer is computed once per tile; per dose the thread adds x*w_x, and the 64->32 and
-// 32->8 layers run on the tensor cores, software-pipelined over doses: MMA stage j carries
-// layer 2 of dose j and layer 3 of dose j-1.
+// stream as causal_effect_kernel).  A tile is 128 (kept state, row) pairs = 128 TMEM lanes,
+// worked on by EIGHT warps: warps q and q+4 of the tile share lane quarter q and split the
+// columns (first-layer outputs 32 + 32, second-layer outputs 16 + 16) and the doses of the
+// 8 -> 2 head (even / odd), so that each SM sub-partition has 4 warps to interleave.  Two
+// tiles per CTA (16 warps, 512 TMEM columns).  The z part of the first layer is computed
+// once per tile; per dose the thread adds x*w_x, and the 64->32 and 32->8 layers run on the
+// tensor cores, software-pipelined over doses: MMA stage j carries layer 2 of dose j and
+// layer 3 of dose j-1.
 constexpr uint32_t EF_A2_HI = 0, EF_A2_LO = 64, EF_D2 = 128, EF_A3_HI = 160, EF_A3_LO = 192, EF_D3 = 224;
 
+__device__ __forceinline__ void tile_sync256(int slot) {
+  if (slot == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
 template <int ZMAX>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict__ image,
                         const __grid_constant__ EffectDev E) {
-  constexpr int KINMAX = ZMAX + 1;
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar_img;
   __shared__ uint64_t bar_mma[2];
@@ -540,8 +548,10 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
   const uint32_t wimg_s = umma::smem_addr(smem);
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int wg = warp >> 2, wtid = tid & 127;
-  const bool issuer_warp = (warp & 3) == 0;
+  const int slot = warp >> 3;          // which of the CTA's two tiles
+  const int q = warp & 3;              // TMEM lane quarter
+  const int c = (warp >> 2) & 1;       // column half / dose parity
+  const bool issuer_warp = (warp & 7) == 0;
   if (tid == 0) {
     umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
     umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
@@ -552,93 +562,95 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
   __syncthreads();
   umma::fence_after_sync();
   const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_slot, 0);
-  const uint32_t tbase = tmem0 + (uint32_t)wg * 256u;
-  const uint32_t trow = tbase + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t bar = umma::smem_addr(&bar_mma[wg]);
+  const uint32_t tbase = tmem0 + (uint32_t)slot * 256u;
+  const uint32_t trow = tbase + ((uint32_t)(q * 32) << 16);
+  const uint32_t bar = umma::smem_addr(&bar_mma[slot]);
   uint32_t parity = 0;
 
   const int n = E.n, zd = P.zd, n_x = E.n_x;
   const int tiles_per_s = (n + TC_ROWS - 1) / TC_ROWS;
   const long long ntiles = (long long)tiles_per_s * E.n_keep;
-  const float* wx = wimg + P.fW1 + zd * 64;   // first-layer weights of the treatment input
-  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < ntiles; tile += (long long)gridDim.x * 2) {
+  const float* wx = wimg + P.fW1 + zd * 64 + c * 32;   // first-layer weights of the treatment input
+  for (long long tile = (long long)blockIdx.x * 2 + slot; tile < ntiles; tile += (long long)gridDim.x * 2) {
     const int s = (int)(tile / tiles_per_s);
-    const int row = (int)(tile - (long long)s * tiles_per_s) * TC_ROWS + wtid;
+    const int row = (int)(tile - (long long)s * tiles_per_s) * TC_ROWS + q * 32 + lane;
     const bool valid = row < n;
     const int lrow = valid ? row : n - 1;
     const int64_t grow = E.row_offset + lrow;
-    // z part of f's first layer: base = b1 + [z0, z1] W1 (ascending rows, like the SIMT engine)
-    float base[64];
+    // z part of f's first layer, this thread's 32 columns: base = b1 + [z0, z1] W1
+    float base[32];
     {
-      float in[KINMAX];
       const float* zs = E.z_samples + ((size_t)s * n + lrow) * zd;
 #pragma unroll
-      for (int d = 0; d < KINMAX; ++d) in[d] = (d < zd) ? zs[d] : 0.f;
-#pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const float4 bb = *reinterpret_cast<const float4*>(wimg + P.fb1 + q * 4);
-        base[q * 4 + 0] = bb.x; base[q * 4 + 1] = bb.y; base[q * 4 + 2] = bb.z; base[q * 4 + 3] = bb.w;
+      for (int i = 0; i < 8; ++i) {
+        const float4 bb = *reinterpret_cast<const float4*>(wimg + P.fb1 + c * 32 + i * 4);
+        base[i * 4 + 0] = bb.x; base[i * 4 + 1] = bb.y; base[i * 4 + 2] = bb.z; base[i * 4 + 3] = bb.w;
       }
 #pragma unroll
       for (int d = 0; d < ZMAX; ++d) {
         if (d < zd && ((P.fmask >> d) & 1ull)) {
-          const float zv = in[d];
+          const float zv = zs[d];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            const float4 ww = *reinterpret_cast<const float4*>(wimg + P.fW1 + d * 64 + q * 4);
-            base[q * 4 + 0] = fmaf(zv, ww.x, base[q * 4 + 0]);
-            base[q * 4 + 1] = fmaf(zv, ww.y, base[q * 4 + 1]);
-            base[q * 4 + 2] = fmaf(zv, ww.z, base[q * 4 + 2]);
-            base[q * 4 + 3] = fmaf(zv, ww.w, base[q * 4 + 3]);
+          for (int i = 0; i < 8; ++i) {
+            const float4 ww = *reinterpret_cast<const float4*>(wimg + P.fW1 + d * 64 + c * 32 + i * 4);
+            base[i * 4 + 0] = fmaf(zv, ww.x, base[i * 4 + 0]);
+            base[i * 4 + 1] = fmaf(zv, ww.y, base[i * 4 + 1]);
+            base[i * 4 + 2] = fmaf(zv, ww.z, base[i * 4 + 2]);
+            base[i * 4 + 3] = fmaf(zv, ww.w, base[i * 4 + 3]);
           }
         }
       }
     }
     float y_prev = 0.f;
+    float nz[4] = {0.f, 0.f, 0.f, 0.f};
+    int nz_group = -1;
 #pragma unroll 1
     for (int j = 0; j < n_x + 2; ++j) {
       if (j < n_x) {
-        // layer 1 of dose j -> A2
+        // layer 1 of dose j, columns [32c, 32c+32) -> A2
         const float xv = E.x_values ? E.x_values[j] : (j == 0 ? 1.f : 0.f);
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t hi[32], lo[32];
+        for (int h = 0; h < 2; ++h) {
+          uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 ww = *reinterpret_cast<const float4*>(wx + c * 32 + q * 4);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.x, base[c * 32 + q * 4 + 0])), hi[q * 4 + 0], lo[q * 4 + 0]);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.y, base[c * 32 + q * 4 + 1])), hi[q * 4 + 1], lo[q * 4 + 1]);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.z, base[c * 32 + q * 4 + 2])), hi[q * 4 + 2], lo[q * 4 + 2]);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.w, base[c * 32 + q * 4 + 3])), hi[q * 4 + 3], lo[q * 4 + 3]);
+          for (int i = 0; i < 4; ++i) {
+            const float4 ww = *reinterpret_cast<const float4*>(wx + h * 16 + i * 4);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.x, base[h * 16 + i * 4 + 0])), hi[i * 4 + 0], lo[i * 4 + 0]);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.y, base[h * 16 + i * 4 + 1])), hi[i * 4 + 1], lo[i * 4 + 1]);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.z, base[h * 16 + i * 4 + 2])), hi[i * 4 + 2], lo[i * 4 + 2]);
+            umma::split_tf32(leaky_mx(fmaf(xv, ww.w, base[h * 16 + i * 4 + 3])), hi[i * 4 + 3], lo[i * 4 + 3]);
           }
-          umma::st32(trow + EF_A2_HI + c * 32, hi);
-          umma::st32(trow + EF_A2_LO + c * 32, lo);
+          umma::st16(trow + EF_A2_HI + c * 32 + h * 16, hi);
+          umma::st16(trow + EF_A2_LO + c * 32 + h * 16, lo);
         }
       }
+      const int jd = j - 2;                                 // dose whose layer-3 output is ready
+      // this warp finishes dose jd (binary: the c == 1 warps, which write y(1) - y(0), do both)
+      const bool head = jd >= 0 && ((jd & 1) == c || (P.binary && jd == 0));
       uint32_t r3[16];
-      if (j >= 2) umma::ld16(trow + EF_D3, r3);            // layer-3 output of dose j-2
+      if (head) umma::ld16(trow + EF_D3, r3);
       if (j >= 1 && j <= n_x) {
-        // layer-2 output of dose j-1 -> bias, LeakyReLU, split -> A3
-        uint32_t r[32], lo[32];
-        umma::ld32(trow + EF_D2, r);
+        // layer-2 output of dose j-1, columns [16c, 16c+16) -> bias, LeakyReLU, split -> A3
+        uint32_t r[16], lo[16];
+        umma::ld16(trow + EF_D2 + c * 16, r);
         umma::wait_ld();
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 b = *reinterpret_cast<const float4*>(wimg + P.fb2 + q * 4);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 0]) + b.x), r[q * 4 + 0], lo[q * 4 + 0]);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 1]) + b.y), r[q * 4 + 1], lo[q * 4 + 1]);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 2]) + b.z), r[q * 4 + 2], lo[q * 4 + 2]);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[q * 4 + 3]) + b.w), r[q * 4 + 3], lo[q * 4 + 3]);
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = *reinterpret_cast<const float4*>(wimg + P.fb2 + c * 16 + i * 4);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 0]) + b.x), r[i * 4 + 0], lo[i * 4 + 0]);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 1]) + b.y), r[i * 4 + 1], lo[i * 4 + 1]);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 2]) + b.z), r[i * 4 + 2], lo[i * 4 + 2]);
+          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 3]) + b.w), r[i * 4 + 3], lo[i * 4 + 3]);
         }
-        umma::st32(trow + EF_A3_HI, r);
-        umma::st32(trow + EF_A3_LO, lo);
+        umma::st16(trow + EF_A3_HI + c * 16, r);
+        umma::st16(trow + EF_A3_LO + c * 16, lo);
       } else {
         umma::wait_ld();
       }
       if (j <= n_x) {
         umma::wait_st();
         umma::fence_before_sync();
-        wg_sync(wg);
+        tile_sync256(slot);
         if (issuer_warp) {
           if (umma::elect_one()) {
             umma::fence_after_sync();
@@ -653,9 +665,8 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
           __syncwarp();
         }
       }
-      if (j >= 2) {
-        // dose j-2: layer 4 (8 -> 2), optional y ~ N(mu, sigma^2) (:703-708), reduction
-        const int jd = j - 2;
+      if (head) {
+        // dose jd: layer 4 (8 -> 2), optional y ~ N(mu, sigma^2) (:703-708), reduction
         float mu = wimg[P.fb4], raw = wimg[P.fb4 + 1];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -667,8 +678,18 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
         float y = mu;
         if (E.sample_y) {
           const float s2 = P.s2y >= 0.f ? P.s2y : softplus_f(raw) + 1e-6f;
-          const float e = E.noise ? E.noise[((size_t)jd * E.n_keep + s) * n + lrow]
-                                  : normal1(E.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)jd);
+          float e;
+          if (E.noise) {
+            e = E.noise[((size_t)jd * E.n_keep + s) * n + lrow];
+          } else {
+            // doses 4g..4g+3 share one Philox block: component jd & 3 of normal4(.., g)
+            if ((jd >> 2) != nz_group) {
+              nz_group = jd >> 2;
+              normal4(E.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)nz_group, nz);
+            }
+            const int k4 = jd & 3;
+            e = k4 == 0 ? nz[0] : (k4 == 1 ? nz[1] : (k4 == 2 ? nz[2] : nz[3]));
+          }
           y = fmaf(sqrtf(s2), e, y);
         }
         if (P.binary) {                                                            // :731

@@ -175,7 +175,12 @@ def run_ours(args):
 
     P = params()
     model = CausalBGM(params=P, random_seed=123)
+    model.set_sampler_engine(args.engine)
     info = model.kernel_info()
+    sinfo = model.sampler_info()
+    tensor = sinfo['engine'] == 'tensor'
+    zmax = 8 if sum(Z_DIMS) <= 8 else (16 if sum(Z_DIMS) <= 16 else 32)
+    kname = ("causal_mh_tc_kernel<%d>" if tensor else "causal_mh_kernel<%d>") % zmax
     x, y, v = make_data(rank)                      # weak scaling: every rank its own n rows
     T = BURN_IN + N_MCMC
     # ---- device-resident arm ----
@@ -244,20 +249,49 @@ def run_ours(args):
         fp32_peak = tf.value
         flop_per_launch = 2.0 * info['macs_per_row'] * n * (T + 1)
         achieved_tflops = flop_per_launch / (kern_ms_mean * 1e-3) / 1e12
-        issued_tflops = 2.0 * info['issued_macs_per_row'] * n * (T + 1) / (kern_ms_mean * 1e-3) / 1e12
+        issued_macs = sinfo['tensor_issued_macs_per_row'] if tensor else info['issued_macs_per_row']
+        issued_tflops = 2.0 * issued_macs * n * (T + 1) / (kern_ms_mean * 1e-3) / 1e12
         bytes_per_launch = 4.0 * n * (V_DIM + 2) + 4.0 * N_MCMC * n * sum(Z_DIMS) + 8.0 * n * (sum(Z_DIMS) + 1)
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get("causal_mh_kernel_dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("causal_mh_tc_kernel_dram_bytes_per_launch" if tensor
+                                                 else "causal_mh_kernel_dram_bytes_per_launch")
         cpu_iters = 10
         cpu_rate, cpu_dt = cpu_reference_rate(cpu_iters, data=(x, y, v))
+        if tensor:
+            # wide layers on the tensor pipe as 3xTF32: three TF32 MMAs per fp32-accurate product.
+            # MEASURED_PEAKS.json holds the dense bf16 peak only; kind::tf32 runs at half that rate.
+            bf16_peak = peaks["bf16_tflops"]
+            roofline = {"bound": "tensor", "achieved": achieved_tflops, "peak": bf16_peak, "unit": "TFLOP/s",
+                        "frac": achieved_tflops / bf16_peak, "traffic": traffic,
+                        "peak_source": peak_src + " bf16_tflops (burst; the kernel is timed alone)",
+                        "issued": issued_tflops, "issued_frac_of_tf32_peak": issued_tflops / (bf16_peak / 2.0),
+                        "fp32_pipe_peak": fp32_peak, "achieved_over_fp32_pipe_peak": achieved_tflops / fp32_peak,
+                        "note": "achieved = ALGORITHMIC 2*%d FLOP per row-iteration (the reference's log-posterior, "
+                                "evaluated once per iteration). The 64-wide layers run on tcgen05 as error-compensated "
+                                "3xTF32 (fp32-level error): the kernel ISSUES 2*%d FLOP-equivalents per row-iteration, "
+                                "nearly all on the tensor pipe at the TF32 rate (= bf16 peak / 2), so an fp32-accurate "
+                                "run of this net cannot exceed ~%.0f algorithmic TFLOP/s; the fp32 FMA pipe peak "
+                                "(%.1f TFLOP/s, measured live) is what the SIMT engine is bound by"
+                                % (info['macs_per_row'], issued_macs,
+                                   bf16_peak / 2.0 * info['macs_per_row'] / max(issued_macs, 1), fp32_peak)}
+        else:
+            roofline = {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                        "frac": achieved_tflops / fp32_peak, "traffic": traffic,
+                        "peak_source": "bgm_fp32_peak_tflops (dependent-FFMA micro-benchmark, measured live)",
+                        "issued": issued_tflops, "issued_frac": issued_tflops / fp32_peak,
+                        "note": "compute-bound SIMT kernel. achieved = ALGORITHMIC 2*%d FLOP per row-iteration "
+                                "(the reference's log-posterior, evaluated once per iteration); the kernel ISSUES "
+                                "2*%d: the v_dim-wide last layer of g_net is evaluated in its %d-dim row space "
+                                "(exact QR identity, DESIGN.md 4.1)"
+                                % (info['macs_per_row'], issued_macs, info['proj_dim'])}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rows_per_gpu": n, "iterations": T, "q_sd": 1.0,
-                       "noise": "in-kernel Philox4x32-10", "l2": "flushed between steps (256 MB memset)",
+                       "noise": "in-kernel Philox4x32-10", "engine": sinfo['engine'], "l2": "flushed between steps (256 MB memset)",
                        "parallelism": "rows sharded x%d, no collective in the sampler" % n_gpus,
                        "acceptance_rate": accept},
             "e2e": {"value": e2e_value, "unit": UNIT,
@@ -265,17 +299,9 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(4 * len(X_VALUES) * N_MCMC),
                     "api": "CausalBGM.predict(x_values=linspace(0,3,20), sample_y=True, bs=n)"},
             "gpu_launches": args.steps,
-            "kernel": {"name": "causal_mh_kernel<8>", "ms_per_launch": kern_ms_mean,
-                       "warps_per_cta": info['warps_per_cta'], "smem_bytes": info['smem_bytes']},
-            "roofline": {"bound": "fp32", "achieved": achieved_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / fp32_peak, "traffic": traffic,
-                         "peak_source": "bgm_fp32_peak_tflops (dependent-FFMA micro-benchmark, measured live)",
-                         "issued": issued_tflops, "issued_frac": issued_tflops / fp32_peak,
-                         "note": "compute-bound SIMT kernel. achieved = ALGORITHMIC 2*%d FLOP per row-iteration "
-                                 "(the reference's log-posterior, evaluated once per iteration); the kernel ISSUES "
-                                 "2*%d: the v_dim-wide last layer of g_net is evaluated in its %d-dim row space "
-                                 "(exact QR identity, DESIGN.md 4.1)"
-                                 % (info['macs_per_row'], info['issued_macs_per_row'], info['proj_dim'])},
+            "kernel": {"name": kname, "engine": sinfo['engine'], "ms_per_launch": kern_ms_mean,
+                       "warps_per_cta": 8, "smem_bytes": sinfo['tensor_smem_bytes'] if tensor else info['smem_bytes']},
+            "roofline": roofline,
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s",
                              "frac": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9 / peaks["hbm_gbs"],
@@ -310,6 +336,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tensor"],
+                    help="sampler engine (bgm_causal_set_sampler); auto = tensor cores when the net shape allows")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
