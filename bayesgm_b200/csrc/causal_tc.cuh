@@ -518,6 +518,495 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
 }
 
 // ---------------------------------------------------------------------------------------
+// The same sampler with EIGHT warps per 128-row tile (16 warps, two tiles per CTA): warps q and
+// q+4 of a tile share TMEM lane quarter q, i.e. two threads per row, and split every layer's
+// columns in halves (c = 0 / 1).  Both threads carry the identical chain state and make the
+// identical accept decision; the per-row scalars that each computes for its half (f-net loss by
+// c = 0, h-net loss by c = 1, the halves of the sigma_v dot product and of the covariate SSE) are
+// exchanged through shared memory once per iteration.  Per stage the epilogue latency halves and
+// each SM sub-partition has 4 warps to interleave instead of 2.
+__device__ __forceinline__ void tile_sync256(int slot) {
+  if (slot == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 2, 256;" ::: "memory");
+}
+
+// 32 outputs [c0, c0+32) of a first layer: out = LeakyReLU(b + in W)
+template <int KINMAX>
+__device__ __forceinline__ void first_layer32(const float* __restrict__ W, const float* __restrict__ b,
+                                              unsigned long long mask, int nin, const float (&in)[KINMAX],
+                                              int c0, float (&out)[32]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 bb = *reinterpret_cast<const float4*>(b + c0 + q * 4);
+    out[q * 4 + 0] = bb.x; out[q * 4 + 1] = bb.y; out[q * 4 + 2] = bb.z; out[q * 4 + 3] = bb.w;
+  }
+#pragma unroll
+  for (int d = 0; d < KINMAX; ++d) {
+    if (d < nin && ((mask >> d) & 1ull)) {
+      const float zv = in[d];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 ww = *reinterpret_cast<const float4*>(W + d * 64 + c0 + q * 4);
+        out[q * 4 + 0] = fmaf(zv, ww.x, out[q * 4 + 0]);
+        out[q * 4 + 1] = fmaf(zv, ww.y, out[q * 4 + 1]);
+        out[q * 4 + 2] = fmaf(zv, ww.z, out[q * 4 + 2]);
+        out[q * 4 + 3] = fmaf(zv, ww.w, out[q * 4 + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) out[j] = leaky_mx(out[j]);
+}
+__device__ __forceinline__ void split_store32(const float (&a)[32], uint32_t tA_hi, uint32_t tA_lo) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {   // 16 columns at a time: the 16-warp kernels have 128 registers per thread
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) umma::split_tf32(a[h * 16 + j], hi[j], lo[j]);
+    umma::st16(tA_hi + h * 16, hi);
+    umma::st16(tA_lo + h * 16, lo);
+  }
+}
+// bias + LeakyReLU (+ sigma_v partial dot) + hi/lo split of 16 accumulator columns, back into the A slots
+template <bool SIG>
+__device__ __forceinline__ void act_block16(uint32_t (&r)[16], const float* __restrict__ bias,
+                                            const float* __restrict__ wsig, float& sig, uint32_t tA_hi,
+                                            uint32_t tA_lo) {
+  uint32_t lo[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + i * 4);
+    const float bb[4] = {b.x, b.y, b.z, b.w};
+    float ws[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (SIG) {
+      const float4 s4 = *reinterpret_cast<const float4*>(wsig + i * 4);
+      ws[0] = s4.x; ws[1] = s4.y; ws[2] = s4.z; ws[3] = s4.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = leaky_mx(__uint_as_float(r[i * 4 + k]) + bb[k]);
+      if constexpr (SIG) sig = fmaf(a, ws[k], sig);
+      umma::split_tf32(a, r[i * 4 + k], lo[i * 4 + k]);
+    }
+  }
+  umma::st16(tA_hi, r);
+  umma::st16(tA_lo, lo);
+}
+// 16 accumulator columns -> LeakyReLU(r + bias) -> hi / lo into the A slots
+__device__ __forceinline__ void act_store16(uint32_t (&r)[16], const float* __restrict__ bias, uint32_t tA_hi,
+                                            uint32_t tA_lo) {
+  uint32_t lo[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b = *reinterpret_cast<const float4*>(bias + i * 4);
+    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 0]) + b.x), r[i * 4 + 0], lo[i * 4 + 0]);
+    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 1]) + b.y), r[i * 4 + 1], lo[i * 4 + 1]);
+    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 2]) + b.z), r[i * 4 + 2], lo[i * 4 + 2]);
+    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 3]) + b.w), r[i * 4 + 3], lo[i * 4 + 3]);
+  }
+  umma::st16(tA_hi, r);
+  umma::st16(tA_lo, lo);
+}
+
+constexpr int TC16_XCH_FLOATS = 2 * 2 * TC_ROWS * 4;   // [slot][half][row][4] exchange buffer
+
+template <int ZMAX>
+__global__ void __launch_bounds__(512, 1)
+causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restrict__ image,
+                      const __grid_constant__ MhDev D) {
+  constexpr int KINMAX = ZMAX + 1;
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar_img;
+  __shared__ uint64_t bar_mma[2];
+  __shared__ uint32_t tmem_slot;
+  __shared__ long long unit_s[2];
+  bulk_load_to_smem(smem, image, (uint32_t)P.image_floats * 4u, &bar_img);
+  const float* wimg = smem;
+  float* xch = smem + P.image_floats;
+  const uint32_t wimg_s = umma::smem_addr(smem);
+
+  const bgm_mh_args& A = D.a;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int slot = warp >> 3;          // which of the CTA's two tiles
+  const int q = warp & 3;              // TMEM lane quarter
+  const int c = (warp >> 2) & 1;       // column half
+  const bool issuer_warp = (warp & 7) == 0;
+  const bool leader = issuer_warp && lane == 0;
+  const int r_in_tile = q * 32 + lane;
+  if (tid == 0) {
+    umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
+    umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) umma::tmem_alloc512(&tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  const uint32_t tbase = tmem0 + (uint32_t)slot * 256u;
+  const uint32_t trow = tbase + ((uint32_t)(q * 32) << 16);
+  const uint32_t bar = umma::smem_addr(&bar_mma[slot]);
+  uint32_t parity = 0;
+  float* my_x = xch + ((slot * 2 + c) * TC_ROWS + r_in_tile) * 4;
+  const float* other_x = xch + ((slot * 2 + (c ^ 1)) * TC_ROWS + r_in_tile) * 4;
+
+  const int n = A.n, zd = P.zd;
+  const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
+  const double q_sd = A.q_sd_dev ? *A.q_sd_dev : 1.0;
+  const bool need_init = !(A.init_mode == 0 && D.mode == 0);
+  const int t_first = need_init ? A.t_begin - 1 : A.t_begin;
+  const int t_last = D.mode == 1 ? A.t_begin : A.t_end;
+  int* sched = A.sched_dev;
+  const int n_iter = t_last - t_first;
+  const int nchunks = D.nchunks;
+  const int chunk_len = (n_iter + nchunks - 1) / nchunks;
+  const long long total_units = (long long)ntiles * nchunks;
+  const int n_mma = P.n_mma;
+
+  auto publish = [&]() {
+    umma::wait_st();
+    umma::fence_before_sync();
+    tile_sync256(slot);
+  };
+  auto stage_wait = [&]() {
+    umma::mbar_wait(bar, parity);
+    parity ^= 1u;
+    umma::fence_after_sync();
+  };
+
+  for (;;) {
+    if (leader) {
+      const long long u = atomicAdd(reinterpret_cast<unsigned int*>(sched), 1u);
+      if (u < total_units) {
+        const int chunk = (int)(u / ntiles);
+        const int tile = (int)(u - (long long)chunk * ntiles);
+        if (chunk > 0) {
+          const volatile int* flag = sched + 1 + tile;
+          while (*flag < chunk) __nanosleep(200);
+          __threadfence();
+        }
+      }
+      unit_s[slot] = u;
+    }
+    tile_sync256(slot);
+    const long long u = unit_s[slot];
+    if (u >= total_units) break;
+    const int chunk = (int)(u / ntiles);
+    const int tile = (int)(u - (long long)chunk * ntiles);
+    const int ta = t_first + chunk * chunk_len;
+    const int tb = min(ta + chunk_len, t_last);
+    const int row = tile * TC_ROWS + r_in_tile;
+    const bool valid = row < n;
+    const bool writer = valid && c == 0;   // one of the row's two threads owns the outputs
+    const int lrow = valid ? row : n - 1;
+    const float x_l = A.x_dev[lrow], y_l = A.y_dev[lrow];
+    const float r0_l = A.r0_dev[lrow];
+    const int64_t grow = A.row_offset + lrow;
+    // this thread's half of the row's projected covariates stays in its TMEM lane for the unit
+    {
+      const float4* tg = reinterpret_cast<const float4*>(A.vproj_dev + (size_t)lrow * A.ldvproj) + c * 8;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t tr[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 v4 = __ldg(tg + h * 4 + i);
+          tr[i * 4 + 0] = __float_as_uint(v4.x); tr[i * 4 + 1] = __float_as_uint(v4.y);
+          tr[i * 4 + 2] = __float_as_uint(v4.z); tr[i * 4 + 3] = __float_as_uint(v4.w);
+        }
+        umma::st16(trow + TC_P + c * 32 + h * 16, tr);
+      }
+      umma::wait_st();
+    }
+    float zc[ZMAX];
+    // ---- initial state (:842) ----
+    if (chunk == 0 && A.init_mode == 2) {
+#pragma unroll
+      for (int g = 0; g < ZMAX / 4; ++g) {
+        if (g * 4 < zd) {
+          float e[4];
+          normal4(A.seed, grow, T_INIT, NOISE_PROPOSAL, g, e);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) zc[g * 4 + i] = e[i];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d) zc[d] = (d < zd) ? __ldcg(A.z_state_dev + (size_t)lrow * zd + d) : 0.f;
+    }
+    float lp_cur = (need_init && chunk == 0) ? 0.f : __ldcg(A.lp_state_dev + lrow);
+    float en[ZMAX];
+    float u_acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < ZMAX; ++d) en[d] = 0.f;
+    if (!A.eps_dev && ta < tb) {
+#pragma unroll
+      for (int g = 0; g < ZMAX / 4; ++g) {
+        if (g * 4 < zd) {
+          float e[4];
+          normal4(A.seed, grow, (uint32_t)ta, NOISE_PROPOSAL, g, e);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) en[g * 4 + i] = e[i];
+        }
+      }
+    }
+    // ---- iterations (:860-898) ----
+#pragma unroll 1
+    for (int t = ta; t < tb; ++t) {
+      const bool init_pass = t < A.t_begin;
+      float in[KINMAX];   // [proposal z' (zd), x]
+#pragma unroll
+      for (int d = 0; d < KINMAX; ++d) in[d] = 0.f;
+      if (init_pass) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) in[d] = zc[d];
+      } else if (A.eps_dev) {
+        const float* e = A.eps_dev + ((size_t)t * n + lrow) * zd;
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)e[d]));
+      } else {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)en[d]));
+      }
+      float prior = 0.f;                                                              // :812
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) prior = fmaf(in[d], in[d], prior);
+      prior *= 0.5f;
+#pragma unroll
+      for (int d = 0; d < KINMAX; ++d)
+        if (d == zd) in[d] = x_l;
+
+      // ---- f layer 1 (my 32 columns) -> A; stage F2 ----
+      {
+        float a1[32];
+        first_layer32<KINMAX>(wimg + P.fW1, wimg + P.fb1, P.fmask, zd + 1, in, c * 32, a1);
+        split_store32(a1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
+      }
+      publish();
+      if (issuer_warp) {
+        if (umma::elect_one()) {
+          umma::fence_after_sync();
+          umma::issue_layer_k64<32>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO, wimg_s + 4u * (uint32_t)P.f2_hi,
+                                    wimg_s + 4u * (uint32_t)P.f2_lo);
+          umma::mma_commit(bar);
+        }
+        __syncwarp();
+      }
+      {
+        float a1[32];   // h layer 1 while f's MMAs run
+        first_layer32<KINMAX>(wimg + P.hW1, wimg + P.hb1, P.hmask, zd + 1, in, c * 32, a1);
+        stage_wait();
+        // f_h2 columns [16c, 16c+16) -> A3 columns [16c ..) ; A3 = [f_h2 (32) | h_h2 (32)]
+        uint32_t r[16];
+        umma::ld16(trow + TC_D + c * 16, r);
+        umma::wait_ld();
+        // A3 lives in TC_P? no: TC_P holds t.  A3 is written after h's MMAs (A slots busy), keep f_h2 in registers.
+        float fh2[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 b = *reinterpret_cast<const float4*>(wimg + P.fb2 + c * 16 + i * 4);
+          fh2[i * 4 + 0] = leaky_mx(__uint_as_float(r[i * 4 + 0]) + b.x);
+          fh2[i * 4 + 1] = leaky_mx(__uint_as_float(r[i * 4 + 1]) + b.y);
+          fh2[i * 4 + 2] = leaky_mx(__uint_as_float(r[i * 4 + 2]) + b.z);
+          fh2[i * 4 + 3] = leaky_mx(__uint_as_float(r[i * 4 + 3]) + b.w);
+        }
+        split_store32(a1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
+        publish();
+        if (issuer_warp) {
+          if (umma::elect_one()) {
+            umma::fence_after_sync();
+            umma::issue_layer_k64<32>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO,
+                                      wimg_s + 4u * (uint32_t)P.h2_hi, wimg_s + 4u * (uint32_t)P.h2_lo);
+            umma::mma_commit(bar);
+          }
+          __syncwarp();
+        }
+        stage_wait();
+        {
+          uint32_t rh[16];
+          umma::ld16(trow + TC_D + c * 16, rh);
+          umma::wait_ld();
+          // f_h2 -> A3 columns [16c..], h_h2 -> A3 columns [32 + 16c..]
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) umma::split_tf32(fh2[j], hi[j], lo[j]);
+          umma::st16(trow + TC_A_HI + c * 16, hi);
+          umma::st16(trow + TC_A_LO + c * 16, lo);
+          act_store16(rh, wimg + P.hb2 + c * 16, trow + TC_A_HI + 32 + c * 16, trow + TC_A_LO + 32 + c * 16);
+        }
+        publish();
+        if (issuer_warp) {
+          if (umma::elect_one()) {
+            umma::fence_after_sync();
+            umma::issue_layer_k64<16>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO,
+                                      wimg_s + 4u * (uint32_t)P.w3_hi, wimg_s + 4u * (uint32_t)P.w3_lo);
+            umma::mma_commit(bar);
+          }
+          __syncwarp();
+        }
+        float g1[32];   // g layer 1 while the layer-3 MMAs run
+        first_layer32<KINMAX>(wimg + P.gW1, wimg + P.gb1, ~0ull, zd, in, c * 32, g1);
+        stage_wait();
+        // ---- heads: c = 0 finishes f_net (outcome model :809-810), c = 1 h_net (treatment model :803-807) ----
+        float my_loss;
+        {
+          uint32_t r8[8];
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=r"(r8[0]), "=r"(r8[1]), "=r"(r8[2]), "=r"(r8[3]), "=r"(r8[4]), "=r"(r8[5]), "=r"(r8[6]),
+                         "=r"(r8[7])
+                       : "r"(trow + TC_D + c * 8));
+          umma::wait_ld();
+          const float* W4 = wimg + (c == 0 ? P.fW4 : P.hW4);
+          const float* b4 = wimg + (c == 0 ? P.fb4 : P.hb4);
+          float mu = b4[0], raw = b4[1];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float a = leaky_mx(__uint_as_float(r8[k]) + wimg[P.b3 + c * 8 + k]);
+            const float2 w2 = *reinterpret_cast<const float2*>(W4 + k * 2);
+            mu = fmaf(a, w2.x, mu);
+            raw = fmaf(a, w2.y, raw);
+          }
+          if (c == 0) {
+            const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(raw) + 1e-6f;
+            const float dy = y_l - mu;
+            my_loss = (dy * dy) / (2.f * s2y) + logf(s2y) / 2.f;
+          } else if (P.binary) {
+            my_loss = fmaxf(mu, 0.f) - mu * x_l + log1pf(expf(-fabsf(mu)));
+          } else {
+            const float s2x = P.s2x >= 0.f ? P.s2x : softplus_f(raw) + 1e-6f;
+            const float dx = x_l - mu;
+            my_loss = (dx * dx) / (2.f * s2x) + logf(s2x) / 2.f;
+          }
+        }
+        // ---- g_net on the tensor cores ----
+        split_store32(g1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
+        float sig = 0.f;
+#pragma unroll 1
+        for (int m = 0; m < n_mma; ++m) {
+          if (m > 0) {
+            uint32_t ra[16], rb[16];
+            umma::ld16(trow + TC_D + c * 32, ra);
+            umma::ld16(trow + TC_D + c * 32 + 16, rb);
+            umma::wait_ld();
+            const float* bias = wimg + P.gb[m - 1] + c * 32;
+            const uint32_t ah = trow + TC_A_HI + c * 32, al = trow + TC_A_LO + c * 32;
+            if (m == n_mma - 1) {
+              act_block16<true>(ra, bias, wimg + P.wsig + c * 32, sig, ah, al);
+              act_block16<true>(rb, bias + 16, wimg + P.wsig + c * 32 + 16, sig, ah + 16, al + 16);
+            } else {
+              act_block16<false>(ra, bias, nullptr, sig, ah, al);
+              act_block16<false>(rb, bias + 16, nullptr, sig, ah + 16, al + 16);
+            }
+          }
+          publish();
+          if (issuer_warp) {
+            if (umma::elect_one()) {
+              umma::fence_after_sync();
+              umma::issue_layer_k64<64>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO,
+                                        wimg_s + 4u * (uint32_t)P.w_hi[m], wimg_s + 4u * (uint32_t)P.w_lo[m]);
+              umma::mma_commit(bar);
+            }
+            __syncwarp();
+          }
+          // independent work under the MMA waits: noise of the next iteration, this iteration's uniform
+          if (!A.eps_dev) {
+            if (m == 0 && t + 1 < tb) {
+#pragma unroll
+              for (int g = 0; g < ZMAX / 4; ++g) {
+                if (g * 4 < zd) {
+                  float e[4];
+                  normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, g, e);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) en[g * 4 + i] = e[i];
+                }
+              }
+            }
+            if (m == 1 && !init_pass) u_acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT);
+          }
+          stage_wait();
+        }
+        // ---- my half of the covariate SSE (:800), then the row's two threads swap their partials ----
+        float sse = 0.f;
+        {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t r[16], tt[16];
+            umma::ld16(trow + TC_D + c * 32 + h * 16, r);
+            umma::ld16(trow + TC_P + c * 32 + h * 16, tt);
+            umma::wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float dd = __uint_as_float(r[j]) - __uint_as_float(tt[j]);
+              sse = fmaf(dd, dd, sse);
+            }
+          }
+        }
+        *reinterpret_cast<float4*>(my_x) = make_float4(my_loss, sig, sse, 0.f);
+        tile_sync256(slot);
+        const float4 ox = *reinterpret_cast<const float4*>(other_x);
+        const float loss_py = c == 0 ? my_loss : ox.x;
+        const float loss_px = c == 0 ? ox.x : my_loss;
+        const float sig0 = c == 0 ? sig : ox.y, sig1 = c == 0 ? ox.y : sig;
+        const float sse0 = c == 0 ? sse : ox.z, sse1 = c == 0 ? ox.z : sse;
+        const float sig_all = (wimg[P.bsig] + sig0) + sig1;
+        const float sse_all = sse0 + sse1;
+        const float s2v = P.s2v >= 0.f ? P.s2v : softplus_f(sig_all) + 1e-6f;
+        const float loss_pv = (sse_all + r0_l) / (2.f * s2v) + ((float)P.p * logf(s2v)) / 2.f;
+        const float lp_prop = -(((loss_pv + loss_px) + loss_py) + prior);              // :814-816
+        if (init_pass) {
+          lp_cur = lp_prop;
+          continue;
+        }
+        // accept: u < exp(min(lp' - lp, 0))  (:868-870); a NaN ratio never accepts
+        const float dlp = lp_prop - lp_cur;
+        const float ratio = (dlp < 0.f) ? expf(dlp) : ((dlp >= 0.f) ? 1.f : __int_as_float(0x7fc00000));
+        bool acc;
+        if (A.u_dev) acc = A.u_dev[(size_t)t * n + lrow] < (double)ratio;
+        else acc = u_acc < ratio;
+        if (acc) {                                                                     // :871
+#pragma unroll
+          for (int d = 0; d < ZMAX; ++d)
+            if (d < zd) zc[d] = in[d];
+          lp_cur = lp_prop;
+        }
+        if (A.accept_mask_dev && writer) A.accept_mask_dev[(size_t)t * n + row] = acc ? 1 : 0;
+        if (A.lp_trace_dev && writer) A.lp_trace_dev[(size_t)t * n + row] = lp_prop;
+        if (A.accept_count_dev && c == 0) {
+          const unsigned b = __ballot_sync(0xffffffffu, acc && valid);
+          if (lane == 0 && b) atomicAdd(A.accept_count_dev + t, __popc(b));
+        }
+        if (t >= A.burn_in && A.out_samples_dev && writer) {                           // :895-896
+          float* dst = A.out_samples_dev + ((size_t)(t - A.burn_in) * n + row) * zd;
+#pragma unroll
+          for (int d = 0; d < ZMAX; ++d)
+            if (d < zd) dst[d] = zc[d];
+        }
+      }
+    }
+    // ---- save state, publish the chunk ----
+    if (writer) {
+      if (D.mode == 0) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) A.z_state_dev[(size_t)row * zd + d] = zc[d];
+      }
+      A.lp_state_dev[row] = lp_cur;
+    }
+    __threadfence();
+    tile_sync256(slot);
+    if (leader) *reinterpret_cast<volatile int*>(sched + 1 + tile) = chunk + 1;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc512(tmem0);
+}
+
+// ---------------------------------------------------------------------------------------
 // Effect kernel, tensor-core engine: f_net on kept states for every dose
 // (infer_from_latent_posterior, causalbgm/base.py:671-763; same contract and the same Philox
 // stream as causal_effect_kernel).  A tile is 128 (kept state, row) pairs = 128 TMEM lanes,
@@ -529,11 +1018,6 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
 // tensor cores, software-pipelined over doses: MMA stage j carries layer 2 of dose j and
 // layer 3 of dose j-1.
 constexpr uint32_t EF_A2_HI = 0, EF_A2_LO = 64, EF_D2 = 128, EF_A3_HI = 160, EF_A3_LO = 192, EF_D3 = 224;
-
-__device__ __forceinline__ void tile_sync256(int slot) {
-  if (slot == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
-  else asm volatile("bar.sync 2, 256;" ::: "memory");
-}
 
 template <int ZMAX>
 __global__ void __launch_bounds__(512, 1)
