@@ -237,7 +237,7 @@ template <int ZMAX>
 static int launch_mh_tc_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream_t st) {
   if (m->tc16 && ZMAX <= 16) {   // 8 warps per tile; needs the exchange buffer behind the image
     auto k = causal_mh_tc16_kernel<ZMAX>;
-    const int smem = m->tc_smem_bytes + TC16_XCH_FLOATS * 4;
+    const int smem = m->tc_smem_bytes + 2 * TC16_XCH_FLOATS * 4;
     BGM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, 512, smem, st>>>(m->tc, m->tc_image_dev, D);
     BGM_CUDA_OK(cudaGetLastError());
@@ -510,7 +510,7 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   m->tc_issued = tc_issued;
   m->tc_smem_bytes = T.image_floats * 4;
   if (T.enabled && m->tc_smem_bytes + 256 > smem_max) m->tc.enabled = 0;
-  m->tc16 = m->tc.enabled && m->tc_smem_bytes + TC16_XCH_FLOATS * 4 + 256 <= smem_max && !getenv("BGM_TC8");
+  m->tc16 = m->tc.enabled && m->tc_smem_bytes + 2 * TC16_XCH_FLOATS * 4 + 128 <= smem_max && !getenv("BGM_TC8");
   if (e == cudaSuccess && m->tc.enabled) {
     e = cudaMalloc(&m->tc_image_dev, tc_image.size() * sizeof(float));
     if (e == cudaSuccess)

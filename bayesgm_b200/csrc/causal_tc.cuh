@@ -608,7 +608,7 @@ __device__ __forceinline__ void act_store16(uint32_t (&r)[16], const float* __re
   umma::st16(tA_lo, lo);
 }
 
-constexpr int TC16_XCH_FLOATS = 2 * 2 * TC_ROWS * 4;   // [slot][half][row][4] exchange buffer
+constexpr int TC16_XCH_FLOATS = 2 * 2 * TC_ROWS * 4;   // [slot][half][row][4] exchange buffer (x2: partials, noise)
 
 template <int ZMAX>
 __global__ void __launch_bounds__(512, 1)
@@ -650,6 +650,13 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
   uint32_t parity = 0;
   float* my_x = xch + ((slot * 2 + c) * TC_ROWS + r_in_tile) * 4;
   const float* other_x = xch + ((slot * 2 + (c ^ 1)) * TC_ROWS + r_in_tile) * 4;
+  // zd <= 8: the row's two threads each draw one group of 4 proposal normals (group c) and
+  // pass it on through shared memory instead of both drawing both
+  constexpr bool SHARE_NOISE = ZMAX == 8;
+  float* xn = xch + TC16_XCH_FLOATS;   // [slot][group][row][4]
+  float* my_n = xn + ((slot * 2 + c) * TC_ROWS + r_in_tile) * 4;
+  const float* n0 = xn + ((slot * 2 + 0) * TC_ROWS + r_in_tile) * 4;
+  const float* n1 = xn + ((slot * 2 + 1) * TC_ROWS + r_in_tile) * 4;
 
   const int n = A.n, zd = P.zd;
   const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
@@ -768,6 +775,12 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
         for (int d = 0; d < ZMAX; ++d)
           if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)e[d]));
       } else {
+        if (SHARE_NOISE && t > ta) {
+          const float4 a4 = *reinterpret_cast<const float4*>(n0);
+          const float4 b4 = *reinterpret_cast<const float4*>(n1);
+          en[0] = a4.x; en[1] = a4.y; en[2] = a4.z; en[3] = a4.w;
+          if (ZMAX > 4) { en[4] = b4.x; en[5] = b4.y; en[6] = b4.z; en[7] = b4.w; }
+        }
 #pragma unroll
         for (int d = 0; d < ZMAX; ++d)
           if (d < zd) in[d] = __fadd_rn(zc[d], (float)(q_sd * (double)en[d]));
@@ -916,17 +929,26 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
           // independent work under the MMA waits: noise of the next iteration, this iteration's uniform
           if (!A.eps_dev) {
             if (m == 0 && t + 1 < tb) {
-#pragma unroll
-              for (int g = 0; g < ZMAX / 4; ++g) {
-                if (g * 4 < zd) {
+              if constexpr (SHARE_NOISE) {
+                if (c * 4 < zd) {
                   float e[4];
-                  normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, g, e);
+                  normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, (uint32_t)c, e);
+                  *reinterpret_cast<float4*>(my_n) = make_float4(e[0], e[1], e[2], e[3]);
+                }
+              } else {
 #pragma unroll
-                  for (int i = 0; i < 4; ++i) en[g * 4 + i] = e[i];
+                for (int g = 0; g < ZMAX / 4; ++g) {
+                  if (g * 4 < zd) {
+                    float e[4];
+                    normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, g, e);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) en[g * 4 + i] = e[i];
+                  }
                 }
               }
             }
-            if (m == 1 && !init_pass) u_acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT);
+            // the accept uniform: drawn by the c == 0 thread, handed over with the partials below
+            if (m == 1 && !init_pass && c == 0) u_acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT);
           }
           stage_wait();
         }
@@ -946,9 +968,10 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
             }
           }
         }
-        *reinterpret_cast<float4*>(my_x) = make_float4(my_loss, sig, sse, 0.f);
+        *reinterpret_cast<float4*>(my_x) = make_float4(my_loss, sig, sse, u_acc);
         tile_sync256(slot);
         const float4 ox = *reinterpret_cast<const float4*>(other_x);
+        if (c == 1) u_acc = ox.w;
         const float loss_py = c == 0 ? my_loss : ox.x;
         const float loss_px = c == 0 ? ox.x : my_loss;
         const float sig0 = c == 0 ? sig : ox.y, sig1 = c == 0 ? ox.y : sig;
