@@ -77,6 +77,7 @@ SYMBOLS = {
     "bgm_causal_set_sampler": (C.c_int, [C.c_void_p, C.c_int]),
     "bgm_causal_sampler_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                           C.POINTER(C.c_longlong)]),
+    "bgm_causal_kernel_name": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "bgm_causal_project": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_void_p]),
     "bgm_causal_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

@@ -187,8 +187,11 @@ class CausalBGM(object):
         issued = C.c_longlong()
         _lib.call("bgm_causal_sampler_info", self._device_model(), C.byref(kind), C.byref(avail), C.byref(smem),
                   C.byref(issued))
+        buf = C.create_string_buffer(64)
+        _lib.call("bgm_causal_kernel_name", self._device_model(), buf, 64)
         return dict(engine={1: 'simt', 2: 'tensor'}[kind.value], tensor_available=bool(avail.value),
-                    tensor_smem_bytes=smem.value, tensor_issued_macs_per_row=issued.value)
+                    tensor_smem_bytes=smem.value, tensor_issued_macs_per_row=issued.value,
+                    kernel=buf.value.decode())
 
     def kernel_info(self):
         smem, warps, nops, proj = C.c_int(), C.c_int(), C.c_int(), C.c_int()

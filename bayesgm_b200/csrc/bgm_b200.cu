@@ -567,6 +567,15 @@ int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_a
   return 0;
 }
 
+int bgm_causal_kernel_name(const bgm_causal* m, char* buf, int len) {
+  if (!m || !buf || len < 1) return fail(BGM_ERR_ARG, "bgm_causal_kernel_name: null argument");
+  const int zd = m->prog.zd;
+  const int zmax = zd <= 8 ? 8 : (zd <= 16 ? 16 : 32);
+  const char* base = !use_tc(m) ? "causal_mh_kernel" : ((m->tc16 && zmax <= 16) ? "causal_mh_tc16_kernel" : "causal_mh_tc_kernel");
+  snprintf(buf, (size_t)len, "%s<%d>", base, zmax);
+  return 0;
+}
+
 int bgm_causal_project(const bgm_causal* m, const float* v_dev, int ldv, int n, float* vproj_dev,
                        int ldvproj, float* r0_dev, void* stream) {
   if (!m) return fail(BGM_ERR_ARG, "bgm_causal_project: null model");

@@ -75,7 +75,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -179,8 +179,7 @@ def run_ours(args):
     info = model.kernel_info()
     sinfo = model.sampler_info()
     tensor = sinfo['engine'] == 'tensor'
-    zmax = 8 if sum(Z_DIMS) <= 8 else (16 if sum(Z_DIMS) <= 16 else 32)
-    kname = ("causal_mh_tc_kernel<%d>" if tensor else "causal_mh_kernel<%d>") % zmax
+    kname = sinfo['kernel']
     x, y, v = make_data(rank)                      # weak scaling: every rank its own n rows
     T = BURN_IN + N_MCMC
     # ---- device-resident arm ----
@@ -204,8 +203,14 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i, False)
+    # W warm-up steps, then keep warming until ~1.5 s of GPU work has run: a step is ~35 ms, and an
+    # idle B200 (120 MHz) needs far longer than 3 such steps to reach its boost clock
+    t_w = time.perf_counter()
+    warm_run = 0
+    while warm_run < args.warmup or (time.perf_counter() - t_w < 1.5 and warm_run < 200):
+        step(warm_run % max(args.steps, 1), False)
+        warm_run += 1
+        torch.cuda.synchronize()
     clocks = ClockSampler(local)
     barrier()
     clocks.start()
@@ -300,7 +305,8 @@ def run_ours(args):
                     "api": "CausalBGM.predict(x_values=linspace(0,3,20), sample_y=True, bs=n)"},
             "gpu_launches": args.steps,
             "kernel": {"name": kname, "engine": sinfo['engine'], "ms_per_launch": kern_ms_mean,
-                       "warps_per_cta": 8, "smem_bytes": sinfo['tensor_smem_bytes'] if tensor else info['smem_bytes']},
+                       "ms_per_launch_min_max": [float(min(kern_ms)), float(max(kern_ms))], "warmup_steps_run": warm_run,
+                       "warps_per_cta": 16 if 'tc16' in kname else 8, "smem_bytes": sinfo['tensor_smem_bytes'] if tensor else info['smem_bytes']},
             "roofline": roofline,
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9,
                              "peak": peaks["hbm_gbs"], "unit": "GB/s",
