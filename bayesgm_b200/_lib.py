@@ -121,6 +121,12 @@ SYMBOLS = {
                                         C.c_void_p]),
     "bgm_causal_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_bgmtrainer_set_iter": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "bgm_bgm_iter_g": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_void_p]),
+    "bgm_bgm_iter_latent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "bgm_bgm_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_hmc_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VarNetDesc)]),
     "bgm_hmc_destroy": (None, [C.c_void_p]),

@@ -474,12 +474,115 @@ class BGM(object):
         data_imputed = miss.astype(np.float32) * imputed + obs_mask * np.nan_to_num(data_np, nan=0.0)  # :662
         return data_imputed, pred_interval
 
-    # ------------------------------------------------- not on the hot path yet
+    # ------------------------------------------------------------ training: fit
+    def _encode_host(self, data):
+        """e_net(data) with the current weights (NumPy fp32; used once, for `data_z_init`, :388)."""
+        self._sync_from_trainer()
+        h = np.asarray(data, np.float32)
+        L = len(self.e_net.layers)
+        for i, (W, b) in enumerate(self.e_net.layers):
+            h = h @ W + b
+            if i < L - 1:
+                h = np.where(h > 0, h, np.float32(0.2) * h).astype(np.float32)
+        return h.astype(np.float32)
+
+    def evaluate(self, data, data_z=None, use_x_sd=True, *, seed=0):
+        """bgm/base.py:446-471: MSE between the data and its reconstruction from `data_z` (or from
+        e_net(data)), generator in inference mode.  With use_x_sd=True the reference adds
+        sigma * N(0,1) (`reparameterize`, TF RNG); here the draw comes from `seed`, so the value
+        agrees with the reference in distribution, exactly for use_x_sd=False."""
+        torch = _lib.require_cuda()
+        x = self._dev(data, torch, torch.float32).contiguous()
+        n = x.shape[0]
+        z = self._dev(self._encode_host(data) if data_z is None else data_z, torch, torch.float32).contiguous()
+        if not use_x_sd:
+            out = torch.zeros(1, dtype=torch.float64, device='cuda')
+            _lib.call("bgm_bgm_evaluate", self._device_trainer(), _lib.ptr(z), _lib.ptr(x), n, _lib.ptr(out),
+                      _lib.stream_ptr())
+            return float(out.cpu()[0]) / (n * self._p['x_dim'])
+        self._sync_from_trainer()
+        pred = self._predict_device(z[None], 1, n, seed)[0]
+        return float(((x - pred) ** 2).mean().cpu())
+
     def fit(self, data, batch_size=32, epochs=100, epochs_per_eval=5, use_egm_init=True, egm_n_iter=20000,
             egm_batches_per_eval=500, verbose=1):
-        raise NotImplementedError(
-            "bayesgm_b200: the BGM training path (bgm/base.py:145-442) has no sm_100a kernels yet; "
-            "load trained weights with set_weights().")
+        """bgm/base.py:343-442: optional EGM warm-start, latent table from e(X) (or N(0,1)), then
+        `epochs+1` epochs of mini-batch `update_g_net` + `update_latent_variable_sgd` (the incomplete
+        last batch is skipped, :401), evaluating every `epochs_per_eval` epochs.  Data, latent table,
+        parameters and optimizer state stay on the device; the epoch permutation comes from NumPy's
+        global generator (`np.random.choice(n, n, replace=False)`, :397) -- bit-exact index stream."""
+        torch = _lib.require_cuda()
+        n = len(data)
+        bs = int(batch_size)
+        if bs > 32:
+            raise NotImplementedError("bayesgm_b200: the training kernels take mini-batches of at most 32 rows")
+        if self._p['save_res']:
+            with open('{}/params.txt'.format(self.save_dir), 'w') as f_params:
+                f_params.write(str(self.params))
+        if use_egm_init:
+            self.egm_init(data, egm_n_iter=egm_n_iter, egm_batches_per_eval=egm_batches_per_eval,
+                          batch_size=batch_size, verbose=verbose)
+            if verbose:
+                print('Initialize latent variables Z with e(V)...')
+            data_z_init = self._encode_host(data)                                              # :388
+        else:
+            if verbose:
+                print('Random initialization of latent variables Z...')
+            data_z_init = np.random.normal(0, 1, size=(n, self._p['z_dim'])).astype('float32')   # :391
+        xd = self._dev(data, torch, torch.float32).contiguous()
+        z = torch.from_numpy(np.ascontiguousarray(data_z_init)).cuda()
+        self.data_z = z
+        tr = self._device_trainer()
+        st = _lib.stream_ptr()
+        _lib.call("bgm_bgmtrainer_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']))
+        gl = torch.zeros(2, dtype=torch.float32, device='cuda')
+        zl = torch.zeros(1, dtype=torch.float32, device='cuda')
+        self.history_loss = []
+        if verbose:
+            print('Iterative Updating Starts ...')
+        for epoch in range(int(epochs) + 1):
+            sample_idx = np.random.choice(n, n, replace=False)                                # :397
+            idx_d = torch.from_numpy(sample_idx.astype(np.int32)).cuda()
+            base = idx_d.data_ptr()
+            for i in range(0, n - bs + 1, bs):                                                # :401
+                ip = C.c_void_p(base + 4 * i)
+                _lib.call("bgm_bgm_iter_g", tr, _lib.ptr(z), _lib.ptr(xd), ip, bs, 1, 1.0, _lib.ptr(gl), st)   # :406
+                _lib.call("bgm_bgm_iter_latent", tr, _lib.ptr(z), _lib.ptr(xd), ip, bs, _lib.ptr(zl), None, st)  # :409-413
+            self._trainer_dirty = True
+            if epoch % epochs_per_eval == 0:                                                  # :425-442
+                mse_x = self.evaluate(data=xd, data_z=z)
+                self.history_loss.append(mse_x)
+                if verbose:
+                    print('Epoch [%d/%d]: MSE_x: %.4f\n' % (epoch, epochs, mse_x))
+                if self._p['save_res']:
+                    gen1, var1 = self.generate(nb_samples=5000)
+                    gen12, var12 = self.generate(nb_samples=5000, use_x_sd=False)
+                    np.savez('%s/data_gen_at_%d.npz' % (self.save_dir, epoch), gen1=gen1, gen12=gen12,
+                             z=z.cpu().numpy(), var1=var1, var12=var12)
+        self.last_iter_losses = tuple(float(a) for a in gl.cpu().numpy()) + (float(zl.cpu()[0]),)
+
+    def iter_step(self, data_z_table, data, batch_idx, *, apply=True):
+        """One mini-batch of the iterative phase on device copies of the given host arrays (parity
+        tests): returns ((loss_x, loss_mse_x), loss_postrior_z, grad rows, updated latent table)."""
+        torch = _lib.require_cuda()
+        tr = self._device_trainer()
+        st = _lib.stream_ptr()
+        if not getattr(self, '_iter_ready', False) or self._trainer_epoch != id(tr):
+            _lib.call("bgm_bgmtrainer_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']))
+            self._iter_ready, self._trainer_epoch = True, id(tr)
+        z = self._dev(data_z_table, torch, torch.float32).contiguous().clone()
+        xd = self._dev(data, torch, torch.float32).contiguous()
+        idx = torch.from_numpy(np.asarray(batch_idx, np.int32)).cuda()
+        bs = len(batch_idx)
+        gl = torch.zeros(2, dtype=torch.float32, device='cuda')
+        zl = torch.zeros(1, dtype=torch.float32, device='cuda')
+        gz = torch.zeros((bs, self._p['z_dim']), dtype=torch.float32, device='cuda')
+        _lib.call("bgm_bgm_iter_g", tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(idx), bs, 1 if apply else 0, 1.0,
+                  _lib.ptr(gl), st)
+        _lib.call("bgm_bgm_iter_latent", tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(idx), bs, _lib.ptr(zl), _lib.ptr(gz), st)
+        self._trainer_dirty = True
+        g = gl.cpu().numpy()
+        return (float(g[0]), float(g[1])), float(zl.cpu()[0]), gz.cpu().numpy(), z.cpu().numpy()
 
     # ------------------------------------------------------------ EGM training
     def _grad_tensor(self, group):

@@ -505,6 +505,98 @@ int bgm_train_iter_latent(bgm_trainer* t, float* zt_dev, float* m_dev, float* v_
   return 0;
 }
 
+// ---------------------------------------------------- iterative phase of BGM.fit ----
+int bgm_bgmtrainer_set_iter(bgm_trainer* t, float lr_theta, float lr_z) {
+  using namespace bgm;
+  if (!t || t->kind != 1) return fail(BGM_ERR_ARG, "bgm_bgmtrainer_set_iter: needs a BGM trainer");
+  t->lr_theta = lr_theta; t->lr_z = lr_z;
+  const int g_params = t->e.w_off[0];
+  if (!t->m_it) {
+    BGM_CUDA_OK(cudaMalloc(&t->m_it, sizeof(float) * (size_t)g_params));
+    BGM_CUDA_OK(cudaMalloc(&t->v_it, sizeof(float) * (size_t)g_params));
+  }
+  BGM_CUDA_OK(cudaMemset(t->m_it, 0, sizeof(float) * (size_t)g_params));
+  BGM_CUDA_OK(cudaMemset(t->v_it, 0, sizeof(float) * (size_t)g_params));
+  t->step_it = t->step_z = 0;
+  t->smem_iter = (4 * t->wm * tr::LD + 5 * t->zd * tr::LD + ((t->zd + 3) & ~3) + 8) * 4 + 64;
+  t->smem_eval = (2 * t->wm * tr::LD + t->zd * tr::LD) * 4 + 64;
+  return 0;
+}
+
+static void bgm_iter_fill(const bgm_trainer* t, bgm::tr::BgmIterArgs& A, float* zt, const float* x, const int* idx,
+                          int bs) {
+  memset(&A, 0, sizeof(A));
+  A.g = t->vg; A.zd = t->zd; A.xd = t->xd; A.bs = bs;
+  A.theta = t->theta[0]; A.grad = t->grad[0]; A.tape = t->tape; A.moving = t->moving;
+  A.zt = zt; A.x = x; A.idx = idx; A.wm = t->wm;
+}
+
+int bgm_bgm_iter_g(bgm_trainer* t, const float* zt_dev, const float* x_dev, const int* idx_dev, int bs, int apply,
+                   float grad_scale, float* losses_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 1 || !t->m_it) return fail(BGM_ERR_ARG, "bgm_bgm_iter_g: call bgm_bgmtrainer_set_iter first");
+  if (!zt_dev || !x_dev || !idx_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_bgm_iter_g: null argument");
+  if (bs < 1 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_bgm_iter_g: batch size must be in [1, 32]");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (apply != 2) {
+    tr::BgmIterArgs A;
+    bgm_iter_fill(t, A, const_cast<float*>(zt_dev), x_dev, idx_dev, bs);
+    A.losses = losses_dev;
+    BGM_CUDA_OK(cudaFuncSetAttribute(tr::bgm_iter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_iter));
+    tr::bgm_iter_kernel<0><<<1, tr::NTH, t->smem_iter, st>>>(A);
+    BGM_CUDA_OK(cudaGetLastError());
+  }
+  if (apply) {   // g_optimizer (:87): Adam(lr_theta, 0.9, 0.99) on the generator parameters only
+    t->step_it += 1;
+    const double k = (double)t->step_it;
+    const float lr_t = (float)(t->lr_theta * std::sqrt(1.0 - std::pow(0.99, k)) / (1.0 - std::pow(0.9, k)));
+    const int n = t->e.w_off[0];
+    const int grid = std::max(1, std::min((n + 255) / 256, t->sm_count * 4));
+    tr::adam_kernel<<<grid, 256, 0, st>>>(t->theta[0], t->grad[0], t->m_it, t->v_it, n, lr_t, 0.9f, 0.99f, 1e-7f,
+                                          grad_scale);
+    BGM_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int bgm_bgm_iter_latent(bgm_trainer* t, float* zt_dev, const float* x_dev, const int* idx_dev, int bs,
+                        float* loss_dev, float* gz_out_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 1 || !t->m_it) return fail(BGM_ERR_ARG, "bgm_bgm_iter_latent: call bgm_bgmtrainer_set_iter first");
+  if (!zt_dev || !x_dev || !idx_dev || !loss_dev) return fail(BGM_ERR_ARG, "bgm_bgm_iter_latent: null argument");
+  if (bs < 1 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_bgm_iter_latent: batch size must be in [1, 32]");
+  tr::BgmIterArgs A;
+  bgm_iter_fill(t, A, zt_dev, x_dev, idx_dev, bs);
+  A.losses = loss_dev;
+  A.gz_out = gz_out_dev;
+  // posterior_optimizer (:88): one optimizer (shared step count), a fresh variable per batch
+  t->step_z += 1;
+  const double k = (double)t->step_z;
+  A.lr_t = (float)(t->lr_z * std::sqrt(1.0 - std::pow(0.99, k)) / (1.0 - std::pow(0.9, k)));
+  A.b1 = 0.9f; A.b2 = 0.99f; A.eps = 1e-7f;
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::bgm_iter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_iter));
+  tr::bgm_iter_kernel<1><<<1, tr::NTH, t->smem_iter, (cudaStream_t)stream>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_bgm_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, int n, double* sum_dev, void* stream) {
+  using namespace bgm;
+  if (!t || t->kind != 1) return fail(BGM_ERR_ARG, "bgm_bgm_evaluate: needs a BGM trainer");
+  if (!zt_dev || !x_dev || !sum_dev || n < 1) return fail(BGM_ERR_ARG, "bgm_bgm_evaluate: bad argument");
+  if (!t->smem_eval) t->smem_eval = (2 * t->wm * tr::LD + t->zd * tr::LD) * 4 + 64;
+  tr::BgmEvalArgs A;
+  memset(&A, 0, sizeof(A));
+  A.g = t->vg; A.zd = t->zd; A.xd = t->xd; A.n = n; A.theta = t->theta[0]; A.moving = t->moving;
+  A.zt = zt_dev; A.x = x_dev; A.sum_out = sum_dev; A.wm = t->wm;
+  BGM_CUDA_OK(cudaMemsetAsync(sum_dev, 0, sizeof(double), (cudaStream_t)stream));
+  BGM_CUDA_OK(cudaFuncSetAttribute(tr::bgm_eval_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_eval));
+  const int grid = std::max(1, std::min((n + 31) / 32, t->sm_count * 2));
+  tr::bgm_eval_kernel<<<grid, tr::NTH, t->smem_eval, (cudaStream_t)stream>>>(A);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int bgm_causal_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, const float* y_dev,
                         const float* v_dev, int n, double* sums_dev, float* z_out_dev, void* stream) {
   using namespace bgm;

@@ -424,5 +424,159 @@ __global__ void __launch_bounds__(NTH, 1) bgm_disc_grad_kernel(const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Iterative phase of BGM.fit (bgm/base.py:145-187, loop :397-415).
+//  MODE 0  update_g_net: loss_x = mean_r sum_c [(x-mu)^2 / (2 s2) + log(s2)/2], gradients of all
+//          generator parameters (input BN gamma/beta, hidden stack, mean / variance heads).
+//  MODE 1  update_latent_variable_sgd: the same likelihood + mean_r |z_r|^2 / 2, gradient w.r.t. the
+//          batch rows of z THROUGH the training-mode BatchNormalization (batch statistics couple
+//          the rows), then Adam on a FRESH variable (the reference wraps every batch in a new
+//          tf.Variable, so the slots start at zero: step = lr_t (1-b1) g / (sqrt((1-b2) g^2) + eps),
+//          SURVEY A.4) written back into the latent table (scatter_nd_update, :410-413).
+// Both calls run the generator in training mode, so both update the BN moving statistics.
+struct BgmIterArgs {
+  VarNet g;
+  int zd, xd, bs;
+  const float* theta;
+  float* grad;
+  float* tape;
+  float* moving;
+  float* zt;           // latent table (n, zd)
+  const float* x;      // data (n, xd)
+  const int* idx;      // (bs)
+  float* losses;       // MODE 0: [2] loss_x, loss_mse_x ; MODE 1: [1] loss_postrior_z
+  float* gz_out;       // MODE 1, optional: (bs, zd) gradient rows (parity tests)
+  float lr_t, b1, b2, eps;
+  int wm;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(NTH, 1) bgm_iter_kernel(const __grid_constant__ BgmIterArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  const int bs = A.bs, xd = A.xd, zd = A.zd;
+  const float inv_bs = 1.f / (float)bs;
+  float* bufA = sm;
+  float* bufB = bufA + A.wm * LD;
+  float* bufC = bufB + A.wm * LD;      // x batch, later layer-input scratch of the backward
+  float* bufD = bufC + A.wm * LD;      // seeds [2*xd][LD]
+  float* zmat = bufD + A.wm * LD;      // [zd][LD]
+  float* ymat = zmat + zd * LD;        // BN output
+  float* nsv = ymat + zd * LD;         // normalised input
+  float* gy = nsv + zd * LD;           // d / d BN output
+  float* gz = gy + zd * LD;            // d / d z
+  float* ssv = gz + zd * LD;           // [zd]
+  float* red = ssv + ((zd + 3) & ~3);  // [8]
+  const float* th = A.theta;
+  const Net& G = A.g.mlp;
+  float* T_g = A.tape;
+  float* T_y = T_g + net_tape_floats(G);
+  gather_cols(A.zt, zd, A.idx, zd, bs, zmat);
+  gather_cols(A.x, xd, A.idx, xd, bs, bufC);
+  if (threadIdx.x < 8) red[threadIdx.x] = 0.f;
+  __syncthreads();
+  bn_train_fwd(th, A.g, bs, zmat, ymat, nsv, ssv, A.moving);
+  copy_mat(ymat, T_y, zd);
+  float* o = mlp_forward(G, th, ymat, bufA, bufB, T_g);
+  // Gaussian NLL over every column; seeds d mean_r(loss_r) / d [mu | raw]
+  {
+    float l = 0.f, se = 0.f;
+    for (int i = threadIdx.x; i < xd * 32; i += NTH) {
+      const int c = i >> 5, r = i & 31;
+      float dmu = 0.f, draw = 0.f;
+      if (r < bs) {
+        const float raw = o[(xd + c) * LD + r];
+        const float s2 = softplus_f(raw) + 1e-6f;
+        const float d = bufC[c * LD + r] - o[c * LD + r];
+        l += (d * d) / (2.f * s2) + 0.5f * logf(s2);
+        se = fmaf(d, d, se);
+        dmu = -d / s2 * inv_bs;
+        draw = (-(d * d) / (2.f * s2 * s2) + 0.5f / s2) * sigmoid_f(raw) * inv_bs;
+      }
+      bufD[c * LD + r] = dmu;
+      bufD[(xd + c) * LD + r] = draw;
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, k);
+      se += __shfl_xor_sync(0xffffffffu, se, k);
+    }
+    if ((threadIdx.x & 31) == 0) { atomicAdd(red + 0, l); atomicAdd(red + 1, se); }
+    __syncthreads();
+  }
+  mlp_backward(G, th, A.grad, T_y, T_g, bufD, bufA, bufB, bufC, gy, false);
+  bn_train_bwd(th, A.g, bs, gy, nsv, ssv, A.grad, false, MODE == 1 ? gz : nullptr);
+  if (MODE == 0) {
+    if (threadIdx.x == 0) {
+      A.losses[0] = red[0] * inv_bs;
+      A.losses[1] = red[1] / (float)(bs * xd);
+    }
+  } else {
+    float pr = 0.f;
+    for (int i = threadIdx.x; i < zd * 32; i += NTH) {
+      const int d = i >> 5, r = i & 31;
+      if (r < bs) {
+        const float z = zmat[d * LD + r];
+        pr = fmaf(z, z, pr);
+        const float g = gz[d * LD + r] + z * inv_bs;           // prior |z|^2/2, mean over the batch
+        if (A.gz_out) A.gz_out[(size_t)r * zd + d] = g;
+        const float m = (1.f - A.b1) * g, v = (1.f - A.b2) * g * g;
+        A.zt[(size_t)A.idx[r] * zd + d] = z - A.lr_t * m / (sqrtf(v) + A.eps);
+      }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) pr += __shfl_xor_sync(0xffffffffu, pr, k);
+    if ((threadIdx.x & 31) == 0) atomicAdd(red + 2, pr);
+    __syncthreads();
+    if (threadIdx.x == 0) A.losses[0] = (red[0] + 0.5f * red[2]) * inv_bs;
+  }
+}
+
+// evaluate (:446-471) with use_x_sd = False: sum over rows and columns of (x - mu(z))^2, generator in
+// inference mode (BN moving statistics).  One CTA per 32 rows.
+struct BgmEvalArgs {
+  VarNet g;
+  int zd, xd, n;
+  const float* theta;
+  const float* moving;
+  const float* zt;
+  const float* x;
+  double* sum_out;
+  int wm;
+};
+__global__ void __launch_bounds__(NTH, 1) bgm_eval_kernel(const __grid_constant__ BgmEvalArgs A) {
+  extern __shared__ __align__(16) float sm[];
+  const int xd = A.xd, zd = A.zd;
+  float* bufA = sm;
+  float* bufB = bufA + A.wm * LD;
+  float* ymat = bufB + A.wm * LD;
+  const float* th = A.theta;
+  for (int row0 = blockIdx.x * 32; row0 < A.n; row0 += gridDim.x * 32) {
+    const int bs = min(32, A.n - row0);
+    for (int i = threadIdx.x; i < zd * 32; i += NTH) {
+      const int d = i >> 5, r = i & 31;
+      float y = 0.f;
+      if (r < bs) {
+        const float z = A.zt[(size_t)(row0 + r) * zd + d];
+        y = (z - A.moving[d]) / sqrtf(A.moving[zd + d] + BN_EPS) * th[A.g.gamma_off + d] + th[A.g.beta_off + d];
+      }
+      ymat[d * LD + r] = y;
+    }
+    __syncthreads();
+    float* o = mlp_forward(A.g.mlp, th, ymat, bufA, bufB, nullptr);
+    float se = 0.f;
+    for (int i = threadIdx.x; i < xd * 32; i += NTH) {
+      const int c = i >> 5, r = i & 31;
+      if (r < bs) {
+        const float d = A.x[(size_t)(row0 + r) * xd + c] - o[c * LD + r];
+        se = fmaf(d, d, se);
+      }
+    }
+#pragma unroll
+    for (int k = 16; k > 0; k >>= 1) se += __shfl_xor_sync(0xffffffffu, se, k);
+    if ((threadIdx.x & 31) == 0) atomicAdd(A.sum_out, (double)se);
+    __syncthreads();
+  }
+}
+
 }  // namespace tr
 }  // namespace bgm

@@ -353,6 +353,26 @@ int bgm_train_iter_latent(bgm_trainer* t, float* zt_dev, float* m_dev, float* v_
 int bgm_causal_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, const float* y_dev,
                         const float* v_dev, int n, double* sums_dev, float* z_out_dev, void* stream);
 
+/* ---- iterative phase of BGM.fit (bgm/base.py:145-187, loop :397-415) on a BGM trainer ----
+ * bgm_bgmtrainer_set_iter: g_optimizer / posterior_optimizer (:87-88, Adam beta = (0.9, 0.99)) state.
+ * bgm_bgm_iter_g: update_g_net on the rows idx_dev of (zt_dev (n,z_dim), x_dev (n,x_dim)): generator in
+ *   TRAINING mode (input BatchNormalization with batch statistics, moving statistics updated),
+ *   losses_dev[2] = loss_x, loss_mse_x; apply 0: gradients only, 1: + Adam, 2: Adam on the gradients
+ *   already in the buffer (after an all-reduce).
+ * bgm_bgm_iter_latent: update_latent_variable_sgd: gradient of mean_r(-log p(x_r|z_r) + |z_r|^2/2) w.r.t.
+ *   the batch rows through the training-mode BatchNormalization, then Adam on a FRESH variable per
+ *   batch (the reference wraps every batch in a new tf.Variable: zero slots, shared step count) written
+ *   back into zt_dev; loss_dev[1]; gz_out_dev (bs,z_dim) optionally receives the gradient rows.
+ * bgm_bgm_evaluate: sum_dev[1] (float64) = sum over rows and columns of (x - mu(z))^2, generator in
+ *   inference mode (evaluate with use_x_sd=False, :446-471). */
+int bgm_bgmtrainer_set_iter(bgm_trainer* t, float lr_theta, float lr_z);
+int bgm_bgm_iter_g(bgm_trainer* t, const float* zt_dev, const float* x_dev, const int* idx_dev, int bs,
+                   int apply, float grad_scale, float* losses_dev, void* stream);
+int bgm_bgm_iter_latent(bgm_trainer* t, float* zt_dev, const float* x_dev, const int* idx_dev, int bs,
+                        float* loss_dev, float* gz_out_dev, void* stream);
+int bgm_bgm_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, int n, double* sum_dev,
+                     void* stream);
+
 /* dst[r][:] = src[idx[r]][:dim] -- mini-batch gather from device-resident data (:406-416). */
 int bgm_gather_rows(const float* src_dev, int ld, const int* idx_dev, int bs, int dim, float* dst_dev,
                     void* stream);

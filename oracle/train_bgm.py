@@ -114,3 +114,85 @@ def gen_step(params, g, e, dz, dx, batch_z, batch_x, noise1, noise2):
     grads = [a.numpy() for a in torch.autograd.grad(loss, plist)]
     losses = tuple(float(a.detach()) for a in (g_adv, e_adv, l2_z, l2_x, reg, loss))
     return losses, grads, stats
+
+
+# ----------------------------------------------------------------------------------------
+# Iterative phase of BGM.fit (bgm/base.py:145-187 and the loop :397-415)
+def iter_g_grads(g, batch_z, batch_x):
+    """update_g_net (:145-164): returns (loss_x, loss_mse, grads in g_param_list order, BN batch stats).
+    The generator runs in training mode (`self.g_net(data_z)`, default training=True)."""
+    gt = g_to_t(g, True)
+    z = torch.tensor(batch_z, dtype=torch.float32)
+    x = torch.tensor(batch_x, dtype=torch.float32)
+    stats = []
+    mu, s2 = var_net_train(gt, z, stats)
+    loss_mse = ((x - mu) ** 2).mean()
+    loss_x = (((x - mu) ** 2) / (2 * s2) + 0.5 * torch.log(s2)).sum(dim=1).mean()
+    grads = torch.autograd.grad(loss_x, g_param_list(gt))
+    return float(loss_x.detach()), float(loss_mse.detach()), [a.numpy() for a in grads], stats
+
+
+def iter_latent_grad(g, batch_z, batch_x):
+    """update_latent_variable_sgd (:167-187): returns (loss_postrior_z, d loss / d batch_z, BN stats)."""
+    gt = g_to_t(g, False)
+    z = torch.tensor(batch_z, dtype=torch.float32, requires_grad=True)
+    x = torch.tensor(batch_x, dtype=torch.float32)
+    stats = []
+    mu, s2 = var_net_train(gt, z, stats)
+    loss = (((x - mu) ** 2) / (2 * s2) + 0.5 * torch.log(s2)).sum(dim=1).mean() + ((z ** 2).sum(dim=1) / 2).mean()
+    (gz,) = torch.autograd.grad(loss, [z])
+    return float(loss.detach()), gz.numpy(), stats
+
+
+def var_net_infer(g, z):
+    """BaseVariationalNet.call(training=False): BN with the moving statistics; NumPy float32."""
+    f32 = np.float32
+    h = (z - g['bn']['mean']) / np.sqrt(g['bn']['var'] + f32(BN_EPS)) * g['bn']['gamma'] + g['bn']['beta']
+    for W, b in g['hidden']:
+        h = h @ W + b
+        h = np.where(h > 0, h, f32(0.2) * h).astype(f32)
+    mean = h @ g['mean'][0] + g['mean'][1]
+    raw = h @ g['var'][0] + g['var'][1]
+    return mean.astype(f32), (np.logaddexp(0, raw) + f32(1e-6)).astype(f32)
+
+
+class BgmIterTrainer(object):
+    """The iterative phase of BGM.fit on host arrays: Keras Adam(lr_theta, .9, .99) on the generator,
+    and for the latent rows Adam(lr_z, .9, .99) applied to a FRESH variable per batch (zero slots,
+    shared step count) followed by scatter_nd_update (:410-413)."""
+
+    def __init__(self, params, g, data_z):
+        from .train import Adam
+        self.params, self.g = params, g
+        self.data_z = np.array(data_z, np.float32)
+        self.g_opt = Adam(params['lr_theta'], 0.9, 0.99)
+        self.lr_z, self.t_z = params['lr_z'], 0
+
+    def step(self, data, batch_idx):
+        bz, bx = self.data_z[batch_idx].copy(), data[batch_idx]
+        loss_x, mse, grads, stats = iter_g_grads(self.g, bz, bx)
+        flat = g_flat_params(self.g)
+        self.g_opt.apply(flat, grads)
+        # write the updated arrays back into the dict (Adam updates in place, keep references in sync)
+        self.g['bn']['gamma'], self.g['bn']['beta'] = flat[0], flat[1]
+        update_moving(self.g, stats)
+        lz, gz, stats = iter_latent_grad(self.g, bz, bx)
+        update_moving(self.g, stats)
+        f32 = np.float32
+        self.t_z += 1
+        lr_t = f32(self.lr_z * np.sqrt(1.0 - 0.99 ** self.t_z) / (1.0 - 0.9 ** self.t_z))
+        m, v = f32(0.1) * gz, f32(1 - 0.99) * gz * gz
+        self.data_z[batch_idx] = bz - lr_t * m / (np.sqrt(v) + f32(1e-7))
+        return (loss_x, mse), lz, gz
+
+    def epoch(self, data, batch_size):
+        n = len(data)
+        sample_idx = np.random.choice(n, n, replace=False)                 # :397
+        last = None
+        for i in range(0, n - batch_size + 1, batch_size):                 # incomplete last batch skipped (:401)
+            last = self.step(data, sample_idx[i:i + batch_size])
+        return last
+
+    def mse(self, data):
+        mu, _ = var_net_infer(self.g, self.data_z)
+        return float(np.mean((data - mu) ** 2))

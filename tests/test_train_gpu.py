@@ -320,3 +320,67 @@ def test_fit_with_egm_init_binary_end_to_end():
     assert m.best_causal_pre.shape == (64, 1)                    # ITE per subject (:559-563)
     ite, interval = m.predict(data, n_mcmc=10, burn_in=10, q_sd=0.5, verbose=0)
     assert ite.shape == (64,) and np.isfinite(ite).all()
+
+
+# ------------------------------------------ BGM: iterative phase of fit (bgm/base.py:145-187) --
+@pytest.mark.parametrize("kw", [dict(x_dim=20, z_dim=4), dict(x_dim=100, z_dim=10, bs=32),
+                                dict(x_dim=7, z_dim=3, bs=11, g_units=(16, 16))])
+def test_bgm_iter_step_tracks_the_oracle(kw):
+    """update_g_net + update_latent_variable_sgd, three consecutive mini-batches: losses, the
+    gradient w.r.t. the latent rows (through the training-mode BatchNormalization), the scattered
+    latent table (fresh-variable Adam), the generator parameters and the BN moving statistics."""
+    import copy
+    bs = kw.pop('bs', 16)
+    params, g, e, dz, dx, m, _, _, _, _ = make_bgm(bs=bs, lr_theta=1e-3, lr_z=1e-2, **kw)
+    x_dim, z_dim = params['x_dim'], params['z_dim']
+    rs = np.random.RandomState(8)
+    n = 80
+    data = rs.standard_normal((n, x_dim)).astype(np.float32)
+    table = rs.standard_normal((n, z_dim)).astype(np.float32)
+    ot = train_bgm.BgmIterTrainer(params, copy.deepcopy(g), table)
+    cur = table.copy()
+    for k in range(3):
+        idx = rs.choice(n, bs, replace=False)
+        (wl, wm), wz, wgz = ot.step(data, idx)
+        (gl, gm), gzl, ggz, cur = m.iter_step(cur, data, idx)
+        np.testing.assert_allclose([gl, gm, gzl], [wl, wm, wz], rtol=3e-4, atol=1e-5)
+        np.testing.assert_allclose(ggz, wgz, rtol=2e-3, atol=2e-5 * max(1.0, np.abs(wgz).max()))
+        # the Adam step on a fresh variable is ~ lr_t * sign(g): rows agree unless a gradient is ~0
+        np.testing.assert_allclose(cur, ot.data_z, rtol=0, atol=2.5e-3)
+        assert np.median(np.abs(cur - ot.data_z)) < 1e-6
+        untouched = np.setdiff1d(np.arange(n), idx)
+        np.testing.assert_array_equal(cur[untouched], table[untouched] if k == 0 else prev[untouched])
+        prev = cur.copy()
+    w = m.get_weights()
+    np.testing.assert_allclose(w['g'][2], ot.g['bn']['mean'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(w['g'][3], ot.g['bn']['var'], rtol=1e-4, atol=1e-5)
+    want_g = train_bgm.g_flat_params(ot.g)
+    got_g = w['g'][:2] + w['g'][4:]
+    for a, b in zip(got_g, want_g):
+        assert np.abs(a - b).max() <= 3 * 1e-3 * 1.01      # k * lr_theta bound
+        assert np.median(np.abs(a - b)) <= 2e-5
+
+
+def test_bgm_fit_end_to_end_tracks_the_oracle_loop():
+    """BGM.fit(use_egm_init=False): the reference's NumPy streams (N(0,1) table, epoch permutations),
+    two epochs of mini-batches with the incomplete last batch skipped, evaluate(use_x_sd=False)."""
+    import copy
+    params = bgm_params(12, 3, lr_theta=1e-3, lr_z=1e-3)
+    g = bgm_oracle_net(params, seed=31)
+    m = bgm_product_model(params, g)
+    n, bs = 70, 16
+    data = np.random.RandomState(4).standard_normal((n, 12)).astype(np.float32)
+    np.random.seed(11)
+    m.fit(data, batch_size=bs, epochs=1, epochs_per_eval=1, use_egm_init=False, verbose=0)
+    np.random.seed(11)
+    z0 = np.random.normal(0, 1, size=(n, 3)).astype('float32')
+    ot = train_bgm.BgmIterTrainer(params, copy.deepcopy(g), z0)
+    for _ in range(2):
+        ot.epoch(data, bs)
+    got_z = m.data_z.cpu().numpy()
+    assert np.median(np.abs(got_z - ot.data_z)) < 1e-5
+    assert np.abs(got_z - ot.data_z).max() < 2 * 8 * 1e-3      # epochs * batches * lr_z bound
+    assert len(m.history_loss) == 2 and all(np.isfinite(m.history_loss))
+    assert abs(m.evaluate(data, m.data_z, use_x_sd=False) - ot.mse(data)) < 1e-3 * max(1.0, ot.mse(data))
+    # use_x_sd=True adds sigma^2 on average
+    assert m.evaluate(data, m.data_z, use_x_sd=True) > m.evaluate(data, m.data_z, use_x_sd=False)
