@@ -84,9 +84,9 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
         if self.proc is None:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
         self.proc.terminate()
@@ -96,7 +96,9 @@ class ClockSampler(object):
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if t_begin is not None and not (t_begin <= ts <= t_end + 0.05):
+                continue
             try:
                 sm.append(float(r[0]))
                 smax = float(r[1])
@@ -205,22 +207,39 @@ def run_ours(args):
 
     # W warm-up steps, then keep warming until ~1.5 s of GPU work has run: a step is ~35 ms, and an
     # idle B200 (120 MHz) needs far longer than 3 such steps to reach its boost clock
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, driver locks) stalled
+    # CUDA calls of the first timed step for 100+ ms when it was started at the timed region's edge
+    clocks = ClockSampler(local)
+    clocks.start()
     t_w = time.perf_counter()
     warm_run = 0
-    while warm_run < args.warmup or (time.perf_counter() - t_w < 1.5 and warm_run < 200):
+    while warm_run < args.warmup or (time.perf_counter() - t_w < 2.5 and warm_run < 200):
         step(warm_run % max(args.steps, 1), False)
         warm_run += 1
         torch.cuda.synchronize()
-    clocks = ClockSampler(local)
-    barrier()
-    clocks.start()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        r = step(i, True)
-    barrier()
-    wall = time.perf_counter() - t0
-    clk = clocks.stop()
-    kern_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    def timed_pass():
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            rr = step(i, True)
+        barrier()
+        t1 = time.perf_counter()
+        return rr, t0, t1, [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+
+    r, t0, t1, kern_ms = timed_pass()
+    first_attempt = None
+    # A pass in which one step takes >1.3x the fastest one was disturbed from outside (observed: single
+    # steps of 70-180 ms next to 34 ms ones right after another CUDA process exits on the box, clocks at
+    # max, no throttle reason).  Like a throttled run it is re-measured ONCE; both are reported.
+    med_all = torch.tensor([max(kern_ms) / max(min(kern_ms), 1e-9)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(med_all, op=dist.ReduceOp.MAX)
+    if float(med_all[0]) > 1.3:
+        first_attempt = {"ms_per_step": 1e3 * (t1 - t0) / args.steps, "ms_per_launch_min_max": [float(min(kern_ms)), float(max(kern_ms))]}
+        time.sleep(2.0)
+        r, t0, t1, kern_ms = timed_pass()
+    wall = t1 - t0
+    clk = clocks.stop(t0, t1)
     accept = float(r['accept_count'].sum().item()) / (T * n)
     tm = torch.tensor([wall, float(np.mean(kern_ms))], dtype=torch.float64, device='cuda')
     if world > 1:
@@ -236,12 +255,27 @@ def run_ours(args):
                              verbose=0)
     for i in range(min(args.warmup, 2)):
         e2e_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        adrf, _ = e2e_step(i)
-    barrier()
-    e2e_wall = time.perf_counter() - t0
+
+    def e2e_pass():
+        barrier()
+        t0 = time.perf_counter()
+        per = []
+        for i in range(args.steps):
+            ts = time.perf_counter()
+            e2e_step(i)                 # returns host arrays: every step ends with its D2H
+            per.append(time.perf_counter() - ts)
+        barrier()
+        return time.perf_counter() - t0, per
+
+    e2e_wall, per = e2e_pass()
+    e2e_first = None
+    ratio = torch.tensor([max(per) / max(min(per), 1e-9)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(ratio, op=dist.ReduceOp.MAX)
+    if float(ratio[0]) > 1.3:           # same rule as the device-resident arm
+        e2e_first = {"ms_per_step": 1e3 * e2e_wall / args.steps}
+        time.sleep(2.0)
+        e2e_wall, per = e2e_pass()
     te = torch.tensor([e2e_wall], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -302,10 +336,12 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(4 * n * (V_DIM + 2)),
                     "d2h_bytes_per_step": int(4 * len(X_VALUES) * N_MCMC),
-                    "api": "CausalBGM.predict(x_values=linspace(0,3,20), sample_y=True, bs=n)"},
+                    "api": "CausalBGM.predict(x_values=linspace(0,3,20), sample_y=True, bs=n)",
+                    "ms_per_step": 1e3 * e2e_wall / args.steps, "remeasured_after_disturbed_pass": e2e_first},
             "gpu_launches": args.steps,
             "kernel": {"name": kname, "engine": sinfo['engine'], "ms_per_launch": kern_ms_mean,
                        "ms_per_launch_min_max": [float(min(kern_ms)), float(max(kern_ms))], "warmup_steps_run": warm_run,
+                       "remeasured_after_disturbed_pass": first_attempt,
                        "warps_per_cta": 16 if 'tc16' in kname else 8, "smem_bytes": sinfo['tensor_smem_bytes'] if tensor else info['smem_bytes']},
             "roofline": roofline,
             "roofline_hbm": {"bound": "hbm", "achieved": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9,
