@@ -58,6 +58,10 @@ __device__ __forceinline__ void wg_sync(int wg) {
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
 __device__ __forceinline__ float leaky_mx(float v) { return fmaxf(v, 0.2f * v); }  // == leaky(v)
+__device__ __forceinline__ float2 leaky_x2(float2 v) {
+  const float2 m = __fmul2_rn(v, make_float2(0.2f, 0.2f));
+  return make_float2(fmaxf(v.x, m.x), fmaxf(v.y, m.y));
+}
 
 // First layer of a net on the FMA pipe for the thread's row: out = LeakyReLU(b + in W), 64 wide,
 // rows of W (inputs) taken in ascending order like the SIMT engine; `mask` skips the rows
@@ -535,34 +539,43 @@ template <int KINMAX>
 __device__ __forceinline__ void first_layer32(const float* __restrict__ W, const float* __restrict__ b,
                                               unsigned long long mask, int nin, const float (&in)[KINMAX],
                                               int c0, float (&out)[32]) {
+  float2 o2[16];
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const float4 bb = *reinterpret_cast<const float4*>(b + c0 + q * 4);
-    out[q * 4 + 0] = bb.x; out[q * 4 + 1] = bb.y; out[q * 4 + 2] = bb.z; out[q * 4 + 3] = bb.w;
+    o2[q * 2 + 0] = make_float2(bb.x, bb.y);
+    o2[q * 2 + 1] = make_float2(bb.z, bb.w);
   }
 #pragma unroll
   for (int d = 0; d < KINMAX; ++d) {
     if (d < nin && ((mask >> d) & 1ull)) {
-      const float zv = in[d];
+      const float2 zv = make_float2(in[d], in[d]);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 ww = *reinterpret_cast<const float4*>(W + d * 64 + c0 + q * 4);
-        out[q * 4 + 0] = fmaf(zv, ww.x, out[q * 4 + 0]);
-        out[q * 4 + 1] = fmaf(zv, ww.y, out[q * 4 + 1]);
-        out[q * 4 + 2] = fmaf(zv, ww.z, out[q * 4 + 2]);
-        out[q * 4 + 3] = fmaf(zv, ww.w, out[q * 4 + 3]);
+        o2[q * 2 + 0] = __ffma2_rn(zv, make_float2(ww.x, ww.y), o2[q * 2 + 0]);
+        o2[q * 2 + 1] = __ffma2_rn(zv, make_float2(ww.z, ww.w), o2[q * 2 + 1]);
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) out[j] = leaky_mx(out[j]);
+  for (int j = 0; j < 16; ++j) {
+    const float2 a = leaky_x2(o2[j]);
+    out[2 * j] = a.x;
+    out[2 * j + 1] = a.y;
+  }
 }
 __device__ __forceinline__ void split_store32(const float (&a)[32], uint32_t tA_hi, uint32_t tA_lo) {
 #pragma unroll
   for (int h = 0; h < 2; ++h) {   // 16 columns at a time: the 16-warp kernels have 128 registers per thread
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) umma::split_tf32(a[h * 16 + j], hi[j], lo[j]);
+    for (int j = 0; j < 16; j += 2) {
+      float2 h2, l2;
+      umma::split_tf32_x2(make_float2(a[h * 16 + j], a[h * 16 + j + 1]), h2, l2);
+      hi[j] = __float_as_uint(h2.x); hi[j + 1] = __float_as_uint(h2.y);
+      lo[j] = __float_as_uint(l2.x); lo[j + 1] = __float_as_uint(l2.y);
+    }
     umma::st16(tA_hi + h * 16, hi);
     umma::st16(tA_lo + h * 16, lo);
   }
@@ -576,18 +589,23 @@ __device__ __forceinline__ void act_block16(uint32_t (&r)[16], const float* __re
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const float4 b = *reinterpret_cast<const float4*>(bias + i * 4);
-    const float bb[4] = {b.x, b.y, b.z, b.w};
-    float ws[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 ws = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (SIG) ws = *reinterpret_cast<const float4*>(wsig + i * 4);
+    const float2 a0 = leaky_x2(__fadd2_rn(make_float2(__uint_as_float(r[i * 4 + 0]), __uint_as_float(r[i * 4 + 1])),
+                                          make_float2(b.x, b.y)));
+    const float2 a1 = leaky_x2(__fadd2_rn(make_float2(__uint_as_float(r[i * 4 + 2]), __uint_as_float(r[i * 4 + 3])),
+                                          make_float2(b.z, b.w)));
     if constexpr (SIG) {
-      const float4 s4 = *reinterpret_cast<const float4*>(wsig + i * 4);
-      ws[0] = s4.x; ws[1] = s4.y; ws[2] = s4.z; ws[3] = s4.w;
+      sig = fmaf(a0.x, ws.x, sig); sig = fmaf(a0.y, ws.y, sig);
+      sig = fmaf(a1.x, ws.z, sig); sig = fmaf(a1.y, ws.w, sig);
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float a = leaky_mx(__uint_as_float(r[i * 4 + k]) + bb[k]);
-      if constexpr (SIG) sig = fmaf(a, ws[k], sig);
-      umma::split_tf32(a, r[i * 4 + k], lo[i * 4 + k]);
-    }
+    float2 h0, l0, h1, l1;
+    umma::split_tf32_x2(a0, h0, l0);
+    umma::split_tf32_x2(a1, h1, l1);
+    r[i * 4 + 0] = __float_as_uint(h0.x); r[i * 4 + 1] = __float_as_uint(h0.y);
+    r[i * 4 + 2] = __float_as_uint(h1.x); r[i * 4 + 3] = __float_as_uint(h1.y);
+    lo[i * 4 + 0] = __float_as_uint(l0.x); lo[i * 4 + 1] = __float_as_uint(l0.y);
+    lo[i * 4 + 2] = __float_as_uint(l1.x); lo[i * 4 + 3] = __float_as_uint(l1.y);
   }
   umma::st16(tA_hi, r);
   umma::st16(tA_lo, lo);
@@ -595,17 +613,8 @@ __device__ __forceinline__ void act_block16(uint32_t (&r)[16], const float* __re
 // 16 accumulator columns -> LeakyReLU(r + bias) -> hi / lo into the A slots
 __device__ __forceinline__ void act_store16(uint32_t (&r)[16], const float* __restrict__ bias, uint32_t tA_hi,
                                             uint32_t tA_lo) {
-  uint32_t lo[16];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 b = *reinterpret_cast<const float4*>(bias + i * 4);
-    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 0]) + b.x), r[i * 4 + 0], lo[i * 4 + 0]);
-    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 1]) + b.y), r[i * 4 + 1], lo[i * 4 + 1]);
-    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 2]) + b.z), r[i * 4 + 2], lo[i * 4 + 2]);
-    umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 3]) + b.w), r[i * 4 + 3], lo[i * 4 + 3]);
-  }
-  umma::st16(tA_hi, r);
-  umma::st16(tA_lo, lo);
+  float dummy = 0.f;
+  act_block16<false>(r, bias, nullptr, dummy, tA_hi, tA_lo);
 }
 
 constexpr int TC16_XCH_FLOATS = 2 * 2 * TC_ROWS * 4;   // [slot][half][row][4] exchange buffer (x2: partials, noise)
@@ -1119,13 +1128,21 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           uint32_t hi[16], lo[16];
+          const float2 xv2 = make_float2(xv, xv);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 ww = *reinterpret_cast<const float4*>(wx + h * 16 + i * 4);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.x, base[h * 16 + i * 4 + 0])), hi[i * 4 + 0], lo[i * 4 + 0]);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.y, base[h * 16 + i * 4 + 1])), hi[i * 4 + 1], lo[i * 4 + 1]);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.z, base[h * 16 + i * 4 + 2])), hi[i * 4 + 2], lo[i * 4 + 2]);
-            umma::split_tf32(leaky_mx(fmaf(xv, ww.w, base[h * 16 + i * 4 + 3])), hi[i * 4 + 3], lo[i * 4 + 3]);
+            const float2 a0 = leaky_x2(__ffma2_rn(xv2, make_float2(ww.x, ww.y),
+                                                  make_float2(base[h * 16 + i * 4 + 0], base[h * 16 + i * 4 + 1])));
+            const float2 a1 = leaky_x2(__ffma2_rn(xv2, make_float2(ww.z, ww.w),
+                                                  make_float2(base[h * 16 + i * 4 + 2], base[h * 16 + i * 4 + 3])));
+            float2 h0, l0, h1, l1;
+            umma::split_tf32_x2(a0, h0, l0);
+            umma::split_tf32_x2(a1, h1, l1);
+            hi[i * 4 + 0] = __float_as_uint(h0.x); hi[i * 4 + 1] = __float_as_uint(h0.y);
+            hi[i * 4 + 2] = __float_as_uint(h1.x); hi[i * 4 + 3] = __float_as_uint(h1.y);
+            lo[i * 4 + 0] = __float_as_uint(l0.x); lo[i * 4 + 1] = __float_as_uint(l0.y);
+            lo[i * 4 + 2] = __float_as_uint(l1.x); lo[i * 4 + 3] = __float_as_uint(l1.y);
           }
           umma::st16(trow + EF_A2_HI + c * 32 + h * 16, hi);
           umma::st16(trow + EF_A2_LO + c * 32 + h * 16, lo);
@@ -1138,19 +1155,10 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
       if (head) umma::ld16(trow + EF_D3, r3);
       if (j >= 1 && j <= n_x) {
         // layer-2 output of dose j-1, columns [16c, 16c+16) -> bias, LeakyReLU, split -> A3
-        uint32_t r[16], lo[16];
+        uint32_t r[16];
         umma::ld16(trow + EF_D2 + c * 16, r);
         umma::wait_ld();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 b = *reinterpret_cast<const float4*>(wimg + P.fb2 + c * 16 + i * 4);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 0]) + b.x), r[i * 4 + 0], lo[i * 4 + 0]);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 1]) + b.y), r[i * 4 + 1], lo[i * 4 + 1]);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 2]) + b.z), r[i * 4 + 2], lo[i * 4 + 2]);
-          umma::split_tf32(leaky_mx(__uint_as_float(r[i * 4 + 3]) + b.w), r[i * 4 + 3], lo[i * 4 + 3]);
-        }
-        umma::st16(trow + EF_A3_HI + c * 16, r);
-        umma::st16(trow + EF_A3_LO + c * 16, lo);
+        act_store16(r, wimg + P.fb2 + c * 16, trow + EF_A3_HI + c * 16, trow + EF_A3_LO + c * 16);
       } else {
         umma::wait_ld();
       }

@@ -89,6 +89,18 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// Packed variant (two values per instruction; sm_100 FMUL2 / FFMA2): Veltkamp's split with the
+// factor 2^13 + 1 -- hi = v rounded to nearest at 24 - 13 = 11 significant bits, lo = v - hi exact.
+// 4 packed FMA-pipe instructions per PAIR instead of IADD3 + LOP3 + FADD per value; the kernels
+// are bound by issue slots, not by the FMA pipe.
+__device__ __forceinline__ void split_tf32_x2(float2 v, float2& hi, float2& lo) {
+  const float2 m1 = make_float2(-1.f, -1.f);
+  const float2 c = __fmul2_rn(v, make_float2(8193.f, 8193.f));
+  const float2 t = __ffma2_rn(v, m1, c);     // c - v
+  hi = __ffma2_rn(t, m1, c);                 // c - (c - v)
+  lo = __ffma2_rn(hi, m1, v);                // v - hi
+}
+
 // ---- descriptors ----
 // shared-memory matrix descriptor (K-major, SWIZZLE_NONE, version 1): start address, LBO, SBO
 // in 16-byte units.  cute::UMMA::SmemDescriptor has the same bit layout.
