@@ -168,16 +168,14 @@ static int push_floats(std::vector<float>& img, const float* p, size_t count) {
 static bool small_net_shape(const HostNet& n) {
   return n.L == 4 && n.dims[1] == 64 && n.dims[2] == 32 && n.dims[3] == 8 && n.dims[4] == 2;
 }
-// first layer [in][64] with its rows remapped onto the input vector [z.., x] -> [zd+1][64]
+// first layer [in][64] as is (its rows in order) + the mask of the entries of the input vector
+// [z.., x] those rows multiply (rows[] is ascending)
 static int pack_first_layer(std::vector<float>& img, const HostNet& net, const std::vector<int>& rows, int zd,
                             unsigned long long& mask) {
-  std::vector<float> w((size_t)(zd + 1) * 64, 0.f);
+  (void)zd;
   mask = 0;
-  for (size_t r = 0; r < rows.size(); ++r) {
-    mask |= 1ull << rows[r];
-    for (int k = 0; k < 64; ++k) w[(size_t)rows[r] * 64 + k] = net.W[0][r * 64 + k];
-  }
-  return push_floats(img, w.data(), w.size());
+  for (size_t r = 0; r < rows.size(); ++r) mask |= 1ull << rows[r];
+  return push_floats(img, net.W[0].data(), rows.size() * 64);
 }
 
 }  // namespace bgm
@@ -235,9 +233,9 @@ static int launch_mh_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream
 }
 template <int ZMAX>
 static int launch_mh_tc_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream_t st) {
-  if (m->tc16 && ZMAX <= 16) {   // 8 warps per tile; needs the exchange buffer behind the image
+  if (m->tc16 && ZMAX <= 12) {   // 8 warps per tile (128 registers per thread: spills beyond zd = 12)
     auto k = causal_mh_tc16_kernel<ZMAX>;
-    const int smem = m->tc_smem_bytes + 2 * TC16_XCH_FLOATS * 4;
+    const int smem = m->tc_smem_bytes + (ZMAX == 8 ? 2 : 1) * TC16_XCH_FLOATS * 4;
     BGM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, 512, smem, st>>>(m->tc, m->tc_image_dev, D);
     BGM_CUDA_OK(cudaGetLastError());
@@ -261,6 +259,7 @@ static int launch_mh(const bgm_causal* m, MhDev& D, cudaStream_t st) {
     BGM_CUDA_OK(cudaMemsetAsync(D.a.sched_dev, 0, sizeof(int) * (size_t)(nt + 1), st));
     const int zd = m->prog.zd;
     if (zd <= 8) return launch_mh_tc_t<8>(m, D, grid, st);
+    if (zd <= 12) return launch_mh_tc_t<12>(m, D, grid, st);
     if (zd <= 16) return launch_mh_tc_t<16>(m, D, grid, st);
     return launch_mh_tc_t<32>(m, D, grid, st);
   }
@@ -510,7 +509,8 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   m->tc_issued = tc_issued;
   m->tc_smem_bytes = T.image_floats * 4;
   if (T.enabled && m->tc_smem_bytes + 256 > smem_max) m->tc.enabled = 0;
-  m->tc16 = m->tc.enabled && m->tc_smem_bytes + 2 * TC16_XCH_FLOATS * 4 + 128 <= smem_max && !getenv("BGM_TC8");
+  m->tc16 = m->tc.enabled && m->tc_smem_bytes + (zd <= 8 ? 2 : 1) * TC16_XCH_FLOATS * 4 + 128 <= smem_max &&
+            !getenv("BGM_TC8");
   if (e == cudaSuccess && m->tc.enabled) {
     e = cudaMalloc(&m->tc_image_dev, tc_image.size() * sizeof(float));
     if (e == cudaSuccess)
@@ -570,8 +570,9 @@ int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_a
 int bgm_causal_kernel_name(const bgm_causal* m, char* buf, int len) {
   if (!m || !buf || len < 1) return fail(BGM_ERR_ARG, "bgm_causal_kernel_name: null argument");
   const int zd = m->prog.zd;
-  const int zmax = zd <= 8 ? 8 : (zd <= 16 ? 16 : 32);
-  const char* base = !use_tc(m) ? "causal_mh_kernel" : ((m->tc16 && zmax <= 16) ? "causal_mh_tc16_kernel" : "causal_mh_tc_kernel");
+  int zmax = zd <= 8 ? 8 : (zd <= 16 ? 16 : 32);
+  if (use_tc(m) && zd > 8 && zd <= 12) zmax = 12;
+  const char* base = !use_tc(m) ? "causal_mh_kernel" : ((m->tc16 && zmax <= 12) ? "causal_mh_tc16_kernel" : "causal_mh_tc_kernel");
   snprintf(buf, (size_t)len, "%s<%d>", base, zmax);
   return 0;
 }

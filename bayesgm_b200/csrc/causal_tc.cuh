@@ -42,8 +42,8 @@ struct TcProgram {
   int gW1, gb1;                               // g first layer [zd][64], bias[64]
   int wsig, bsig;                             // sigma_v head: column v_dim of g's last layer
   // f / h: in -> 64 -> 32 -> 8 -> 2
-  int fW1, fb1, hW1, hb1;                     // first layers over the input vector [z.., x]: [zd+1][64]
-  unsigned long long fmask, hmask;            // input rows each net really uses
+  int fW1, fb1, hW1, hb1;                     // first layers: the rows of [z.., x] each net uses, in order: [popc(mask)][64]
+  unsigned long long fmask, hmask;            // which entries of the input vector [z.., x] those rows multiply
   int f2_hi, f2_lo, h2_hi, h2_lo;             // second layers, [16][32][4] images
   int fb2, hb2;
   int w3_hi, w3_lo, b3;                       // third layers of f and h as one block-diagonal
@@ -75,13 +75,16 @@ __device__ __forceinline__ void first_layer(const float* __restrict__ W, const f
     const float4 bb = *reinterpret_cast<const float4*>(b + q * 4);
     out[q * 4 + 0] = bb.x; out[q * 4 + 1] = bb.y; out[q * 4 + 2] = bb.z; out[q * 4 + 3] = bb.w;
   }
+  int wr = 0;   // packed row of W
 #pragma unroll
   for (int d = 0; d < KINMAX; ++d) {
     if (d < nin && ((mask >> d) & 1ull)) {
       const float zv = in[d];
+      const float* Wd = W + wr * 64;
+      ++wr;
 #pragma unroll
       for (int q = 0; q < 16; ++q) {
-        const float4 ww = *reinterpret_cast<const float4*>(W + d * 64 + q * 4);
+        const float4 ww = *reinterpret_cast<const float4*>(Wd + q * 4);
         out[q * 4 + 0] = fmaf(zv, ww.x, out[q * 4 + 0]);
         out[q * 4 + 1] = fmaf(zv, ww.y, out[q * 4 + 1]);
         out[q * 4 + 2] = fmaf(zv, ww.z, out[q * 4 + 2]);
@@ -546,13 +549,16 @@ __device__ __forceinline__ void first_layer32(const float* __restrict__ W, const
     o2[q * 2 + 0] = make_float2(bb.x, bb.y);
     o2[q * 2 + 1] = make_float2(bb.z, bb.w);
   }
+  int wr = 0;   // packed row of W
 #pragma unroll
   for (int d = 0; d < KINMAX; ++d) {
     if (d < nin && ((mask >> d) & 1ull)) {
       const float2 zv = make_float2(in[d], in[d]);
+      const float* Wd = W + wr * 64 + c0;
+      ++wr;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 ww = *reinterpret_cast<const float4*>(W + d * 64 + c0 + q * 4);
+        const float4 ww = *reinterpret_cast<const float4*>(Wd + q * 4);
         o2[q * 2 + 0] = __ffma2_rn(zv, make_float2(ww.x, ww.y), o2[q * 2 + 0]);
         o2[q * 2 + 1] = __ffma2_rn(zv, make_float2(ww.z, ww.w), o2[q * 2 + 1]);
       }
@@ -1086,7 +1092,8 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
   const int n = E.n, zd = P.zd, n_x = E.n_x;
   const int tiles_per_s = (n + TC_ROWS - 1) / TC_ROWS;
   const long long ntiles = (long long)tiles_per_s * E.n_keep;
-  const float* wx = wimg + P.fW1 + zd * 64 + c * 32;   // first-layer weights of the treatment input
+  // first-layer weights of the treatment input: the last packed row of f's first layer
+  const float* wx = wimg + P.fW1 + (__popcll(P.fmask) - 1) * 64 + c * 32;
   for (long long tile = (long long)blockIdx.x * 2 + slot; tile < ntiles; tile += (long long)gridDim.x * 2) {
     const int s = (int)(tile / tiles_per_s);
     const int row = (int)(tile - (long long)s * tiles_per_s) * TC_ROWS + q * 32 + lane;
@@ -1102,13 +1109,16 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
         const float4 bb = *reinterpret_cast<const float4*>(wimg + P.fb1 + c * 32 + i * 4);
         base[i * 4 + 0] = bb.x; base[i * 4 + 1] = bb.y; base[i * 4 + 2] = bb.z; base[i * 4 + 3] = bb.w;
       }
+      int wr = 0;
 #pragma unroll
       for (int d = 0; d < ZMAX; ++d) {
         if (d < zd && ((P.fmask >> d) & 1ull)) {
           const float zv = zs[d];
+          const float* Wd = wimg + P.fW1 + wr * 64 + c * 32;
+          ++wr;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 ww = *reinterpret_cast<const float4*>(wimg + P.fW1 + d * 64 + c * 32 + i * 4);
+            const float4 ww = *reinterpret_cast<const float4*>(Wd + i * 4);
             base[i * 4 + 0] = fmaf(zv, ww.x, base[i * 4 + 0]);
             base[i * 4 + 1] = fmaf(zv, ww.y, base[i * 4 + 1]);
             base[i * 4 + 2] = fmaf(zv, ww.z, base[i * 4 + 2]);
