@@ -655,16 +655,19 @@ class BGM(object):
         self._apply(0, group)
         return tuple(float(a) for a in losses.cpu().numpy())
 
-    def egm_init(self, data, egm_n_iter=10000, batch_size=32, egm_batches_per_eval=500, verbose=1, *, group=None):
+    def egm_init(self, data, egm_n_iter=10000, batch_size=32, egm_batches_per_eval=500, verbose=1, *, group=None,
+                 eval_during=True):
         """bgm/base.py:294-340: mini-batches from `Base_sampler` (its shuffled index stream is
-        NumPy's legacy generator, bit-exact), prior draws from `z_sampler.get_batch`.  The
-        periodic generate()/evaluate()/np.savez of :317-339 is not run."""
+        NumPy's legacy generator, bit-exact), prior draws from `z_sampler.get_batch`.  Every
+        `egm_batches_per_eval` iterations evaluate() (and, with save_res, generate()/np.savez) runs
+        like :317-339 (`eval_during=False` skips it); history in `self.egm_history`."""
         torch = _lib.require_cuda()
         data = np.asarray(data, dtype=np.float32)
         self.data_sampler = Base_sampler(x=data, y=data, v=data, batch_size=batch_size, normalize=False)   # :295
         dloss = torch.zeros(3, dtype=torch.float32, device='cuda')
         gloss = torch.zeros(6, dtype=torch.float32, device='cuda')
         rs = self._noise_rng
+        self.egm_history = []
         if verbose:
             print('EGM Initialization Starts ...')
         for it in range(int(egm_n_iter) + 1):
@@ -682,11 +685,25 @@ class BGM(object):
             n2 = self._dev(rs.standard_normal(bx.shape).astype(np.float32), torch, torch.float32)
             self._gen_call(z, x, n1, n2, gloss)
             self._apply(0, group)
-            if verbose and it % egm_batches_per_eval == 0:
-                d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
-                print('EGM Initialization Iter [%d] : g_loss_adv[%.4f], e_loss_adv [%.4f], l2_loss_z [%.4f], '
-                      'l2_loss_x [%.4f], sd^2_loss[%.4f], g_e_loss [%.4f], dz_loss [%.4f], dx_loss[%.4f], d_loss [%.4f]'
-                      % (it, g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1], d[2]))
+            if it % egm_batches_per_eval == 0:                                             # :310-337
+                if verbose:
+                    d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
+                    print('EGM Initialization Iter [%d] : g_loss_adv[%.4f], e_loss_adv [%.4f], l2_loss_z [%.4f], '
+                          'l2_loss_x [%.4f], sd^2_loss[%.4f], g_e_loss [%.4f], dz_loss [%.4f], dx_loss[%.4f], d_loss [%.4f]'
+                          % (it, g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1], d[2]))
+                if eval_during:
+                    self._trainer_dirty = True
+                    mse_sd = self.evaluate(data=data, use_x_sd=True)
+                    mse = self.evaluate(data=data, use_x_sd=False)
+                    self.egm_history.append((it, mse_sd, mse))
+                    if verbose:
+                        print('iter [%d/%d]: MSE_x: %.4f\n' % (it, egm_n_iter, mse_sd))
+                        print('iter [%d/%d]: MSE_x no x_sd: %.4f\n' % (it, egm_n_iter, mse))
+                    if self._p['save_res']:
+                        gen1, var1 = self.generate(nb_samples=5000)
+                        gen12, var12 = self.generate(nb_samples=5000, use_x_sd=False)
+                        np.savez('%s/init_data_gen_at_%d.npz' % (self.save_dir, it), gen1=gen1, gen12=gen12,
+                                 z=self._encode_host(data), var1=var1, var12=var12)
         if verbose:
             print('EGM Initialization Ends.')
         return tuple(float(a) for a in dloss.cpu().numpy()), tuple(float(a) for a in gloss.cpu().numpy())

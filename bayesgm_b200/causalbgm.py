@@ -660,13 +660,14 @@ class CausalBGM(object):
         return tuple(float(a) for a in losses.cpu().numpy())
 
     def egm_init(self, data, egm_n_iter=30000, batch_size=32, egm_batches_per_eval=500, verbose=1, *,
-                 group=None, chunk=64):
+                 group=None, chunk=64, eval_during=True):
         """causalbgm/base.py:380-431.  The data set stays on the device; mini-batch indices
         and prior draws come from NumPy's global generator in the reference's exact call
         order (g_d_freq x [choice, get_batch], then [get_batch, choice]) -- bit-exact index
         streams -- generated `chunk` iterations ahead and uploaded in one copy; the batches
         are gathered on the device.  Returns the last (dz_loss, d_loss) and generator losses.
-        The periodic evaluate()/save_data of :418-430 is not run."""
+        Every `egm_batches_per_eval` iterations the model is evaluated like :425-430 (`eval_during=False`
+        skips it); the (iteration, mse_x, mse_y, mse_v) history is kept in `self.egm_history`."""
         torch = _lib.require_cuda()
         data_x, data_y, data_v = data
         n = len(data_x)
@@ -686,6 +687,7 @@ class CausalBGM(object):
         by = torch.empty(bs, dtype=torch.float32, device='cuda')
         if verbose:
             print('EGM Initialization Starts ...')
+        self.egm_history = []
         total = int(egm_n_iter) + 1
         it = 0
         while it < total:
@@ -716,11 +718,18 @@ class CausalBGM(object):
                 _lib.call("bgm_train_gen_grad", tr, C.c_void_p(zz_d[c, freq].data_ptr()), _lib.ptr(bv), _lib.ptr(bx),
                           _lib.ptr(by), bs, _lib.ptr(gloss), st)
                 self._apply(0, group)
-                if verbose and (it + c) % egm_batches_per_eval == 0:
-                    d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
-                    print('EGM Initialization Iter [%d] : e_loss_adv [%.4f], l2_loss_v [%.4f], l2_loss_z [%.4f], '
-                          'l2_loss_x [%.4f], l2_loss_y [%.4f], g_e_loss [%.4f], dz_loss [%.4f], d_loss [%.4f]'
-                          % (it + c, g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1]))
+                if (it + c) % egm_batches_per_eval == 0:                                     # :418-430
+                    if verbose:
+                        d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
+                        print('EGM Initialization Iter [%d] : e_loss_adv [%.4f], l2_loss_v [%.4f], l2_loss_z [%.4f], '
+                              'l2_loss_x [%.4f], l2_loss_y [%.4f], g_e_loss [%.4f], dz_loss [%.4f], d_loss [%.4f]'
+                              % (it + c, g[0], g[1], g[2], g[3], g[4], g[5], d[0], d[1]))
+                    if eval_during:
+                        self._trainer_dirty = True
+                        causal_pre, mse_x, mse_y, mse_v = self.evaluate(data=(xd, yd, vd))
+                        self.egm_history.append((it + c, float(mse_x), float(mse_y), float(mse_v)))
+                        if self._p['save_res']:
+                            self._save_data('{}/causal_pre_egm_init_iter-{}.txt'.format(self.save_dir, it + c), causal_pre)
             it += cnt
         if verbose:
             print('EGM Initialization Ends.')
