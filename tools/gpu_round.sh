@@ -13,6 +13,8 @@ timeout 600 python bench.py --engine simt > $OUT/${TAG}_bench_1gpu_simt.json 2> 
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $OUT/${TAG}_bench_reference_arm.json 2> $OUT/${TAG}_bench_ref.err
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 > $OUT/${TAG}_ncu_launch.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"causal_(mh|effect)" -s 1 -c 4 \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"causal_mh" -s 2 -c 1 \
     -o $OUT/${TAG}_mh_prof -f python bench.py --steps 1 --warmup 1 > $OUT/${TAG}_ncu_full.log 2>&1
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"causal_effect" -c 1 \
+    -o $OUT/${TAG}_effect_prof -f python bench.py --steps 1 --warmup 1 > $OUT/${TAG}_ncu_full_effect.log 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.log; cat $OUT/${TAG}_smoke.log | tail -2; cat $OUT/${TAG}_bench_1gpu.json
