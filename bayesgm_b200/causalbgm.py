@@ -404,8 +404,8 @@ class CausalBGM(object):
                 bs=10000, *, seed=None, group=None, row_offset=0, verbose=1):
         """causalbgm/base.py:573-668 -> (effect, posterior interval).
 
-        The kept states never leave the device: each `bs` slice is sampled and reduced
-        to ITE draws / ADRF partial sums on the GPU.  Under torch.distributed pass
+        The kept states never leave the device: the `bs` slices are sampled (several per
+        launch when q_sd is fixed) and reduced to ITE draws / ADRF partial sums on the GPU.  Under torch.distributed pass
         `group` (and this rank's global `row_offset`): every rank processes its own
         shard of rows and the ADRF sums are all-reduced once at the end (no collective
         inside the sampling loop).
@@ -434,8 +434,18 @@ class CausalBGM(object):
         else:
             sums = torch.zeros((len(x_values), n_mcmc), dtype=torch.float64, device='cuda')
             n_seen = 0
-        for start in range(0, n_test, bs):
-            end = min(start + bs, n_test)
+        # The reference runs one independent MH per `bs` slice (:630, :650).  With a fixed q_sd the
+        # chains of different slices do not interact and the Philox noise is keyed by the global
+        # row, so several slices are sampled in ONE launch (identical results, a full grid instead
+        # of ceil(bs/128) row tiles); with the adaptive rule the acceptance window is per slice.
+        step_rows = bs
+        if not adaptive:
+            zd_ = sum(self._p['z_dims'])
+            per_row = 4.0 * int(n_mcmc) * (zd_ + 2)                 # kept states + effect draws
+            budget = min(16e9, 0.3 * torch.cuda.mem_get_info()[0])
+            step_rows = max(bs, int(budget // per_row) // bs * bs)
+        for start in range(0, n_test, step_rows):
+            end = min(start + step_rows, n_test)
             _, x, y, v, ldv, n = self._stage((data_x[start:end], data_y[start:end], data_v[start:end]))
             r = self._mh_device(x, y, v, ldv, n, int(burn_in), int(n_mcmc), q_sd, adaptive, 1.0, 0.25, 0.05,
                                 50, 100, seed, row_offset + start)
