@@ -140,16 +140,18 @@ def test_mh_philox_run_replayed_through_oracle(engine):
     assert abs(nz['u'].mean() - 0.5) < 0.02 and nz['u'].min() >= 0 and nz['u'].max() < 1
 
 
-def test_mh_adaptive_q_sd_matches_oracle():
-    params = causal_params(20, [1, 1, 1, 2])
+@pytest.mark.parametrize("v_dim,n,engine", [(20, 64, 'simt'), (200, 200, 'tensor'), (200, 200, 'simt')])
+def test_mh_adaptive_q_sd_matches_oracle(v_dim, n, engine):
+    """Adaptive proposal scale (:880-890): one launch per 50-iteration stretch with the chain state
+    handed over through z_state / lp_state, the rule evaluated on the device in between."""
+    params = causal_params(v_dim, [1, 1, 1, 2])
     nets = causal_nets(params)
-    n = 64
-    data = causal_data(n, 20)
+    data = causal_data(n, v_dim)
     burn_in, n_keep = 230, 10
     nz = injected_noise(n, 5, burn_in + n_keep)
     so, tro = causal.mh_sampler(params, nets, data, q_sd=None, initial_q_sd=3.0, burn_in=burn_in,
                                 n_keep=n_keep, noise=causal.InjectedNoise(**nz), return_trace=True)
-    m = product_model(params, nets)
+    m = product_model(params, nets, engine)
     sg, trg = m.metropolis_hastings_sampler(data, q_sd=None, initial_q_sd=3.0, burn_in=burn_in,
                                             n_keep=n_keep, noise=nz, return_trace=True, verbose=0)
     assert len(set(tro['q_sd'])) >= 3                       # the rule fired
