@@ -39,7 +39,9 @@ CASES = [
 
 # every case on the fp32 FMA-pipe engine; the standard net shapes (CASES[:4]) also on the
 # tensor-core engine (3xTF32) -- same tolerances for both
-ENGINE_CASES = [c + ('simt',) for c in CASES] + [c + ('tensor',) for c in CASES[:4]]
+ENGINE_CASES = ([c + ('simt',) for c in CASES] + [c + ('tensor',) for c in CASES[:4]] +
+                [(1, 200, [1, 1, 1, 2], False, {}, 'tensor'), (129, 200, [2, 3, 2, 5], False, {}, 'tensor'),
+                 (257, 100, [4, 4, 4, 4], True, dict(g_units=[64, 64]), 'tensor')])   # single row; zd=12; zd=16, 2-layer g
 
 
 @pytest.mark.parametrize("n,v_dim,z_dims,binary,extra,engine", ENGINE_CASES)
