@@ -125,6 +125,19 @@ class BGM(object):
                     dz=[a.copy() for a in self.dz_net.trainable_list()],
                     dx=[a.copy() for a in self.dx_net.trainable_list()])
 
+    def save_weights(self, path):
+        """All network weights (Keras-layout arrays) into one .npz -- stands in for the reference's
+        `*.weights.h5` files (:335-338, :433-436); `load_weights` restores them."""
+        w = self.get_weights()
+        np.savez(path, **{"%s_%d" % (k, i): a for k, arrs in w.items() for i, a in enumerate(arrs)})
+
+    def load_weights(self, path):
+        z = np.load(path)
+        got = {}
+        for k in ('g', 'e', 'dz', 'dx'):
+            got[k] = [z["%s_%d" % (k, i)] for i in range(sum(1 for name in z.files if name.startswith(k + "_")))]
+        self.set_weights(**got)
+
     def _drop_trainer(self):
         if self._trainer is not None:
             _lib.load().bgm_trainer_destroy(self._trainer)
@@ -554,6 +567,8 @@ class BGM(object):
                 self.history_loss.append(mse_x)
                 if verbose:
                     print('Epoch [%d/%d]: MSE_x: %.4f\n' % (epoch, epochs, mse_x))
+                if self._p['save_model']:                                                     # :433-436
+                    self.save_weights(self.checkpoint_path + "/weights_at_%d.npz" % epoch)
                 if self._p['save_res']:
                     gen1, var1 = self.generate(nb_samples=5000)
                     gen12, var12 = self.generate(nb_samples=5000, use_x_sd=False)
@@ -704,6 +719,8 @@ class BGM(object):
                         gen12, var12 = self.generate(nb_samples=5000, use_x_sd=False)
                         np.savez('%s/init_data_gen_at_%d.npz' % (self.save_dir, it), gen1=gen1, gen12=gen12,
                                  z=self._encode_host(data), var1=var1, var12=var12)
+                    if self._p['save_model']:                                                 # :334-338
+                        self.save_weights(self.checkpoint_path + "/weights_at_egm_init_%d.npz" % it)
         if verbose:
             print('EGM Initialization Ends.')
         return tuple(float(a) for a in dloss.cpu().numpy()), tuple(float(a) for a in gloss.cpu().numpy())

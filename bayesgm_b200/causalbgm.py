@@ -591,6 +591,8 @@ class CausalBGM(object):
                     best_loss = mse_y
                     self.best_causal_pre = causal_pre
                     self.best_epoch = epoch
+                    if self._p['save_model']:                                                # :527-530
+                        self.save_weights('{}/weights_at_{}.npz'.format(self.checkpoint_path, epoch))
                 if self._p['save_res']:
                     self._save_data('{}/causal_pre_at_{}.{}'.format(self.save_dir, epoch, save_format), causal_pre)
         self.last_iter_losses = tuple(float(a) for a in nl.cpu().numpy()) + (float(zl.cpu()[0]),)
@@ -638,6 +640,19 @@ class CausalBGM(object):
         self._sync_from_trainer()
         return dict(g=self.g_net.get_weights(), e=self.e_net.get_weights(), f=self.f_net.get_weights(),
                     h=self.h_net.get_weights(), dz=[a.copy() for a in self.dz_net.trainable_list()])
+
+    def save_weights(self, path):
+        """All network weights (Keras-layout arrays) into one .npz -- the counterpart of the
+        reference's tf.train.Checkpoint (:100-113, :527-530); `load_weights` restores them."""
+        w = self.get_weights()
+        np.savez(path, **{"%s_%d" % (k, i): a for k, arrs in w.items() for i, a in enumerate(arrs)})
+
+    def load_weights(self, path):
+        z = np.load(path)
+        got = {}
+        for k in ('g', 'e', 'f', 'h', 'dz'):
+            got[k] = [z["%s_%d" % (k, i)] for i in range(sum(1 for name in z.files if name.startswith(k + "_")))]
+        self.set_weights(**got)
 
     def train_disc_step(self, data_z, data_v, *, epsilon=None, group=None):
         """causalbgm/base.py:305-330 -> (dz_loss, d_loss).  `epsilon` is the U(0,1) draw of

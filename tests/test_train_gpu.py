@@ -384,3 +384,40 @@ def test_bgm_fit_end_to_end_tracks_the_oracle_loop():
     assert abs(m.evaluate(data, m.data_z, use_x_sd=False) - ot.mse(data)) < 1e-3 * max(1.0, ot.mse(data))
     # use_x_sd=True adds sigma^2 on average
     assert m.evaluate(data, m.data_z, use_x_sd=True) > m.evaluate(data, m.data_z, use_x_sd=False)
+
+
+def test_save_model_and_save_res_paths(tmp_path):
+    """save_model / save_res of the params dict: weights and results are written where the reference
+    writes its checkpoints / result files, and load_weights restores a model that predicts identically."""
+    import os
+    # BGM
+    params = bgm_params(8, 2, lr=1e-3, lr_theta=1e-3, lr_z=1e-3, output_dir=str(tmp_path), save_model=True, save_res=True,
+                        dataset='bgm_case')       # the timestamped directories have 1 s resolution: keep the two models apart
+    g = bgm_oracle_net(params, seed=31)
+    m = bgm_product_model(params, g)
+    data = np.random.RandomState(3).standard_normal((64, 8)).astype(np.float32)
+    np.random.seed(2)
+    m.fit(data, batch_size=16, epochs=1, epochs_per_eval=1, use_egm_init=True, egm_n_iter=2, egm_batches_per_eval=2,
+          verbose=0)
+    assert os.path.exists(m.checkpoint_path + "/weights_at_1.npz")
+    assert os.path.exists(m.checkpoint_path + "/weights_at_egm_init_2.npz")
+    assert os.path.exists(m.save_dir + "/data_gen_at_1.npz") and os.path.exists(m.save_dir + "/params.txt")
+    m2 = bgm_product_model(params, bgm_oracle_net(params, seed=99))
+    m2.load_weights(m.checkpoint_path + "/weights_at_1.npz")
+    z = np.random.RandomState(1).standard_normal((1, 10, 2)).astype(np.float32)
+    zero = np.zeros((1, 10, 8), np.float32)
+    np.testing.assert_array_equal(m.predict_on_posteriors(z, noise=zero), m2.predict_on_posteriors(z, noise=zero))
+    # CausalBGM
+    cp = causal_params(12, [1, 1, 1, 1], output_dir=str(tmp_path), save_model=True, save_res=True, dataset='causal_case')
+    cm = product_model(cp, causal_nets(cp))
+    cdata = causal_data(48, 12)
+    np.random.seed(3)
+    cm.fit(cdata, epochs=1, epochs_per_eval=1, batch_size=16, use_egm_init=True, egm_n_iter=2, egm_batches_per_eval=2,
+           verbose=0)
+    saved = [f for f in os.listdir(cm.checkpoint_path) if f.startswith("weights_at_")]
+    assert saved and os.path.exists(cm.save_dir + "/causal_pre_egm_init_iter-2.txt")
+    cm2 = product_model(cp, causal_nets(cp, seed=5))
+    cm2.load_weights(os.path.join(cm.checkpoint_path, saved[0]))
+    zz = np.random.RandomState(2).standard_normal((48, 4)).astype(np.float32)
+    if saved[0] == "weights_at_%d.npz" % cm.best_epoch and cm.best_epoch == 1:
+        np.testing.assert_array_equal(cm.get_log_posterior(*cdata, zz), cm2.get_log_posterior(*cdata, zz))
