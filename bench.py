@@ -297,7 +297,13 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get("causal_mh_tc_kernel_dram_bytes_per_launch" if tensor
                                                  else "causal_mh_kernel_dram_bytes_per_launch")
         cpu_iters = 10
-        cpu_rate, cpu_dt = cpu_reference_rate(cpu_iters, data=(x, y, v))
+        if world == 1:
+            cpu_rate, cpu_dt = cpu_reference_rate(cpu_iters, data=(x, y, v))
+            cpu_baseline = {"value": cpu_rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": "%d MH iterations over all n=%d rows, NumPy BLAS (%.1f s)" % (cpu_iters, n, cpu_dt)}
+        else:   # the CPU baseline is timed at N=1 only
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                            "sample": "not timed at N>1 (see the N=1 line)"}
         if tensor:
             # wide layers on the tensor pipe as 3xTF32: three TF32 MMAs per fp32-accurate product.
             # MEASURED_PEAKS.json holds the dense bf16 peak only; kind::tf32 runs at half that rate.
@@ -338,7 +344,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(4 * len(X_VALUES) * N_MCMC),
                     "api": "CausalBGM.predict(x_values=linspace(0,3,20), sample_y=True, bs=n)",
                     "ms_per_step": 1e3 * e2e_wall / args.steps, "remeasured_after_disturbed_pass": e2e_first},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,
+            "launches_per_step": ["causal_project_kernel", kname],
             "kernel": {"name": kname, "engine": sinfo['engine'], "ms_per_launch": kern_ms_mean,
                        "ms_per_launch_min_max": [float(min(kern_ms)), float(max(kern_ms))], "warmup_steps_run": warm_run,
                        "remeasured_after_disturbed_pass": first_attempt,
@@ -349,9 +356,7 @@ def run_ours(args):
                              "frac": bytes_per_launch / (kern_ms_mean * 1e-3) / 1e9 / peaks["hbm_gbs"],
                              "peak_source": peak_src,
                              "note": "north_star asks for the HBM fraction; the kernel is not HBM-bound (SURVEY F7)"},
-            "cpu_baseline": {"value": cpu_rate, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                             "sample": "%d MH iterations over all n=%d rows, NumPy BLAS (%.1f s)"
-                                       % (cpu_iters, n, cpu_dt)},
+            "cpu_baseline": cpu_baseline,
             "clocks": clk,
         }
         emit(out)
