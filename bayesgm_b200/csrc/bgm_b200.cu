@@ -261,6 +261,7 @@ static int launch_mh(const bgm_causal* m, MhDev& D, cudaStream_t st) {
     if (zd <= 8) return launch_mh_tc_t<8>(m, D, grid, st);
     if (zd <= 12) return launch_mh_tc_t<12>(m, D, grid, st);
     if (zd <= 16) return launch_mh_tc_t<16>(m, D, grid, st);
+    if (zd <= 20) return launch_mh_tc_t<20>(m, D, grid, st);
     return launch_mh_tc_t<32>(m, D, grid, st);
   }
   const int ntiles = (D.a.n + TILE_ROWS - 1) / TILE_ROWS;
@@ -572,6 +573,7 @@ int bgm_causal_kernel_name(const bgm_causal* m, char* buf, int len) {
   const int zd = m->prog.zd;
   int zmax = zd <= 8 ? 8 : (zd <= 16 ? 16 : 32);
   if (use_tc(m) && zd > 8 && zd <= 12) zmax = 12;
+  if (use_tc(m) && zd > 16 && zd <= 20) zmax = 20;
   const char* base = !use_tc(m) ? "causal_mh_kernel" : ((m->tc16 && zmax <= 12) ? "causal_mh_tc16_kernel" : "causal_mh_tc_kernel");
   snprintf(buf, (size_t)len, "%s<%d>", base, zmax);
   return 0;

@@ -354,8 +354,6 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
         }
         __syncwarp();
       }
-      float g1[64];   // g_net layer 1 while h's MMAs run
-      first_layer<KINMAX>(wimg + P.gW1, wimg + P.gb1, ~0ull, zd, in, g1);
       stage_wait();
       {
         uint32_t r[32];
@@ -374,6 +372,8 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
         }
         __syncwarp();
       }
+      float g1[64];   // g_net layer 1 while the layer-3 MMAs run
+      first_layer<KINMAX>(wimg + P.gW1, wimg + P.gb1, ~0ull, zd, in, g1);
       stage_wait();
       float loss_py, loss_px;
       {
