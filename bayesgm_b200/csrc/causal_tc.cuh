@@ -57,6 +57,28 @@ __device__ __forceinline__ void wg_sync(int wg) {
   if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
   else asm volatile("bar.sync 2, 128;" ::: "memory");
 }
+// Publishing a stage: only the warp that issues the MMAs has to WAIT for the other warps' TMEM
+// writes; the others only announce theirs (bar.arrive) and go on to whatever does not depend on
+// the MMAs.  A warp cannot run a whole stage ahead: its next step waits on the MMA mbarrier, which
+// completes only after the issuer has passed this barrier.
+__device__ __forceinline__ void wg_publish(int wg, bool issuer_warp) {
+  if (issuer_warp) {
+    if (wg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+  } else {
+    if (wg == 0) asm volatile("bar.arrive 1, 128;" ::: "memory");
+    else asm volatile("bar.arrive 2, 128;" ::: "memory");
+  }
+}
+__device__ __forceinline__ void tile_publish256(int slot, bool issuer_warp) {
+  if (issuer_warp) {
+    if (slot == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+    else asm volatile("bar.sync 2, 256;" ::: "memory");
+  } else {
+    if (slot == 0) asm volatile("bar.arrive 1, 256;" ::: "memory");
+    else asm volatile("bar.arrive 2, 256;" ::: "memory");
+  }
+}
 __device__ __forceinline__ float leaky_mx(float v) { return fmaxf(v, 0.2f * v); }  // == leaky(v)
 __device__ __forceinline__ float2 leaky_x2(float2 v) {
   const float2 m = __fmul2_rn(v, make_float2(0.2f, 0.2f));
@@ -165,7 +187,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int wg = warp >> 2, wtid = tid & 127;
-  const bool issuer_warp = (warp & 3) == 0;
+  const bool issuer_warp = (warp & 3) == 3;   // highest warp id of the group: the arbiter favours it
   if (tid == 0) {
     umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
     umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
@@ -198,7 +220,7 @@ causal_mh_tc_kernel(const __grid_constant__ TcProgram P, const float* __restrict
   auto publish = [&]() {
     umma::wait_st();
     umma::fence_before_sync();
-    wg_sync(wg);
+    wg_publish(wg, issuer_warp);
   };
   auto stage_wait = [&]() {
     umma::mbar_wait(bar, parity);
@@ -646,7 +668,7 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
   const int slot = warp >> 3;          // which of the CTA's two tiles
   const int q = warp & 3;              // TMEM lane quarter
   const int c = (warp >> 2) & 1;       // column half
-  const bool issuer_warp = (warp & 7) == 0;
+  const bool issuer_warp = (warp & 7) == 7;   // highest warp id of the tile: the arbiter favours it
   const bool leader = issuer_warp && lane == 0;
   const int r_in_tile = q * 32 + lane;
   if (tid == 0) {
@@ -689,7 +711,7 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
   auto publish = [&]() {
     umma::wait_st();
     umma::fence_before_sync();
-    tile_sync256(slot);
+    tile_publish256(slot, issuer_warp);
   };
   auto stage_wait = [&]() {
     umma::mbar_wait(bar, parity);
@@ -1073,7 +1095,7 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
   const int slot = warp >> 3;          // which of the CTA's two tiles
   const int q = warp & 3;              // TMEM lane quarter
   const int c = (warp >> 2) & 1;       // column half / dose parity
-  const bool issuer_warp = (warp & 7) == 0;
+  const bool issuer_warp = (warp & 7) == 7;   // highest warp id of the tile: the arbiter favours it
   if (tid == 0) {
     umma::mbar_init(umma::smem_addr(&bar_mma[0]), 1);
     umma::mbar_init(umma::smem_addr(&bar_mma[1]), 1);
@@ -1175,7 +1197,7 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
       if (j <= n_x) {
         umma::wait_st();
         umma::fence_before_sync();
-        tile_sync256(slot);
+        tile_publish256(slot, issuer_warp);
         if (issuer_warp) {
           if (umma::elect_one()) {
             umma::fence_after_sync();
