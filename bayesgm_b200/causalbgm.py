@@ -366,23 +366,47 @@ class CausalBGM(object):
             return samples, tr
         return samples
 
-    def _effect_device(self, z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=None):
+    def _effect_device(self, z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=None, memoise=True):
+        """ITE draws (n_keep, n) or ADRF partial sums (n_x, n_keep) on the device.  memoise: evaluate
+        f_net once per DISTINCT kept state of a row (a rejected proposal repeats the state) and
+        combine -- identical results, ~acceptance-rate of the f_net work (bgm_causal_effect_index /
+        _compact / _heads / _combine); falls back to the direct kernel for a single kept state."""
         torch = _lib.require_cuda()
         m = self._device_model()
-        if self._p['binary_treatment']:
-            ite = torch.empty((n_keep, n), dtype=torch.float32, device='cuda')
-            nz = self._to_device(noise, torch) if noise is not None else None
-            _lib.call("bgm_causal_effect", m, _lib.ptr(z_samples), n_keep, n, None, 2, int(bool(sample_y)),
-                      int(seed) & (2 ** 64 - 1), int(row_offset), _lib.ptr(nz), None, _lib.ptr(ite),
-                      _lib.stream_ptr())
-            return ite
-        xv = torch.tensor(np.asarray(x_values, dtype=np.float32), device='cuda')
-        sums = torch.zeros((len(x_values), n_keep), dtype=torch.float64, device='cuda')
+        st = _lib.stream_ptr()
+        binary = bool(self._p['binary_treatment'])
         nz = self._to_device(noise, torch) if noise is not None else None
-        _lib.call("bgm_causal_effect", m, _lib.ptr(z_samples), n_keep, n, _lib.ptr(xv), len(x_values),
-                  int(bool(sample_y)), int(seed) & (2 ** 64 - 1), int(row_offset), _lib.ptr(nz),
-                  _lib.ptr(sums), None, _lib.stream_ptr())
-        return sums
+        seed = int(seed) & (2 ** 64 - 1)
+        if binary:
+            out = torch.empty((n_keep, n), dtype=torch.float32, device='cuda')
+            xv, n_x = None, 2
+        else:
+            xv = torch.tensor(np.asarray(x_values, dtype=np.float32), device='cuda')
+            n_x = len(x_values)
+            out = torch.zeros((n_x, n_keep), dtype=torch.float64, device='cuda')
+        total = n_keep * n
+        if not memoise or n_keep < 2 or total >= 2 ** 31:
+            _lib.call("bgm_causal_effect", m, _lib.ptr(z_samples), n_keep, n, _lib.ptr(xv), n_x, int(bool(sample_y)),
+                      seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
+                      _lib.ptr(out) if binary else None, st)
+            return out
+        zd = sum(self._p['z_dims'])
+        first = torch.empty(total, dtype=torch.int32, device='cuda')
+        pos = torch.empty(total, dtype=torch.int32, device='cuda')
+        scratch = torch.empty((total + 2047) // 2048, dtype=torch.int32, device='cuda')
+        _lib.call("bgm_causal_effect_index", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(first), _lib.ptr(pos),
+                  _lib.ptr(scratch), st)
+        n_distinct = int(pos[-1].item())                      # the one host sync of the memoised path
+        zlist = torch.empty((n_distinct, zd), dtype=torch.float32, device='cuda')
+        _lib.call("bgm_causal_effect_compact", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(first), _lib.ptr(pos),
+                  _lib.ptr(zlist), st)
+        heads = torch.empty((n_distinct, n_x, 2), dtype=torch.float32, device='cuda')
+        _lib.call("bgm_causal_effect_heads", m, _lib.ptr(zlist), n_distinct, _lib.ptr(xv), n_x, _lib.ptr(heads), st)
+        _lib.call("bgm_causal_effect_combine", m, _lib.ptr(heads), _lib.ptr(pos), n_keep, n, n_x, int(bool(sample_y)),
+                  seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
+                  _lib.ptr(out) if binary else None, st)
+        self.last_distinct_fraction = n_distinct / float(total)
+        return out
 
     def infer_from_latent_posterior(self, data_posterior_z, x_values=None, sample_y=True, eps=1e-6, *,
                                     seed=None, noise=None):

@@ -657,20 +657,87 @@ int bgm_mh_noise(uint64_t seed, int64_t row_offset, int n, int zd, int t_begin, 
   return 0;
 }
 
+// ---- memoised effect evaluation (causal.cuh) ----
+int bgm_causal_effect_index(const float* z_samples_dev, int n_keep, int n, int zd, int* first_dev, int* pos_dev,
+                            int* scratch_dev, void* stream) {
+  if (!z_samples_dev || !first_dev || !pos_dev || !scratch_dev || n_keep < 1 || n < 1 || zd < 1)
+    return fail(BGM_ERR_ARG, "bgm_causal_effect_index: bad argument");
+  const long long total = (long long)n_keep * n;
+  if (total > 0x7fffffffLL) return fail(BGM_ERR_UNSUPPORTED, "bgm_causal_effect_index: n_keep * n must be < 2^31");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  effect_distinct_kernel<<<grid, 256, 0, st>>>(z_samples_dev, n_keep, n, zd, first_dev);
+  const int nblocks = (int)((total + SCAN_TILE - 1) / SCAN_TILE);
+  scan_block_kernel<<<nblocks, 256, 0, st>>>(first_dev, pos_dev, total, scratch_dev);
+  scan_totals_kernel<<<1, 1024, 0, st>>>(scratch_dev, nblocks);
+  scan_add_kernel<<<nblocks, 256, 0, st>>>(pos_dev, total, scratch_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_causal_effect_compact(const float* z_samples_dev, int n_keep, int n, int zd, const int* first_dev,
+                              const int* pos_dev, float* zlist_dev, void* stream) {
+  if (!z_samples_dev || !first_dev || !pos_dev || !zlist_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect_compact: null pointer");
+  const long long total = (long long)n_keep * n;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
+  effect_compact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z_samples_dev, n_keep, n, zd, first_dev, pos_dev,
+                                                                zlist_dev);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const int* pos_dev, int n_keep, int n,
+                              int n_x, int sample_y, uint64_t seed, int64_t row_offset, const float* noise_dev,
+                              double* adrf_sum_dev, float* ite_dev, void* stream) {
+  if (!m || !heads_dev || !pos_dev || n_keep < 1 || n < 1) return fail(BGM_ERR_ARG, "bgm_causal_effect_combine: bad argument");
+  CombineDev C;
+  memset(&C, 0, sizeof(C));
+  C.heads = heads_dev; C.pos = pos_dev; C.n_keep = n_keep; C.n = n;
+  C.binary = m->prog.binary; C.n_x = C.binary ? 2 : n_x;
+  if (C.binary ? !ite_dev : (!adrf_sum_dev || n_x < 1))
+    return fail(BGM_ERR_ARG, "bgm_causal_effect_combine: binary needs ite_dev, continuous adrf_sum_dev and n_x >= 1");
+  C.sample_y = sample_y ? 1 : 0; C.s2y = m->prog.s2y; C.seed = seed; C.row_offset = row_offset; C.noise = noise_dev;
+  C.adrf_sum = adrf_sum_dev; C.ite = ite_dev;
+  const long long ntiles = (long long)((n + 31) / 32) * n_keep;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 7) / 8, (long long)m->sm_count * 16));
+  effect_combine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int effect_launch(const bgm_causal* m, const float* z_samples_dev, int n_keep, int n,
+                         const float* x_values_dev, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
+                         const float* noise_dev, double* adrf_sum_dev, float* ite_dev, float* heads_dev, void* stream);
+
 int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_keep, int n,
                       const float* x_values_dev, int n_x, int sample_y, uint64_t seed,
                       int64_t row_offset, const float* noise_dev, double* adrf_sum_dev, float* ite_dev,
                       void* stream) {
+  return effect_launch(m, z_samples_dev, n_keep, n, x_values_dev, n_x, sample_y, seed, row_offset, noise_dev,
+                       adrf_sum_dev, ite_dev, nullptr, stream);
+}
+
+int bgm_causal_effect_heads(const bgm_causal* m, const float* states_dev, int n_states, const float* x_values_dev,
+                            int n_x, float* heads_dev, void* stream) {
+  if (!heads_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect_heads: null output");
+  return effect_launch(m, states_dev, 1, n_states, x_values_dev, n_x, 0, 0, 0, nullptr, nullptr, nullptr, heads_dev,
+                       stream);
+}
+
+static int effect_launch(const bgm_causal* m, const float* z_samples_dev, int n_keep, int n,
+                         const float* x_values_dev, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
+                         const float* noise_dev, double* adrf_sum_dev, float* ite_dev, float* heads_dev, void* stream) {
   if (!m || !z_samples_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect: null model / samples");
   if (n_keep < 1 || n < 1) return fail(BGM_ERR_ARG, "bgm_causal_effect: n_keep and n must be >= 1");
   EffectDev E;
   memset(&E, 0, sizeof(E));
+  E.heads = heads_dev;
   if (m->prog.binary) {
-    if (!ite_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect: binary treatment needs ite_dev");
+    if (!ite_dev && !heads_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect: binary treatment needs ite_dev");
     E.x_values = nullptr;
     E.n_x = 2;
   } else {
-    if (!x_values_dev || n_x < 1 || !adrf_sum_dev)
+    if (!x_values_dev || n_x < 1 || (!adrf_sum_dev && !heads_dev))
       return fail(BGM_ERR_ARG, "bgm_causal_effect: continuous treatment needs x_values_dev, n_x >= 1 and adrf_sum_dev");
     E.x_values = x_values_dev;
     E.n_x = n_x;

@@ -379,6 +379,8 @@ struct EffectDev {
   const float* noise;      // optional injected N(0,1): (n_x, n_keep, n)
   double* adrf_sum;        // (n_x, n_keep)
   float* ite;              // (n_keep, n)
+  float* heads;            // heads mode (bgm_causal_effect_heads): (n_keep*n, n_x, 2) = (mu_y, raw sigma head),
+                           // no noise, no reduction
 };
 
 __global__ void __launch_bounds__(MAX_WARPS * 32, 1)
@@ -426,6 +428,14 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
       }
       __syncwarp();
       float y = S.scr[lane];                                                     // mu_y
+      if (E.heads) {
+        if (valid) {
+          float2* hp = reinterpret_cast<float2*>(E.heads) + ((size_t)s * n + row) * E.n_x + j;
+          *hp = make_float2(y, S.scr[TILE_ROWS + lane]);
+        }
+        __syncwarp();
+        continue;
+      }
       if (E.sample_y) {                                                          // :703-708
         const float s2 = P.s2y >= 0.f ? P.s2y : softplus_f(S.scr[TILE_ROWS + lane]) + 1e-6f;
         float e;
@@ -448,6 +458,165 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
         if (lane == 0) atomicAdd(E.adrf_sum + (size_t)j * E.n_keep + s, (double)part);
+      }
+    }
+  }
+}
+
+// ---- memoised effect evaluation --------------------------------------------------------------
+// A rejected proposal repeats the chain state, so at an acceptance rate a only a fraction ~a of the
+// kept states of a row are distinct; f_net is deterministic, hence (mu_y, sigma_y) need to be
+// evaluated once per DISTINCT state (bgm_causal_effect_heads on the compacted list) and every
+// (kept state, row, dose) then only draws its own noise and accumulates (this kernel).  Results are
+// identical to evaluating f_net at every kept state (infer_from_latent_posterior, :671-763).
+// first[row*n_keep + s] = 1 iff the kept state s of the row differs from state s-1 (s = 0: always).
+__global__ void effect_distinct_kernel(const float* __restrict__ z_samples, int n_keep, int n, int zd,
+                                       int* __restrict__ first) {
+  const long long total = (long long)n_keep * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(i / n), row = (int)(i - (long long)s * n);
+    int f = 1;
+    if (s > 0) {
+      const float* a = z_samples + ((size_t)s * n + row) * zd;
+      const float* b = a - (size_t)n * zd;
+      f = 0;
+      for (int d = 0; d < zd; ++d) f |= (__float_as_uint(a[d]) != __float_as_uint(b[d]));
+    }
+    first[(size_t)row * n_keep + s] = f;
+  }
+}
+// distinct states, compacted: zlist[pos[row*n_keep+s] - 1] = z[s][row] where first == 1 (pos = inclusive scan)
+__global__ void effect_compact_kernel(const float* __restrict__ z_samples, int n_keep, int n, int zd,
+                                      const int* __restrict__ first, const int* __restrict__ pos,
+                                      float* __restrict__ zlist) {
+  const long long total = (long long)n_keep * n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int row = (int)(i / n_keep), s = (int)(i - (long long)row * n_keep);
+    if (first[i]) {
+      const float* a = z_samples + ((size_t)s * n + row) * zd;
+      float* o = zlist + (size_t)(pos[i] - 1) * zd;
+      for (int d = 0; d < zd; ++d) o[d] = a[d];
+    }
+  }
+}
+// Inclusive prefix sum of int32 (three small launches): per-block scans of 2048 elements, a
+// single-block scan of the block totals, then the offsets are added.  scratch: ceil(n/2048) ints.
+constexpr int SCAN_TILE = 2048;
+__global__ void __launch_bounds__(256) scan_block_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                         long long n, int* __restrict__ totals) {
+  __shared__ int wsum[8];
+  const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  int v[8], run = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    run += v[k];
+    v[k] = run;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = run;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+  for (int w = 0; w < warp; ++w) woff += wsum[w];
+  const int off = woff + inc - run;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < n) out[base + k] = v[k] + off;
+  if (threadIdx.x == 255) totals[blockIdx.x] = off + run;
+}
+__global__ void __launch_bounds__(1024) scan_totals_kernel(int* __restrict__ totals, int nblocks) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < nblocks; b0 += 1024) {
+    const int i = b0 + threadIdx.x;
+    const int x = i < nblocks ? totals[i] : 0;
+    int inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += wsum[w];
+    const int carry = carry_s;
+    if (i < nblocks) totals[i] = carry + woff + inc - x;   // exclusive offset of block i
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + woff + inc;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) scan_add_kernel(int* __restrict__ out, long long n,
+                                                       const int* __restrict__ totals) {
+  const long long base = (long long)blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  const int off = totals[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if (base + k < n) out[base + k] += off;
+}
+struct CombineDev {
+  const float* heads;      // (n_distinct, n_x, 2)
+  const int* pos;          // (n, n_keep) inclusive scan of `first`: distinct index + 1 of every (row, s)
+  int n_keep, n, n_x, binary, sample_y;
+  float s2y;               // fixed variance or < 0
+  uint64_t seed;
+  int64_t row_offset;
+  const float* noise;      // optional injected N(0,1): (n_x, n_keep, n)
+  double* adrf_sum;        // (n_x, n_keep)
+  float* ite;              // (n_keep, n)
+};
+// one warp = 32 consecutive rows of one kept state
+__global__ void __launch_bounds__(256) effect_combine_kernel(const __grid_constant__ CombineDev C) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int tiles_per_s = (C.n + 31) / 32;
+  const long long ntiles = (long long)tiles_per_s * C.n_keep;
+  for (long long tile = warp0; tile < ntiles; tile += nwarps) {
+    const int s = (int)(tile / tiles_per_s);
+    const int row = (int)(tile - (long long)s * tiles_per_s) * 32 + lane;
+    const bool valid = row < C.n;
+    const int lrow = valid ? row : C.n - 1;
+    const int64_t grow = C.row_offset + lrow;
+    const float2* h = reinterpret_cast<const float2*>(C.heads) +
+                      (size_t)(C.pos[(size_t)lrow * C.n_keep + s] - 1) * C.n_x;
+    float nz4[4] = {0.f, 0.f, 0.f, 0.f};
+    float y_prev = 0.f;
+    for (int j = 0; j < C.n_x; ++j) {
+      const float2 mr = __ldg(h + j);
+      float y = mr.x;
+      if (C.sample_y) {
+        const float s2 = C.s2y >= 0.f ? C.s2y : softplus_f(mr.y) + 1e-6f;
+        float e;
+        if (C.noise) {
+          e = C.noise[((size_t)j * C.n_keep + s) * C.n + lrow];
+        } else {
+          if ((j & 3) == 0) normal4(C.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)(j >> 2), nz4);
+          const int k4 = j & 3;
+          e = k4 == 0 ? nz4[0] : (k4 == 1 ? nz4[1] : (k4 == 2 ? nz4[2] : nz4[3]));
+        }
+        y = fmaf(sqrtf(s2), e, y);
+      }
+      if (C.binary) {
+        if (j == 0) y_prev = y;
+        else if (valid) C.ite[(size_t)s * C.n + row] = y_prev - y;
+      } else {
+        float part = valid ? y : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        if (lane == 0) atomicAdd(C.adrf_sum + (size_t)j * C.n_keep + s, (double)part);
       }
     }
   }

@@ -1223,6 +1223,10 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
           raw = fmaf(a, wf.y, raw);
         }
         float y = mu;
+        if (E.heads) {            // heads mode: (mu_y, raw sigma head) per (state, dose), nothing else
+          if (valid && (jd & 1) == c)
+            reinterpret_cast<float2*>(E.heads)[((size_t)s * n + row) * n_x + jd] = make_float2(mu, raw);
+        } else {
         if (E.sample_y) {
           const float s2 = P.s2y >= 0.f ? P.s2y : softplus_f(raw) + 1e-6f;
           float e;
@@ -1247,6 +1251,7 @@ causal_effect_tc_kernel(const __grid_constant__ TcProgram P, const float* __rest
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
           if (lane == 0) atomicAdd(E.adrf_sum + (size_t)jd * E.n_keep + s, (double)part);
+        }
         }
       }
       if (j <= n_x) {
