@@ -465,8 +465,10 @@ class CausalBGM(object):
         step_rows = bs
         if not adaptive:
             zd_ = sum(self._p['z_dims'])
-            per_row = 4.0 * int(n_mcmc) * (zd_ + 2)                 # kept states + effect draws
-            budget = min(16e9, 0.3 * torch.cuda.mem_get_info()[0])
+            n_x_ = 2 if binary else len(x_values)
+            # kept states + effect draws + the memoised path's index arrays and (worst case) heads
+            per_row = float(n_mcmc) * (4.0 * (zd_ + 2) + 8.0 + 8.0 * n_x_)
+            budget = min(24e9, 0.3 * torch.cuda.mem_get_info()[0])
             step_rows = max(bs, int(budget // per_row) // bs * bs)
         for start in range(0, n_test, step_rows):
             end = min(start + step_rows, n_test)
