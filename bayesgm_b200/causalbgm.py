@@ -391,19 +391,20 @@ class CausalBGM(object):
                       _lib.ptr(out) if binary else None, st)
             return out
         zd = sum(self._p['z_dims'])
-        first = torch.empty(total, dtype=torch.int32, device='cuda')
-        pos = torch.empty(total, dtype=torch.int32, device='cuda')
-        scratch = torch.empty((total + 2047) // 2048, dtype=torch.int32, device='cuda')
-        _lib.call("bgm_causal_effect_index", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(first), _lib.ptr(pos),
-                  _lib.ptr(scratch), st)
-        n_distinct = int(pos[-1].item())                      # the one host sync of the memoised path
+        local = torch.empty(total, dtype=torch.int32, device='cuda')
+        rowtot = torch.empty(n, dtype=torch.int32, device='cuda')
+        rowend = torch.empty(n, dtype=torch.int32, device='cuda')
+        scratch = torch.empty((n + 2047) // 2048, dtype=torch.int32, device='cuda')
+        _lib.call("bgm_causal_effect_index", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(local), _lib.ptr(rowtot),
+                  _lib.ptr(rowend), _lib.ptr(scratch), st)
+        n_distinct = int(rowend[-1].item())                   # the one host sync of the memoised path
         zlist = torch.empty((n_distinct, zd), dtype=torch.float32, device='cuda')
-        _lib.call("bgm_causal_effect_compact", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(first), _lib.ptr(pos),
+        _lib.call("bgm_causal_effect_compact", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(local), _lib.ptr(rowend),
                   _lib.ptr(zlist), st)
         heads = torch.empty((n_distinct, n_x, 2), dtype=torch.float32, device='cuda')
         _lib.call("bgm_causal_effect_heads", m, _lib.ptr(zlist), n_distinct, _lib.ptr(xv), n_x, _lib.ptr(heads), st)
-        _lib.call("bgm_causal_effect_combine", m, _lib.ptr(heads), _lib.ptr(pos), n_keep, n, n_x, int(bool(sample_y)),
-                  seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
+        _lib.call("bgm_causal_effect_combine", m, _lib.ptr(heads), _lib.ptr(local), _lib.ptr(rowend), n_keep, n, n_x,
+                  int(bool(sample_y)), seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
                   _lib.ptr(out) if binary else None, st)
         self.last_distinct_fraction = n_distinct / float(total)
         return out

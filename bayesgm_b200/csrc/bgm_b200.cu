@@ -658,41 +658,42 @@ int bgm_mh_noise(uint64_t seed, int64_t row_offset, int n, int zd, int t_begin, 
 }
 
 // ---- memoised effect evaluation (causal.cuh) ----
-int bgm_causal_effect_index(const float* z_samples_dev, int n_keep, int n, int zd, int* first_dev, int* pos_dev,
-                            int* scratch_dev, void* stream) {
-  if (!z_samples_dev || !first_dev || !pos_dev || !scratch_dev || n_keep < 1 || n < 1 || zd < 1)
+int bgm_causal_effect_index(const float* z_samples_dev, int n_keep, int n, int zd, int* local_dev, int* rowtot_dev,
+                            int* rowend_dev, int* scratch_dev, void* stream) {
+  if (!z_samples_dev || !local_dev || !rowtot_dev || !rowend_dev || !scratch_dev || n_keep < 1 || n < 1 || zd < 1 || zd > 32)
     return fail(BGM_ERR_ARG, "bgm_causal_effect_index: bad argument");
-  const long long total = (long long)n_keep * n;
-  if (total > 0x7fffffffLL) return fail(BGM_ERR_UNSUPPORTED, "bgm_causal_effect_index: n_keep * n must be < 2^31");
+  if ((long long)n_keep * n > 0x7fffffffLL) return fail(BGM_ERR_UNSUPPORTED, "bgm_causal_effect_index: n_keep * n must be < 2^31");
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
-  effect_distinct_kernel<<<grid, 256, 0, st>>>(z_samples_dev, n_keep, n, zd, first_dev);
-  const int nblocks = (int)((total + SCAN_TILE - 1) / SCAN_TILE);
-  scan_block_kernel<<<nblocks, 256, 0, st>>>(first_dev, pos_dev, total, scratch_dev);
+  const int grid = std::max(1, std::min((n + 127) / 128, 148 * 8));
+  if (zd <= 8) effect_rowscan_kernel<8><<<grid, 128, 0, st>>>(z_samples_dev, n_keep, n, zd, local_dev, rowtot_dev);
+  else if (zd <= 16) effect_rowscan_kernel<16><<<grid, 128, 0, st>>>(z_samples_dev, n_keep, n, zd, local_dev, rowtot_dev);
+  else effect_rowscan_kernel<32><<<grid, 128, 0, st>>>(z_samples_dev, n_keep, n, zd, local_dev, rowtot_dev);
+  const int nblocks = (n + SCAN_TILE - 1) / SCAN_TILE;
+  scan_block_kernel<<<nblocks, 256, 0, st>>>(rowtot_dev, rowend_dev, n, scratch_dev);
   scan_totals_kernel<<<1, 1024, 0, st>>>(scratch_dev, nblocks);
-  scan_add_kernel<<<nblocks, 256, 0, st>>>(pos_dev, total, scratch_dev);
+  scan_add_kernel<<<nblocks, 256, 0, st>>>(rowend_dev, n, scratch_dev);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int bgm_causal_effect_compact(const float* z_samples_dev, int n_keep, int n, int zd, const int* first_dev,
-                              const int* pos_dev, float* zlist_dev, void* stream) {
-  if (!z_samples_dev || !first_dev || !pos_dev || !zlist_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect_compact: null pointer");
-  const long long total = (long long)n_keep * n;
-  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 32);
-  effect_compact_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(z_samples_dev, n_keep, n, zd, first_dev, pos_dev,
-                                                                zlist_dev);
+int bgm_causal_effect_compact(const float* z_samples_dev, int n_keep, int n, int zd, const int* local_dev,
+                              const int* rowend_dev, float* zlist_dev, void* stream) {
+  if (!z_samples_dev || !local_dev || !rowend_dev || !zlist_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect_compact: null pointer");
+  const int grid = std::max(1, std::min((n + 127) / 128, 148 * 8));
+  effect_compact_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(z_samples_dev, n_keep, n, zd, local_dev, rowend_dev,
+                                                               zlist_dev);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const int* pos_dev, int n_keep, int n,
-                              int n_x, int sample_y, uint64_t seed, int64_t row_offset, const float* noise_dev,
-                              double* adrf_sum_dev, float* ite_dev, void* stream) {
-  if (!m || !heads_dev || !pos_dev || n_keep < 1 || n < 1) return fail(BGM_ERR_ARG, "bgm_causal_effect_combine: bad argument");
+int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const int* local_dev, const int* rowend_dev,
+                              int n_keep, int n, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
+                              const float* noise_dev, double* adrf_sum_dev, float* ite_dev, void* stream) {
+  if (!m || !heads_dev || !local_dev || !rowend_dev || n_keep < 1 || n < 1)
+    return fail(BGM_ERR_ARG, "bgm_causal_effect_combine: bad argument");
   CombineDev C;
   memset(&C, 0, sizeof(C));
-  C.heads = heads_dev; C.pos = pos_dev; C.n_keep = n_keep; C.n = n;
+  C.heads = heads_dev; C.local = local_dev; C.rowend = rowend_dev; C.n_keep = n_keep; C.n = n;
   C.binary = m->prog.binary; C.n_x = C.binary ? 2 : n_x;
   if (C.binary ? !ite_dev : (!adrf_sum_dev || n_x < 1))
     return fail(BGM_ERR_ARG, "bgm_causal_effect_combine: binary needs ite_dev, continuous adrf_sum_dev and n_x >= 1");

@@ -469,35 +469,48 @@ causal_effect_kernel(const __grid_constant__ CausalProgram P, const float* __res
 // evaluated once per DISTINCT state (bgm_causal_effect_heads on the compacted list) and every
 // (kept state, row, dose) then only draws its own noise and accumulates (this kernel).  Results are
 // identical to evaluating f_net at every kept state (infer_from_latent_posterior, :671-763).
-// first[row*n_keep + s] = 1 iff the kept state s of the row differs from state s-1 (s = 0: always).
-__global__ void effect_distinct_kernel(const float* __restrict__ z_samples, int n_keep, int n, int zd,
-                                       int* __restrict__ first) {
-  const long long total = (long long)n_keep * n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(i / n), row = (int)(i - (long long)s * n);
-    int f = 1;
-    if (s > 0) {
+// Index of the distinct states, all accesses coalesced (thread = row, sequential over the kept states):
+// local[s*n + row] = number of distinct states among states 0..s of the row (>= 1; it changes exactly
+// where state s differs bitwise from state s-1); rowtot[row] = local[(n_keep-1)*n + row].
+template <int ZMAX>
+__global__ void effect_rowscan_kernel(const float* __restrict__ z_samples, int n_keep, int n, int zd,
+                                      int* __restrict__ local, int* __restrict__ rowtot) {
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    float prev[ZMAX];
+    int c = 0;
+    for (int s = 0; s < n_keep; ++s) {
       const float* a = z_samples + ((size_t)s * n + row) * zd;
-      const float* b = a - (size_t)n * zd;
-      f = 0;
-      for (int d = 0; d < zd; ++d) f |= (__float_as_uint(a[d]) != __float_as_uint(b[d]));
+      int f = s == 0;
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d) {
+        if (d < zd) {
+          const float v = a[d];
+          if (s > 0) f |= (__float_as_uint(v) != __float_as_uint(prev[d]));
+          prev[d] = v;
+        }
+      }
+      c += f;
+      local[(size_t)s * n + row] = c;
     }
-    first[(size_t)row * n_keep + s] = f;
+    rowtot[row] = c;
   }
 }
-// distinct states, compacted: zlist[pos[row*n_keep+s] - 1] = z[s][row] where first == 1 (pos = inclusive scan)
+// distinct states, compacted row by row: the states of `row` occupy zlist[rowend[row]-rowtot .. rowend[row])
+// (rowend = inclusive scan of rowtot)
 __global__ void effect_compact_kernel(const float* __restrict__ z_samples, int n_keep, int n, int zd,
-                                      const int* __restrict__ first, const int* __restrict__ pos,
+                                      const int* __restrict__ local, const int* __restrict__ rowend,
                                       float* __restrict__ zlist) {
-  const long long total = (long long)n_keep * n;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int row = (int)(i / n_keep), s = (int)(i - (long long)row * n_keep);
-    if (first[i]) {
-      const float* a = z_samples + ((size_t)s * n + row) * zd;
-      float* o = zlist + (size_t)(pos[i] - 1) * zd;
-      for (int d = 0; d < zd; ++d) o[d] = a[d];
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x) {
+    const int base = rowend[row] - local[(size_t)(n_keep - 1) * n + row];
+    int cprev = 0;
+    for (int s = 0; s < n_keep; ++s) {
+      const int c = local[(size_t)s * n + row];
+      if (c != cprev) {
+        const float* a = z_samples + ((size_t)s * n + row) * zd;
+        float* o = zlist + (size_t)(base + c - 1) * zd;
+        for (int d = 0; d < zd; ++d) o[d] = a[d];
+        cprev = c;
+      }
     }
   }
 }
@@ -568,7 +581,8 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int* __restrict__ out, lo
 }
 struct CombineDev {
   const float* heads;      // (n_distinct, n_x, 2)
-  const int* pos;          // (n, n_keep) inclusive scan of `first`: distinct index + 1 of every (row, s)
+  const int* local;        // (n_keep, n) per-row running count of distinct states
+  const int* rowend;       // (n) inclusive scan of the per-row totals
   int n_keep, n, n_x, binary, sample_y;
   float s2y;               // fixed variance or < 0
   uint64_t seed;
@@ -590,8 +604,8 @@ __global__ void __launch_bounds__(256) effect_combine_kernel(const __grid_consta
     const bool valid = row < C.n;
     const int lrow = valid ? row : C.n - 1;
     const int64_t grow = C.row_offset + lrow;
-    const float2* h = reinterpret_cast<const float2*>(C.heads) +
-                      (size_t)(C.pos[(size_t)lrow * C.n_keep + s] - 1) * C.n_x;
+    const int ref = C.rowend[lrow] - C.local[(size_t)(C.n_keep - 1) * C.n + lrow] + C.local[(size_t)s * C.n + lrow] - 1;
+    const float2* h = reinterpret_cast<const float2*>(C.heads) + (size_t)ref * C.n_x;
     float nz4[4] = {0.f, 0.f, 0.f, 0.f};
     float y_prev = 0.f;
     for (int j = 0; j < C.n_x; ++j) {

@@ -177,23 +177,25 @@ int bgm_causal_effect(const bgm_causal* m, const float* z_samples_dev, int n_kee
  * fraction ~ acceptance rate of a row's kept states are distinct, and f_net is deterministic: (mu_y,
  * sigma_y head) are evaluated once per DISTINCT state and every (kept state, row, dose) then only
  * draws its noise and accumulates.  Identical results (same Philox draws, same f_net arithmetic).
- *   bgm_causal_effect_index   first_dev[row*n_keep+s] = 1 iff kept state s of the row differs (bitwise)
- *                             from state s-1 (s = 0: 1); pos_dev = inclusive prefix sum of first_dev
- *                             (pos_dev[n*n_keep-1] = number of distinct states); scratch_dev:
- *                             ceil(n*n_keep/2048) ints.  n*n_keep < 2^31.
- *   bgm_causal_effect_compact zlist_dev[(pos-1)] = the distinct states, (n_distinct, zd).
+ *   bgm_causal_effect_index   local_dev[s*n+row] = number of distinct states among kept states 0..s of the
+ *                             row (it changes exactly where state s differs bitwise from state s-1);
+ *                             rowtot_dev[row] = the row's total; rowend_dev = inclusive prefix sum of
+ *                             rowtot_dev (rowend_dev[n-1] = number of distinct states); scratch_dev:
+ *                             ceil(n/2048) ints.  n*n_keep < 2^31, zd <= 32.
+ *   bgm_causal_effect_compact zlist_dev (n_distinct, zd): the distinct states, row by row (the states of
+ *                             `row` occupy [rowend[row]-rowtot[row], rowend[row])).
  *   bgm_causal_effect_heads   heads_dev (n_states, n_x, 2) = (mu_y, raw sigma_y head) of f_net at every
  *                             dose (binary: n_x = 2, doses {1, 0}, x_values_dev NULL) for a list of states.
- *   bgm_causal_effect_combine the reductions of bgm_causal_effect from heads_dev and pos_dev. */
-int bgm_causal_effect_index(const float* z_samples_dev, int n_keep, int n, int zd, int* first_dev, int* pos_dev,
-                            int* scratch_dev, void* stream);
-int bgm_causal_effect_compact(const float* z_samples_dev, int n_keep, int n, int zd, const int* first_dev,
-                              const int* pos_dev, float* zlist_dev, void* stream);
+ *   bgm_causal_effect_combine the reductions of bgm_causal_effect from heads_dev, local_dev, rowend_dev. */
+int bgm_causal_effect_index(const float* z_samples_dev, int n_keep, int n, int zd, int* local_dev, int* rowtot_dev,
+                            int* rowend_dev, int* scratch_dev, void* stream);
+int bgm_causal_effect_compact(const float* z_samples_dev, int n_keep, int n, int zd, const int* local_dev,
+                              const int* rowend_dev, float* zlist_dev, void* stream);
 int bgm_causal_effect_heads(const bgm_causal* m, const float* states_dev, int n_states, const float* x_values_dev,
                             int n_x, float* heads_dev, void* stream);
-int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const int* pos_dev, int n_keep, int n,
-                              int n_x, int sample_y, uint64_t seed, int64_t row_offset, const float* noise_dev,
-                              double* adrf_sum_dev, float* ite_dev, void* stream);
+int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const int* local_dev, const int* rowend_dev,
+                              int n_keep, int n, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
+                              const float* noise_dev, double* adrf_sum_dev, float* ite_dev, void* stream);
 
 /* --------------------------------------------------------------- BGM / HMC -- */
 /* The generator of BGM, `BaseVariationalNet` (networks/base.py:53-117), in
