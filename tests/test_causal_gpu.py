@@ -315,3 +315,32 @@ def test_full_size_properties():
     idx = rs.choice(n, 256, replace=False)
     want = causal.log_posterior(params, nets, x[idx], y[idx], v[idx], tr1['z_final'][idx])
     lp_close(lp[idx], want)
+
+
+@pytest.mark.parametrize("binary,engine", [(False, 'tensor'), (True, 'tensor'), (False, 'simt')])
+def test_memoised_effect_equals_direct_evaluation(binary, engine):
+    """Kept states with long runs of repeats (what a 25 % acceptance rate produces): evaluating f_net
+    once per distinct state and combining gives exactly what evaluating it at every kept state gives."""
+    z_dims = [3, 6, 3, 6] if binary else [1, 1, 1, 2]
+    v_dim = 100 if binary else 200
+    params = causal_params(v_dim, z_dims, binary)
+    m = product_model(params, causal_nets(params), engine)
+    rs = np.random.RandomState(12)
+    n, n_keep, zd = 333, 40, sum(z_dims)
+    zs = np.empty((n_keep, n, zd), np.float32)
+    zs[0] = rs.standard_normal((n, zd))
+    for s in range(1, n_keep):                       # each row moves with probability 0.25
+        move = rs.uniform(size=n) < 0.25
+        zs[s] = np.where(move[:, None], zs[s - 1] + 0.3 * rs.standard_normal((n, zd)).astype(np.float32), zs[s - 1])
+    import torch
+    zd_ = torch.from_numpy(zs).cuda()
+    xv = None if binary else np.linspace(0, 3, 7)
+    for sample_y in (False, True):
+        a = m._effect_device(zd_, n_keep, n, xv, sample_y, 5, 1000, memoise=True).cpu().numpy()
+        frac = m.last_distinct_fraction
+        b = m._effect_device(zd_, n_keep, n, xv, sample_y, 5, 1000, memoise=False).cpu().numpy()
+        if binary:
+            np.testing.assert_array_equal(a, b)      # per-subject values: bit-identical
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-9)   # float64 sums, atomic order only
+    assert 0.2 < frac < 0.35
