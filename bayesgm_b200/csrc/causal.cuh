@@ -218,7 +218,6 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
 
   const bgm_mh_args& A = D.a;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int warps = blockDim.x >> 5;
   const WarpSmem S = warp_smem(smem + P.image_floats + warp * P.per_warp_floats, P);
   const int n = A.n, zd = P.zd;
   const int ntiles = (n + TILE_ROWS - 1) / TILE_ROWS;
