@@ -398,6 +398,11 @@ class CausalBGM(object):
         _lib.call("bgm_causal_effect_index", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(local), _lib.ptr(rowtot),
                   _lib.ptr(rowend), _lib.ptr(scratch), st)
         n_distinct = int(rowend[-1].item())                   # the one host sync of the memoised path
+        if 8.0 * n_distinct * n_x > min(32e9, 0.4 * torch.cuda.mem_get_info()[0]):
+            # the (mu, sigma) table of the distinct states would not fit comfortably: evaluate directly
+            del local, rowtot, rowend, scratch
+            return self._effect_device(z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=noise,
+                                       memoise=False)
         zlist = torch.empty((n_distinct, zd), dtype=torch.float32, device='cuda')
         _lib.call("bgm_causal_effect_compact", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(local), _lib.ptr(rowend),
                   _lib.ptr(zlist), st)

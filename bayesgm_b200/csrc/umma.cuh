@@ -92,7 +92,8 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 // Packed variant (two values per instruction; sm_100 FMUL2 / FFMA2): Veltkamp's split with the
 // factor 2^13 + 1 -- hi = v rounded to nearest at 24 - 13 = 11 significant bits, lo = v - hi exact.
 // 4 packed FMA-pipe instructions per PAIR instead of IADD3 + LOP3 + FADD per value; the kernels
-// are bound by issue slots, not by the FMA pipe.
+// are bound by issue slots, not by the FMA pipe.  Range: v * 8193 must not overflow, i.e. |v| < 4.1e34
+// (beyond that hi is NaN and the proposal is rejected); NaN / inf inputs propagate as NaN.
 __device__ __forceinline__ void split_tf32_x2(float2 v, float2& hi, float2& lo) {
   const float2 m1 = make_float2(-1.f, -1.f);
   const float2 c = __fmul2_rn(v, make_float2(8193.f, 8193.f));
