@@ -94,3 +94,56 @@ def test_disc_gradient_matches_float64_finite_differences():
         fd = (loss64(d1) - loss64(d2)) / (2 * h)
         np.testing.assert_allclose(grads[idx][pos], fd, rtol=2e-3, atol=2e-5)
     assert d_loss >= dz_loss          # the penalty is non-negative
+
+
+# ---- BGM iterative phase (oracle/train_bgm.py): the autograd gradients against float64 finite differences ----
+def _bgm_loss64(g, z, x, with_prior):
+    """float64 NumPy restatement of the losses of bgm/base.py:150-153 / :173-180, generator in training mode."""
+    z = z.astype(np.float64)
+    mu_b = z.mean(axis=0)
+    var_b = ((z - mu_b) ** 2).mean(axis=0)
+    h = (z - mu_b) / np.sqrt(var_b + 1e-3) * g['bn']['gamma'].astype(np.float64) + g['bn']['beta'].astype(np.float64)
+    for W, b in g['hidden']:
+        h = h @ W.astype(np.float64) + b.astype(np.float64)
+        h = np.where(h > 0, h, 0.2 * h)
+    mean = h @ g['mean'][0].astype(np.float64) + g['mean'][1].astype(np.float64)
+    s2 = np.logaddexp(0, h @ g['var'][0].astype(np.float64) + g['var'][1].astype(np.float64)) + 1e-6
+    loss = (((x - mean) ** 2) / (2 * s2) + 0.5 * np.log(s2)).sum(axis=1).mean()
+    if with_prior:
+        loss += ((z ** 2).sum(axis=1) / 2).mean()
+    return loss
+
+
+def test_bgm_iterative_oracle_gradients_match_finite_differences():
+    from oracle import train_bgm
+    rs = np.random.RandomState(5)
+    g = onets.init_variational(rs, 3, 6, [8, 8], bias_scale=0.1, bn_random=True)
+    z = rs.standard_normal((7, 3)).astype(np.float32)
+    x = rs.standard_normal((7, 6)).astype(np.float32)
+    # latent gradient, through the batch statistics of the input BatchNormalization
+    loss, gz, _ = train_bgm.iter_latent_grad(g, z, x)
+    assert abs(loss - _bgm_loss64(g, z, x, True)) < 1e-4 * max(1.0, abs(loss))
+    h = 1e-4
+    for (r, d) in [(0, 0), (3, 1), (6, 2)]:
+        zp, zm = z.astype(np.float64).copy(), z.astype(np.float64).copy()
+        zp[r, d] += h
+        zm[r, d] -= h
+        fd = (_bgm_loss64(g, zp, x, True) - _bgm_loss64(g, zm, x, True)) / (2 * h)
+        assert abs(gz[r, d] - fd) < 2e-3 * max(1.0, abs(fd)), (r, d, gz[r, d], fd)
+    # parameter gradients of update_g_net: BN gamma and one entry of the variance head
+    loss_x, mse, grads, _ = train_bgm.iter_g_grads(g, z, x)
+    assert abs(loss_x - _bgm_loss64(g, z, x, False)) < 1e-4 * max(1.0, abs(loss_x))
+    import copy
+    for which, idx in (("gamma", 1), ("var", (2, 4))):
+        gp, gm = copy.deepcopy(g), copy.deepcopy(g)
+        if which == "gamma":
+            gp['bn']['gamma'] = gp['bn']['gamma'].astype(np.float64); gp['bn']['gamma'][idx] += h
+            gm['bn']['gamma'] = gm['bn']['gamma'].astype(np.float64); gm['bn']['gamma'][idx] -= h
+            got = grads[0][idx]
+        else:
+            Wp = gp['var'][0].astype(np.float64); Wp[idx] += h
+            Wm = gm['var'][0].astype(np.float64); Wm[idx] -= h
+            gp['var'] = (Wp, gp['var'][1]); gm['var'] = (Wm, gm['var'][1])
+            got = grads[-2][idx]
+        fd = (_bgm_loss64(gp, z, x, False) - _bgm_loss64(gm, z, x, False)) / (2 * h)
+        assert abs(got - fd) < 2e-3 * max(1.0, abs(fd)), (which, got, fd)
