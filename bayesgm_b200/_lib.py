@@ -149,6 +149,7 @@ SYMBOLS = {
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgm_hmc_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_hmc_heads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 

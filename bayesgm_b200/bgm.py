@@ -404,17 +404,23 @@ class BGM(object):
         n_keep, n, _ = zs.shape
         return self._predict_device(zs, n_keep, n, seed, noise=noise).cpu().numpy()
 
-    def generate(self, nb_samples=1000, use_x_sd=True, *, seed=0):
-        """bgm/base.py:483-509: z ~ N(0,I) through the generator -> (x, sigma^2)."""
+    def generate(self, nb_samples=1000, use_x_sd=True, *, seed=None):
+        """bgm/base.py:483-509: z ~ N(0,I) through the generator -> (x, sigma^2).  Like the reference
+        every call draws fresh z (and fresh N(0,1) for use_x_sd) -- from the model's private generator,
+        or reproducibly from `seed`."""
         torch = _lib.require_cuda()
+        if seed is None:
+            seed = int(self._noise_rng.randint(0, 2 ** 31 - 1))
         z = torch.from_numpy(np.random.RandomState(seed).standard_normal((nb_samples, self._p['z_dim']))
                              .astype(np.float32)).cuda()
-        zeros = torch.zeros((1, nb_samples, self._p['x_dim']), dtype=torch.float32, device='cuda')
-        mu = self._predict_device(z[None], 1, nb_samples, seed, noise=zeros)[0]
-        draw = self._predict_device(z[None], 1, nb_samples, seed)[0]
-        ones = torch.ones_like(zeros)
-        sd = self._predict_device(z[None], 1, nb_samples, seed, noise=ones)[0] - mu
-        return (draw if use_x_sd else mu).cpu().numpy(), (sd * sd).cpu().numpy()
+        mu = torch.empty((nb_samples, self._p['x_dim']), dtype=torch.float32, device='cuda')
+        var = torch.empty_like(mu)
+        _lib.call("bgm_hmc_heads", self._device_model(), _lib.ptr(z), nb_samples, _lib.ptr(mu), _lib.ptr(var),
+                  _lib.stream_ptr())
+        if use_x_sd:
+            draw = self._predict_device(z[None], 1, nb_samples, seed)[0]
+            return draw.cpu().numpy(), var.cpu().numpy()
+        return mu.cpu().numpy(), var.cpu().numpy()
 
     def predict(self, data, alpha=0.05, return_samples=False, bs=100, n_mcmc=5000, burn_in=5000, step_size=0.01,
                 num_leapfrog_steps=10, seed=42, *, group=None, row_offset=0, n_total=None, verbose=1):
@@ -600,6 +606,17 @@ class BGM(object):
         return (float(g[0]), float(g[1])), float(zl.cpu()[0]), gz.cpu().numpy(), z.cpu().numpy()
 
     # ------------------------------------------------------------ EGM training
+    def _offset_streams(self, group):
+        """Data-parallel contract (`group=`): see CausalBGM._offset_streams -- rank 0 keeps the
+        single-GPU host streams, rank r > 0 reseeds NumPy's global generator (mini-batch order, prior
+        z) and its private noise generator once per model."""
+        import torch.distributed as dist
+        r = dist.get_rank(group)
+        if r > 0 and not getattr(self, '_streams_offset', False):
+            np.random.seed((1024 + 7919 * r) % (2 ** 32))
+            self._noise_rng = np.random.RandomState((self._noise_rng.randint(0, 2 ** 31 - 1) + 104729 * r) % (2 ** 32))
+        self._streams_offset = True
+
     def _grad_tensor(self, group):
         torch = _lib.require_cuda()
         n, ptr = C.c_int(), C.c_void_p()
@@ -677,8 +694,15 @@ class BGM(object):
         `egm_batches_per_eval` iterations evaluate() (and, with save_res, generate()/np.savez) runs
         like :317-339 (`eval_during=False` skips it); history in `self.egm_history`."""
         torch = _lib.require_cuda()
+        if group is not None:
+            self._offset_streams(group)
         data = np.asarray(data, dtype=np.float32)
-        self.data_sampler = Base_sampler(x=data, y=data, v=data, batch_size=batch_size, normalize=False)   # :295
+        ds_seed = 123
+        if group is not None:
+            import torch.distributed as dist
+            ds_seed = 123 + 7919 * dist.get_rank(group)
+        self.data_sampler = Base_sampler(x=data, y=data, v=data, batch_size=batch_size, normalize=False,
+                                         random_seed=ds_seed)                                        # :295
         dloss = torch.zeros(3, dtype=torch.float32, device='cuda')
         gloss = torch.zeros(6, dtype=torch.float32, device='cuda')
         rs = self._noise_rng

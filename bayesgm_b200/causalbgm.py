@@ -476,6 +476,7 @@ class CausalBGM(object):
             per_row = float(n_mcmc) * (4.0 * (zd_ + 2) + 8.0 + 8.0 * n_x_)
             budget = min(24e9, 0.3 * torch.cuda.mem_get_info()[0])
             step_rows = max(bs, int(budget // per_row) // bs * bs)
+        acc_tail = []
         for start in range(0, n_test, step_rows):
             end = min(start + step_rows, n_test)
             _, x, y, v, ldv, n = self._stage((data_x[start:end], data_y[start:end], data_v[start:end]))
@@ -483,6 +484,9 @@ class CausalBGM(object):
                                 50, 100, seed, row_offset + start)
             eff = self._effect_device(r['samples'], int(n_mcmc), n, x_values, sample_y, seed,
                                       row_offset + start)
+            T_ = int(burn_in) + int(n_mcmc)
+            w_ = min(100, T_)
+            acc_tail.append((r['accept_count'][T_ - w_:].sum(), w_ * n))                # :901, read back once below
             if binary:                                                            # :640-642
                 ite_mean[start:end] = eff.mean(dim=0).cpu().numpy()
                 lower[start:end] = _quantile_dim0(torch, eff, alpha / 2).cpu().numpy()
@@ -490,6 +494,11 @@ class CausalBGM(object):
             else:                                                                 # :660-661
                 sums += eff
                 n_seen += n
+        if acc_tail:
+            tot = torch.stack([a for a, _ in acc_tail]).sum()
+            self.last_acceptance_rate = float(tot.item()) / float(sum(c for _, c in acc_tail))
+            if verbose:
+                print(f"Final MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
         if binary:
             return ite_mean, np.stack([lower, upper], axis=1)
         ce = merge_adrf(sums, n_seen, group) if group is not None else \
@@ -630,6 +639,20 @@ class CausalBGM(object):
         self.last_iter_losses = tuple(float(a) for a in nl.cpu().numpy()) + (float(zl.cpu()[0]),)
 
     # ------------------------------------------------------------ EGM training
+    def _offset_streams(self, group):
+        """Data-parallel contract (`group=`): every rank trains on its own mini-batches, so the host
+        streams must differ per rank -- `Gaussian_sampler.__init__` reseeds NumPy's global generator to
+        1024 on EVERY rank (prior_samplers.py:24), which would make all ranks draw the same indices,
+        prior z and epsilon and turn the gradient all-reduce into a no-op.  Rank 0 keeps the single-GPU
+        streams; rank r > 0 reseeds the global generator and its private epsilon generator once per
+        model with a rank-dependent seed."""
+        import torch.distributed as dist
+        r = dist.get_rank(group)
+        if r > 0 and not getattr(self, '_streams_offset', False):
+            np.random.seed((1024 + 7919 * r) % (2 ** 32))
+            self._eps_rng = np.random.RandomState((self._eps_rng.randint(0, 2 ** 31 - 1) + 104729 * r) % (2 ** 32))
+        self._streams_offset = True
+
     def _grad_tensor(self, group):
         """torch view (no copy) of the trainer's flat gradient buffer, for all-reduce."""
         torch = _lib.require_cuda()
@@ -726,6 +749,8 @@ class CausalBGM(object):
         Every `egm_batches_per_eval` iterations the model is evaluated like :425-430 (`eval_during=False`
         skips it); the (iteration, mse_x, mse_y, mse_v) history is kept in `self.egm_history`."""
         torch = _lib.require_cuda()
+        if group is not None:
+            self._offset_streams(group)
         data_x, data_y, data_v = data
         n = len(data_x)
         p, zd = self._p['v_dim'], sum(self._p['z_dims'])

@@ -192,6 +192,7 @@ struct bgm_causal {
   int effect_warps = 0;
   int effect_smem_bytes = 0;
   int sm_count = 0;
+  int smem_max = 0;            // opt-in shared memory per block of the device
   long long macs = 0, issued = 0;
   // tensor-core engine (causal_tc.cuh); tc.enabled == 0 when the net shape is outside it
   TcProgram tc;
@@ -493,6 +494,7 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   m->effect_warps = std::min(fit(f_floats), MAX_WARPS);
   m->effect_smem_bytes = (f_floats + m->effect_warps * P.per_warp_floats) * 4;
   m->sm_count = sms;
+  m->smem_max = smem_max;
   m->prog = P;
   m->macs = pk.macs;
   m->issued = pk.issued;
@@ -588,11 +590,13 @@ int bgm_causal_project(const bgm_causal* m, const float* v_dev, int ldv, int n, 
   if (ldvproj < m->proj_dim || ldvproj % 4 != 0)
     return fail(BGM_ERR_ARG, "bgm_causal_project: ldvproj must be >= proj_dim and a multiple of 4");
   const int p = m->prog.p, HP = m->proj_hp;
-  const int smem = (p * HP + p) * 4;
+  int smem = (p * HP + p) * 4;
+  const int stage = smem <= m->smem_max - 1024;   // else U is read through L1/L2 (v_dim >~ 890)
+  if (!stage) smem = 0;
   BGM_CUDA_OK(cudaFuncSetAttribute(causal_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const int grid = std::max(1, std::min((n + 7) / 8, m->sm_count * 2));
   causal_project_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(v_dev, ldv, n, p, HP, m->proj_dev, vproj_dev,
-                                                                   ldvproj, r0_dev);
+                                                                   ldvproj, r0_dev, stage);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -822,5 +826,4 @@ extern "C" int bgm_fp32_peak_tflops(double* tflops, void* stream) {
   return 0;
 }
 
-#include "hmc_api.cuh"
-#include "train_api.cuh"
+// hmc_api.cu / train_api.cu / bnn.cu / host_rng.cu are separate translation units (bayesgm_b200/_build.py)

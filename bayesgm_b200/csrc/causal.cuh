@@ -655,12 +655,18 @@ __global__ void mh_adapt_qsd_kernel(const int* __restrict__ accept_count, int t,
 __global__ void __launch_bounds__(256)
 causal_project_kernel(const float* __restrict__ v, int ldv, int n, int p, int HP,
                       const float* __restrict__ Ub, float* __restrict__ t, int ldt,
-                      float* __restrict__ r0) {
+                      float* __restrict__ r0, int stage) {
   extern __shared__ __align__(16) float psm[];
-  float* U = psm;            // [p][HP]
-  float* b = psm + p * HP;   // [p]
-  for (int i = threadIdx.x; i < p * HP + p; i += blockDim.x) psm[i] = Ub[i];
-  __syncthreads();
+  // U [p][HP] | b [p]: staged in shared memory when it fits (stage != 0), else read through L1/L2
+  // (v_dim >~ 890 at HP = 64 exceeds the 227 KB opt-in limit)
+  const float* U = Ub;
+  const float* b = Ub + p * HP;
+  if (stage) {
+    for (int i = threadIdx.x; i < p * HP + p; i += blockDim.x) psm[i] = Ub[i];
+    __syncthreads();
+    U = psm;
+    b = psm + p * HP;
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
   for (int row = blockIdx.x * warps + warp; row < n; row += gridDim.x * warps) {
     const float* vr = v + (size_t)row * ldv;

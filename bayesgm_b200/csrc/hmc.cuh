@@ -56,6 +56,7 @@ struct HmcDev {
   float* out_grad;        // EVAL: (n,zd)
   float* out_x;           // PREDICT: (n_rows, x_dim) draws
   const float* noise_x;   // PREDICT: optional injected N(0,1) (n_rows, x_dim)
+  float* out_var;         // PREDICT: if non-NULL, out_x receives mu and out_var sigma^2 (no draw)
   int n_per_sample;       // PREDICT: n (rows per sample), for the Philox key
   int sample0;            // PREDICT: index of the first sample in this call
 };
@@ -243,7 +244,14 @@ __device__ __forceinline__ float hmc_program(const HmcProgram& P, const HmcDev& 
           if (predict) {
             // bgm/base.py:517-521: x = mu + sqrt(softplus(raw)+1e-6) * N(0,1)
             float e4[4];
-            if (D.noise_x) {
+            if (D.out_var) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                e4[q] = 0.f;
+                if (rvalid && c + q < P.x_dim)
+                  D.out_var[(size_t)r * P.x_dim + c + q] = softplus_f(acc[i][4 + q]) + 1e-6f;
+              }
+            } else if (D.noise_x) {
 #pragma unroll
               for (int q = 0; q < 4; ++q) e4[q] = (c + q < P.x_dim) ? D.noise_x[(size_t)r * P.x_dim + c + q] : 0.f;
             } else {

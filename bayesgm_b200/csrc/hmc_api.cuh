@@ -307,4 +307,21 @@ int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, in
   return hmc_launch(m, m->prog_fwd, D, n_keep * n, (cudaStream_t)stream);
 }
 
+int bgm_hmc_heads(const bgm_hmc* m, const float* z_dev, int n, float* out_mu_dev, float* out_var_dev,
+                  void* stream) {
+  using namespace bgm;
+  if (!m || !z_dev || !out_mu_dev || !out_var_dev) return fail(BGM_ERR_ARG, "bgm_hmc_heads: null model / pointer");
+  if (n < 1) return fail(BGM_ERR_ARG, "bgm_hmc_heads: n must be >= 1");
+  HmcDev D;
+  memset(&D, 0, sizeof(D));
+  D.a.n = n;
+  D.a.ldx = 0;
+  D.mode = HMC_PREDICT;
+  D.z_in = z_dev;
+  D.out_x = out_mu_dev;
+  D.out_var = out_var_dev;
+  D.n_per_sample = n;
+  return hmc_launch(m, m->prog_fwd, D, n, (cudaStream_t)stream);
+}
+
 }  // extern "C"

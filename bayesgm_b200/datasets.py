@@ -2,8 +2,9 @@
 
 Only what the benchmark / tests need to build inputs on a box where /root/reference
 is absent.  Written from the formulas in `src/bayesgm/datasets/causal_samplers.py:40-67`,
-`base_sampler.py:29-46` and `prior_samplers.py:20-59`; tests/test_datasets_parity.py
-checks bit-equality against the reference modules when they are importable.
+`base_sampler.py:29-46` and `prior_samplers.py:20-59`; tests/test_golden.py checks bit-equality
+against outputs of the reference modules themselves (tests/golden/reference_datasets.npz, made by
+tests/golden/make_golden.py where /root/reference is importable).
 """
 import math
 

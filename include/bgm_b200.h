@@ -282,6 +282,11 @@ int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, in
                     uint64_t seed, int64_t row_offset, const float* noise_dev, float* out_x_dev,
                     void* stream);
 
+/* The generator's heads (bgm/base.py:483-509 `generate`, networks/base.py:98-111): mu(z) and
+ * sigma^2(z) = softplus(raw) + 1e-6 for z_dev (n, z_dim) -> out_mu_dev, out_var_dev (n, x_dim). */
+int bgm_hmc_heads(const bgm_hmc* m, const float* z_dev, int n, float* out_mu_dev, float* out_var_dev,
+                  void* stream);
+
 /* ------------------------------------------------------- EGM training steps -- */
 /* The Discriminator of networks/base.py:338-385: n_hidden blocks of
  * Dense -> BatchNormalization (batch statistics in every call, eps 1e-3) -> tanh, then
