@@ -39,6 +39,15 @@ class MhArgs(C.Structure):
     ]
 
 
+class MtState(C.Structure):
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int), ("has_gauss", C.c_int), ("gauss", C.c_double)]
+
+
+class BnnNetDesc(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("dims", C.POINTER(C.c_int)), ("bn", C.POINTER(C.c_float)),
+                ("params", C.POINTER(C.c_float))]
+
+
 class VarNetDesc(C.Structure):
     _fields_ = [("z_dim", C.c_int), ("x_dim", C.c_int), ("n_hidden", C.c_int),
                 ("units", C.POINTER(C.c_int)), ("bn", C.POINTER(C.c_float)),
@@ -149,6 +158,23 @@ SYMBOLS = {
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgm_hmc_predict": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64,
                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_bnn_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_float, C.c_float,
+                                 C.c_float, C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc)]),
+    "bgm_bnn_destroy": (None, [C.c_void_p]),
+    "bgm_bnn_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "bgm_bnn_scratch_doubles": (C.c_longlong, [C.c_void_p, C.c_int]),
+    "bgm_bnn_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                  C.c_uint64, C.c_int, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_bnn_mh": (C.c_int, [C.c_void_p, C.POINTER(MhArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_bnn_effect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_uint64,
+                                 C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_bnn_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int64, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_host_choice": (C.c_int, [C.POINTER(MtState), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "bgm_host_normal": (C.c_int, [C.POINTER(MtState), C.c_double, C.c_double, C.c_longlong, C.c_void_p]),
+    "bgm_host_rand": (C.c_int, [C.POINTER(MtState), C.c_longlong, C.c_void_p]),
+    "bgm_host_egm_stream": (C.c_int, [C.POINTER(MtState), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "bgm_hmc_heads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -8,8 +8,10 @@ kwargs, return types and error behaviour for the path this package accelerates -
 host NumPy arrays like the reference's; underneath every method calls the C ABI of
 libbgm_b200.so (include/bgm_b200.h) on device buffers.  There is no CPU fallback.
 
-Deterministic networks only (`use_bnn=False`): the Bayesian (DenseFlipout) nets are
-stochastic per call and batch-coupled and are not built yet.
+`use_bnn=False`: deterministic networks (networks/base.py), persistent tcgen05 / SIMT sampler.
+`use_bnn=True` (the shipped default): Bayesian networks (networks/bnn.py: input BatchNormalization on
+batch statistics + DenseFlipout) -- every evaluation draws fresh network noise and couples the rows
+of a `bs` slice through the batch statistics, see csrc/bnn.cuh.
 """
 import ctypes as C
 import datetime
@@ -19,7 +21,7 @@ import numpy as np
 
 from . import _lib
 from .datasets import Gaussian_sampler
-from .nets import DenseNet, DiscNet
+from .nets import DenseNet, DiscNet, BayesDenseNet
 from .shard import merge_adrf, finish_adrf
 
 _DEFAULTS = dict(use_bnn=True, g_units=[64] * 5, e_units=[64] * 5, f_units=[64, 32, 8],
@@ -48,19 +50,18 @@ class CausalBGM(object):
         p = dict(_DEFAULTS)
         p.update(params)
         self._p = p
-        if p['use_bnn']:
-            raise NotImplementedError(
-                "bayesgm_b200: use_bnn=True (DenseFlipout + training-mode BatchNorm, networks/bnn.py) "
-                "is not built; pass use_bnn=False (deterministic nets, networks/base.py).")
+        self._bnn = bool(p['use_bnn'])
         if random_seed is not None:
             np.random.seed(random_seed)
         zd = sum(p['z_dims'])
         z0, z1, z2, _ = p['z_dims']
         rng = np.random.RandomState(random_seed) if random_seed is not None else np.random
-        self.g_net = DenseNet(zd, p['v_dim'] + 1, 'g_net', p['g_units'], rng)          # :74
-        self.e_net = DenseNet(p['v_dim'], zd, 'e_net', p['e_units'], rng)              # :76
-        self.f_net = DenseNet(z0 + z1 + 1, 2, 'f_net', p['f_units'], rng)              # :78
-        self.h_net = DenseNet(z0 + z2, 2, 'h_net', p['h_units'], rng)                  # :80
+        Net = BayesDenseNet if self._bnn else DenseNet                                 # :64-81
+        self.g_net = Net(zd, p['v_dim'] + 1, 'g_net', p['g_units'], rng)               # :65 / :74
+        self.e_net = Net(p['v_dim'], zd, 'e_net', p['e_units'], rng)                   # :67 / :76
+        self.f_net = Net(z0 + z1 + 1, 2, 'f_net', p['f_units'], rng)                   # :69 / :78
+        self.h_net = Net(z0 + z2, 2, 'h_net', p['h_units'], rng)                       # :71 / :80
+        self._bnn_calls = 0              # get_log_posterior call counter (keys the network-noise stream)
         self.dz_net = DiscNet(zd, 'dz_net', p['dz_units'], rng)                        # :83
         self.z_sampler = Gaussian_sampler(mean=np.zeros(zd), sd=1.0)                  # :88 (reseeds to 1024)
         self._trainer = None
@@ -127,6 +128,9 @@ class CausalBGM(object):
         self._drop_handle()
 
     def _device_trainer(self):
+        if self._bnn:
+            raise NotImplementedError("bayesgm_b200: this entry point of the single-CTA training kernels takes "
+                                      "deterministic nets; Bayesian nets train through the layered engine")
         if self._trainer is None:
             _lib.require_cuda()
             p = self._p
@@ -142,7 +146,10 @@ class CausalBGM(object):
 
     def _drop_handle(self):
         if self._handle is not None:
-            _lib.load().bgm_causal_destroy(self._handle)
+            if self._bnn:
+                _lib.load().bgm_bnn_destroy(self._handle)
+            else:
+                _lib.load().bgm_causal_destroy(self._handle)
             self._handle = None
 
     def __del__(self):
@@ -155,6 +162,18 @@ class CausalBGM(object):
     def _device_model(self):
         """Packs g/f/h for the kernels (once per weight change)."""
         self._sync_from_trainer()
+        if self._handle is None and self._bnn:
+            _lib.require_cuda()
+            p = self._p
+            zd4 = (C.c_int * 4)(*[int(d) for d in p['z_dims']])
+            gd, gk = self.g_net.desc()
+            fd, fk = self.f_net.desc()
+            hd, hk = self.h_net.desc()
+            h = C.c_void_p()
+            sig = [float(p[k]) if k in p else -1.0 for k in ('sigma_v', 'sigma_x', 'sigma_y')]
+            _lib.call("bgm_bnn_create", C.byref(h), zd4, int(p['v_dim']), int(bool(p['binary_treatment'])),
+                      sig[0], sig[1], sig[2], C.byref(gd), C.byref(fd), C.byref(hd))
+            self._handle = h
         if self._handle is None:
             _lib.require_cuda()
             p = self._p
@@ -183,6 +202,14 @@ class CausalBGM(object):
             _lib.call("bgm_causal_set_sampler", self._handle, {'auto': 0, 'simt': 1, 'tensor': 2}[engine])
 
     def sampler_info(self):
+        if self._bnn:
+            smem, rows = C.c_int(), C.c_int()
+            macs = C.c_longlong()
+            _lib.call("bgm_bnn_info", self._device_model(), C.byref(smem), C.byref(rows), C.byref(macs))
+            return dict(engine='bnn', tensor_available=False, tensor_smem_bytes=0, smem_bytes=smem.value,
+                        rows_per_cta=rows.value, macs_per_eval=macs.value,
+                        kernel='bnn_mh_kernel<%d>' % (8 if sum(self._p['z_dims']) <= 8 else
+                                                     16 if sum(self._p['z_dims']) <= 16 else 32))
         kind, avail, smem = C.c_int(), C.c_int(), C.c_int()
         issued = C.c_longlong()
         _lib.call("bgm_causal_sampler_info", self._device_model(), C.byref(kind), C.byref(avail), C.byref(smem),
@@ -205,6 +232,10 @@ class CausalBGM(object):
         """Per-data-set device buffers: the projected covariates (models with proj_dim > 0,
         see bgm_causal_project) and the scratch of the in-kernel work scheduler."""
         torch = _lib.require_cuda()
+        if self._bnn:
+            nd = _lib.load().bgm_bnn_scratch_doubles(self._device_model(), n)
+            return dict(vproj=None, r0=None, ldvproj=0, sched=None,
+                        scratch=torch.empty(int(nd), dtype=torch.float64, device='cuda'))
         sched = torch.empty((n + 31) // 32 + 1, dtype=torch.int32, device='cuda')
         if not hasattr(self, '_proj_dim') or self._handle is None:
             self._proj_dim = self.kernel_info()['proj_dim']
@@ -252,8 +283,10 @@ class CausalBGM(object):
         return torch, x, y, v, ldv, n
 
     # --------------------------------------------------------------- hot path
-    def get_log_posterior(self, data_x, data_y, data_v, data_z, eps=1e-6):
-        """causalbgm/base.py:765-817 -> (n,) float32 NumPy array."""
+    def get_log_posterior(self, data_x, data_y, data_v, data_z, eps=1e-6, *, seed=None, call=None):
+        """causalbgm/base.py:765-817 -> (n,) float32 NumPy array.  With Bayesian nets every call
+        draws fresh network noise (Philox stream `seed`, call id `call`; by default a per-model seed
+        and a running call counter) and normalises the inputs with the statistics of this batch."""
         torch, x, y, v, ldv, n = self._stage((data_x, data_y, data_v))
         z = self._to_device(data_z, torch)
         zd = sum(self._p['z_dims'])
@@ -261,6 +294,18 @@ class CausalBGM(object):
             raise ValueError("data_z must have shape (%d, %d)" % (n, zd))
         out = torch.empty(n, dtype=torch.float32, device='cuda')
         aux = self._aux(v, ldv, n)
+        if self._bnn:
+            if seed is None:
+                if not hasattr(self, '_bnn_seed'):
+                    self._bnn_seed = int(np.random.randint(0, 2 ** 31 - 1))
+                seed = self._bnn_seed
+            if call is None:
+                call = self._bnn_calls
+                self._bnn_calls += 1
+            _lib.call("bgm_bnn_logpost", self._device_model(), _lib.ptr(x), _lib.ptr(y), _lib.ptr(v), ldv, _lib.ptr(z),
+                      n, int(seed) & (2 ** 64 - 1), 0, 0, int(call) & 0xFFFFFFFF, _lib.ptr(aux['scratch']),
+                      _lib.ptr(out), _lib.stream_ptr())
+            return out.cpu().numpy()
         _lib.call("bgm_causal_logpost", self._device_model(), _lib.ptr(x), _lib.ptr(y), _lib.ptr(v), ldv,
                   _lib.ptr(aux['vproj']), aux['ldvproj'], _lib.ptr(aux['r0']), _lib.ptr(z), n, _lib.ptr(out),
                   _lib.ptr(aux['sched']), _lib.stream_ptr())
@@ -268,7 +313,7 @@ class CausalBGM(object):
 
     def _mh_device(self, x, y, v, ldv, n, burn_in, n_keep, q_sd, adaptive_sd, initial_q_sd,
                    target_acceptance_rate, tolerance, adjustment_interval, window_size,
-                   seed, row_offset, noise=None, trace=False, keep_samples=True, aux=None):
+                   seed, row_offset, noise=None, trace=False, keep_samples=True, aux=None, slice_id=0):
         """Runs the sampler on staged device buffers; returns a dict of device tensors."""
         torch = _lib.require_cuda()
         aux = aux if aux is not None else self._aux(v, ldv, n)
@@ -286,7 +331,8 @@ class CausalBGM(object):
         a.ldv, a.n = ldv, n
         if aux['vproj'] is not None:
             a.vproj_dev, a.r0_dev, a.ldvproj = aux['vproj'].data_ptr(), aux['r0'].data_ptr(), aux['ldvproj']
-        a.sched_dev = aux['sched'].data_ptr()
+        if aux['sched'] is not None:
+            a.sched_dev = aux['sched'].data_ptr()
         a.z_state_dev, a.lp_state_dev = z_state.data_ptr(), lp_state.data_ptr()
         a.burn_in = burn_in
         a.q_sd_dev = q.data_ptr()
@@ -312,9 +358,21 @@ class CausalBGM(object):
             a.accept_mask_dev = out['accept_mask'].data_ptr()
             a.lp_trace_dev = out['lp_trace'].data_ptr()
         st = _lib.stream_ptr()
+        if self._bnn:
+            # Bayesian nets: one launch per iteration inside bgm_bnn_mh (batch statistics couple the rows)
+            lpc = None
+            if trace:
+                out['lp_cur_trace'] = torch.zeros((T, n), dtype=torch.float32, device=dev)
+                lpc = out['lp_cur_trace']
+
+            def run(args):
+                _lib.call("bgm_bnn_mh", m, C.byref(args), int(slice_id), _lib.ptr(aux['scratch']), _lib.ptr(lpc), st)
+        else:
+            def run(args):
+                _lib.call("bgm_causal_mh", m, C.byref(args), st)
         if not adaptive_sd:
             a.t_begin, a.t_end = 0, T
-            _lib.call("bgm_causal_mh", m, C.byref(a), st)
+            run(a)
         else:
             # q_sd changes after iterations 50, 100, ... < burn_in (:880): one launch per
             # constant-q_sd stretch, the rule itself runs on the device in between.
@@ -323,7 +381,7 @@ class CausalBGM(object):
             for c in cuts + [None]:
                 end = T if c is None else c + 1
                 a.t_begin, a.t_end = begin, end
-                _lib.call("bgm_causal_mh", m, C.byref(a), st)
+                run(a)
                 a.init_mode = 0
                 if c is not None:
                     _lib.call("bgm_mh_adapt_qsd", C.c_void_p(acc_count.data_ptr()), c, window_size, n,
@@ -363,6 +421,8 @@ class CausalBGM(object):
             tr = dict(accept=r['accept_mask'].cpu().numpy().astype(bool), lp_prop=r['lp_trace'].cpu().numpy(),
                       accept_count=counts, q_sd_final=self.last_q_sd,
                       z_final=r['z_state'].cpu().numpy(), lp_final=r['lp_state'].cpu().numpy())
+            if 'lp_cur_trace' in r:
+                tr['lp_cur'] = r['lp_cur_trace'].cpu().numpy()
             return samples, tr
         return samples
 
@@ -385,6 +445,17 @@ class CausalBGM(object):
             n_x = len(x_values)
             out = torch.zeros((n_x, n_keep), dtype=torch.float64, device='cuda')
         total = n_keep * n
+        if self._bnn:
+            # one f_net call per (kept state, dose) with its own network noise: nothing to memoise
+            stats = torch.empty((n_keep, 2 * (self._p['z_dims'][0] + self._p['z_dims'][1])), dtype=torch.float32,
+                                device='cuda')
+            for s0 in range(0, n_keep, 65535):
+                s1 = min(s0 + 65535, n_keep)
+                assert s0 == 0, "more than 65535 kept states per call are not supported with Bayesian nets"
+                _lib.call("bgm_bnn_effect", m, _lib.ptr(z_samples), s1 - s0, n, _lib.ptr(xv), n_x, int(bool(sample_y)),
+                          seed, int(row_offset), _lib.ptr(nz), _lib.ptr(stats), None if binary else _lib.ptr(out),
+                          _lib.ptr(out) if binary else None, st)
+            return out
         if not memoise or n_keep < 2 or total >= 2 ** 31:
             _lib.call("bgm_causal_effect", m, _lib.ptr(z_samples), n_keep, n, _lib.ptr(xv), n_x, int(bool(sample_y)),
                       seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
@@ -469,7 +540,7 @@ class CausalBGM(object):
         # row, so several slices are sampled in ONE launch (identical results, a full grid instead
         # of ceil(bs/128) row tiles); with the adaptive rule the acceptance window is per slice.
         step_rows = bs
-        if not adaptive:
+        if not adaptive and not self._bnn:     # Bayesian nets: the rows of a slice share batch statistics
             zd_ = sum(self._p['z_dims'])
             n_x_ = 2 if binary else len(x_values)
             # kept states + effect draws + the memoised path's index arrays and (worst case) heads
@@ -481,7 +552,7 @@ class CausalBGM(object):
             end = min(start + step_rows, n_test)
             _, x, y, v, ldv, n = self._stage((data_x[start:end], data_y[start:end], data_v[start:end]))
             r = self._mh_device(x, y, v, ldv, n, int(burn_in), int(n_mcmc), q_sd, adaptive, 1.0, 0.25, 0.05,
-                                50, 100, seed, row_offset + start)
+                                50, 100, seed, row_offset + start, slice_id=(row_offset + start) // bs)
             eff = self._effect_device(r['samples'], int(n_mcmc), n, x_values, sample_y, seed,
                                       row_offset + start)
             T_ = int(burn_in) + int(n_mcmc)

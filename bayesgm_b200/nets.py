@@ -72,6 +72,76 @@ class DenseNet(object):
                 o += a.size
 
 
+class BayesDenseNet(object):
+    """`BayesianFullyConnectedNet` (networks/bnn.py:4-38): BatchNormalization on the input, then
+    `tfp.layers.DenseFlipout` layers (LeakyReLU(0.2) between them).  Per layer: kernel posterior loc
+    and untransformed scale rho (sigma = finfo(float32).eps + softplus(rho)), deterministic bias loc.
+    TFP 0.18 default initialisers: loc, bias ~ N(0, 0.1^2), rho ~ N(-3, 0.1^2); Keras BN defaults."""
+
+    def __init__(self, input_dim, output_dim, model_name, nb_units, rng=None):
+        self.input_dim, self.output_dim = int(input_dim), int(output_dim)
+        self.model_name = model_name
+        self.nb_units = [int(u) for u in nb_units]
+        self.dims = [self.input_dim] + self.nb_units + [self.output_dim]
+        rng = rng if rng is not None else np.random
+        k = self.input_dim
+        self.bn = dict(gamma=np.ones(k, np.float32), beta=np.zeros(k, np.float32),
+                       mean=np.zeros(k, np.float32), var=np.ones(k, np.float32))
+        self.layers = []
+        for i in range(len(self.dims) - 1):
+            fi, fo = self.dims[i], self.dims[i + 1]
+            self.layers.append([(0.1 * rng.standard_normal((fi, fo))).astype(np.float32),
+                                (-3.0 + 0.1 * rng.standard_normal((fi, fo))).astype(np.float32),
+                                (0.1 * rng.standard_normal(fo)).astype(np.float32)])
+
+    # Keras order: BN [gamma, beta, moving_mean, moving_variance], then per DenseFlipout layer
+    # [kernel_posterior_loc, kernel_posterior_untransformed_scale, bias_posterior_loc]
+    def get_weights(self):
+        out = [self.bn[k].copy() for k in ('gamma', 'beta', 'mean', 'var')]
+        for layer in self.layers:
+            out += [a.copy() for a in layer]
+        return out
+
+    def set_weights(self, weights):
+        assert len(weights) == 4 + 3 * len(self.layers), "expected BN(4) + loc/rho/bias per DenseFlipout layer"
+        for k, w in zip(('gamma', 'beta', 'mean', 'var'), weights[:4]):
+            w = np.asarray(w, np.float32)
+            assert w.shape == (self.input_dim,)
+            self.bn[k] = w.copy()
+        for i, layer in enumerate(self.layers):
+            for j in range(3):
+                w = np.asarray(weights[4 + 3 * i + j], np.float32)
+                assert w.shape == layer[j].shape, "%s layer %d: shape mismatch" % (self.model_name, i)
+                layer[j] = w.copy()
+
+    def flat_params(self):
+        """Trainable parameters, Keras trainable_variables order: gamma | beta | (loc, rho, bias) per layer."""
+        parts = [self.bn['gamma'], self.bn['beta']] + [a.ravel() for layer in self.layers for a in layer]
+        return np.ascontiguousarray(np.concatenate(parts).astype(np.float32))
+
+    def load_flat(self, flat):
+        k = self.input_dim
+        self.bn['gamma'], self.bn['beta'] = np.array(flat[:k], np.float32), np.array(flat[k:2 * k], np.float32)
+        o = 2 * k
+        for layer in self.layers:
+            for j in range(3):
+                a = layer[j]
+                layer[j] = np.array(flat[o:o + a.size], np.float32).reshape(a.shape)
+                o += a.size
+
+    def desc(self):
+        """(bgm_bnn_net_desc, keep-alive tuple) for the C ABI."""
+        dims = (C.c_int * len(self.dims))(*self.dims)
+        bn = np.ascontiguousarray(np.concatenate([self.bn['gamma'], self.bn['beta']]), np.float32)
+        flat = np.ascontiguousarray(np.concatenate([a.ravel() for layer in self.layers for a in layer]), np.float32)
+        d = _lib.BnnNetDesc(len(self.layers), C.cast(dims, C.POINTER(C.c_int)), bn.ctypes.data_as(C.POINTER(C.c_float)),
+                            flat.ctypes.data_as(C.POINTER(C.c_float)))
+        return d, (dims, bn, flat)
+
+    def as_oracle_params(self):
+        return dict(bn=dict(self.bn), layers=[tuple(layer) for layer in self.layers])
+
+
 class VariationalNet(object):
     """`BaseVariationalNet` (networks/base.py:53-117): BatchNormalization on the input,
     Dense+LeakyReLU(0.2) hidden layers, a mean head and a softplus(+eps) variance head.

@@ -197,6 +197,70 @@ int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const
                               int n_keep, int n, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
                               const float* noise_dev, double* adrf_sum_dev, float* ite_dev, void* stream);
 
+/* ------------------------------------------- CausalBGM on Bayesian networks -- */
+/* `use_bnn: True` (the default of every shipped CausalBGM config, causalbgm/base.py:64-72):
+ * g / f / h are `BayesianFullyConnectedNet`s (networks/bnn.py:4-38): a BatchNormalization on
+ * the input that uses the statistics of the CALL's batch (Keras hands the outer call's
+ * `training=True` default down to the sub-layer; eps 1e-3, biased variance), then
+ * tfp.layers.DenseFlipout layers with LeakyReLU(0.2) between them.  A DenseFlipout call draws
+ * ONE kernel perturbation dW = sigma * N(0,1), sigma = finfo(float32).eps + softplus(rho), shared
+ * by the rows of the batch, and per-row Rademacher vectors: y = x loc + ((x o s_in) dW) o s_out + b.
+ * Descriptor arrays are HOST memory: bn = gamma[in] | beta[in]; params = per layer
+ * loc[in][out], rho[in][out] (`kernel_posterior_untransformed_scale`), bias[out].
+ * Widths: layer inputs <= 64 (so hidden widths <= 64), sum(z_dims) <= 32. */
+typedef struct {
+  int n_layers;
+  const int* dims;
+  const float* bn;
+  const float* params;
+} bgm_bnn_net_desc;
+
+typedef struct bgm_bnn bgm_bnn; /* opaque: loc / sigma / bias images of g, f, h */
+
+int bgm_bnn_create(bgm_bnn** out, const int z_dims[4], int v_dim, int binary_treatment, float sigma_v,
+                   float sigma_x, float sigma_y, const bgm_bnn_net_desc* g_net,
+                   const bgm_bnn_net_desc* f_net, const bgm_bnn_net_desc* h_net);
+void bgm_bnn_destroy(bgm_bnn* m);
+/* shared-memory bytes per CTA, rows per CTA, multiply-adds per row per log-posterior evaluation
+ * (2 x the deterministic count: loc and perturbation products). */
+int bgm_bnn_info(const bgm_bnn* m, int* smem_bytes, int* rows_per_cta, long long* macs_per_eval);
+/* Number of doubles of scratch (per-CTA partial sums of the batch statistics) the calls below
+ * need for n rows; -1 on a bad argument. */
+long long bgm_bnn_scratch_doubles(const bgm_bnn* m, int n);
+
+/* CausalBGM.get_log_posterior (causalbgm/base.py:765-817) with Bayesian nets: ONE call of each
+ * net on the batch of n rows -- batch statistics over these n rows, Flipout noise from the Philox
+ * streams (seed, slice, call) (csrc/bnn.cuh; restated in oracle/bnn.py).  v_dev: (n, ldv),
+ * ldv % 4 == 0, 16-byte aligned; z_dev: (n, zd). */
+int bgm_bnn_logpost(const bgm_bnn* m, const float* x_dev, const float* y_dev, const float* v_dev, int ldv,
+                    const float* z_dev, int n, uint64_t seed, int slice, int64_t row_offset, uint32_t call,
+                    double* scratch_dev, float* out_logp_dev, void* stream);
+
+/* CausalBGM.metropolis_hastings_sampler (:820-904) with Bayesian nets: iterations
+ * [t_begin, t_end) over the n rows of ONE `bs` slice (they share batch statistics): one launch per
+ * iteration; proposal and current state are BOTH evaluated every iteration with fresh network
+ * noise (call ids 2t, 2t+1) like :865-866.  Uses the fields of bgm_mh_args except vproj_dev,
+ * r0_dev, sched_dev and lp_state_dev; init_mode 0/1: z_state_dev given, 2: z0 ~ N(0,1).
+ * lp_trace_dev receives the proposals' log-posteriors, lp_cur_trace_dev (T,n; may be NULL) the
+ * current states'.  `slice` keys the kernel-perturbation stream (slices are independent runs). */
+int bgm_bnn_mh(const bgm_bnn* m, const bgm_mh_args* args, int slice, double* scratch_dev,
+               float* lp_cur_trace_dev, void* stream);
+
+/* CausalBGM.infer_from_latent_posterior (:671-763) with a Bayesian f_net: one f_net call per
+ * (kept state s, dose j) on the n rows of state s (call id s*n_x + j; batch statistics of z0, z1
+ * over those rows; the tiled dose column has batch variance 0 and normalises to beta exactly as in
+ * the reference).  Arguments as bgm_causal_effect; stats_scratch_dev: n_keep * 2 * (z0+z1) floats. */
+int bgm_bnn_effect(const bgm_bnn* m, const float* z_samples_dev, int n_keep, int n, const float* x_values_dev,
+                   int n_x, int sample_y, uint64_t seed, int64_t row_offset, const float* noise_dev,
+                   float* stats_scratch_dev, double* adrf_sum_dev, float* ite_dev, void* stream);
+
+/* Test hook: the Flipout noise of (net 0 g / 1 f / 2 h, layer, call) exactly as the kernels draw
+ * it: eps_dev (K, N) unit normals, sign_in_dev (rows, K), sign_out_dev (rows, N) as +-1 int8 for
+ * global rows row_offset + [0, rows); any pointer may be NULL. */
+int bgm_bnn_noise(const bgm_bnn* m, uint64_t seed, int slice, int net, int layer, uint32_t call,
+                  int64_t row_offset, int rows, float* eps_dev, signed char* sign_in_dev,
+                  signed char* sign_out_dev, void* stream);
+
 /* --------------------------------------------------------------- BGM / HMC -- */
 /* The generator of BGM, `BaseVariationalNet` (networks/base.py:53-117), in
  * inference mode as bgm/base.py:679 calls it: BatchNormalization on z with its
@@ -401,6 +465,31 @@ int bgm_bgm_iter_latent(bgm_trainer* t, float* zt_dev, const float* x_dev, const
                         float* loss_dev, float* gz_out_dev, void* stream);
 int bgm_bgm_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, int n, double* sum_dev,
                      void* stream);
+
+/* ---- host-side index / prior streams (no device work) ----
+ * NumPy's LEGACY generator (MT19937 `RandomState`) restated natively so that the mini-batch index
+ * and prior streams of the training loops are produced bit-exactly off the Python thread:
+ * `np.random.choice(n, bs, replace=False)` (causalbgm/base.py:406,:413; a full permutation of n per
+ * call), `np.random.normal` (`Gaussian_sampler.get_batch`, prior_samplers.py:46-59) and
+ * `np.random.rand`.  The state is exactly `np.random.get_state()`: key[624], pos, has_gauss,
+ * cached_gaussian, and is written back with `np.random.set_state()` by the caller. */
+typedef struct {
+  uint32_t key[624];
+  int pos;
+  int has_gauss;
+  double gauss;
+} bgm_mt19937_state;
+/* out[size] = np.random.choice(n, size, replace=False); work: n int32 of scratch. */
+int bgm_host_choice(bgm_mt19937_state* st, int n, int size, int32_t* out, int32_t* work);
+/* out[count] = np.random.normal(loc, scale, count).astype(float32) */
+int bgm_host_normal(bgm_mt19937_state* st, double loc, double scale, long long count, float* out);
+/* out[count] = np.random.rand(count) */
+int bgm_host_rand(bgm_mt19937_state* st, long long count, double* out);
+/* `iters` iterations of egm_init's draws in the reference's order (:405-413): g_d_freq x [choice,
+ * get_batch], then [get_batch, choice].  idx_out: (iters, g_d_freq+1, bs) int32,
+ * z_out: (iters, g_d_freq+1, bs, zd) float32; work: n int32. */
+int bgm_host_egm_stream(bgm_mt19937_state* st, int n, int bs, int zd, int g_d_freq, int iters, int32_t* idx_out,
+                        float* z_out, int32_t* work);
 
 /* dst[r][:] = src[idx[r]][:dim] -- mini-batch gather from device-resident data (:406-416). */
 int bgm_gather_rows(const float* src_dev, int ld, const int* idx_dev, int bs, int dim, float* dst_dev,
