@@ -448,37 +448,55 @@ class BGM(object):
         if verbose:
             print(f"TFP MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
         zs = r['samples']
+        return self._predictive_reduce(zs, data_np, miss, n, xd, int(n_mcmc), alpha, return_samples, bs, seed,
+                                       row_offset)
+
+    def _predictive_reduce(self, zs, data_np, miss, n, xd, n_mcmc, alpha, return_samples, bs, seed, row_offset):
+        """bgm/base.py:603-663 on the device: posterior-predictive draws for every kept state, their mean
+        (imputation) and the alpha/2, 1-alpha/2 quantiles of the missing entries.  The reference loops over
+        `bs`-row slices on the host and concatenates (n_mcmc, n, x_dim) draws; here the rows are processed in
+        chunks sized to a memory budget (the Philox noise is keyed by the global row, so the chunking does not
+        change any draw), each chunk is reduced on the device with ONE sort, and the results come back in one
+        device-to-host copy at the end.  `bs` only sets the chunk granularity."""
+        torch = _lib.require_cuda()
         same_pattern = bool(np.all(miss == miss[0]))                               # :622-623
         miss_idx = np.where(miss[0])[0]
         bs = max(1, int(bs))
-        imputed = np.empty((n, xd), np.float32)
+        free = torch.cuda.mem_get_info()[0]
+        per_row = 4.0 * n_mcmc * xd * 3.2            # draws + sorted copy + temporaries
+        rows = max(bs, int(min(12e9, 0.3 * free) // per_row) // bs * bs)
+        q_lo, q_hi = alpha / 2.0, 1.0 - alpha / 2.0
+
+        def q_pair(srt):
+            out = []
+            for q in (q_lo, q_hi):
+                pos = q * (srt.shape[0] - 1)
+                lo = int(np.floor(pos))
+                hi = min(lo + 1, srt.shape[0] - 1)
+                out.append(srt[lo] + (srt[hi] - srt[lo]) * float(pos - lo))
+            return out
+        imputed_d = torch.empty((n, xd), dtype=torch.float32, device='cuda')
+        k_cols = miss_idx.size if same_pattern else xd
+        lo_d = torch.empty((n, k_cols), dtype=torch.float32, device='cuda')
+        up_d = torch.empty((n, k_cols), dtype=torch.float32, device='cuda')
+        midx_d = torch.from_numpy(miss_idx).cuda() if same_pattern and miss_idx.size else None
         all_draws = [] if return_samples else None
-        lowers, uppers = [], []
-        miss_dev = torch.from_numpy(miss).cuda()
-        for i in range(0, n, bs):                                                  # :607-612
-            j = min(i + bs, n)
+        for i in range(0, n, rows):                                                # :607-612
+            j = min(i + rows, n)
             zb = zs[:, i:j, :].contiguous()
-            draws = self._predict_device(zb, int(n_mcmc), j - i, seed, row_offset=row_offset + i)
+            draws = self._predict_device(zb, n_mcmc, j - i, seed, row_offset=row_offset + i)
             if return_samples:
                 all_draws.append(draws.cpu().numpy())
-            imputed[i:j] = draws.mean(dim=0).cpu().numpy()                         # :660
-            if same_pattern:
-                if miss_idx.size:
-                    dim = draws[:, :, torch.from_numpy(miss_idx).cuda()]
-                    lowers.append(quantile_dim0(torch, dim, alpha / 2.0).cpu().numpy())
-                    uppers.append(quantile_dim0(torch, dim, 1.0 - alpha / 2.0).cpu().numpy())
-            else:
-                lo = quantile_dim0(torch, draws, alpha / 2.0).cpu().numpy()
-                up = quantile_dim0(torch, draws, 1.0 - alpha / 2.0).cpu().numpy()
-                lowers.append(lo)
-                uppers.append(up)
+            imputed_d[i:j] = draws.mean(dim=0)                                     # :660
+            if k_cols:
+                part = draws[:, :, midx_d] if same_pattern else draws
+                lo_d[i:j], up_d[i:j] = q_pair(torch.sort(part, dim=0).values)
+            del draws
+        imputed = imputed_d.cpu().numpy()
+        lo, up = lo_d.cpu().numpy(), up_d.cpu().numpy()
         if same_pattern:
-            if miss_idx.size == 0:
-                pred_interval = np.zeros((n, 0, 2), dtype=np.float32)
-            else:
-                pred_interval = np.stack([np.concatenate(lowers, 0), np.concatenate(uppers, 0)], axis=-1)
+            pred_interval = np.stack([lo, up], axis=-1) if k_cols else np.zeros((n, 0, 2), dtype=np.float32)
         else:
-            lo, up = np.concatenate(lowers, 0), np.concatenate(uppers, 0)
             pred_interval = []
             for i in range(n):                                                     # :637-649
                 idx = np.where(miss[i])[0]
@@ -486,7 +504,6 @@ class BGM(object):
                     pred_interval.append(np.zeros((0, 2), dtype=np.float32))
                 else:
                     pred_interval.append(np.stack([lo[i, idx], up[i, idx]], axis=-1))
-        del miss_dev
         if return_samples:
             return np.concatenate(all_draws, axis=1), pred_interval
         obs_mask = 1.0 - miss.astype(np.float32)

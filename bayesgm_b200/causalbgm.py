@@ -220,6 +220,13 @@ class CausalBGM(object):
                     tensor_smem_bytes=smem.value, tensor_issued_macs_per_row=issued.value,
                     kernel=buf.value.decode())
 
+    def launch_smem_bytes(self):
+        """Dynamic shared memory of the sampler launch (what ncu reports as dynamic smem per block)."""
+        si = self.sampler_info()
+        if si['engine'] == 'tensor':
+            return si['tensor_smem_bytes']
+        return si['smem_bytes'] if si['engine'] == 'bnn' else self.kernel_info()['smem_bytes']
+
     def kernel_info(self):
         smem, warps, nops, proj = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         macs, issued = C.c_longlong(), C.c_longlong()
@@ -843,18 +850,30 @@ class CausalBGM(object):
         self.egm_history = []
         total = int(egm_n_iter) + 1
         it = 0
+        # NumPy's global generator is continued natively on a background thread (csrc/host_rng.cu): the
+        # reference's draw order -- g_d_freq x [choice(n, bs) :406, get_batch :407], then [get_batch :412,
+        # choice :413] -- bit-exact, `chunk` iterations per hand-over; the state goes back into np.random
+        # when the loop ends (`choice` without replacement permutes all n indices per call: at n >= 1e5 that
+        # is more host time than the training step it feeds)
+        from ._hostrng import EgmProducer
+        prod = EgmProducer(n, bs, zd, freq, total, chunk=int(chunk))
+        try:
+            self._egm_loop(prod, total, freq, bs, p, zd, xd, yd, vd, tr, st, dloss, gloss, bz, bv, bx, by, group,
+                           egm_batches_per_eval, verbose, eval_during, torch)
+        finally:
+            prod.close(drain=True)
+        if verbose:
+            print('EGM Initialization Ends.')
+        d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
+        return (float(d[0]), float(d[1])), tuple(float(a) for a in g)
+
+    def _egm_loop(self, prod, total, freq, bs, p, zd, xd, yd, vd, tr, st, dloss, gloss, bz, bv, bx, by, group,
+                  egm_batches_per_eval, verbose, eval_during, torch):
+        it = 0
         while it < total:
-            cnt = min(int(chunk), total - it)
-            idx = np.empty((cnt, freq + 1, bs), np.int32)
-            zz = np.empty((cnt, freq + 1, bs, zd), np.float32)
-            eps = np.empty((cnt, freq), np.float32)
-            for c in range(cnt):                                                  # host RNG, reference order
-                for k in range(freq):
-                    idx[c, k] = np.random.choice(n, bs, replace=False)            # :406
-                    zz[c, k] = self.z_sampler.get_batch(bs)                       # :407
-                    eps[c, k] = self._eps_rng.uniform()
-                zz[c, freq] = self.z_sampler.get_batch(bs)                        # :412
-                idx[c, freq] = np.random.choice(n, bs, replace=False)             # :413
+            idx, zz = prod.get()
+            cnt = idx.shape[0]
+            eps = self._eps_rng.uniform(size=(cnt, freq)).astype(np.float32)
             idx_d = torch.from_numpy(idx).cuda()
             zz_d = torch.from_numpy(zz).cuda()
             for c in range(cnt):
@@ -884,7 +903,3 @@ class CausalBGM(object):
                         if self._p['save_res']:
                             self._save_data('{}/causal_pre_egm_init_iter-{}.txt'.format(self.save_dir, it + c), causal_pre)
             it += cnt
-        if verbose:
-            print('EGM Initialization Ends.')
-        d, g = dloss.cpu().numpy(), gloss.cpu().numpy()
-        return (float(d[0]), float(d[1])), tuple(float(a) for a in g)

@@ -565,7 +565,13 @@ int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_a
   if (!m) return fail(BGM_ERR_ARG, "bgm_causal_sampler_info: null model");
   if (active_kind) *active_kind = use_tc(m) ? 2 : 1;
   if (tensor_available) *tensor_available = m->tc.enabled;
-  if (tensor_smem_bytes) *tensor_smem_bytes = m->tc_smem_bytes;
+  if (tensor_smem_bytes) {
+    // dynamic shared memory of the launch: weight image (+ the exchange buffers of the 16-warp kernel)
+    const int zd = m->prog.zd;
+    int smem = m->tc_smem_bytes;
+    if (m->tc16 && zd <= 12) smem += (zd <= 8 ? 2 : 1) * TC16_XCH_FLOATS * 4;
+    *tensor_smem_bytes = smem;
+  }
   if (tensor_issued_macs_per_row) *tensor_issued_macs_per_row = m->tc_issued;
   return 0;
 }

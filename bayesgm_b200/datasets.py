@@ -108,3 +108,18 @@ def acic_shaped_binary(n=20000, p=100, seed=0):
     x = (rs.uniform(size=n) < 1.0 / (1.0 + np.exp(-(v[:, 0] + v[:, 1])))).astype(np.float32)
     y = (x + v[:, 0] + 0.5 * v[:, 2] + rs.standard_normal(n)).astype(np.float32)
     return x.reshape(-1, 1), y.reshape(-1, 1), _standardize(v)
+
+
+def simulate_z_hetero(n=20000, k=3, d=20 - 1, seed=42):
+    """simulators.py:163-204 (same NumPy global-generator call order): X (n, d) = noisy low-rank
+    projection of a k-dim latent Z, Y (n,) = sin(Z w) + heteroskedastic noise."""
+    np.random.seed(seed)
+    Z = np.random.randn(n, k)
+    A = np.random.randn(d, k)
+    X = 0.2 * Z @ A.T + 0.1 * np.random.randn(n, d)
+    w = np.random.randn(k)
+    u = np.random.randn(k)
+    mean_Y = np.sin(Z @ w)
+    std_Y = 0.1 + 0.5 * 1 / (1 + np.exp(-(Z @ u)))
+    Y = mean_Y + std_Y * np.random.randn(n)
+    return X, Y

@@ -147,3 +147,24 @@ def test_hmc_small_step_accepts_and_adapts():
     assert np.mean(tr['accept']) > 0.9           # tiny steps conserve energy
     assert tr['step'][16] > tr['step'][0]        # so the shared step size grows (16 adaptation steps)
     assert tr['step'][-1] == tr['step'][17]      # and freezes after int(0.8*burn_in)
+
+
+def test_torch_cpu_restatement_matches_numpy_oracle():
+    """oracle/causal_torch.py (the multi-threaded CPU timing arm of bench.py) is the same algorithm as
+    oracle/causal.py: same log-posterior, and on the same NumPy RNG stream the same chains."""
+    import torch
+    from oracle import causal_torch
+    for binary in (False, True):
+        params = causal_params(12, [1, 2, 1, 2], binary=binary)
+        nets = causal_nets(params)
+        x, y, v = causal_data(64, 12, binary=binary)
+        z = np.random.RandomState(3).standard_normal((64, 6)).astype(np.float32)
+        want = causal.log_posterior(params, nets, x, y, v, z)
+        tn = causal_torch.to_torch_nets(nets)
+        got = causal_torch.log_posterior(params, tn, *[torch.from_numpy(a) for a in (x, y, v, z)]).numpy()
+        np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5)
+        a = causal_torch.mh_sampler(params, nets, (x, y, v), q_sd=0.4, burn_in=2, n_keep=4, rs=np.random.RandomState(9))
+        b = causal.mh_sampler(params, nets, (x, y, v), q_sd=0.4, burn_in=2, n_keep=4,
+                              noise=causal.NumpyGlobalNoise(np.random.RandomState(9)))
+        same = (a == b).all(axis=(0, 2))
+        assert same.mean() > 0.9
