@@ -873,7 +873,7 @@ class CausalBGM(object):
         while it < total:
             idx, zz = prod.get()
             cnt = idx.shape[0]
-            eps = self._eps_rng.uniform(size=(cnt, freq)).astype(np.float32)
+            eps = np.array([[self._eps_rng.uniform() for _ in range(freq)] for _ in range(cnt)], np.float32).reshape(cnt, freq)
             idx_d = torch.from_numpy(idx).cuda()
             zz_d = torch.from_numpy(zz).cuda()
             for c in range(cnt):

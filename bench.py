@@ -217,9 +217,11 @@ class Dist(object):
             dist.destroy_process_group()
 
 
-def timed_passes(D, steps, step_fn, ratio_limit=1.3):
+def timed_passes(D, steps, step_fn, ratio_limit=1.3, per_step_ms=None):
     """K steps between barriers; a pass in which one step takes > ratio_limit x the fastest one was disturbed
-    from outside (observed right after another CUDA process exits on the box) and is re-measured ONCE."""
+    from outside (observed right after another CUDA process exits on the box) and is re-measured ONCE.
+    per_step_ms(): device-side per-step times (CUDA events) for steps that return before the GPU is done;
+    default: host time per step (steps that end with their device-to-host copy)."""
     def one():
         D.barrier()
         t0 = time.perf_counter()
@@ -229,7 +231,10 @@ def timed_passes(D, steps, step_fn, ratio_limit=1.3):
             step_fn(i)
             per.append(time.perf_counter() - ts)
         D.barrier()
-        return time.perf_counter() - t0, per, t0
+        wall = time.perf_counter() - t0
+        if per_step_ms is not None:
+            per = per_step_ms()
+        return wall, per, t0
     wall, per, t0 = one()
     first = None
     if D.max(max(per) / max(min(per), 1e-9))[0] > ratio_limit:
@@ -304,7 +309,8 @@ def run_sampler(args, cfg):
         step(warm_run % max(args.steps, 1), False)
         warm_run += 1
         torch.cuda.synchronize()
-    wall, first_attempt, t0, t1 = timed_passes(D, args.steps, step)
+    wall, first_attempt, t0, t1 = timed_passes(D, args.steps, step,
+                                               per_step_ms=lambda: [a.elapsed_time(b) for a, b in zip(ev0, ev1)])
     kern_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     clk = clocks.stop(t0, t1)
     accept = float(last['r']['accept_count'].sum().item()) / (T * n)
@@ -508,7 +514,8 @@ def run_cfg5(args):
     for i in range(max(1, min(args.warmup, 2))):
         step(0, False)
         torch.cuda.synchronize()
-    wall, first, t0, t1 = timed_passes(D, args.steps, step)
+    wall, first, t0, t1 = timed_passes(D, args.steps, step,
+                                       per_step_ms=lambda: [a.elapsed_time(b) for a, b in zip(ev0, ev1)])
     kern_ms = D.max(float(np.mean([a.elapsed_time(b) for a, b in zip(ev0, ev1)])))[0]
     clk = clocks.stop(t0, t1)
     T = burn_in + n_mcmc
