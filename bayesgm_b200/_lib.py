@@ -170,6 +170,27 @@ SYMBOLS = {
                                  C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "bgm_bnn_noise": (C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int64, C.c_int,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_lt_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc),
+                                C.POINTER(DiscDesc), C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint64]),
+    "bgm_lt_destroy": (None, [C.c_void_p]),
+    "bgm_lt_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "bgm_lt_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bgm_lt_set_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bgm_lt_set_call": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "bgm_lt_disc_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_void_p,
+                                   C.c_void_p]),
+    "bgm_lt_gen_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_void_p]),
+    "bgm_lt_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "bgm_lt_set_iter": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float]),
+    "bgm_lt_iter_nets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                   C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "bgm_lt_iter_latent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p]),
+    "bgm_lt_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                  C.c_void_p, C.c_void_p]),
     "bgm_host_choice": (C.c_int, [C.POINTER(MtState), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_host_normal": (C.c_int, [C.POINTER(MtState), C.c_double, C.c_double, C.c_longlong, C.c_void_p]),
     "bgm_host_rand": (C.c_int, [C.POINTER(MtState), C.c_longlong, C.c_void_p]),

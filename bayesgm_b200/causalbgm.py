@@ -66,6 +66,9 @@ class CausalBGM(object):
         self.z_sampler = Gaussian_sampler(mean=np.zeros(zd), sd=1.0)                  # :88 (reseeds to 1024)
         self._trainer = None
         self._trainer_dirty = False      # device parameters newer than the host arrays
+        self._layered = self._bnn        # which training engine _device_trainer() builds
+        self._lt_seed = int(np.random.RandomState(random_seed).randint(1, 2 ** 31 - 1)) if random_seed is not None \
+            else 20240229
         self._eps_rng = np.random.RandomState(0 if random_seed is None else random_seed)
         if self.timestamp is None:
             self.timestamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
@@ -100,9 +103,30 @@ class CausalBGM(object):
         self._drop_handle()
         self._drop_trainer()
 
+    # Two training engines behind the same calls: the fused single-CTA kernels (csrc/train.cuh: deterministic
+    # nets, batch <= 32) and the layered engine (csrc/layered.cuh: Bayesian nets, any batch size / width).
+    _LT_NAMES = dict(bgm_trainer_destroy="bgm_lt_destroy", bgm_trainer_buffers="bgm_lt_buffers",
+                     bgm_trainer_get_params="bgm_lt_get_params", bgm_trainer_set_params="bgm_lt_set_params",
+                     bgm_train_disc_grad="bgm_lt_disc_grad", bgm_train_gen_grad="bgm_lt_gen_grad",
+                     bgm_train_adam="bgm_lt_adam", bgm_trainer_set_iter="bgm_lt_set_iter",
+                     bgm_train_iter_nets="bgm_lt_iter_nets", bgm_train_iter_latent="bgm_lt_iter_latent",
+                     bgm_causal_evaluate="bgm_lt_evaluate")
+
+    def _tfn(self, name):
+        """Symbol of the active training engine for the generic entry-point name."""
+        return self._LT_NAMES[name] if self._layered else name
+
+    def _set_layered(self, on):
+        """Chooses the training engine (Bayesian nets always train on the layered one)."""
+        on = bool(on) or self._bnn
+        if on != self._layered:
+            self._sync_from_trainer()
+            self._drop_trainer()
+            self._layered = on
+
     def _drop_trainer(self):
         if self._trainer is not None:
-            _lib.load().bgm_trainer_destroy(self._trainer)
+            getattr(_lib.load(), self._tfn("bgm_trainer_destroy"))(self._trainer)
             self._trainer = None
             self._trainer_dirty = False
 
@@ -113,9 +137,9 @@ class CausalBGM(object):
             return
         n = C.c_int()
         for group in (0, 1):
-            _lib.call("bgm_trainer_buffers", self._trainer, group, C.byref(n), None, None)
+            _lib.call(self._tfn("bgm_trainer_buffers"), self._trainer, group, C.byref(n), None, None)
             flat = np.empty(n.value, np.float32)
-            _lib.call("bgm_trainer_get_params", self._trainer, group, flat.ctypes.data_as(C.c_void_p))
+            _lib.call(self._tfn("bgm_trainer_get_params"), self._trainer, group, flat.ctypes.data_as(C.c_void_p))
             if group == 0:
                 o = 0
                 for net in (self.g_net, self.e_net, self.f_net, self.h_net):
@@ -127,10 +151,28 @@ class CausalBGM(object):
         self._trainer_dirty = False
         self._drop_handle()
 
-    def _device_trainer(self):
+    def _lt_desc(self, net):
+        """bgm_bnn_net_desc of a net for the layered engine (deterministic nets: bn = NULL)."""
         if self._bnn:
-            raise NotImplementedError("bayesgm_b200: this entry point of the single-CTA training kernels takes "
-                                      "deterministic nets; Bayesian nets train through the layered engine")
+            return net.desc()
+        dims = (C.c_int * len(net.dims))(*net.dims)
+        flat = net.flat_params()
+        d = _lib.BnnNetDesc(len(net.layers), C.cast(dims, C.POINTER(C.c_int)), None, flat.ctypes.data_as(C.POINTER(C.c_float)))
+        return d, (dims, flat)
+
+    def _device_trainer(self):
+        if self._trainer is None and self._layered:
+            _lib.require_cuda()
+            p = self._p
+            zd4 = (C.c_int * 4)(*[int(d) for d in p['z_dims']])
+            descs = [self._lt_desc(net) for net in (self.g_net, self.e_net, self.f_net, self.h_net)]
+            dd, dk = self.dz_net.desc()
+            h = C.c_void_p()
+            _lib.call("bgm_lt_create", C.byref(h), zd4, int(p['v_dim']), int(bool(p['binary_treatment'])),
+                      int(bool(p['use_z_rec'])), int(self._bnn), C.byref(descs[0][0]), C.byref(descs[1][0]),
+                      C.byref(descs[2][0]), C.byref(descs[3][0]), C.byref(dd), float(p['lr']), 0.9, 0.99,
+                      float(p['kl_weight']) if self._bnn else 0.0, int(self._lt_seed))
+            self._trainer = h
         if self._trainer is None:
             _lib.require_cuda()
             p = self._p
@@ -626,11 +668,11 @@ class CausalBGM(object):
         sums = torch.zeros(3, dtype=torch.float64, device='cuda')
         if data_z is None:
             z = torch.empty((n, zd), dtype=torch.float32, device='cuda')
-            _lib.call("bgm_causal_evaluate", tr, None, _lib.ptr(x), _lib.ptr(y), _lib.ptr(vc), n, _lib.ptr(sums),
+            _lib.call(self._tfn("bgm_causal_evaluate"), tr, None, _lib.ptr(x), _lib.ptr(y), _lib.ptr(vc), n, _lib.ptr(sums),
                       _lib.ptr(z), _lib.stream_ptr())
         else:
             z = self._to_device(data_z, torch)
-            _lib.call("bgm_causal_evaluate", tr, _lib.ptr(z), _lib.ptr(x), _lib.ptr(y), _lib.ptr(vc), n,
+            _lib.call(self._tfn("bgm_causal_evaluate"), tr, _lib.ptr(z), _lib.ptr(x), _lib.ptr(y), _lib.ptr(vc), n,
                       _lib.ptr(sums), None, _lib.stream_ptr())
         s = sums.cpu().numpy()
         mse_v, mse_x, mse_y = np.float32(s[0] / (n * p)), np.float32(s[1] / n), np.float32(s[2] / n)
@@ -658,7 +700,11 @@ class CausalBGM(object):
         p, zd = self._p['v_dim'], sum(self._p['z_dims'])
         bs = int(batch_size)
         if bs > 32:
-            raise NotImplementedError("bayesgm_b200: the training kernels take mini-batches of at most 32 rows")
+            # the fused single-CTA kernels take at most 32 rows: larger mini-batches train on the layered engine
+            if use_egm_init:
+                raise NotImplementedError("bayesgm_b200: egm_init takes mini-batches of at most 32 rows (the fused "
+                                          "gradient-penalty kernel); pass use_egm_init=False or batch_size <= 32")
+            self._set_layered(True)
         if self._p['save_res']:
             with open('{}/params.txt'.format(self.save_dir), 'w') as f_params:
                 f_params.write(str(self.params))
@@ -674,7 +720,7 @@ class CausalBGM(object):
                 print('Initialize latent variables Z with e(V)...')
             z = torch.empty((n, zd), dtype=torch.float32, device='cuda')                    # :479
             sums = torch.zeros(3, dtype=torch.float64, device='cuda')
-            _lib.call("bgm_causal_evaluate", tr, None, _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), n, _lib.ptr(sums),
+            _lib.call(self._tfn("bgm_causal_evaluate"), tr, None, _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), n, _lib.ptr(sums),
                       _lib.ptr(z), st)
         else:
             if verbose:
@@ -684,7 +730,7 @@ class CausalBGM(object):
         m_z, v_z = torch.zeros_like(z), torch.zeros_like(z)
         slot = torch.full((n,), -1, dtype=torch.int32, device='cuda')
         sig = self._sigmas()
-        _lib.call("bgm_trainer_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']), sig[0], sig[1], sig[2])
+        _lib.call(self._tfn("bgm_trainer_set_iter"), tr, float(self._p['lr_theta']), float(self._p['lr_z']), sig[0], sig[1], sig[2])
         nl = torch.zeros(6, dtype=torch.float32, device='cuda')
         zl = torch.zeros(1, dtype=torch.float32, device='cuda')
         best_loss = np.inf
@@ -697,10 +743,14 @@ class CausalBGM(object):
             for i in range(0, n, bs):
                 b = min(bs, n - i)
                 ip = C.c_void_p(base + 4 * i)
-                _lib.call("bgm_train_iter_nets", tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, 1,
+                _lib.call(self._tfn("bgm_train_iter_nets"), tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, 1,
                           1.0, _lib.ptr(nl), st)                                             # :500-502
-                _lib.call("bgm_train_iter_latent", tr, _lib.ptr(z), _lib.ptr(m_z), _lib.ptr(v_z), _lib.ptr(slot), n,
-                          _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, _lib.ptr(zl), st)     # :505
+                if self._layered:
+                    _lib.call("bgm_lt_iter_latent", tr, _lib.ptr(z), _lib.ptr(m_z), _lib.ptr(v_z), _lib.ptr(slot), n,
+                              _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, _lib.ptr(zl), None, st)
+                else:
+                    _lib.call("bgm_train_iter_latent", tr, _lib.ptr(z), _lib.ptr(m_z), _lib.ptr(v_z), _lib.ptr(slot), n,
+                              _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), ip, b, _lib.ptr(zl), st)     # :505
             self._trainer_dirty = True
             if epoch % epochs_per_eval == 0:                                                 # :517-532
                 causal_pre, mse_x, mse_y, mse_v = self.evaluate(data=(xd, yd, vd), data_z=z)
@@ -735,7 +785,7 @@ class CausalBGM(object):
         """torch view (no copy) of the trainer's flat gradient buffer, for all-reduce."""
         torch = _lib.require_cuda()
         n, ptr = C.c_int(), C.c_void_p()
-        _lib.call("bgm_trainer_buffers", self._device_trainer(), group, C.byref(n), None, C.byref(ptr))
+        _lib.call(self._tfn("bgm_trainer_buffers"), self._device_trainer(), group, C.byref(n), None, C.byref(ptr))
 
         class _View(object):
             __cuda_array_interface__ = dict(shape=(n.value,), typestr='<f4', data=(ptr.value, False), version=2)
@@ -747,7 +797,7 @@ class CausalBGM(object):
             import torch.distributed as dist
             dist.all_reduce(self._grad_tensor(group_id), group=dist_group)
             scale = 1.0 / dist.get_world_size(dist_group)
-        _lib.call("bgm_train_adam", self._device_trainer(), group_id, float(scale), _lib.stream_ptr())
+        _lib.call(self._tfn("bgm_train_adam"), self._device_trainer(), group_id, float(scale), _lib.stream_ptr())
         self._trainer_dirty = True
 
     def gradients(self, which, data_z, data_v, data_x=None, data_y=None, epsilon=0.5):
@@ -758,15 +808,68 @@ class CausalBGM(object):
         v = self._to_device(data_v, torch)
         if which == 'disc':
             losses = torch.empty(2, dtype=torch.float32, device='cuda')
-            _lib.call("bgm_train_disc_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), z.shape[0],
+            _lib.call(self._tfn("bgm_train_disc_grad"), self._device_trainer(), _lib.ptr(z), _lib.ptr(v), z.shape[0],
                       float(epsilon), 10.0, _lib.ptr(losses), _lib.stream_ptr())
             return losses.cpu().numpy(), self._grad_tensor(1).cpu().numpy()
         x = self._to_device(data_x, torch).reshape(-1)
         y = self._to_device(data_y, torch).reshape(-1)
         losses = torch.empty(6, dtype=torch.float32, device='cuda')
-        _lib.call("bgm_train_gen_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), _lib.ptr(x), _lib.ptr(y),
+        _lib.call(self._tfn("bgm_train_gen_grad"), self._device_trainer(), _lib.ptr(z), _lib.ptr(v), _lib.ptr(x), _lib.ptr(y),
                   z.shape[0], _lib.ptr(losses), _lib.stream_ptr())
         return losses.cpu().numpy(), self._grad_tensor(0).cpu().numpy()
+
+    def set_noise_counter(self, counter):
+        """Layered engine: the step counter that keys the network noise of the next training step
+        (call ids 16*counter + k, csrc/layered_api.cuh) -- lets tests replay a step through the oracle."""
+        self._set_layered(True)
+        _lib.call("bgm_lt_set_call", self._device_trainer(), int(counter) & 0xFFFFFFFF)
+
+    def iter_gradients(self, data_z_table, data, batch_idx):
+        """(losses[6], flat group-0 gradient) of update_g/h/f_net (:156-243) on the rows `batch_idx`,
+        WITHOUT the optimizer updates.  Test hook."""
+        torch = _lib.require_cuda()
+        data_x, data_y, data_v = data
+        z = self._to_device(data_z_table, torch).contiguous()
+        xd = self._to_device(data_x, torch).reshape(-1).contiguous()
+        yd = self._to_device(data_y, torch).reshape(-1).contiguous()
+        vd = self._to_device(data_v, torch).contiguous()
+        idx = torch.from_numpy(np.asarray(batch_idx, np.int32)).cuda()
+        tr = self._device_trainer()
+        sig = self._sigmas()
+        if not getattr(self, '_iter_ready', None) is tr:
+            _lib.call(self._tfn("bgm_trainer_set_iter"), tr, float(self._p['lr_theta']), float(self._p['lr_z']), sig[0],
+                      sig[1], sig[2])
+            self._iter_ready = tr
+        nl = torch.zeros(6, dtype=torch.float32, device='cuda')
+        _lib.call(self._tfn("bgm_train_iter_nets"), tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(yd), _lib.ptr(vd), _lib.ptr(idx),
+                  len(batch_idx), 0, 1.0, _lib.ptr(nl), _lib.stream_ptr())
+        return nl.cpu().numpy(), self._grad_tensor(0).cpu().numpy()
+
+    def latent_step(self, data_z_table, data, batch_idx):
+        """One update_latent_variable_sgd (:246-302) on copies of the given arrays (layered engine):
+        returns (loss_postrior_z, gradient rows (bs, zd), updated latent table).  Test hook."""
+        torch = _lib.require_cuda()
+        self._set_layered(True)
+        data_x, data_y, data_v = data
+        z = self._to_device(data_z_table, torch).contiguous().clone()
+        n, zd = z.shape
+        xd = self._to_device(data_x, torch).reshape(-1).contiguous()
+        yd = self._to_device(data_y, torch).reshape(-1).contiguous()
+        vd = self._to_device(data_v, torch).contiguous()
+        idx = torch.from_numpy(np.asarray(batch_idx, np.int32)).cuda()
+        tr = self._device_trainer()
+        sig = self._sigmas()
+        if not getattr(self, '_iter_ready', None) is tr:
+            _lib.call("bgm_lt_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']), sig[0], sig[1], sig[2])
+            self._iter_ready = tr
+        m_z, v_z = torch.zeros_like(z), torch.zeros_like(z)
+        slot = torch.full((n,), -1, dtype=torch.int32, device='cuda')
+        zl = torch.zeros(1, dtype=torch.float32, device='cuda')
+        gz = torch.zeros((len(batch_idx), zd), dtype=torch.float32, device='cuda')
+        _lib.call("bgm_lt_iter_latent", tr, _lib.ptr(z), _lib.ptr(m_z), _lib.ptr(v_z), _lib.ptr(slot), n, _lib.ptr(xd),
+                  _lib.ptr(yd), _lib.ptr(vd), _lib.ptr(idx), len(batch_idx), _lib.ptr(zl), _lib.ptr(gz), _lib.stream_ptr())
+        assert int((slot != -1).sum().item()) == 0
+        return float(zl.cpu()[0]), gz.cpu().numpy(), z.cpu().numpy()
 
     def get_weights(self):
         """dict of Keras-layout weight lists of g, e, f, h and dz (trainable_variables order)."""
@@ -798,7 +901,7 @@ class CausalBGM(object):
         if epsilon is None:
             epsilon = float(self._eps_rng.uniform())
         losses = torch.empty(2, dtype=torch.float32, device='cuda')
-        _lib.call("bgm_train_disc_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), bs, float(epsilon), 10.0,
+        _lib.call(self._tfn("bgm_train_disc_grad"), self._device_trainer(), _lib.ptr(z), _lib.ptr(v), bs, float(epsilon), 10.0,
                   _lib.ptr(losses), _lib.stream_ptr())
         self._apply(1, group)
         l = losses.cpu().numpy()
@@ -812,7 +915,7 @@ class CausalBGM(object):
         x = self._to_device(data_x, torch).reshape(-1)
         y = self._to_device(data_y, torch).reshape(-1)
         losses = torch.empty(6, dtype=torch.float32, device='cuda')
-        _lib.call("bgm_train_gen_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(v), _lib.ptr(x), _lib.ptr(y),
+        _lib.call(self._tfn("bgm_train_gen_grad"), self._device_trainer(), _lib.ptr(z), _lib.ptr(v), _lib.ptr(x), _lib.ptr(y),
                   z.shape[0], _lib.ptr(losses), _lib.stream_ptr())
         self._apply(0, group)
         return tuple(float(a) for a in losses.cpu().numpy())
@@ -880,14 +983,14 @@ class CausalBGM(object):
                 for k in range(freq):
                     ip = C.c_void_p(idx_d[c, k].data_ptr())
                     _lib.call("bgm_gather_rows", _lib.ptr(vd), p, ip, bs, p, _lib.ptr(bv), st)
-                    _lib.call("bgm_train_disc_grad", tr, C.c_void_p(zz_d[c, k].data_ptr()), _lib.ptr(bv), bs,
+                    _lib.call(self._tfn("bgm_train_disc_grad"), tr, C.c_void_p(zz_d[c, k].data_ptr()), _lib.ptr(bv), bs,
                               float(eps[c, k]), 10.0, _lib.ptr(dloss), st)
                     self._apply(1, group)
                 ip = C.c_void_p(idx_d[c, freq].data_ptr())
                 _lib.call("bgm_gather_rows", _lib.ptr(vd), p, ip, bs, p, _lib.ptr(bv), st)
                 _lib.call("bgm_gather_rows", _lib.ptr(xd), 1, ip, bs, 1, _lib.ptr(bx), st)
                 _lib.call("bgm_gather_rows", _lib.ptr(yd), 1, ip, bs, 1, _lib.ptr(by), st)
-                _lib.call("bgm_train_gen_grad", tr, C.c_void_p(zz_d[c, freq].data_ptr()), _lib.ptr(bv), _lib.ptr(bx),
+                _lib.call(self._tfn("bgm_train_gen_grad"), tr, C.c_void_p(zz_d[c, freq].data_ptr()), _lib.ptr(bv), _lib.ptr(bx),
                           _lib.ptr(by), bs, _lib.ptr(gloss), st)
                 self._apply(0, group)
                 if (it + c) % egm_batches_per_eval == 0:                                     # :418-430

@@ -29,7 +29,7 @@
 //         j = net<<8 | layer<<4 | blk): s_in[k] = bit k, s_out[c] = bit K+c, set = -1
 //   call  = 2t (proposal) / 2t+1 (current state) in the sampler; s*n_x + j in the effect kernel.
 #pragma once
-#include "common.cuh"
+#include "bnn_noise.cuh"
 
 namespace bgm {
 namespace bnn {
@@ -37,8 +37,6 @@ namespace bnn {
 constexpr int BNN_THREADS = 256;
 constexpr int BNN_MAXL = 8;
 constexpr int BNN_MAXK = 64;
-constexpr uint32_t NOISE_BNN_W = 5, NOISE_BNN_SIGN = 6;
-enum { NET_G = 0, NET_F = 1, NET_H = 2, NET_E = 3 };
 
 struct BnnLayer {
   int K, N, N32;                       // in, out, out padded to a multiple of 32
@@ -60,23 +58,6 @@ constexpr int W_FLOATS = BNN_MAXK * 32;                     // one weight chunk 
 
 __device__ __forceinline__ float flip(float a, uint32_t bit) {
   return __uint_as_float(__float_as_uint(a) ^ (bit << 31));
-}
-
-// 32 sign bits starting at bit `o` of the (net, layer) sign stream of this row / call
-__device__ __forceinline__ uint32_t sign_bits32(uint64_t seed, int64_t grow, uint32_t call, int net_id, int l, int o) {
-  const int w0 = o >> 5, sh = o & 31;
-  const uint32_t jb = ((uint32_t)net_id << 8) | ((uint32_t)l << 4);
-  const uint4 b0 = noise_block(seed, grow, call, NOISE_BNN_SIGN, jb | (uint32_t)(w0 >> 2));
-  const int i0 = w0 & 3;
-  const uint32_t lo = i0 == 0 ? b0.x : (i0 == 1 ? b0.y : (i0 == 2 ? b0.z : b0.w));
-  if (sh == 0) return lo;
-  uint32_t hi;
-  if (i0 < 3) {
-    hi = i0 == 0 ? b0.y : (i0 == 1 ? b0.z : b0.w);
-  } else {
-    hi = noise_block(seed, grow, call, NOISE_BNN_SIGN, jb | (uint32_t)((w0 + 1) >> 2)).x;
-  }
-  return (lo >> sh) | (hi << (32 - sh));
 }
 
 // CTA-wide: loc and dW = sigma * eps of output columns [32c, 32c+32) of a layer -> Wl / Wd [K][32]

@@ -14,7 +14,7 @@
 // workspace as dW (K,N) and int8 sign matrices, so forward, input-backward and parameter-backward
 // read the same draw.
 #pragma once
-#include "bnn.cuh"
+#include "bnn_noise.cuh"
 
 namespace bgm {
 namespace lt {
@@ -371,7 +371,6 @@ __global__ void nll_loss_kernel(const NllArgs A) {
       const float l = mu[0], xv = t[0];
       loss += (fmaxf(l, 0.f) - l * xv + log1pf(expf(-fabsf(l)))) * invB;
       const float pr = sigmoid_l(l);
-      mse += (xv - pr) * (xv - pr) * 0.f;          // loss_mse of the binary branch is the CE itself (:198-199)
       dmu[0] = (pr - xv) * invB;
       continue;
     }
@@ -428,6 +427,23 @@ __global__ void latent_adam_kernel(float* __restrict__ z, float* __restrict__ m,
 }
 __global__ void set_slots_kernel(int* __restrict__ slot, const int* __restrict__ idx, int B, int value_is_pos) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) slot[idx[b]] = value_is_pos ? b : -1;
+}
+
+// prior of update_latent_variable_sgd (:291-292): loss += sum(z^2) / (2B); z (n values, in place) -> z / B
+__global__ void prior_scale_kernel(float* __restrict__ z, int n, float invB, float* __restrict__ loss) {
+  __shared__ float red[8];
+  float part = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = z[i];
+    part = fmaf(v, v, part);
+    z[i] = v * invB;
+  }
+  part = block_sum(part, red);
+  if (threadIdx.x == 0) loss[0] += 0.5f * part * invB;
+}
+// loss_postrior_z = loss_pv_z + loss_px_z + loss_py_zx + loss_prior_z (:294)
+__global__ void sum_losses_kernel(const float* __restrict__ l, float* __restrict__ out) {
+  if (threadIdx.x == 0) out[0] = ((l[0] + l[2]) + l[4]) + l[6];
 }
 
 // sum over rows and columns of (T - P[:, :D])^2 -> float64 accumulator

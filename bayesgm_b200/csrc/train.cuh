@@ -66,6 +66,7 @@ struct DiscArgs {
   float gp_weight;           // 10 (:323)
   float* losses;             // [2]: dz_loss, d_loss
   int wm;
+  const float* zenc_in;      // optional (bs, zd): z_ = e_net(v) computed elsewhere (Bayesian e_net, layered engine)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -715,11 +716,12 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
   const float* th_s = A.theta_d;
   float* gacc = A.grad_d;
   for (int i = threadIdx.x; i < dz.n_params; i += NTH) gacc[i] = 0.f;
-  load_cols(A.v, A.p, 0, A.p, bs, bufA);
+  if (A.zenc_in) load_cols(A.zenc_in, A.zd, 0, A.zd, bs, bufA);
+  else load_cols(A.v, A.p, 0, A.p, bs, bufA);
   load_cols(A.z, A.zd, 0, A.zd, bs, zmat);
   __syncthreads();
   // z_ = e_net(v)   (:310; no gradient flows to e_net here)
-  float* ze = mlp_forward(A.e, A.theta, bufA, bufA, bufB, nullptr);
+  float* ze = A.zenc_in ? bufA : mlp_forward(A.e, A.theta, bufA, bufA, bufB, nullptr);
   const float inv_bs = 1.f / (float)bs;
   for (int i = threadIdx.x; i < A.zd * 32; i += NTH) {
     const int d = i >> 5, r = i & 31;

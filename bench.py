@@ -159,7 +159,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    iters = 10
+    iters = 30
     data = make_data(0)
     for _ in range(args.warmup):
         cpu_reference_rate(1, data, warm=0)
@@ -346,7 +346,7 @@ def run_sampler(args, cfg):
             traffic = json.load(open(tpath)).get("causal_mh_tc_kernel_dram_bytes_per_launch" if tensor
                                                  else "causal_mh_kernel_dram_bytes_per_launch")
         if world == 1:
-            cpu_iters = 10
+            cpu_iters = 100
             if bnn:
                 cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": "see the cfg3 line (deterministic nets); the Bayesian-net CPU oracle is NumPy, single-threaded"}

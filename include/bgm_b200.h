@@ -466,6 +466,43 @@ int bgm_bgm_iter_latent(bgm_trainer* t, float* zt_dev, const float* x_dev, const
 int bgm_bgm_evaluate(bgm_trainer* t, const float* zt_dev, const float* x_dev, int n, double* sum_dev,
                      void* stream);
 
+/* ---- layered training engine: the same training steps for BAYESIAN nets, any batch size, any width ----
+ * The single-CTA kernels above fuse a whole step but take deterministic nets, batches <= 32 and widths that fit
+ * one SM's shared memory.  bgm_lt_* runs the steps of CausalBGM (train_disc_step / train_gen_step
+ * causalbgm/base.py:305-377, update_g/h/f_net :156-243, update_latent_variable_sgd :246-302, evaluate :534-556)
+ * as a sequence of per-layer kernels (csrc/layered.cuh): Dense / DenseFlipout forward, input- and parameter-
+ * backward, BatchNormalization on batch statistics forward / backward, the losses, Keras Adam.  Nets are
+ * described by bgm_bnn_net_desc; bayes == 0: deterministic Dense stacks (bn == NULL, params = kernel, bias per
+ * layer).  Parameter group 0 = g | e | f | h, each in Keras trainable_variables order (gamma, beta, then loc, rho,
+ * bias per DenseFlipout layer); group 1 = dz_net.  Network noise: Philox (seed; call id 16*counter + k, see
+ * bgm_lt_set_call; signs keyed by the row's position in the batch), restated in oracle/train_bnn.py.
+ * The gradient-penalty step (bgm_lt_disc_grad) reuses the fused discriminator kernel and keeps its batch <= 32
+ * limit; every other step takes any batch size.  The workspace grows (cudaMalloc) when a larger batch arrives. */
+typedef struct bgm_lt bgm_lt;
+int bgm_lt_create(bgm_lt** out, const int z_dims[4], int v_dim, int binary_treatment, int use_z_rec, int bayes,
+                  const bgm_bnn_net_desc* g_net, const bgm_bnn_net_desc* e_net, const bgm_bnn_net_desc* f_net,
+                  const bgm_bnn_net_desc* h_net, const bgm_disc_desc* dz_net, float lr, float beta_1, float beta_2,
+                  float kl_weight, uint64_t seed);
+void bgm_lt_destroy(bgm_lt* t);
+int bgm_lt_buffers(bgm_lt* t, int group, int* n_params, float** theta_dev, float** grad_dev);
+int bgm_lt_get_params(bgm_lt* t, int group, float* host_out);
+int bgm_lt_set_params(bgm_lt* t, int group, const float* host_in);
+/* Sets the step counter that keys the network noise of the next step (every step increments it). */
+int bgm_lt_set_call(bgm_lt* t, uint32_t call_counter);
+int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, float epsilon, float gp_weight,
+                     float* losses_dev, void* stream);
+int bgm_lt_gen_grad(bgm_lt* t, const float* z_dev, const float* v_dev, const float* x_dev, const float* y_dev, int bs,
+                    float* losses_dev, void* stream);
+int bgm_lt_adam(bgm_lt* t, int group, float grad_scale, void* stream);
+int bgm_lt_set_iter(bgm_lt* t, float lr_theta, float lr_z, float sigma_v, float sigma_x, float sigma_y);
+int bgm_lt_iter_nets(bgm_lt* t, const float* zt_dev, const float* x_dev, const float* y_dev, const float* v_dev,
+                     const int* idx_dev, int bs, int apply, float grad_scale, float* losses_dev, void* stream);
+int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev, int* slot_dev, long long n,
+                       const float* x_dev, const float* y_dev, const float* v_dev, const int* idx_dev, int bs,
+                       float* loss_dev, float* gz_out_dev, void* stream);
+int bgm_lt_evaluate(bgm_lt* t, const float* zt_dev, const float* x_dev, const float* y_dev, const float* v_dev, int n,
+                    double* sums_dev, float* z_out_dev, void* stream);
+
 /* ---- host-side index / prior streams (no device work) ----
  * NumPy's LEGACY generator (MT19937 `RandomState`) restated natively so that the mini-batch index
  * and prior streams of the training loops are produced bit-exactly off the Python thread:

@@ -1,0 +1,156 @@
+"""GPU parity of the layered training engine (csrc/layered.cuh): CausalBGM's training steps on Bayesian nets
+(DenseFlipout + batch-statistics BatchNorm) against torch autograd over the same Philox noise
+(oracle/train_bnn.py), and on deterministic nets (any batch size) against oracle/train.py."""
+import numpy as np
+import pytest
+
+from oracle import train as otrain
+from oracle import train_bnn as obt
+from helpers import causal_params, causal_nets, causal_data, product_model
+from test_bnn_gpu import bnn_case, product as bnn_product
+
+pytestmark = pytest.mark.gpu
+
+
+def flat_bnn(grads, order='gefh'):
+    return np.concatenate([a.ravel() for k in order for a in grads[k]])
+
+
+def close(got, want, rtol=2e-3, what=""):
+    scale = max(np.abs(want).max(), 1e-6)
+    err = np.abs(got - want).max() / scale
+    assert err < rtol, (what, err, np.abs(want).max())
+
+
+def per_tensor_close(flat_got, grad_lists, order, rtol=3e-3):
+    o = 0
+    for k in order:
+        for i, w in enumerate(grad_lists[k]):
+            g = flat_got[o:o + w.size].reshape(w.shape)
+            o += w.size
+            scale = max(np.abs(w).max(), 1e-5)
+            err = np.abs(g - w).max() / scale
+            assert err < rtol, (k, i, err, np.abs(w).max())
+    assert o == flat_got.size
+
+
+BNN_CASES = [dict(v_dim=200, z_dims=[1, 1, 1, 7]), dict(v_dim=100, z_dims=[3, 6, 3, 6], binary=True),
+             dict(v_dim=37, z_dims=[2, 1, 2, 4], g_units=(20, 12), f_units=(9, 5), h_units=(33, 8))]
+
+
+def make_model(case, seed=77):
+    params, nets = bnn_case(**case)
+    m = bnn_product(params, nets)
+    m._lt_seed = seed
+    return params, nets, m
+
+
+@pytest.mark.parametrize("case", BNN_CASES)
+@pytest.mark.parametrize("bs", [32, 7, 80])
+def test_bnn_gen_step_gradients(case, bs):
+    params, nets, m = make_model(case)
+    x, y, v = causal_data(bs, params['v_dim'], binary=params['binary_treatment'])
+    z = np.random.RandomState(1).standard_normal((bs, sum(params['z_dims']))).astype(np.float32)
+    m.set_noise_counter(5)
+    losses, flat = m.gradients('gen', z, v, x, y)
+    wl, wg = obt.gen_step(params, nets, m.dz_net.as_oracle_params(), z, v, x, y, seed=77, ctr=5)
+    np.testing.assert_allclose(losses, wl, rtol=3e-4, atol=1e-5)
+    per_tensor_close(flat, wg, 'gefh')
+
+
+@pytest.mark.parametrize("case", BNN_CASES[:2])
+def test_bnn_disc_step_gradients(case):
+    params, nets, m = make_model(case)
+    bs = 32
+    x, y, v = causal_data(bs, params['v_dim'], binary=params['binary_treatment'])
+    z = np.random.RandomState(2).standard_normal((bs, sum(params['z_dims']))).astype(np.float32)
+    m.set_noise_counter(9)
+    losses, flat = m.gradients('disc', z, v, epsilon=0.37)
+    dzl, dl, grads = obt.disc_step(params, nets, m.dz_net.as_oracle_params(), z, v, 0.37, seed=77, ctr=9)
+    np.testing.assert_allclose(losses, [dzl, dl], rtol=5e-4, atol=1e-5)
+    want = np.concatenate([g.ravel() for g in grads])
+    close(flat, want, 3e-3, "disc gradient")
+
+
+@pytest.mark.parametrize("case", BNN_CASES)
+def test_bnn_iterative_steps(case):
+    params, nets, m = make_model(case)
+    n, bs = 300, 32
+    zd = sum(params['z_dims'])
+    x, y, v = causal_data(n, params['v_dim'], binary=params['binary_treatment'])
+    rs = np.random.RandomState(4)
+    zt = rs.standard_normal((n, zd)).astype(np.float32)
+    idx = rs.choice(n, bs, replace=False)
+    m.set_noise_counter(3)
+    losses, flat = m.iter_gradients(zt, (x, y, v), idx)
+    wl, wg = obt.iter_nets_step(params, nets, zt[idx], x[idx], y[idx], v[idx], seed=77, ctr=3)
+    np.testing.assert_allclose(losses, wl, rtol=5e-4, atol=1e-5)
+    # group 0 = g | e | f | h: e has no gradient in this phase
+    wg['e'] = [np.zeros(tuple(a.shape), np.float32) for a in obt.param_list(obt.net_to_t(nets['e'], False))]
+    per_tensor_close(flat, wg, 'gefh')
+    # latent step
+    m.set_noise_counter(4)
+    loss, gz, z_new = m.latent_step(zt, (x, y, v), idx)
+    wloss, wgz = obt.latent_step(params, nets, zt[idx], x[idx], y[idx], v[idx], seed=77, ctr=4)
+    assert abs(loss - wloss) < 5e-4 * max(1.0, abs(wloss))
+    close(gz, wgz, 3e-3, "latent gradient")
+    # Keras Adam on the gathered variable: first step moves the batch rows by lr * sign(g), the others not at all
+    lr = params['lr_z']
+    moved = z_new - zt
+    others = np.setdiff1d(np.arange(n), idx)
+    assert np.abs(moved[others]).max() == 0.0
+    big = np.abs(wgz) > 1e-4
+    np.testing.assert_allclose(moved[idx][big], (-lr * np.sign(wgz))[big], rtol=2e-2)
+
+
+def test_bnn_evaluate_matches_oracle_across_chunks():
+    params, nets, m = make_model(BNN_CASES[0])
+    n = 17000                                   # > one 16384-row chunk
+    x, y, v = causal_data(n, params['v_dim'])
+    m.set_noise_counter(11)
+    causal_pre, mse_x, mse_y, mse_v = m.evaluate((x, y, v), nb_intervals=5)
+    wx, wy, wv, wz = obt.evaluate_mse(params, nets, (x, y, v), seed=77, ctr=11)
+    np.testing.assert_allclose([mse_x, mse_y, mse_v], [wx, wy, wv], rtol=5e-4)
+    assert causal_pre.shape == (5,) and np.isfinite(causal_pre).all()
+    zt = np.random.RandomState(0).standard_normal((n, sum(params['z_dims']))).astype(np.float32)
+    m.set_noise_counter(12)
+    _, mse_x, mse_y, mse_v = m.evaluate((x, y, v), data_z=zt, nb_intervals=3)
+    wx, wy, wv, _ = obt.evaluate_mse(params, nets, (x, y, v), seed=77, ctr=12, data_z=zt)
+    np.testing.assert_allclose([mse_x, mse_y, mse_v], [wx, wy, wv], rtol=5e-4)
+
+
+@pytest.mark.parametrize("bs", [32, 100])
+def test_deterministic_nets_on_the_layered_engine(bs):
+    """use_bnn=False through the same kernels (no Flipout, no input BN): any batch size."""
+    params = causal_params(200, [1, 1, 1, 2])
+    nets = causal_nets(params)
+    m = product_model(params, nets)
+    m._set_layered(True)
+    x, y, v = causal_data(bs, 200)
+    z = np.random.RandomState(1).standard_normal((bs, 5)).astype(np.float32)
+    losses, flat = m.gradients('gen', z, v, x, y)
+    wl, wg = otrain.gen_step(params, nets, m.dz_net.as_oracle_params(), z, v, x, y)
+    np.testing.assert_allclose(losses, wl, rtol=3e-4, atol=1e-6)
+    per_tensor_close(flat, wg, 'gefh')
+
+
+def test_bnn_fit_runs_end_to_end_on_shipped_config():
+    """src/configs/Sim_Hirano_Imbens.yaml verbatim (use_bnn: True): egm_init + iterative phase + predict."""
+    from bayesgm_b200 import CausalBGM
+    from bayesgm_b200.datasets import Sim_Hirano_Imbens_sampler
+    params = dict(dataset='Sim_Hirano_Imbens', output_dir='/tmp/bgm_b200_test', save_res=False, save_model=False,
+                  binary_treatment=False, use_bnn=True, z_dims=[1, 1, 1, 7], v_dim=200, lr_theta=0.0001, lr_z=0.0001,
+                  g_units=[64] * 5, f_units=[64, 32, 8], h_units=[64, 32, 8], kl_weight=0.0001, lr=0.0002, g_d_freq=5,
+                  use_z_rec=True, e_units=[64] * 5, dz_units=[64, 32, 8])
+    x, y, v = Sim_Hirano_Imbens_sampler(N=640, v_dim=200).load_all()
+    m = CausalBGM(params=params, random_seed=3)
+    w0 = m.get_weights()
+    m.fit(data=(x, y, v), epochs=1, epochs_per_eval=1, use_egm_init=True, egm_n_iter=30, egm_batches_per_eval=10, verbose=0)
+    w1 = m.get_weights()
+    for k in ('g', 'e', 'f', 'h', 'dz'):
+        assert any(np.abs(a - b).max() > 0 for a, b in zip(w0[k], w1[k])), k
+        assert all(np.isfinite(a).all() for a in w1[k])
+    assert m.data_z.shape == (640, 10) and np.isfinite(m.data_z).all()
+    assert len(m.egm_history) == 4 and all(np.isfinite(h[1:]).all() for h in m.egm_history)
+    adrf, interval = m.predict(data=(x, y, v), alpha=0.05, n_mcmc=10, burn_in=10, x_values=[0.5, 1.5], q_sd=1.0, bs=320, verbose=0)
+    assert np.isfinite(adrf).all() and interval.shape == (2, 2)
