@@ -191,6 +191,25 @@ SYMBOLS = {
                                      C.c_void_p]),
     "bgm_lt_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                   C.c_void_p, C.c_void_p]),
+    "bgm_ltb_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(VarNetDesc), C.POINTER(NetDesc),
+                                 C.POINTER(DiscDesc), C.POINTER(DiscDesc), C.c_float, C.c_float, C.c_float,
+                                 C.c_float, C.c_float]),
+    "bgm_ltb_destroy": (None, [C.c_void_p]),
+    "bgm_ltb_buffers": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "bgm_ltb_get_params": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "bgm_ltb_bn_moving": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "bgm_ltb_adam": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
+    "bgm_ltb_disc_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_ltb_gen_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p]),
+    "bgm_ltb_set_iter": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "bgm_ltb_iter_g": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p, C.c_void_p]),
+    "bgm_ltb_iter_latent": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
+    "bgm_ltb_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "bgm_ltb_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_host_choice": (C.c_int, [C.POINTER(MtState), C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "bgm_host_normal": (C.c_int, [C.POINTER(MtState), C.c_double, C.c_double, C.c_longlong, C.c_void_p]),
     "bgm_host_rand": (C.c_int, [C.POINTER(MtState), C.c_longlong, C.c_void_p]),

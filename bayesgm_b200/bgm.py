@@ -83,6 +83,7 @@ class BGM(object):
         self.z_sampler = Gaussian_sampler(mean=np.zeros(p['z_dim']), sd=1.0)                 # :85
         self._trainer = None
         self._trainer_dirty = False
+        self._layered = False
         self._noise_rng = np.random.RandomState(0 if random_seed is None else random_seed)
         if self.timestamp is None:
             self.timestamp = datetime.datetime.now().strftime('%Y%m%d_%H%M%S')
@@ -138,24 +139,54 @@ class BGM(object):
             got[k] = [z["%s_%d" % (k, i)] for i in range(sum(1 for name in z.files if name.startswith(k + "_")))]
         self.set_weights(**got)
 
+    # Two training engines behind the same calls (same device parameter layout): the fused single-CTA kernels
+    # (csrc/train_bgm.cuh: batch <= 32, x_dim up to ~110) and the layered engine (csrc/layered.cuh: any x_dim,
+    # any batch size, gamma == 0).
+    _LT_NAMES = dict(bgm_bgmtrainer_create="bgm_ltb_create", bgm_trainer_destroy="bgm_ltb_destroy",
+                     bgm_trainer_buffers="bgm_ltb_buffers", bgm_trainer_get_params="bgm_ltb_get_params",
+                     bgm_trainer_bn_moving="bgm_ltb_bn_moving", bgm_bgm_train_disc_grad="bgm_ltb_disc_grad",
+                     bgm_bgm_train_gen_grad="bgm_ltb_gen_grad", bgm_train_adam="bgm_ltb_adam",
+                     bgm_bgmtrainer_set_iter="bgm_ltb_set_iter", bgm_bgm_iter_g="bgm_ltb_iter_g",
+                     bgm_bgm_iter_latent="bgm_ltb_iter_latent", bgm_bgm_evaluate="bgm_ltb_evaluate")
+
+    def _tfn(self, name):
+        return self._LT_NAMES[name] if self._layered else name
+
+    def _set_layered(self, on):
+        if bool(on) != self._layered:
+            self._sync_from_trainer()
+            self._drop_trainer()
+            self._layered = bool(on)
+
     def _drop_trainer(self):
         if self._trainer is not None:
-            _lib.load().bgm_trainer_destroy(self._trainer)
+            getattr(_lib.load(), self._tfn("bgm_trainer_destroy"))(self._trainer)
             self._trainer = None
             self._trainer_dirty = False
+
+    def _create_trainer(self, layered):
+        p = self._p
+        gd, gk = self.g_net.desc()
+        ed, ek = self.e_net.desc()
+        zd_, zk = self.dz_net.desc()
+        xd_, xk = self.dx_net.desc()
+        h = C.c_void_p()
+        _lib.call("bgm_ltb_create" if layered else "bgm_bgmtrainer_create", C.byref(h), C.byref(gd), C.byref(ed),
+                  C.byref(zd_), C.byref(xd_), float(p['lr']), 0.5, 0.9, float(p['alpha']), float(p['gamma']))   # Adam betas :83-85
+        return h
 
     def _device_trainer(self):
         if self._trainer is None:
             _lib.require_cuda()
-            p = self._p
-            gd, gk = self.g_net.desc()
-            ed, ek = self.e_net.desc()
-            zd_, zk = self.dz_net.desc()
-            xd_, xk = self.dx_net.desc()
-            h = C.c_void_p()
-            _lib.call("bgm_bgmtrainer_create", C.byref(h), C.byref(gd), C.byref(ed), C.byref(zd_), C.byref(xd_),
-                      float(p['lr']), 0.5, 0.9, float(p['alpha']), float(p['gamma']))          # Adam betas :83-85
-            self._trainer = h
+            if not self._layered:
+                try:
+                    self._trainer = self._create_trainer(False)
+                except _lib.BgmError as e:
+                    if e.code != -4:          # BGM_ERR_NOMEM: x_dim too wide for one SM's shared memory
+                        raise
+                    self._layered = True
+            if self._trainer is None:
+                self._trainer = self._create_trainer(True)
         return self._trainer
 
     def _sync_from_trainer(self):
@@ -165,9 +196,9 @@ class BGM(object):
             return
         n = C.c_int()
         zd, xd = self._p['z_dim'], self._p['x_dim']
-        _lib.call("bgm_trainer_buffers", self._trainer, 0, C.byref(n), None, None)
+        _lib.call(self._tfn("bgm_trainer_buffers"), self._trainer, 0, C.byref(n), None, None)
         flat = np.empty(n.value, np.float32)
-        _lib.call("bgm_trainer_get_params", self._trainer, 0, flat.ctypes.data_as(C.c_void_p))
+        _lib.call(self._tfn("bgm_trainer_get_params"), self._trainer, 0, flat.ctypes.data_as(C.c_void_p))
         g = self.g_net
         g.bn['gamma'], g.bn['beta'] = flat[:zd].copy(), flat[zd:2 * zd].copy()
         o = 2 * zd
@@ -185,11 +216,11 @@ class BGM(object):
         g.var = [wcat[:, xd:].copy(), bcat[xd:].copy()]
         self.e_net.load_flat(flat[o:])
         mv = np.empty(2 * zd, np.float32)
-        _lib.call("bgm_trainer_bn_moving", self._trainer, mv.ctypes.data_as(C.c_void_p), 0)
+        _lib.call(self._tfn("bgm_trainer_bn_moving"), self._trainer, mv.ctypes.data_as(C.c_void_p), 0)
         g.bn['mean'], g.bn['var'] = mv[:zd].copy(), mv[zd:].copy()
-        _lib.call("bgm_trainer_buffers", self._trainer, 1, C.byref(n), None, None)
+        _lib.call(self._tfn("bgm_trainer_buffers"), self._trainer, 1, C.byref(n), None, None)
         flat = np.empty(n.value, np.float32)
-        _lib.call("bgm_trainer_get_params", self._trainer, 1, flat.ctypes.data_as(C.c_void_p))
+        _lib.call(self._tfn("bgm_trainer_get_params"), self._trainer, 1, flat.ctypes.data_as(C.c_void_p))
         k = self.dz_net.flat_params().size
         self.dz_net.load_flat(flat[:k])
         self.dx_net.load_flat(flat[k:])
@@ -511,16 +542,33 @@ class BGM(object):
         return data_imputed, pred_interval
 
     # ------------------------------------------------------------ training: fit
-    def _encode_host(self, data):
-        """e_net(data) with the current weights (NumPy fp32; used once, for `data_z_init`, :388)."""
+    def _encode_device(self, data):
+        """e_net(data) with the current weights -> device tensor (n, z_dim) (`data_z_init`, :388; the
+        `data_z=None` branch of evaluate, :452-453).  Runs on the layered engine's Dense kernels."""
+        torch = _lib.require_cuda()
+        x = self._dev(data, torch, torch.float32).contiguous()
+        n = x.shape[0]
+        z = torch.empty((n, self._p['z_dim']), dtype=torch.float32, device='cuda')
+        if self._layered and self._trainer is not None:
+            _lib.call("bgm_ltb_encode", self._trainer, _lib.ptr(x), n, _lib.ptr(z), _lib.stream_ptr())
+            return z
         self._sync_from_trainer()
-        h = np.asarray(data, np.float32)
-        L = len(self.e_net.layers)
-        for i, (W, b) in enumerate(self.e_net.layers):
-            h = h @ W + b
-            if i < L - 1:
-                h = np.where(h > 0, h, np.float32(0.2) * h).astype(np.float32)
-        return h.astype(np.float32)
+        p = dict(self._p)
+        saved_gamma = self._p['gamma']
+        self._p['gamma'] = 0.0                     # the encoder pass does not depend on it
+        try:
+            h = self._create_trainer(True)
+        finally:
+            self._p['gamma'] = saved_gamma
+        try:
+            _lib.call("bgm_ltb_encode", h, _lib.ptr(x), n, _lib.ptr(z), _lib.stream_ptr())
+            torch.cuda.synchronize()
+        finally:
+            _lib.load().bgm_ltb_destroy(h)
+        return z
+
+    def _encode_host(self, data):
+        return self._encode_device(data).cpu().numpy()
 
     def evaluate(self, data, data_z=None, use_x_sd=True, *, seed=0):
         """bgm/base.py:446-471: MSE between the data and its reconstruction from `data_z` (or from
@@ -530,10 +578,10 @@ class BGM(object):
         torch = _lib.require_cuda()
         x = self._dev(data, torch, torch.float32).contiguous()
         n = x.shape[0]
-        z = self._dev(self._encode_host(data) if data_z is None else data_z, torch, torch.float32).contiguous()
+        z = self._encode_device(data) if data_z is None else self._dev(data_z, torch, torch.float32).contiguous()
         if not use_x_sd:
             out = torch.zeros(1, dtype=torch.float64, device='cuda')
-            _lib.call("bgm_bgm_evaluate", self._device_trainer(), _lib.ptr(z), _lib.ptr(x), n, _lib.ptr(out),
+            _lib.call(self._tfn("bgm_bgm_evaluate"), self._device_trainer(), _lib.ptr(z), _lib.ptr(x), n, _lib.ptr(out),
                       _lib.stream_ptr())
             return float(out.cpu()[0]) / (n * self._p['x_dim'])
         self._sync_from_trainer()
@@ -551,7 +599,7 @@ class BGM(object):
         n = len(data)
         bs = int(batch_size)
         if bs > 32:
-            raise NotImplementedError("bayesgm_b200: the training kernels take mini-batches of at most 32 rows")
+            self._set_layered(True)      # the fused single-CTA kernels take at most 32 rows
         if self._p['save_res']:
             with open('{}/params.txt'.format(self.save_dir), 'w') as f_params:
                 f_params.write(str(self.params))
@@ -560,17 +608,17 @@ class BGM(object):
                           batch_size=batch_size, verbose=verbose)
             if verbose:
                 print('Initialize latent variables Z with e(V)...')
-            data_z_init = self._encode_host(data)                                              # :388
+            data_z_init = self._encode_device(data)                                            # :388
         else:
             if verbose:
                 print('Random initialization of latent variables Z...')
             data_z_init = np.random.normal(0, 1, size=(n, self._p['z_dim'])).astype('float32')   # :391
         xd = self._dev(data, torch, torch.float32).contiguous()
-        z = torch.from_numpy(np.ascontiguousarray(data_z_init)).cuda()
+        z = data_z_init.clone() if isinstance(data_z_init, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(data_z_init)).cuda()
         self.data_z = z
         tr = self._device_trainer()
         st = _lib.stream_ptr()
-        _lib.call("bgm_bgmtrainer_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']))
+        _lib.call(self._tfn("bgm_bgmtrainer_set_iter"), tr, float(self._p['lr_theta']), float(self._p['lr_z']))
         gl = torch.zeros(2, dtype=torch.float32, device='cuda')
         zl = torch.zeros(1, dtype=torch.float32, device='cuda')
         self.history_loss = []
@@ -582,8 +630,8 @@ class BGM(object):
             base = idx_d.data_ptr()
             for i in range(0, n - bs + 1, bs):                                                # :401
                 ip = C.c_void_p(base + 4 * i)
-                _lib.call("bgm_bgm_iter_g", tr, _lib.ptr(z), _lib.ptr(xd), ip, bs, 1, 1.0, _lib.ptr(gl), st)   # :406
-                _lib.call("bgm_bgm_iter_latent", tr, _lib.ptr(z), _lib.ptr(xd), ip, bs, _lib.ptr(zl), None, st)  # :409-413
+                _lib.call(self._tfn("bgm_bgm_iter_g"), tr, _lib.ptr(z), _lib.ptr(xd), ip, bs, 1, 1.0, _lib.ptr(gl), st)   # :406
+                _lib.call(self._tfn("bgm_bgm_iter_latent"), tr, _lib.ptr(z), _lib.ptr(xd), ip, bs, _lib.ptr(zl), None, st)  # :409-413
             self._trainer_dirty = True
             if epoch % epochs_per_eval == 0:                                                  # :425-442
                 mse_x = self.evaluate(data=xd, data_z=z)
@@ -606,7 +654,7 @@ class BGM(object):
         tr = self._device_trainer()
         st = _lib.stream_ptr()
         if not getattr(self, '_iter_ready', False) or self._trainer_epoch != id(tr):
-            _lib.call("bgm_bgmtrainer_set_iter", tr, float(self._p['lr_theta']), float(self._p['lr_z']))
+            _lib.call(self._tfn("bgm_bgmtrainer_set_iter"), tr, float(self._p['lr_theta']), float(self._p['lr_z']))
             self._iter_ready, self._trainer_epoch = True, id(tr)
         z = self._dev(data_z_table, torch, torch.float32).contiguous().clone()
         xd = self._dev(data, torch, torch.float32).contiguous()
@@ -615,9 +663,9 @@ class BGM(object):
         gl = torch.zeros(2, dtype=torch.float32, device='cuda')
         zl = torch.zeros(1, dtype=torch.float32, device='cuda')
         gz = torch.zeros((bs, self._p['z_dim']), dtype=torch.float32, device='cuda')
-        _lib.call("bgm_bgm_iter_g", tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(idx), bs, 1 if apply else 0, 1.0,
+        _lib.call(self._tfn("bgm_bgm_iter_g"), tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(idx), bs, 1 if apply else 0, 1.0,
                   _lib.ptr(gl), st)
-        _lib.call("bgm_bgm_iter_latent", tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(idx), bs, _lib.ptr(zl), _lib.ptr(gz), st)
+        _lib.call(self._tfn("bgm_bgm_iter_latent"), tr, _lib.ptr(z), _lib.ptr(xd), _lib.ptr(idx), bs, _lib.ptr(zl), _lib.ptr(gz), st)
         self._trainer_dirty = True
         g = gl.cpu().numpy()
         return (float(g[0]), float(g[1])), float(zl.cpu()[0]), gz.cpu().numpy(), z.cpu().numpy()
@@ -637,7 +685,7 @@ class BGM(object):
     def _grad_tensor(self, group):
         torch = _lib.require_cuda()
         n, ptr = C.c_int(), C.c_void_p()
-        _lib.call("bgm_trainer_buffers", self._device_trainer(), group, C.byref(n), None, C.byref(ptr))
+        _lib.call(self._tfn("bgm_trainer_buffers"), self._device_trainer(), group, C.byref(n), None, C.byref(ptr))
 
         class _View(object):
             __cuda_array_interface__ = dict(shape=(n.value,), typestr='<f4', data=(ptr.value, False), version=2)
@@ -649,15 +697,15 @@ class BGM(object):
             import torch.distributed as dist
             dist.all_reduce(self._grad_tensor(group_id), group=dist_group)
             scale = 1.0 / dist.get_world_size(dist_group)
-        _lib.call("bgm_train_adam", self._device_trainer(), group_id, float(scale), _lib.stream_ptr())
+        _lib.call(self._tfn("bgm_train_adam"), self._device_trainer(), group_id, float(scale), _lib.stream_ptr())
         self._trainer_dirty = True
 
     def _disc_call(self, z, x, eps_z, eps_x, noise, losses):
-        _lib.call("bgm_bgm_train_disc_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(x), z.shape[0],
+        _lib.call(self._tfn("bgm_bgm_train_disc_grad"), self._device_trainer(), _lib.ptr(z), _lib.ptr(x), z.shape[0],
                   float(eps_z), float(eps_x), _lib.ptr(noise), _lib.ptr(losses), _lib.stream_ptr())
 
     def _gen_call(self, z, x, n1, n2, losses):
-        _lib.call("bgm_bgm_train_gen_grad", self._device_trainer(), _lib.ptr(z), _lib.ptr(x), z.shape[0],
+        _lib.call(self._tfn("bgm_bgm_train_gen_grad"), self._device_trainer(), _lib.ptr(z), _lib.ptr(x), z.shape[0],
                   _lib.ptr(n1), _lib.ptr(n2), _lib.ptr(losses), _lib.stream_ptr())
 
     def gradients(self, which, data_z, data_x, *, eps_z=0.5, eps_x=0.5, noise=None, noise2=None):
@@ -713,6 +761,8 @@ class BGM(object):
         torch = _lib.require_cuda()
         if group is not None:
             self._offset_streams(group)
+        if int(batch_size) > 32:
+            self._set_layered(True)      # the fused single-CTA kernels take at most 32 rows
         data = np.asarray(data, dtype=np.float32)
         ds_seed = 123
         if group is not None:

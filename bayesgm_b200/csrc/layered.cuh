@@ -446,6 +446,155 @@ __global__ void sum_losses_kernel(const float* __restrict__ l, float* __restrict
   if (threadIdx.x == 0) out[0] = ((l[0] + l[2]) + l[4]) + l[6];
 }
 
+// ---------------------------------------------------------------- BGM flavour (bgm/base.py:145-291) ----
+// Keras BatchNormalization moving statistics, momentum .99 (biased batch variance = 1/inv^2 - 1e-3)
+__global__ void moving_update_kernel(float* __restrict__ moving, const float* __restrict__ mean,
+                                     const float* __restrict__ inv, int K) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    const float var = 1.f / (inv[k] * inv[k]) - 1e-3f;
+    moving[k] = moving[k] * 0.99f + mean[k] * 0.01f;
+    moving[K + k] = moving[K + k] * 0.99f + var * 0.01f;
+  }
+}
+// inference-mode BatchNorm: statistics = the moving ones
+__global__ void moving_to_stats_kernel(const float* __restrict__ moving, int K, float* __restrict__ mean,
+                                       float* __restrict__ inv) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    mean[k] = moving[k];
+    inv[k] = 1.f / sqrtf(moving[K + k] + 1e-3f);
+  }
+}
+// BaseVariationalNet heads + reparameterize (networks/base.py:106-117): out (B, 2 xd) = [mu | raw],
+// x = mu + sqrt(softplus(raw) + 1e-6) * noise
+__global__ void reparam_kernel(const float* __restrict__ out, const float* __restrict__ noise, int B, int xd,
+                               float* __restrict__ x) {
+  const long long total = (long long)B * xd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / xd), j = (int)(i - (long long)b * xd);
+    const float mu = out[(size_t)b * 2 * xd + j], raw = out[(size_t)b * 2 * xd + xd + j];
+    x[i] = fmaf(noise[i], sqrtf(softplus_l(raw) + 1e-6f), mu);
+  }
+}
+// its backward: dOut[:, :xd] (+)= dX ; dOut[:, xd:] (+)= dX * noise * 0.5 / sqrt(s) * sigmoid(raw)
+__global__ void reparam_bwd_kernel(const float* __restrict__ dX, const float* __restrict__ out,
+                                   const float* __restrict__ noise, int B, int xd, float* __restrict__ dOut, int accumulate) {
+  const long long total = (long long)B * xd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / xd), j = (int)(i - (long long)b * xd);
+    const float raw = out[(size_t)b * 2 * xd + xd + j];
+    const float s = softplus_l(raw) + 1e-6f;
+    const float d = dX[i];
+    const float dr = d * noise[i] * 0.5f / sqrtf(s) * sigmoid_l(raw);
+    float* dm = dOut + (size_t)b * 2 * xd + j;
+    float* dv = dm + xd;
+    if (accumulate) { *dm += d; *dv += dr; } else { *dm = d; *dv = dr; }
+  }
+}
+
+// LSGAN discriminator losses (bgm/base.py:221-224): dz_loss, dx_loss, d_loss and d loss / d D of the four calls
+__global__ void bgm_disc_loss_kernel(const float* __restrict__ dz, const float* __restrict__ dz_,
+                                     const float* __restrict__ dx, const float* __restrict__ dx_, int B,
+                                     float* __restrict__ ddz, float* __restrict__ ddz_, float* __restrict__ ddx,
+                                     float* __restrict__ ddx_, float* __restrict__ losses) {
+  __shared__ float red[8];
+  const float invB = 1.f / (float)B;
+  float lz = 0.f, lx = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float a = 0.9f - dz[b], c = 0.1f - dz_[b], e = 0.9f - dx[b], f = 0.1f - dx_[b];
+    lz += (a * a + c * c) * invB * 0.5f;
+    lx += (e * e + f * f) * invB * 0.5f;
+    ddz[b] = -a * invB; ddz_[b] = -c * invB; ddx[b] = -e * invB; ddx_[b] = -f * invB;
+  }
+  lz = block_sum(lz, red);
+  lx = block_sum(lx, red);
+  if (threadIdx.x == 0) { losses[0] = lz; losses[1] = lx; losses[2] = lx + lz; }
+}
+
+struct BgmGenLossArgs {
+  int B, xd, zd;
+  float alpha;
+  const float *x, *z;                 // batch (B, xd), (B, zd)
+  const float *out1;                  // g(z) (B, 2 xd)
+  const float *x2;                    // x__ = reparameterize(g(z_)) (B, xd)
+  const float *z2;                    // z__ = e(x_) (B, zd)
+  const float *dx_, *dz_;             // dx_net(x_), dz_net(z_) (B)
+  float *dX2, *dZ2, *ddx, *ddz;       // gradients w.r.t. x__, z__, the two discriminator outputs
+  float *dOut1;                       // (B, 2 xd): the alpha * reg_loss part (raw columns), mean columns zero
+  float* losses;                      // [6]: g_loss_adv, e_loss_adv, l2_loss_z, l2_loss_x, reg_loss, g_e_loss (:291)
+};
+__global__ void bgm_gen_loss_kernel(const BgmGenLossArgs A) {
+  __shared__ float red[8];
+  const int B = A.B, xd = A.xd, zd = A.zd;
+  const float invB = 1.f / (float)B;
+  float gadv = 0.f, eadv = 0.f, l2z = 0.f, l2x = 0.f, reg = 0.f;
+  for (int i = threadIdx.x; i < B * xd; i += blockDim.x) {
+    const int b = i / xd, j = i - b * xd;
+    const float df = A.x2[i] - A.x[i];
+    l2x += df * df;
+    A.dX2[i] = 10.f * 2.f * df / (float)(B * xd);
+    const float raw = A.out1[(size_t)b * 2 * xd + xd + j];
+    const float s = softplus_l(raw) + 1e-6f;
+    reg += s * s;
+    A.dOut1[(size_t)b * 2 * xd + j] = 0.f;
+    A.dOut1[(size_t)b * 2 * xd + xd + j] = A.alpha * 2.f * s / (float)(B * xd) * sigmoid_l(raw);
+  }
+  for (int i = threadIdx.x; i < B * zd; i += blockDim.x) {
+    const float df = A.z2[i] - A.z[i];
+    l2z += df * df;
+    A.dZ2[i] = 10.f * 2.f * df / (float)(B * zd);
+  }
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float a = 0.9f - A.dx_[b], c = 0.9f - A.dz_[b];
+    gadv += a * a * invB;
+    eadv += c * c * invB;
+    A.ddx[b] = -2.f * a * invB;
+    A.ddz[b] = -2.f * c * invB;
+  }
+  gadv = block_sum(gadv, red);
+  eadv = block_sum(eadv, red);
+  l2z = block_sum(l2z, red) / (float)(B * zd);
+  l2x = block_sum(l2x, red) / (float)(B * xd);
+  reg = block_sum(reg, red) / (float)(B * xd);
+  if (threadIdx.x == 0) {
+    A.losses[0] = gadv; A.losses[1] = eadv; A.losses[2] = l2z; A.losses[3] = l2x; A.losses[4] = reg;
+    A.losses[5] = gadv + eadv + 10.f * (l2x + l2z) + A.alpha * reg;
+  }
+}
+
+// Gaussian NLL with a per-element variance (bgm/base.py:150-153, :173-177): loss = mean_b sum_j [(x-mu)^2/(2s) + log(s)/2],
+// out (B, 2 xd) = [mu | raw], s = softplus(raw) + 1e-6; dOut fully written; losses[0] = loss, losses[1] = mean (x-mu)^2
+__global__ void bgm_nll_kernel(const float* __restrict__ x, const float* __restrict__ out, int B, int xd,
+                               float* __restrict__ dOut, float* __restrict__ losses) {
+  __shared__ float red[8];
+  const float invB = 1.f / (float)B;
+  float loss = 0.f, mse = 0.f;
+  for (int i = threadIdx.x; i < B * xd; i += blockDim.x) {
+    const int b = i / xd, j = i - b * xd;
+    const float mu = out[(size_t)b * 2 * xd + j], raw = out[(size_t)b * 2 * xd + xd + j];
+    const float s = softplus_l(raw) + 1e-6f;
+    const float df = x[i] - mu;
+    loss += (df * df / (2.f * s) + 0.5f * logf(s)) * invB;
+    mse += df * df;
+    dOut[(size_t)b * 2 * xd + j] = -df / s * invB;
+    dOut[(size_t)b * 2 * xd + xd + j] = (-df * df / (2.f * s * s) + 0.5f / s) * sigmoid_l(raw) * invB;
+  }
+  loss = block_sum(loss, red);
+  mse = block_sum(mse, red);
+  if (threadIdx.x == 0) { losses[0] = loss; losses[1] = mse / (float)(B * xd); }
+}
+
+// Adam on a FRESH variable per batch (bgm/base.py:402-413: the batch rows are wrapped in a new tf.Variable, so the
+// slots start at zero; the optimizer's step count is shared): z[idx[b]] -= lr_t * m / (sqrt(v) + eps)
+__global__ void fresh_adam_rows_kernel(float* __restrict__ zt, const int* __restrict__ idx, const float* __restrict__ gz,
+                                       int B, int zd, float lr_t, float b1, float b2, float eps) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * zd; i += gridDim.x * blockDim.x) {
+    const int b = i / zd, d = i - b * zd;
+    const float g = gz[i];
+    const float m = (1.f - b1) * g, v = (1.f - b2) * g * g;
+    zt[(size_t)idx[b] * zd + d] -= lr_t * m / (sqrtf(v) + eps);
+  }
+}
+
 // sum over rows and columns of (T - P[:, :D])^2 -> float64 accumulator
 __global__ void sq_err_kernel(const float* __restrict__ T, int ldt, const float* __restrict__ P, int ldp, long long B, int D,
                               int sigmoid_p, double* __restrict__ out) {

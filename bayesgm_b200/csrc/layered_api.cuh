@@ -21,7 +21,8 @@ constexpr int LT_MAXL = 8;
 struct LNet {
   int L = 0;
   int dims[LT_MAXL + 1];
-  int bayes = 0, net_id = 0;
+  int bayes = 0, net_id = 0;                   // bayes = bn_in && flip (BayesianFullyConnectedNet)
+  int bn_in = 0, flip = 0;                      // input BatchNormalization / DenseFlipout layers
   int base = 0, n_params = 0;                  // slice of the group-0 flat vector
   int off_gamma = -1, off_beta = -1;           // absolute offsets (Bayesian nets)
   int off_w[LT_MAXL], off_rho[LT_MAXL], off_b[LT_MAXL];
@@ -44,6 +45,15 @@ struct DiscPass {
   float *xhat[LT_MAXL], *out[LT_MAXL], *mean[LT_MAXL], *inv[LT_MAXL];
   const float* in = nullptr;
   float* d = nullptr;                           // (B, 1)
+};
+
+struct Arena;
+struct Ctx {                                    // what the generic passes need from a trainer
+  Arena* ar;
+  const float* th0;                             // parameter group 0
+  float* g0;                                    // its gradient buffer
+  int sm;
+  uint64_t seed;
 };
 
 struct Arena {
@@ -84,6 +94,27 @@ struct bgm_lt {
   int sm_count = 148, smem_disc = 0, wm_disc = 4;
 };
 
+// BGM flavour (bgm/base.py:145-291): generator = BaseVariationalNet (input BatchNormalization in training mode +
+// Dense stack + [mean | variance] heads as ONE final layer of width 2 x_dim), encoder e_net, discriminators dz / dx.
+// Same device parameter layout as the fused BGM trainer (bgm_bgmtrainer_create).
+struct bgm_ltb {
+  bgm::lt::LNet g, e;
+  bgm::tr::Disc dz, dx;
+  int dx_base = 0;
+  int zd = 0, xd = 0, n_g = 0, n0 = 0, n1 = 0;
+  float *theta[2] = {nullptr, nullptr}, *grad[2] = {nullptr, nullptr};
+  float *m_pre[2] = {nullptr, nullptr}, *v_pre[2] = {nullptr, nullptr};
+  long long step_pre[2] = {0, 0};
+  float *m_it = nullptr, *v_it = nullptr;
+  long long step_g = 0, step_z = 0;
+  double lr = 0, b1 = 0.5, b2 = 0.9, lr_theta = 5e-3, lr_z = 5e-3;
+  float alpha = 0.f, gamma = 0.f;
+  float* moving = nullptr;       // [2 zd] moving mean | variance of the generator's input BatchNormalization
+  bgm::lt::Arena arena;
+  float* scratch = nullptr;
+  int sm_count = 148;
+};
+
 namespace bgm {
 namespace lt {
 
@@ -94,53 +125,57 @@ static inline int grid_for(long long total, int sm) {
 static size_t pass_bytes(const LNet& n, long long B) {
   size_t b = 0;
   auto al = [](size_t x) { return (x + 255) / 256 * 256 + 256; };
-  if (n.bayes) b += 2 * al(4 * n.dims[0]) + 2 * al(4 * B * n.dims[0]) + 2 * al(4 * n.dims[0]);
+  if (n.bn_in) b += 2 * al(4 * n.dims[0]) + 2 * al(4 * B * n.dims[0]) + 2 * al(4 * n.dims[0]);
   for (int l = 0; l < n.L; ++l) {
     const size_t K = n.dims[l], N = n.dims[l + 1];
     b += al(4 * B * N) + al(4 * B * K);                       // output, input gradient
-    if (n.bayes) b += al(4 * K * N) + al(B * K) + al(B * N);
+    if (n.flip) b += al(4 * K * N) + al(B * K) + al(B * N);
   }
   b += al(4 * B * n.dims[n.L]);                              // output gradient
   return b;
 }
+static size_t disc_bytes(const tr::Disc& dz, long long B) {
+  size_t b = 0;
+  for (int l = 0; l <= dz.L; ++l) b += 8 * (size_t)(4 * B * std::max(dz.dims[l], dz.dims[l + 1]) + 512);
+  return b;
+}
 static size_t step_bytes(const bgm_lt* t, long long B) {
   size_t b = 3 * pass_bytes(t->g, B) + 2 * pass_bytes(t->e, B) + 2 * pass_bytes(t->f, B) + 2 * pass_bytes(t->h, B);
-  size_t disc = 0;
-  for (int l = 0; l <= t->dz.L; ++l) disc += 8 * (size_t)(4 * B * std::max(t->dz.dims[l], t->dz.dims[l + 1]) + 512);
-  b += disc + 16 * (size_t)(4 * B * (t->p + 1 + t->zd + 8) + 512);
+  b += disc_bytes(t->dz, B) + 16 * (size_t)(4 * B * (t->p + 1 + t->zd + 8) + 512);
   return b + (1 << 16);
 }
-static int ensure_arena(bgm_lt* t, long long B) {
-  const size_t need = step_bytes(t, B);
-  if (need > t->arena.cap) {
+static int ensure_arena_bytes(Arena& ar, size_t need) {
+  if (need > ar.cap) {
     BGM_CUDA_OK(cudaDeviceSynchronize());
-    if (t->arena.base) cudaFree(t->arena.base);
-    t->arena.base = nullptr;
-    t->arena.cap = 0;
-    BGM_CUDA_OK(cudaMalloc(&t->arena.base, need));
-    t->arena.cap = need;
+    if (ar.base) cudaFree(ar.base);
+    ar.base = nullptr;
+    ar.cap = 0;
+    BGM_CUDA_OK(cudaMalloc(&ar.base, need));
+    ar.cap = need;
   }
-  t->arena.used = 0;
-  t->arena.overflow = false;
+  ar.used = 0;
+  ar.overflow = false;
   return 0;
 }
-static int arena_ok(bgm_lt* t, const char* fn) {
-  if (t->arena.overflow) return fail(BGM_ERR_NOMEM, std::string(fn) + ": workspace estimate too small (internal error)");
+static int ensure_arena(bgm_lt* t, long long B) { return ensure_arena_bytes(t->arena, step_bytes(t, B)); }
+static Ctx ctx_of(bgm_lt* t) { return Ctx{&t->arena, t->theta[0], t->grad[0], t->sm_count, t->seed}; }
+static int arena_ok(Arena& ar, const char* fn) {
+  if (ar.overflow) return fail(BGM_ERR_NOMEM, std::string(fn) + ": workspace estimate too small (internal error)");
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 // ---- one forward call of a net on B rows.  ext_mean / ext_inv: batch statistics computed elsewhere (chunked
 // evaluation: the statistics are those of the WHOLE batch, the chunk only holds some of its rows). ----
-static void net_fwd(bgm_lt* t, const LNet& net, Pass& P, const float* X, int ldx, int B, uint32_t call, int64_t row0,
+static void net_fwd(const Ctx& C, const LNet& net, Pass& P, const float* X, int ldx, int B, uint32_t call, int64_t row0,
                     int const_col, const float* ext_mean, const float* ext_inv, cudaStream_t st) {
-  Arena& ar = t->arena;
-  const float* th = t->theta[0];
-  const int sm = t->sm_count;
+  Arena& ar = *C.ar;
+  const float* th = C.th0;
+  const int sm = C.sm;
   P.net = &net;
   P.B = B;
   const int K0 = net.dims[0];
-  if (net.bayes) {
+  if (net.bn_in) {
     P.xhat = ar.get<float>((size_t)B * K0);
     P.a[0] = ar.get<float>((size_t)B * K0);
     P.lda[0] = K0;
@@ -161,12 +196,12 @@ static void net_fwd(bgm_lt* t, const LNet& net, Pass& P, const float* X, int ldx
   for (int l = 0; l < net.L; ++l) {
     const int K = net.dims[l], N = net.dims[l + 1];
     P.dW[l] = nullptr; P.sin[l] = nullptr; P.sout[l] = nullptr;
-    if (net.bayes) {
+    if (net.flip) {
       P.dW[l] = ar.get<float>((size_t)K * N);
       P.sin[l] = ar.get<signed char>((size_t)B * K);
       P.sout[l] = ar.get<signed char>((size_t)B * N);
       const long long work = std::max<long long>((long long)K * N / 4, (long long)B * ((K + N + 31) / 32));
-      flipout_noise_kernel<<<grid_for(work, sm), 256, 0, st>>>(th + net.off_rho[l], K, N, t->seed, 0, net.net_id, l, call,
+      flipout_noise_kernel<<<grid_for(work, sm), 256, 0, st>>>(th + net.off_rho[l], K, N, C.seed, 0, net.net_id, l, call,
                                                               row0, B, P.dW[l], P.sin[l], P.sout[l]);
     }
     P.a[l + 1] = ar.get<float>((size_t)B * N);
@@ -178,19 +213,19 @@ static void net_fwd(bgm_lt* t, const LNet& net, Pass& P, const float* X, int ldx
 }
 
 // ---- backward of one call: parameter gradients (+= into grad[0]) and / or the gradient w.r.t. the net's input ----
-static void net_bwd(bgm_lt* t, const LNet& net, const Pass& P, const float* dOut, bool param_grads, float* dX, int lddx,
+static void net_bwd(const Ctx& C, const LNet& net, const Pass& P, const float* dOut, bool param_grads, float* dX, int lddx,
                     bool accumulate_dx, cudaStream_t st) {
-  Arena& ar = t->arena;
-  const float* th = t->theta[0];
-  float* g = t->grad[0];
-  const int sm = t->sm_count, B = P.B;
+  Arena& ar = *C.ar;
+  const float* th = C.th0;
+  float* g = C.g0;
+  const int sm = C.sm, B = P.B;
   const float* dY = dOut;
   for (int l = net.L - 1; l >= 0; --l) {
     const int K = net.dims[l], N = net.dims[l + 1];
     if (param_grads)
       dense_bwd_param_kernel<<<grid_for((long long)K * N, sm), 256, 0, st>>>(
-          P.a[l], P.lda[l], dY, N, net.bayes ? th + net.off_rho[l] : nullptr, P.dW[l], P.sin[l], P.sout[l], B, K, N,
-          g + net.off_w[l], net.bayes ? g + net.off_rho[l] : nullptr, g + net.off_b[l]);
+          P.a[l], P.lda[l], dY, N, net.flip ? th + net.off_rho[l] : nullptr, P.dW[l], P.sin[l], P.sout[l], B, K, N,
+          g + net.off_w[l], net.flip ? g + net.off_rho[l] : nullptr, g + net.off_b[l]);
     if (l > 0) {
       float* dA = ar.get<float>((size_t)B * K);
       dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + net.off_w[l], P.dW[l], P.sin[l],
@@ -198,7 +233,7 @@ static void net_bwd(bgm_lt* t, const LNet& net, const Pass& P, const float* dOut
       dY = dA;
       continue;
     }
-    if (net.bayes) {
+    if (net.bn_in) {
       if (!param_grads && !dX) break;
       float* dA0 = ar.get<float>((size_t)B * K);
       dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + net.off_w[0], P.dW[0], P.sin[0],
@@ -220,11 +255,9 @@ static void net_bwd(bgm_lt* t, const LNet& net, const Pass& P, const float* dOut
 }
 
 // ---- Discriminator (networks/base.py:338-385): Dense -> BN(batch statistics) -> tanh blocks, Dense(1) ----
-static void disc_fwd(bgm_lt* t, DiscPass& D, const float* Z, int B, cudaStream_t st) {
-  Arena& ar = t->arena;
-  const tr::Disc& dz = t->dz;
-  const float* th = t->theta[1];
-  const int sm = t->sm_count;
+static void disc_fwd(const Ctx& C, const tr::Disc& dz, const float* th, DiscPass& D, const float* Z, int B, cudaStream_t st) {
+  Arena& ar = *C.ar;
+  const int sm = C.sm;
   D.in = Z;
   const float* a = Z;
   for (int l = 0; l < dz.L; ++l) {
@@ -246,12 +279,12 @@ static void disc_fwd(bgm_lt* t, DiscPass& D, const float* Z, int B, cudaStream_t
   dense_fwd_kernel<<<grid_for(B, sm), 256, 0, st>>>(a, K, th + dz.w_off[dz.L], nullptr, nullptr, nullptr,
                                                    th + dz.b_off[dz.L], B, K, 1, D.d, 1, 0);
 }
-// gradient of sum_b dd[b] * D(z)[b] w.r.t. z, added into dZ (B, zd)
-static void disc_bwd_input(bgm_lt* t, const DiscPass& D, const float* dd, int B, float* dZ, cudaStream_t st) {
-  Arena& ar = t->arena;
-  const tr::Disc& dz = t->dz;
-  const float* th = t->theta[1];
-  const int sm = t->sm_count;
+// Backward of one discriminator call from dd (B) = d loss / d D: parameter gradients (+= into g, Keras order of
+// tr::Disc) when g != NULL, and the gradient w.r.t. the input added into dZ (B, dims[0]) when dZ != NULL.
+static void disc_bwd(const Ctx& C, const tr::Disc& dz, const float* th, float* g, const DiscPass& D, const float* dd, int B,
+                     float* dZ, cudaStream_t st) {
+  Arena& ar = *C.ar;
+  const int sm = C.sm;
   const float* dY = dd;
   int N = 1;
   for (int l = dz.L; l >= 0; --l) {
@@ -261,14 +294,20 @@ static void disc_bwd_input(bgm_lt* t, const DiscPass& D, const float* dd, int B,
       float* s1 = ar.get<float>(N);
       float* s2 = ar.get<float>(N);
       float* dPre = ar.get<float>((size_t)B * N);
-      bn_bwd_sums_kernel<<<(N + 127) / 128, 128, 0, st>>>(dY, D.out[l], D.xhat[l], B, N, 2, s1, s2, nullptr, nullptr);
+      bn_bwd_sums_kernel<<<(N + 127) / 128, 128, 0, st>>>(dY, D.out[l], D.xhat[l], B, N, 2, s1, s2,
+                                                          g ? g + dz.g_off[l] : nullptr, g ? g + dz.be_off[l] : nullptr);
       bn_bwd_input_kernel<<<grid_for((long long)B * N, sm), 256, 0, st>>>(dY, D.out[l], D.xhat[l], D.inv[l], th + dz.g_off[l],
                                                                          s1, s2, B, N, 2, dPre, N, 0);
       dY = dPre;
     }
+    const float* A_in = l == 0 ? D.in : D.out[l - 1];
+    if (g)
+      dense_bwd_param_kernel<<<grid_for((long long)K * N, sm), 256, 0, st>>>(A_in, K, dY, N, nullptr, nullptr, nullptr, nullptr, B,
+                                                                            K, N, g + dz.w_off[l], nullptr, g + dz.b_off[l]);
     if (l == 0) {
-      dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + dz.w_off[0], nullptr, nullptr, nullptr,
-                                                                            nullptr, 0, B, K, N, dZ, K, 1);
+      if (dZ)
+        dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + dz.w_off[0], nullptr, nullptr, nullptr,
+                                                                              nullptr, 0, B, K, N, dZ, K, 1);
     } else {
       float* dA = ar.get<float>((size_t)B * K);
       dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + dz.w_off[l], nullptr, nullptr, nullptr,
@@ -288,6 +327,8 @@ static int fill_net(const bgm_bnn_net_desc* d, LNet& n, int net_id, int bayes, i
     return fail(BGM_ERR_ARG, std::string(name) + ": input / output width does not match z_dims / v_dim");
   n.L = d->n_layers;
   n.bayes = bayes;
+  n.bn_in = bayes;
+  n.flip = bayes;
   n.net_id = net_id;
   n.base = off;
   for (int l = 0; l <= n.L; ++l) {
@@ -478,8 +519,9 @@ int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, 
   if (rc) return rc;
   const uint32_t c0 = t->call_ctr * 16u;
   t->call_ctr += 1;
+  const Ctx C = ctx_of(t);
   Pass eA;
-  net_fwd(t, t->e, eA, v_dev, t->p, bs, c0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->e, eA, v_dev, t->p, bs, c0, 0, -1, nullptr, nullptr, st);
   tr::DiscArgs A;
   memset(&A, 0, sizeof(A));
   A.dz = t->dz; A.zd = t->zd; A.p = t->p; A.bs = bs;
@@ -488,7 +530,7 @@ int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, 
   A.epsilon = epsilon; A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm_disc;
   BGM_CUDA_OK(cudaFuncSetAttribute(tr::disc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_disc));
   tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, st>>>(A);
-  return arena_ok(t, "bgm_lt_disc_grad");
+  return arena_ok(t->arena, "bgm_lt_disc_grad");
 }
 
 // train_gen_step gradients (causalbgm/base.py:332-370).  Net calls and their noise ids (16*ctr + k): g(z) for v_
@@ -510,22 +552,23 @@ int bgm_lt_gen_grad(bgm_lt* t, const float* z_dev, const float* v_dev, const flo
   const uint32_t c0 = t->call_ctr * 16u;
   t->call_ctr += 1;
   zero(t->grad[0], t->n0, sm, st);
+  const Ctx C = ctx_of(t);
   Pass gA, gB, gC, eA, eB, fA, fB, hA, hB;
-  net_fwd(t, t->g, gA, z_dev, zd, B, c0 + 0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->g, gB, z_dev, zd, B, c0 + 1, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->e, eA, v_dev, p, B, c0 + 0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->e, eB, gA.out(), p + 1, B, c0 + 1, 0, -1, nullptr, nullptr, st);       // e(v_): the first p columns of g(z)
+  net_fwd(C, t->g, gA, z_dev, zd, B, c0 + 0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->g, gB, z_dev, zd, B, c0 + 1, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->e, eA, v_dev, p, B, c0 + 0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->e, eB, gA.out(), p + 1, B, c0 + 1, 0, -1, nullptr, nullptr, st);       // e(v_): the first p columns of g(z)
   const float* zenc = eA.out();
-  net_fwd(t, t->g, gC, zenc, zd, B, c0 + 2, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->g, gC, zenc, zd, B, c0 + 2, 0, -1, nullptr, nullptr, st);
   DiscPass D;
-  disc_fwd(t, D, zenc, B, st);
+  disc_fwd(C, t->dz, t->theta[1], D, zenc, B, st);
   float* fin = ar.get<float>((size_t)B * kf);
   float* hin = ar.get<float>((size_t)B * std::max(kh, 1));
   build_fh_inputs(t, zenc, zd, x_dev, B, fin, hin, st);
-  net_fwd(t, t->f, fA, fin, kf, B, c0 + 0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->f, fB, fin, kf, B, c0 + 1, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->h, hA, hin, kh, B, c0 + 0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->h, hB, hin, kh, B, c0 + 1, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->f, fA, fin, kf, B, c0 + 0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->f, fB, fin, kf, B, c0 + 1, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->h, hA, hin, kh, B, c0 + 0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->h, hB, hin, kh, B, c0 + 1, 0, -1, nullptr, nullptr, st);
   GenLossArgs L;
   memset(&L, 0, sizeof(L));
   L.B = B; L.p = p; L.zd = zd; L.binary = t->binary; L.use_z_rec = t->use_z_rec;
@@ -542,18 +585,18 @@ int bgm_lt_gen_grad(bgm_lt* t, const float* z_dev, const float* v_dev, const flo
   float* dgA = ar.get<float>((size_t)B * (p + 1));
   zero(dZ, (long long)B * zd, sm, st);
   zero(dgA, (long long)B * (p + 1), sm, st);
-  disc_bwd_input(t, D, L.dd, B, dZ, st);
-  net_bwd(t, t->g, gC, L.dgC, true, dZ, zd, true, st);
-  net_bwd(t, t->f, fA, L.dfA, true, dFin, kf, false, st);
-  net_bwd(t, t->f, fB, L.dfB, true, dFin, kf, true, st);
-  net_bwd(t, t->h, hA, L.dhA, true, dHin, kh, false, st);
-  net_bwd(t, t->h, hB, L.dhB, true, dHin, kh, true, st);
+  disc_bwd(C, t->dz, t->theta[1], nullptr, D, L.dd, B, dZ, st);
+  net_bwd(C, t->g, gC, L.dgC, true, dZ, zd, true, st);
+  net_bwd(C, t->f, fA, L.dfA, true, dFin, kf, false, st);
+  net_bwd(C, t->f, fB, L.dfB, true, dFin, kf, true, st);
+  net_bwd(C, t->h, hA, L.dhA, true, dHin, kh, false, st);
+  net_bwd(C, t->h, hB, L.dhB, true, dHin, kh, true, st);
   scatter_fh_grads(t, dFin, dHin, B, dZ, st);
-  net_bwd(t, t->e, eB, L.deB, true, dgA, p + 1, false, st);   // d loss / d v_ lands in the first p columns of g(z)'s output gradient
-  net_bwd(t, t->g, gA, dgA, true, nullptr, 0, false, st);
-  net_bwd(t, t->g, gB, L.dgB, true, nullptr, 0, false, st);
-  net_bwd(t, t->e, eA, dZ, true, nullptr, 0, false, st);
-  return arena_ok(t, "bgm_lt_gen_grad");
+  net_bwd(C, t->e, eB, L.deB, true, dgA, p + 1, false, st);   // d loss / d v_ lands in the first p columns of g(z)'s output gradient
+  net_bwd(C, t->g, gA, dgA, true, nullptr, 0, false, st);
+  net_bwd(C, t->g, gB, L.dgB, true, nullptr, 0, false, st);
+  net_bwd(C, t->e, eA, dZ, true, nullptr, 0, false, st);
+  return arena_ok(t->arena, "bgm_lt_gen_grad");
 }
 
 int bgm_lt_set_iter(bgm_lt* t, float lr_theta, float lr_z, float sigma_v, float sigma_x, float sigma_y) {
@@ -604,10 +647,11 @@ int bgm_lt_iter_nets(bgm_lt* t, const float* zt_dev, const float* x_dev, const f
     float* fin = ar.get<float>((size_t)B * kf);
     float* hin = ar.get<float>((size_t)B * std::max(kh, 1));
     build_fh_inputs(t, zb, zd, xb, B, fin, hin, st);
+    const Ctx C = ctx_of(t);
     Pass gP, hP, fP;
-    net_fwd(t, t->g, gP, zb, zd, B, c0, 0, -1, nullptr, nullptr, st);
-    net_fwd(t, t->h, hP, hin, kh, B, c0, 0, -1, nullptr, nullptr, st);
-    net_fwd(t, t->f, fP, fin, kf, B, c0, 0, -1, nullptr, nullptr, st);
+    net_fwd(C, t->g, gP, zb, zd, B, c0, 0, -1, nullptr, nullptr, st);
+    net_fwd(C, t->h, hP, hin, kh, B, c0, 0, -1, nullptr, nullptr, st);
+    net_fwd(C, t->f, fP, fin, kf, B, c0, 0, -1, nullptr, nullptr, st);
     const Pass* passes[3] = {&gP, &hP, &fP};
     const float* targets[3] = {vb, xb, yb};
     const int Ds[3] = {p, 1, 1};
@@ -628,9 +672,9 @@ int bgm_lt_iter_nets(bgm_lt* t, const float* zt_dev, const float* x_dev, const f
           kl_grad_kernel<<<grid_for(cnt, sm), 256, 0, st>>>(t->theta[0] + net.off_w[l], t->theta[0] + net.off_rho[l], cnt, t->kl_weight,
                                                            t->grad[0] + net.off_w[l], t->grad[0] + net.off_rho[l], losses_dev + 2 * i);
         }
-      net_bwd(t, net, *passes[i], dO, true, nullptr, 0, false, st);
+      net_bwd(C, net, *passes[i], dO, true, nullptr, 0, false, st);
     }
-    rc = arena_ok(t, "bgm_lt_iter_nets");
+    rc = arena_ok(t->arena, "bgm_lt_iter_nets");
     if (rc) return rc;
   }
   if (apply != 0) {
@@ -680,13 +724,14 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   float* fin = ar.get<float>((size_t)B * kf);
   float* hin = ar.get<float>((size_t)B * std::max(kh, 1));
   build_fh_inputs(t, zb, zd, xb, B, fin, hin, st);
+  const Ctx C = ctx_of(t);
   Pass gA, gB, hA, hB, fA, fB;
-  net_fwd(t, t->g, gA, zb, zd, B, c0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->g, gB, zb, zd, B, c0 + 1, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->h, hA, hin, kh, B, c0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->h, hB, hin, kh, B, c0 + 1, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->f, fA, fin, kf, B, c0, 0, -1, nullptr, nullptr, st);
-  net_fwd(t, t->f, fB, fin, kf, B, c0 + 1, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->g, gA, zb, zd, B, c0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->g, gB, zb, zd, B, c0 + 1, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->h, hA, hin, kh, B, c0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->h, hB, hin, kh, B, c0 + 1, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->f, fA, fin, kf, B, c0, 0, -1, nullptr, nullptr, st);
+  net_fwd(C, t->f, fB, fin, kf, B, c0 + 1, 0, -1, nullptr, nullptr, st);
   const Pass* A[3] = {&gA, &hA, &fA};
   const Pass* R[3] = {&gB, &hB, &fB};
   const float* targets[3] = {vb, xb, yb};
@@ -711,12 +756,12 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   // prior (:291-292): mean_b |z_b|^2 / 2  ->  dZ = z / B
   gather_cols_kernel<<<grid_for((long long)B * zd, sm), 256, 0, st>>>(zb, zd, nullptr, 0, zd, B, dZ, zd, 0);
   prior_scale_kernel<<<1, 256, 0, st>>>(dZ, B * zd, 1.f / (float)B, losses + 6);
-  net_bwd(t, t->g, gA, dA[0], false, dZ, zd, true, st);
-  net_bwd(t, t->g, gB, dR[0], false, dZ, zd, true, st);
-  net_bwd(t, t->h, hA, dA[1], false, dHin, kh, false, st);
-  net_bwd(t, t->h, hB, dR[1], false, dHin, kh, true, st);
-  net_bwd(t, t->f, fA, dA[2], false, dFin, kf, false, st);
-  net_bwd(t, t->f, fB, dR[2], false, dFin, kf, true, st);
+  net_bwd(C, t->g, gA, dA[0], false, dZ, zd, true, st);
+  net_bwd(C, t->g, gB, dR[0], false, dZ, zd, true, st);
+  net_bwd(C, t->h, hA, dA[1], false, dHin, kh, false, st);
+  net_bwd(C, t->h, hB, dR[1], false, dHin, kh, true, st);
+  net_bwd(C, t->f, fA, dA[2], false, dFin, kf, false, st);
+  net_bwd(C, t->f, fB, dR[2], false, dFin, kf, true, st);
   scatter_fh_grads(t, dFin, dHin, B, dZ, st);
   sum_losses_kernel<<<1, 32, 0, st>>>(losses, loss_dev);
   if (gz_out_dev) BGM_CUDA_OK(cudaMemcpyAsync(gz_out_dev, dZ, sizeof(float) * (size_t)B * zd, cudaMemcpyDeviceToDevice, st));
@@ -725,7 +770,7 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   set_slots_kernel<<<grid_for(B, sm), 256, 0, st>>>(slot_dev, idx_dev, B, 1);
   latent_adam_kernel<<<grid_for(n * zd, sm), 256, 0, st>>>(zt_dev, m_dev, v_adam_dev, slot_dev, dZ, n, zd, lr_t, 0.9f, 0.99f, 1e-7f);
   set_slots_kernel<<<grid_for(B, sm), 256, 0, st>>>(slot_dev, idx_dev, B, 0);
-  return arena_ok(t, "bgm_lt_iter_latent");
+  return arena_ok(t->arena, "bgm_lt_iter_latent");
 }
 
 // CausalBGM.evaluate (causalbgm/base.py:534-556), the part that touches every row, in row chunks: the batch
@@ -746,6 +791,7 @@ int bgm_lt_evaluate(bgm_lt* t, const float* zt_dev, const float* x_dev, const fl
   if (rc) return rc;
   const uint32_t c0 = t->call_ctr * 16u;
   t->call_ctr += 1;
+  const Ctx C = ctx_of(t);
   // whole-batch buffers (freed on return): z, f / h inputs, statistics
   float *zall = nullptr, *fin = nullptr, *hin = nullptr, *stats = nullptr;
   const int nstat = 2 * (p + zd + kf + std::max(kh, 1));
@@ -774,7 +820,7 @@ int bgm_lt_evaluate(bgm_lt* t, const float* zt_dev, const float* x_dev, const fl
       const int B = std::min(chunk, n - r0);
       t->arena.used = 0;
       Pass eP;
-      net_fwd(t, t->e, eP, v_dev + (size_t)r0 * p, p, B, c0, r0, -1, st_v, st_v + p, st);
+      net_fwd(C, t->e, eP, v_dev + (size_t)r0 * p, p, B, c0, r0, -1, st_v, st_v + p, st);
       BGM_CUDA_OK(cudaMemcpyAsync(zall + (size_t)r0 * zd, eP.out(), sizeof(float) * (size_t)B * zd, cudaMemcpyDeviceToDevice, st));
     }
     Z = zall;
@@ -790,18 +836,401 @@ int bgm_lt_evaluate(bgm_lt* t, const float* zt_dev, const float* x_dev, const fl
     const int B = std::min(chunk, n - r0);
     t->arena.used = 0;
     Pass gP, fP, hP;
-    net_fwd(t, t->g, gP, Z + (size_t)r0 * zd, zd, B, c0, r0, -1, st_z, st_z + zd, st);
+    net_fwd(C, t->g, gP, Z + (size_t)r0 * zd, zd, B, c0, r0, -1, st_z, st_z + zd, st);
     sq_err_kernel<<<grid_for((long long)B * p, sm), 256, 0, st>>>(v_dev + (size_t)r0 * p, p, gP.out(), p + 1, B, p, 0, sums_dev);
     t->arena.used = 0;
-    net_fwd(t, t->h, hP, hin + (size_t)r0 * kh, kh, B, c0, r0, -1, st_h, st_h + kh, st);
+    net_fwd(C, t->h, hP, hin + (size_t)r0 * kh, kh, B, c0, r0, -1, st_h, st_h + kh, st);
     sq_err_kernel<<<grid_for(B, sm), 256, 0, st>>>(x_dev + r0, 1, hP.out(), 2, B, 1, t->binary, sums_dev + 1);
     t->arena.used = 0;
-    net_fwd(t, t->f, fP, fin + (size_t)r0 * kf, kf, B, c0, r0, -1, st_f, st_f + kf, st);
+    net_fwd(C, t->f, fP, fin + (size_t)r0 * kf, kf, B, c0, r0, -1, st_f, st_f + kf, st);
     sq_err_kernel<<<grid_for(B, sm), 256, 0, st>>>(y_dev + r0, 1, fP.out(), 2, B, 1, 0, sums_dev + 2);
   }
-  rc = arena_ok(t, "bgm_lt_evaluate");
+  rc = arena_ok(t->arena, "bgm_lt_evaluate");
   cleanup();
   return rc;
+}
+
+// ------------------------------------------------------------------------------------------ BGM flavour ----
+void bgm_ltb_destroy(bgm_ltb* t) {
+  if (!t) return;
+  for (int g = 0; g < 2; ++g) {
+    if (t->theta[g]) cudaFree(t->theta[g]);
+    if (t->grad[g]) cudaFree(t->grad[g]);
+    if (t->m_pre[g]) cudaFree(t->m_pre[g]);
+    if (t->v_pre[g]) cudaFree(t->v_pre[g]);
+  }
+  if (t->m_it) cudaFree(t->m_it);
+  if (t->v_it) cudaFree(t->v_it);
+  if (t->moving) cudaFree(t->moving);
+  if (t->scratch) cudaFree(t->scratch);
+  if (t->arena.base) cudaFree(t->arena.base);
+  delete t;
+}
+
+int bgm_ltb_create(bgm_ltb** out, const bgm_varnet_desc* g, const bgm_net_desc* e_net, const bgm_disc_desc* dz_net,
+                   const bgm_disc_desc* dx_net, float lr, float beta_1, float beta_2, float alpha, float gamma) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!out || !g || !e_net || !dz_net || !dx_net) return fail(BGM_ERR_ARG, "bgm_ltb_create: null argument");
+  *out = nullptr;
+  if (gamma != 0.f)
+    return fail(BGM_ERR_UNSUPPORTED, "bgm_ltb_create: the layered engine has no gradient-penalty double backward (gamma must be 0)");
+  if (!g->units || !g->bn || !g->hidden_params || !g->mean_params || !g->var_params || g->n_hidden < 1 || g->n_hidden + 1 > LT_MAXL)
+    return fail(BGM_ERR_ARG, "bgm_ltb_create: bad generator description");
+  if (!e_net->dims || !e_net->params || e_net->n_layers < 1 || e_net->n_layers > LT_MAXL)
+    return fail(BGM_ERR_ARG, "bgm_ltb_create: bad encoder description");
+  const int zd = g->z_dim, xd = g->x_dim, nh = g->n_hidden;
+  if (e_net->dims[0] != xd || e_net->dims[e_net->n_layers] != zd) return fail(BGM_ERR_ARG, "bgm_ltb_create: e_net must map x_dim -> z_dim");
+  bgm_ltb* t = new bgm_ltb();
+  t->zd = zd; t->xd = xd; t->alpha = alpha; t->gamma = gamma;
+  t->lr = lr; t->b1 = beta_1; t->b2 = beta_2;
+  int off = 0;
+  LNet& G = t->g;
+  G.L = nh + 1; G.bn_in = 1; G.flip = 0; G.bayes = 0; G.net_id = 0; G.base = 0;
+  G.off_gamma = off; off += zd;
+  G.off_beta = off; off += zd;
+  G.dims[0] = zd;
+  for (int l = 0; l < nh; ++l) G.dims[l + 1] = g->units[l];
+  G.dims[nh + 1] = 2 * xd;
+  for (int l = 0; l < G.L; ++l) {
+    G.off_w[l] = off; off += G.dims[l] * G.dims[l + 1];
+    G.off_rho[l] = -1;
+    G.off_b[l] = off; off += G.dims[l + 1];
+  }
+  G.n_params = off;
+  t->n_g = off;
+  LNet& E = t->e;
+  E.L = e_net->n_layers; E.base = off; E.net_id = 3;
+  for (int l = 0; l <= E.L; ++l) E.dims[l] = e_net->dims[l];
+  for (int l = 0; l < E.L; ++l) {
+    E.off_w[l] = off; off += E.dims[l] * E.dims[l + 1];
+    E.off_rho[l] = -1;
+    E.off_b[l] = off; off += E.dims[l + 1];
+  }
+  E.n_params = off - E.base;
+  t->n0 = off;
+  int rc;
+  if ((rc = tr_fill_disc(dz_net, t->dz, zd, "dz_net")) || (rc = tr_fill_disc(dx_net, t->dx, xd, "dx_net"))) { delete t; return rc; }
+  t->dx_base = t->dz.n_params;
+  t->n1 = t->dz.n_params + t->dx.n_params;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
+  const int n[2] = {t->n0, t->n1};
+  for (int gi = 0; gi < 2 && e == cudaSuccess; ++gi) {
+    const size_t bytes = sizeof(float) * (size_t)n[gi];
+    float** arrs[4] = {&t->theta[gi], &t->grad[gi], &t->m_pre[gi], &t->v_pre[gi]};
+    for (float** a : arrs) {
+      if (e == cudaSuccess) e = cudaMalloc(a, bytes);
+      if (e == cudaSuccess) e = cudaMemset(*a, 0, bytes);
+    }
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&t->m_it, sizeof(float) * (size_t)t->n_g);
+  if (e == cudaSuccess) e = cudaMalloc(&t->v_it, sizeof(float) * (size_t)t->n_g);
+  if (e == cudaSuccess) e = cudaMemset(t->m_it, 0, sizeof(float) * (size_t)t->n_g);
+  if (e == cudaSuccess) e = cudaMemset(t->v_it, 0, sizeof(float) * (size_t)t->n_g);
+  if (e == cudaSuccess) e = cudaMalloc(&t->moving, sizeof(float) * 2 * zd);
+  if (e == cudaSuccess) e = cudaMalloc(&t->scratch, sizeof(float) * 64);
+  if (e == cudaSuccess) {
+    std::vector<float> host(t->n0, 0.f);
+    memcpy(host.data() + G.off_gamma, g->bn, sizeof(float) * zd);
+    memcpy(host.data() + G.off_beta, g->bn + zd, sizeof(float) * zd);
+    const float* p = g->hidden_params;
+    for (int l = 0; l < nh; ++l) {
+      const int cnt = G.dims[l] * G.dims[l + 1] + G.dims[l + 1];
+      memcpy(host.data() + G.off_w[l], p, sizeof(float) * cnt);
+      p += cnt;
+    }
+    const int last = G.dims[nh];
+    for (int k = 0; k < last; ++k)
+      for (int c = 0; c < xd; ++c) {
+        host[G.off_w[nh] + (size_t)k * 2 * xd + c] = g->mean_params[(size_t)k * xd + c];
+        host[G.off_w[nh] + (size_t)k * 2 * xd + xd + c] = g->var_params[(size_t)k * xd + c];
+      }
+    for (int c = 0; c < xd; ++c) {
+      host[G.off_b[nh] + c] = g->mean_params[(size_t)last * xd + c];
+      host[G.off_b[nh] + xd + c] = g->var_params[(size_t)last * xd + c];
+    }
+    memcpy(host.data() + E.base, e_net->params, sizeof(float) * E.n_params);
+    e = cudaMemcpy(t->theta[0], host.data(), sizeof(float) * t->n0, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t->moving, g->bn + 2 * zd, sizeof(float) * 2 * zd, cudaMemcpyHostToDevice);
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(t->theta[1], dz_net->params, sizeof(float) * t->dz.n_params, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(t->theta[1] + t->dx_base, dx_net->params, sizeof(float) * t->dx.n_params, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    bgm_ltb_destroy(t);
+    return fail(BGM_ERR_CUDA, std::string("bgm_ltb_create: ") + cudaGetErrorString(e));
+  }
+  *out = t;
+  return 0;
+}
+
+int bgm_ltb_buffers(bgm_ltb* t, int group, int* n_params, float** theta_dev, float** grad_dev) {
+  if (!t || group < 0 || group > 1) return bgm::fail(BGM_ERR_ARG, "bgm_ltb_buffers: bad trainer / group");
+  if (n_params) *n_params = group == 0 ? t->n0 : t->n1;
+  if (theta_dev) *theta_dev = t->theta[group];
+  if (grad_dev) *grad_dev = t->grad[group];
+  return 0;
+}
+int bgm_ltb_get_params(bgm_ltb* t, int group, float* host_out) {
+  using namespace bgm;
+  if (!t || group < 0 || group > 1 || !host_out) return fail(BGM_ERR_ARG, "bgm_ltb_get_params: bad argument");
+  BGM_CUDA_OK(cudaMemcpy(host_out, t->theta[group], sizeof(float) * (size_t)(group == 0 ? t->n0 : t->n1), cudaMemcpyDeviceToHost));
+  return 0;
+}
+int bgm_ltb_bn_moving(bgm_ltb* t, float* host_inout, int set) {
+  using namespace bgm;
+  if (!t || !host_inout) return fail(BGM_ERR_ARG, "bgm_ltb_bn_moving: needs a trainer and a buffer");
+  if (set) BGM_CUDA_OK(cudaMemcpy(t->moving, host_inout, sizeof(float) * 2 * t->zd, cudaMemcpyHostToDevice));
+  else BGM_CUDA_OK(cudaMemcpy(host_inout, t->moving, sizeof(float) * 2 * t->zd, cudaMemcpyDeviceToHost));
+  return 0;
+}
+int bgm_ltb_adam(bgm_ltb* t, int group, float grad_scale, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!t || group < 0 || group > 1) return fail(BGM_ERR_ARG, "bgm_ltb_adam: bad trainer / group");
+  const int n = group == 0 ? t->n0 : t->n1;
+  t->step_pre[group] += 1;
+  const float lr_t = lr_t_of(t->lr, t->b1, t->b2, t->step_pre[group]);
+  lt::adam_kernel<<<grid_for(n, t->sm_count), 256, 0, (cudaStream_t)stream>>>(t->theta[group], t->grad[group], t->m_pre[group],
+                                                                           t->v_pre[group], n, lr_t, (float)t->b1, (float)t->b2,
+                                                                           1e-7f, grad_scale);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+namespace bgm {
+namespace lt {
+static size_t ltb_step_bytes(const bgm_ltb* t, long long B) {
+  size_t b = 2 * pass_bytes(t->g, B) + 2 * pass_bytes(t->e, B) + 2 * disc_bytes(t->dz, B) + 2 * disc_bytes(t->dx, B);
+  b += 12 * (size_t)(4 * B * (2 * t->xd + t->zd + 8) + 512);
+  return b + (1 << 16);
+}
+static Ctx ctx_of(bgm_ltb* t) { return Ctx{&t->arena, t->theta[0], t->grad[0], t->sm_count, 0}; }
+// generator forward in TRAINING mode: batch statistics + the moving-statistics update Keras does on every such call
+static void g_fwd_train(bgm_ltb* t, const Ctx& C, Pass& P, const float* Z, int ldz, int B, cudaStream_t st) {
+  net_fwd(C, t->g, P, Z, ldz, B, 0, 0, -1, nullptr, nullptr, st);
+  moving_update_kernel<<<1, 64, 0, st>>>(t->moving, P.mean, P.inv, t->zd);
+}
+}  // namespace lt
+}  // namespace bgm
+
+extern "C" {
+
+// BGM.train_disc_step gradients (bgm/base.py:190-240, gamma == 0) into group 1 = [dz | dx]
+int bgm_ltb_disc_grad(bgm_ltb* t, const float* z_dev, const float* x_dev, int bs, float eps_z, float eps_x,
+                      const float* noise_dev, float* losses_dev, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  (void)eps_z; (void)eps_x;     // only the gradient penalty (gamma != 0) reads the interpolation draws
+  if (!t || !z_dev || !x_dev || !noise_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_ltb_disc_grad: null argument");
+  if (bs < 2) return fail(BGM_ERR_ARG, "bgm_ltb_disc_grad: batch size must be >= 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_arena_bytes(t->arena, ltb_step_bytes(t, bs));
+  if (rc) return rc;
+  Arena& ar = t->arena;
+  const Ctx C = ctx_of(t);
+  const int B = bs, xd = t->xd, zd = t->zd, sm = t->sm_count;
+  zero(t->grad[1], t->n1, sm, st);
+  Pass eA, gA;
+  net_fwd(C, t->e, eA, x_dev, xd, B, 0, 0, -1, nullptr, nullptr, st);            // z_ = e(x) (:203)
+  g_fwd_train(t, C, gA, z_dev, zd, B, st);                                        // (:207)
+  float* xgen = ar.get<float>((size_t)B * xd);
+  reparam_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(gA.out(), noise_dev, B, xd, xgen);   // x_ (:208)
+  const float* thz = t->theta[1];
+  const float* thx = t->theta[1] + t->dx_base;
+  DiscPass Dz, Dz_, Dx, Dx_;
+  disc_fwd(C, t->dz, thz, Dz, z_dev, B, st);
+  disc_fwd(C, t->dz, thz, Dz_, eA.out(), B, st);
+  disc_fwd(C, t->dx, thx, Dx, x_dev, B, st);
+  disc_fwd(C, t->dx, thx, Dx_, xgen, B, st);
+  float* dd = ar.get<float>(4 * (size_t)B);
+  bgm_disc_loss_kernel<<<1, 256, 0, st>>>(Dz.d, Dz_.d, Dx.d, Dx_.d, B, dd, dd + B, dd + 2 * B, dd + 3 * B, losses_dev);
+  disc_bwd(C, t->dz, thz, t->grad[1], Dz, dd, B, nullptr, st);
+  disc_bwd(C, t->dz, thz, t->grad[1], Dz_, dd + B, B, nullptr, st);
+  disc_bwd(C, t->dx, thx, t->grad[1] + t->dx_base, Dx, dd + 2 * B, B, nullptr, st);
+  disc_bwd(C, t->dx, thx, t->grad[1] + t->dx_base, Dx_, dd + 3 * B, B, nullptr, st);
+  return arena_ok(t->arena, "bgm_ltb_disc_grad");
+}
+
+// BGM.train_gen_step gradients (bgm/base.py:247-285) into group 0 = [g | e]
+int bgm_ltb_gen_grad(bgm_ltb* t, const float* z_dev, const float* x_dev, int bs, const float* noise1_dev,
+                     const float* noise2_dev, float* losses_dev, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!t || !z_dev || !x_dev || !noise1_dev || !noise2_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_ltb_gen_grad: null argument");
+  if (bs < 2) return fail(BGM_ERR_ARG, "bgm_ltb_gen_grad: batch size must be >= 2");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_arena_bytes(t->arena, ltb_step_bytes(t, bs));
+  if (rc) return rc;
+  Arena& ar = t->arena;
+  const Ctx C = ctx_of(t);
+  const int B = bs, xd = t->xd, zd = t->zd, sm = t->sm_count;
+  zero(t->grad[0], t->n0, sm, st);
+  Pass gA, gB, eA, eB;
+  g_fwd_train(t, C, gA, z_dev, zd, B, st);                                        // :258
+  float* x1 = ar.get<float>((size_t)B * xd);
+  reparam_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(gA.out(), noise1_dev, B, xd, x1);    // x_ :259
+  net_fwd(C, t->e, eA, x_dev, xd, B, 0, 0, -1, nullptr, nullptr, st);            // z_ :262
+  net_fwd(C, t->e, eB, x1, xd, B, 0, 0, -1, nullptr, nullptr, st);               // z__ :264
+  g_fwd_train(t, C, gB, eA.out(), zd, B, st);                                     // :266
+  float* x2 = ar.get<float>((size_t)B * xd);
+  reparam_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(gB.out(), noise2_dev, B, xd, x2);    // x__ :267
+  const float* thz = t->theta[1];
+  const float* thx = t->theta[1] + t->dx_base;
+  DiscPass Dx_, Dz_;
+  disc_fwd(C, t->dx, thx, Dx_, x1, B, st);                                         // :269
+  disc_fwd(C, t->dz, thz, Dz_, eA.out(), B, st);                                   // :270
+  BgmGenLossArgs L;
+  memset(&L, 0, sizeof(L));
+  L.B = B; L.xd = xd; L.zd = zd; L.alpha = t->alpha;
+  L.x = x_dev; L.z = z_dev; L.out1 = gA.out(); L.x2 = x2; L.z2 = eB.out(); L.dx_ = Dx_.d; L.dz_ = Dz_.d;
+  L.dX2 = ar.get<float>((size_t)B * xd); L.dZ2 = ar.get<float>((size_t)B * zd); L.ddx = ar.get<float>(B); L.ddz = ar.get<float>(B);
+  L.dOut1 = ar.get<float>((size_t)B * 2 * xd);
+  L.losses = losses_dev;
+  bgm_gen_loss_kernel<<<1, 256, 0, st>>>(L);
+  float* dOut2 = ar.get<float>((size_t)B * 2 * xd);
+  float* dZ_ = ar.get<float>((size_t)B * zd);          // gradient w.r.t. z_ = e(x)
+  float* dX1 = ar.get<float>((size_t)B * xd);          // gradient w.r.t. x_
+  zero(dZ_, (long long)B * zd, sm, st);
+  zero(dX1, (long long)B * xd, sm, st);
+  reparam_bwd_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(L.dX2, gB.out(), noise2_dev, B, xd, dOut2, 0);
+  net_bwd(C, t->g, gB, dOut2, true, dZ_, zd, true, st);
+  disc_bwd(C, t->dz, thz, nullptr, Dz_, L.ddz, B, dZ_, st);
+  net_bwd(C, t->e, eB, L.dZ2, true, dX1, xd, true, st);
+  disc_bwd(C, t->dx, thx, nullptr, Dx_, L.ddx, B, dX1, st);
+  reparam_bwd_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(dX1, gA.out(), noise1_dev, B, xd, L.dOut1, 1);
+  net_bwd(C, t->g, gA, L.dOut1, true, nullptr, 0, false, st);
+  net_bwd(C, t->e, eA, dZ_, true, nullptr, 0, false, st);
+  return arena_ok(t->arena, "bgm_ltb_gen_grad");
+}
+
+int bgm_ltb_set_iter(bgm_ltb* t, float lr_theta, float lr_z) {
+  using namespace bgm;
+  if (!t) return fail(BGM_ERR_ARG, "bgm_ltb_set_iter: null trainer");
+  t->lr_theta = lr_theta; t->lr_z = lr_z;
+  t->step_g = 0; t->step_z = 0;
+  BGM_CUDA_OK(cudaMemset(t->m_it, 0, sizeof(float) * (size_t)t->n_g));
+  BGM_CUDA_OK(cudaMemset(t->v_it, 0, sizeof(float) * (size_t)t->n_g));
+  return 0;
+}
+
+// update_g_net (bgm/base.py:145-164) on the rows idx_dev
+int bgm_ltb_iter_g(bgm_ltb* t, const float* zt_dev, const float* x_dev, const int* idx_dev, int bs, int apply,
+                   float grad_scale, float* losses_dev, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!t || !zt_dev || !x_dev || !idx_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_ltb_iter_g: null argument");
+  if (bs < 1) return fail(BGM_ERR_ARG, "bgm_ltb_iter_g: batch size must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = bs, xd = t->xd, zd = t->zd, sm = t->sm_count;
+  if (apply != 2) {
+    int rc = ensure_arena_bytes(t->arena, ltb_step_bytes(t, bs));
+    if (rc) return rc;
+    Arena& ar = t->arena;
+    const Ctx C = ctx_of(t);
+    zero(t->grad[0], t->n_g, sm, st);
+    float* zb = ar.get<float>((size_t)B * zd);
+    float* xb = ar.get<float>((size_t)B * xd);
+    gather_cols_kernel<<<grid_for((long long)B * zd, sm), 256, 0, st>>>(zt_dev, zd, idx_dev, 0, zd, B, zb, zd, 0);
+    gather_cols_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(x_dev, xd, idx_dev, 0, xd, B, xb, xd, 0);
+    Pass gP;
+    g_fwd_train(t, C, gP, zb, zd, B, st);
+    float* dOut = ar.get<float>((size_t)B * 2 * xd);
+    bgm_nll_kernel<<<1, 256, 0, st>>>(xb, gP.out(), B, xd, dOut, losses_dev);
+    net_bwd(C, t->g, gP, dOut, true, nullptr, 0, false, st);
+    rc = arena_ok(t->arena, "bgm_ltb_iter_g");
+    if (rc) return rc;
+  }
+  if (apply != 0) {
+    t->step_g += 1;
+    const float lr_t = lr_t_of(t->lr_theta, 0.9, 0.99, t->step_g);
+    lt::adam_kernel<<<grid_for(t->n_g, sm), 256, 0, st>>>(t->theta[0], t->grad[0], t->m_it, t->v_it, t->n_g, lr_t, 0.9f, 0.99f, 1e-7f,
+                                                       grad_scale);
+    BGM_CUDA_OK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// update_latent_variable_sgd (bgm/base.py:167-187) + the write-back of :410-413
+int bgm_ltb_iter_latent(bgm_ltb* t, float* zt_dev, const float* x_dev, const int* idx_dev, int bs, float* loss_dev,
+                        float* gz_out_dev, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!t || !zt_dev || !x_dev || !idx_dev || !loss_dev) return fail(BGM_ERR_ARG, "bgm_ltb_iter_latent: null argument");
+  if (bs < 1) return fail(BGM_ERR_ARG, "bgm_ltb_iter_latent: batch size must be >= 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = ensure_arena_bytes(t->arena, ltb_step_bytes(t, bs));
+  if (rc) return rc;
+  Arena& ar = t->arena;
+  const Ctx C = ctx_of(t);
+  const int B = bs, xd = t->xd, zd = t->zd, sm = t->sm_count;
+  float* zb = ar.get<float>((size_t)B * zd);
+  float* xb = ar.get<float>((size_t)B * xd);
+  gather_cols_kernel<<<grid_for((long long)B * zd, sm), 256, 0, st>>>(zt_dev, zd, idx_dev, 0, zd, B, zb, zd, 0);
+  gather_cols_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(x_dev, xd, idx_dev, 0, xd, B, xb, xd, 0);
+  Pass gP;
+  g_fwd_train(t, C, gP, zb, zd, B, st);
+  float* dOut = ar.get<float>((size_t)B * 2 * xd);
+  float* losses = t->scratch;
+  zero(losses, 8, sm, st);
+  bgm_nll_kernel<<<1, 256, 0, st>>>(xb, gP.out(), B, xd, dOut, losses);
+  float* dZ = ar.get<float>((size_t)B * zd);
+  gather_cols_kernel<<<grid_for((long long)B * zd, sm), 256, 0, st>>>(zb, zd, nullptr, 0, zd, B, dZ, zd, 0);
+  prior_scale_kernel<<<1, 256, 0, st>>>(dZ, B * zd, 1.f / (float)B, losses);        // loss_px_z + loss_prior_z (:179)
+  net_bwd(C, t->g, gP, dOut, false, dZ, zd, true, st);
+  BGM_CUDA_OK(cudaMemcpyAsync(loss_dev, losses, sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (gz_out_dev) BGM_CUDA_OK(cudaMemcpyAsync(gz_out_dev, dZ, sizeof(float) * (size_t)B * zd, cudaMemcpyDeviceToDevice, st));
+  t->step_z += 1;
+  const float lr_t = lr_t_of(t->lr_z, 0.9, 0.99, t->step_z);
+  fresh_adam_rows_kernel<<<grid_for((long long)B * zd, sm), 256, 0, st>>>(zt_dev, idx_dev, dZ, B, zd, lr_t, 0.9f, 0.99f, 1e-7f);
+  return arena_ok(t->arena, "bgm_ltb_iter_latent");
+}
+
+// evaluate(use_x_sd=False) (bgm/base.py:446-471): sum over rows and columns of (x - mu(z))^2, generator in inference mode
+int bgm_ltb_evaluate(bgm_ltb* t, const float* zt_dev, const float* x_dev, int n, double* sum_dev, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!t || !zt_dev || !x_dev || !sum_dev || n < 1) return fail(BGM_ERR_ARG, "bgm_ltb_evaluate: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = std::min(n, 8192), xd = t->xd, zd = t->zd, sm = t->sm_count;
+  int rc = ensure_arena_bytes(t->arena, ltb_step_bytes(t, chunk));
+  if (rc) return rc;
+  const Ctx C = ctx_of(t);
+  zero(reinterpret_cast<float*>(sum_dev), 2, sm, st);
+  float* stats = t->scratch + 8;         // zd <= 16 in practice; scratch holds 64 floats
+  if (2 * zd > 56) return fail(BGM_ERR_UNSUPPORTED, "bgm_ltb_evaluate: z_dim <= 28");
+  moving_to_stats_kernel<<<1, 64, 0, st>>>(t->moving, zd, stats, stats + zd);
+  for (int r0 = 0; r0 < n; r0 += chunk) {
+    const int B = std::min(chunk, n - r0);
+    t->arena.used = 0;
+    Pass gP;
+    net_fwd(C, t->g, gP, zt_dev + (size_t)r0 * zd, zd, B, 0, r0, -1, stats, stats + zd, st);
+    sq_err_kernel<<<grid_for((long long)B * xd, sm), 256, 0, st>>>(x_dev + (size_t)r0 * xd, xd, gP.out(), 2 * xd, B, xd, 0, sum_dev);
+  }
+  return arena_ok(t->arena, "bgm_ltb_evaluate");
+}
+
+// e_net(x) for all n rows -> z_out_dev (n, z_dim)  (`data_z_init = self.e_net(data)`, bgm/base.py:388)
+int bgm_ltb_encode(bgm_ltb* t, const float* x_dev, int n, float* z_out_dev, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!t || !x_dev || !z_out_dev || n < 1) return fail(BGM_ERR_ARG, "bgm_ltb_encode: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunk = std::min(n, 8192), xd = t->xd, zd = t->zd;
+  int rc = ensure_arena_bytes(t->arena, ltb_step_bytes(t, chunk));
+  if (rc) return rc;
+  const Ctx C = ctx_of(t);
+  for (int r0 = 0; r0 < n; r0 += chunk) {
+    const int B = std::min(chunk, n - r0);
+    t->arena.used = 0;
+    Pass eP;
+    net_fwd(C, t->e, eP, x_dev + (size_t)r0 * xd, xd, B, 0, r0, -1, nullptr, nullptr, st);
+    BGM_CUDA_OK(cudaMemcpyAsync(z_out_dev + (size_t)r0 * zd, eP.out(), sizeof(float) * (size_t)B * zd, cudaMemcpyDeviceToDevice, st));
+  }
+  return arena_ok(t->arena, "bgm_ltb_encode");
 }
 
 }  // extern "C"

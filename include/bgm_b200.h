@@ -503,6 +503,32 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
 int bgm_lt_evaluate(bgm_lt* t, const float* zt_dev, const float* x_dev, const float* y_dev, const float* v_dev, int n,
                     double* sums_dev, float* z_out_dev, void* stream);
 
+/* BGM flavour of the layered engine (bgm/base.py:145-291): the entry points of bgm_bgmtrainer_create /
+ * bgm_bgm_train_disc_grad / bgm_bgm_train_gen_grad / bgm_train_adam / bgm_trainer_bn_moving /
+ * bgm_bgmtrainer_set_iter / bgm_bgm_iter_g / bgm_bgm_iter_latent / bgm_bgm_evaluate with the same arguments,
+ * the same device parameter layout and the same semantics, for any x_dim and any batch size (the fused kernels
+ * stop at x_dim ~ 110 and 32 rows).  gamma (gradient-penalty weight, :236) must be 0: the layered engine has no
+ * double backward.  bgm_ltb_encode: e_net(x) for n rows (`data_z_init = self.e_net(data)`, :388). */
+typedef struct bgm_ltb bgm_ltb;
+int bgm_ltb_create(bgm_ltb** out, const bgm_varnet_desc* g_net, const bgm_net_desc* e_net, const bgm_disc_desc* dz_net,
+                   const bgm_disc_desc* dx_net, float lr, float beta_1, float beta_2, float alpha, float gamma);
+void bgm_ltb_destroy(bgm_ltb* t);
+int bgm_ltb_buffers(bgm_ltb* t, int group, int* n_params, float** theta_dev, float** grad_dev);
+int bgm_ltb_get_params(bgm_ltb* t, int group, float* host_out);
+int bgm_ltb_bn_moving(bgm_ltb* t, float* host_inout, int set);
+int bgm_ltb_adam(bgm_ltb* t, int group, float grad_scale, void* stream);
+int bgm_ltb_disc_grad(bgm_ltb* t, const float* z_dev, const float* x_dev, int bs, float eps_z, float eps_x,
+                      const float* noise_dev, float* losses_dev, void* stream);
+int bgm_ltb_gen_grad(bgm_ltb* t, const float* z_dev, const float* x_dev, int bs, const float* noise1_dev,
+                     const float* noise2_dev, float* losses_dev, void* stream);
+int bgm_ltb_set_iter(bgm_ltb* t, float lr_theta, float lr_z);
+int bgm_ltb_iter_g(bgm_ltb* t, const float* zt_dev, const float* x_dev, const int* idx_dev, int bs, int apply,
+                   float grad_scale, float* losses_dev, void* stream);
+int bgm_ltb_iter_latent(bgm_ltb* t, float* zt_dev, const float* x_dev, const int* idx_dev, int bs, float* loss_dev,
+                        float* gz_out_dev, void* stream);
+int bgm_ltb_evaluate(bgm_ltb* t, const float* zt_dev, const float* x_dev, int n, double* sum_dev, void* stream);
+int bgm_ltb_encode(bgm_ltb* t, const float* x_dev, int n, float* z_out_dev, void* stream);
+
 /* ---- host-side index / prior streams (no device work) ----
  * NumPy's LEGACY generator (MT19937 `RandomState`) restated natively so that the mini-batch index
  * and prior streams of the training loops are produced bit-exactly off the Python thread:

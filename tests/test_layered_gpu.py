@@ -154,3 +154,86 @@ def test_bnn_fit_runs_end_to_end_on_shipped_config():
     assert len(m.egm_history) == 4 and all(np.isfinite(h[1:]).all() for h in m.egm_history)
     adrf, interval = m.predict(data=(x, y, v), alpha=0.05, n_mcmc=10, burn_in=10, x_values=[0.5, 1.5], q_sd=1.0, bs=320, verbose=0)
     assert np.isfinite(adrf).all() and interval.shape == (2, 2)
+
+
+# ------------------------------------------------------------------ BGM flavour (a14) ----
+from oracle import train_bgm                                   # noqa: E402
+from oracle import train                                        # noqa: E402
+from test_train_gpu import make_bgm, bgm_gen_device_layout, check_grads, split_like   # noqa: E402
+
+BGM_WIDE = [dict(x_dim=500, z_dim=10, bs=32), dict(x_dim=500, z_dim=10, bs=64, alpha=0.1), dict(x_dim=100, z_dim=10, bs=96),
+            dict(x_dim=33, z_dim=5, bs=17, g_units=(16, 16), e_units=[16, 16], alpha=0.5)]
+
+
+@pytest.mark.parametrize("kw", BGM_WIDE)
+def test_bgm_layered_gen_and_disc_gradients(kw):
+    """BASELINE cfg-5 width (x_dim = 500) and batches > 32: beyond the fused single-CTA kernels."""
+    params, g, e, dz, dx, m, z, x, n1, n2 = make_bgm(**kw)
+    m._set_layered(True)
+    want_losses, want, stats = train_bgm.gen_step(params, g, e, dz, dx, z, x, n1, n2)
+    losses, flat = m.gradients('gen', z, x, noise=n1, noise2=n2)
+    np.testing.assert_allclose(losses, want_losses, rtol=3e-4, atol=1e-6)
+    want_dev = bgm_gen_device_layout(want, g, params['x_dim'])
+    check_grads(split_like(flat, want_dev), want_dev)
+    want_losses, want, stats = train_bgm.disc_step(params, g, e, dz, dx, z, x, 0.3, 0.7, n1)
+    losses, flat = m.gradients('disc', z, x, eps_z=0.3, eps_x=0.7, noise=n1)
+    np.testing.assert_allclose(losses, want_losses, rtol=3e-4, atol=2e-6)
+    check_grads(split_like(flat, want), want)
+
+
+def test_bgm_wide_model_falls_back_to_the_layered_engine_and_trains():
+    """x_dim = 500 does not fit the fused kernels (BGM_ERR_NOMEM): the model picks the layered engine by itself;
+    steps track the oracle, the moving statistics follow Keras' update, fit() runs end to end."""
+    params, g, e, dz, dx, m, z, x, n1, n2 = make_bgm(x_dim=500, z_dim=10, bs=32, lr=1e-3)
+    import copy
+    g0 = copy.deepcopy(g)
+    gen_opt, d_opt = train.Adam(1e-3, 0.5, 0.9), train.Adam(1e-3, 0.5, 0.9)
+    for k in range(2):
+        _, grads, stats = train_bgm.disc_step(params, g, e, dz, dx, z, x, 0.3, 0.7, n1)
+        d_opt.apply(train.disc_flat_params(dz) + train.disc_flat_params(dx), grads)
+        train_bgm.update_moving(g, stats)
+        m.train_disc_step(z, x, eps_z=0.3, eps_x=0.7, noise=n1)
+        _, grads, stats = train_bgm.gen_step(params, g, e, dz, dx, z, x, n1, n2)
+        gen_opt.apply(train_bgm.g_flat_params(g) + train.flat_params(e), grads)
+        train_bgm.update_moving(g, stats)
+        m.train_gen_step(z, x, noise1=n1, noise2=n2)
+    assert m._layered
+    w = m.get_weights()
+    np.testing.assert_allclose(w['g'][2], g['bn']['mean'], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(w['g'][3], g['bn']['var'], rtol=1e-4, atol=1e-5)
+    assert not np.allclose(w['g'][2], g0['bn']['mean'])
+    want_g = [g['bn']['gamma'], g['bn']['beta']] + [a for W, b in g['hidden'] for a in (W, b)] + list(g['mean']) + list(g['var'])
+    for a, b in zip(w['g'][:2] + w['g'][4:], want_g):
+        assert np.median(np.abs(a - b)) <= 2e-5
+    # iterative phase on the same engine: gradient rows and updated rows vs the oracle
+    rs = np.random.RandomState(8)
+    n = 200
+    data = rs.standard_normal((n, 500)).astype(np.float32)
+    zt = rs.standard_normal((n, 10)).astype(np.float32)
+    idx = rs.choice(n, 48, replace=False)
+    gnow = dict(bn=dict(gamma=w['g'][0], beta=w['g'][1], mean=w['g'][2], var=w['g'][3]),
+                hidden=[(w['g'][4 + 2 * i], w['g'][5 + 2 * i]) for i in range(len(g['hidden']))],
+                mean=(w['g'][-4], w['g'][-3]), var=(w['g'][-2], w['g'][-1]))
+    lx, lm, gg, _ = train_bgm.iter_g_grads(gnow, zt[idx], data[idx])
+    (gl, gm), gzl, ggz, cur = m.iter_step(zt, data, idx, apply=False)
+    assert abs(gl - lx) < 3e-4 * max(1, abs(lx)) and abs(gm - lm) < 3e-4 * max(1, abs(lm))
+    wl, wgz, _ = train_bgm.iter_latent_grad(gnow, zt[idx], data[idx])
+    assert abs(gzl - wl) < 3e-4 * max(1, abs(wl))
+    assert np.abs(ggz - wgz).max() < 3e-3 * np.abs(wgz).max()
+    assert np.abs(cur[np.setdiff1d(np.arange(n), idx)] - zt[np.setdiff1d(np.arange(n), idx)]).max() == 0
+    # evaluate / encode / fit
+    mse = m.evaluate(data, data_z=zt, use_x_sd=False)
+    assert np.isfinite(mse)
+    m2_params, g2, *_ = make_bgm(x_dim=500, z_dim=10, bs=32)
+    from helpers import bgm_product_model
+    m2 = bgm_product_model(dict(m2_params, save_res=False, save_model=False), g2)
+    m2.fit(data, batch_size=64, epochs=1, epochs_per_eval=1, use_egm_init=True, egm_n_iter=6, egm_batches_per_eval=3, verbose=0)
+    assert m2._layered and np.isfinite(m2.history_loss).all()
+    zenc = m2._encode_host(data)
+    want = data
+    L = len(m2.e_net.layers)
+    for i, (W, b) in enumerate(m2.e_net.layers):
+        want = want @ W + b
+        if i < L - 1:
+            want = np.where(want > 0, want, 0.2 * want)
+    np.testing.assert_allclose(zenc, want, rtol=2e-4, atol=2e-4)

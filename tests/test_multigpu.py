@@ -80,6 +80,10 @@ def _egm_worker(rank, world, port, out):
         x, y, v = causal_data(32, 200, seed=10 + r)
         batches.append((rs.standard_normal((32, 5)).astype(np.float32), v, x, y))
     m = product_model(params, nets)
+    # the discriminator is initialised from NumPy's global generator: give every model the same one
+    dz0 = [np.random.RandomState(9).standard_normal(a.shape).astype(np.float32) * 0.3 + (1.0 if i % 4 == 2 else 0.0)
+           for i, a in enumerate(m.dz_net.trainable_list())]
+    m.set_weights(dz=dz0)
     z, v, x, y = batches[rank]
     m.train_gen_step(z, v, x, y, group=dist.group.WORLD)
     m.train_disc_step(z, v, epsilon=0.3, group=dist.group.WORLD)
@@ -90,6 +94,7 @@ def _egm_worker(rank, world, port, out):
     if rank == 0:
         # single process: average of the two gradients, then the same Adam step
         ref = product_model(params, nets)
+        ref.set_weights(dz=dz0)
         tr = ref._device_trainer()
         for group_id, which in ((0, 'gen'), (1, 'disc')):
             tot = None
