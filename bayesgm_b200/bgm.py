@@ -150,6 +150,10 @@ class BGM(object):
                      bgm_bgm_iter_latent="bgm_ltb_iter_latent", bgm_bgm_evaluate="bgm_ltb_evaluate")
 
     def _tfn(self, name):
+        """Symbol of the active training engine.  The engine is only known once the trainer exists (a model too
+        wide for the fused kernels falls back to the layered engine at creation)."""
+        if self._trainer is None and name not in ("bgm_trainer_destroy", "bgm_bgmtrainer_create"):
+            self._device_trainer()
         return self._LT_NAMES[name] if self._layered else name
 
     def _set_layered(self, on):

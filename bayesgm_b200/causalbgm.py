@@ -523,16 +523,29 @@ class CausalBGM(object):
             del local, rowtot, rowend, scratch
             return self._effect_device(z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=noise,
                                        memoise=False)
-        zlist = torch.empty((n_distinct, zd), dtype=torch.float32, device='cuda')
+        # the number of distinct states changes from call to call: carve these two out of workspaces that only
+        # grow (geometrically), so that repeated predict() calls do not cudaMalloc / cudaFree gigabytes each time
+        zlist = self._workspace('zlist', n_distinct * zd, torch).view(n_distinct, zd)
         _lib.call("bgm_causal_effect_compact", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(local), _lib.ptr(rowend),
                   _lib.ptr(zlist), st)
-        heads = torch.empty((n_distinct, n_x, 2), dtype=torch.float32, device='cuda')
+        heads = self._workspace('heads', n_distinct * n_x * 2, torch).view(n_distinct, n_x, 2)
         _lib.call("bgm_causal_effect_heads", m, _lib.ptr(zlist), n_distinct, _lib.ptr(xv), n_x, _lib.ptr(heads), st)
         _lib.call("bgm_causal_effect_combine", m, _lib.ptr(heads), _lib.ptr(local), _lib.ptr(rowend), n_keep, n, n_x,
                   int(bool(sample_y)), seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
                   _lib.ptr(out) if binary else None, st)
         self.last_distinct_fraction = n_distinct / float(total)
         return out
+
+    def _workspace(self, name, numel, torch):
+        """float32 device workspace of at least `numel` elements, kept on the model and grown by >= 1.3x."""
+        ws = getattr(self, '_ws', None)
+        if ws is None:
+            ws = self._ws = {}
+        t = ws.get(name)
+        if t is None or t.numel() < numel:
+            ws[name] = None
+            t = ws[name] = torch.empty(int(max(numel, 1) * 1.3) + 1024, dtype=torch.float32, device='cuda')
+        return t[:numel]
 
     def infer_from_latent_posterior(self, data_posterior_z, x_values=None, sample_y=True, eps=1e-6, *,
                                     seed=None, noise=None):
