@@ -13,6 +13,7 @@ struct bgm_bnn {
   float* image_dev = nullptr;
   int smem_bytes = 0;
   int zmax = 0;
+  int sm_count = 148;
   long long macs = 0;
 };
 
@@ -63,18 +64,25 @@ static int pack_net(const bgm_bnn_net_desc* d, const char* name, int want_in, in
 
 static int zmax_of(int zd) { return zd <= 8 ? 8 : (zd <= 16 ? 16 : 32); }
 
+// Rows (= threads) per CTA.  One CTA per SM (shared memory): a slice smaller than SMs x 256 rows is cut into one
+// wave of equal CTAs (n = 20000 on 148 SMs: 125 CTAs of 160 rows instead of 79 of 256), larger slices use 256.
+static int rows_per_cta(const bgm_bnn* m, int n) {
+  const int per_sm = (n + m->sm_count - 1) / m->sm_count;
+  const int warps = std::min(8, std::max(2, (per_sm + 31) / 32));
+  return warps * 32;
+}
 template <int ZMAX>
-static int launch_mh(const bgm_bnn* m, const BnnMhDev& D, int ncta, cudaStream_t st) {
+static int launch_mh(const bgm_bnn* m, const BnnMhDev& D, int nth, int ncta, cudaStream_t st) {
   BGM_CUDA_OK(cudaFuncSetAttribute(bnn_mh_kernel<ZMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_bytes));
-  bnn_mh_kernel<ZMAX><<<ncta, BNN_THREADS, m->smem_bytes, st>>>(m->prog, m->image_dev, D);
+  bnn_mh_kernel<ZMAX><<<ncta, nth, m->smem_bytes, st>>>(m->prog, m->image_dev, D);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
-static int launch(const bgm_bnn* m, const BnnMhDev& D, int ncta, cudaStream_t st) {
+static int launch(const bgm_bnn* m, const BnnMhDev& D, int nth, int ncta, cudaStream_t st) {
   switch (m->zmax) {
-    case 8: return launch_mh<8>(m, D, ncta, st);
-    case 16: return launch_mh<16>(m, D, ncta, st);
-    default: return launch_mh<32>(m, D, ncta, st);
+    case 8: return launch_mh<8>(m, D, nth, ncta, st);
+    case 16: return launch_mh<16>(m, D, nth, ncta, st);
+    default: return launch_mh<32>(m, D, nth, ncta, st);
   }
 }
 
@@ -113,6 +121,11 @@ int bgm_bnn_create(bgm_bnn** out, const int z_dims[4], int v_dim, int binary_tre
     return fail(rc == -2 ? BGM_ERR_UNSUPPORTED : BGM_ERR_ARG, "bgm_bnn_create: " + err);
   }
   m->zmax = zmax_of(zd);
+  {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (m->sm_count < 1) m->sm_count = 148;
+  }
   const int NP = 4 * m->zmax + 2;
   m->smem_bytes = (2 * ACT_FLOATS + 2 * W_FLOATS + 8 * NP + NP + 8) * 4;
   cudaError_t e = cudaMalloc(&m->image_dev, image.size() * sizeof(float));
@@ -142,7 +155,7 @@ int bgm_bnn_info(const bgm_bnn* m, int* smem_bytes, int* rows_per_cta, long long
 
 long long bgm_bnn_scratch_doubles(const bgm_bnn* m, int n) {
   if (!m || n < 1) return -1;
-  const long long ncta = (n + bgm::bnn::BNN_THREADS - 1) / bgm::bnn::BNN_THREADS;
+  const long long ncta = (n + 63) / 64;     // upper bound: the smallest CTA is 64 rows
   return 2 * ncta * (4 * m->zmax + 2);
 }
 
@@ -170,12 +183,13 @@ int bgm_bnn_logpost(const bgm_bnn* m, const float* x_dev, const float* y_dev, co
   D.a.seed = seed; D.a.row_offset = row_offset; D.a.init_mode = 1;
   D.slice = slice; D.call0 = call; D.z_in = z_dev; D.out_lp = out_logp_dev; D.part = scratch_dev;
   D.t = 0;
-  const int ncta = (n + BNN_THREADS - 1) / BNN_THREADS;
+  const int nth = rows_per_cta(m, n);
+  const int ncta = (n + nth - 1) / nth;
   D.mode = 2;
-  rc = launch(m, D, ncta, (cudaStream_t)stream);
+  rc = launch(m, D, nth, ncta, (cudaStream_t)stream);
   if (rc) return rc;
   D.mode = 1;
-  return launch(m, D, ncta, (cudaStream_t)stream);
+  return launch(m, D, nth, ncta, (cudaStream_t)stream);
 }
 
 int bgm_bnn_mh(const bgm_bnn* m, const bgm_mh_args* a, int slice, double* scratch_dev, float* lp_cur_trace_dev,
@@ -196,18 +210,19 @@ int bgm_bnn_mh(const bgm_bnn* m, const bgm_mh_args* a, int slice, double* scratc
   D.slice = slice;
   D.part = scratch_dev;
   D.lp_cur_trace = lp_cur_trace_dev;
-  const int ncta = (a->n + BNN_THREADS - 1) / BNN_THREADS;
+  const int nth = rows_per_cta(m, a->n);
+  const int ncta = (a->n + nth - 1) / nth;
   cudaStream_t st = (cudaStream_t)stream;
   // statistics of the first iteration (and the initial draw for init_mode 2), then one launch per iteration
   D.mode = 2;
   D.t = a->t_begin;
-  rc = launch(m, D, ncta, st);
+  rc = launch(m, D, nth, ncta, st);
   if (rc) return rc;
   D.mode = 0;
   D.a.init_mode = 0;
   for (int t = a->t_begin; t < a->t_end; ++t) {
     D.t = t;
-    rc = launch(m, D, ncta, st);
+    rc = launch(m, D, nth, ncta, st);
     if (rc) return rc;
   }
   return 0;

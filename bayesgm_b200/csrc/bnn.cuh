@@ -53,7 +53,7 @@ struct BnnProgram {
   BnnNet g, f, h;
 };
 
-constexpr int ACT_FLOATS = BNN_MAXK * BNN_THREADS;          // one activation buffer [64][256]
+constexpr int ACT_FLOATS = BNN_MAXK * BNN_THREADS;          // one activation buffer [64][rows per CTA], sized for 256
 constexpr int W_FLOATS = BNN_MAXK * 32;                     // one weight chunk [64][32]
 
 __device__ __forceinline__ float flip(float a, uint32_t bit) {
@@ -65,7 +65,7 @@ __device__ __forceinline__ void stage_chunk(const BnnLayer& Ly, const float* __r
                                             uint64_t seed, int slice, int net_id, int l, uint32_t call, int c, int tid) {
   const int N4 = (Ly.N + 3) & ~3;
   const int64_t base = ((int64_t)slice << 44) | ((int64_t)net_id << 40) | ((int64_t)l << 36);
-  for (int i = tid; i < Ly.K * 8; i += BNN_THREADS) {
+  for (int i = tid; i < Ly.K * 8; i += (int)blockDim.x) {
     const int k = i >> 3, q = i & 7;
     const int col = c * 32 + q * 4;
     const float4 lo = __ldg(reinterpret_cast<const float4*>(image + Ly.loc_off + (size_t)k * Ly.N32 + col));
@@ -85,12 +85,12 @@ __device__ __forceinline__ void stage_chunk(const BnnLayer& Ly, const float* __r
 template <int W>
 __device__ __forceinline__ void chunk_mac(const float* __restrict__ in, const float* __restrict__ Wl,
                                           const float* __restrict__ Wd, int K, uint64_t sin, uint32_t sout,
-                                          const float* __restrict__ bias, int tid, float (&acc)[W]) {
+                                          const float* __restrict__ bias, int tid, int nth, float (&acc)[W]) {
 #pragma unroll
   for (int j = 0; j < W; ++j) acc[j] = 0.f;
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {                       // ((x o s_in) dW)
-    const float a = flip(in[k * BNN_THREADS + tid], (uint32_t)((sin >> k) & 1ull));
+    const float a = flip(in[k * nth + tid], (uint32_t)((sin >> k) & 1ull));
     const float4* w = reinterpret_cast<const float4*>(Wd + k * 32);
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
@@ -105,7 +105,7 @@ __device__ __forceinline__ void chunk_mac(const float* __restrict__ in, const fl
   for (int j = 0; j < W; ++j) acc[j] = flip(acc[j], (sout >> j) & 1u);   // o s_out
 #pragma unroll 4
   for (int k = 0; k < K; ++k) {                       // + x loc
-    const float a = in[k * BNN_THREADS + tid];
+    const float a = in[k * nth + tid];
     const float4* w = reinterpret_cast<const float4*>(Wl + k * 32);
 #pragma unroll
     for (int q = 0; q < W / 4; ++q) {
@@ -127,6 +127,7 @@ struct NetCtx {
   int slice;
   int64_t grow;                      // global row of this thread (sign streams)
   int tid;
+  int nth;                           // rows (threads) per CTA = stride of the activation columns
 };
 
 // Forward pass of one Bayesian net for the thread's row.  The (already batch-normalised) input must
@@ -150,21 +151,21 @@ __device__ __forceinline__ void net_forward(const BnnNet& net, int net_id, const
       const float* bias = X.image + Ly.bias_off + c * 32;
       if (Ly.N <= 8) {                                  // narrow layers (32 -> 8, 8 -> 2): 8 accumulators
         float acc[8];
-        chunk_mac<8>(in, X.Wl, X.Wd, Ly.K, sin, sout, bias, X.tid, acc);
+        chunk_mac<8>(in, X.Wl, X.Wd, Ly.K, sin, sout, bias, X.tid, X.nth, acc);
         if (!last) {
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (j < Ly.N) out[j * BNN_THREADS + X.tid] = leaky(acc[j]);
+            if (j < Ly.N) out[j * X.nth + X.tid] = leaky(acc[j]);
         } else {
           fin(c, acc, 8);
         }
       } else {
         float acc[32];
-        chunk_mac<32>(in, X.Wl, X.Wd, Ly.K, sin, sout, bias, X.tid, acc);
+        chunk_mac<32>(in, X.Wl, X.Wd, Ly.K, sin, sout, bias, X.tid, X.nth, acc);
         if (!last) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (c * 32 + j < Ly.N) out[(c * 32 + j) * BNN_THREADS + X.tid] = leaky(acc[j]);
+            if (c * 32 + j < Ly.N) out[(c * 32 + j) * X.nth + X.tid] = leaky(acc[j]);
         } else {
           fin(c, acc, 32);
         }
@@ -202,7 +203,7 @@ __device__ __forceinline__ float eval_logpost(const BnnProgram& P, const NetCtx&
     const float* gm = img + P.g.bn_off;
 #pragma unroll
     for (int d = 0; d < ZMAX; ++d)
-      if (d < zd) X.actA[d * BNN_THREADS + X.tid] = bn_apply(z[d], S.zmean[d], S.zinv[d], gm[d], gm[zd + d]);
+      if (d < zd) X.actA[d * X.nth + X.tid] = bn_apply(z[d], S.zmean[d], S.zinv[d], gm[d], gm[zd + d]);
   }
   float sse = 0.f, raw_v = 0.f;
   net_forward(P.g, NET_G, X, call, [&](int c, const float* acc, int W) {
@@ -238,7 +239,7 @@ __device__ __forceinline__ float eval_logpost(const BnnProgram& P, const NetCtx&
       int idx = -1;
       if (d < d0) idx = d;
       else if (d >= d0 + d1 && d < d0 + d1 + d2) idx = d - d1;
-      if (idx >= 0 && d < zd) X.actA[idx * BNN_THREADS + X.tid] = bn_apply(z[d], S.zmean[d], S.zinv[d], hm[idx], hm[kin + idx]);
+      if (idx >= 0 && d < zd) X.actA[idx * X.nth + X.tid] = bn_apply(z[d], S.zmean[d], S.zinv[d], hm[idx], hm[kin + idx]);
     }
   }
   float mu_x = 0.f, raw_x = 0.f;
@@ -257,8 +258,8 @@ __device__ __forceinline__ float eval_logpost(const BnnProgram& P, const NetCtx&
     const int kin = P.f.kin;
 #pragma unroll
     for (int d = 0; d < ZMAX; ++d)
-      if (d < d0 + d1 && d < zd) X.actA[d * BNN_THREADS + X.tid] = bn_apply(z[d], S.zmean[d], S.zinv[d], fm[d], fm[kin + d]);
-    X.actA[(d0 + d1) * BNN_THREADS + X.tid] = bn_apply(x_l, S.xmean, S.xinv, fm[d0 + d1], fm[kin + d0 + d1]);
+      if (d < d0 + d1 && d < zd) X.actA[d * X.nth + X.tid] = bn_apply(z[d], S.zmean[d], S.zinv[d], fm[d], fm[kin + d]);
+    X.actA[(d0 + d1) * X.nth + X.tid] = bn_apply(x_l, S.xmean, S.xinv, fm[d0 + d1], fm[kin + d0 + d1]);
   }
   float mu_y = 0.f, raw_y = 0.f;
   net_forward(P.f, NET_F, X, call, [&](int, const float* acc, int) { mu_y = acc[0]; raw_y = acc[1]; });
@@ -294,11 +295,11 @@ __device__ __forceinline__ void stats_partial(const float (&zp)[ZMAX], const flo
   put(4 * ZMAX, x_l);
   put(4 * ZMAX + 1, x_l * x_l);
   __syncthreads();
-  for (int i = threadIdx.x; i < NP; i += BNN_THREADS) {
+  for (int i = threadIdx.x; i < NP; i += (int)blockDim.x) {
     const int d = i % ZMAX;
     double s = 0.0;
     if (i >= 4 * ZMAX || d < zd)
-      for (int w = 0; w < BNN_THREADS / 32; ++w) s += (double)red[w * NP + i];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += (double)red[w * NP + i];
     part[i] = s;
   }
   __syncthreads();
@@ -354,7 +355,8 @@ bnn_mh_kernel(const __grid_constant__ BnnProgram P, const float* __restrict__ im
   const int tid = threadIdx.x;
   const int n = A.n, zd = P.zd;
   const int ncta = gridDim.x;
-  const int row = blockIdx.x * BNN_THREADS + tid;
+  const int nth = (int)blockDim.x;     // rows per CTA: chosen by the host so that one wave of CTAs covers the slice
+  const int row = blockIdx.x * nth + tid;
   const bool valid = row < n;
   const int lrow = valid ? row : n - 1;
   const int64_t grow = A.row_offset + lrow;
@@ -396,22 +398,23 @@ bnn_mh_kernel(const __grid_constant__ BnnProgram P, const float* __restrict__ im
   {
     const double* part = D.part + (size_t)(t & 1) * ncta * NP;
     double* sums = reinterpret_cast<double*>(actA);   // scratch before the activations are written
-    for (int i = tid; i < NP; i += BNN_THREADS) {
+    for (int i = tid; i < NP; i += nth) {
       double s = 0.0;
       for (int b = 0; b < ncta; ++b) s += part[(size_t)b * NP + i];
       sums[i] = s;
     }
     __syncthreads();
     const double inv_n = 1.0 / (double)n;
-    if (tid < 2 * ZMAX) {
-      const int which = tid / ZMAX, d = tid % ZMAX;       // 0: proposal, 1: current state
+    for (int i = tid; i < 2 * ZMAX; i += nth) {
+      const int which = i / ZMAX, d = i % ZMAX;           // 0: proposal, 1: current state
       if (d < zd) {
         const double m = sums[which * 2 * ZMAX + d] * inv_n;
         const double var = fmax(sums[which * 2 * ZMAX + ZMAX + d] * inv_n - m * m, 0.0);
         st[which * 2 * ZMAX + d] = (float)m;
         st[which * 2 * ZMAX + ZMAX + d] = 1.f / sqrtf((float)var + 1e-3f);
       }
-    } else if (tid == 2 * ZMAX) {
+    }
+    if (tid == 0) {
       const double m = sums[4 * ZMAX] * inv_n;
       const double var = fmax(sums[4 * ZMAX + 1] * inv_n - m * m, 0.0);
       st[4 * ZMAX] = (float)m;
@@ -421,7 +424,7 @@ bnn_mh_kernel(const __grid_constant__ BnnProgram P, const float* __restrict__ im
   }
   NetCtx X;
   X.image = image; X.actA = actA; X.actB = actB; X.Wl = Wl; X.Wd = Wd;
-  X.seed = A.seed; X.slice = D.slice; X.grow = grow; X.tid = tid;
+  X.seed = A.seed; X.slice = D.slice; X.grow = grow; X.tid = tid; X.nth = nth;
   const float* vrow = A.v_dev + (size_t)lrow * A.ldv;
   ColStats Sp{st, st + ZMAX, st[4 * ZMAX], st[4 * ZMAX + 1]};
   ColStats Sc{st + 2 * ZMAX, st + 3 * ZMAX, st[4 * ZMAX], st[4 * ZMAX + 1]};
@@ -544,7 +547,7 @@ bnn_effect_kernel(const __grid_constant__ BnnProgram P, const float* __restrict_
   const int d0 = P.d0, d1 = P.d1, kin = P.f.kin, nc = d0 + d1;
   NetCtx X;
   X.image = image; X.actA = actA; X.actB = actB; X.Wl = Wl; X.Wd = Wd;
-  X.seed = E.seed; X.slice = 0; X.grow = grow; X.tid = tid;
+  X.seed = E.seed; X.slice = 0; X.grow = grow; X.tid = tid; X.nth = BNN_THREADS;
   const float* z = E.zs + ((size_t)s * n + lrow) * P.zd;
   const float* stt = E.stats + (size_t)s * 2 * nc;
   const float* fm = image + P.f.bn_off;

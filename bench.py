@@ -324,7 +324,7 @@ def run_sampler(args, cfg):
         return model.predict((xh, yh, vh), alpha=0.01, n_mcmc=N_MCMC, burn_in=BURN_IN,
                              x_values=None if binary else X_VALUES, q_sd=1.0, sample_y=True, bs=n, seed=2000 + i,
                              row_offset=lo, group=D.group, verbose=0)
-    for i in range(min(args.warmup, 2)):
+    for i in range(max(args.warmup, 3)):
         e2e_step(i)
     e2e_wall, e2e_first, _, _ = timed_passes(D, args.steps, e2e_step)
     e2e_value = n * T * n_gpus * args.steps / e2e_wall
