@@ -162,6 +162,7 @@ SYMBOLS = {
                                  C.c_float, C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc), C.POINTER(BnnNetDesc)]),
     "bgm_bnn_destroy": (None, [C.c_void_p]),
     "bgm_bnn_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "bgm_bnn_set_plan": (C.c_int, [C.c_void_p, C.c_int]),
     "bgm_bnn_scratch_doubles": (C.c_longlong, [C.c_void_p, C.c_int]),
     "bgm_bnn_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                   C.c_uint64, C.c_int, C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]),

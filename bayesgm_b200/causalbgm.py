@@ -216,6 +216,8 @@ class CausalBGM(object):
             _lib.call("bgm_bnn_create", C.byref(h), zd4, int(p['v_dim']), int(bool(p['binary_treatment'])),
                       sig[0], sig[1], sig[2], C.byref(gd), C.byref(fd), C.byref(hd))
             self._handle = h
+            if getattr(self, 'bnn_plan', None):          # 1: thread = row, 2 (default): two threads per row
+                _lib.call("bgm_bnn_set_plan", h, int(self.bnn_plan))
         if self._handle is None:
             _lib.require_cuda()
             p = self._p
@@ -250,8 +252,9 @@ class CausalBGM(object):
             _lib.call("bgm_bnn_info", self._device_model(), C.byref(smem), C.byref(rows), C.byref(macs))
             return dict(engine='bnn', tensor_available=False, tensor_smem_bytes=0, smem_bytes=smem.value,
                         rows_per_cta=rows.value, macs_per_eval=macs.value,
-                        kernel='bnn_mh_kernel<%d>' % (8 if sum(self._p['z_dims']) <= 8 else
-                                                     16 if sum(self._p['z_dims']) <= 16 else 32))
+                        kernel=('bnn_mh_kernel<%d>' if getattr(self, 'bnn_plan', 2) == 1 else 'bnn_mh2_kernel<%d>') % (
+                            (8 if sum(self._p['z_dims']) <= 8 else 16 if sum(self._p['z_dims']) <= 16 else 32) //
+                            (1 if getattr(self, 'bnn_plan', 2) == 1 else 2)))
         kind, avail, smem = C.c_int(), C.c_int(), C.c_int()
         issued = C.c_longlong()
         _lib.call("bgm_causal_sampler_info", self._device_model(), C.byref(kind), C.byref(avail), C.byref(smem),

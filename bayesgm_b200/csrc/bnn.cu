@@ -6,13 +6,15 @@
 #include <string>
 #include <vector>
 
-#include "bnn.cuh"
+#include "bnn2.cuh"
 
 struct bgm_bnn {
   bgm::bnn::BnnProgram prog;
   float* image_dev = nullptr;
   int smem_bytes = 0;
   int zmax = 0;
+  int plan = 2;                 // 1: thread = row (bnn.cuh), 2: two threads per row, chunk program (bnn2.cuh)
+  bgm::bnn::BnnProgram2 prog2;
   int sm_count = 148;
   long long macs = 0;
 };
@@ -66,7 +68,9 @@ static int zmax_of(int zd) { return zd <= 8 ? 8 : (zd <= 16 ? 16 : 32); }
 
 // Rows (= threads) per CTA.  One CTA per SM (shared memory): a slice smaller than SMs x 256 rows is cut into one
 // wave of equal CTAs (n = 20000 on 148 SMs: 125 CTAs of 160 rows instead of 79 of 256), larger slices use 256.
+static int rows_per_cta2(const bgm_bnn* m, int n);
 static int rows_per_cta(const bgm_bnn* m, int n) {
+  if (m->plan == 2) return rows_per_cta2(m, n);
   const int per_sm = (n + m->sm_count - 1) / m->sm_count;
   const int warps = std::min(8, std::max(2, (per_sm + 31) / 32));
   return warps * 32;
@@ -78,7 +82,53 @@ static int launch_mh(const bgm_bnn* m, const BnnMhDev& D, int nth, int ncta, cud
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
+// ---- plan 2 ----
+static int add_chunks(BnnProgram2& Q, const BnnNet& net, int net_id) {
+  for (int l = 0; l < net.L; ++l) {
+    const BnnLayer& Ly = net.layer[l];
+    const int nchunk = Ly.N32 / 32;
+    for (int c = 0; c < nchunk; ++c) {
+      if (Q.nchunks >= B2_MAXCH) return -1;
+      BnnChunk& C = Q.ch[Q.nchunks++];
+      C.loc_off = Ly.loc_off; C.scale_off = Ly.scale_off; C.bias_off = Ly.bias_off;
+      C.K = (short)Ly.K; C.N = (short)Ly.N; C.N32 = (short)Ly.N32; C.N4 = (short)((Ly.N + 3) & ~3);
+      C.c = (unsigned char)c; C.net = (unsigned char)net_id; C.layer = (unsigned char)l;
+      C.flags = 0;
+      if (c == 0) C.flags |= CH_LAYER_FIRST;
+      if (c == nchunk - 1) C.flags |= CH_LAYER_LAST;
+      if (l == net.L - 1) C.flags |= CH_FINAL;
+      if (Ly.N <= 8) C.flags |= CH_NARROW;
+      if (l == 0 && c == 0) C.flags |= CH_NET_FIRST;
+    }
+  }
+  return 0;
+}
+static int rows_per_cta2(const bgm_bnn* m, int n) {      // two CTAs per SM, 16 rows per warp
+  const int per_slot = (n + 2 * m->sm_count - 1) / (2 * m->sm_count);
+  const int warps = std::min(8, std::max(2, (per_slot + 15) / 16));
+  return warps * 16;
+}
+static int smem2(const bgm_bnn* m, int nrows) {
+  const int NP = 4 * m->zmax + 2;
+  return (2 * BNN_MAXK * nrows + 4 * W_FLOATS + 8 * NP + NP + 8) * 4;
+}
+template <int ZH>
+static int launch_mh2(const bgm_bnn* m, const BnnMhDev& D, int nrows, int ncta, cudaStream_t st) {
+  const int smem = smem2(m, nrows);
+  BGM_CUDA_OK(cudaFuncSetAttribute(bnn_mh2_kernel<ZH>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2(m, 128)));
+  bnn_mh2_kernel<ZH><<<ncta, 2 * nrows, smem, st>>>(m->prog2, m->image_dev, D);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
 static int launch(const bgm_bnn* m, const BnnMhDev& D, int nth, int ncta, cudaStream_t st) {
+  if (m->plan == 2) {
+    const int nrows = nth;      // the callers pass rows per CTA
+    switch (m->zmax) {
+      case 8: return launch_mh2<4>(m, D, nrows, ncta, st);
+      case 16: return launch_mh2<8>(m, D, nrows, ncta, st);
+      default: return launch_mh2<16>(m, D, nrows, ncta, st);
+    }
+  }
   switch (m->zmax) {
     case 8: return launch_mh<8>(m, D, nth, ncta, st);
     case 16: return launch_mh<16>(m, D, nth, ncta, st);
@@ -121,6 +171,9 @@ int bgm_bnn_create(bgm_bnn** out, const int z_dims[4], int v_dim, int binary_tre
     return fail(rc == -2 ? BGM_ERR_UNSUPPORTED : BGM_ERR_ARG, "bgm_bnn_create: " + err);
   }
   m->zmax = zmax_of(zd);
+  m->prog2.P = P;
+  m->prog2.nchunks = 0;
+  if (add_chunks(m->prog2, P.g, NET_G) || add_chunks(m->prog2, P.h, NET_H) || add_chunks(m->prog2, P.f, NET_F)) m->plan = 1;
   {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -147,15 +200,22 @@ void bgm_bnn_destroy(bgm_bnn* m) {
 
 int bgm_bnn_info(const bgm_bnn* m, int* smem_bytes, int* rows_per_cta, long long* macs_per_eval) {
   if (!m) return bgm::fail(BGM_ERR_ARG, "bgm_bnn_info: null model");
-  if (smem_bytes) *smem_bytes = m->smem_bytes;
-  if (rows_per_cta) *rows_per_cta = bgm::bnn::BNN_THREADS;
+  if (smem_bytes) *smem_bytes = m->plan == 2 ? bgm::bnn::smem2(m, 128) : m->smem_bytes;
+  if (rows_per_cta) *rows_per_cta = m->plan == 2 ? 128 : bgm::bnn::BNN_THREADS;
   if (macs_per_eval) *macs_per_eval = m->macs;
+  return 0;
+}
+
+int bgm_bnn_set_plan(bgm_bnn* m, int plan) {
+  if (!m || (plan != 1 && plan != 2)) return bgm::fail(BGM_ERR_ARG, "bgm_bnn_set_plan: plan must be 1 or 2");
+  if (plan == 2 && m->prog2.nchunks == 0) return bgm::fail(BGM_ERR_UNSUPPORTED, "bgm_bnn_set_plan: no chunk program for this model");
+  m->plan = plan;
   return 0;
 }
 
 long long bgm_bnn_scratch_doubles(const bgm_bnn* m, int n) {
   if (!m || n < 1) return -1;
-  const long long ncta = (n + 63) / 64;     // upper bound: the smallest CTA is 64 rows
+  const long long ncta = (n + 31) / 32;     // upper bound: the smallest CTA holds 32 rows
   return 2 * ncta * (4 * m->zmax + 2);
 }
 

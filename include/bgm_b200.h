@@ -224,6 +224,10 @@ void bgm_bnn_destroy(bgm_bnn* m);
 /* shared-memory bytes per CTA, rows per CTA, multiply-adds per row per log-posterior evaluation
  * (2 x the deterministic count: loc and perturbation products). */
 int bgm_bnn_info(const bgm_bnn* m, int* smem_bytes, int* rows_per_cta, long long* macs_per_eval);
+/* Execution plan of bgm_bnn_logpost / bgm_bnn_mh: 1 = one thread per row (csrc/bnn.cuh), 2 (default) = two threads
+ * per row over a table-driven chunk program with double-buffered weight chunks (csrc/bnn2.cuh).  Same noise
+ * streams, same per-accumulator arithmetic. */
+int bgm_bnn_set_plan(bgm_bnn* m, int plan);
 /* Number of doubles of scratch (per-CTA partial sums of the batch statistics) the calls below
  * need for n rows; -1 on a bad argument. */
 long long bgm_bnn_scratch_doubles(const bgm_bnn* m, int n);

@@ -26,9 +26,11 @@ def bnn_case(v_dim, z_dims, binary=False, g_units=(64,) * 5, f_units=(64, 32, 8)
     return params, nets
 
 
-def product(params, nets):
+def product(params, nets, plan=None):
     from bayesgm_b200 import CausalBGM
     m = CausalBGM(params=params, random_seed=None)
+    if plan:
+        m.bnn_plan = plan
     kw = {}
     for k in 'gefh':
         w = [nets[k]['bn'][q] for q in ('gamma', 'beta', 'mean', 'var')]
@@ -73,13 +75,14 @@ def test_noise_streams_match_oracle():
 
 @pytest.mark.parametrize("case", CASES)
 @pytest.mark.parametrize("n", [300, 1])
-def test_log_posterior_matches_oracle(case, n):
+@pytest.mark.parametrize("plan", [1, 2])
+def test_log_posterior_matches_oracle(case, n, plan):
     params, nets = bnn_case(**case)
     if n == 1 and case['v_dim'] != 200:
         pytest.skip("single-row batch checked on the standard shapes")
     x, y, v = causal_data(n, params['v_dim'], binary=params['binary_treatment'])
     z = np.random.RandomState(2).standard_normal((n, sum(params['z_dims']))).astype(np.float32)
-    m = product(params, nets)
+    m = product(params, nets, plan)
     for call in (0, 7):
         got = m.get_log_posterior(x, y, v, z, seed=99, call=call)
         want = obnn.log_posterior(params, nets, x, y, v, z, obnn.PhiloxFlipout(99), call=call)
@@ -90,15 +93,16 @@ def test_log_posterior_matches_oracle(case, n):
     assert np.abs(other - got).max() > 1e-3
 
 
-@pytest.mark.parametrize("case", CASES[:3])
+@pytest.mark.parametrize("case", CASES[:4])
 @pytest.mark.parametrize("mode", ["injected", "philox"])
-def test_mh_trace_matches_oracle(case, mode):
+@pytest.mark.parametrize("plan", [1, 2])
+def test_mh_trace_matches_oracle(case, mode, plan):
     params, nets = bnn_case(**case)
     n, burn_in, n_keep, seed = 300, 4, 6, 4242
     T = burn_in + n_keep
     zd = sum(params['z_dims'])
     data = causal_data(n, params['v_dim'], binary=params['binary_treatment'])
-    m = product(params, nets)
+    m = product(params, nets, plan)
     if mode == "injected":
         nz = injected_noise(n, zd, T)
         sg, tr = m.metropolis_hastings_sampler(data, q_sd=0.3, burn_in=burn_in, n_keep=n_keep, seed=seed, noise=nz,
