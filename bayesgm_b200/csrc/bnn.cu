@@ -11,6 +11,7 @@
 struct bgm_bnn {
   bgm::bnn::BnnProgram prog;
   float* image_dev = nullptr;
+  float* dw_dev = nullptr;      // plan 2: kernel perturbations of the running iteration (one sampler run at a time per model)
   int smem_bytes = 0;
   int zmax = 0;
   int plan = 2;                 // 1: thread = row (bnn.cuh), 2: two threads per row, chunk program (bnn2.cuh)
@@ -103,6 +104,17 @@ static int add_chunks(BnnProgram2& Q, const BnnNet& net, int net_id) {
   }
   return 0;
 }
+static int add_segments(BnnProgram2& Q, const BnnNet& net, int net_id) {
+  for (int l = 0; l < net.L; ++l) {
+    if (Q.nseg >= 24) return -1;
+    const BnnLayer& Ly = net.layer[l];
+    BnnSeg& S = Q.seg[Q.nseg++];
+    S.scale_off = Ly.scale_off; S.K = Ly.K; S.N32 = Ly.N32; S.N4 = (Ly.N + 3) & ~3; S.net = net_id; S.layer = l;
+    S.g0 = Q.ngroups;
+    Q.ngroups += Ly.K * Ly.N32 / 4;
+  }
+  return 0;
+}
 static int rows_per_cta2(const bgm_bnn* m, int n) {      // two CTAs per SM, 16 rows per warp
   const int per_slot = (n + 2 * m->sm_count - 1) / (2 * m->sm_count);
   const int warps = std::min(8, std::max(2, (per_slot + 15) / 16));
@@ -173,7 +185,12 @@ int bgm_bnn_create(bgm_bnn** out, const int z_dims[4], int v_dim, int binary_tre
   m->zmax = zmax_of(zd);
   m->prog2.P = P;
   m->prog2.nchunks = 0;
-  if (add_chunks(m->prog2, P.g, NET_G) || add_chunks(m->prog2, P.h, NET_H) || add_chunks(m->prog2, P.f, NET_F)) m->plan = 1;
+  m->prog2.nseg = 0; m->prog2.ngroups = 0; m->prog2.image_floats = (int)image.size();
+  if (add_chunks(m->prog2, P.g, NET_G) || add_chunks(m->prog2, P.h, NET_H) || add_chunks(m->prog2, P.f, NET_F) ||
+      add_segments(m->prog2, P.g, NET_G) || add_segments(m->prog2, P.h, NET_H) || add_segments(m->prog2, P.f, NET_F)) {
+    m->plan = 1;
+    m->prog2.nchunks = 0;
+  }
   {
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -183,8 +200,10 @@ int bgm_bnn_create(bgm_bnn** out, const int z_dims[4], int v_dim, int binary_tre
   m->smem_bytes = (2 * ACT_FLOATS + 2 * W_FLOATS + 8 * NP + NP + 8) * 4;
   cudaError_t e = cudaMalloc(&m->image_dev, image.size() * sizeof(float));
   if (e == cudaSuccess) e = cudaMemcpy(m->image_dev, image.data(), image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMalloc(&m->dw_dev, 4 * image.size() * sizeof(float));
   if (e != cudaSuccess) {
     if (m->image_dev) cudaFree(m->image_dev);
+    if (m->dw_dev) cudaFree(m->dw_dev);
     delete m;
     return fail(BGM_ERR_CUDA, std::string("bgm_bnn_create: ") + cudaGetErrorString(e));
   }
@@ -195,6 +214,7 @@ int bgm_bnn_create(bgm_bnn** out, const int z_dims[4], int v_dim, int binary_tre
 void bgm_bnn_destroy(bgm_bnn* m) {
   if (!m) return;
   if (m->image_dev) cudaFree(m->image_dev);
+  if (m->dw_dev) cudaFree(m->dw_dev);
   delete m;
 }
 
@@ -241,7 +261,7 @@ int bgm_bnn_logpost(const bgm_bnn* m, const float* x_dev, const float* y_dev, co
   memset(&D, 0, sizeof(D));
   D.a.x_dev = x_dev; D.a.y_dev = y_dev; D.a.v_dev = v_dev; D.a.ldv = ldv; D.a.n = n;
   D.a.seed = seed; D.a.row_offset = row_offset; D.a.init_mode = 1;
-  D.slice = slice; D.call0 = call; D.z_in = z_dev; D.out_lp = out_logp_dev; D.part = scratch_dev;
+  D.slice = slice; D.call0 = call; D.z_in = z_dev; D.out_lp = out_logp_dev; D.part = scratch_dev; D.dw = m->dw_dev;
   D.t = 0;
   const int nth = rows_per_cta(m, n);
   const int ncta = (n + nth - 1) / nth;
@@ -269,6 +289,7 @@ int bgm_bnn_mh(const bgm_bnn* m, const bgm_mh_args* a, int slice, double* scratc
   D.a = *a;
   D.slice = slice;
   D.part = scratch_dev;
+  D.dw = m->dw_dev;
   D.lp_cur_trace = lp_cur_trace_dev;
   const int nth = rows_per_cta(m, a->n);
   const int ncta = (a->n + nth - 1) / nth;

@@ -315,6 +315,7 @@ struct BnnMhDev {
   float* out_lp;       // mode 1: (n)
   double* part;        // [2][ncta][NP] partial sums; launch t reads parity t&1, writes (t+1)&1
   float* lp_cur_trace; // (T, n) or NULL
+  float* dw;           // plan 2: [2 parity][2 evaluations][image floats] kernel perturbations of the iteration
 };
 
 template <int ZMAX>
