@@ -109,10 +109,6 @@ SYMBOLS = {
     "bgm_causal_effect_combine": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_uint64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                             C.c_void_p]),
-    "bgm_causal_effect_combine_agg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                                C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "bgm_causal_effect_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_uint64,
-                                           C.c_void_p, C.c_void_p]),
     "bgm_fp32_peak_tflops": (C.c_int, [C.POINTER(C.c_double), C.c_void_p]),
     "bgm_trainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int,
                                      C.POINTER(NetDesc), C.POINTER(NetDesc), C.POINTER(NetDesc),

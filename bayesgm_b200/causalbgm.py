@@ -478,8 +478,7 @@ class CausalBGM(object):
             return samples, tr
         return samples
 
-    def _effect_device(self, z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=None, memoise=True,
-                       aggregate=None):
+    def _effect_device(self, z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=None, memoise=True):
         """ITE draws (n_keep, n) or ADRF partial sums (n_x, n_keep) on the device.  memoise: evaluate
         f_net once per DISTINCT kept state of a row (a rejected proposal repeats the state) and
         combine -- identical results, ~acceptance-rate of the f_net work (bgm_causal_effect_index /
@@ -534,42 +533,11 @@ class CausalBGM(object):
                   _lib.ptr(zlist), st)
         heads = self._workspace('heads', n_distinct * n_x * 2, torch).view(n_distinct, n_x, 2)
         _lib.call("bgm_causal_effect_heads", m, _lib.ptr(zlist), n_distinct, _lib.ptr(xv), n_x, _lib.ptr(heads), st)
-        self.last_distinct_fraction = n_distinct / float(total)
-        if aggregate is not None:
-            # continuous treatment, Philox noise: only sum mu and sum sigma^2 per (dose, kept state) are needed -- the
-            # row mean of independent normals is one normal (bgm_causal_effect_combine_agg); the draw happens once,
-            # after all slices / shards have been added (bgm_causal_effect_finish)
-            mu_sum, s2_sum = aggregate
-            _lib.call("bgm_causal_effect_combine_agg", m, _lib.ptr(heads), _lib.ptr(local), _lib.ptr(rowend), n_keep, n, n_x,
-                      int(bool(sample_y)), _lib.ptr(mu_sum), _lib.ptr(s2_sum), st)
-            return None
         _lib.call("bgm_causal_effect_combine", m, _lib.ptr(heads), _lib.ptr(local), _lib.ptr(rowend), n_keep, n, n_x,
                   int(bool(sample_y)), seed, int(row_offset), _lib.ptr(nz), None if binary else _lib.ptr(out),
                   _lib.ptr(out) if binary else None, st)
+        self.last_distinct_fraction = n_distinct / float(total)
         return out
-
-    def _can_aggregate(self, n_keep, n, n_x, noise):
-        """The aggregated reduction serves continuous treatments on deterministic nets with in-kernel noise, through
-        the memoised path (>= 2 kept states, < 2^31 (state, row) pairs, <= 32 doses)."""
-        return (not self._bnn and not self._p['binary_treatment'] and noise is None and n_keep >= 2
-                and n_keep * n < 2 ** 31 and n_x <= 32)
-
-    def _finish_aggregate(self, mu_sum, s2_sum, n_total, sample_y, seed, group=None):
-        """All-reduce the per-(dose, kept state) sums over the ranks, then ONE N(0,1) per (dose, kept state)."""
-        torch = _lib.require_cuda()
-        cnt = torch.tensor([float(n_total)], dtype=torch.float64, device='cuda')
-        if group is not None:
-            from .shard import all_reduce_sum
-            packed = torch.cat([mu_sum.reshape(-1), s2_sum.reshape(-1), cnt])      # one collective
-            all_reduce_sum(packed, group)
-            k = mu_sum.numel()
-            mu_sum, s2_sum, cnt = packed[:k].view_as(mu_sum), packed[k:2 * k].view_as(s2_sum), packed[2 * k:]
-            n_total = float(cnt.item())
-        out = torch.empty(mu_sum.shape, dtype=torch.float32, device='cuda')
-        _lib.call("bgm_causal_effect_finish", _lib.ptr(mu_sum.contiguous()), _lib.ptr(s2_sum.contiguous()), mu_sum.shape[0],
-                  mu_sum.shape[1], float(n_total), int(bool(sample_y)), int(seed) & (2 ** 64 - 1), _lib.ptr(out),
-                  _lib.stream_ptr())
-        return out.cpu().numpy()
 
     def _workspace(self, name, numel, torch):
         """float32 device workspace of at least `numel` elements, kept on the model and grown by >= 1.3x."""
@@ -595,11 +563,6 @@ class CausalBGM(object):
         if self._p['binary_treatment']:
             return self._effect_device(zs, n_keep, n, None, sample_y, seed, 0, noise).cpu().numpy()
         x_values = np.atleast_1d(np.asarray(x_values, dtype=float))
-        if self._can_aggregate(n_keep, n, len(x_values), noise):
-            mu_sum = torch.zeros((len(x_values), n_keep), dtype=torch.float64, device='cuda')
-            s2_sum = torch.zeros_like(mu_sum)
-            if self._effect_device(zs, n_keep, n, x_values, sample_y, seed, 0, aggregate=(mu_sum, s2_sum)) is None:
-                return self._finish_aggregate(mu_sum, s2_sum, n, sample_y, seed)
         sums = self._effect_device(zs, n_keep, n, x_values, sample_y, seed, 0, noise)
         return (sums / float(n)).float().cpu().numpy()
 
@@ -637,9 +600,6 @@ class CausalBGM(object):
         else:
             sums = torch.zeros((len(x_values), n_mcmc), dtype=torch.float64, device='cuda')
             n_seen = 0
-            agg = None
-            if self._can_aggregate(int(n_mcmc), min(n_test, 2 ** 20), len(x_values), None):
-                agg = (torch.zeros_like(sums), torch.zeros_like(sums))
         # The reference runs one independent MH per `bs` slice (:630, :650).  With a fixed q_sd the
         # chains of different slices do not interact and the Philox noise is keyed by the global
         # row, so several slices are sampled in ONE launch (identical results, a full grid instead
@@ -658,11 +618,8 @@ class CausalBGM(object):
             _, x, y, v, ldv, n = self._stage((data_x[start:end], data_y[start:end], data_v[start:end]))
             r = self._mh_device(x, y, v, ldv, n, int(burn_in), int(n_mcmc), q_sd, adaptive, 1.0, 0.25, 0.05,
                                 50, 100, seed, row_offset + start, slice_id=(row_offset + start) // bs)
-            use_agg = (not binary) and agg is not None and self._can_aggregate(int(n_mcmc), n, len(x_values), None)
             eff = self._effect_device(r['samples'], int(n_mcmc), n, x_values, sample_y, seed,
-                                      row_offset + start, aggregate=agg if use_agg else None)
-            if use_agg and eff is not None:          # the memoised path was not taken (table too large): per-row sums
-                use_agg = False
+                                      row_offset + start)
             T_ = int(burn_in) + int(n_mcmc)
             w_ = min(100, T_)
             acc_tail.append((r['accept_count'][T_ - w_:].sum(), w_ * n))                # :901, read back once below
@@ -671,8 +628,7 @@ class CausalBGM(object):
                 lower[start:end] = _quantile_dim0(torch, eff, alpha / 2).cpu().numpy()
                 upper[start:end] = _quantile_dim0(torch, eff, 1 - alpha / 2).cpu().numpy()
             else:                                                                 # :660-661
-                if not use_agg:
-                    sums += eff
+                sums += eff
                 n_seen += n
         if acc_tail:
             tot = torch.stack([a for a, _ in acc_tail]).sum()
@@ -681,12 +637,6 @@ class CausalBGM(object):
                 print(f"Final MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
         if binary:
             return ite_mean, np.stack([lower, upper], axis=1)
-        if agg is not None:
-            # per-row draws of slices that bypassed the aggregated path (none in practice) are already sums of y: add
-            # them to the mean part
-            agg[0].add_(sums)
-            ce = self._finish_aggregate(agg[0], agg[1], n_seen, sample_y, seed, group)
-            return finish_adrf(ce, alpha)
         ce = merge_adrf(sums, n_seen, group) if group is not None else \
             (sums / float(n_seen)).float().cpu().numpy()                          # :663
         return finish_adrf(ce, alpha)                                             # :665-667

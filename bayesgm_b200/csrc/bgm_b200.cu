@@ -716,36 +716,6 @@ int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const
   return 0;
 }
 
-int bgm_causal_effect_combine_agg(const bgm_causal* m, const float* heads_dev, const int* local_dev, const int* rowend_dev,
-                                  int n_keep, int n, int n_x, int sample_y, double* mu_sum_dev, double* s2_sum_dev,
-                                  void* stream) {
-  if (!m || !heads_dev || !local_dev || !rowend_dev || !mu_sum_dev || n_keep < 1 || n < 1 || n_x < 1)
-    return fail(BGM_ERR_ARG, "bgm_causal_effect_combine_agg: bad argument");
-  if (m->prog.binary) return fail(BGM_ERR_ARG, "bgm_causal_effect_combine_agg: continuous treatments only (the ITE is per subject)");
-  if (sample_y && !s2_sum_dev) return fail(BGM_ERR_ARG, "bgm_causal_effect_combine_agg: s2_sum_dev required with sample_y");
-  if (n_x > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_causal_effect_combine_agg: at most 32 doses per call");
-  CombineAggDev C;
-  memset(&C, 0, sizeof(C));
-  C.heads = heads_dev; C.local = local_dev; C.rowend = rowend_dev; C.n_keep = n_keep; C.n = n; C.n_x = n_x;
-  C.sample_y = sample_y ? 1 : 0; C.s2y = m->prog.s2y; C.mu_sum = mu_sum_dev; C.s2_sum = s2_sum_dev;
-  C.s_tile = std::max(1, std::min(n_keep, (96 * 1024) / (8 * n_x)));
-  const int smem = 2 * n_x * C.s_tile * 4;
-  BGM_CUDA_OK(cudaFuncSetAttribute(effect_combine_agg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  effect_combine_agg_kernel<32><<<(n + 255) / 256, 256, smem, (cudaStream_t)stream>>>(C);
-  BGM_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-int bgm_causal_effect_finish(const double* mu_sum_dev, const double* s2_sum_dev, int n_x, int n_keep, double n_total,
-                             int sample_y, uint64_t seed, float* out_dev, void* stream) {
-  if (!mu_sum_dev || !out_dev || n_x < 1 || n_keep < 1 || !(n_total > 0) || (sample_y && !s2_sum_dev))
-    return fail(BGM_ERR_ARG, "bgm_causal_effect_finish: bad argument");
-  effect_finish_kernel<<<std::max(1, std::min((n_x * n_keep + 255) / 256, 1024)), 256, 0, (cudaStream_t)stream>>>(
-      mu_sum_dev, s2_sum_dev, n_x, n_keep, n_total, sample_y ? 1 : 0, seed, out_dev);
-  BGM_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 static int effect_launch(const bgm_causal* m, const float* z_samples_dev, int n_keep, int n,
                          const float* x_values_dev, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
                          const float* noise_dev, double* adrf_sum_dev, float* ite_dev, float* heads_dev, void* stream);

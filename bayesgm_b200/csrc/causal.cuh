@@ -635,90 +635,6 @@ __global__ void __launch_bounds__(256) effect_combine_kernel(const __grid_consta
   }
 }
 
-// Aggregated form of the continuous-treatment reduction (:753-759).  The reference draws y ~ N(mu, sigma^2) per
-// (kept state, row, dose) and returns only the MEAN over the rows; the sum of independent normals is normal, so
-// sum_rows y = sum_rows mu + sqrt(sum_rows sigma^2) * N(0,1) exactly in distribution.  This pass therefore only
-// accumulates sum mu and sum sigma^2 per (dose, kept state) -- no per-row Philox draws (1e9 of them at the bench
-// size) -- and effect_finish_kernel draws ONE normal per (dose, kept state) after the shards have been added.
-// One thread per row walks the row's kept states with the heads of its current distinct state in registers
-// (re-read only where the state changes); the 32 rows of a warp are summed with shuffles, warps meet in shared memory.
-struct CombineAggDev {
-  const float* heads;      // (n_distinct, n_x, 2)
-  const int* local;        // (n_keep, n)
-  const int* rowend;       // (n)
-  int n_keep, n, n_x, sample_y, s_tile;
-  float s2y;
-  double* mu_sum;          // (n_x, n_keep) +=
-  double* s2_sum;          // (n_x, n_keep) += (sample_y only)
-};
-template <int NXMAX>
-__global__ void __launch_bounds__(256) effect_combine_agg_kernel(const __grid_constant__ CombineAggDev C) {
-  extern __shared__ float acc_s[];               // [2][n_x][s_tile]
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int row = blockIdx.x * 256 + tid;
-  const bool valid = row < C.n;
-  const int lrow = valid ? row : C.n - 1;
-  const int nx = C.n_x, n = C.n, n_keep = C.n_keep;
-  const int base = C.rowend[lrow] - C.local[(size_t)(n_keep - 1) * n + lrow] - 1;
-  float mu[NXMAX], s2[NXMAX];
-#pragma unroll
-  for (int j = 0; j < NXMAX; ++j) { mu[j] = 0.f; s2[j] = 0.f; }
-  int cur = -1;
-  for (int s0 = 0; s0 < n_keep; s0 += C.s_tile) {
-    const int len = min(C.s_tile, n_keep - s0);
-    for (int i = tid; i < 2 * nx * len; i += 256) acc_s[i] = 0.f;
-    __syncthreads();
-    for (int sl = 0; sl < len; ++sl) {
-      const int ref = base + C.local[(size_t)(s0 + sl) * n + lrow];
-      if (ref != cur) {
-        cur = ref;
-        const float2* h = reinterpret_cast<const float2*>(C.heads) + (size_t)ref * nx;
-#pragma unroll
-        for (int j = 0; j < NXMAX; ++j)
-          if (j < nx) {
-            const float2 mr = __ldg(h + j);
-            mu[j] = valid ? mr.x : 0.f;
-            s2[j] = valid ? (C.s2y >= 0.f ? C.s2y : softplus_f(mr.y) + 1e-6f) : 0.f;
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < NXMAX; ++j) {
-        if (j < nx) {
-          float a = mu[j], b = s2[j];
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            a += __shfl_xor_sync(0xffffffffu, a, o);
-            if (C.sample_y) b += __shfl_xor_sync(0xffffffffu, b, o);
-          }
-          if (lane == 0) {
-            atomicAdd(&acc_s[j * len + sl], a);
-            if (C.sample_y) atomicAdd(&acc_s[(nx + j) * len + sl], b);
-          }
-        }
-      }
-    }
-    __syncthreads();
-    for (int i = tid; i < nx * len; i += 256) {
-      const int j = i / len, sl = i - j * len;
-      atomicAdd(C.mu_sum + (size_t)j * n_keep + s0 + sl, (double)acc_s[i]);
-      if (C.sample_y) atomicAdd(C.s2_sum + (size_t)j * n_keep + s0 + sl, (double)acc_s[nx * len + i]);
-    }
-    __syncthreads();
-  }
-}
-// out[j][s] = (mu_sum + sqrt(s2_sum) * N(0,1)) / n_total; the normal is keyed by (seed, kept state s, dose j) only, so
-// the result does not depend on how the rows were sharded
-__global__ void effect_finish_kernel(const double* __restrict__ mu_sum, const double* __restrict__ s2_sum, int n_x, int n_keep,
-                                     double n_total, int sample_y, uint64_t seed, float* __restrict__ out) {
-  const int total = n_x * n_keep;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i / n_keep, s = i - j * n_keep;
-    double v = mu_sum[i];
-    if (sample_y) v += sqrt(fmax(s2_sum[i], 0.0)) * (double)normal1(seed, (int64_t)s, (uint32_t)j, 7u, 0u);
-    out[i] = (float)(v / n_total);
-  }
-}
-
 // 1-thread kernel: the q_sd adaptation rule, causalbgm/base.py:880-890.
 __global__ void mh_adapt_qsd_kernel(const int* __restrict__ accept_count, int t, int window,
                                     long long n_total, double target, double tol, double* q_sd) {

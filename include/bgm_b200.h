@@ -197,19 +197,6 @@ int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const
                               int n_keep, int n, int n_x, int sample_y, uint64_t seed, int64_t row_offset,
                               const float* noise_dev, double* adrf_sum_dev, float* ite_dev, void* stream);
 
-/* Aggregated form of the continuous-treatment reduction (causalbgm/base.py:753-759).  The reference draws
- * y ~ N(mu, sigma^2) for every (kept state, row, dose) and returns only the MEAN over the rows; a sum of independent
- * normals is normal, so sum_rows y = sum_rows mu + sqrt(sum_rows sigma^2) * N(0,1) exactly in distribution.
- * bgm_causal_effect_combine_agg adds, per (dose, kept state), sum mu into mu_sum_dev and sum sigma^2 into s2_sum_dev
- * ((n_x, n_keep) float64, caller-zeroed; shards / `bs` slices add into the same arrays; n_x <= 32);
- * bgm_causal_effect_finish then draws ONE normal per (dose, kept state) -- Philox keyed by (seed, s, j) only, so the
- * result is independent of the sharding -- and writes (mu_sum + sqrt(s2_sum) e) / n_total to out_dev (n_x, n_keep). */
-int bgm_causal_effect_combine_agg(const bgm_causal* m, const float* heads_dev, const int* local_dev, const int* rowend_dev,
-                                  int n_keep, int n, int n_x, int sample_y, double* mu_sum_dev, double* s2_sum_dev,
-                                  void* stream);
-int bgm_causal_effect_finish(const double* mu_sum_dev, const double* s2_sum_dev, int n_x, int n_keep, double n_total,
-                             int sample_y, uint64_t seed, float* out_dev, void* stream);
-
 /* ------------------------------------------- CausalBGM on Bayesian networks -- */
 /* `use_bnn: True` (the default of every shipped CausalBGM config, causalbgm/base.py:64-72):
  * g / f / h are `BayesianFullyConnectedNet`s (networks/bnn.py:4-38): a BatchNormalization on

@@ -234,33 +234,6 @@ def test_effect_sample_y_philox_is_distributionally_right():
     assert np.any(drawn != mean_only)
 
 
-def test_aggregated_outcome_noise_has_the_variance_of_the_row_mean():
-    """sample_y=True, continuous: the reference draws y ~ N(mu, sigma^2) per (state, row, dose) and returns the row
-    mean; the product draws ONE normal per (state, dose) with variance sum_rows sigma^2 / n^2 -- the same distribution.
-    Checked against the per-row form: mean part identical, spread of the noise part = oracle's sqrt(sum sigma^2) / n."""
-    from oracle.nets import softplus
-    params = causal_params(16, [1, 1, 1, 1])
-    nets = causal_nets(params)
-    n, n_keep = 700, 600
-    rs = np.random.RandomState(8)
-    zs = np.repeat(rs.standard_normal((1, n, 4)).astype(np.float32), n_keep, axis=0)      # the same state every time
-    zs[1::2] += 0.0
-    m = product_model(params, nets)
-    xs = [0.5, 2.0]
-    mean_only = m.infer_from_latent_posterior(zs, x_values=xs, sample_y=False)
-    drawn = m.infer_from_latent_posterior(zs, x_values=xs, sample_y=True, seed=11)
-    for j, xv in enumerate(xs):
-        out = causal.f_net_on(params, nets, zs[0], np.full((n, 1), xv, np.float32))
-        want_sd = np.sqrt((softplus(out[:, 1]) + 1e-6).sum()) / n
-        got = drawn[j] - mean_only[j]
-        assert abs(got.std() / want_sd - 1.0) < 0.12, (got.std(), want_sd)
-        assert abs(got.mean()) < 4 * want_sd / np.sqrt(n_keep)
-    # a different seed is a different draw, the same seed the same draw
-    again = m.infer_from_latent_posterior(zs, x_values=xs, sample_y=True, seed=11)
-    np.testing.assert_array_equal(again, drawn)
-    assert np.any(m.infer_from_latent_posterior(zs, x_values=xs, sample_y=True, seed=12) != drawn)
-
-
 def test_predict_continuous_matches_oracle_on_replayed_noise():
     params = causal_params(40, [1, 1, 1, 2])
     nets = causal_nets(params)
