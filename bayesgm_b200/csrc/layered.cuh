@@ -67,6 +67,7 @@ __global__ void dense_fwd_kernel(const float* __restrict__ A, int lda, const flo
     float acc = 0.f, accp = 0.f;
     if (dW) {
       const signed char* si = s_in + (size_t)b * K;
+#pragma unroll 8
       for (int k = 0; k < K; ++k) {
         const float av = a[k];
         acc = fmaf(av, W[(size_t)k * N + c], acc);
@@ -74,6 +75,7 @@ __global__ void dense_fwd_kernel(const float* __restrict__ A, int lda, const flo
       }
       acc = acc + (float)s_out[(size_t)b * N + c] * accp;
     } else {
+#pragma unroll 8
       for (int k = 0; k < K; ++k) acc = fmaf(a[k], W[(size_t)k * N + c], acc);
     }
     acc += bias[c];
@@ -95,6 +97,7 @@ __global__ void dense_bwd_input_kernel(const float* __restrict__ dY, int ldy, co
     float acc = 0.f, accp = 0.f;
     if (dW) {
       const signed char* so = s_out + (size_t)b * N;
+#pragma unroll 8
       for (int c = 0; c < N; ++c) {
         const float d = dy[c];
         acc = fmaf(d, W[(size_t)k * N + c], acc);
@@ -102,6 +105,7 @@ __global__ void dense_bwd_input_kernel(const float* __restrict__ dY, int ldy, co
       }
       acc += (float)s_in[(size_t)b * K + k] * accp;
     } else {
+#pragma unroll 8
       for (int c = 0; c < N; ++c) acc = fmaf(dy[c], W[(size_t)k * N + c], acc);
     }
     if (A_post) acc *= (A_post[(size_t)b * lda + k] > 0.f ? 1.f : 0.2f);
@@ -121,6 +125,7 @@ __global__ void dense_bwd_param_kernel(const float* __restrict__ A, int lda, con
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i / N, c = i - k * N;
     float acc = 0.f, accp = 0.f, accb = 0.f;
+#pragma unroll 8
     for (int b = 0; b < B; ++b) {
       const float a = A[(size_t)b * lda + k], d = dY[(size_t)b * ldy + c];
       acc = fmaf(a, d, acc);
