@@ -8,6 +8,7 @@ __version__ = "0.1.0"
 
 from .causalbgm import CausalBGM  # noqa: F401
 from .bgm import BGM  # noqa: F401
+from .variants import IdentifiableCausalBGM, FullMCMCCausalBGM  # noqa: F401
 from . import datasets  # noqa: F401
 
-__all__ = ["CausalBGM", "BGM", "datasets"]
+__all__ = ["CausalBGM", "BGM", "IdentifiableCausalBGM", "FullMCMCCausalBGM", "datasets"]

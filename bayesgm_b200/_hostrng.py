@@ -104,3 +104,51 @@ class EgmProducer(object):
                     pass
         self.thread.join()
         self.stream.to_numpy()
+
+
+class FloydProducer(object):
+    """Same hand-over interface as EgmProducer for `egm_init(index_stream='floyd')`: mini-batch indices
+    drawn WITHOUT permuting all n rows (NumPy's Generator.choice: Floyd's subset sampling + a shuffle of
+    the subset) and the prior draws from the same PCG64 generator, seeded by one draw from `np.random`
+    (so `np.random.seed` still fixes the run).  The same distribution as the reference's
+    `np.random.choice(n, bs, replace=False)` (bgm/base.py:406) at O(bs) instead of O(n) per draw -- not
+    the same stream: the bit-exact continuation of NumPy's legacy generator is EgmProducer."""
+
+    def __init__(self, n, bs, zd, freq, total, chunk=64, depth=4):
+        self.rng = np.random.Generator(np.random.PCG64(int(np.random.randint(0, 2 ** 31 - 1))))
+        self.q = queue.Queue(maxsize=depth)
+        self._err = None
+        self._stop = False
+
+        def work():
+            try:
+                done = 0
+                while done < total and not self._stop:
+                    cnt = min(chunk, total - done)
+                    idx = np.empty((cnt, freq + 1, bs), np.int32)
+                    for c in range(cnt):
+                        for k in range(freq + 1):
+                            idx[c, k] = self.rng.choice(n, bs, replace=False)
+                    z = self.rng.standard_normal((cnt, freq + 1, bs, zd), dtype=np.float32)
+                    self.q.put((idx, z))
+                    done += cnt
+            except BaseException as e:
+                self._err = e
+                self.q.put(None)
+        self.thread = threading.Thread(target=work, daemon=True)
+        self.thread.start()
+
+    def get(self):
+        item = self.q.get()
+        if item is None:
+            raise self._err
+        return item
+
+    def close(self, drain=False):
+        self._stop = True
+        while self.thread.is_alive() or not self.q.empty():
+            try:
+                self.q.get(timeout=0.05)
+            except queue.Empty:
+                pass
+        self.thread.join()

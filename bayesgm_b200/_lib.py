@@ -36,6 +36,7 @@ class MhArgs(C.Structure):
         ("seed", C.c_uint64), ("row_offset", C.c_int64),
         ("out_samples_dev", C.c_void_p), ("accept_count_dev", C.c_void_p),
         ("accept_mask_dev", C.c_void_p), ("lp_trace_dev", C.c_void_p),
+        ("prior_dev", C.c_void_p), ("ldprior", C.c_int),
     ]
 
 
@@ -92,6 +93,11 @@ SYMBOLS = {
     "bgm_causal_logpost": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_void_p]),
+    "bgm_causal_logpost_cond": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "bgm_causal_prior_rows": (C.c_int, [C.POINTER(NetDesc), C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p]),
     "bgm_causal_mh": (C.c_int, [C.c_void_p, C.POINTER(MhArgs), C.c_void_p]),
     "bgm_mh_adapt_qsd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_double, C.c_double,
                                    C.c_void_p, C.c_void_p]),

@@ -365,8 +365,9 @@ class CausalBGM(object):
 
     def _mh_device(self, x, y, v, ldv, n, burn_in, n_keep, q_sd, adaptive_sd, initial_q_sd,
                    target_acceptance_rate, tolerance, adjustment_interval, window_size,
-                   seed, row_offset, noise=None, trace=False, keep_samples=True, aux=None, slice_id=0):
-        """Runs the sampler on staged device buffers; returns a dict of device tensors."""
+                   seed, row_offset, noise=None, trace=False, keep_samples=True, aux=None, slice_id=0, prior=None):
+        """Runs the sampler on staged device buffers; returns a dict of device tensors.  `prior`: device
+        rows (n, zd+1) of a conditional prior (IdentifiableCausalBGM), see bgm_mh_args.prior_dev."""
         torch = _lib.require_cuda()
         aux = aux if aux is not None else self._aux(v, ldv, n)
         zd = sum(self._p['z_dims'])
@@ -392,6 +393,12 @@ class CausalBGM(object):
         a.out_samples_dev = samples.data_ptr() if keep_samples else None
         a.accept_count_dev = acc_count.data_ptr()
         keep = [aux]
+        if prior is not None:
+            if self._bnn:
+                raise NotImplementedError("bayesgm_b200: conditional prior with Bayesian nets")
+            assert prior.shape == (n, zd + 1) and prior.is_contiguous()
+            a.prior_dev, a.ldprior = prior.data_ptr(), zd + 1
+            keep.append(prior)
         if noise is not None:
             z0 = self._to_device(noise['z0'], torch)
             eps = self._to_device(noise['eps'], torch)
@@ -937,15 +944,19 @@ class CausalBGM(object):
         return tuple(float(a) for a in losses.cpu().numpy())
 
     def egm_init(self, data, egm_n_iter=30000, batch_size=32, egm_batches_per_eval=500, verbose=1, *,
-                 group=None, chunk=64, eval_during=True):
+                 group=None, chunk=64, eval_during=True, index_stream='numpy'):
         """causalbgm/base.py:380-431.  The data set stays on the device; mini-batch indices
         and prior draws come from NumPy's global generator in the reference's exact call
         order (g_d_freq x [choice, get_batch], then [get_batch, choice]) -- bit-exact index
         streams -- generated `chunk` iterations ahead and uploaded in one copy; the batches
         are gathered on the device.  Returns the last (dz_loss, d_loss) and generator losses.
         Every `egm_batches_per_eval` iterations the model is evaluated like :425-430 (`eval_during=False`
-        skips it); the (iteration, mse_x, mse_y, mse_v) history is kept in `self.egm_history`."""
+        skips it); the (iteration, mse_x, mse_y, mse_v) history is kept in `self.egm_history`.
+        `index_stream='floyd'` draws the mini-batches by subset sampling instead (same distribution,
+        O(batch) instead of O(n) host work per draw, NOT NumPy's legacy stream; _hostrng.FloydProducer)."""
         torch = _lib.require_cuda()
+        if index_stream not in ('numpy', 'floyd'):
+            raise ValueError("index_stream must be 'numpy' or 'floyd'")
         if group is not None:
             self._offset_streams(group)
         data_x, data_y, data_v = data
@@ -974,8 +985,8 @@ class CausalBGM(object):
         # choice :413] -- bit-exact, `chunk` iterations per hand-over; the state goes back into np.random
         # when the loop ends (`choice` without replacement permutes all n indices per call: at n >= 1e5 that
         # is more host time than the training step it feeds)
-        from ._hostrng import EgmProducer
-        prod = EgmProducer(n, bs, zd, freq, total, chunk=int(chunk))
+        from ._hostrng import EgmProducer, FloydProducer
+        prod = (EgmProducer if index_stream == 'numpy' else FloydProducer)(n, bs, zd, freq, total, chunk=int(chunk))
         try:
             self._egm_loop(prod, total, freq, bs, p, zd, xd, yd, vd, tr, st, dloss, gloss, bz, bv, bx, by, group,
                            egm_batches_per_eval, verbose, eval_during, torch)

@@ -250,7 +250,8 @@ static int launch_mh_tc_t(const bgm_causal* m, const MhDev& D, int grid, cudaStr
 }
 static bool use_tc(const bgm_causal* m) { return m->tc.enabled && m->sampler != 1; }
 static int launch_mh(const bgm_causal* m, MhDev& D, cudaStream_t st) {
-  if (use_tc(m)) {
+  // the conditional prior (bgm_mh_args.prior_dev) is a flag of the SIMT engine only
+  if (use_tc(m) && !D.a.prior_dev) {
     // 128-row tiles, two warpgroups per CTA
     const int nt = (D.a.n + TC_ROWS - 1) / TC_ROWS;
     const int grid = std::max(1, std::min((nt + 1) / 2, m->sm_count));
@@ -611,7 +612,17 @@ int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_d
                        const float* v_dev, int ldv, const float* vproj_dev, int ldvproj,
                        const float* r0_dev, const float* z_dev, int n, float* out_logp_dev,
                        int* sched_dev, void* stream) {
+  return bgm_causal_logpost_cond(m, x_dev, y_dev, v_dev, ldv, vproj_dev, ldvproj, r0_dev, z_dev, n, nullptr, 0,
+                                 out_logp_dev, sched_dev, stream);
+}
+
+int bgm_causal_logpost_cond(const bgm_causal* m, const float* x_dev, const float* y_dev,
+                            const float* v_dev, int ldv, const float* vproj_dev, int ldvproj,
+                            const float* r0_dev, const float* z_dev, int n, const float* prior_dev,
+                            int ldprior, float* out_logp_dev, int* sched_dev, void* stream) {
   if (!m) return fail(BGM_ERR_ARG, "bgm_causal_logpost: null model");
+  if (prior_dev && ldprior < m->prog.zd + 1)
+    return fail(BGM_ERR_ARG, "bgm_causal_logpost_cond: ldprior must be >= zd + 1");
   int rc = check_data("bgm_causal_logpost", m, x_dev, y_dev, v_dev, ldv, vproj_dev, ldvproj, r0_dev, sched_dev, n);
   if (rc) return rc;
   if (!z_dev || !out_logp_dev) return fail(BGM_ERR_ARG, "bgm_causal_logpost: null z / out pointer");
@@ -622,6 +633,8 @@ int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_d
   D.a.z_state_dev = const_cast<float*>(z_dev);
   D.a.lp_state_dev = out_logp_dev;
   D.a.init_mode = 1;
+  D.a.prior_dev = prior_dev;
+  D.a.ldprior = ldprior;
   D.mode = 1;
   return launch_mh(m, D, (cudaStream_t)stream);
 }
@@ -640,6 +653,8 @@ int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* a, void* stream) {
   if (a->init_mode == 2 && a->eps_dev)
     return fail(BGM_ERR_ARG, "bgm_causal_mh: init_mode 2 draws from Philox; pass z_state with injected noise");
   if (!a->q_sd_dev) return fail(BGM_ERR_ARG, "bgm_causal_mh: q_sd_dev is required");
+  if (a->prior_dev && a->ldprior < m->prog.zd + 1)
+    return fail(BGM_ERR_ARG, "bgm_causal_mh: ldprior must be >= zd + 1");
   MhDev D;
   D.a = *a;
   D.mode = 0;

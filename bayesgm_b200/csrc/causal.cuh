@@ -144,7 +144,8 @@ __device__ __forceinline__ void run_one(const TileOp& op, const float* __restric
 __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const float* __restrict__ wimg,
                                               const WarpSmem& S, const float* __restrict__ v,
                                               int ldv, int row0, int n, int lane, float x_l,
-                                              float y_l, float r0_l) {
+                                              float y_l, float r0_l,
+                                              const float* __restrict__ prior_row = nullptr) {
   const int rg = lane >> 3, cg = lane & 7;
   float sse[RPT];
 #pragma unroll
@@ -187,11 +188,20 @@ __device__ __forceinline__ float eval_logpost(const CausalProgram& P, const floa
         loss_px = (d * d) / (2.f * s2x) + logf(s2x) / 2.f;
       }
       float prior = 0.f;
-      for (int d = 0; d < P.zd; ++d) {
-        const float z = S.zin[act_idx(d, lane)];
-        prior = fmaf(z, z, prior);
+      if (prior_row) {  // z | u ~ N(mu(u), sigma^2(u) I), causalbgm/identifiable.py:540-548
+        for (int d = 0; d < P.zd; ++d) {
+          const float dz = S.zin[act_idx(d, lane)] - prior_row[d];
+          prior = fmaf(dz, dz, prior);
+        }
+        const float s2z = prior_row[P.zd];
+        prior = prior / (2.f * s2z) + ((float)P.zd * logf(s2z)) / 2.f;
+      } else {
+        for (int d = 0; d < P.zd; ++d) {
+          const float z = S.zin[act_idx(d, lane)];
+          prior = fmaf(z, z, prior);
+        }
+        prior *= 0.5f;                                                            // :812
       }
-      prior *= 0.5f;                                                              // :812
       result = -(((loss + loss_px) + result) + prior);                            // :814-816
     }
     __syncwarp();  // scratch rows are reused by the next net
@@ -263,6 +273,7 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
     const float x_l = A.x_dev[lrow], y_l = A.y_dev[lrow];
     const float r0_l = P.proj ? A.r0_dev[lrow] : 0.f;
     const int64_t grow = A.row_offset + lrow;
+    const float* prior_row = A.prior_dev ? A.prior_dev + (size_t)lrow * A.ldprior : nullptr;
     float zc[ZMAX];
     // input buffer: rows [0,zd) proposal, row zd = x, remaining pad rows zero
     for (int k = zd; k < P.kin; ++k) S.zin[act_idx(k, lane)] = (k == zd) ? x_l : 0.f;
@@ -312,7 +323,7 @@ causal_mh_kernel(const __grid_constant__ CausalProgram P, const float* __restric
         }
       }
       __syncwarp();
-      const float lp_prop = eval_logpost(P, wimg, S, vdat, ldd, row0, n, lane, x_l, y_l, r0_l);
+      const float lp_prop = eval_logpost(P, wimg, S, vdat, ldd, row0, n, lane, x_l, y_l, r0_l, prior_row);
       if (init_pass) {
         lp_cur = lp_prop;
         continue;

@@ -618,5 +618,22 @@ __global__ void sq_err_kernel(const float* __restrict__ T, int ldt, const float*
   if ((threadIdx.x & 31) == 0) atomicAdd(out, part);
 }
 
+// IdentifiableCausalBGM (causalbgm/identifiable.py:540-543): row r of the conditional prior =
+// prior_net(one_hot(u_r)) = table[seg[r]]: mu_z[zd], then sigma^2 = softplus(last output) + 1e-6.
+__global__ void prior_rows_kernel(const float* __restrict__ table, int zd, const int* __restrict__ seg, int n_seg,
+                                  int n, float* __restrict__ prior, int ldprior) {
+  const long long total = (long long)n * (zd + 1);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / (zd + 1)), d = (int)(i - (long long)r * (zd + 1));
+    const int u = min(max(seg[r], 0), n_seg - 1);
+    const float t = table[(size_t)u * (zd + 1) + d];
+    prior[(size_t)r * ldprior + d] = d < zd ? t : softplus_l(t) + 1e-6f;
+  }
+}
+
+__global__ void eye_kernel(float* __restrict__ a, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += gridDim.x * blockDim.x) a[i] = (i / n == i % n) ? 1.f : 0.f;
+}
+
 }  // namespace lt
 }  // namespace bgm

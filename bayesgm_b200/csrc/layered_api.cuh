@@ -1233,4 +1233,47 @@ int bgm_ltb_encode(bgm_ltb* t, const float* x_dev, int n, float* z_out_dev, void
   return arena_ok(t->arena, "bgm_ltb_encode");
 }
 
+// Conditional prior rows for bgm_mh_args.prior_dev / bgm_causal_logpost_cond: prior_net evaluated on the
+// n_segments one-hot inputs (a table of n_segments x (zd+1)), gathered by each row's segment.
+int bgm_causal_prior_rows(const bgm_net_desc* prior_net, int n_segments, int zd, const int* seg_dev, int n,
+                          float* prior_dev, int ldprior, void* stream) {
+  using namespace bgm;
+  using namespace bgm::lt;
+  if (!prior_net || !seg_dev || !prior_dev || n < 1 || n_segments < 1 || zd < 1 || ldprior < zd + 1)
+    return fail(BGM_ERR_ARG, "bgm_causal_prior_rows: bad argument");
+  const int L = prior_net->n_layers;
+  if (L < 1 || prior_net->dims[0] != n_segments || prior_net->dims[L] != zd + 1)
+    return fail(BGM_ERR_ARG, "bgm_causal_prior_rows: prior_net must map n_segments -> zd + 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t n_par = 0;
+  int wmax = n_segments;
+  for (int l = 0; l < L; ++l) {
+    n_par += (size_t)prior_net->dims[l] * prior_net->dims[l + 1] + prior_net->dims[l + 1];
+    wmax = std::max(wmax, prior_net->dims[l + 1]);
+  }
+  float* buf = nullptr;
+  const size_t act = (size_t)n_segments * wmax;
+  BGM_CUDA_OK(cudaMalloc(&buf, sizeof(float) * (n_par + 2 * act)));
+  cudaError_t e = cudaMemcpyAsync(buf, prior_net->params, sizeof(float) * n_par, cudaMemcpyHostToDevice, st);
+  float* a = buf + n_par;
+  float* b = a + act;
+  if (e == cudaSuccess) {
+    eye_kernel<<<4, 256, 0, st>>>(a, n_segments);
+    const float* w = buf;
+    for (int l = 0; l < L; ++l) {
+      const int K = prior_net->dims[l], N = prior_net->dims[l + 1];
+      dense_fwd_kernel<<<grid_for((long long)n_segments * N, 148), 256, 0, st>>>(a, K, w, nullptr, nullptr, nullptr, w + (size_t)K * N,
+                                                                            n_segments, K, N, b, N, l + 1 < L ? 1 : 0);
+      w += (size_t)K * N + N;
+      std::swap(a, b);
+    }
+    prior_rows_kernel<<<grid_for((long long)n * (zd + 1), 148), 256, 0, st>>>(a, zd, seg_dev, n_segments, n, prior_dev, ldprior);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(buf);
+  if (e != cudaSuccess) return fail(BGM_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
 }  // extern "C"

@@ -443,9 +443,9 @@ def run_cfg4(args):
     clocks = ClockSampler(D.local)
     clocks.start()
 
-    def step(i, group=D.group):
+    def step(i, group=D.group, index_stream='numpy'):
         model.egm_init((xd, yd, vd), egm_n_iter=iters - 1, batch_size=32, egm_batches_per_eval=10 ** 9, verbose=0,
-                       group=group, eval_during=False)
+                       group=group, eval_during=False, index_stream=index_stream)
         torch.cuda.synchronize()
     for i in range(max(1, min(args.warmup, 2))):
         step(i)
@@ -454,6 +454,10 @@ def run_cfg4(args):
     wall_nc = None
     if D.world > 1:        # the same without the collective: its share of the step
         wall_nc, _, _, _ = timed_passes(D, args.steps, lambda i: step(i, None), ratio_limit=1.5)
+    # the same steps fed by subset-sampled mini-batches (O(batch) host work per draw instead of the O(n)
+    # permutation behind np.random.choice(n, 32, replace=False)): what the device path does when the host stream is not the limit
+    step(0, D.group, 'floyd')
+    wall_fl, _, _, _ = timed_passes(D, args.steps, lambda i: step(i, D.group, 'floyd'), ratio_limit=1.5)
     if D.rank == 0:
         value = iters * args.steps / wall
         emit({"metric": "EGM training iterations/sec (5 discriminator + 1 generator steps, batch 32 per GPU)", "value": value,
@@ -468,6 +472,9 @@ def run_cfg4(args):
                          "collective": "NCCL all-reduce of the flat gradient buffer (dz: ~3k floats x5, g|e|f|h: ~66k floats x1)",
                          "index_stream": "NumPy legacy generator continued natively on a background thread (bit-exact)"},
               "mini_batches_per_s_per_gpu": 6 * value,
+              "index_stream_floyd": {"value": iters * args.steps / wall_fl, "unit": "EGM iterations/s",
+                                     "ms_per_step": 1e3 * wall_fl / args.steps,
+                                     "note": "egm_init(index_stream='floyd'): same distribution of mini-batches, not NumPy's stream"},
               "iterations_per_s_without_collective": None if wall_nc is None else iters * args.steps / wall_nc,
               "allreduce_share_of_step": None if wall_nc is None else max(0.0, 1.0 - wall_nc / wall),
               "reference_level": "tutorial tqdm: ~55 mini-batches/s in the iterative phase (docs/source/causalbgm/tutorial_py.ipynb:372)",

@@ -108,6 +108,12 @@ int bgm_causal_logpost(const bgm_causal* m, const float* x_dev, const float* y_d
                        const float* v_dev, int ldv, const float* vproj_dev, int ldvproj,
                        const float* r0_dev, const float* z_dev, int n, float* out_logp_dev,
                        int* sched_dev, void* stream);
+/* The same with the conditional prior rows of bgm_mh_args.prior_dev
+ * (IdentifiableCausalBGM.get_log_posterior, causalbgm/identifiable.py:505-556). */
+int bgm_causal_logpost_cond(const bgm_causal* m, const float* x_dev, const float* y_dev,
+                            const float* v_dev, int ldv, const float* vproj_dev, int ldvproj,
+                            const float* r0_dev, const float* z_dev, int n, const float* prior_dev,
+                            int ldprior, float* out_logp_dev, int* sched_dev, void* stream);
 
 /* CausalBGM.metropolis_hastings_sampler (causalbgm/base.py:820-904): iterations
  * [t_begin, t_end) of n independent random-walk MH chains in ONE persistent launch.
@@ -145,7 +151,18 @@ typedef struct {
   int* accept_count_dev;    /* (T) accepted proposals per iteration (atomicAdd)   */
   uint8_t* accept_mask_dev; /* (T,n) per-row accept decisions (trace)             */
   float* lp_trace_dev;      /* (T,n) proposed log-posteriors (trace)              */
+  /* conditional prior z | u ~ N(mu(u), sigma^2(u) I) of IdentifiableCausalBGM.get_log_posterior
+   * (causalbgm/identifiable.py:540-548): row i holds mu_z[zd] then sigma^2; NULL = the N(0,I)
+   * prior of causalbgm/base.py:812.  Runs on the SIMT engine.                                    */
+  const float* prior_dev;   /* (n,ldprior), ldprior >= zd+1                        */
+  int ldprior;
 } bgm_mh_args;
+
+/* Rows for bgm_mh_args.prior_dev: prior_net (n_segments -> zd+1, BaseFullyConnectedNet) evaluated on
+ * the one-hot auxiliary variable u of every row (causalbgm/identifiable.py:540-543, :566-570):
+ * prior_dev[r] = (mu_z[zd], softplus(last output)+1e-6) of segment seg_dev[r].  Synchronises the stream. */
+int bgm_causal_prior_rows(const bgm_net_desc* prior_net, int n_segments, int zd, const int* seg_dev, int n,
+                          float* prior_dev, int ldprior, void* stream);
 
 int bgm_causal_mh(const bgm_causal* m, const bgm_mh_args* args, void* stream);
 

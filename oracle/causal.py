@@ -19,8 +19,10 @@ def _split(params):
     return d0, d1, d2, d3
 
 
-def log_posterior(params, nets, data_x, data_y, data_v, data_z, eps=1e-6):
-    """causalbgm/base.py:765-817, float32 throughout."""
+def log_posterior(params, nets, data_x, data_y, data_v, data_z, eps=1e-6, prior=None):
+    """causalbgm/base.py:765-817, float32 throughout.  `prior=(mu_z (n,zd), sigma2_z (n,))` replaces
+    the N(0,I) prior by the conditional one of IdentifiableCausalBGM.get_log_posterior
+    (causalbgm/identifiable.py:505-556, prior term :540-548)."""
     d0, d1, d2, _ = _split(params)
     p = params['v_dim']
     f32 = np.float32
@@ -58,7 +60,13 @@ def log_posterior(params, nets, data_x, data_y, data_v, data_z, eps=1e-6):
     else:                                                               # :806
         loss_px = ((x - mu_x) ** 2).sum(axis=1) / (2 * s2x) + np.log(s2x) / 2
     loss_py = ((y - mu_y) ** 2).sum(axis=1) / (2 * s2y) + np.log(s2y) / 2   # :809
-    loss_prior = (z ** 2).sum(axis=1) / 2                               # :812
+    if prior is None:
+        loss_prior = (z ** 2).sum(axis=1) / 2                           # :812
+    else:                                                               # identifiable.py:540-548
+        mu_z, s2z = np.asarray(prior[0], f32), np.asarray(prior[1], f32).reshape(-1)
+        term1 = ((z - mu_z) ** 2).sum(axis=1) / (f32(2.0) * s2z)
+        term2 = f32(z.shape[1]) * np.log(s2z) / f32(2.0)
+        loss_prior = term1 + term2
     return (-(loss_pv + loss_px + loss_py + loss_prior)).astype(f32)    # :814-816
 
 
@@ -106,8 +114,13 @@ class NumpyGlobalNoise(object):
 def mh_sampler(params, nets, data, initial_q_sd=1.0, q_sd=None, burn_in=5000, n_keep=3000,
                target_acceptance_rate=0.25, tolerance=0.05, adjustment_interval=50,
                adaptive_sd=None, window_size=100, noise=None, recompute_current=True,
-               return_trace=False):
+               return_trace=False, prior=None, nets_at=None):
     """causalbgm/base.py:820-904.
+
+    `prior`: conditional prior rows of IdentifiableCausalBGM (identifiable.py:559-616 is this loop
+    with `data_u` passed on).  `nets_at(t)`: the nets of iteration t -- FullMCMCCausalBGM draws one
+    posterior weight sample per iteration and evaluates BOTH states with it
+    (causalbgm/fullmcmc.py:438-449), so the current state's value cannot be cached.
 
     `recompute_current=True` evaluates the current state's log-posterior every
     iteration exactly like :866; False caches it (what the CUDA kernel does --
@@ -131,9 +144,11 @@ def mh_sampler(params, nets, data, initial_q_sd=1.0, q_sd=None, burn_in=5000, n_
     cur_lp = None
     while len(samples) < n_keep:                                         # :860
         proposed_state = current_state + noise.proposal(q_sd, n, zd)     # :862
-        prop_lp = log_posterior(params, nets, data_x, data_y, data_v, proposed_state)  # :865
-        if recompute_current or cur_lp is None:
-            cur_lp = log_posterior(params, nets, data_x, data_y, data_v, current_state)  # :866
+        if nets_at is not None:                                          # fullmcmc.py:441-444
+            nets = nets_at(counter)
+        prop_lp = log_posterior(params, nets, data_x, data_y, data_v, proposed_state, prior=prior)  # :865
+        if recompute_current or cur_lp is None or nets_at is not None:
+            cur_lp = log_posterior(params, nets, data_x, data_y, data_v, current_state, prior=prior)  # :866
         ratio = np.exp(np.minimum(prop_lp - cur_lp, 0))                  # :868 (float32)
         indices = noise.uniform(n) < ratio                               # :870 (f64 < f32)
         current_state[indices] = proposed_state[indices]                 # :871
@@ -170,9 +185,20 @@ def f_net_on(params, nets, z, xcol):
     return mlp_forward(nets['f'], inp)
 
 
+def conditional_prior(params, prior_net, segments, eps=1e-6):
+    """IdentifiableCausalBGM's p(z|u) (causalbgm/identifiable.py:540-543): prior_net on the one-hot
+    rows of `segments` (:566-570) -> (mu_z (n,zd), sigma2_z (n,)), float32."""
+    zd = sum(params['z_dims'])
+    u = np.eye(int(params.get('n_segments', 10)), dtype=np.float32)[np.asarray(segments)]
+    out = mlp_forward(prior_net, u)
+    return out[:, :zd], softplus(out[:, -1]) + np.float32(eps)
+
+
 def infer_from_latent_posterior(params, nets, data_posterior_z, x_values=None, sample_y=True,
-                                eps=1e-6, normal_fn=None):
-    """causalbgm/base.py:671-763.
+                                eps=1e-6, normal_fn=None, nets_at=None):
+    """causalbgm/base.py:671-763.  `nets_at(s)`: the nets paired with kept state s
+    (FullMCMCCausalBGM.infer_from_latent_posterior, causalbgm/fullmcmc.py:285-342; same outputs,
+    this function keeps the base class's (len(x_values), n_keep) orientation).
 
     `normal_fn(shape)` supplies the N(0,1) draws of tf.random.normal (:704,:725,
     :753); required when sample_y=True (TF's stream is not reproducible outside TF).
@@ -200,7 +226,7 @@ def infer_from_latent_posterior(params, nets, data_posterior_z, x_values=None, s
             mu_all = np.empty((n_keep, n), f32)
             s2_all = np.empty((n_keep, n), f32)
             for s in range(n_keep):
-                mu, s2 = head(f_net_on(params, nets, zs[s], np.full((n, 1), xv, f32)))
+                mu, s2 = head(f_net_on(params, nets_at(s) if nets_at else nets, zs[s], np.full((n, 1), xv, f32)))
                 mu_all[s] = mu
                 s2_all[s] = s2
             mus.append(mu_all)
@@ -214,7 +240,7 @@ def infer_from_latent_posterior(params, nets, data_posterior_z, x_values=None, s
         mu_all = np.empty((n_keep, n), f32)
         s2_all = np.empty((n_keep, n), f32)
         for s in range(n_keep):
-            mu, s2 = head(f_net_on(params, nets, zs[s], np.full((n, 1), f32(xv), f32)))
+            mu, s2 = head(f_net_on(params, nets_at(s) if nets_at else nets, zs[s], np.full((n, 1), f32(xv), f32)))
             mu_all[s] = mu
             s2_all[s] = s2
         out[j] = draw(mu_all, s2_all).mean(axis=1)                       # :759

@@ -26,9 +26,11 @@ def test_library_loads_and_exports_header_symbols():
 
 def test_mh_args_struct_layout_matches_header():
     # pointers 8 bytes, ints 4, natural alignment:
-    # x,y,v | ldv,n | vproj,r0 | ldvproj(+pad) | sched | z,lp | 4 ints | q_sd,eps,u | seed,row_offset | 4 ptrs
-    assert ctypes.sizeof(_lib.MhArgs) == 24 + 8 + 16 + 8 + 8 + 16 + 16 + 24 + 16 + 32
+    # x,y,v | ldv,n | vproj,r0 | ldvproj(+pad) | sched | z,lp | 4 ints | q_sd,eps,u | seed,row_offset | 4 ptrs |
+    # prior, ldprior(+pad)
+    assert ctypes.sizeof(_lib.MhArgs) == 24 + 8 + 16 + 8 + 8 + 16 + 16 + 24 + 16 + 32 + 16
     assert _lib.MhArgs.sched_dev.offset == 56 and _lib.MhArgs.q_sd_dev.offset == 96
+    assert _lib.MhArgs.prior_dev.offset == 168
 
 
 def test_hmc_args_struct_layout_matches_header():

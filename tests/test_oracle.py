@@ -168,3 +168,37 @@ def test_torch_cpu_restatement_matches_numpy_oracle():
                               noise=causal.NumpyGlobalNoise(np.random.RandomState(9)))
         same = (a == b).all(axis=(0, 2))
         assert same.mean() > 0.9
+
+
+def test_conditional_prior_and_per_iteration_nets_reduce_to_the_base_algorithm():
+    """oracle.causal: identifiable.py:540-548 with mu = 0, sigma^2 = 1 is the N(0, I) prior of base.py:812; a
+    constant `nets_at` (fullmcmc.py:441-449 with one weight sample) is the base sampler."""
+    from helpers import causal_params, causal_nets, causal_data, injected_noise
+    from oracle import causal as oc
+    from oracle import nets as onets
+    params = causal_params(20, [1, 1, 1, 2], n_segments=4)
+    nets = causal_nets(params)
+    n, T = 40, 12
+    x, y, v = causal_data(n, 20)
+    z = np.random.RandomState(0).standard_normal((n, 5)).astype(np.float32)
+    base = oc.log_posterior(params, nets, x, y, v, z)
+    unit = (np.zeros((n, 5), np.float32), np.ones(n, np.float32))
+    np.testing.assert_allclose(oc.log_posterior(params, nets, x, y, v, z, prior=unit), base, rtol=1e-6, atol=1e-5)
+    # by hand for one row: -(sum (z - mu)^2 / (2 s2) + zd log(s2) / 2) replaces -sum z^2 / 2
+    prior_net = onets.init_mlp(np.random.RandomState(3), [4, 64, 6], 0.5)
+    seg = np.random.RandomState(1).randint(0, 4, size=n)
+    mu, s2 = oc.conditional_prior(params, prior_net, seg)
+    assert mu.shape == (n, 5) and s2.shape == (n,) and np.all(s2 > 0)
+    assert np.array_equal(mu[seg == seg[0]], np.repeat(mu[:1], (seg == seg[0]).sum(), axis=0))   # a table over segments
+    got = oc.log_posterior(params, nets, x, y, v, z, prior=(mu, s2))
+    want = base.astype(np.float64) + (z.astype(np.float64) ** 2).sum(1) / 2 - (
+        ((z - mu).astype(np.float64) ** 2).sum(1) / (2 * s2) + 5 * np.log(s2.astype(np.float64)) / 2)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3)
+    nz = injected_noise(n, 5, T)
+    mk = lambda: oc.InjectedNoise(nz['z0'], nz['eps'], nz['u'])
+    a = oc.mh_sampler(params, nets, (x, y, v), q_sd=0.5, burn_in=4, n_keep=8, noise=mk())
+    b = oc.mh_sampler(params, None, (x, y, v), q_sd=0.5, burn_in=4, n_keep=8, noise=mk(), nets_at=lambda t: nets)
+    assert np.array_equal(a, b)
+    c = oc.infer_from_latent_posterior(params, nets, a, x_values=[0.5], sample_y=False)
+    d = oc.infer_from_latent_posterior(params, None, a, x_values=[0.5], sample_y=False, nets_at=lambda s: nets)
+    assert np.array_equal(c, d)
