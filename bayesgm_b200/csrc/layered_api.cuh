@@ -122,6 +122,24 @@ static inline int grid_for(long long total, int sm) {
   return (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm * 8));
 }
 
+// tiled launches of the two dense kernels (layered.cuh, dense_tile_kernel)
+static inline void dense_fwd(const float* A, int lda, const float* W, const float* dW, const signed char* s_in,
+                             const signed char* s_out, const float* bias, int B, int K, int N, float* out, int ldo, int act,
+                             cudaStream_t st) {
+  DenseTileArgs a;
+  a.X = A; a.ldx = lda; a.sX = s_in; a.W = W; a.dW = dW; a.sO = s_out; a.bias = bias; a.A_post = nullptr; a.lda = 0;
+  a.O = out; a.ldo = ldo; a.B = B; a.K = K; a.N = N; a.act = act; a.accumulate = 0;
+  dense_tile_kernel<false><<<dim3((N + 31) / 32, (B + 31) / 32), 256, 0, st>>>(a);
+}
+static inline void dense_bwd_input(const float* dY, int ldy, const float* W, const float* dW, const signed char* s_in,
+                                   const signed char* s_out, const float* A_post, int lda, int B, int K, int N, float* dA,
+                                   int ldd, int accumulate, cudaStream_t st) {
+  DenseTileArgs a;
+  a.X = dY; a.ldx = ldy; a.sX = s_out; a.W = W; a.dW = dW; a.sO = s_in; a.bias = nullptr; a.A_post = A_post; a.lda = lda;
+  a.O = dA; a.ldo = ldd; a.B = B; a.K = K; a.N = N; a.act = 0; a.accumulate = accumulate;
+  dense_tile_kernel<true><<<dim3((K + 31) / 32, (B + 31) / 32), 256, 0, st>>>(a);
+}
+
 static size_t pass_bytes(const LNet& n, long long B) {
   size_t b = 0;
   auto al = [](size_t x) { return (x + 255) / 256 * 256 + 256; };
@@ -206,9 +224,9 @@ static void net_fwd(const Ctx& C, const LNet& net, Pass& P, const float* X, int 
     }
     P.a[l + 1] = ar.get<float>((size_t)B * N);
     P.lda[l + 1] = N;
-    dense_fwd_kernel<<<grid_for((long long)B * N, sm), 256, 0, st>>>(P.a[l], P.lda[l], th + net.off_w[l], P.dW[l], P.sin[l],
+    dense_fwd(P.a[l], P.lda[l], th + net.off_w[l], P.dW[l], P.sin[l],
                                                                     P.sout[l], th + net.off_b[l], B, K, N, P.a[l + 1], N,
-                                                                    l < net.L - 1 ? 1 : 0);
+                                                                    l < net.L - 1 ? 1 : 0, st);
   }
 }
 
@@ -228,16 +246,16 @@ static void net_bwd(const Ctx& C, const LNet& net, const Pass& P, const float* d
           g + net.off_w[l], net.flip ? g + net.off_rho[l] : nullptr, g + net.off_b[l]);
     if (l > 0) {
       float* dA = ar.get<float>((size_t)B * K);
-      dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + net.off_w[l], P.dW[l], P.sin[l],
-                                                                            P.sout[l], P.a[l], P.lda[l], B, K, N, dA, K, 0);
+      dense_bwd_input(dY, N, th + net.off_w[l], P.dW[l], P.sin[l],
+                                                                            P.sout[l], P.a[l], P.lda[l], B, K, N, dA, K, 0, st);
       dY = dA;
       continue;
     }
     if (net.bn_in) {
       if (!param_grads && !dX) break;
       float* dA0 = ar.get<float>((size_t)B * K);
-      dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + net.off_w[0], P.dW[0], P.sin[0],
-                                                                            P.sout[0], nullptr, 0, B, K, N, dA0, K, 0);
+      dense_bwd_input(dY, N, th + net.off_w[0], P.dW[0], P.sin[0],
+                                                                            P.sout[0], nullptr, 0, B, K, N, dA0, K, 0, st);
       float* s1 = ar.get<float>(K);
       float* s2 = ar.get<float>(K);
       bn_bwd_sums_kernel<<<(K + 127) / 128, 128, 0, st>>>(dA0, nullptr, P.xhat, B, K, 0, s1, s2,
@@ -247,9 +265,9 @@ static void net_bwd(const Ctx& C, const LNet& net, const Pass& P, const float* d
         bn_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dA0, nullptr, P.xhat, P.inv, th + net.off_gamma,
                                                                            s1, s2, B, K, 0, dX, lddx, accumulate_dx ? 1 : 0);
     } else if (dX) {
-      dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + net.off_w[0], nullptr, nullptr,
+      dense_bwd_input(dY, N, th + net.off_w[0], nullptr, nullptr,
                                                                             nullptr, nullptr, 0, B, K, N, dX, lddx,
-                                                                            accumulate_dx ? 1 : 0);
+                                                                            accumulate_dx ? 1 : 0, st);
     }
   }
 }
@@ -267,8 +285,8 @@ static void disc_fwd(const Ctx& C, const tr::Disc& dz, const float* th, DiscPass
     D.out[l] = ar.get<float>((size_t)B * N);
     D.mean[l] = ar.get<float>(N);
     D.inv[l] = ar.get<float>(N);
-    dense_fwd_kernel<<<grid_for((long long)B * N, sm), 256, 0, st>>>(a, K, th + dz.w_off[l], nullptr, nullptr, nullptr,
-                                                                    th + dz.b_off[l], B, K, N, D.pre[l], N, 0);
+    dense_fwd(a, K, th + dz.w_off[l], nullptr, nullptr, nullptr,
+                                                                    th + dz.b_off[l], B, K, N, D.pre[l], N, 0, st);
     col_stats_kernel<<<N, 256, 0, st>>>(D.pre[l], N, B, N, D.mean[l], D.inv[l]);
     bn_fwd_kernel<<<grid_for((long long)B * N, sm), 256, 0, st>>>(D.pre[l], N, D.mean[l], D.inv[l], th + dz.g_off[l],
                                                                  th + dz.be_off[l], B, N, D.xhat[l], D.out[l], 2, -1);
@@ -276,8 +294,8 @@ static void disc_fwd(const Ctx& C, const tr::Disc& dz, const float* th, DiscPass
   }
   const int K = dz.dims[dz.L];
   D.d = ar.get<float>(B);
-  dense_fwd_kernel<<<grid_for(B, sm), 256, 0, st>>>(a, K, th + dz.w_off[dz.L], nullptr, nullptr, nullptr,
-                                                   th + dz.b_off[dz.L], B, K, 1, D.d, 1, 0);
+  dense_fwd(a, K, th + dz.w_off[dz.L], nullptr, nullptr, nullptr,
+                                                   th + dz.b_off[dz.L], B, K, 1, D.d, 1, 0, st);
 }
 // Backward of one discriminator call from dd (B) = d loss / d D: parameter gradients (+= into g, Keras order of
 // tr::Disc) when g != NULL, and the gradient w.r.t. the input added into dZ (B, dims[0]) when dZ != NULL.
@@ -306,12 +324,12 @@ static void disc_bwd(const Ctx& C, const tr::Disc& dz, const float* th, float* g
                                                                             K, N, g + dz.w_off[l], nullptr, g + dz.b_off[l]);
     if (l == 0) {
       if (dZ)
-        dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + dz.w_off[0], nullptr, nullptr, nullptr,
-                                                                              nullptr, 0, B, K, N, dZ, K, 1);
+        dense_bwd_input(dY, N, th + dz.w_off[0], nullptr, nullptr, nullptr,
+                                                                              nullptr, 0, B, K, N, dZ, K, 1, st);
     } else {
       float* dA = ar.get<float>((size_t)B * K);
-      dense_bwd_input_kernel<<<grid_for((long long)B * K, sm), 256, 0, st>>>(dY, N, th + dz.w_off[l], nullptr, nullptr, nullptr,
-                                                                            nullptr, 0, B, K, N, dA, K, 0);
+      dense_bwd_input(dY, N, th + dz.w_off[l], nullptr, nullptr, nullptr,
+                                                                            nullptr, 0, B, K, N, dA, K, 0, st);
       dY = dA;
       N = K;
     }
@@ -1262,8 +1280,8 @@ int bgm_causal_prior_rows(const bgm_net_desc* prior_net, int n_segments, int zd,
     const float* w = buf;
     for (int l = 0; l < L; ++l) {
       const int K = prior_net->dims[l], N = prior_net->dims[l + 1];
-      dense_fwd_kernel<<<grid_for((long long)n_segments * N, 148), 256, 0, st>>>(a, K, w, nullptr, nullptr, nullptr, w + (size_t)K * N,
-                                                                            n_segments, K, N, b, N, l + 1 < L ? 1 : 0);
+      dense_fwd(a, K, w, nullptr, nullptr, nullptr, w + (size_t)K * N,
+                                                                            n_segments, K, N, b, N, l + 1 < L ? 1 : 0, st);
       w += (size_t)K * N + N;
       std::swap(a, b);
     }
