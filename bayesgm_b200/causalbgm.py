@@ -913,6 +913,13 @@ class CausalBGM(object):
             got[k] = [z["%s_%d" % (k, i)] for i in range(sum(1 for name in z.files if name.startswith(k + "_")))]
         self.set_weights(**got)
 
+    def load_tf_checkpoint(self, path):
+        """Restores the nets from a checkpoint written by the reference (`tf.train.Checkpoint`, :112-127): `path` is a
+        checkpoint prefix (`.../ckpt-5`) or the directory a CheckpointManager wrote.  Deterministic nets only; see
+        bayesgm_b200/tf_checkpoint.py for the format reader and its validation status."""
+        from .tf_checkpoint import load_tf_checkpoint
+        return load_tf_checkpoint(self, path)
+
     def train_disc_step(self, data_z, data_v, *, epsilon=None, group=None):
         """causalbgm/base.py:305-330 -> (dz_loss, d_loss).  `epsilon` is the U(0,1) draw of
         :307 (TensorFlow's stream in the reference; here a private RandomState unless given).
