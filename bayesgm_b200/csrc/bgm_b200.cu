@@ -724,6 +724,13 @@ int bgm_causal_effect_combine(const bgm_causal* m, const float* heads_dev, const
     return fail(BGM_ERR_ARG, "bgm_causal_effect_combine: binary needs ite_dev, continuous adrf_sum_dev and n_x >= 1");
   C.sample_y = sample_y ? 1 : 0; C.s2y = m->prog.s2y; C.seed = seed; C.row_offset = row_offset; C.noise = noise_dev;
   C.adrf_sum = adrf_sum_dev; C.ite = ite_dev;
+  if (n >= 4096) {
+    // row-major walk: enough rows to fill the GPU with (row block, dose group) CTAs
+    const long long blocks = (long long)((n + 127) / 128) * ((C.n_x + 3) / 4);
+    effect_combine_rows_kernel<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>(C);
+    BGM_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const long long ntiles = (long long)((n + 31) / 32) * n_keep;
   const int grid = (int)std::max<long long>(1, std::min<long long>((ntiles + 7) / 8, (long long)m->sm_count * 16));
   effect_combine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(C);

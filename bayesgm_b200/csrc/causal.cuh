@@ -646,6 +646,82 @@ __global__ void __launch_bounds__(256) effect_combine_kernel(const __grid_consta
   }
 }
 
+// The same reductions, row-major: thread = row, block = 128 rows x one group of 4 doses, the thread walks
+// its row's kept states in order.  A rejected proposal repeats the state, so the (mu, sigma) of the group
+// stay in registers until the running count `local` moves (each head is read once, 32 contiguous bytes),
+// where the kernel above gathers 8 bytes per (kept state, row, dose) at a ~20 KB stride across the warp.
+// Same Philox draws (normal4 of (row, s, group)), same float warp sums; per-warp partials of a segment of
+// kept states are parked in shared memory and added to the float64 accumulators once per block in warp
+// order (4x fewer atomics).
+constexpr int COMBINE_SEG = 256;
+__global__ void __launch_bounds__(128) effect_combine_rows_kernel(const __grid_constant__ CombineDev C) {
+  __shared__ float part[4][COMBINE_SEG][4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_groups = (C.n_x + 3) >> 2;
+  const int group = blockIdx.x % n_groups;
+  const int row = (blockIdx.x / n_groups) * 128 + threadIdx.x;
+  const bool valid = row < C.n;
+  const int lrow = valid ? row : C.n - 1;
+  const int64_t grow = C.row_offset + lrow;
+  const int j0 = group * 4;
+  const int nj = min(4, C.n_x - j0);
+  const int base = C.rowend[lrow] - C.local[(size_t)(C.n_keep - 1) * C.n + lrow] - 1;
+  int cur = -1;
+  float mu[4] = {0.f, 0.f, 0.f, 0.f}, sd[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s0 = 0; s0 < C.n_keep; s0 += COMBINE_SEG) {
+    const int s1 = min(s0 + COMBINE_SEG, C.n_keep);
+    for (int s = s0; s < s1; ++s) {
+      const int loc = C.local[(size_t)s * C.n + lrow];
+      if (loc != cur) {
+        cur = loc;
+        const float2* h = reinterpret_cast<const float2*>(C.heads) + (size_t)(base + loc) * C.n_x + j0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < nj) {
+            const float2 mr = __ldg(h + k);
+            mu[k] = mr.x;
+            sd[k] = C.sample_y ? sqrtf(C.s2y >= 0.f ? C.s2y : softplus_f(mr.y) + 1e-6f) : 0.f;
+          }
+        }
+      }
+      float y[4] = {mu[0], mu[1], mu[2], mu[3]};
+      if (C.sample_y) {
+        float e[4];
+        if (C.noise) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) e[k] = k < nj ? C.noise[((size_t)(j0 + k) * C.n_keep + s) * C.n + lrow] : 0.f;
+        } else {
+          normal4(C.seed, grow, (uint32_t)s, NOISE_EFFECT, (uint32_t)group, e);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) y[k] = fmaf(sd[k], e[k], y[k]);
+      }
+      if (C.binary) {
+        if (valid) C.ite[(size_t)s * C.n + row] = y[0] - y[1];
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float v = valid ? y[k] : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        y[k] = v;
+      }
+      if (lane == 0) *reinterpret_cast<float4*>(part[warp][s - s0]) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+    if (C.binary) continue;
+    __syncthreads();
+    for (int i = threadIdx.x; i < (s1 - s0) * 4; i += 128) {
+      const int ss = i >> 2, k = i & 3;
+      if (k < nj) {
+        const double tot = (((double)part[0][ss][k] + (double)part[1][ss][k]) + (double)part[2][ss][k]) + (double)part[3][ss][k];
+        atomicAdd(C.adrf_sum + (size_t)(j0 + k) * C.n_keep + s0 + ss, tot);
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // 1-thread kernel: the q_sd adaptation rule, causalbgm/base.py:880-890.
 __global__ void mh_adapt_qsd_kernel(const int* __restrict__ accept_count, int t, int window,
                                     long long n_total, double target, double tol, double* q_sd) {

@@ -317,8 +317,9 @@ def test_full_size_properties():
     lp_close(lp[idx], want)
 
 
-@pytest.mark.parametrize("binary,engine", [(False, 'tensor'), (True, 'tensor'), (False, 'simt')])
-def test_memoised_effect_equals_direct_evaluation(binary, engine):
+@pytest.mark.parametrize("binary,engine,n,n_keep", [(False, 'tensor', 333, 40), (True, 'tensor', 333, 40), (False, 'simt', 333, 40),
+                                                     (False, 'tensor', 4321, 300), (True, 'tensor', 4100, 17)])
+def test_memoised_effect_equals_direct_evaluation(binary, engine, n, n_keep):
     """Kept states with long runs of repeats (what a 25 % acceptance rate produces): evaluating f_net
     once per distinct state and combining gives exactly what evaluating it at every kept state gives."""
     z_dims = [3, 6, 3, 6] if binary else [1, 1, 1, 2]
@@ -326,7 +327,7 @@ def test_memoised_effect_equals_direct_evaluation(binary, engine):
     params = causal_params(v_dim, z_dims, binary)
     m = product_model(params, causal_nets(params), engine)
     rs = np.random.RandomState(12)
-    n, n_keep, zd = 333, 40, sum(z_dims)
+    zd = sum(z_dims)                                 # n >= 4096: the row-major combine kernel (segments of 256 kept states)
     zs = np.empty((n_keep, n, zd), np.float32)
     zs[0] = rs.standard_normal((n, zd))
     for s in range(1, n_keep):                       # each row moves with probability 0.25
@@ -335,10 +336,11 @@ def test_memoised_effect_equals_direct_evaluation(binary, engine):
     import torch
     zd_ = torch.from_numpy(zs).cuda()
     xv = None if binary else np.linspace(0, 3, 7)
-    for sample_y in (False, True):
-        a = m._effect_device(zd_, n_keep, n, xv, sample_y, 5, 1000, memoise=True).cpu().numpy()
+    nz = rs.standard_normal((2 if binary else 7, n_keep, n)).astype(np.float32)
+    for sample_y, noise in ((False, None), (True, None), (True, nz)):
+        a = m._effect_device(zd_, n_keep, n, xv, sample_y, 5, 1000, noise=noise, memoise=True).cpu().numpy()
         frac = m.last_distinct_fraction
-        b = m._effect_device(zd_, n_keep, n, xv, sample_y, 5, 1000, memoise=False).cpu().numpy()
+        b = m._effect_device(zd_, n_keep, n, xv, sample_y, 5, 1000, noise=noise, memoise=False).cpu().numpy()
         if binary:
             np.testing.assert_array_equal(a, b)      # per-subject values: bit-identical
         else:
