@@ -91,7 +91,7 @@ struct bgm_lt {
   float* scratch = nullptr;      // 64 floats of loss accumulators
   uint64_t seed = 0;
   uint32_t call_ctr = 0;
-  int sm_count = 148, smem_disc = 0, wm_disc = 4;
+  int sm_count = 148, smem_disc = 0, wm_disc = 4, stage_disc = 0;
 };
 
 // BGM flavour (bgm/base.py:145-291): generator = BaseVariationalNet (input BatchNormalization in training mode +
@@ -451,6 +451,8 @@ int bgm_lt_create(bgm_lt** out, const int z_dims[4], int v_dim, int binary_treat
   t->n1 = t->dz.n_params;
   t->wm_disc = (std::max(t->zd, 4) + 3) / 4 * 4;
   t->smem_disc = (2 * t->wm_disc * tr::LD + 3 * t->zd * tr::LD + tr::disc_smem_floats(t->dz, true)) * 4 + 64;
+  t->stage_disc = t->smem_disc + 8 * t->dz.n_params <= 200 * 1024;     // DiscArgs.stage: parameters + gradients in shared memory
+  if (t->stage_disc) t->smem_disc += 8 * t->dz.n_params;
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -545,7 +547,7 @@ int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, 
   A.dz = t->dz; A.zd = t->zd; A.p = t->p; A.bs = bs;
   A.theta = nullptr; A.theta_d = t->theta[1]; A.grad_d = t->grad[1];
   A.z = z_dev; A.v = nullptr; A.zenc_in = eA.out();
-  A.epsilon = epsilon; A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm_disc;
+  A.epsilon = epsilon; A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm_disc; A.stage = t->stage_disc;
   BGM_CUDA_OK(cudaFuncSetAttribute(tr::disc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_disc));
   tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, st>>>(A);
   return arena_ok(t->arena, "bgm_lt_disc_grad");

@@ -67,6 +67,9 @@ struct DiscArgs {
   float* losses;             // [2]: dz_loss, d_loss
   int wm;
   const float* zenc_in;      // optional (bs, zd): z_ = e_net(v) computed elsewhere (Bayesian e_net, layered engine)
+  int stage;                 // != 0: 2 * dz.n_params extra floats of shared memory hold the discriminator's parameters
+                             // and its gradient accumulators for the whole kernel (thread = feature loops otherwise pay an
+                             // L2 round trip per weight and a global read-modify-write per gradient)
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -715,6 +718,12 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
   disc_carve(dz, zhat + A.zd * LD, true, B, scr, sbar, outv);
   const float* th_s = A.theta_d;
   float* gacc = A.grad_d;
+  if (A.stage) {
+    float* th_sm = outv + 64;
+    gacc = th_sm + dz.n_params;
+    for (int i = threadIdx.x; i < dz.n_params; i += NTH) th_sm[i] = A.theta_d[i];
+    th_s = th_sm;
+  }
   for (int i = threadIdx.x; i < dz.n_params; i += NTH) gacc[i] = 0.f;
   if (A.zenc_in) load_cols(A.zenc_in, A.zd, 0, A.zd, bs, bufA);
   else load_cols(A.v, A.p, 0, A.p, bs, bufA);
@@ -773,6 +782,8 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
   __syncthreads();
   disc_double_backward(dz, th_s, B, bs, UB0, scr, sbar, gacc, A.gp_weight, disc_maxd(dz));
   __syncthreads();
+  if (A.stage)
+    for (int i = threadIdx.x; i < dz.n_params; i += NTH) A.grad_d[i] = gacc[i];
   if (threadIdx.x == 0) {
     const float dz_loss = -mean_d + mean_d_;               // :316
     A.losses[0] = dz_loss;

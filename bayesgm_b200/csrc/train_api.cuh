@@ -20,6 +20,7 @@ struct bgm_trainer {
   long long step[2] = {0, 0};
   double lr = 0, b1 = 0.9, b2 = 0.99;
   int wm = 0, smem_gen = 0, smem_disc = 0, sm_count = 0;
+  int stage_disc = 0;
   // BGM flavour (kind == 1): variational generator, two discriminators
   int kind = 0;
   bgm::tr::VarNet vg;
@@ -277,6 +278,9 @@ int bgm_trainer_create(bgm_trainer** out, const int z_dims[4], int v_dim, int bi
     delete t;
     return fail(BGM_ERR_NOMEM, "bgm_trainer_create: v_dim / layer widths too large for the single-CTA training kernels");
   }
+  // discriminator parameters + gradient accumulators in shared memory when they fit (DiscArgs.stage)
+  t->stage_disc = t->smem_disc + 8 * D.n_params <= smem_max - 1024;
+  if (t->stage_disc) t->smem_disc += 8 * D.n_params;
   t->tape_floats = 2 * tr::net_tape_floats(t->g) + 2 * tr::net_tape_floats(t->e) + tr::net_tape_floats(t->f) +
                    tr::net_tape_floats(t->h) + (v_dim + zd) * tr::LD + 64;
   const int n[2] = {t->n_gen, t->n_disc};
@@ -360,6 +364,7 @@ int bgm_train_disc_grad(bgm_trainer* t, const float* z_dev, const float* v_dev, 
   A.e = t->e; A.dz = t->dz; A.zd = t->zd; A.p = t->p; A.bs = bs;
   A.theta = t->theta[0]; A.theta_d = t->theta[1]; A.grad_d = t->grad[1];
   A.z = z_dev; A.v = v_dev; A.epsilon = epsilon; A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm;
+  A.stage = t->stage_disc;
   BGM_CUDA_OK(cudaFuncSetAttribute(tr::disc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_disc));
   tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, (cudaStream_t)stream>>>(A);
   BGM_CUDA_OK(cudaGetLastError());
