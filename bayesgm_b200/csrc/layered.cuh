@@ -25,10 +25,23 @@ __device__ __forceinline__ float softplus_l(float t) { return fmaxf(t, 0.f) + lo
 __device__ __forceinline__ float sigmoid_l(float t) { return 1.f / (1.f + expf(-t)); }
 
 // dW[k][c] = (FEPS + softplus(rho[k][c])) * eps(k, c);  s_in (B,K), s_out (B,N) as +-1 int8.
+// Scalars that change from step to step, kept in device memory so that a captured CUDA graph of a step can be
+// replayed unchanged (layered_api.cuh, run_step): the noise call counter, the WGAN-GP interpolation draw and the
+// bias-corrected Adam learning rates.
+struct StepScalars {
+  uint32_t ctr;
+  float eps;
+  float lr[4];
+};
+__global__ void set_scalars_kernel(StepScalars* dst, const StepScalars v) { *dst = v; }
+
+// ctr_dev != NULL: the call id is 16 * ctr_dev[0] + call (call = the k of the step's net call).
 __global__ void flipout_noise_kernel(const float* __restrict__ rho, int K, int N, uint64_t seed, int slice, int net_id,
                                      int l, uint32_t call, int64_t row0, int B, float* __restrict__ dW,
-                                     signed char* __restrict__ s_in, signed char* __restrict__ s_out) {
+                                     signed char* __restrict__ s_in, signed char* __restrict__ s_out,
+                                     const uint32_t* __restrict__ ctr_dev) {
   using namespace bgm::bnn;
+  if (ctr_dev) call += 16u * ctr_dev[0];
   const int N4 = (N + 3) & ~3;
   const int64_t base = ((int64_t)slice << 44) | ((int64_t)net_id << 40) | ((int64_t)l << 36);
   const int gid = blockIdx.x * blockDim.x + threadIdx.x, gsz = gridDim.x * blockDim.x;
@@ -451,7 +464,9 @@ __global__ void nll_loss_kernel(const NllArgs A) {
 
 // Keras Adam (TF 2.10 optimizer_v2): m, v, theta updated in place on scale * grad.
 __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
-                            float* __restrict__ v, int n, float lr_t, float b1, float b2, float eps, float scale) {
+                            float* __restrict__ v, int n, float lr_t, float b1, float b2, float eps, float scale,
+                            const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = *lr_dev;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float g = scale * grad[i];
     const float mi = b1 * m[i] + (1.f - b1) * g;
@@ -466,7 +481,8 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
 // moments and moves; only the batch rows receive a gradient.  slot[row] = position in the batch or -1.
 __global__ void latent_adam_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
                                    const int* __restrict__ slot, const float* __restrict__ grad, long long n, int zd,
-                                   float lr_t, float b1, float b2, float eps) {
+                                   float lr_t, float b1, float b2, float eps, const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = *lr_dev;
   const long long total = n * zd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / zd;

@@ -7,7 +7,9 @@
 #pragma once
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -54,11 +56,13 @@ struct Ctx {                                    // what the generic passes need 
   float* g0;                                    // its gradient buffer
   int sm;
   uint64_t seed;
+  const uint32_t* ctr_dev = nullptr;            // device-resident call counter (graph replay), see StepScalars
 };
 
 struct Arena {
   char* base = nullptr;
   size_t cap = 0, used = 0;
+  size_t gen = 0;                               // bumped when the block moves: captured graphs hold its addresses
   bool overflow = false;
   template <class T> T* get(size_t n) {
     const size_t bytes = (n * sizeof(T) + 255) / 256 * 256;
@@ -92,6 +96,23 @@ struct bgm_lt {
   uint64_t seed = 0;
   uint32_t call_ctr = 0;
   int sm_count = 148, smem_disc = 0, wm_disc = 4, stage_disc = 0;
+  // ---- CUDA-graph replay of a step (run_step) ----
+  struct GraphEntry {
+    int fn, bs, flag;
+    const void* ptr[10];
+    long long n;
+    size_t arena_gen;
+    cudaGraphExec_t exec;
+  };
+  std::vector<GraphEntry> graphs;
+  cudaStream_t cap_stream = nullptr;       // capture only, never executes
+  bgm::lt::StepScalars* sc_dev = nullptr;  // device copy of the step's changing scalars
+  // mini-batch inputs (z, v, x, y rows or int32 row indices) are copied here and losses come back from here, so
+  // that a replayed graph always reads and writes the same addresses whatever buffers the caller passes
+  float *z_stage = nullptr, *v_stage = nullptr, *x_stage = nullptr, *y_stage = nullptr, *loss_stage = nullptr;
+  int* idx_stage = nullptr;
+  int stage_rows = 0;
+  int use_graphs = 1;                      // BGM_LT_GRAPHS=0 in the environment: plain launches
 };
 
 // BGM flavour (bgm/base.py:145-291): generator = BaseVariationalNet (input BatchNormalization in training mode +
@@ -170,6 +191,7 @@ static int ensure_arena_bytes(Arena& ar, size_t need) {
     ar.cap = 0;
     BGM_CUDA_OK(cudaMalloc(&ar.base, need));
     ar.cap = need;
+    ar.gen += 1;
   }
   ar.used = 0;
   ar.overflow = false;
@@ -180,6 +202,73 @@ static Ctx ctx_of(bgm_lt* t) { return Ctx{&t->arena, t->theta[0], t->grad[0], t-
 static int arena_ok(Arena& ar, const char* fn) {
   if (ar.overflow) return fail(BGM_ERR_NOMEM, std::string(fn) + ": workspace estimate too small (internal error)");
   BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---- CUDA-graph replay.  A layered step is 15-250 small launches whose host cost (2-4 us each) rivals their GPU
+// time at batch 32; its launch sequence depends only on (function, batch size, argument addresses), so it is
+// captured once on a private stream and replayed.  What changes from step to step -- the noise call counter, the
+// Adam bias corrections, the WGAN-GP epsilon -- lives in device memory (StepScalars, written by one 1-thread
+// kernel in front of the graph); mini-batch rows / indices that arrive at changing addresses are copied to a
+// fixed staging buffer first.  `body(stream, dev)` issues the step's launches; dev = true: read the scalars from
+// t->sc_dev.
+static inline uint32_t __float_as_uint_host(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static void drop_graphs(bgm_lt* t) {
+  for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);
+  t->graphs.clear();
+}
+static int ensure_stage(bgm_lt* t, int rows) {
+  if (rows <= t->stage_rows) return 0;
+  BGM_CUDA_OK(cudaDeviceSynchronize());
+  drop_graphs(t);
+  if (t->z_stage) cudaFree(t->z_stage);
+  if (t->idx_stage) cudaFree(t->idx_stage);
+  t->z_stage = nullptr; t->idx_stage = nullptr; t->stage_rows = 0;
+  // one block: z (rows, zd) | v (rows, p) | x (rows) | y (rows) | losses (16)
+  const size_t fl = (size_t)rows * (t->zd + t->p + 2) + 16;
+  BGM_CUDA_OK(cudaMalloc(&t->z_stage, sizeof(float) * fl));
+  BGM_CUDA_OK(cudaMalloc(&t->idx_stage, sizeof(int) * (size_t)rows));
+  t->v_stage = t->z_stage + (size_t)rows * t->zd;
+  t->x_stage = t->v_stage + (size_t)rows * t->p;
+  t->y_stage = t->x_stage + rows;
+  t->loss_stage = t->y_stage + rows;
+  t->stage_rows = rows;
+  return 0;
+}
+template <class Body>
+static int run_step(bgm_lt* t, int fn, int bs, int flag, long long n, std::initializer_list<const void*> ptrs,
+                    const StepScalars& sc, cudaStream_t st, Body body) {
+  if (!t->use_graphs) return body(st, false);
+  if (!t->sc_dev) BGM_CUDA_OK(cudaMalloc(&t->sc_dev, sizeof(StepScalars)));
+  if (!t->cap_stream) BGM_CUDA_OK(cudaStreamCreateWithFlags(&t->cap_stream, cudaStreamNonBlocking));
+  set_scalars_kernel<<<1, 1, 0, st>>>(t->sc_dev, sc);
+  bgm_lt::GraphEntry key;
+  memset(&key, 0, sizeof(key));
+  key.fn = fn; key.bs = bs; key.flag = flag; key.n = n; key.arena_gen = t->arena.gen;
+  int i = 0;
+  for (const void* q : ptrs) key.ptr[i++] = q;
+  for (auto& g : t->graphs)
+    if (g.fn == key.fn && g.bs == key.bs && g.flag == key.flag && g.n == key.n && g.arena_gen == key.arena_gen &&
+        memcmp(g.ptr, key.ptr, sizeof(key.ptr)) == 0) {
+      t->arena.used = 0;
+      BGM_CUDA_OK(cudaGraphLaunch(g.exec, st));
+      return 0;
+    }
+  if (t->graphs.size() >= 48) drop_graphs(t);
+  BGM_CUDA_OK(cudaStreamBeginCapture(t->cap_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = body(t->cap_stream, true);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(t->cap_stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(BGM_ERR_CUDA, std::string("layered step capture: ") + cudaGetErrorString(e));
+  const cudaError_t e2 = cudaGraphInstantiate(&key.exec, graph, 0ull);
+  cudaGraphDestroy(graph);
+  if (e2 != cudaSuccess) return fail(BGM_ERR_CUDA, std::string("layered step graph: ") + cudaGetErrorString(e2));
+  t->graphs.push_back(key);
+  BGM_CUDA_OK(cudaGraphLaunch(key.exec, st));
   return 0;
 }
 
@@ -220,7 +309,7 @@ static void net_fwd(const Ctx& C, const LNet& net, Pass& P, const float* X, int 
       P.sout[l] = ar.get<signed char>((size_t)B * N);
       const long long work = std::max<long long>((long long)K * N / 4, (long long)B * ((K + N + 31) / 32));
       flipout_noise_kernel<<<grid_for(work, sm), 256, 0, st>>>(th + net.off_rho[l], K, N, C.seed, 0, net.net_id, l, call,
-                                                              row0, B, P.dW[l], P.sin[l], P.sout[l]);
+                                                              row0, B, P.dW[l], P.sin[l], P.sout[l], C.ctr_dev);
     }
     P.a[l + 1] = ar.get<float>((size_t)B * N);
     P.lda[l + 1] = N;
@@ -416,6 +505,11 @@ void bgm_lt_destroy(bgm_lt* t) {
   if (t->v_it) cudaFree(t->v_it);
   if (t->scratch) cudaFree(t->scratch);
   if (t->arena.base) cudaFree(t->arena.base);
+  for (auto& g : t->graphs) cudaGraphExecDestroy(g.exec);
+  if (t->cap_stream) cudaStreamDestroy(t->cap_stream);
+  if (t->sc_dev) cudaFree(t->sc_dev);
+  if (t->z_stage) cudaFree(t->z_stage);
+  if (t->idx_stage) cudaFree(t->idx_stage);
   delete t;
 }
 
@@ -453,6 +547,10 @@ int bgm_lt_create(bgm_lt** out, const int z_dims[4], int v_dim, int binary_treat
   t->smem_disc = (2 * t->wm_disc * tr::LD + 3 * t->zd * tr::LD + tr::disc_smem_floats(t->dz, true)) * 4 + 64;
   t->stage_disc = t->smem_disc + 8 * t->dz.n_params <= 200 * 1024;     // DiscArgs.stage: parameters + gradients in shared memory
   if (t->stage_disc) t->smem_disc += 8 * t->dz.n_params;
+  {
+    const char* g = getenv("BGM_LT_GRAPHS");
+    t->use_graphs = !(g && g[0] == '0');
+  }
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, dev);
@@ -521,7 +619,7 @@ int bgm_lt_adam(bgm_lt* t, int group, float grad_scale, void* stream) {
   const float lr_t = lr_t_of(t->lr, t->b1, t->b2, t->step_pre[group]);
   lt::adam_kernel<<<grid_for(n, t->sm_count), 256, 0, (cudaStream_t)stream>>>(t->theta[group], t->grad[group], t->m_pre[group],
                                                                            t->v_pre[group], n, lr_t, (float)t->b1, (float)t->b2,
-                                                                           1e-7f, grad_scale);
+                                                                           1e-7f, grad_scale, nullptr);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -534,23 +632,46 @@ int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, 
   using namespace bgm::lt;
   if (!t || !z_dev || !v_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_lt_disc_grad: null argument");
   if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_lt_disc_grad: the gradient-penalty kernel takes batches of 2..32 rows");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st0 = (cudaStream_t)stream;
   int rc = ensure_arena(t, bs);
   if (rc) return rc;
-  const uint32_t c0 = t->call_ctr * 16u;
+  const float* zsrc = z_dev;
+  if (t->use_graphs) {
+    if ((rc = ensure_stage(t, bs))) return rc;
+    BGM_CUDA_OK(cudaMemcpyAsync(t->z_stage, z_dev, sizeof(float) * (size_t)bs * t->zd, cudaMemcpyDeviceToDevice, st0));
+    BGM_CUDA_OK(cudaMemcpyAsync(t->v_stage, v_dev, sizeof(float) * (size_t)bs * t->p, cudaMemcpyDeviceToDevice, st0));
+    zsrc = t->z_stage;
+    v_dev = t->v_stage;
+  }
+  float* const losses_out = losses_dev;
+  if (t->use_graphs) losses_dev = t->loss_stage;
+  StepScalars sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.ctr = t->call_ctr;
+  sc.eps = epsilon;
+  const uint32_t c0_host = t->call_ctr * 16u;
   t->call_ctr += 1;
-  const Ctx C = ctx_of(t);
-  Pass eA;
-  net_fwd(C, t->e, eA, v_dev, t->p, bs, c0, 0, -1, nullptr, nullptr, st);
-  tr::DiscArgs A;
-  memset(&A, 0, sizeof(A));
-  A.dz = t->dz; A.zd = t->zd; A.p = t->p; A.bs = bs;
-  A.theta = nullptr; A.theta_d = t->theta[1]; A.grad_d = t->grad[1];
-  A.z = z_dev; A.v = nullptr; A.zenc_in = eA.out();
-  A.epsilon = epsilon; A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm_disc; A.stage = t->stage_disc;
   BGM_CUDA_OK(cudaFuncSetAttribute(tr::disc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t->smem_disc));
-  tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, st>>>(A);
-  return arena_ok(t->arena, "bgm_lt_disc_grad");
+  rc = run_step(t, 1, bs, 0, 0, {(const void*)(uintptr_t)__float_as_uint_host(gp_weight)}, sc, st0, [&](cudaStream_t st, bool dev) -> int {
+    t->arena.used = 0;
+    Ctx C = ctx_of(t);
+    if (dev) C.ctr_dev = &t->sc_dev->ctr;
+    const uint32_t c0 = dev ? 0u : c0_host;
+    Pass eA;
+    net_fwd(C, t->e, eA, v_dev, t->p, bs, c0, 0, -1, nullptr, nullptr, st);
+    tr::DiscArgs A;
+    memset(&A, 0, sizeof(A));
+    A.dz = t->dz; A.zd = t->zd; A.p = t->p; A.bs = bs;
+    A.theta = nullptr; A.theta_d = t->theta[1]; A.grad_d = t->grad[1];
+    A.z = zsrc; A.v = nullptr; A.zenc_in = eA.out();
+    A.epsilon = epsilon; A.eps_dev = dev ? &t->sc_dev->eps : nullptr;
+    A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm_disc; A.stage = t->stage_disc;
+    tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, st>>>(A);
+    return arena_ok(t->arena, "bgm_lt_disc_grad");
+  });
+  if (rc == 0 && t->use_graphs)
+    BGM_CUDA_OK(cudaMemcpyAsync(losses_out, t->loss_stage, sizeof(float) * 2, cudaMemcpyDeviceToDevice, st0));
+  return rc;
 }
 
 // train_gen_step gradients (causalbgm/base.py:332-370).  Net calls and their noise ids (16*ctr + k): g(z) for v_
@@ -562,17 +683,37 @@ int bgm_lt_gen_grad(bgm_lt* t, const float* z_dev, const float* v_dev, const flo
   using namespace bgm::lt;
   if (!t || !z_dev || !v_dev || !x_dev || !y_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_lt_gen_grad: null argument");
   if (bs < 2) return fail(BGM_ERR_ARG, "bgm_lt_gen_grad: batch size must be >= 2");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st0 = (cudaStream_t)stream;
   int rc = ensure_arena(t, bs);
   if (rc) return rc;
+  const float* zsrc = z_dev;
+  if (t->use_graphs) {
+    if ((rc = ensure_stage(t, bs))) return rc;
+    BGM_CUDA_OK(cudaMemcpyAsync(t->z_stage, z_dev, sizeof(float) * (size_t)bs * t->zd, cudaMemcpyDeviceToDevice, st0));
+    BGM_CUDA_OK(cudaMemcpyAsync(t->v_stage, v_dev, sizeof(float) * (size_t)bs * t->p, cudaMemcpyDeviceToDevice, st0));
+    BGM_CUDA_OK(cudaMemcpyAsync(t->x_stage, x_dev, sizeof(float) * (size_t)bs, cudaMemcpyDeviceToDevice, st0));
+    BGM_CUDA_OK(cudaMemcpyAsync(t->y_stage, y_dev, sizeof(float) * (size_t)bs, cudaMemcpyDeviceToDevice, st0));
+    zsrc = t->z_stage;
+    v_dev = t->v_stage; x_dev = t->x_stage; y_dev = t->y_stage;
+  }
+  float* const losses_out = losses_dev;
+  if (t->use_graphs) losses_dev = t->loss_stage;
+  StepScalars sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.ctr = t->call_ctr;
+  const uint32_t c0_host = t->call_ctr * 16u;
+  t->call_ctr += 1;
+  rc = run_step(t, 2, bs, 0, 0, {}, sc, st0, [&](cudaStream_t st, bool dev) -> int {
+  t->arena.used = 0;
+  const float* z_dev = zsrc;      // the staged copy inside a replayed graph
   Arena& ar = t->arena;
   const int B = bs, p = t->p, zd = t->zd, sm = t->sm_count;
   const int d0 = t->z_dims[0], d1 = t->z_dims[1], d2 = t->z_dims[2];
   const int kf = d0 + d1 + 1, kh = d0 + d2;
-  const uint32_t c0 = t->call_ctr * 16u;
-  t->call_ctr += 1;
+  const uint32_t c0 = dev ? 0u : c0_host;
   zero(t->grad[0], t->n0, sm, st);
-  const Ctx C = ctx_of(t);
+  Ctx C = ctx_of(t);
+  if (dev) C.ctr_dev = &t->sc_dev->ctr;
   Pass gA, gB, gC, eA, eB, fA, fB, hA, hB;
   net_fwd(C, t->g, gA, z_dev, zd, B, c0 + 0, 0, -1, nullptr, nullptr, st);
   net_fwd(C, t->g, gB, z_dev, zd, B, c0 + 1, 0, -1, nullptr, nullptr, st);
@@ -617,6 +758,10 @@ int bgm_lt_gen_grad(bgm_lt* t, const float* z_dev, const float* v_dev, const flo
   net_bwd(C, t->g, gB, L.dgB, true, nullptr, 0, false, st);
   net_bwd(C, t->e, eA, dZ, true, nullptr, 0, false, st);
   return arena_ok(t->arena, "bgm_lt_gen_grad");
+  });
+  if (rc == 0 && t->use_graphs)
+    BGM_CUDA_OK(cudaMemcpyAsync(losses_out, t->loss_stage, sizeof(float) * 6, cudaMemcpyDeviceToDevice, st0));
+  return rc;
 }
 
 int bgm_lt_set_iter(bgm_lt* t, float lr_theta, float lr_z, float sigma_v, float sigma_x, float sigma_y) {
@@ -643,17 +788,37 @@ int bgm_lt_iter_nets(bgm_lt* t, const float* zt_dev, const float* x_dev, const f
   using namespace bgm::lt;
   if (!t || !zt_dev || !x_dev || !y_dev || !v_dev || !idx_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_lt_iter_nets: null argument");
   if (bs < 1) return fail(BGM_ERR_ARG, "bgm_lt_iter_nets: batch size must be >= 1");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st0 = (cudaStream_t)stream;
   const int B = bs, p = t->p, zd = t->zd, sm = t->sm_count;
   const LNet* nets[3] = {&t->g, &t->h, &t->f};
+  int rc = ensure_arena(t, bs);
+  if (rc) return rc;
+  const int* isrc = idx_dev;
+  if (t->use_graphs) {
+    if ((rc = ensure_stage(t, bs))) return rc;
+    BGM_CUDA_OK(cudaMemcpyAsync(t->idx_stage, idx_dev, sizeof(int) * (size_t)bs, cudaMemcpyDeviceToDevice, st0));
+    isrc = t->idx_stage;
+  }
+  StepScalars sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.ctr = t->call_ctr;
+  const uint32_t c0_host = t->call_ctr * 16u;
+  if (apply != 2) t->call_ctr += 1;
+  float lr_host[3] = {0.f, 0.f, 0.f};
+  if (apply != 0)
+    for (int i = 0; i < 3; ++i) {
+      t->step_it[i] += 1;
+      lr_host[i] = sc.lr[i] = lr_t_of(t->lr_theta, 0.9, 0.99, t->step_it[i]);
+    }
+  return run_step(t, 3, bs, apply, 0, {zt_dev, x_dev, y_dev, v_dev, losses_dev, (const void*)(uintptr_t)__float_as_uint_host(grad_scale)}, sc, st0,
+                  [&](cudaStream_t st, bool dev) -> int {
+  t->arena.used = 0;
+  const int* idx_dev = isrc;
   if (apply != 2) {
-    int rc = ensure_arena(t, bs);
-    if (rc) return rc;
     Arena& ar = t->arena;
     const int d0 = t->z_dims[0], d1 = t->z_dims[1], d2 = t->z_dims[2];
     const int kf = d0 + d1 + 1, kh = d0 + d2;
-    const uint32_t c0 = t->call_ctr * 16u;
-    t->call_ctr += 1;
+    const uint32_t c0 = dev ? 0u : c0_host;
     zero(t->grad[0], t->n0, sm, st);
     zero(losses_dev, 6, sm, st);
     float* zb = ar.get<float>((size_t)B * zd);
@@ -667,7 +832,8 @@ int bgm_lt_iter_nets(bgm_lt* t, const float* zt_dev, const float* x_dev, const f
     float* fin = ar.get<float>((size_t)B * kf);
     float* hin = ar.get<float>((size_t)B * std::max(kh, 1));
     build_fh_inputs(t, zb, zd, xb, B, fin, hin, st);
-    const Ctx C = ctx_of(t);
+    Ctx C = ctx_of(t);
+    if (dev) C.ctr_dev = &t->sc_dev->ctr;
     Pass gP, hP, fP;
     net_fwd(C, t->g, gP, zb, zd, B, c0, 0, -1, nullptr, nullptr, st);
     net_fwd(C, t->h, hP, hin, kh, B, c0, 0, -1, nullptr, nullptr, st);
@@ -694,21 +860,22 @@ int bgm_lt_iter_nets(bgm_lt* t, const float* zt_dev, const float* x_dev, const f
         }
       net_bwd(C, net, *passes[i], dO, true, nullptr, 0, false, st);
     }
-    rc = arena_ok(t->arena, "bgm_lt_iter_nets");
-    if (rc) return rc;
+    const int rc2 = arena_ok(t->arena, "bgm_lt_iter_nets");
+    if (rc2) return rc2;
   }
   if (apply != 0) {
     for (int i = 0; i < 3; ++i) {
       const LNet& net = *nets[i];
-      t->step_it[i] += 1;
-      const float lr_t = lr_t_of(t->lr_theta, 0.9, 0.99, t->step_it[i]);
       lt::adam_kernel<<<grid_for(net.n_params, sm), 256, 0, st>>>(t->theta[0] + net.base, t->grad[0] + net.base, t->m_it + net.base,
-                                                               t->v_it + net.base, net.n_params, lr_t, 0.9f, 0.99f, 1e-7f, grad_scale);
+                                                               t->v_it + net.base, net.n_params, lr_host[i], 0.9f, 0.99f, 1e-7f, grad_scale,
+                                                               dev ? &t->sc_dev->lr[i] : nullptr);
     }
     BGM_CUDA_OK(cudaGetLastError());
   }
   return 0;
+  });
 }
+
 
 // update_latent_variable_sgd (causalbgm/base.py:246-302): g, h, f are each called TWICE (mean and variance heads
 // come from separate calls, :259-286; noise ids 16*ctr and 16*ctr+1), gradient of loss_postrior_z w.r.t. the batch
@@ -722,15 +889,31 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   if (!t || !zt_dev || !m_dev || !v_adam_dev || !slot_dev || !x_dev || !y_dev || !v_dev || !idx_dev || !loss_dev)
     return fail(BGM_ERR_ARG, "bgm_lt_iter_latent: null argument");
   if (bs < 1 || n < bs) return fail(BGM_ERR_ARG, "bgm_lt_iter_latent: bad batch size / table size");
-  cudaStream_t st = (cudaStream_t)stream;
+  cudaStream_t st0 = (cudaStream_t)stream;
   int rc = ensure_arena(t, bs);
   if (rc) return rc;
+  const int* isrc = idx_dev;
+  if (t->use_graphs) {
+    if ((rc = ensure_stage(t, bs))) return rc;
+    BGM_CUDA_OK(cudaMemcpyAsync(t->idx_stage, idx_dev, sizeof(int) * (size_t)bs, cudaMemcpyDeviceToDevice, st0));
+    isrc = t->idx_stage;
+  }
+  StepScalars sc;
+  memset(&sc, 0, sizeof(sc));
+  sc.ctr = t->call_ctr;
+  const uint32_t c0_host = t->call_ctr * 16u;
+  t->call_ctr += 1;
+  t->step_z += 1;
+  const float lr_t = sc.lr[3] = lr_t_of(t->lr_z, 0.9, 0.99, t->step_z);
+  return run_step(t, 4, bs, 0, n, {zt_dev, m_dev, v_adam_dev, slot_dev, x_dev, y_dev, v_dev, loss_dev, gz_out_dev}, sc, st0,
+                  [&](cudaStream_t st, bool dev) -> int {
+  t->arena.used = 0;
+  const int* idx_dev = isrc;
   Arena& ar = t->arena;
   const int B = bs, p = t->p, zd = t->zd, sm = t->sm_count;
   const int d0 = t->z_dims[0], d1 = t->z_dims[1], d2 = t->z_dims[2];
   const int kf = d0 + d1 + 1, kh = d0 + d2;
-  const uint32_t c0 = t->call_ctr * 16u;
-  t->call_ctr += 1;
+  const uint32_t c0 = dev ? 0u : c0_host;
   float* losses = t->scratch;            // [0..1] v, [2..3] x, [4..5] y, [6] prior
   zero(losses, 8, sm, st);
   float* zb = ar.get<float>((size_t)B * zd);
@@ -744,7 +927,8 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   float* fin = ar.get<float>((size_t)B * kf);
   float* hin = ar.get<float>((size_t)B * std::max(kh, 1));
   build_fh_inputs(t, zb, zd, xb, B, fin, hin, st);
-  const Ctx C = ctx_of(t);
+  Ctx C = ctx_of(t);
+  if (dev) C.ctr_dev = &t->sc_dev->ctr;
   Pass gA, gB, hA, hB, fA, fB;
   net_fwd(C, t->g, gA, zb, zd, B, c0, 0, -1, nullptr, nullptr, st);
   net_fwd(C, t->g, gB, zb, zd, B, c0 + 1, 0, -1, nullptr, nullptr, st);
@@ -785,12 +969,12 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   scatter_fh_grads(t, dFin, dHin, B, dZ, st);
   sum_losses_kernel<<<1, 32, 0, st>>>(losses, loss_dev);
   if (gz_out_dev) BGM_CUDA_OK(cudaMemcpyAsync(gz_out_dev, dZ, sizeof(float) * (size_t)B * zd, cudaMemcpyDeviceToDevice, st));
-  t->step_z += 1;
-  const float lr_t = lr_t_of(t->lr_z, 0.9, 0.99, t->step_z);
   set_slots_kernel<<<grid_for(B, sm), 256, 0, st>>>(slot_dev, idx_dev, B, 1);
-  latent_adam_kernel<<<grid_for(n * zd, sm), 256, 0, st>>>(zt_dev, m_dev, v_adam_dev, slot_dev, dZ, n, zd, lr_t, 0.9f, 0.99f, 1e-7f);
+  latent_adam_kernel<<<grid_for(n * zd, sm), 256, 0, st>>>(zt_dev, m_dev, v_adam_dev, slot_dev, dZ, n, zd, lr_t, 0.9f, 0.99f, 1e-7f,
+                                                           dev ? &t->sc_dev->lr[3] : nullptr);
   set_slots_kernel<<<grid_for(B, sm), 256, 0, st>>>(slot_dev, idx_dev, B, 0);
   return arena_ok(t->arena, "bgm_lt_iter_latent");
+  });
 }
 
 // CausalBGM.evaluate (causalbgm/base.py:534-556), the part that touches every row, in row chunks: the batch
@@ -1014,7 +1198,7 @@ int bgm_ltb_adam(bgm_ltb* t, int group, float grad_scale, void* stream) {
   const float lr_t = lr_t_of(t->lr, t->b1, t->b2, t->step_pre[group]);
   lt::adam_kernel<<<grid_for(n, t->sm_count), 256, 0, (cudaStream_t)stream>>>(t->theta[group], t->grad[group], t->m_pre[group],
                                                                            t->v_pre[group], n, lr_t, (float)t->b1, (float)t->b2,
-                                                                           1e-7f, grad_scale);
+                                                                           1e-7f, grad_scale, nullptr);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -1168,7 +1352,7 @@ int bgm_ltb_iter_g(bgm_ltb* t, const float* zt_dev, const float* x_dev, const in
     t->step_g += 1;
     const float lr_t = lr_t_of(t->lr_theta, 0.9, 0.99, t->step_g);
     lt::adam_kernel<<<grid_for(t->n_g, sm), 256, 0, st>>>(t->theta[0], t->grad[0], t->m_it, t->v_it, t->n_g, lr_t, 0.9f, 0.99f, 1e-7f,
-                                                       grad_scale);
+                                                       grad_scale, nullptr);
     BGM_CUDA_OK(cudaGetLastError());
   }
   return 0;

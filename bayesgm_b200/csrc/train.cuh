@@ -67,6 +67,7 @@ struct DiscArgs {
   float* losses;             // [2]: dz_loss, d_loss
   int wm;
   const float* zenc_in;      // optional (bs, zd): z_ = e_net(v) computed elsewhere (Bayesian e_net, layered engine)
+  const float* eps_dev;      // optional: epsilon read from device memory (replayed CUDA graphs)
   int stage;                 // != 0: 2 * dz.n_params extra floats of shared memory hold the discriminator's parameters
                              // and its gradient accumulators for the whole kernel (thread = feature loops otherwise pay an
                              // L2 round trip per weight and a global read-modify-write per gradient)
@@ -708,6 +709,7 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
   extern __shared__ __align__(16) float sm[];
   const Disc& dz = A.dz;
   const int bs = A.bs;
+  const float epsilon = A.eps_dev ? *A.eps_dev : A.epsilon;
   float* bufA = sm;
   float* bufB = bufA + A.wm * LD;
   float* zmat = bufB + A.wm * LD;           // z      [zd][LD]
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(NTH, 1) disc_grad_kernel(const __grid_constant
     const int d = i >> 5, r = i & 31;
     const float zz = zmat[d * LD + r], ze_ = r < bs ? ze[d * LD + r] : 0.f;
     zenc[d * LD + r] = ze_;
-    zhat[d * LD + r] = r < bs ? zz * A.epsilon + ze_ * (1.f - A.epsilon) : 0.f;      // :311
+    zhat[d * LD + r] = r < bs ? zz * epsilon + ze_ * (1.f - epsilon) : 0.f;      // :311
   }
   __syncthreads();
   float mean_d = 0.f, mean_d_ = 0.f;

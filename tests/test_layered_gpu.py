@@ -156,6 +156,33 @@ def test_bnn_fit_runs_end_to_end_on_shipped_config():
     assert np.isfinite(adrf).all() and interval.shape == (2, 2)
 
 
+@pytest.mark.parametrize("bnn", [True, False])
+def test_graph_replay_is_bit_identical_to_plain_launches(bnn, monkeypatch):
+    """The layered steps are captured once as CUDA graphs and replayed with their changing scalars (noise call
+    counter, Adam bias corrections, WGAN-GP epsilon) in device memory: the same fit with BGM_LT_GRAPHS=0 (plain
+    launches, scalars by value) must give the same parameters and latent table, bit for bit."""
+    from bayesgm_b200 import CausalBGM
+    from bayesgm_b200.datasets import Sim_Hirano_Imbens_sampler
+    params = dict(dataset='Sim_Hirano_Imbens', output_dir='/tmp/bgm_b200_test', save_res=False, save_model=False,
+                  binary_treatment=False, use_bnn=bnn, z_dims=[1, 1, 1, 2], v_dim=40, lr_theta=0.001, lr_z=0.001,
+                  g_units=[64] * 3, f_units=[64, 32, 8], h_units=[64, 32, 8], kl_weight=0.0001, lr=0.0002, g_d_freq=5,
+                  use_z_rec=True, e_units=[64] * 3, dz_units=[64, 32, 8])
+    x, y, v = Sim_Hirano_Imbens_sampler(N=192, v_dim=40).load_all()
+    out = {}
+    for flag in ('0', '1'):
+        monkeypatch.setenv('BGM_LT_GRAPHS', flag)
+        np.random.seed(11)
+        m = CausalBGM(params=dict(params), random_seed=3)
+        if not bnn:
+            m._set_layered(True)
+        m.fit(data=(x, y, v), epochs=1, epochs_per_eval=10, use_egm_init=True, egm_n_iter=12, egm_batches_per_eval=100, verbose=0)
+        w = m.get_weights()
+        out[flag] = [a for k in ('g', 'e', 'f', 'h', 'dz') for a in w[k]] + [m.data_z]
+    assert len(out['0']) == len(out['1'])
+    for a, b in zip(out['0'], out['1']):
+        np.testing.assert_array_equal(a, b)
+
+
 # ------------------------------------------------------------------ BGM flavour (a14) ----
 from oracle import train_bgm                                   # noqa: E402
 from oracle import train                                        # noqa: E402
