@@ -34,31 +34,45 @@ def quantile_dim0(torch, a, q):
     return srt[lo] + (srt[hi] - srt[lo]) * float(pos - lo)
 
 
-def nan_coded(data, ind_x1, n, x_dim):
+def nan_coded(data, ind_x1, n, x_dim, with_extra=False):
     """The dense equivalent of tfp_mcmc_sampler's `ind_x1` forms (bgm/base.py:741-775):
-    a copy of `data` with NaN at every entry that is NOT listed as observed."""
+    a copy of `data` with NaN at every entry that is NOT listed as observed.
+
+    A feature may be listed several times for a row (legal in the reference: the gathered terms of
+    :689-700 simply add).  With `with_extra=True` the function returns (data', extra_cols): data' has one
+    more column per (feature, repeat level) that occurs, holding the value where the row lists the feature
+    at least that often and NaN elsewhere; the caller evaluates it with a generator whose heads repeat those
+    output columns (VariationalNet.with_extra_columns).  Without it duplicates raise."""
     data = np.array(data, dtype=np.float32, copy=True)
     if ind_x1 is None:
-        return data
-    obs = np.zeros((n, x_dim), dtype=bool)
+        return (data, []) if with_extra else data
+    counts = np.zeros((n, x_dim), dtype=np.int32)
     if isinstance(ind_x1, (list, tuple)) and len(ind_x1) > 0 and isinstance(ind_x1[0], (list, tuple)):
         assert len(ind_x1) == n, "len(ind_x1)=%d != n_samples=%d" % (len(ind_x1), n)
         assert max(len(r) for r in ind_x1) > 0, "No observed features"
         for i, row in enumerate(ind_x1):
-            if len(set(row)) != len(row):
-                raise NotImplementedError("bayesgm_b200: duplicate feature indices in ind_x1 are not supported")
-            obs[i, np.asarray(row, dtype=np.int64)] = True
+            np.add.at(counts[i], np.asarray(row, dtype=np.int64), 1)
     else:
         ind = np.asarray(ind_x1, dtype=np.int64)
         if ind.ndim == 1:
             ind = np.broadcast_to(ind[None, :], (n, ind.shape[0]))
         elif ind.ndim != 2:
             raise ValueError("ind_x1 must be rank 1 or 2 if tensor-like.")
-        for i in range(n):
-            if len(np.unique(ind[i])) != ind.shape[1]:
-                raise NotImplementedError("bayesgm_b200: duplicate feature indices in ind_x1 are not supported")
-        np.put_along_axis(obs, ind, True, axis=1)
-    data[~obs] = np.nan
+        np.add.at(counts, (np.repeat(np.arange(n), ind.shape[1]), ind.reshape(-1)), 1)
+    extra_cols, extra_data = [], []
+    if counts.max() > 1:
+        if not with_extra:
+            raise NotImplementedError("bayesgm_b200: duplicate feature indices in ind_x1 need the caller to pass "
+                                      "with_extra=True and an extended generator")
+        for level in range(2, int(counts.max()) + 1):
+            for j in np.nonzero((counts >= level).any(axis=0))[0]:
+                extra_cols.append(int(j))
+                extra_data.append(np.where(counts[:, j] >= level, data[:, j], np.float32(np.nan)))
+    data[counts == 0] = np.nan
+    if with_extra:
+        if extra_cols:
+            data = np.concatenate([data, np.stack(extra_data, axis=1).astype(np.float32)], axis=1)
+        return data, extra_cols
     return data
 
 
@@ -243,7 +257,20 @@ class BGM(object):
         except Exception:
             pass
 
+    def _extended_model(self, extra_cols):
+        """A throw-away device model whose heads repeat `extra_cols` (duplicate indices in ind_x1); the caller
+        destroys it with bgm_hmc_destroy."""
+        self._sync_from_trainer()
+        _lib.require_cuda()
+        d, keep = self.g_net.with_extra_columns(extra_cols).desc()
+        h = C.c_void_p()
+        _lib.call("bgm_hmc_create", C.byref(h), C.byref(d))
+        del keep
+        return h
+
     def _device_model(self):
+        if getattr(self, '_handle_override', None) is not None:
+            return self._handle_override
         self._sync_from_trainer()
         if self._handle is None:
             _lib.require_cuda()
@@ -261,10 +288,10 @@ class BGM(object):
         return dict(smem_bytes=smem.value, n_ops=nops.value, macs_per_grad=macs.value,
                     issued_macs_per_grad=issued.value)
 
-    def _stage_x(self, data, torch):
+    def _stage_x(self, data, torch, n_extra=0):
         """Host (n,x_dim) array with NaN = missing -> device (n,ldx), ldx % 4 == 0,
-        pad columns NaN (= not observed)."""
-        xd = self._p['x_dim']
+        pad columns NaN (= not observed).  n_extra: virtual columns of nan_coded(with_extra=True)."""
+        xd = self._p['x_dim'] + int(n_extra)
         if isinstance(data, torch.Tensor):
             t = data.float()
         else:
@@ -301,18 +328,24 @@ class BGM(object):
             ind = np.asarray(ind_x1, dtype=np.int64)
             msk = np.ones(ind.shape, bool) if obs_mask is None else np.asarray(obs_mask) > 0
             lists = [ind[i][msk[i]].tolist() for i in range(n)]
-            data_x = nan_coded(data_x, lists, n, xd)
-        x, ldx, n = self._stage_x(data_x, torch)
+            data_x, extra = nan_coded(data_x, lists, n, xd, with_extra=True)
+        else:
+            extra = []
+        x, ldx, n = self._stage_x(data_x, torch, len(extra))
         z = self._dev(data_z, torch, torch.float32)
         if z.shape != (n, self._p['z_dim']):
             raise ValueError("data_z must have shape (%d, %d)" % (n, self._p['z_dim']))
         lp = torch.empty(n, dtype=torch.float32, device='cuda')
         g = torch.empty((n, self._p['z_dim']), dtype=torch.float32, device='cuda') if return_grad else None
-        _lib.call("bgm_hmc_logpost_grad", self._device_model(), _lib.ptr(x), ldx, _lib.ptr(z), n, _lib.ptr(lp),
-                  _lib.ptr(g), _lib.stream_ptr())
-        if return_grad:
-            return lp.cpu().numpy(), g.cpu().numpy()
-        return lp.cpu().numpy()
+        model = self._extended_model(extra) if extra else self._device_model()
+        try:
+            _lib.call("bgm_hmc_logpost_grad", model, _lib.ptr(x), ldx, _lib.ptr(z), n, _lib.ptr(lp),
+                      _lib.ptr(g), _lib.stream_ptr())
+            res = (lp.cpu().numpy(), g.cpu().numpy()) if return_grad else lp.cpu().numpy()
+        finally:
+            if extra:
+                _lib.load().bgm_hmc_destroy(model)
+        return res
 
     def _hmc_device(self, x, ldx, n, n_mcmc, burn_in, step_size, num_leapfrog_steps, seed, row_offset=0,
                     noise=None, trace=False, group=None, n_total=None, keep_samples=True,
@@ -394,9 +427,18 @@ class BGM(object):
         torch = _lib.require_cuda()
         data = np.asarray(data, dtype=np.float32)
         n, xd = data.shape
-        x, ldx, n = self._stage_x(nan_coded(data, ind_x1, n, xd), torch)
-        r = self._hmc_device(x, ldx, n, int(n_mcmc), int(burn_in), float(step_size), int(num_leapfrog_steps),
-                             seed, noise=noise, trace=return_trace)
+        coded, extra = nan_coded(data, ind_x1, n, xd, with_extra=True)
+        x, ldx, n = self._stage_x(coded, torch, len(extra))
+        # duplicate indices: sample with a generator whose heads repeat the duplicated outputs
+        self._handle_override = self._extended_model(extra) if extra else None
+        try:
+            r = self._hmc_device(x, ldx, n, int(n_mcmc), int(burn_in), float(step_size), int(num_leapfrog_steps),
+                                 seed, noise=noise, trace=return_trace)
+            torch.cuda.synchronize()
+        finally:
+            if self._handle_override is not None:
+                _lib.load().bgm_hmc_destroy(self._handle_override)
+            self._handle_override = None
         T = int(burn_in) + int(n_mcmc)
         counts = r['accept_count'].cpu().numpy()[:T]
         self.last_acceptance_rate = float(counts[int(burn_in):].sum()) / max(1, int(n_mcmc) * n)   # :825

@@ -196,6 +196,21 @@ class VariationalNet(object):
                             C.cast(units, C.POINTER(C.c_int)), fp(bn), fp(hp), fp(mp), fp(vp))
         return d, (units, bn, hp, mp, vp)
 
+    def with_extra_columns(self, cols):
+        """A copy whose mean / variance heads carry, after the x_dim real outputs, one more output per entry of
+        `cols` (a copy of that output's head column): a feature listed m times in `ind_x1` is observed through
+        m identical outputs, which adds its likelihood term m times like the gather of bgm/base.py:689-700."""
+        cols = np.asarray(cols, dtype=np.int64)
+        out = VariationalNet.__new__(VariationalNet)
+        out.input_dim, out.output_dim = self.input_dim, self.output_dim + len(cols)
+        out.model_name, out.nb_units = self.model_name, list(self.nb_units)
+        out.bn = {k: v.copy() for k, v in self.bn.items()}
+        out.hidden = [[W.copy(), b.copy()] for W, b in self.hidden]
+        ext = lambda layer: [np.concatenate([layer[0], layer[0][:, cols]], axis=1).astype(np.float32),
+                             np.concatenate([layer[1], layer[1][cols]]).astype(np.float32)]
+        out.mean, out.var = ext(self.mean), ext(self.var)
+        return out
+
     def as_oracle_params(self):
         return dict(bn=dict(self.bn), hidden=[(W, b) for W, b in self.hidden],
                     mean=(self.mean[0], self.mean[1]), var=(self.var[0], self.var[1]))

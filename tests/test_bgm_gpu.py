@@ -113,6 +113,33 @@ def test_hmc_index_list_form_equals_nan_form():
     np.testing.assert_array_equal(c, d)
 
 
+def test_duplicate_indices_in_ind_x1_add_like_the_reference_gather():
+    """bgm/base.py:689-700 gathers (x, mu, sigma^2) at ind_x1 and sums: a feature listed m times counts m times."""
+    params, p, x, w, xn = make_case(41, 12, 3, (32, 32), 0.0)
+    m = bgm_product_model(params, p)
+    rs = np.random.RandomState(4)
+    z = rs.standard_normal((41, 3)).astype(np.float32)
+    lists = [rs.randint(0, 12, size=rs.randint(1, 9)).tolist() for _ in range(41)]     # with repeats, ragged
+    assert any(len(set(r)) < len(r) for r in lists)
+    ind, mask = bgm.pad_index_lists(lists, 41)
+    want = bgm.log_posterior(p, z, x, ind, mask)
+    got, g = m.get_log_posterior(z, x, ind, mask, return_grad=True)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3)
+    # weights = multiplicities in the oracle's dense gradient form
+    cnt = np.zeros((41, 12), np.float32)
+    for i, r in enumerate(lists):
+        np.add.at(cnt[i], r, 1)
+    wl, wg = bgm.log_posterior_and_grad(p, z, x, cnt)
+    np.testing.assert_allclose(got, wl, rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(g, wg, rtol=2e-4, atol=2e-4 * max(1.0, np.abs(wg).max()))
+    # the sampler accepts the same lists; a fixed (K,) list with a repeat too
+    a = m.tfp_mcmc_sampler(x, ind_x1=lists, n_mcmc=3, burn_in=4, seed=3, verbose=0)
+    assert a.shape == (3, 41, 3) and np.isfinite(a).all()
+    b = m.tfp_mcmc_sampler(x, ind_x1=[0, 3, 3, 7], n_mcmc=3, burn_in=4, seed=3, verbose=0)
+    c = m.tfp_mcmc_sampler(x, ind_x1=[0, 3, 7], n_mcmc=3, burn_in=4, seed=3, verbose=0)
+    assert np.isfinite(b).all() and not np.array_equal(b, c)
+
+
 def test_hmc_philox_run_replayed_through_oracle():
     params, p, x, w, xn = make_case(200, 10, 3, (64,) * 5, 0.0)
     m = bgm_product_model(params, p)
