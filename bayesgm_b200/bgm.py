@@ -526,9 +526,10 @@ class BGM(object):
             print(f"TFP MCMC Acceptance Rate: {self.last_acceptance_rate:.4f}")
         zs = r['samples']
         return self._predictive_reduce(zs, data_np, miss, n, xd, int(n_mcmc), alpha, return_samples, bs, seed,
-                                       row_offset)
+                                       row_offset, x_dev=x[:, :xd])
 
-    def _predictive_reduce(self, zs, data_np, miss, n, xd, n_mcmc, alpha, return_samples, bs, seed, row_offset):
+    def _predictive_reduce(self, zs, data_np, miss, n, xd, n_mcmc, alpha, return_samples, bs, seed, row_offset,
+                           x_dev=None):
         """bgm/base.py:603-663 on the device: posterior-predictive draws for every kept state, their mean
         (imputation) and the alpha/2, 1-alpha/2 quantiles of the missing entries.  The reference loops over
         `bs`-row slices on the host and concatenates (n_mcmc, n, x_dim) draws; here the rows are processed in
@@ -564,27 +565,42 @@ class BGM(object):
             draws = self._predict_device(zb, n_mcmc, j - i, seed, row_offset=row_offset + i)
             if return_samples:
                 all_draws.append(draws.cpu().numpy())
-            imputed_d[i:j] = draws.mean(dim=0)                                     # :660
-            if k_cols:
+            # one pass over the draws: thread = (row, feature) column keeps the few smallest / largest values
+            # (bgm_column_quantiles); a quantile deep inside the sample (> 16 order statistics from an end, e.g.
+            # n_mcmc = 3000 at alpha = 0.05) falls back to a device sort
+            M = (j - i) * xd
+            mean_c = imputed_d[i:j]
+            lo_c = torch.empty((j - i, xd), dtype=torch.float32, device='cuda') if k_cols else None
+            up_c = torch.empty((j - i, xd), dtype=torch.float32, device='cuda') if k_cols else None
+            deep = k_cols and max(int(np.floor(q_lo * (n_mcmc - 1))) + 2, n_mcmc - int(np.floor(q_hi * (n_mcmc - 1)))) > 16
+            if deep:
+                imputed_d[i:j] = draws.mean(dim=0)                                 # :660
                 part = draws[:, :, midx_d] if same_pattern else draws
                 lo_d[i:j], up_d[i:j] = q_pair(torch.sort(part, dim=0).values)
+            else:
+                _lib.call("bgm_column_quantiles", _lib.ptr(draws), int(n_mcmc), int(M), float(q_lo), float(q_hi),
+                          _lib.ptr(mean_c), _lib.ptr(lo_c), _lib.ptr(up_c), _lib.stream_ptr())
+                if k_cols:
+                    lo_d[i:j] = lo_c[:, midx_d] if same_pattern else lo_c
+                    up_d[i:j] = up_c[:, midx_d] if same_pattern else up_c
             del draws
-        imputed = imputed_d.cpu().numpy()
-        lo, up = lo_d.cpu().numpy(), up_d.cpu().numpy()
+        if return_samples:
+            draws_np = np.concatenate(all_draws, axis=1)
+        # the rest stays on the device too: observed entries are put back (:662) and, for a ragged missing
+        # pattern, the interval bounds of the missing entries are compacted before the one copy to the host
+        if x_dev is None:
+            x_dev = torch.from_numpy(np.ascontiguousarray(data_np)).cuda()
+        miss_d = torch.isnan(x_dev)
         if same_pattern:
+            lo, up = lo_d.cpu().numpy(), up_d.cpu().numpy()
             pred_interval = np.stack([lo, up], axis=-1) if k_cols else np.zeros((n, 0, 2), dtype=np.float32)
         else:
-            pred_interval = []
-            for i in range(n):                                                     # :637-649
-                idx = np.where(miss[i])[0]
-                if idx.size == 0:
-                    pred_interval.append(np.zeros((0, 2), dtype=np.float32))
-                else:
-                    pred_interval.append(np.stack([lo[i, idx], up[i, idx]], axis=-1))
+            # :637-649, one (k_i, 2) array per row -- cut from the row-major list of all missing entries
+            pairs = torch.stack([lo_d[miss_d], up_d[miss_d]], dim=-1).cpu().numpy()
+            pred_interval = np.split(pairs, np.cumsum(miss.sum(axis=1))[:-1])
         if return_samples:
-            return np.concatenate(all_draws, axis=1), pred_interval
-        obs_mask = 1.0 - miss.astype(np.float32)
-        data_imputed = miss.astype(np.float32) * imputed + obs_mask * np.nan_to_num(data_np, nan=0.0)  # :662
+            return draws_np, pred_interval
+        data_imputed = torch.where(miss_d, imputed_d, x_dev).cpu().numpy()                        # :662
         return data_imputed, pred_interval
 
     # ------------------------------------------------------------ training: fit

@@ -74,6 +74,61 @@ static int hmc_launch(const bgm_hmc* m, const HmcProgram& P, HmcDev& D, int n_ro
 
 }  // namespace bgm
 
+namespace bgm {
+struct ColQ {
+  const float* draws;
+  int S;
+  long long M;
+  float *mean, *lo, *hi;
+  int lo_idx, hi_idx;
+  float lo_frac, hi_frac;
+};
+template <int K>
+__global__ void __launch_bounds__(128) column_quantiles_kernel(const ColQ Q) {
+  for (long long m = blockIdx.x * 128ll + threadIdx.x; m < Q.M; m += (long long)gridDim.x * 128ll) {
+    float small[K], large[K];     // ascending: small[0] is the minimum; large[0] is the maximum (descending)
+#pragma unroll
+    for (int k = 0; k < K; ++k) { small[k] = __int_as_float(0x7f800000); large[k] = __int_as_float(0xff800000); }
+    float sum = 0.f;
+    for (int s = 0; s < Q.S; ++s) {
+      float v = __ldg(Q.draws + (size_t)s * Q.M + m);
+      sum += v;
+      if (Q.lo) {
+        if (v < small[K - 1]) {
+          float c = v;
+#pragma unroll
+          for (int k = 0; k < K; ++k) { const float a = small[k]; small[k] = fminf(a, c); c = fmaxf(a, c); }
+        }
+        if (v > large[K - 1]) {
+          float c = v;
+#pragma unroll
+          for (int k = 0; k < K; ++k) { const float a = large[k]; large[k] = fmaxf(a, c); c = fminf(a, c); }
+        }
+      }
+    }
+    Q.mean[m] = sum / (float)Q.S;
+    if (Q.lo) {
+      auto ord = [&](int idx) -> float {          // idx-th order statistic (0 = minimum), taken from the nearer end
+        float r = 0.f;
+        if (idx < K && idx < Q.S) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) if (k == idx) r = small[k];
+        } else {
+          const int t = Q.S - 1 - idx;
+#pragma unroll
+          for (int k = 0; k < K; ++k) if (k == t) r = large[k];
+        }
+        return r;
+      };
+      const float a = ord(Q.lo_idx), b = ord(min(Q.lo_idx + 1, Q.S - 1));
+      Q.lo[m] = a + (b - a) * Q.lo_frac;
+      const float c = ord(Q.hi_idx), d = ord(min(Q.hi_idx + 1, Q.S - 1));
+      Q.hi[m] = c + (d - c) * Q.hi_frac;
+    }
+  }
+}
+}  // namespace bgm
+
 extern "C" {
 
 int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
@@ -322,6 +377,34 @@ int bgm_hmc_heads(const bgm_hmc* m, const float* z_dev, int n, float* out_mu_dev
   D.out_var = out_var_dev;
   D.n_per_sample = n;
   return hmc_launch(m, m->prog_fwd, D, n, (cudaStream_t)stream);
+}
+
+// Posterior-predictive reduction of BGM.predict (bgm/base.py:640-660): for every column m of draws (S, M) the mean
+// over the S kept states and np.quantile(., q) at two levels (linear interpolation between the order statistics
+// lo = floor(q (S - 1)) and lo + 1, the same fp32 formula as a sort would feed).  Thread = column: one pass over
+// the draws (coalesced across columns) keeping the K smallest and K largest values in sorted register arrays,
+// instead of sorting S x M values.  K = order statistics needed from either end (<= 16).
+int bgm_column_quantiles(const float* draws_dev, int S, long long M, double q_lo, double q_hi, float* mean_dev,
+                         float* lo_dev, float* hi_dev, void* stream) {
+  using namespace bgm;
+  if (!draws_dev || !mean_dev || S < 1 || M < 1) return fail(BGM_ERR_ARG, "bgm_column_quantiles: bad argument");
+  if (!(q_lo >= 0.0 && q_lo <= 1.0 && q_hi >= 0.0 && q_hi <= 1.0)) return fail(BGM_ERR_ARG, "bgm_column_quantiles: q outside [0, 1]");
+  ColQ Q;
+  Q.draws = draws_dev; Q.S = S; Q.M = M; Q.mean = mean_dev; Q.lo = lo_dev; Q.hi = hi_dev;
+  const double pl = q_lo * (S - 1), ph = q_hi * (S - 1);
+  Q.lo_idx = (int)std::floor(pl); Q.lo_frac = (float)(pl - Q.lo_idx);
+  Q.hi_idx = (int)std::floor(ph); Q.hi_frac = (float)(ph - Q.hi_idx);
+  const int need_lo = std::min(Q.lo_idx + 2, S);                 // smallest values needed
+  const int need_hi = std::min(S - Q.hi_idx, S);                 // largest values needed (index hi_idx and hi_idx + 1)
+  const int K = (lo_dev && hi_dev) ? std::max(need_lo, need_hi) : 1;
+  const unsigned grid = (unsigned)std::min<long long>((M + 127) / 128, 1 << 20);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (K <= 4) column_quantiles_kernel<4><<<grid, 128, 0, st>>>(Q);
+  else if (K <= 8) column_quantiles_kernel<8><<<grid, 128, 0, st>>>(Q);
+  else if (K <= 16) column_quantiles_kernel<16><<<grid, 128, 0, st>>>(Q);
+  else return fail(BGM_ERR_UNSUPPORTED, "bgm_column_quantiles: more than 16 order statistics from one end; sort instead");
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

@@ -548,7 +548,8 @@ def run_cfg5(args):
                          "rows_per_gpu": n, "collectives_per_step": 0 if D.world == 1 else int(0.8 * burn_in),
                          "collective": "NCCL all-reduce of ONE float64 (sum of accept probabilities) per adaptation step"},
               "e2e": {"value": n * T * D.world * args.steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": int(4 * n * 500),
-                      "d2h_bytes_per_step": int(4 * n * 500 * 3), "api": "BGM.predict(data_with_NaN, bs=1000, group=WORLD)",
+                      "d2h_bytes_per_step": int(4 * n * 500 + 8 * int(np.isnan(data).sum())),     # imputed matrix + (lower, upper) of every missing entry
+                      "api": "BGM.predict(data_with_NaN, bs=1000, group=WORLD)",
                       "ms_per_step": 1e3 * e2e_wall / args.steps},
               "gpu_launches": int((0.8 * burn_in * 2 + 1) * args.steps),
               "kernel": {"name": "hmc_kernel", "ms_per_launch_set": kern_ms, "smem_bytes": info['smem_bytes']},

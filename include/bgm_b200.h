@@ -367,6 +367,14 @@ int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, in
                     uint64_t seed, int64_t row_offset, const float* noise_dev, float* out_x_dev,
                     void* stream);
 
+/* Reduction of the posterior-predictive draws in BGM.predict (bgm/base.py:640-660): per column of
+ * draws_dev (S, M) the mean over S and np.quantile at q_lo / q_hi (linear interpolation), in one
+ * pass (thread = column keeps the few smallest / largest values in registers).  lo_dev / hi_dev may
+ * both be NULL (mean only).  BGM_ERR_UNSUPPORTED when a quantile needs more than 16 order statistics
+ * from one end of the sample (the caller sorts instead). */
+int bgm_column_quantiles(const float* draws_dev, int S, long long M, double q_lo, double q_hi,
+                         float* mean_dev, float* lo_dev, float* hi_dev, void* stream);
+
 /* The generator's heads (bgm/base.py:483-509 `generate`, networks/base.py:98-111): mu(z) and
  * sigma^2(z) = softplus(raw) + 1e-6 for z_dev (n, z_dim) -> out_mu_dev, out_var_dev (n, x_dim). */
 int bgm_hmc_heads(const bgm_hmc* m, const float* z_dev, int n, float* out_mu_dev, float* out_var_dev,

@@ -207,6 +207,38 @@ def test_predict_imputation_shapes_and_semantics():
         m.predict(x, alpha=0.0, verbose=0)
 
 
+@pytest.mark.parametrize("S,alpha", [(1, 0.5), (2, 0.1), (25, 0.2), (100, 0.05), (100, 0.1), (200, 0.1), (333, 0.05), (7, 1.0)])
+def test_column_quantiles_kernel_against_numpy(S, alpha):
+    """bgm_column_quantiles (mean and np.quantile at alpha/2, 1 - alpha/2 of every column in one pass)."""
+    import torch
+    from bayesgm_b200 import _lib
+    rs = np.random.RandomState(S)
+    M = 1000 + S
+    draws = rs.standard_normal((S, M)).astype(np.float32)
+    draws[:, :7] = np.round(draws[:, :7])                     # ties
+    d = torch.from_numpy(draws).cuda()
+    mean = torch.empty(M, dtype=torch.float32, device='cuda')
+    lo, hi = torch.empty_like(mean), torch.empty_like(mean)
+    _lib.call("bgm_column_quantiles", _lib.ptr(d), S, M, alpha / 2, 1 - alpha / 2, _lib.ptr(mean), _lib.ptr(lo), _lib.ptr(hi),
+              _lib.stream_ptr())
+    np.testing.assert_allclose(mean.cpu().numpy(), draws.mean(axis=0), rtol=1e-5, atol=1e-6)
+    d64 = draws.astype(np.float64)     # (np.quantile on float32 input interpolates in float32 and is off by up to ~5e-6)
+    np.testing.assert_allclose(lo.cpu().numpy(), np.quantile(d64, alpha / 2, axis=0), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(hi.cpu().numpy(), np.quantile(d64, 1 - alpha / 2, axis=0), rtol=1e-6, atol=1e-6)
+    if S == 333:      # 16 + order statistics from an end: the entry point refuses, BGM.predict sorts instead
+        with pytest.raises(_lib.BgmError):
+            _lib.call("bgm_column_quantiles", _lib.ptr(d), S, M, 0.2, 0.8, _lib.ptr(mean), _lib.ptr(lo), _lib.ptr(hi), _lib.stream_ptr())
+
+
+def test_imputation_deep_quantiles_fall_back_to_the_sort():
+    params, p, x, w, xn = make_case(30, 9, 2, (16,), 0.3)
+    m = bgm_product_model(params, p)
+    smp, iv = m.predict(xn, alpha=0.5, return_samples=True, bs=16, n_mcmc=120, burn_in=8, seed=4, verbose=0)
+    want_imp, want_iv = bgm.impute_from_samples(xn, smp, 0.5)
+    for a, b in zip(iv, want_iv):
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-4)
+
+
 def test_imputation_matches_oracle_reduction():
     """predict()'s device-side reductions equal the oracle's host reductions on the same draws."""
     params, p, x, w, xn = make_case(40, 9, 2, (16,), 0.3)
