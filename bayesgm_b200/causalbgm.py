@@ -41,6 +41,25 @@ def _quantile_dim0(torch, a, q):
     return srt[lo] + (srt[hi] - srt[lo]) * frac
 
 
+def _ite_summary(torch, eff, alpha):
+    """causalbgm/base.py:640-642 on the device: mean and the alpha/2, 1 - alpha/2 quantiles over the kept states of
+    the per-subject draws eff (n_keep, n) -> three (n,) NumPy arrays.  One pass (bgm_column_quantiles: thread =
+    subject, the few smallest / largest draws in registers); a device sort only when a quantile sits more than 16
+    order statistics from an end of the sample."""
+    S, n = eff.shape
+    q_lo, q_hi = alpha / 2.0, 1.0 - alpha / 2.0
+    need = max(int(np.floor(q_lo * (S - 1))) + 2, S - int(np.floor(q_hi * (S - 1))))
+    if need > 16:
+        return (eff.mean(dim=0).cpu().numpy(), _quantile_dim0(torch, eff, q_lo).cpu().numpy(),
+                _quantile_dim0(torch, eff, q_hi).cpu().numpy())
+    eff = eff.contiguous()
+    out = torch.empty((3, n), dtype=torch.float32, device='cuda')
+    _lib.call("bgm_column_quantiles", _lib.ptr(eff), int(S), int(n), float(q_lo), float(q_hi), _lib.ptr(out[0]), _lib.ptr(out[1]),
+              _lib.ptr(out[2]), _lib.stream_ptr())
+    h = out.cpu().numpy()
+    return h[0], h[1], h[2]
+
+
 class CausalBGM(object):
     """See the reference docstring, causalbgm/base.py:12-54, for `params`."""
 
@@ -631,9 +650,7 @@ class CausalBGM(object):
             w_ = min(100, T_)
             acc_tail.append((r['accept_count'][T_ - w_:].sum(), w_ * n))                # :901, read back once below
             if binary:                                                            # :640-642
-                ite_mean[start:end] = eff.mean(dim=0).cpu().numpy()
-                lower[start:end] = _quantile_dim0(torch, eff, alpha / 2).cpu().numpy()
-                upper[start:end] = _quantile_dim0(torch, eff, 1 - alpha / 2).cpu().numpy()
+                ite_mean[start:end], lower[start:end], upper[start:end] = _ite_summary(torch, eff, alpha)
             else:                                                                 # :660-661
                 sums += eff
                 n_seen += n
