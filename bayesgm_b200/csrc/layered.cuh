@@ -477,25 +477,7 @@ __global__ void adam_kernel(float* __restrict__ theta, const float* __restrict__
   }
 }
 
-// Keras Adam on a GATHERED variable = dense sweep over the whole latent table: every row decays its
-// moments and moves; only the batch rows receive a gradient.  slot[row] = position in the batch or -1.
-__global__ void latent_adam_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
-                                   const int* __restrict__ slot, const float* __restrict__ grad, long long n, int zd,
-                                   float lr_t, float b1, float b2, float eps, const float* __restrict__ lr_dev) {
-  if (lr_dev) lr_t = *lr_dev;
-  const long long total = n * zd;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / zd;
-    const int d = (int)(i - r * zd);
-    const int s = slot[r];
-    const float g = s >= 0 ? grad[(size_t)s * zd + d] : 0.f;
-    const float mi = b1 * m[i] + (1.f - b1) * g;
-    const float vi = b2 * v[i] + (1.f - b2) * g * g;
-    m[i] = mi;
-    v[i] = vi;
-    z[i] -= lr_t * mi / (sqrtf(vi) + eps);
-  }
-}
+// (the dense Keras-Adam sweep over the latent table is tr::latent_adam_sweep_kernel, train.cuh)
 __global__ void set_slots_kernel(int* __restrict__ slot, const int* __restrict__ idx, int B, int value_is_pos) {
   for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) slot[idx[b]] = value_is_pos ? b : -1;
 }

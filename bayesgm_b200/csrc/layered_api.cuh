@@ -970,8 +970,8 @@ int bgm_lt_iter_latent(bgm_lt* t, float* zt_dev, float* m_dev, float* v_adam_dev
   sum_losses_kernel<<<1, 32, 0, st>>>(losses, loss_dev);
   if (gz_out_dev) BGM_CUDA_OK(cudaMemcpyAsync(gz_out_dev, dZ, sizeof(float) * (size_t)B * zd, cudaMemcpyDeviceToDevice, st));
   set_slots_kernel<<<grid_for(B, sm), 256, 0, st>>>(slot_dev, idx_dev, B, 1);
-  latent_adam_kernel<<<grid_for(n * zd, sm), 256, 0, st>>>(zt_dev, m_dev, v_adam_dev, slot_dev, dZ, n, zd, lr_t, 0.9f, 0.99f, 1e-7f,
-                                                           dev ? &t->sc_dev->lr[3] : nullptr);
+  tr::launch_latent_adam_sweep(zt_dev, m_dev, v_adam_dev, slot_dev, dZ, n, zd, lr_t, 0.9f, 0.99f, 1e-7f,
+                               dev ? &t->sc_dev->lr[3] : nullptr, sm, st);
   set_slots_kernel<<<grid_for(B, sm), 256, 0, st>>>(slot_dev, idx_dev, B, 0);
   return arena_ok(t->arena, "bgm_lt_iter_latent");
   });

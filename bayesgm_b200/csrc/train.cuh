@@ -1222,25 +1222,79 @@ __global__ void latent_mark_kernel(const int* __restrict__ idx, int bs, int* __r
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r < bs) slot[idx[r]] = r;
 }
-__global__ void latent_adam_sweep_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
-                                         int* __restrict__ slot, const float* __restrict__ gz, long long n, int zd,
-                                         float lr_t, float b1, float b2, float eps) {
+// The one HBM-bound kernel of the path: 6 floats of traffic per table element (z, m, v read and written) plus the
+// row's slot.  Thread = 4 consecutive elements of the flat (n * zd) arrays (16-byte loads / stores); a quad lies in
+// one or two rows (up to four when zd < 4) and almost never in a batch row, so the rows' slots are tested first and
+// the gradient gather (with its per-element division) only runs for the bs quads that need it.  lr_dev: optional
+// device-resident learning rate (replayed CUDA graphs).
+template <typename IndexT>
+__global__ void __launch_bounds__(256) latent_adam_sweep_kernel(float* __restrict__ z, float* __restrict__ m, float* __restrict__ v,
+                                                                const int* __restrict__ slot, const float* __restrict__ gz,
+                                                                long long n, int zd, float lr_t, float b1, float b2, float eps,
+                                                                const float* __restrict__ lr_dev) {
+  if (lr_dev) lr_t = *lr_dev;
   const long long total = n * zd;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const long long nq = total >> 2;
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (long long q = blockIdx.x * 256ll + threadIdx.x; q < nq; q += (long long)gridDim.x * 256ll) {
+    const long long i = q << 2;
+    // the three streams first: the slot test must not sit between their issue and their use
+    const float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i),
+                 z4 = *reinterpret_cast<const float4*>(z + i);
+    const IndexT r0 = (IndexT)i / (IndexT)zd, r3 = (IndexT)(i + 3) / (IndexT)zd;
+    int smax = __ldg(slot + r0);
+    if (r3 != r0) {
+      smax = max(smax, __ldg(slot + r3));
+      for (IndexT r = r0 + 1; r < r3; ++r) smax = max(smax, __ldg(slot + r));
+    }
+    const bool hit = smax >= 0;
+    float mm[4] = {m4.x * b1, m4.y * b1, m4.z * b1, m4.w * b1};
+    float vv[4] = {v4.x * b2, v4.y * b2, v4.z * b2, v4.w * b2};
+    float zz[4] = {z4.x, z4.y, z4.z, z4.w};
+    if (hit) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const IndexT row = (IndexT)(i + e) / (IndexT)zd;
+        const int sl = slot[row];
+        if (sl >= 0) {
+          const float g = gz[(size_t)sl * zd + (int)((i + e) - (long long)row * zd)];
+          mm[e] += c1 * g;
+          vv[e] += c2 * g * g;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) zz[e] -= lr_t * mm[e] / (sqrtf(vv[e]) + eps);
+    *reinterpret_cast<float4*>(m + i) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(z + i) = make_float4(zz[0], zz[1], zz[2], zz[3]);
+  }
+  // tail (total not a multiple of 4)
+  if (blockIdx.x == 0 && threadIdx.x < (total & 3)) {
+    const long long i = (nq << 2) + threadIdx.x;
     const long long row = i / zd;
-    const int d = (int)(i - row * zd);
-    const int s = slot[row];
+    const int sl = slot[row];
     float mi = m[i] * b1, vi = v[i] * b2;
-    if (s >= 0) {
-      const float g = gz[(size_t)s * zd + d];
-      mi += (1.f - b1) * g;
-      vi += (1.f - b2) * g * g;
+    if (sl >= 0) {
+      const float g = gz[(size_t)sl * zd + (int)(i - row * zd)];
+      mi += c1 * g;
+      vi += c2 * g * g;
     }
     m[i] = mi;
     v[i] = vi;
     z[i] -= lr_t * mi / (sqrtf(vi) + eps);
   }
+}
+// launch helper shared by the fused and the layered trainers
+static inline void launch_latent_adam_sweep(float* z, float* m, float* v, const int* slot, const float* gz, long long n, int zd,
+                                            float lr_t, float b1, float b2, float eps, const float* lr_dev, int sm_count,
+                                            cudaStream_t st) {
+  const long long nq = (n * zd) >> 2;
+  const int grid = (int)std::max<long long>(1, std::min<long long>((nq + 255) / 256, (long long)sm_count * 16));
+  if (n * zd < (1ll << 31))
+    latent_adam_sweep_kernel<unsigned int><<<grid, 256, 0, st>>>(z, m, v, slot, gz, n, zd, lr_t, b1, b2, eps, lr_dev);
+  else
+    latent_adam_sweep_kernel<long long><<<grid, 256, 0, st>>>(z, m, v, slot, gz, n, zd, lr_t, b1, b2, eps, lr_dev);
 }
 __global__ void latent_unmark_kernel(const int* __restrict__ idx, int bs, int* __restrict__ slot) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;

@@ -501,10 +501,7 @@ int bgm_train_iter_latent(bgm_trainer* t, float* zt_dev, float* m_dev, float* v_
   const double k = (double)t->step_z;
   const float lr_t = (float)(t->lr_z * std::sqrt(1.0 - std::pow(0.99, k)) / (1.0 - std::pow(0.9, k)));
   tr::latent_mark_kernel<<<1, 32, 0, st>>>(idx_dev, bs, slot_dev);
-  const long long total = n * t->zd;
-  const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)t->sm_count * 8));
-  tr::latent_adam_sweep_kernel<<<grid, 256, 0, st>>>(zt_dev, m_dev, v_dev_adam, slot_dev, t->gz, n, t->zd, lr_t, 0.9f,
-                                                     0.99f, 1e-7f);
+  tr::launch_latent_adam_sweep(zt_dev, m_dev, v_dev_adam, slot_dev, t->gz, n, t->zd, lr_t, 0.9f, 0.99f, 1e-7f, nullptr, t->sm_count, st);
   tr::latent_unmark_kernel<<<1, 32, 0, st>>>(idx_dev, bs, slot_dev);
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
