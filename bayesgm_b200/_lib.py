@@ -222,6 +222,9 @@ SYMBOLS = {
     "bgm_host_rand": (C.c_int, [C.POINTER(MtState), C.c_longlong, C.c_void_p]),
     "bgm_host_egm_stream": (C.c_int, [C.POINTER(MtState), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p, C.c_void_p]),
+    "bgm_hmc_set_engine": (C.c_int, [C.c_void_p, C.c_int]),
+    "bgm_hmc_engine_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                      C.POINTER(C.c_longlong)]),
     "bgm_column_quantiles": (C.c_int, [C.c_void_p, C.c_int, C.c_longlong, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "bgm_hmc_heads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

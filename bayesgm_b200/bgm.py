@@ -266,6 +266,8 @@ class BGM(object):
         h = C.c_void_p()
         _lib.call("bgm_hmc_create", C.byref(h), C.byref(d))
         del keep
+        if getattr(self, 'hmc_engine', 'auto') == 'simt':
+            _lib.call("bgm_hmc_set_engine", h, 1)
         return h
 
     def _device_model(self):
@@ -278,7 +280,26 @@ class BGM(object):
             h = C.c_void_p()
             _lib.call("bgm_hmc_create", C.byref(h), C.byref(d))
             self._handle = h
+            kind = {'auto': 0, 'simt': 1, 'tensor': 2}[getattr(self, 'hmc_engine', 'auto')]
+            if kind:
+                _lib.call("bgm_hmc_set_engine", h, kind)
         return self._handle
+
+    def set_hmc_engine(self, engine='auto'):
+        """'auto' (tensor-core engine when every hidden layer of g_net is 64 wide), 'simt' or 'tensor' (raises if
+        unavailable).  Both run the same algorithm on the same Philox streams; DESIGN.md 4.3 / 4.3b."""
+        if engine not in ('auto', 'simt', 'tensor'):
+            raise ValueError("engine must be 'auto', 'simt' or 'tensor'")
+        self.hmc_engine = engine
+        if self._handle is not None:
+            _lib.call("bgm_hmc_set_engine", self._handle, {'auto': 0, 'simt': 1, 'tensor': 2}[engine])
+
+    def hmc_engine_info(self):
+        kind, avail, smem = C.c_int(), C.c_int(), C.c_int()
+        issued = C.c_longlong()
+        _lib.call("bgm_hmc_engine_info", self._device_model(), C.byref(kind), C.byref(avail), C.byref(smem), C.byref(issued))
+        return dict(engine={1: 'simt', 2: 'tensor'}[kind.value], tensor_available=bool(avail.value),
+                    tensor_smem_bytes=smem.value, tensor_issued_macs_per_grad=issued.value)
 
     def kernel_info(self):
         smem, nops = C.c_int(), C.c_int()

@@ -3,10 +3,12 @@
 // Included by bgm_b200.cu.
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "hmc.cuh"
+#include "hmc_tc.cuh"
 
 struct bgm_hmc {
   bgm::HmcProgram prog;      // forward + backward (one gradient evaluation)
@@ -15,6 +17,12 @@ struct bgm_hmc {
   int sm_count = 0;
   int smem_max = 0;
   long long macs = 0, issued = 0;
+  // tensor-core engine (hmc_tc.cuh): pre-split operand images of one evaluation + the resident small arrays
+  bgm::HmcTcProgram tc;
+  float* tc_stream_dev = nullptr;
+  float* tc_small_dev = nullptr;
+  long long tc_issued = 0;
+  int engine = 0;            // 0 auto (tensor when available), 1 SIMT, 2 tensor
 };
 
 namespace bgm {
@@ -68,6 +76,53 @@ static int hmc_launch(const bgm_hmc* m, const HmcProgram& P, HmcDev& D, int n_ro
   const int grid = std::max(1, std::min(nblocks, m->sm_count));
   BGM_CUDA_OK(cudaFuncSetAttribute(hmc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, m->smem_max - HMC_SMEM_RESERVE));
   hmc_kernel<<<grid, ncons * 32, smem, st>>>(P, m->image_dev, D);
+  BGM_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace bgm
+
+namespace bgm {
+
+// host twin of umma::split_tf32
+static inline void ht_split_host(float v, float& hi, float& lo) {
+  uint32_t b;
+  memcpy(&b, &v, 4);
+  b = (b + 0x1000u) & 0xffffe000u;
+  memcpy(&hi, &b, 4);
+  lo = v - hi;
+}
+// appends the [hi | lo] UMMA image of B (K = 64 x N = 64, element (k, n) = fill(k, n)) in layout [K/4][N][4]
+template <class F>
+static void ht_add_image(std::vector<float>& stream, F fill) {
+  const size_t base = stream.size();
+  stream.resize(base + HT_IMG_FLOATS, 0.f);
+  for (int k = 0; k < 64; ++k)
+    for (int n = 0; n < 64; ++n) {
+      float hi, lo;
+      ht_split_host(fill(k, n), hi, lo);
+      const size_t idx = (size_t)(k / 4) * (64 * 4) + (size_t)n * 4 + (k % 4);
+      stream[base + idx] = hi;
+      stream[base + 64 * 64 + idx] = lo;
+    }
+}
+static bool hmc_use_tc(const bgm_hmc* m) { return m->tc.enabled && m->engine != 1; }
+
+static int hmc_tc_launch(const bgm_hmc* m, HmcDev& D, int n_rows, cudaStream_t st) {
+  const int smem = (HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats) * 4;
+  const int nblocks = (n_rows + HT_ROWS - 1) / HT_ROWS;
+  const int grid = std::max(1, std::min(nblocks, m->sm_count));
+  const int zd = m->tc.zd;
+#define BGM_HT_LAUNCH(Z)                                                                                              \
+  do {                                                                                                                \
+    BGM_CUDA_OK(cudaFuncSetAttribute(hmc_tc_kernel<Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
+    hmc_tc_kernel<Z><<<grid, HT_ROWS, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_small_dev, D);                        \
+  } while (0)
+  if (zd <= 4) BGM_HT_LAUNCH(4);
+  else if (zd <= 8) BGM_HT_LAUNCH(8);
+  else if (zd <= 12) BGM_HT_LAUNCH(12);
+  else BGM_HT_LAUNCH(16);
+#undef BGM_HT_LAUNCH
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -230,6 +285,49 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
   m->macs = macs;
   m->issued = pk.issued;
 
+  // ---- tensor-core engine: every hidden layer 64 wide, at least two of them ----
+  std::vector<float> tstream, tsmall;
+  {
+    HmcTcProgram& T = m->tc;
+    memset(&T, 0, sizeof(T));
+    bool ok = nh >= 2;
+    for (int l = 0; l < nh; ++l) ok = ok && g->units[l] == 64;
+    if (ok) {
+      T.enabled = 1;
+      T.zd = zd; T.kin = P.kin; T.x_dim = xd; T.nh = nh;
+      T.n_chunks = (xd + 31) / 32;
+      T.n_img = 2 * (nh - 1) + 2 * T.n_chunks;
+      for (int d = 0; d < zd; ++d) { T.bn_mean[d] = P.bn_mean[d]; T.bn_inv[d] = P.bn_inv[d]; T.bn_beta[d] = P.bn_beta[d]; }
+      for (int l = 1; l < nh; ++l)                              // forward hidden layers 2..nh: B[k][n] = W_l[k][n]
+        ht_add_image(tstream, [&](int k, int n) { return Wl[l][(size_t)k * 64 + n]; });
+      for (int c = 0; c < T.n_chunks; ++c) {
+        auto feat = [&](int q) { return c * 32 + (q & 31); };
+        // head forward: B[k][n] = (n < 32 ? Wm : Wv)[k][feature]
+        ht_add_image(tstream, [&](int k, int n) { return feat(n) < xd ? (n < 32 ? Wm : Wv)[(size_t)k * xd + feat(n)] : 0.f; });
+        // head backward: B[k][n] = (k < 32 ? Wm : Wv)[n][feature of k]
+        ht_add_image(tstream, [&](int k, int n) { return feat(k) < xd ? (k < 32 ? Wm : Wv)[(size_t)n * xd + feat(k)] : 0.f; });
+      }
+      for (int l = nh - 1; l >= 1; --l)                         // backward hidden layers: B[k][n] = W_l[n][k]
+        ht_add_image(tstream, [&](int k, int n) { return Wl[l][(size_t)n * 64 + k]; });
+      T.off_W1 = 0;
+      tsmall.resize((size_t)zd * 64, 0.f);
+      for (int d = 0; d < zd; ++d)
+        for (int j = 0; j < 64; ++j) tsmall[(size_t)d * 64 + j] = Wl[0][(size_t)d * 64 + j];
+      T.off_b1 = (int)tsmall.size();
+      for (int j = 0; j < 64; ++j) tsmall.push_back(bl[0][j]);
+      T.off_bh = (int)tsmall.size();
+      for (int l = 1; l < nh; ++l)
+        for (int j = 0; j < 64; ++j) tsmall.push_back(bl[l][j]);
+      T.off_bm = (int)tsmall.size();
+      for (int q = 0; q < 32 * T.n_chunks; ++q) tsmall.push_back(q < xd ? bm[q] : 0.f);
+      T.off_bv = (int)tsmall.size();
+      for (int q = 0; q < 32 * T.n_chunks; ++q) tsmall.push_back(q < xd ? bv[q] : 0.f);
+      while (tsmall.size() % 4) tsmall.push_back(0.f);
+      T.small_floats = (int)tsmall.size();
+      m->tc_issued = 3LL * 64 * 64 * T.n_img + 2LL * zd * 64;   // 3 TF32 passes per 64 x 64 product + the first layer twice
+    }
+  }
+
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -237,8 +335,23 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
   if (e == cudaSuccess) e = cudaMalloc(&m->image_dev, pk.image.size() * sizeof(float));
   if (e == cudaSuccess)
     e = cudaMemcpy(m->image_dev, pk.image.data(), pk.image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && m->tc.enabled) {
+    if ((HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats) * 4 > m->smem_max - HMC_SMEM_RESERVE) m->tc.enabled = 0;
+  }
+  if (e == cudaSuccess && m->tc.enabled) {
+    e = cudaMalloc(&m->tc_stream_dev, tstream.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->tc_small_dev, tsmall.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(m->tc_stream_dev, tstream.data(), tstream.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(m->tc_small_dev, tsmall.data(), tsmall.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
+  {
+    const char* eng = getenv("BGM_HMC_ENGINE");                 // "simt" / "tensor": override for experiments
+    if (eng && eng[0] == 's') m->engine = 1;
+  }
   if (e != cudaSuccess) {
     if (m->image_dev) cudaFree(m->image_dev);
+    if (m->tc_stream_dev) cudaFree(m->tc_stream_dev);
+    if (m->tc_small_dev) cudaFree(m->tc_small_dev);
     delete m;
     return fail(BGM_ERR_CUDA, std::string("bgm_hmc_create: ") + cudaGetErrorString(e));
   }
@@ -254,7 +367,29 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
 void bgm_hmc_destroy(bgm_hmc* m) {
   if (!m) return;
   if (m->image_dev) cudaFree(m->image_dev);
+  if (m->tc_stream_dev) cudaFree(m->tc_stream_dev);
+  if (m->tc_small_dev) cudaFree(m->tc_small_dev);
   delete m;
+}
+
+int bgm_hmc_set_engine(bgm_hmc* m, int kind) {
+  using namespace bgm;
+  if (!m) return fail(BGM_ERR_ARG, "bgm_hmc_set_engine: null model");
+  if (kind < 0 || kind > 2) return fail(BGM_ERR_ARG, "bgm_hmc_set_engine: kind must be 0 (auto), 1 (SIMT) or 2 (tensor)");
+  if (kind == 2 && !m->tc.enabled)
+    return fail(BGM_ERR_UNSUPPORTED, "bgm_hmc_set_engine: the tensor engine needs >= 2 hidden layers, all 64 wide");
+  m->engine = kind;
+  return 0;
+}
+int bgm_hmc_engine_info(const bgm_hmc* m, int* active_kind, int* tensor_available, int* tensor_smem_bytes,
+                        long long* tensor_issued_macs_per_grad) {
+  using namespace bgm;
+  if (!m) return fail(BGM_ERR_ARG, "bgm_hmc_engine_info: null model");
+  if (active_kind) *active_kind = hmc_use_tc(m) ? 2 : 1;
+  if (tensor_available) *tensor_available = m->tc.enabled;
+  if (tensor_smem_bytes) *tensor_smem_bytes = m->tc.enabled ? (HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats) * 4 : 0;
+  if (tensor_issued_macs_per_grad) *tensor_issued_macs_per_grad = m->tc_issued;
+  return 0;
 }
 
 int bgm_hmc_info(const bgm_hmc* m, int* smem_bytes, int* n_ops, long long* macs_per_grad,
@@ -293,6 +428,7 @@ int bgm_hmc_logpost_grad(const bgm_hmc* m, const float* x_dev, int ldx, const fl
   D.mode = HMC_EVAL;
   D.z_in = z_dev;
   D.out_grad = out_grad_dev;
+  if (hmc_use_tc(m)) return hmc_tc_launch(m, D, n, (cudaStream_t)stream);
   return hmc_launch(m, m->prog, D, n, (cudaStream_t)stream);
 }
 
@@ -315,6 +451,7 @@ int bgm_hmc_run(const bgm_hmc* m, const bgm_hmc_args* a, void* stream) {
   memset(&D, 0, sizeof(D));
   D.a = *a;
   D.mode = HMC_RUN;
+  if (hmc_use_tc(m)) return hmc_tc_launch(m, D, a->n, (cudaStream_t)stream);
   return hmc_launch(m, m->prog, D, a->n, (cudaStream_t)stream);
 }
 

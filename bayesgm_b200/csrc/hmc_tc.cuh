@@ -1,0 +1,545 @@
+// BGM HMC, tensor-core engine (tcgen05 / TMEM): the same contract as hmc_kernel (hmc.cuh) --
+// bgm/base.py:665-705 (get_log_posterior) under :709-830 (TFP HamiltonianMonteCarlo +
+// SimpleStepSizeAdaptation), same Philox streams, same arguments -- for the standard
+// generator shape (every hidden layer 64 wide, at least two of them).
+//
+// Plan.  A CTA owns a tile of 128 observations = 128 TMEM lanes, worked on by SIXTEEN warps: warps q, q+4, q+8, q+12
+// share lane quarter q and split the columns four ways (16 of a hidden layer's 64 outputs, 8 of a head chunk's 32
+// features), so that every scheduler has four warps to interleave; the four threads of a row carry the chain
+// state (z, momentum, gradient) redundantly and exchange their partial sums (likelihood, first-layer transpose)
+// through shared memory, added in a fixed order, so they stay bit-identical.  Every 64-wide product of one gradient evaluation runs on the tensor cores as 3xTF32
+// (umma.cuh: hi*hi + lo*hi + hi*lo, fp32-level error):
+//   forward   h_l   = LeakyReLU(h_{l-1} W_l + b_l), l = 2..nh             (A = h_{l-1} in TMEM, D 64 columns)
+//   heads     [mu | raw]_c = h_nh [Wm_c | Wv_c], 32 features per chunk c   (A = h_nh stays resident)
+//             the thread turns its 32 (mu, raw) pairs and its 32 data values into d loss / d mu, d loss / d raw,
+//   head bwd  d loss / d h_nh += [dmu | draw]_c [Wm_c | Wv_c]^T            (A = [dmu | draw]_c, accumulating D)
+//   backward  d loss / d h_{l-1} = (d loss / d a_l) W_l^T, l = nh..2.
+// Only the first layer (z_dim inputs) and its transpose stay on the FMA pipe.  The head passes are software-
+// pipelined: MMA stage k carries the forward of chunk k and the backward of chunk k-1.  No weight is resident:
+// every operand is a pre-split [hi | lo] image of 32 KB streamed from L2 through a 4-slot shared-memory ring with
+// cp.async.bulk on mbarriers (1.28 MB per evaluation at x_dim = 500, shared by the tile's 128 rows), refilled as
+// soon as the MMAs that read a slot have committed.
+#pragma once
+#include "hmc.cuh"
+#include "umma.cuh"
+
+namespace bgm {
+
+constexpr int HT_ROWS = 128;
+constexpr int HT_TPR = 4;                    // threads per row
+constexpr int HT_THREADS = HT_ROWS * HT_TPR;
+constexpr int HT_IMG_FLOATS = 2 * 64 * 64;   // [hi | lo] of a K = 64, N = 64 operand in UMMA layout [K/4][N][4]
+constexpr int HT_SLOTS = 4;
+constexpr uint32_t HT_A_HI = 0, HT_A_LO = 64, HT_D = 128, HT_B_HI = 192, HT_B_LO = 256, HT_DH = 320;
+
+struct HmcTcProgram {
+  int enabled;
+  int zd, kin, x_dim, nh;
+  int n_chunks;                 // ceil(x_dim / 32)
+  int n_img;                    // images per gradient evaluation: (nh - 1) + 2 n_chunks + (nh - 1)
+  float bn_mean[HMC_MAXZ], bn_inv[HMC_MAXZ], bn_beta[HMC_MAXZ];
+  // resident small arrays (float offsets): W1 [zd][64], b1 [64], hidden biases [(nh-1)][64], bm, bv [32 n_chunks]
+  int off_W1, off_b1, off_bh, off_bm, off_bv, small_floats;
+};
+
+struct HtCtx {
+  const HmcTcProgram* P;
+  const float* stream;          // global image stream of one evaluation, n_img x HT_IMG_FLOATS
+  float* ring;                  // shared: HT_SLOTS x HT_IMG_FLOATS
+  const float* small;           // shared: resident small arrays
+  uint64_t* full;               // [HT_SLOTS]
+  uint32_t mma_bar;             // shared address of the MMA-completion barrier
+  uint32_t tbase, trow;         // TMEM base / this warp's lane quarter
+  uint32_t img_it, img_total;   // images consumed so far / in the whole launch (identical in every thread)
+  uint32_t mma_parity;
+  bool issuer_warp;
+};
+
+__device__ __forceinline__ void ht_fill(const HtCtx& C, uint32_t img_index_in_launch, int slot) {
+  const uint32_t i = img_index_in_launch % (uint32_t)C.P->n_img;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  mbar_expect_tx(C.full + slot, HT_IMG_FLOATS * 4u);
+  bulk_g2s(C.ring + slot * HT_IMG_FLOATS, C.stream + (size_t)i * HT_IMG_FLOATS, HT_IMG_FLOATS * 4u, C.full + slot);
+}
+
+// D (+)= A * B as 3xTF32, K = 64; acc0: accumulate onto D from the first MMA on.
+__device__ __forceinline__ void ht_issue(uint32_t tD, uint32_t tA_hi, uint32_t tA_lo, uint32_t b_img_saddr, uint32_t acc0) {
+  constexpr uint32_t idesc = umma::idesc_tf32_m128(64);
+  uint64_t dh = umma::smem_desc(b_img_saddr, 64 * 16, 128), dl = umma::smem_desc(b_img_saddr + 64 * 64 * 4, 64 * 16, 128);
+#pragma unroll
+  for (int ks = 0; ks < 8; ++ks) {
+    umma::mma_tf32_ts(tD, tA_hi + ks * 8, dh, idesc, (ks > 0) ? 1u : acc0);
+    umma::mma_tf32_ts(tD, tA_lo + ks * 8, dh, idesc, 1);
+    umma::mma_tf32_ts(tD, tA_hi + ks * 8, dl, idesc, 1);
+    dh += (64 * 32) >> 4;
+    dl += (64 * 32) >> 4;
+  }
+}
+
+// One MMA stage: the tile's A operands are published (tcgen05.st + fence + CTA barrier), the issuer waits for the
+// stage's images, issues, commits; everybody waits for the commit; the consumed slots are refilled.
+//   n_img = 1: D_target (+)= A_src * image;  n_img = 2: first image -> (DH += B), second -> (D = A).
+template <class Issue>
+__device__ __forceinline__ void ht_stage(HtCtx& C, int n_img, Issue issue) {
+  umma::wait_st();
+  umma::fence_before_sync();
+  __syncthreads();
+  if (C.issuer_warp) {
+    if (umma::elect_one()) {
+      for (int j = 0; j < n_img; ++j) {
+        const uint32_t it = C.img_it + j;
+        mbar_wait(C.full + (it % HT_SLOTS), (it / HT_SLOTS) & 1u);
+      }
+      umma::fence_after_sync();
+      issue();
+      umma::mma_commit(C.mma_bar);
+    }
+    __syncwarp();
+  }
+  umma::mbar_wait(C.mma_bar, C.mma_parity);
+  C.mma_parity ^= 1u;
+  umma::fence_after_sync();
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < n_img; ++j) {
+      const uint32_t it = C.img_it + j;
+      if (it + HT_SLOTS < C.img_total) ht_fill(C, it + HT_SLOTS, it % HT_SLOTS);
+    }
+  }
+  C.img_it += n_img;
+}
+__device__ __forceinline__ uint32_t ht_slot_addr(const HtCtx& C, uint32_t it) {
+  return umma::smem_addr(C.ring + (it % HT_SLOTS) * HT_IMG_FLOATS);
+}
+
+// bias + LeakyReLU (sign bits into `bits` at position base..base+15) + split, 16 columns, D -> A
+__device__ __forceinline__ void ht_act16(const uint32_t (&r)[16], const float* bias, unsigned long long& bits, int base,
+                                         uint32_t t_hi, uint32_t t_lo) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float v = __uint_as_float(r[i]) + bias[i];
+    if (v > 0.f) bits |= 1ull << (base + i);
+    else v *= 0.2f;
+    umma::split_tf32(v, hi[i], lo[i]);
+  }
+  umma::st16(t_hi, hi);
+  umma::st16(t_lo, lo);
+}
+// gradient through a LeakyReLU whose sign bits are `bits` + split, 16 columns
+__device__ __forceinline__ void ht_mask16(const uint32_t (&r)[16], unsigned long long bits, int base, uint32_t t_hi, uint32_t t_lo) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float g = __uint_as_float(r[i]);
+    const float v = ((bits >> (base + i)) & 1ull) ? g : 0.2f * g;
+    umma::split_tf32(v, hi[i], lo[i]);
+  }
+  umma::st16(t_hi, hi);
+  umma::st16(t_lo, lo);
+}
+
+// One gradient evaluation for the thread's row at z: returns the likelihood loss (0 unless want_lp) and leaves
+// d loss / d z_in (before the BatchNormalization scale) in gz.
+template <int ZMAX>
+__device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float (&z)[ZMAX], int lrow, bool want_lp,
+                                         float (&gz)[ZMAX]) {
+  const HmcTcProgram& P = *C.P;
+  const int zd = P.zd, nh = P.nh, NC = P.n_chunks;
+  const float* W1 = C.small + P.off_W1;
+  unsigned long long sg[HMC_MAXL];
+#pragma unroll
+  for (int l = 0; l < HMC_MAXL; ++l) sg[l] = 0ull;
+  // ---- layer 1 on the FMA pipe: a1 = b1 + BN(z) W1 ----
+  {
+    float zin[ZMAX];
+#pragma unroll
+    for (int d = 0; d < ZMAX; ++d) zin[d] = d < zd ? (z[d] - P.bn_mean[d]) * P.bn_inv[d] + P.bn_beta[d] : 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float a[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) a[i] = C.small[P.off_b1 + h * 16 + i];
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d) {
+        if (d < zd) {
+          const float zv = zin[d];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(W1 + d * 64 + h * 16 + i);
+            a[i] = fmaf(zv, w.x, a[i]); a[i + 1] = fmaf(zv, w.y, a[i + 1]);
+            a[i + 2] = fmaf(zv, w.z, a[i + 2]); a[i + 3] = fmaf(zv, w.w, a[i + 3]);
+          }
+        }
+      }
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = a[i];
+        if (v > 0.f) sg[0] |= 1ull << (h * 16 + i);
+        else v *= 0.2f;
+        umma::split_tf32(v, hi[i], lo[i]);
+      }
+      umma::st16(C.trow + HT_A_HI + h * 16, hi);
+      umma::st16(C.trow + HT_A_LO + h * 16, lo);
+    }
+  }
+  // ---- hidden layers 2..nh ----
+#pragma unroll 1
+  for (int l = 1; l < nh; ++l) {
+    const uint32_t it = C.img_it;
+    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
+    const float* bias = C.small + P.off_bh + (l - 1) * 64;
+    unsigned long long bits = 0ull;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint32_t r[16];
+      umma::ld16(C.trow + HT_D + h * 16, r);
+      umma::wait_ld();
+      ht_act16(r, bias + h * 16, bits, h * 16, C.trow + HT_A_HI + h * 16, C.trow + HT_A_LO + h * 16);
+    }
+#pragma unroll
+    for (int q = 0; q < HMC_MAXL; ++q)
+      if (q == l) sg[q] = bits;
+  }
+  // ---- heads, software-pipelined over chunks of 32 features ----
+  float loss = 0.f;
+  const float* xrow = D.a.x_dev + (size_t)lrow * D.a.ldx;
+#pragma unroll 1
+  for (int k = 0; k <= NC; ++k) {
+    // this chunk's data values: issued before the stage so that their latency hides behind the MMAs
+    float4 xv[8];
+    if (k < NC) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = k * 32 + i * 4;
+        xv[i] = (c < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + c))
+                              : make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
+                                            __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+      }
+    }
+    const uint32_t it = C.img_it;
+    const int n_img = (k > 0 ? 1 : 0) + (k < NC ? 1 : 0);
+    ht_stage(C, n_img, [&]() {
+      uint32_t j = it;
+      if (k > 0) {
+        ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, j), k > 1 ? 1u : 0u);
+        ++j;
+      }
+      if (k < NC) ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, j), 0u);
+    });
+    if (k == NC) break;
+    const float* bm = C.small + P.off_bm + k * 32;
+    const float* bv = C.small + P.off_bv + k * 32;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t rm[16], rr[16];
+      umma::ld16(C.trow + HT_D + h * 16, rm);
+      umma::ld16(C.trow + HT_D + 32 + h * 16, rr);
+      umma::wait_ld();
+      uint32_t mh[16], ml[16], vh[16], vl[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int q = h * 16 + i;                      // feature k*32 + q
+        const float4 x4 = xv[q >> 2];
+        const float xs = (q & 3) == 0 ? x4.x : ((q & 3) == 1 ? x4.y : ((q & 3) == 2 ? x4.z : x4.w));
+        const bool obs = (k * 32 + q < P.x_dim) && (xs == xs);                         // NaN = missing
+        const float mu = __uint_as_float(rm[i]) + bm[q];
+        const float raw = __uint_as_float(rr[i]) + bv[q];
+        const float e = expf(-fabsf(raw));
+        const float s2 = (fmaxf(raw, 0.f) + log1pf(e)) + 1e-6f;                        // softplus + eps
+        const float inv = 1.f / s2;
+        const float d = obs ? xs - mu : 0.f;
+        const float r1 = 1.f / (1.f + e);
+        const float sig = raw >= 0.f ? r1 : e * r1;
+        if (want_lp && obs) loss += (d * d) * (0.5f * inv) + 0.5f * logf(s2);           // bgm/base.py:683-684
+        const float dmu = obs ? -d * inv : 0.f;
+        const float draw = obs ? (0.5f * inv - (0.5f * d * d) * (inv * inv)) * sig : 0.f;
+        umma::split_tf32(dmu, mh[i], ml[i]);
+        umma::split_tf32(draw, vh[i], vl[i]);
+      }
+      umma::st16(C.trow + HT_B_HI + h * 16, mh);
+      umma::st16(C.trow + HT_B_LO + h * 16, ml);
+      umma::st16(C.trow + HT_B_HI + 32 + h * 16, vh);
+      umma::st16(C.trow + HT_B_LO + 32 + h * 16, vl);
+    }
+  }
+  // ---- d loss / d h_nh -> through the last LeakyReLU -> A ----
+  {
+    unsigned long long bits = 0ull;
+#pragma unroll
+    for (int q = 0; q < HMC_MAXL; ++q)
+      if (q == nh - 1) bits = sg[q];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint32_t r[16];
+      umma::ld16(C.trow + HT_DH + h * 16, r);
+      umma::wait_ld();
+      ht_mask16(r, bits, h * 16, C.trow + HT_A_HI + h * 16, C.trow + HT_A_LO + h * 16);
+    }
+  }
+  // ---- backward hidden layers nh..2: d loss / d h_{l-1} = (d loss / d a_l) W_l^T ----
+  float ga[64];
+#pragma unroll 1
+  for (int l = nh - 1; l >= 1; --l) {
+    const uint32_t it = C.img_it;
+    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
+    unsigned long long bits = 0ull;
+#pragma unroll
+    for (int q = 0; q < HMC_MAXL; ++q)
+      if (q == l - 1) bits = sg[q];
+    if (l > 1) {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t r[16];
+        umma::ld16(C.trow + HT_D + h * 16, r);
+        umma::wait_ld();
+        ht_mask16(r, bits, h * 16, C.trow + HT_A_HI + h * 16, C.trow + HT_A_LO + h * 16);
+      }
+    } else {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        uint32_t r[16];
+        umma::ld16(C.trow + HT_D + h * 16, r);
+        umma::wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float g = __uint_as_float(r[i]);
+          ga[h * 16 + i] = ((bits >> (h * 16 + i)) & 1ull) ? g : 0.2f * g;
+        }
+      }
+    }
+  }
+  // ---- layer 1 transposed on the FMA pipe: d loss / d z_in[d] = sum_j ga[j] W1[d][j] ----
+#pragma unroll
+  for (int d = 0; d < ZMAX; ++d) {
+    float s = 0.f;
+    if (d < zd) {
+#pragma unroll
+      for (int j = 0; j < 64; j += 4) {
+        const float4 w = *reinterpret_cast<const float4*>(W1 + d * 64 + j);
+        s = fmaf(ga[j], w.x, s); s = fmaf(ga[j + 1], w.y, s); s = fmaf(ga[j + 2], w.z, s); s = fmaf(ga[j + 3], w.w, s);
+      }
+    }
+    gz[d] = s;
+  }
+  return loss;
+}
+
+template <int ZMAX>
+__global__ void __launch_bounds__(HT_ROWS, 1)
+hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ stream, const float* __restrict__ small_g,
+              const __grid_constant__ HmcDev D) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t full[HT_SLOTS];
+  __shared__ uint64_t mma_bar_s;
+  __shared__ uint32_t tmem_slot;
+  const bgm_hmc_args& A = D.a;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int n_rows = A.n, zd = P.zd;
+  const int nblocks = (n_rows + HT_ROWS - 1) / HT_ROWS;
+  const int L = A.num_leapfrog;
+  const bool need_init = D.mode != HMC_RUN || A.init_mode != 0;
+  const int steps = D.mode == HMC_RUN ? A.t_end - A.t_begin : 0;
+  const int evals_per_block = (need_init ? 1 : 0) + steps * L;
+  int my_blocks = 0;
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) ++my_blocks;
+
+  HtCtx C;
+  C.P = &P;
+  C.stream = stream;
+  C.ring = smem;
+  float* small_s = smem + HT_SLOTS * HT_IMG_FLOATS;
+  C.small = small_s;
+  C.full = full;
+  C.mma_bar = umma::smem_addr(&mma_bar_s);
+  C.img_it = 0;
+  C.img_total = (uint32_t)my_blocks * (uint32_t)evals_per_block * (uint32_t)P.n_img;
+  C.mma_parity = 0;
+  C.issuer_warp = warp == 3;
+  if (tid == 0) {
+    for (int s = 0; s < HT_SLOTS; ++s) mbar_init(full + s, 1);
+    umma::mbar_init(C.mma_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    for (int s = 0; s < HT_SLOTS; ++s)
+      if ((uint32_t)s < C.img_total) ht_fill(C, (uint32_t)s, s);
+  }
+  for (int i = tid; i < P.small_floats; i += HT_ROWS) small_s[i] = small_g[i];
+  if (warp == 0) umma::tmem_alloc512(&tmem_slot);
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  C.tbase = __shfl_sync(0xffffffffu, tmem_slot, 0);
+  C.trow = C.tbase + ((uint32_t)(warp * 32) << 16);
+  const float eps = (D.mode == HMC_RUN && A.step_dev) ? *A.step_dev : 0.f;
+
+  for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const int row = b * HT_ROWS + tid;
+    const bool valid = row < n_rows;
+    const int lrow = valid ? row : n_rows - 1;
+    const int64_t grow = A.row_offset + lrow;
+    float z[ZMAX], p[ZMAX], g[ZMAX], gz[ZMAX];
+#pragma unroll
+    for (int d = 0; d < ZMAX; ++d) { z[d] = 0.f; p[d] = 0.f; g[d] = 0.f; }
+
+    // log posterior and gradient from an evaluation's outputs (bgm/base.py:702-704)
+    auto finish = [&](float loss) -> float {
+      float prior = 0.f;
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) {
+          prior = fmaf(z[d], z[d], prior);
+          g[d] = -(gz[d] * P.bn_inv[d] + z[d]);
+        }
+      return -(0.5f * prior + loss);
+    };
+
+    if (D.mode != HMC_RUN) {   // EVAL: log p and gradient at z_in
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) z[d] = D.z_in[(size_t)lrow * zd + d];
+      const float loss = ht_eval<ZMAX>(C, D, z, lrow, true, gz);
+      const float lp = finish(loss);
+      if (valid) {
+        A.lp_state_dev[row] = lp;
+        if (D.out_grad)
+#pragma unroll
+          for (int d = 0; d < ZMAX; ++d)
+            if (d < zd) D.out_grad[(size_t)row * zd + d] = g[d];
+      }
+      continue;
+    }
+
+    // ---- chain state (bgm/base.py:778) ----
+    if (A.init_mode == 2) {
+#pragma unroll
+      for (int gi = 0; gi < ZMAX / 4; ++gi) {
+        if (gi * 4 < zd) {
+          float e[4];
+          normal4(A.seed, grow, T_INIT, NOISE_MOMENTUM, gi, e);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) z[gi * 4 + q] = e[q];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) z[d] = A.z_state_dev[(size_t)lrow * zd + d];
+    }
+    float lp_cur;
+    if (need_init) {
+      const float loss = ht_eval<ZMAX>(C, D, z, lrow, true, gz);
+      lp_cur = finish(loss);
+      if (valid) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) {
+            A.z_state_dev[(size_t)row * zd + d] = z[d];
+            A.g_state_dev[(size_t)row * zd + d] = g[d];
+          }
+      }
+    } else {
+      lp_cur = A.lp_state_dev[lrow];
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) g[d] = A.g_state_dev[(size_t)lrow * zd + d];
+    }
+
+    // ---- HMC steps (TFP 0.18 HamiltonianMonteCarlo, unit mass) ----
+#pragma unroll 1
+    for (int t = A.t_begin; t < A.t_end; ++t) {
+      float ke0 = 0.f;
+#pragma unroll
+      for (int gi = 0; gi < ZMAX / 4; ++gi) {
+        if (gi * 4 < zd) {
+          float e[4];
+          if (A.mom_dev) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              e[q] = (gi * 4 + q < zd) ? A.mom_dev[((size_t)t * A.n + lrow) * zd + gi * 4 + q] : 0.f;
+          } else {
+            normal4(A.seed, grow, (uint32_t)t, NOISE_MOMENTUM, gi, e);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int d = gi * 4 + q;
+            if (d < zd) {
+              ke0 = fmaf(e[q], e[q], ke0);
+              p[d] = e[q] + (0.5f * eps) * g[d];
+            }
+          }
+        }
+      }
+      ke0 *= 0.5f;
+      float lp_new = lp_cur;
+#pragma unroll 1
+      for (int l = 0; l < L; ++l) {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) z[d] += eps * p[d];
+        const bool last = l == L - 1;
+        const float loss = ht_eval<ZMAX>(C, D, z, lrow, last, gz);
+        const float lp = finish(loss);
+        if (last) lp_new = lp;
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) p[d] += eps * g[d];
+      }
+      float ke1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d)
+        if (d < zd) {
+          const float pp = p[d] - (0.5f * eps) * g[d];
+          ke1 = fmaf(pp, pp, ke1);
+        }
+      ke1 *= 0.5f;
+      float log_accept = (lp_new - lp_cur) + (ke0 - ke1);
+      if (!(fabsf(log_accept) <= 3.0e38f)) log_accept = -INFINITY;   // NaN / inf energy: reject
+      float logu;
+      if (A.logu_dev) logu = A.logu_dev[(size_t)t * A.n + lrow];
+      else logu = logf(u01_open1(noise_block(A.seed, grow, (uint32_t)t, NOISE_ACCEPT, 0).x));
+      const bool acc = logu < log_accept;
+      if (acc) {
+        lp_cur = lp_new;
+        if (valid)
+#pragma unroll
+          for (int d = 0; d < ZMAX; ++d)
+            if (d < zd) {
+              A.z_state_dev[(size_t)row * zd + d] = z[d];
+              A.g_state_dev[(size_t)row * zd + d] = g[d];
+            }
+      } else {
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) {
+            z[d] = A.z_state_dev[(size_t)lrow * zd + d];
+            g[d] = A.g_state_dev[(size_t)lrow * zd + d];
+          }
+      }
+      if (A.accept_mask_dev && valid) A.accept_mask_dev[(size_t)t * A.n + row] = acc ? 1 : 0;
+      if (A.log_accept_dev && valid) A.log_accept_dev[(size_t)t * A.n + row] = log_accept;
+      if (A.accept_count_dev) {
+        const unsigned bal = __ballot_sync(0xffffffffu, acc && valid);
+        if (lane == 0 && bal) atomicAdd(A.accept_count_dev + t, __popc(bal));
+      }
+      if (A.accept_stat_dev) {   // SimpleStepSizeAdaptation: mean over ALL chains of exp(min(log_accept, 0))
+        float a = valid ? expf(fminf(log_accept, 0.f)) : 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) atomicAdd(A.accept_stat_dev + t, (double)a);
+      }
+      if (t >= A.burn_in && A.out_samples_dev && valid) {
+        float* dst = A.out_samples_dev + ((size_t)(t - A.burn_in) * A.n + row) * zd;
+#pragma unroll
+        for (int d = 0; d < ZMAX; ++d)
+          if (d < zd) dst[d] = z[d];
+      }
+    }
+    if (valid) A.lp_state_dev[row] = lp_cur;
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) umma::tmem_dealloc512(C.tbase);
+}
+
+}  // namespace bgm

@@ -82,6 +82,17 @@ __device__ __forceinline__ void st32(uint32_t taddr, const uint32_t (&r)[32]) {
       : "memory");
 }
 
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
 // ---- fp32 -> (hi, lo), both tf32-exact up to the truncation of lo's last bits ----
 // hi = v rounded to nearest at 11 significant bits; lo = v - hi is exact in fp32.
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {

@@ -309,6 +309,17 @@ void bgm_hmc_destroy(bgm_hmc* m);
 int bgm_hmc_info(const bgm_hmc* m, int* smem_bytes, int* n_ops, long long* macs_per_grad,
                  long long* issued_macs_per_grad);
 
+/* HMC engines, two execution plans of the SAME algorithm (same arguments, same Philox streams) behind
+ * bgm_hmc_logpost_grad / bgm_hmc_run:
+ *   1  SIMT   : streamed fp32 tiles on the FMA pipe (hmc.cuh), any hidden widths <= 64;
+ *   2  tensor : every 64-wide product of a gradient evaluation on the 5th-gen tensor cores (tcgen05, operands
+ *               and accumulators in TMEM) as error-compensated 3xTF32 (hmc_tc.cuh).  Needs >= 2 hidden layers,
+ *               all 64 wide.
+ * kind 0 = auto (tensor when available).  bgm_hmc_predict / bgm_hmc_heads always run on the SIMT engine. */
+int bgm_hmc_set_engine(bgm_hmc* m, int kind);
+int bgm_hmc_engine_info(const bgm_hmc* m, int* active_kind, int* tensor_available, int* tensor_smem_bytes,
+                        long long* tensor_issued_macs_per_grad);
+
 /* BGM.get_log_posterior (bgm/base.py:665-705) and its gradient w.r.t. z (what TFP's
  * HMC obtains by autodiff).  x_dev: (n, ldx), ldx % 4 == 0, 16-byte aligned; a NaN
  * entry is a MISSING observation (the input convention of BGM.predict, :527-545) and
