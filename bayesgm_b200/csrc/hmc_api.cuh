@@ -108,19 +108,23 @@ static void ht_add_image(std::vector<float>& stream, F fill) {
 }
 static bool hmc_use_tc(const bgm_hmc* m) { return m->tc.enabled && m->engine != 1; }
 
+static int hmc_tc_zmax(int zd) { return zd <= 4 ? 4 : (zd <= 8 ? 8 : (zd <= 12 ? 12 : 16)); }
+static int hmc_tc_smem(const bgm_hmc* m) {
+  return (HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats + HT_TPR * (hmc_tc_zmax(m->tc.zd) + 1) * HT_ROWS) * 4;
+}
 static int hmc_tc_launch(const bgm_hmc* m, HmcDev& D, int n_rows, cudaStream_t st) {
-  const int smem = (HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats) * 4;
+  const int smem = hmc_tc_smem(m);
   const int nblocks = (n_rows + HT_ROWS - 1) / HT_ROWS;
   const int grid = std::max(1, std::min(nblocks, m->sm_count));
-  const int zd = m->tc.zd;
+  const int zmax = hmc_tc_zmax(m->tc.zd);
 #define BGM_HT_LAUNCH(Z)                                                                                              \
   do {                                                                                                                \
     BGM_CUDA_OK(cudaFuncSetAttribute(hmc_tc_kernel<Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
-    hmc_tc_kernel<Z><<<grid, HT_ROWS, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_small_dev, D);                        \
+    hmc_tc_kernel<Z><<<grid, HT_THREADS, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_small_dev, D);                     \
   } while (0)
-  if (zd <= 4) BGM_HT_LAUNCH(4);
-  else if (zd <= 8) BGM_HT_LAUNCH(8);
-  else if (zd <= 12) BGM_HT_LAUNCH(12);
+  if (zmax == 4) BGM_HT_LAUNCH(4);
+  else if (zmax == 8) BGM_HT_LAUNCH(8);
+  else if (zmax == 12) BGM_HT_LAUNCH(12);
   else BGM_HT_LAUNCH(16);
 #undef BGM_HT_LAUNCH
   BGM_CUDA_OK(cudaGetLastError());
@@ -336,7 +340,7 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
   if (e == cudaSuccess)
     e = cudaMemcpy(m->image_dev, pk.image.data(), pk.image.size() * sizeof(float), cudaMemcpyHostToDevice);
   if (e == cudaSuccess && m->tc.enabled) {
-    if ((HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats) * 4 > m->smem_max - HMC_SMEM_RESERVE) m->tc.enabled = 0;
+    if (hmc_tc_smem(m) > m->smem_max - HMC_SMEM_RESERVE) m->tc.enabled = 0;
   }
   if (e == cudaSuccess && m->tc.enabled) {
     e = cudaMalloc(&m->tc_stream_dev, tstream.size() * sizeof(float));
@@ -387,7 +391,7 @@ int bgm_hmc_engine_info(const bgm_hmc* m, int* active_kind, int* tensor_availabl
   if (!m) return fail(BGM_ERR_ARG, "bgm_hmc_engine_info: null model");
   if (active_kind) *active_kind = hmc_use_tc(m) ? 2 : 1;
   if (tensor_available) *tensor_available = m->tc.enabled;
-  if (tensor_smem_bytes) *tensor_smem_bytes = m->tc.enabled ? (HT_SLOTS * HT_IMG_FLOATS + m->tc.small_floats) * 4 : 0;
+  if (tensor_smem_bytes) *tensor_smem_bytes = m->tc.enabled ? hmc_tc_smem(m) : 0;
   if (tensor_issued_macs_per_grad) *tensor_issued_macs_per_grad = m->tc_issued;
   return 0;
 }

@@ -50,6 +50,9 @@ struct HtCtx {
   uint64_t* full;               // [HT_SLOTS]
   uint32_t mma_bar;             // shared address of the MMA-completion barrier
   uint32_t tbase, trow;         // TMEM base / this warp's lane quarter
+  int cg;                       // which quarter of the columns this thread owns (0..3)
+  int r_in_tile;                // row of the tile (TMEM lane)
+  float* xch;                   // shared: [HT_TPR][ZMAX + 1][HT_ROWS] partial sums exchanged between a row's threads
   uint32_t img_it, img_total;   // images consumed so far / in the whole launch (identical in every thread)
   uint32_t mma_parity;
   bool issuer_warp;
@@ -111,14 +114,14 @@ __device__ __forceinline__ uint32_t ht_slot_addr(const HtCtx& C, uint32_t it) {
   return umma::smem_addr(C.ring + (it % HT_SLOTS) * HT_IMG_FLOATS);
 }
 
-// bias + LeakyReLU (sign bits into `bits` at position base..base+15) + split, 16 columns, D -> A
-__device__ __forceinline__ void ht_act16(const uint32_t (&r)[16], const float* bias, unsigned long long& bits, int base,
-                                         uint32_t t_hi, uint32_t t_lo) {
+// bias + LeakyReLU (sign bits of the thread's 16 columns into `bits`) + split, D -> A
+__device__ __forceinline__ void ht_act16(const uint32_t (&r)[16], const float* bias, uint32_t& bits, uint32_t t_hi, uint32_t t_lo) {
   uint32_t hi[16], lo[16];
+  bits = 0u;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     float v = __uint_as_float(r[i]) + bias[i];
-    if (v > 0.f) bits |= 1ull << (base + i);
+    if (v > 0.f) bits |= 1u << i;
     else v *= 0.2f;
     umma::split_tf32(v, hi[i], lo[i]);
   }
@@ -126,96 +129,85 @@ __device__ __forceinline__ void ht_act16(const uint32_t (&r)[16], const float* b
   umma::st16(t_lo, lo);
 }
 // gradient through a LeakyReLU whose sign bits are `bits` + split, 16 columns
-__device__ __forceinline__ void ht_mask16(const uint32_t (&r)[16], unsigned long long bits, int base, uint32_t t_hi, uint32_t t_lo) {
+__device__ __forceinline__ void ht_mask16(const uint32_t (&r)[16], uint32_t bits, uint32_t t_hi, uint32_t t_lo) {
   uint32_t hi[16], lo[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float g = __uint_as_float(r[i]);
-    const float v = ((bits >> (base + i)) & 1ull) ? g : 0.2f * g;
+    const float v = ((bits >> i) & 1u) ? g : 0.2f * g;
     umma::split_tf32(v, hi[i], lo[i]);
   }
   umma::st16(t_hi, hi);
   umma::st16(t_lo, lo);
 }
 
-// One gradient evaluation for the thread's row at z: returns the likelihood loss (0 unless want_lp) and leaves
-// d loss / d z_in (before the BatchNormalization scale) in gz.
+// One gradient evaluation for the thread's row at z (identical in the row's four threads): returns the likelihood
+// loss (0 unless want_lp) and leaves d loss / d z_in (before the BatchNormalization scale) in gz -- both summed over
+// the four threads' partials in a fixed order, so the four copies agree bit for bit.
 template <int ZMAX>
 __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float (&z)[ZMAX], int lrow, bool want_lp,
                                          float (&gz)[ZMAX]) {
   const HmcTcProgram& P = *C.P;
   const int zd = P.zd, nh = P.nh, NC = P.n_chunks;
-  const float* W1 = C.small + P.off_W1;
-  unsigned long long sg[HMC_MAXL];
+  const int cg = C.cg;
+  const float* W1 = C.small + P.off_W1 + cg * 16;          // this thread's 16 columns of W1 [zd][64]
+  uint32_t sg[HMC_MAXL];
 #pragma unroll
-  for (int l = 0; l < HMC_MAXL; ++l) sg[l] = 0ull;
-  // ---- layer 1 on the FMA pipe: a1 = b1 + BN(z) W1 ----
+  for (int l = 0; l < HMC_MAXL; ++l) sg[l] = 0u;
+  const uint32_t tA_hi = C.trow + HT_A_HI + cg * 16, tA_lo = C.trow + HT_A_LO + cg * 16;
+  // ---- layer 1 on the FMA pipe: a1 = b1 + BN(z) W1, columns [16 cg, 16 cg + 16) ----
   {
-    float zin[ZMAX];
+    float a[16];
 #pragma unroll
-    for (int d = 0; d < ZMAX; ++d) zin[d] = d < zd ? (z[d] - P.bn_mean[d]) * P.bn_inv[d] + P.bn_beta[d] : 0.f;
+    for (int i = 0; i < 16; ++i) a[i] = C.small[P.off_b1 + cg * 16 + i];
 #pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      float a[16];
+    for (int d = 0; d < ZMAX; ++d) {
+      if (d < zd) {
+        const float zv = (z[d] - P.bn_mean[d]) * P.bn_inv[d] + P.bn_beta[d];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) a[i] = C.small[P.off_b1 + h * 16 + i];
-#pragma unroll
-      for (int d = 0; d < ZMAX; ++d) {
-        if (d < zd) {
-          const float zv = zin[d];
-#pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 w = *reinterpret_cast<const float4*>(W1 + d * 64 + h * 16 + i);
-            a[i] = fmaf(zv, w.x, a[i]); a[i + 1] = fmaf(zv, w.y, a[i + 1]);
-            a[i + 2] = fmaf(zv, w.z, a[i + 2]); a[i + 3] = fmaf(zv, w.w, a[i + 3]);
-          }
+        for (int i = 0; i < 16; i += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(W1 + d * 64 + i);
+          a[i] = fmaf(zv, w.x, a[i]); a[i + 1] = fmaf(zv, w.y, a[i + 1]);
+          a[i + 2] = fmaf(zv, w.z, a[i + 2]); a[i + 3] = fmaf(zv, w.w, a[i + 3]);
         }
       }
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float v = a[i];
-        if (v > 0.f) sg[0] |= 1ull << (h * 16 + i);
-        else v *= 0.2f;
-        umma::split_tf32(v, hi[i], lo[i]);
-      }
-      umma::st16(C.trow + HT_A_HI + h * 16, hi);
-      umma::st16(C.trow + HT_A_LO + h * 16, lo);
     }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      float v = a[i];
+      if (v > 0.f) sg[0] |= 1u << i;
+      else v *= 0.2f;
+      umma::split_tf32(v, hi[i], lo[i]);
+    }
+    umma::st16(tA_hi, hi);
+    umma::st16(tA_lo, lo);
   }
   // ---- hidden layers 2..nh ----
 #pragma unroll 1
   for (int l = 1; l < nh; ++l) {
     const uint32_t it = C.img_it;
     ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
-    const float* bias = C.small + P.off_bh + (l - 1) * 64;
-    unsigned long long bits = 0ull;
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      uint32_t r[16];
-      umma::ld16(C.trow + HT_D + h * 16, r);
-      umma::wait_ld();
-      ht_act16(r, bias + h * 16, bits, h * 16, C.trow + HT_A_HI + h * 16, C.trow + HT_A_LO + h * 16);
-    }
+    uint32_t r[16], bits;
+    umma::ld16(C.trow + HT_D + cg * 16, r);
+    umma::wait_ld();
+    ht_act16(r, C.small + P.off_bh + (l - 1) * 64 + cg * 16, bits, tA_hi, tA_lo);
 #pragma unroll
     for (int q = 0; q < HMC_MAXL; ++q)
       if (q == l) sg[q] = bits;
   }
-  // ---- heads, software-pipelined over chunks of 32 features ----
+  // ---- heads, software-pipelined over chunks of 32 features; this thread: features 8 cg .. 8 cg + 7 of a chunk ----
   float loss = 0.f;
-  const float* xrow = D.a.x_dev + (size_t)lrow * D.a.ldx;
+  const float* xrow = D.a.x_dev + (size_t)lrow * D.a.ldx + cg * 8;
 #pragma unroll 1
   for (int k = 0; k <= NC; ++k) {
     // this chunk's data values: issued before the stage so that their latency hides behind the MMAs
-    float4 xv[8];
-    if (k < NC) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = k * 32 + i * 4;
-        xv[i] = (c < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + c))
-                              : make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000),
-                                            __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
-      }
+    float4 x0, x1;
+    {
+      const float qn = __int_as_float(0x7fc00000);
+      const int c = k * 32 + cg * 8;
+      x0 = (k < NC && c < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32)) : make_float4(qn, qn, qn, qn);
+      x1 = (k < NC && c + 4 < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32 + 4)) : make_float4(qn, qn, qn, qn);
     }
     const uint32_t it = C.img_it;
     const int n_img = (k > 0 ? 1 : 0) + (k < NC ? 1 : 0);
@@ -228,105 +220,98 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
       if (k < NC) ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, j), 0u);
     });
     if (k == NC) break;
-    const float* bm = C.small + P.off_bm + k * 32;
-    const float* bv = C.small + P.off_bv + k * 32;
+    const float* bm = C.small + P.off_bm + k * 32 + cg * 8;
+    const float* bv = C.small + P.off_bv + k * 32 + cg * 8;
+    uint32_t rm[8], rr[8];
+    umma::ld8(C.trow + HT_D + cg * 8, rm);
+    umma::ld8(C.trow + HT_D + 32 + cg * 8, rr);
+    umma::wait_ld();
+    const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    uint32_t mh[8], ml[8], vh[8], vl[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      uint32_t rm[16], rr[16];
-      umma::ld16(C.trow + HT_D + h * 16, rm);
-      umma::ld16(C.trow + HT_D + 32 + h * 16, rr);
-      umma::wait_ld();
-      uint32_t mh[16], ml[16], vh[16], vl[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int q = h * 16 + i;                      // feature k*32 + q
-        const float4 x4 = xv[q >> 2];
-        const float xs = (q & 3) == 0 ? x4.x : ((q & 3) == 1 ? x4.y : ((q & 3) == 2 ? x4.z : x4.w));
-        const bool obs = (k * 32 + q < P.x_dim) && (xs == xs);                         // NaN = missing
-        const float mu = __uint_as_float(rm[i]) + bm[q];
-        const float raw = __uint_as_float(rr[i]) + bv[q];
-        const float e = expf(-fabsf(raw));
-        const float s2 = (fmaxf(raw, 0.f) + log1pf(e)) + 1e-6f;                        // softplus + eps
-        const float inv = 1.f / s2;
-        const float d = obs ? xs - mu : 0.f;
-        const float r1 = 1.f / (1.f + e);
-        const float sig = raw >= 0.f ? r1 : e * r1;
-        if (want_lp && obs) loss += (d * d) * (0.5f * inv) + 0.5f * logf(s2);           // bgm/base.py:683-684
-        const float dmu = obs ? -d * inv : 0.f;
-        const float draw = obs ? (0.5f * inv - (0.5f * d * d) * (inv * inv)) * sig : 0.f;
-        umma::split_tf32(dmu, mh[i], ml[i]);
-        umma::split_tf32(draw, vh[i], vl[i]);
-      }
-      umma::st16(C.trow + HT_B_HI + h * 16, mh);
-      umma::st16(C.trow + HT_B_LO + h * 16, ml);
-      umma::st16(C.trow + HT_B_HI + 32 + h * 16, vh);
-      umma::st16(C.trow + HT_B_LO + 32 + h * 16, vl);
+    for (int i = 0; i < 8; ++i) {
+      const bool obs = (k * 32 + cg * 8 + i < P.x_dim) && (xs[i] == xs[i]);           // NaN = missing
+      const float mu = __uint_as_float(rm[i]) + bm[i];
+      const float raw = __uint_as_float(rr[i]) + bv[i];
+      const float e = expf(-fabsf(raw));
+      const float s2 = (fmaxf(raw, 0.f) + log1pf(e)) + 1e-6f;                          // softplus + eps
+      const float inv = 1.f / s2;
+      const float d = obs ? xs[i] - mu : 0.f;
+      const float r1 = 1.f / (1.f + e);
+      const float sig = raw >= 0.f ? r1 : e * r1;
+      if (want_lp && obs) loss += (d * d) * (0.5f * inv) + 0.5f * logf(s2);             // bgm/base.py:683-684
+      const float dmu = obs ? -d * inv : 0.f;
+      const float draw = obs ? (0.5f * inv - (0.5f * d * d) * (inv * inv)) * sig : 0.f;
+      umma::split_tf32(dmu, mh[i], ml[i]);
+      umma::split_tf32(draw, vh[i], vl[i]);
     }
+    umma::st8(C.trow + HT_B_HI + cg * 8, mh);
+    umma::st8(C.trow + HT_B_LO + cg * 8, ml);
+    umma::st8(C.trow + HT_B_HI + 32 + cg * 8, vh);
+    umma::st8(C.trow + HT_B_LO + 32 + cg * 8, vl);
   }
   // ---- d loss / d h_nh -> through the last LeakyReLU -> A ----
   {
-    unsigned long long bits = 0ull;
+    uint32_t bits = 0u;
 #pragma unroll
     for (int q = 0; q < HMC_MAXL; ++q)
       if (q == nh - 1) bits = sg[q];
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      uint32_t r[16];
-      umma::ld16(C.trow + HT_DH + h * 16, r);
-      umma::wait_ld();
-      ht_mask16(r, bits, h * 16, C.trow + HT_A_HI + h * 16, C.trow + HT_A_LO + h * 16);
-    }
+    uint32_t r[16];
+    umma::ld16(C.trow + HT_DH + cg * 16, r);
+    umma::wait_ld();
+    ht_mask16(r, bits, tA_hi, tA_lo);
   }
   // ---- backward hidden layers nh..2: d loss / d h_{l-1} = (d loss / d a_l) W_l^T ----
-  float ga[64];
+  float ga[16];
 #pragma unroll 1
   for (int l = nh - 1; l >= 1; --l) {
     const uint32_t it = C.img_it;
     ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
-    unsigned long long bits = 0ull;
+    uint32_t bits = 0u;
 #pragma unroll
     for (int q = 0; q < HMC_MAXL; ++q)
       if (q == l - 1) bits = sg[q];
+    uint32_t r[16];
+    umma::ld16(C.trow + HT_D + cg * 16, r);
+    umma::wait_ld();
     if (l > 1) {
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        uint32_t r[16];
-        umma::ld16(C.trow + HT_D + h * 16, r);
-        umma::wait_ld();
-        ht_mask16(r, bits, h * 16, C.trow + HT_A_HI + h * 16, C.trow + HT_A_LO + h * 16);
-      }
+      ht_mask16(r, bits, tA_hi, tA_lo);
     } else {
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        uint32_t r[16];
-        umma::ld16(C.trow + HT_D + h * 16, r);
-        umma::wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float g = __uint_as_float(r[i]);
-          ga[h * 16 + i] = ((bits >> (h * 16 + i)) & 1ull) ? g : 0.2f * g;
-        }
+      for (int i = 0; i < 16; ++i) {
+        const float g = __uint_as_float(r[i]);
+        ga[i] = ((bits >> i) & 1u) ? g : 0.2f * g;
       }
     }
   }
-  // ---- layer 1 transposed on the FMA pipe: d loss / d z_in[d] = sum_j ga[j] W1[d][j] ----
+  // ---- layer 1 transposed on the FMA pipe: partial d loss / d z_in[d] over this thread's 16 columns; the four
+  // partials of a row (and of the likelihood loss) meet in shared memory and are added in a fixed order ----
+  float* xc = C.xch + (size_t)cg * (ZMAX + 1) * HT_ROWS + C.r_in_tile;
 #pragma unroll
   for (int d = 0; d < ZMAX; ++d) {
-    float s = 0.f;
     if (d < zd) {
+      float sacc = 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; j += 4) {
+      for (int j = 0; j < 16; j += 4) {
         const float4 w = *reinterpret_cast<const float4*>(W1 + d * 64 + j);
-        s = fmaf(ga[j], w.x, s); s = fmaf(ga[j + 1], w.y, s); s = fmaf(ga[j + 2], w.z, s); s = fmaf(ga[j + 3], w.w, s);
+        sacc = fmaf(ga[j], w.x, sacc); sacc = fmaf(ga[j + 1], w.y, sacc);
+        sacc = fmaf(ga[j + 2], w.z, sacc); sacc = fmaf(ga[j + 3], w.w, sacc);
       }
+      xc[d * HT_ROWS] = sacc;
     }
-    gz[d] = s;
   }
-  return loss;
+  xc[ZMAX * HT_ROWS] = loss;
+  __syncthreads();
+  const float* x0p = C.xch + C.r_in_tile;
+  const int strd = (ZMAX + 1) * HT_ROWS;
+#pragma unroll
+  for (int d = 0; d < ZMAX; ++d)
+    gz[d] = d < zd ? (x0p[d * HT_ROWS] + x0p[strd + d * HT_ROWS]) + (x0p[2 * strd + d * HT_ROWS] + x0p[3 * strd + d * HT_ROWS]) : 0.f;
+  return (x0p[ZMAX * HT_ROWS] + x0p[strd + ZMAX * HT_ROWS]) + (x0p[2 * strd + ZMAX * HT_ROWS] + x0p[3 * strd + ZMAX * HT_ROWS]);
 }
 
 template <int ZMAX>
-__global__ void __launch_bounds__(HT_ROWS, 1)
+__global__ void __launch_bounds__(HT_THREADS, 1)
 hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ stream, const float* __restrict__ small_g,
               const __grid_constant__ HmcDev D) {
   extern __shared__ __align__(128) float smem[];
@@ -351,12 +336,15 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
   C.ring = smem;
   float* small_s = smem + HT_SLOTS * HT_IMG_FLOATS;
   C.small = small_s;
+  C.xch = small_s + P.small_floats;
+  C.cg = warp >> 2;
+  C.r_in_tile = (warp & 3) * 32 + lane;
   C.full = full;
   C.mma_bar = umma::smem_addr(&mma_bar_s);
   C.img_it = 0;
   C.img_total = (uint32_t)my_blocks * (uint32_t)evals_per_block * (uint32_t)P.n_img;
   C.mma_parity = 0;
-  C.issuer_warp = warp == 3;
+  C.issuer_warp = warp == 15;
   if (tid == 0) {
     for (int s = 0; s < HT_SLOTS; ++s) mbar_init(full + s, 1);
     umma::mbar_init(C.mma_bar, 1);
@@ -364,19 +352,21 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
     for (int s = 0; s < HT_SLOTS; ++s)
       if ((uint32_t)s < C.img_total) ht_fill(C, (uint32_t)s, s);
   }
-  for (int i = tid; i < P.small_floats; i += HT_ROWS) small_s[i] = small_g[i];
+  for (int i = tid; i < P.small_floats; i += HT_THREADS) small_s[i] = small_g[i];
   if (warp == 0) umma::tmem_alloc512(&tmem_slot);
   umma::fence_before_sync();
   __syncthreads();
   umma::fence_after_sync();
   C.tbase = __shfl_sync(0xffffffffu, tmem_slot, 0);
-  C.trow = C.tbase + ((uint32_t)(warp * 32) << 16);
+  C.trow = C.tbase + ((uint32_t)((warp & 3) * 32) << 16);
   const float eps = (D.mode == HMC_RUN && A.step_dev) ? *A.step_dev : 0.f;
 
   for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
-    const int row = b * HT_ROWS + tid;
-    const bool valid = row < n_rows;
-    const int lrow = valid ? row : n_rows - 1;
+    const int row = b * HT_ROWS + C.r_in_tile;
+    const bool owner = C.cg == 0;               // one of the row's four threads owns the outputs
+    const bool valid = row < n_rows && owner;
+    const bool in_range = row < n_rows;
+    const int lrow = in_range ? row : n_rows - 1;
     const int64_t grow = A.row_offset + lrow;
     float z[ZMAX], p[ZMAX], g[ZMAX], gz[ZMAX];
 #pragma unroll
