@@ -304,13 +304,22 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
       for (int d = 0; d < zd; ++d) { T.bn_mean[d] = P.bn_mean[d]; T.bn_inv[d] = P.bn_inv[d]; T.bn_beta[d] = P.bn_beta[d]; }
       for (int l = 1; l < nh; ++l)                              // forward hidden layers 2..nh: B[k][n] = W_l[k][n]
         ht_add_image(tstream, [&](int k, int n) { return Wl[l][(size_t)k * 64 + n]; });
-      for (int c = 0; c < T.n_chunks; ++c) {
+      // head images in the order the software pipeline of hmc_tc.cuh consumes them:
+      // HF_0; then per chunk k: HB_{k-1} (k > 0), HF_{k+1} (k + 1 < NC); finally HB_{NC-1}
+      auto add_hf = [&](int c) {   // head forward: B[k][n] = (n < 32 ? Wm : Wv)[k][feature]
         auto feat = [&](int q) { return c * 32 + (q & 31); };
-        // head forward: B[k][n] = (n < 32 ? Wm : Wv)[k][feature]
         ht_add_image(tstream, [&](int k, int n) { return feat(n) < xd ? (n < 32 ? Wm : Wv)[(size_t)k * xd + feat(n)] : 0.f; });
-        // head backward: B[k][n] = (k < 32 ? Wm : Wv)[n][feature of k]
+      };
+      auto add_hb = [&](int c) {   // head backward: B[k][n] = (k < 32 ? Wm : Wv)[n][feature of k]
+        auto feat = [&](int q) { return c * 32 + (q & 31); };
         ht_add_image(tstream, [&](int k, int n) { return feat(k) < xd ? (k < 32 ? Wm : Wv)[(size_t)n * xd + feat(k)] : 0.f; });
+      };
+      add_hf(0);
+      for (int c = 0; c < T.n_chunks; ++c) {
+        if (c > 0) add_hb(c - 1);
+        if (c + 1 < T.n_chunks) add_hf(c + 1);
       }
+      add_hb(T.n_chunks - 1);
       for (int l = nh - 1; l >= 1; --l)                         // backward hidden layers: B[k][n] = W_l[n][k]
         ht_add_image(tstream, [&](int k, int n) { return Wl[l][(size_t)n * 64 + k]; });
       T.off_W1 = 0;

@@ -30,7 +30,7 @@ constexpr int HT_TPR = 4;                    // threads per row
 constexpr int HT_THREADS = HT_ROWS * HT_TPR;
 constexpr int HT_IMG_FLOATS = 2 * 64 * 64;   // [hi | lo] of a K = 64, N = 64 operand in UMMA layout [K/4][N][4]
 constexpr int HT_SLOTS = 4;
-constexpr uint32_t HT_A_HI = 0, HT_A_LO = 64, HT_D = 128, HT_B_HI = 192, HT_B_LO = 256, HT_DH = 320;
+constexpr uint32_t HT_A_HI = 0, HT_A_LO = 64, HT_D = 128, HT_B_HI = 192, HT_B_LO = 256, HT_DH = 320, HT_D2 = 384;
 
 struct HmcTcProgram {
   int enabled;
@@ -83,11 +83,11 @@ __device__ __forceinline__ void ht_issue(uint32_t tD, uint32_t tA_hi, uint32_t t
 // stage's images, issues, commits; everybody waits for the commit; the consumed slots are refilled.
 //   n_img = 1: D_target (+)= A_src * image;  n_img = 2: first image -> (DH += B), second -> (D = A).
 template <class Issue>
-__device__ __forceinline__ void ht_stage(HtCtx& C, int n_img, Issue issue) {
+__device__ __forceinline__ void ht_stage_begin(HtCtx& C, int n_img, Issue issue) {
   umma::wait_st();
   umma::fence_before_sync();
   __syncthreads();
-  if (C.issuer_warp) {
+  if (n_img > 0 && C.issuer_warp) {
     if (umma::elect_one()) {
       for (int j = 0; j < n_img; ++j) {
         const uint32_t it = C.img_it + j;
@@ -99,16 +99,25 @@ __device__ __forceinline__ void ht_stage(HtCtx& C, int n_img, Issue issue) {
     }
     __syncwarp();
   }
-  umma::mbar_wait(C.mma_bar, C.mma_parity);
-  C.mma_parity ^= 1u;
-  umma::fence_after_sync();
-  if (threadIdx.x == 0) {
-    for (int j = 0; j < n_img; ++j) {
-      const uint32_t it = C.img_it + j;
-      if (it + HT_SLOTS < C.img_total) ht_fill(C, it + HT_SLOTS, it % HT_SLOTS);
+}
+__device__ __forceinline__ void ht_stage_end(HtCtx& C, int n_img) {
+  if (n_img > 0) {
+    umma::mbar_wait(C.mma_bar, C.mma_parity);
+    C.mma_parity ^= 1u;
+    umma::fence_after_sync();
+    if (threadIdx.x == 0) {
+      for (int j = 0; j < n_img; ++j) {
+        const uint32_t it = C.img_it + j;
+        if (it + HT_SLOTS < C.img_total) ht_fill(C, it + HT_SLOTS, it % HT_SLOTS);
+      }
     }
+    C.img_it += n_img;
   }
-  C.img_it += n_img;
+}
+template <class Issue>
+__device__ __forceinline__ void ht_stage(HtCtx& C, int n_img, Issue issue) {
+  ht_stage_begin(C, n_img, issue);
+  ht_stage_end(C, n_img);
 }
 __device__ __forceinline__ uint32_t ht_slot_addr(const HtCtx& C, uint32_t it) {
   return umma::smem_addr(C.ring + (it % HT_SLOTS) * HT_IMG_FLOATS);
@@ -196,35 +205,45 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
     for (int q = 0; q < HMC_MAXL; ++q)
       if (q == l) sg[q] = bits;
   }
-  // ---- heads, software-pipelined over chunks of 32 features; this thread: features 8 cg .. 8 cg + 7 of a chunk ----
+  // ---- heads over chunks of 32 features; this thread: features 8 cg .. 8 cg + 7 of a chunk.  Software pipeline:
+  // while the threads turn chunk k's (mu, raw) (accumulator D_{k&1}) into d loss / d (mu, raw), the tensor cores
+  // run the forward of chunk k+1 (into the other accumulator) and the backward of chunk k-1 (from the operand the
+  // previous iteration published); the new operand is stored only after those MMAs have committed. ----
   float loss = 0.f;
   const float* xrow = D.a.x_dev + (size_t)lrow * D.a.ldx + cg * 8;
-#pragma unroll 1
-  for (int k = 0; k <= NC; ++k) {
-    // this chunk's data values: issued before the stage so that their latency hides behind the MMAs
-    float4 x0, x1;
-    {
-      const float qn = __int_as_float(0x7fc00000);
-      const int c = k * 32 + cg * 8;
-      x0 = (k < NC && c < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32)) : make_float4(qn, qn, qn, qn);
-      x1 = (k < NC && c + 4 < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32 + 4)) : make_float4(qn, qn, qn, qn);
-    }
+  const float qn = __int_as_float(0x7fc00000);
+  auto load_x = [&](int k, float4& a, float4& b) {
+    const int c = k * 32 + cg * 8;
+    a = (k < NC && c < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32)) : make_float4(qn, qn, qn, qn);
+    b = (k < NC && c + 4 < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32 + 4)) : make_float4(qn, qn, qn, qn);
+  };
+  float4 x0, x1;
+  load_x(0, x0, x1);
+  {
     const uint32_t it = C.img_it;
-    const int n_img = (k > 0 ? 1 : 0) + (k < NC ? 1 : 0);
-    ht_stage(C, n_img, [&]() {
+    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
+  }
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    const uint32_t it = C.img_it;
+    const int n_img = (k > 0 ? 1 : 0) + (k + 1 < NC ? 1 : 0);
+    const uint32_t tD_cur = C.tbase + ((k & 1) ? HT_D2 : HT_D), tD_next = C.tbase + ((k & 1) ? HT_D : HT_D2);
+    ht_stage_begin(C, n_img, [&]() {
       uint32_t j = it;
       if (k > 0) {
         ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, j), k > 1 ? 1u : 0u);
         ++j;
       }
-      if (k < NC) ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, j), 0u);
+      if (k + 1 < NC) ht_issue(tD_next, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, j), 0u);
     });
-    if (k == NC) break;
+    float4 xn0, xn1;
+    load_x(k + 1, xn0, xn1);
     const float* bm = C.small + P.off_bm + k * 32 + cg * 8;
     const float* bv = C.small + P.off_bv + k * 32 + cg * 8;
+    const uint32_t tcur = tD_cur + ((uint32_t)((C.r_in_tile >> 5) * 32) << 16);
     uint32_t rm[8], rr[8];
-    umma::ld8(C.trow + HT_D + cg * 8, rm);
-    umma::ld8(C.trow + HT_D + 32 + cg * 8, rr);
+    umma::ld8(tcur + cg * 8, rm);
+    umma::ld8(tcur + 32 + cg * 8, rr);
     umma::wait_ld();
     const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
     uint32_t mh[8], ml[8], vh[8], vl[8];
@@ -245,10 +264,17 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
       umma::split_tf32(dmu, mh[i], ml[i]);
       umma::split_tf32(draw, vh[i], vl[i]);
     }
+    ht_stage_end(C, n_img);        // the backward of chunk k-1 has read the old operand: it may be replaced now
     umma::st8(C.trow + HT_B_HI + cg * 8, mh);
     umma::st8(C.trow + HT_B_LO + cg * 8, ml);
     umma::st8(C.trow + HT_B_HI + 32 + cg * 8, vh);
     umma::st8(C.trow + HT_B_LO + 32 + cg * 8, vl);
+    x0 = xn0;
+    x1 = xn1;
+  }
+  {
+    const uint32_t it = C.img_it;
+    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, it), NC > 1 ? 1u : 0u); });
   }
   // ---- d loss / d h_nh -> through the last LeakyReLU -> A ----
   {
