@@ -123,6 +123,14 @@ __device__ __forceinline__ uint32_t ht_slot_addr(const HtCtx& C, uint32_t it) {
   return umma::smem_addr(C.ring + (it % HT_SLOTS) * HT_IMG_FLOATS);
 }
 
+// 1 / x for x in a safe range (no zero / denormal / inf): MUFU.RCP + one Newton step, within 1 ulp.  The plain
+// division compiles to a range check with a slow-path call per use (~8 more instructions, two uses per feature).
+__device__ __forceinline__ float ht_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
 // bias + LeakyReLU (sign bits of the thread's 16 columns into `bits`) + split, D -> A
 __device__ __forceinline__ void ht_act16(const uint32_t (&r)[16], const float* bias, uint32_t& bits, uint32_t t_hi, uint32_t t_lo) {
   uint32_t hi[16], lo[16];
@@ -238,25 +246,30 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
     });
     float4 xn0, xn1;
     load_x(k + 1, xn0, xn1);
-    const float* bm = C.small + P.off_bm + k * 32 + cg * 8;
-    const float* bv = C.small + P.off_bv + k * 32 + cg * 8;
+    const float4 bm0 = *reinterpret_cast<const float4*>(C.small + P.off_bm + k * 32 + cg * 8),
+                 bm1 = *reinterpret_cast<const float4*>(C.small + P.off_bm + k * 32 + cg * 8 + 4),
+                 bv0 = *reinterpret_cast<const float4*>(C.small + P.off_bv + k * 32 + cg * 8),
+                 bv1 = *reinterpret_cast<const float4*>(C.small + P.off_bv + k * 32 + cg * 8 + 4);
+    const float bm[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
+    const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
     const uint32_t tcur = tD_cur + ((uint32_t)((C.r_in_tile >> 5) * 32) << 16);
     uint32_t rm[8], rr[8];
     umma::ld8(tcur + cg * 8, rm);
     umma::ld8(tcur + 32 + cg * 8, rr);
     umma::wait_ld();
     const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    const int n_here = P.x_dim - (k * 32 + cg * 8);      // features of this thread's group that exist
     uint32_t mh[8], ml[8], vh[8], vl[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const bool obs = (k * 32 + cg * 8 + i < P.x_dim) && (xs[i] == xs[i]);           // NaN = missing
+      const bool obs = (i < n_here) && (xs[i] == xs[i]);                               // NaN = missing
       const float mu = __uint_as_float(rm[i]) + bm[i];
       const float raw = __uint_as_float(rr[i]) + bv[i];
       const float e = expf(-fabsf(raw));
       const float s2 = (fmaxf(raw, 0.f) + log1pf(e)) + 1e-6f;                          // softplus + eps
-      const float inv = 1.f / s2;
+      const float inv = ht_rcp(s2);
       const float d = obs ? xs[i] - mu : 0.f;
-      const float r1 = 1.f / (1.f + e);
+      const float r1 = ht_rcp(1.f + e);
       const float sig = raw >= 0.f ? r1 : e * r1;
       if (want_lp && obs) loss += (d * d) * (0.5f * inv) + 0.5f * logf(s2);             // bgm/base.py:683-684
       const float dmu = obs ? -d * inv : 0.f;
