@@ -39,12 +39,23 @@ def make_case(n, x_dim, z_dim, units, miss, seed=5):
     return params, p, x, w, xn
 
 
-@pytest.mark.parametrize("n,x_dim,z_dim,units,miss", CASES)
-def test_log_posterior_and_gradient_parity(n, x_dim, z_dim, units, miss):
+def engine_model(params, p, engine):
+    """engine: 'simt' | 'tensor' (skips when the net shape has no tensor engine) -- BGM.set_hmc_engine."""
+    m = bgm_product_model(params, p)
+    if engine == 'tensor' and not m.hmc_engine_info()['tensor_available']:
+        pytest.skip("no tensor engine for this net shape (needs >= 2 hidden layers, all 64 wide)")
+    m.set_hmc_engine(engine)
+    assert m.hmc_engine_info()['engine'] == engine
+    return m
+
+
+@pytest.mark.parametrize("engine", ["simt", "tensor"])
+@pytest.mark.parametrize("n,x_dim,z_dim,units,miss", CASES + [(300, 97, 7, (64, 64), 0.5), (129, 32, 12, (64,) * 6, 0.1)])
+def test_log_posterior_and_gradient_parity(n, x_dim, z_dim, units, miss, engine):
     params, p, x, w, xn = make_case(n, x_dim, z_dim, units, miss)
     z = np.random.RandomState(1).standard_normal((n, z_dim)).astype(np.float32)
     want_lp, want_g = bgm.log_posterior_and_grad(p, z, x, w)
-    m = bgm_product_model(params, p)
+    m = engine_model(params, p, engine)
     lp, g = m.get_log_posterior(z, xn, return_grad=True)
     assert lp.shape == (n,) and g.shape == (n, z_dim)
     err = np.abs(lp - want_lp) / np.maximum(1, np.abs(want_lp))
@@ -76,15 +87,16 @@ def compare_hmc(sg, trg, so, tro, log_u, burn_in):
     return clean.mean()
 
 
-@pytest.mark.parametrize("n,x_dim,z_dim,units,miss", CASES[:4])
-def test_hmc_injected_noise_matches_oracle(n, x_dim, z_dim, units, miss):
+@pytest.mark.parametrize("engine", ["simt", "tensor"])
+@pytest.mark.parametrize("n,x_dim,z_dim,units,miss", CASES[:4] + [(300, 97, 7, (64, 64), 0.5)])
+def test_hmc_injected_noise_matches_oracle(n, x_dim, z_dim, units, miss, engine):
     params, p, x, w, xn = make_case(n, x_dim, z_dim, units, miss)
     burn_in, n_mcmc, L, step = 10, 6, 5, 0.02
     nz = hmc_noise(n, z_dim, burn_in + n_mcmc)
     so, tro = bgm.hmc_sampler(p, x, w, z0=nz['z0'], n_mcmc=n_mcmc, burn_in=burn_in, step_size=step,
                               num_leapfrog_steps=L, momentum=nz['momentum'], log_u=nz['log_u'],
                               return_trace=True)
-    m = bgm_product_model(params, p)
+    m = engine_model(params, p, engine)
     sg, trg = m.tfp_mcmc_sampler(xn, n_mcmc=n_mcmc, burn_in=burn_in, step_size=step, num_leapfrog_steps=L,
                                  noise=nz, return_trace=True, verbose=0)
     assert sg.shape == so.shape == (n_mcmc, n, z_dim) and sg.dtype == np.float32
@@ -140,9 +152,10 @@ def test_duplicate_indices_in_ind_x1_add_like_the_reference_gather():
     assert np.isfinite(b).all() and not np.array_equal(b, c)
 
 
-def test_hmc_philox_run_replayed_through_oracle():
+@pytest.mark.parametrize("engine", ["simt", "tensor"])
+def test_hmc_philox_run_replayed_through_oracle(engine):
     params, p, x, w, xn = make_case(200, 10, 3, (64,) * 5, 0.0)
-    m = bgm_product_model(params, p)
+    m = engine_model(params, p, engine)
     burn_in, n_mcmc, L, seed = 10, 10, 10, 42
     sg, trg = m.tfp_mcmc_sampler(xn, n_mcmc=n_mcmc, burn_in=burn_in, step_size=0.01, num_leapfrog_steps=L,
                                  seed=seed, return_trace=True, verbose=0)
