@@ -220,10 +220,16 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
   float loss = 0.f;
   const float* xrow = D.a.x_dev + (size_t)lrow * D.a.ldx + cg * 8;
   const float qn = __int_as_float(0x7fc00000);
+  // (asm volatile: the loads must be ISSUED here, one chunk ahead, not sunk to their first use)
+  auto ldg4 = [](const float* p) -> float4 {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+  };
   auto load_x = [&](int k, float4& a, float4& b) {
     const int c = k * 32 + cg * 8;
-    a = (k < NC && c < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32)) : make_float4(qn, qn, qn, qn);
-    b = (k < NC && c + 4 < D.a.ldx) ? __ldg(reinterpret_cast<const float4*>(xrow + k * 32 + 4)) : make_float4(qn, qn, qn, qn);
+    a = (k < NC && c < D.a.ldx) ? ldg4(xrow + k * 32) : make_float4(qn, qn, qn, qn);
+    b = (k < NC && c + 4 < D.a.ldx) ? ldg4(xrow + k * 32 + 4) : make_float4(qn, qn, qn, qn);
   };
   float4 x0, x1;
   load_x(0, x0, x1);
