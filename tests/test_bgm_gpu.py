@@ -50,7 +50,8 @@ def engine_model(params, p, engine):
 
 
 @pytest.mark.parametrize("engine", ["simt", "tensor"])
-@pytest.mark.parametrize("n,x_dim,z_dim,units,miss", CASES + [(300, 97, 7, (64, 64), 0.5), (129, 32, 12, (64,) * 6, 0.1)])
+@pytest.mark.parametrize("n,x_dim,z_dim,units,miss", CASES + [(300, 97, 7, (64, 64), 0.5), (129, 32, 12, (64,) * 6, 0.1), (70, 33, 16, (64, 64, 64), 0.2),
+                                                          (5, 3, 1, (64, 64), 0.0)])
 def test_log_posterior_and_gradient_parity(n, x_dim, z_dim, units, miss, engine):
     params, p, x, w, xn = make_case(n, x_dim, z_dim, units, miss)
     z = np.random.RandomState(1).standard_normal((n, z_dim)).astype(np.float32)
