@@ -120,7 +120,7 @@ static int hmc_tc_launch(const bgm_hmc* m, HmcDev& D, int n_rows, cudaStream_t s
 #define BGM_HT_LAUNCH(Z)                                                                                              \
   do {                                                                                                                \
     BGM_CUDA_OK(cudaFuncSetAttribute(hmc_tc_kernel<Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
-    hmc_tc_kernel<Z><<<grid, HT_THREADS, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_small_dev, D);                     \
+    hmc_tc_kernel<Z><<<grid, HT_THREADS + 32, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_small_dev, D);                     \
   } while (0)
   if (zmax == 4) BGM_HT_LAUNCH(4);
   else if (zmax == 8) BGM_HT_LAUNCH(8);

@@ -82,12 +82,26 @@ __device__ __forceinline__ void ht_issue(uint32_t tD, uint32_t tA_hi, uint32_t t
 // One MMA stage: the tile's A operands are published (tcgen05.st + fence + CTA barrier), the issuer waits for the
 // stage's images, issues, commits; everybody waits for the commit; the consumed slots are refilled.
 //   n_img = 1: D_target (+)= A_src * image;  n_img = 2: first image -> (DH += B), second -> (D = A).
-template <class Issue>
-__device__ __forceinline__ void ht_stage_begin(HtCtx& C, int n_img, Issue issue) {
+// The tile's 16 math warps never issue: a 17th CONTROL warp waits for the streamed images, issues the MMAs, commits,
+// and refills the ring, following the same barrier schedule (ht_eval_ctrl).  (With the issue on a math warp every
+// other warp waited ~500 cycles per head chunk at the next barrier for it: 17 % of the warp time was barrier stall.)
+//   math warps:    ht_publish()  ... math ...  ht_wait_mma()
+//   control warp:  ht_ctrl_begin(issue) ........ ht_ctrl_end()
+__device__ __forceinline__ void ht_publish() {
   umma::wait_st();
   umma::fence_before_sync();
   __syncthreads();
-  if (n_img > 0 && C.issuer_warp) {
+}
+__device__ __forceinline__ void ht_wait_mma(HtCtx& C) {
+  umma::mbar_wait(C.mma_bar, C.mma_parity);
+  C.mma_parity ^= 1u;
+  umma::fence_after_sync();
+}
+template <class Issue>
+__device__ __forceinline__ void ht_ctrl_begin(HtCtx& C, int n_img, Issue issue) {
+  umma::fence_before_sync();
+  __syncthreads();
+  if (n_img > 0) {
     if (umma::elect_one()) {
       for (int j = 0; j < n_img; ++j) {
         const uint32_t it = C.img_it + j;
@@ -100,12 +114,10 @@ __device__ __forceinline__ void ht_stage_begin(HtCtx& C, int n_img, Issue issue)
     __syncwarp();
   }
 }
-__device__ __forceinline__ void ht_stage_end(HtCtx& C, int n_img) {
+__device__ __forceinline__ void ht_ctrl_end(HtCtx& C, int n_img) {
   if (n_img > 0) {
-    umma::mbar_wait(C.mma_bar, C.mma_parity);
-    C.mma_parity ^= 1u;
-    umma::fence_after_sync();
-    if (threadIdx.x == 0) {
+    ht_wait_mma(C);
+    if ((threadIdx.x & 31) == 0) {
       for (int j = 0; j < n_img; ++j) {
         const uint32_t it = C.img_it + j;
         if (it + HT_SLOTS < C.img_total) ht_fill(C, it + HT_SLOTS, it % HT_SLOTS);
@@ -113,11 +125,6 @@ __device__ __forceinline__ void ht_stage_end(HtCtx& C, int n_img) {
     }
     C.img_it += n_img;
   }
-}
-template <class Issue>
-__device__ __forceinline__ void ht_stage(HtCtx& C, int n_img, Issue issue) {
-  ht_stage_begin(C, n_img, issue);
-  ht_stage_end(C, n_img);
 }
 __device__ __forceinline__ uint32_t ht_slot_addr(const HtCtx& C, uint32_t it) {
   return umma::smem_addr(C.ring + (it % HT_SLOTS) * HT_IMG_FLOATS);
@@ -203,8 +210,8 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
   // ---- hidden layers 2..nh ----
 #pragma unroll 1
   for (int l = 1; l < nh; ++l) {
-    const uint32_t it = C.img_it;
-    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
+    ht_publish();
+    ht_wait_mma(C);
     uint32_t r[16], bits;
     umma::ld16(C.trow + HT_D + cg * 16, r);
     umma::wait_ld();
@@ -233,23 +240,13 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
   };
   float4 x0, x1;
   load_x(0, x0, x1);
-  {
-    const uint32_t it = C.img_it;
-    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
-  }
+  ht_publish();
+  ht_wait_mma(C);
 #pragma unroll 1
   for (int k = 0; k < NC; ++k) {
-    const uint32_t it = C.img_it;
     const int n_img = (k > 0 ? 1 : 0) + (k + 1 < NC ? 1 : 0);
-    const uint32_t tD_cur = C.tbase + ((k & 1) ? HT_D2 : HT_D), tD_next = C.tbase + ((k & 1) ? HT_D : HT_D2);
-    ht_stage_begin(C, n_img, [&]() {
-      uint32_t j = it;
-      if (k > 0) {
-        ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, j), k > 1 ? 1u : 0u);
-        ++j;
-      }
-      if (k + 1 < NC) ht_issue(tD_next, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, j), 0u);
-    });
+    const uint32_t tD_cur = C.tbase + ((k & 1) ? HT_D2 : HT_D);
+    ht_publish();
     float4 xn0, xn1;
     load_x(k + 1, xn0, xn1);
     const float4 bm0 = *reinterpret_cast<const float4*>(C.small + P.off_bm + k * 32 + cg * 8),
@@ -283,7 +280,7 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
       umma::split_tf32(dmu, mh[i], ml[i]);
       umma::split_tf32(draw, vh[i], vl[i]);
     }
-    ht_stage_end(C, n_img);        // the backward of chunk k-1 has read the old operand: it may be replaced now
+    if (n_img > 0) ht_wait_mma(C);   // the backward of chunk k-1 has read the old operand: it may be replaced now
     umma::st8(C.trow + HT_B_HI + cg * 8, mh);
     umma::st8(C.trow + HT_B_LO + cg * 8, ml);
     umma::st8(C.trow + HT_B_HI + 32 + cg * 8, vh);
@@ -291,10 +288,8 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
     x0 = xn0;
     x1 = xn1;
   }
-  {
-    const uint32_t it = C.img_it;
-    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, it), NC > 1 ? 1u : 0u); });
-  }
+  ht_publish();
+  ht_wait_mma(C);
   // ---- d loss / d h_nh -> through the last LeakyReLU -> A ----
   {
     uint32_t bits = 0u;
@@ -310,8 +305,8 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
   float ga[16];
 #pragma unroll 1
   for (int l = nh - 1; l >= 1; --l) {
-    const uint32_t it = C.img_it;
-    ht_stage(C, 1, [&]() { ht_issue(C.tbase + HT_D, C.tbase + HT_A_HI, C.tbase + HT_A_LO, ht_slot_addr(C, it), 0u); });
+    ht_publish();
+    ht_wait_mma(C);
     uint32_t bits = 0u;
 #pragma unroll
     for (int q = 0; q < HMC_MAXL; ++q)
@@ -355,8 +350,46 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
   return (x0p[ZMAX * HT_ROWS] + x0p[strd + ZMAX * HT_ROWS]) + (x0p[2 * strd + ZMAX * HT_ROWS] + x0p[3 * strd + ZMAX * HT_ROWS]);
 }
 
+// The control warp's side of one gradient evaluation: the same barriers as ht_eval, the MMA issue and the ring.
+__device__ __forceinline__ void ht_eval_ctrl(HtCtx& C) {
+  const HmcTcProgram& P = *C.P;
+  const int nh = P.nh, NC = P.n_chunks;
+  const uint32_t tA_hi = C.tbase + HT_A_HI, tA_lo = C.tbase + HT_A_LO;
+  auto plain = [&]() {                                  // D = A * image
+    const uint32_t it = C.img_it;
+    ht_ctrl_begin(C, 1, [&]() { ht_issue(C.tbase + HT_D, tA_hi, tA_lo, ht_slot_addr(C, it), 0u); });
+    ht_ctrl_end(C, 1);
+  };
+#pragma unroll 1
+  for (int l = 1; l < nh; ++l) plain();                 // forward hidden layers
+  plain();                                              // head forward of chunk 0
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    const uint32_t it = C.img_it;
+    const int n_img = (k > 0 ? 1 : 0) + (k + 1 < NC ? 1 : 0);
+    const uint32_t tD_next = C.tbase + ((k & 1) ? HT_D : HT_D2);
+    ht_ctrl_begin(C, n_img, [&]() {
+      uint32_t j = it;
+      if (k > 0) {
+        ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, j), k > 1 ? 1u : 0u);
+        ++j;
+      }
+      if (k + 1 < NC) ht_issue(tD_next, tA_hi, tA_lo, ht_slot_addr(C, j), 0u);
+    });
+    ht_ctrl_end(C, n_img);
+  }
+  {
+    const uint32_t it = C.img_it;
+    ht_ctrl_begin(C, 1, [&]() { ht_issue(C.tbase + HT_DH, C.tbase + HT_B_HI, C.tbase + HT_B_LO, ht_slot_addr(C, it), NC > 1 ? 1u : 0u); });
+    ht_ctrl_end(C, 1);
+  }
+#pragma unroll 1
+  for (int l = nh - 1; l >= 1; --l) plain();            // backward hidden layers
+  __syncthreads();                                      // the math warps' exchange barrier
+}
+
 template <int ZMAX>
-__global__ void __launch_bounds__(HT_THREADS, 1)
+__global__ void __launch_bounds__(HT_THREADS + 32, 1)
 hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ stream, const float* __restrict__ small_g,
               const __grid_constant__ HmcDev D) {
   extern __shared__ __align__(128) float smem[];
@@ -389,15 +422,15 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
   C.img_it = 0;
   C.img_total = (uint32_t)my_blocks * (uint32_t)evals_per_block * (uint32_t)P.n_img;
   C.mma_parity = 0;
-  C.issuer_warp = warp == 15;
-  if (tid == 0) {
+  C.issuer_warp = warp == 16;
+  if (tid == HT_THREADS) {                     // lane 0 of the control warp owns the ring
     for (int s = 0; s < HT_SLOTS; ++s) mbar_init(full + s, 1);
     umma::mbar_init(C.mma_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < HT_SLOTS; ++s)
       if ((uint32_t)s < C.img_total) ht_fill(C, (uint32_t)s, s);
   }
-  for (int i = tid; i < P.small_floats; i += HT_THREADS) small_s[i] = small_g[i];
+  for (int i = tid; i < P.small_floats; i += HT_THREADS + 32) small_s[i] = small_g[i];
   if (warp == 0) umma::tmem_alloc512(&tmem_slot);
   umma::fence_before_sync();
   __syncthreads();
@@ -406,6 +439,10 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
   C.trow = C.tbase + ((uint32_t)((warp & 3) * 32) << 16);
   const float eps = (D.mode == HMC_RUN && A.step_dev) ? *A.step_dev : 0.f;
 
+  if (C.issuer_warp) {                         // control warp: one ht_eval_ctrl per evaluation of the math warps
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x)
+      for (int e = 0; e < evals_per_block; ++e) ht_eval_ctrl(C);
+  } else
   for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const int row = b * HT_ROWS + C.r_in_tile;
     const bool owner = C.cg == 0;               // one of the row's four threads owns the outputs
