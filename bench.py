@@ -109,6 +109,11 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        # an exiting nvidia-smi holds driver locks for a while: launches of this process were seen to stall by
+        # 50-90 ms for up to half a second afterwards (per_step_ms of the first end-to-end pass on a fresh box:
+        # [52.8, 139.0, 55.2, 105.7, 102.3] against a steady 52.7 two seconds later) -- let it settle before the
+        # next timed region
+        time.sleep(2.0)
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, r in self.rows:
@@ -237,10 +242,12 @@ def timed_passes(D, steps, step_fn, ratio_limit=1.3, per_step_ms=None):
         return wall, per, t0
     wall, per, t0 = one()
     first = None
+    scale = 1.0 if per_step_ms is not None else 1e3
     if D.max(max(per) / max(min(per), 1e-9))[0] > ratio_limit:
-        first = {"ms_per_step": 1e3 * wall / steps}
+        first = {"ms_per_step": 1e3 * wall / steps, "per_step_ms": [round(scale * p, 2) for p in per]}
         time.sleep(2.0)
         wall, per, t0 = one()
+    timed_passes.last_per_step_ms = [round(scale * p, 2) for p in per]
     return D.max(wall)[0], first, t0, t0 + wall
 
 
@@ -327,6 +334,7 @@ def run_sampler(args, cfg):
     for i in range(max(args.warmup, 3)):
         e2e_step(i)
     e2e_wall, e2e_first, _, _ = timed_passes(D, args.steps, e2e_step)
+    e2e_per_step = list(timed_passes.last_per_step_ms)
     e2e_value = n * T * n_gpus * args.steps / e2e_wall
 
     if rank == 0:
@@ -404,7 +412,8 @@ def run_sampler(args, cfg):
                     "api": "CausalBGM.predict(%s, sample_y=True, bs=n%s)" % ("x_values=linspace(0,3,20)" if not binary else "binary",
                                                                             ", group=WORLD" if world > 1 else ""),
                     "collectives_per_step": 0 if world == 1 else (2 if not binary else 0),
-                    "ms_per_step": 1e3 * e2e_wall / args.steps, "remeasured_after_disturbed_pass": e2e_first},
+                    "ms_per_step": 1e3 * e2e_wall / args.steps, "per_step_ms": e2e_per_step,
+                    "remeasured_after_disturbed_pass": e2e_first},
             "gpu_launches": (2 if not bnn else T + 1) * args.steps,
             "launches_per_step": launches,
             "kernel": {"name": kname, "engine": sinfo['engine'], "ms_per_launch": kern_ms_mean,
