@@ -20,6 +20,7 @@ struct bgm_hmc {
   // tensor-core engine (hmc_tc.cuh): pre-split operand images of one evaluation + the resident small arrays
   bgm::HmcTcProgram tc;
   float* tc_stream_dev = nullptr;
+  float* tc_stream_fwd_dev = nullptr;   // forward-only stream (posterior-predictive draws)
   float* tc_small_dev = nullptr;
   long long tc_issued = 0;
   int engine = 0;            // 0 auto (tensor when available), 1 SIMT, 2 tensor
@@ -120,7 +121,7 @@ static int hmc_tc_launch(const bgm_hmc* m, HmcDev& D, int n_rows, cudaStream_t s
 #define BGM_HT_LAUNCH(Z)                                                                                              \
   do {                                                                                                                \
     BGM_CUDA_OK(cudaFuncSetAttribute(hmc_tc_kernel<Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));            \
-    hmc_tc_kernel<Z><<<grid, HT_THREADS + 32, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_small_dev, D);                     \
+    hmc_tc_kernel<Z><<<grid, HT_THREADS + 32, smem, st>>>(m->tc, m->tc_stream_dev, m->tc_stream_fwd_dev, m->tc_small_dev, D);                     \
   } while (0)
   if (zmax == 4) BGM_HT_LAUNCH(4);
   else if (zmax == 8) BGM_HT_LAUNCH(8);
@@ -290,7 +291,7 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
   m->issued = pk.issued;
 
   // ---- tensor-core engine: every hidden layer 64 wide, at least two of them ----
-  std::vector<float> tstream, tsmall;
+  std::vector<float> tstream, tstream_fwd, tsmall;
   {
     HmcTcProgram& T = m->tc;
     memset(&T, 0, sizeof(T));
@@ -314,6 +315,14 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
         auto feat = [&](int q) { return c * 32 + (q & 31); };
         ht_add_image(tstream, [&](int k, int n) { return feat(k) < xd ? (k < 32 ? Wm : Wv)[(size_t)n * xd + feat(k)] : 0.f; });
       };
+      // forward-only stream: hidden layers, then the head-forward images in chunk order
+      for (int l = 1; l < nh; ++l)
+        ht_add_image(tstream_fwd, [&](int k, int n) { return Wl[l][(size_t)k * 64 + n]; });
+      for (int c = 0; c < T.n_chunks; ++c) {
+        auto feat = [&](int q) { return c * 32 + (q & 31); };
+        ht_add_image(tstream_fwd, [&](int k, int n) { return feat(n) < xd ? (n < 32 ? Wm : Wv)[(size_t)k * xd + feat(n)] : 0.f; });
+      }
+      T.n_img_fwd = (nh - 1) + T.n_chunks;
       add_hf(0);
       for (int c = 0; c < T.n_chunks; ++c) {
         if (c > 0) add_hb(c - 1);
@@ -353,6 +362,9 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
   }
   if (e == cudaSuccess && m->tc.enabled) {
     e = cudaMalloc(&m->tc_stream_dev, tstream.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&m->tc_stream_fwd_dev, tstream_fwd.size() * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->tc_stream_fwd_dev, tstream_fwd.data(), tstream_fwd.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&m->tc_small_dev, tsmall.size() * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpy(m->tc_stream_dev, tstream.data(), tstream.size() * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(m->tc_small_dev, tsmall.data(), tsmall.size() * sizeof(float), cudaMemcpyHostToDevice);
@@ -364,6 +376,7 @@ int bgm_hmc_create(bgm_hmc** out, const bgm_varnet_desc* g) {
   if (e != cudaSuccess) {
     if (m->image_dev) cudaFree(m->image_dev);
     if (m->tc_stream_dev) cudaFree(m->tc_stream_dev);
+    if (m->tc_stream_fwd_dev) cudaFree(m->tc_stream_fwd_dev);
     if (m->tc_small_dev) cudaFree(m->tc_small_dev);
     delete m;
     return fail(BGM_ERR_CUDA, std::string("bgm_hmc_create: ") + cudaGetErrorString(e));
@@ -381,6 +394,7 @@ void bgm_hmc_destroy(bgm_hmc* m) {
   if (!m) return;
   if (m->image_dev) cudaFree(m->image_dev);
   if (m->tc_stream_dev) cudaFree(m->tc_stream_dev);
+  if (m->tc_stream_fwd_dev) cudaFree(m->tc_stream_fwd_dev);
   if (m->tc_small_dev) cudaFree(m->tc_small_dev);
   delete m;
 }
@@ -509,6 +523,7 @@ int bgm_hmc_predict(const bgm_hmc* m, const float* z_samples_dev, int n_keep, in
   D.noise_x = noise_dev;
   D.n_per_sample = n;
   D.sample0 = sample0;
+  if (hmc_use_tc(m)) return hmc_tc_launch(m, D, n_keep * n, (cudaStream_t)stream);
   return hmc_launch(m, m->prog_fwd, D, n_keep * n, (cudaStream_t)stream);
 }
 
@@ -526,6 +541,7 @@ int bgm_hmc_heads(const bgm_hmc* m, const float* z_dev, int n, float* out_mu_dev
   D.out_x = out_mu_dev;
   D.out_var = out_var_dev;
   D.n_per_sample = n;
+  if (hmc_use_tc(m)) return hmc_tc_launch(m, D, n, (cudaStream_t)stream);
   return hmc_launch(m, m->prog_fwd, D, n, (cudaStream_t)stream);
 }
 

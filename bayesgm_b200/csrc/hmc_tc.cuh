@@ -37,6 +37,7 @@ struct HmcTcProgram {
   int zd, kin, x_dim, nh;
   int n_chunks;                 // ceil(x_dim / 32)
   int n_img;                    // images per gradient evaluation: (nh - 1) + 2 n_chunks + (nh - 1)
+  int n_img_fwd;                // images of the forward-only stream (posterior-predictive draws): (nh - 1) + n_chunks
   float bn_mean[HMC_MAXZ], bn_inv[HMC_MAXZ], bn_beta[HMC_MAXZ];
   // resident small arrays (float offsets): W1 [zd][64], b1 [64], hidden biases [(nh-1)][64], bm, bv [32 n_chunks]
   int off_W1, off_b1, off_bh, off_bm, off_bv, small_floats;
@@ -54,12 +55,13 @@ struct HtCtx {
   int r_in_tile;                // row of the tile (TMEM lane)
   float* xch;                   // shared: [HT_TPR][ZMAX + 1][HT_ROWS] partial sums exchanged between a row's threads
   uint32_t img_it, img_total;   // images consumed so far / in the whole launch (identical in every thread)
+  uint32_t n_img;               // images of one pass over `stream` (the stream is periodic)
   uint32_t mma_parity;
   bool issuer_warp;
 };
 
 __device__ __forceinline__ void ht_fill(const HtCtx& C, uint32_t img_index_in_launch, int slot) {
-  const uint32_t i = img_index_in_launch % (uint32_t)C.P->n_img;
+  const uint32_t i = img_index_in_launch % C.n_img;
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   mbar_expect_tx(C.full + slot, HT_IMG_FLOATS * 4u);
   bulk_g2s(C.ring + slot * HT_IMG_FLOATS, C.stream + (size_t)i * HT_IMG_FLOATS, HT_IMG_FLOATS * 4u, C.full + slot);
@@ -388,10 +390,125 @@ __device__ __forceinline__ void ht_eval_ctrl(HtCtx& C) {
   __syncthreads();                                      // the math warps' exchange barrier
 }
 
+// ---- forward only: posterior-predictive draws x = mu + sqrt(sigma^2) N(0,1) (bgm/base.py:517-521) or the heads ----
+// Same Philox keys and arithmetic as the SIMT engine's predict mode (hmc.cuh).  The forward-only stream holds the
+// hidden layers and the head-forward images; the control warp issues the forward of chunk k+1 while the math warps
+// turn chunk k into draws.
+template <int ZMAX>
+__device__ __forceinline__ void ht_predict(HtCtx& C, const HmcDev& D, const float (&z)[ZMAX], int r, bool rvalid) {
+  const HmcTcProgram& P = *C.P;
+  const int zd = P.zd, nh = P.nh, NC = P.n_chunks;
+  const int cg = C.cg;
+  const float* W1 = C.small + P.off_W1 + cg * 16;
+  const uint32_t tA_hi = C.trow + HT_A_HI + cg * 16, tA_lo = C.trow + HT_A_LO + cg * 16;
+  {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = C.small[P.off_b1 + cg * 16 + i];
+#pragma unroll
+    for (int d = 0; d < ZMAX; ++d) {
+      if (d < zd) {
+        const float zv = (z[d] - P.bn_mean[d]) * P.bn_inv[d] + P.bn_beta[d];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(W1 + d * 64 + i);
+          a[i] = fmaf(zv, w.x, a[i]); a[i + 1] = fmaf(zv, w.y, a[i + 1]);
+          a[i + 2] = fmaf(zv, w.z, a[i + 2]); a[i + 3] = fmaf(zv, w.w, a[i + 3]);
+        }
+      }
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float v = a[i] > 0.f ? a[i] : 0.2f * a[i];
+      umma::split_tf32(v, hi[i], lo[i]);
+    }
+    umma::st16(tA_hi, hi);
+    umma::st16(tA_lo, lo);
+  }
+#pragma unroll 1
+  for (int l = 1; l < nh; ++l) {
+    ht_publish();
+    ht_wait_mma(C);
+    uint32_t rr[16], bits;
+    umma::ld16(C.trow + HT_D + cg * 16, rr);
+    umma::wait_ld();
+    ht_act16(rr, C.small + P.off_bh + (l - 1) * 64 + cg * 16, bits, tA_hi, tA_lo);
+  }
+  ht_publish();
+  ht_wait_mma(C);                                   // head forward of chunk 0
+  const int s_idx = D.sample0 + r / D.n_per_sample;
+  const int64_t grow = D.a.row_offset + (r - (r / D.n_per_sample) * D.n_per_sample);
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    const uint32_t tD_cur = C.tbase + ((k & 1) ? HT_D2 : HT_D);
+    ht_publish();                                    // everybody is done with the accumulator chunk k+1 goes into
+    const int c0 = k * 32 + cg * 8;
+    const float4 bm0 = *reinterpret_cast<const float4*>(C.small + P.off_bm + c0), bm1 = *reinterpret_cast<const float4*>(C.small + P.off_bm + c0 + 4),
+                 bv0 = *reinterpret_cast<const float4*>(C.small + P.off_bv + c0), bv1 = *reinterpret_cast<const float4*>(C.small + P.off_bv + c0 + 4);
+    const float bm[8] = {bm0.x, bm0.y, bm0.z, bm0.w, bm1.x, bm1.y, bm1.z, bm1.w};
+    const float bv[8] = {bv0.x, bv0.y, bv0.z, bv0.w, bv1.x, bv1.y, bv1.z, bv1.w};
+    const uint32_t tcur = tD_cur + ((uint32_t)((C.r_in_tile >> 5) * 32) << 16);
+    uint32_t rm[8], rw[8];
+    umma::ld8(tcur + cg * 8, rm);
+    umma::ld8(tcur + 32 + cg * 8, rw);
+    umma::wait_ld();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + h * 4;
+      float e4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!D.out_var) {
+        if (D.noise_x) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) e4[q] = (c + q < P.x_dim) ? D.noise_x[(size_t)r * P.x_dim + c + q] : 0.f;
+        } else {
+          normal4(D.a.seed, grow, (uint32_t)s_idx, NOISE_PREDICT, (uint32_t)(c >> 2), e4);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = h * 4 + q;
+        const float mu = __uint_as_float(rm[i]) + bm[i];
+        const float s2 = softplus_f(__uint_as_float(rw[i]) + bv[i]) + 1e-6f;
+        if (rvalid && c + q < P.x_dim) {
+          if (D.out_var) {
+            D.out_x[(size_t)r * P.x_dim + c + q] = mu;
+            D.out_var[(size_t)r * P.x_dim + c + q] = s2;
+          } else {
+            D.out_x[(size_t)r * P.x_dim + c + q] = fmaf(e4[q], sqrtf(s2), mu);
+          }
+        }
+      }
+    }
+    if (k + 1 < NC) ht_wait_mma(C);
+  }
+}
+__device__ __forceinline__ void ht_predict_ctrl(HtCtx& C) {
+  const HmcTcProgram& P = *C.P;
+  const int nh = P.nh, NC = P.n_chunks;
+  const uint32_t tA_hi = C.tbase + HT_A_HI, tA_lo = C.tbase + HT_A_LO;
+  auto plain = [&]() {
+    const uint32_t it = C.img_it;
+    ht_ctrl_begin(C, 1, [&]() { ht_issue(C.tbase + HT_D, tA_hi, tA_lo, ht_slot_addr(C, it), 0u); });
+    ht_ctrl_end(C, 1);
+  };
+#pragma unroll 1
+  for (int l = 1; l < nh; ++l) plain();
+  plain();
+#pragma unroll 1
+  for (int k = 0; k < NC; ++k) {
+    const uint32_t it = C.img_it;
+    const int n_img = k + 1 < NC ? 1 : 0;
+    const uint32_t tD_next = C.tbase + ((k & 1) ? HT_D : HT_D2);
+    ht_ctrl_begin(C, n_img, [&]() { ht_issue(tD_next, tA_hi, tA_lo, ht_slot_addr(C, it), 0u); });
+    ht_ctrl_end(C, n_img);
+  }
+}
+
 template <int ZMAX>
 __global__ void __launch_bounds__(HT_THREADS + 32, 1)
-hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ stream, const float* __restrict__ small_g,
-              const __grid_constant__ HmcDev D) {
+hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ stream, const float* __restrict__ stream_fwd,
+              const float* __restrict__ small_g, const __grid_constant__ HmcDev D) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t full[HT_SLOTS];
   __shared__ uint64_t mma_bar_s;
@@ -410,7 +527,9 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
 
   HtCtx C;
   C.P = &P;
-  C.stream = stream;
+  const bool predict = D.mode == HMC_PREDICT;
+  C.stream = predict ? stream_fwd : stream;
+  C.n_img = (uint32_t)(predict ? P.n_img_fwd : P.n_img);
   C.ring = smem;
   float* small_s = smem + HT_SLOTS * HT_IMG_FLOATS;
   C.small = small_s;
@@ -420,7 +539,7 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
   C.full = full;
   C.mma_bar = umma::smem_addr(&mma_bar_s);
   C.img_it = 0;
-  C.img_total = (uint32_t)my_blocks * (uint32_t)evals_per_block * (uint32_t)P.n_img;
+  C.img_total = (uint32_t)my_blocks * (uint32_t)evals_per_block * C.n_img;
   C.mma_parity = 0;
   C.issuer_warp = warp == 16;
   if (tid == HT_THREADS) {                     // lane 0 of the control warp owns the ring
@@ -441,7 +560,20 @@ hmc_tc_kernel(const __grid_constant__ HmcTcProgram P, const float* __restrict__ 
 
   if (C.issuer_warp) {                         // control warp: one ht_eval_ctrl per evaluation of the math warps
     for (int b = blockIdx.x; b < nblocks; b += gridDim.x)
-      for (int e = 0; e < evals_per_block; ++e) ht_eval_ctrl(C);
+      for (int e = 0; e < evals_per_block; ++e) {
+        if (predict) ht_predict_ctrl(C);
+        else ht_eval_ctrl(C);
+      }
+  } else if (predict) {
+    for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
+      const int row = b * HT_ROWS + C.r_in_tile;
+      const bool rvalid = row < n_rows;
+      const int lrow = rvalid ? row : n_rows - 1;
+      float z[ZMAX];
+#pragma unroll
+      for (int d = 0; d < ZMAX; ++d) z[d] = d < zd ? D.z_in[(size_t)lrow * zd + d] : 0.f;
+      ht_predict<ZMAX>(C, D, z, lrow, rvalid);
+    }
   } else
   for (int b = blockIdx.x; b < nblocks; b += gridDim.x) {
     const int row = b * HT_ROWS + C.r_in_tile;

@@ -315,7 +315,7 @@ int bgm_hmc_info(const bgm_hmc* m, int* smem_bytes, int* n_ops, long long* macs_
  *   2  tensor : every 64-wide product of a gradient evaluation on the 5th-gen tensor cores (tcgen05, operands
  *               and accumulators in TMEM) as error-compensated 3xTF32 (hmc_tc.cuh).  Needs >= 2 hidden layers,
  *               all 64 wide.
- * kind 0 = auto (tensor when available).  bgm_hmc_predict / bgm_hmc_heads always run on the SIMT engine. */
+ * kind 0 = auto (tensor when available); bgm_hmc_predict / bgm_hmc_heads follow the same choice (forward-only pass). */
 int bgm_hmc_set_engine(bgm_hmc* m, int kind);
 int bgm_hmc_engine_info(const bgm_hmc* m, int* active_kind, int* tensor_available, int* tensor_smem_bytes,
                         long long* tensor_issued_macs_per_grad);
