@@ -61,6 +61,14 @@ struct HmcDev {
   int sample0;            // PREDICT: index of the first sample in this call
 };
 
+// 1 / x for x in a safe range (no zero / denormal / inf): MUFU.RCP + one Newton step, within 1 ulp.  A plain division
+// compiles to a range test with a slow-path call per use.
+__device__ __forceinline__ float rcp_newton(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.f), r);
+}
+
 // ------------------------------------------------------------- mbarriers -----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -275,9 +283,9 @@ __device__ __forceinline__ float hmc_program(const HmcProgram& P, const HmcDev& 
               const float raw = acc[i][4 + q];
               const float e = expf(-fabsf(raw));
               const float s2 = (fmaxf(raw, 0.f) + log1pf(e)) + 1e-6f;                // :  softplus + eps
-              const float inv = 1.f / s2;
+              const float inv = rcp_newton(s2);
               const float d = obs ? xs[q] - acc[i][q] : 0.f;
-              const float r1 = 1.f / (1.f + e);
+              const float r1 = rcp_newton(1.f + e);
               const float sig = raw >= 0.f ? r1 : e * r1;
               if (want_lp && obs) loss8[i] += (d * d) * (0.5f * inv) + 0.5f * logf(s2);   // bgm/base.py:683-684
               acc[i][q] = obs ? -d * inv : 0.f;                                           // d loss / d mu

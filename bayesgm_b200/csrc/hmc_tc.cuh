@@ -132,14 +132,6 @@ __device__ __forceinline__ uint32_t ht_slot_addr(const HtCtx& C, uint32_t it) {
   return umma::smem_addr(C.ring + (it % HT_SLOTS) * HT_IMG_FLOATS);
 }
 
-// 1 / x for x in a safe range (no zero / denormal / inf): MUFU.RCP + one Newton step, within 1 ulp.  The plain
-// division compiles to a range check with a slow-path call per use (~8 more instructions, two uses per feature).
-__device__ __forceinline__ float ht_rcp(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return fmaf(r, fmaf(-x, r, 1.f), r);
-}
-
 // bias + LeakyReLU (sign bits of the thread's 16 columns into `bits`) + split, D -> A
 __device__ __forceinline__ void ht_act16(const uint32_t (&r)[16], const float* bias, uint32_t& bits, uint32_t t_hi, uint32_t t_lo) {
   uint32_t hi[16], lo[16];
@@ -272,9 +264,9 @@ __device__ __forceinline__ float ht_eval(HtCtx& C, const HmcDev& D, const float 
       const float raw = __uint_as_float(rr[i]) + bv[i];
       const float e = expf(-fabsf(raw));
       const float s2 = (fmaxf(raw, 0.f) + log1pf(e)) + 1e-6f;                          // softplus + eps
-      const float inv = ht_rcp(s2);
+      const float inv = rcp_newton(s2);
       const float d = obs ? xs[i] - mu : 0.f;
-      const float r1 = ht_rcp(1.f + e);
+      const float r1 = rcp_newton(1.f + e);
       const float sig = raw >= 0.f ? r1 : e * r1;
       if (want_lp && obs) loss += (d * d) * (0.5f * inv) + 0.5f * logf(s2);             // bgm/base.py:683-684
       const float dmu = obs ? -d * inv : 0.f;
