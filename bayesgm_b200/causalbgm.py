@@ -741,9 +741,7 @@ class CausalBGM(object):
         bs = int(batch_size)
         if bs > 32:
             # the fused single-CTA kernels take at most 32 rows: larger mini-batches train on the layered engine
-            if use_egm_init:
-                raise NotImplementedError("bayesgm_b200: egm_init takes mini-batches of at most 32 rows (the fused "
-                                          "gradient-penalty kernel); pass use_egm_init=False or batch_size <= 32")
+            # (the WGAN-GP discriminator step through csrc/disc_big.cuh)
             self._set_layered(True)
         if self._p['save_res']:
             with open('{}/params.txt'.format(self.save_dir), 'w') as f_params:
@@ -988,6 +986,8 @@ class CausalBGM(object):
         p, zd = self._p['v_dim'], sum(self._p['z_dims'])
         freq = int(self._p['g_d_freq'])
         bs = int(batch_size)
+        if bs > 32:          # more than the fused kernels' 32 rows: layered engine, WGAN-GP step through csrc/disc_big.cuh
+            self._set_layered(True)
         xd = self._to_device(data_x, torch).reshape(-1).contiguous()
         yd = self._to_device(data_y, torch).reshape(-1).contiguous()
         vd = self._to_device(data_v, torch).contiguous()

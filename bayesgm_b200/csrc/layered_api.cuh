@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "layered.cuh"
+#include "disc_big.cuh"
 
 namespace bgm {
 namespace lt {
@@ -181,6 +182,7 @@ static size_t disc_bytes(const tr::Disc& dz, long long B) {
 static size_t step_bytes(const bgm_lt* t, long long B) {
   size_t b = 3 * pass_bytes(t->g, B) + 2 * pass_bytes(t->e, B) + 2 * pass_bytes(t->f, B) + 2 * pass_bytes(t->h, B);
   b += disc_bytes(t->dz, B) + 16 * (size_t)(4 * B * (t->p + 1 + t->zd + 8) + 512);
+  if (B > 32) b += 4 * tr::disc_big_floats(t->dz, (int)B) + 1024;     // workspace of disc_grad_big_kernel
   return b + (1 << 16);
 }
 static int ensure_arena_bytes(Arena& ar, size_t need) {
@@ -631,7 +633,7 @@ int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, 
   using namespace bgm;
   using namespace bgm::lt;
   if (!t || !z_dev || !v_dev || !losses_dev) return fail(BGM_ERR_ARG, "bgm_lt_disc_grad: null argument");
-  if (bs < 2 || bs > 32) return fail(BGM_ERR_UNSUPPORTED, "bgm_lt_disc_grad: the gradient-penalty kernel takes batches of 2..32 rows");
+  if (bs < 2) return fail(BGM_ERR_ARG, "bgm_lt_disc_grad: batch size must be >= 2");
   cudaStream_t st0 = (cudaStream_t)stream;
   int rc = ensure_arena(t, bs);
   if (rc) return rc;
@@ -666,7 +668,17 @@ int bgm_lt_disc_grad(bgm_lt* t, const float* z_dev, const float* v_dev, int bs, 
     A.z = zsrc; A.v = nullptr; A.zenc_in = eA.out();
     A.epsilon = epsilon; A.eps_dev = dev ? &t->sc_dev->eps : nullptr;
     A.gp_weight = gp_weight; A.losses = losses_dev; A.wm = t->wm_disc; A.stage = t->stage_disc;
-    tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, st>>>(A);
+    if (bs <= 32) {
+      tr::disc_grad_kernel<<<1, tr::NTH, t->smem_disc, st>>>(A);
+    } else {     // more than 32 rows: the same algorithm on a global workspace (disc_big.cuh)
+      tr::BigDiscArgs G;
+      memset(&G, 0, sizeof(G));
+      G.dz = t->dz; G.B = bs; G.zd = t->zd; G.theta_d = t->theta[1]; G.grad_d = t->grad[1];
+      G.z = zsrc; G.zenc = eA.out(); G.epsilon = epsilon; G.eps_dev = A.eps_dev; G.gp_weight = gp_weight;
+      G.losses = losses_dev;
+      G.ws = t->arena.get<float>(tr::disc_big_floats(t->dz, bs));
+      tr::disc_grad_big_kernel<<<1, 512, 0, st>>>(G);
+    }
     return arena_ok(t->arena, "bgm_lt_disc_grad");
   });
   if (rc == 0 && t->use_graphs)

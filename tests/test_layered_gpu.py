@@ -72,6 +72,49 @@ def test_bnn_disc_step_gradients(case):
     close(flat, want, 3e-3, "disc gradient")
 
 
+@pytest.mark.parametrize("bs", [33, 96, 257])
+@pytest.mark.parametrize("bnn", [False, True])
+def test_disc_step_gradients_beyond_32_rows(bs, bnn):
+    """train_disc_step (causalbgm/base.py:305-323) on mini-batches the fused kernel cannot hold: the three
+    discriminator passes and the gradient-penalty double backward of csrc/disc_big.cuh against torch autograd."""
+    if bnn:
+        params, nets, m = make_model(BNN_CASES[0])
+    else:
+        params = causal_params(200, [1, 1, 1, 2])
+        nets = causal_nets(params)
+        m = product_model(params, nets)
+        m._set_layered(True)
+    x, y, v = causal_data(bs, params['v_dim'], binary=params['binary_treatment'])
+    z = np.random.RandomState(2).standard_normal((bs, sum(params['z_dims']))).astype(np.float32)
+    if bnn:
+        m.set_noise_counter(9)
+        losses, flat = m.gradients('disc', z, v, epsilon=0.37)
+        dzl, dl, grads = obt.disc_step(params, nets, m.dz_net.as_oracle_params(), z, v, 0.37, seed=77, ctr=9)
+    else:
+        losses, flat = m.gradients('disc', z, v, epsilon=0.37)
+        dzl, dl, grads = otrain.disc_step(params, nets, m.dz_net.as_oracle_params(), z, v, 0.37)
+    np.testing.assert_allclose(losses, [dzl, dl], rtol=5e-4, atol=1e-5)
+    want = np.concatenate([np.asarray(g).ravel() for g in grads])
+    close(flat, want, 3e-3, "disc gradient")
+
+
+def test_fit_with_batch_64_runs_egm_and_iterative_phase():
+    from bayesgm_b200 import CausalBGM
+    from bayesgm_b200.datasets import Sim_Hirano_Imbens_sampler
+    params = dict(dataset='Sim_Hirano_Imbens', output_dir='/tmp/bgm_b200_test', save_res=False, save_model=False,
+                  binary_treatment=False, use_bnn=False, z_dims=[1, 1, 1, 2], v_dim=40, lr_theta=0.001, lr_z=0.001,
+                  g_units=[64] * 3, f_units=[64, 32, 8], h_units=[64, 32, 8], kl_weight=0.0001, lr=0.0002, g_d_freq=5,
+                  use_z_rec=True, e_units=[64] * 3, dz_units=[64, 32, 8])
+    x, y, v = Sim_Hirano_Imbens_sampler(N=256, v_dim=40).load_all()
+    m = CausalBGM(params=params, random_seed=3)
+    w0 = m.get_weights()
+    m.fit(data=(x, y, v), batch_size=64, epochs=1, epochs_per_eval=10, use_egm_init=True, egm_n_iter=8, egm_batches_per_eval=100, verbose=0)
+    w1 = m.get_weights()
+    for k in ('g', 'e', 'f', 'h', 'dz'):
+        assert any(np.abs(a - b).max() > 0 for a, b in zip(w0[k], w1[k])), k
+        assert all(np.isfinite(a).all() for a in w1[k])
+
+
 @pytest.mark.parametrize("case", BNN_CASES)
 def test_bnn_iterative_steps(case):
     params, nets, m = make_model(case)
