@@ -201,6 +201,10 @@ struct bgm_causal {
   long long tc_issued = 0;     // FMA-equivalents per row per evaluation (tensor + FMA pipe)
   int sampler = 0;             // 0: auto, 1: SIMT engine, 2: tensor-core engine
   int tc16 = 0;                // tensor engine with 8 warps per tile (fits in shared memory)
+  // 8-warp-per-tile sampler with the first layers of f and h on the tensor cores too (z_dim <= 6): its own image
+  TcProgram tc16p;
+  float* tc16_image_dev = nullptr;
+  int tc16_l1 = 0;
 };
 
 static int check_data(const char* fn, const bgm_causal* m, const float* x, const float* y, const float* v,
@@ -232,10 +236,25 @@ static int launch_mh_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream
   BGM_CUDA_OK(cudaGetLastError());
   return 0;
 }
+// dynamic shared memory of causal_mh_tc16_kernel<8, true>: image, partials [2][2][128][4], noise [2][128][4] + [2][128][zd - 4]
+static int tc16_l1_smem(const TcProgram& T) {
+  const int n1s = T.zd > 4 ? T.zd - 4 : 0;
+  return T.image_floats * 4 + TC16_XCH_FLOATS * 4 + 2 * TC_ROWS * 16 + 2 * TC_ROWS * n1s * 4;
+}
 template <int ZMAX>
 static int launch_mh_tc_t(const bgm_causal* m, const MhDev& D, int grid, cudaStream_t st) {
   if (m->tc16 && ZMAX <= 12) {   // 8 warps per tile (128 registers per thread: spills beyond zd = 12)
-    auto k = causal_mh_tc16_kernel<ZMAX>;
+    if constexpr (ZMAX == 8) {
+      if (m->tc16_l1) {          // first layers of f and h on the tensor cores as well
+        auto k = causal_mh_tc16_kernel<ZMAX, true>;
+        const int smem = tc16_l1_smem(m->tc16p);
+        BGM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        k<<<grid, 512, smem, st>>>(m->tc16p, m->tc16_image_dev, D);
+        BGM_CUDA_OK(cudaGetLastError());
+        return 0;
+      }
+    }
+    auto k = causal_mh_tc16_kernel<ZMAX, false>;
     const int smem = m->tc_smem_bytes + (ZMAX == 8 ? 2 : 1) * TC16_XCH_FLOATS * 4;
     BGM_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     k<<<grid, 512, smem, st>>>(m->tc, m->tc_image_dev, D);
@@ -412,14 +431,18 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   P.per_warp_floats = (ACT_ROWS + kin + SCR_SLOTS) * TILE_ROWS;
 
   // ---- tensor-core engine: g hidden layers 64 wide, projected likelihood, standard f / h ----
-  TcProgram T;
+  TcProgram T, T16;
   memset(&T, 0, sizeof(T));
-  std::vector<float> tc_image;
+  memset(&T16, 0, sizeof(T16));
+  std::vector<float> tc_image, tc16_image;
   long long tc_issued = 0;
-  {
-    bool ok = proj_dim == 64 && g.L >= 3 && g.L - 1 <= TC_MAX_MMA && small_net_shape(f) && small_net_shape(h);
-    for (int l = 1; l < g.L; ++l) ok = ok && g.dims[l] == 64;
-    if (ok) {
+  bool tc_ok = proj_dim == 64 && g.L >= 3 && g.L - 1 <= TC_MAX_MMA && small_net_shape(f) && small_net_shape(h);
+  for (int l = 1; l < g.L; ++l) tc_ok = tc_ok && g.dims[l] == 64;
+  // l1 = false: the image of causal_mh_tc_kernel / causal_effect_tc_kernel / causal_mh_tc16_kernel<ZMAX, false>;
+  // l1 = true: the image of causal_mh_tc16_kernel<8, true> -- no fp32 first layers of f / h and no effect-only pieces,
+  // but [z.., x, 0.., 1] (8) -> [f_h1 | h_h1] (128) as tf32 hi / lo images
+  auto pack_tc = [&](TcProgram& T, std::vector<float>& tc_image, bool l1) {
+    {
       T.zd = zd; T.p = v_dim; T.binary = P.binary;
       T.s2v = P.s2v; T.s2x = P.s2x; T.s2y = P.s2y;
       T.n_mma = g.L - 1;
@@ -440,12 +463,27 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
         for (int c = 0; c < 8; ++c) { b3[c] = f.b[2][c]; b3[8 + c] = h.b[2][c]; }
         pack_mma_k64(tc_image, w3, 16, T.w3_hi, T.w3_lo);
         T.b3 = push_floats(tc_image, b3.data(), 16);
-        // the effect kernel runs f alone: f_h2 (32) -> [f_h3 (8) | 0 (8)]
-        std::vector<float> f3((size_t)32 * 16, 0.f);
-        for (int k = 0; k < 32; ++k)
-          for (int c = 0; c < 8; ++c) f3[(size_t)k * 16 + c] = f.W[2][(size_t)k * 8 + c];
-        pack_mma_k64(tc_image, f3, 16, T.f3_hi, T.f3_lo, 32);
-        T.fb3 = push_floats(tc_image, f.b[2].data(), 8);
+        if (!l1) {
+          // the effect kernel runs f alone: f_h2 (32) -> [f_h3 (8) | 0 (8)]
+          std::vector<float> f3((size_t)32 * 16, 0.f);
+          for (int k = 0; k < 32; ++k)
+            for (int c = 0; c < 8; ++c) f3[(size_t)k * 16 + c] = f.W[2][(size_t)k * 8 + c];
+          pack_mma_k64(tc_image, f3, 16, T.f3_hi, T.f3_lo, 32);
+          T.fb3 = push_floats(tc_image, f.b[2].data(), 8);
+        } else {
+          // rows: input j of [z_0 .. z_{zd-1}, x, 0.., 1 (row 7)]; columns: f_h1 (64) | h_h1 (64)
+          std::vector<float> w1((size_t)8 * 128, 0.f);
+          for (size_t r = 0; r < f_rows.size(); ++r)
+            for (int c = 0; c < 64; ++c) w1[(size_t)f_rows[r] * 128 + c] = f.W[0][r * 64 + c];
+          for (size_t r = 0; r < h_rows.size(); ++r)
+            for (int c = 0; c < 64; ++c) w1[(size_t)h_rows[r] * 128 + 64 + c] = h.W[0][r * 64 + c];
+          for (int c = 0; c < 64; ++c) {
+            w1[(size_t)7 * 128 + c] = f.b[0][c];
+            w1[(size_t)7 * 128 + 64 + c] = h.b[0][c];
+          }
+          T.l1_k = 8;
+          pack_mma_k64(tc_image, w1, 128, T.l1_hi, T.l1_lo, 8);
+        }
       }
       for (int m = 0; m + 1 < T.n_mma; ++m) T.gb[m] = push_floats(tc_image, g.b[m + 1].data(), 64);
       T.gW1 = push_floats(tc_image, g.W[0].data(), (size_t)zd * 64);
@@ -455,10 +493,12 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
       for (int k = 0; k < 64; ++k) wsig[k] = g.W[g.L - 1][(size_t)k * NL + v_dim];
       T.wsig = push_floats(tc_image, wsig.data(), 64);
       T.bsig = push_floats(tc_image, &g.b[g.L - 1][v_dim], 1);
-      T.fW1 = pack_first_layer(tc_image, f, f_rows, zd, T.fmask);
-      T.fb1 = push_floats(tc_image, f.b[0].data(), 64);
-      T.hW1 = pack_first_layer(tc_image, h, h_rows, zd, T.hmask);
-      T.hb1 = push_floats(tc_image, h.b[0].data(), 64);
+      if (!l1) {
+        T.fW1 = pack_first_layer(tc_image, f, f_rows, zd, T.fmask);
+        T.fb1 = push_floats(tc_image, f.b[0].data(), 64);
+        T.hW1 = pack_first_layer(tc_image, h, h_rows, zd, T.hmask);
+        T.hb1 = push_floats(tc_image, h.b[0].data(), 64);
+      }
       T.fb2 = push_floats(tc_image, f.b[1].data(), 32);
       T.hb2 = push_floats(tc_image, h.b[1].data(), 32);
       T.fW4 = push_floats(tc_image, f.W[3].data(), 16);
@@ -468,10 +508,14 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
       while (tc_image.size() % 4) tc_image.push_back(0.f);
       T.image_floats = (int)tc_image.size();
       T.enabled = 1;
-      // tensor pipe: 3 TF32 products per FMA of the 64x64 layers; FMA pipe: the narrow layers
-      tc_issued = 3LL * (4096LL * T.n_mma + 2 * 64 * 32 + 64 * 16) + (long long)zd * 64 + 64 +
-                  (long long)(f.dims[0] + h.dims[0]) * 64 + 2 * 16;
     }
+  };
+  if (tc_ok) {
+    pack_tc(T, tc_image, false);
+    // tensor pipe: 3 TF32 products per FMA of the 64x64 layers; FMA pipe: the narrow layers
+    tc_issued = 3LL * (4096LL * T.n_mma + 2 * 64 * 32 + 64 * 16) + (long long)zd * 64 + 64 +
+                (long long)(f.dims[0] + h.dims[0]) * 64 + 2 * 16;
+    if (zd + 2 <= 8) pack_tc(T16, tc16_image, true);
   }
 
   int dev = 0, smem_max = 0, sms = 0;
@@ -515,12 +559,21 @@ int bgm_causal_create(bgm_causal** out, const int z_dims[4], int v_dim, int bina
   if (T.enabled && m->tc_smem_bytes + 256 > smem_max) m->tc.enabled = 0;
   m->tc16 = m->tc.enabled && m->tc_smem_bytes + (zd <= 8 ? 2 : 1) * TC16_XCH_FLOATS * 4 + 128 <= smem_max &&
             !getenv("BGM_TC8");
+  m->tc16p = T16;
+  m->tc16_l1 = m->tc16 && T16.enabled && tc16_l1_smem(T16) + 128 <= smem_max &&
+               !getenv("BGM_TC16_NO_L1");
   if (e == cudaSuccess && m->tc.enabled) {
     e = cudaMalloc(&m->tc_image_dev, tc_image.size() * sizeof(float));
     if (e == cudaSuccess)
       e = cudaMemcpy(m->tc_image_dev, tc_image.data(), tc_image.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
+  if (e == cudaSuccess && m->tc16_l1) {
+    e = cudaMalloc(&m->tc16_image_dev, tc16_image.size() * sizeof(float));
+    if (e == cudaSuccess)
+      e = cudaMemcpy(m->tc16_image_dev, tc16_image.data(), tc16_image.size() * sizeof(float), cudaMemcpyHostToDevice);
+  }
   if (e != cudaSuccess) {
+    if (m->tc16_image_dev) cudaFree(m->tc16_image_dev);
     if (m->tc_image_dev) cudaFree(m->tc_image_dev);
     if (m->proj_dev) cudaFree(m->proj_dev);
     if (m->image_dev) cudaFree(m->image_dev);
@@ -536,6 +589,7 @@ void bgm_causal_destroy(bgm_causal* m) {
   if (m->image_dev) cudaFree(m->image_dev);
   if (m->proj_dev) cudaFree(m->proj_dev);
   if (m->tc_image_dev) cudaFree(m->tc_image_dev);
+  if (m->tc16_image_dev) cudaFree(m->tc16_image_dev);
   delete m;
 }
 
@@ -571,6 +625,7 @@ int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_a
     const int zd = m->prog.zd;
     int smem = m->tc_smem_bytes;
     if (m->tc16 && zd <= 12) smem += (zd <= 8 ? 2 : 1) * TC16_XCH_FLOATS * 4;
+    if (m->tc16_l1) smem = tc16_l1_smem(m->tc16p);
     *tensor_smem_bytes = smem;
   }
   if (tensor_issued_macs_per_row) *tensor_issued_macs_per_row = m->tc_issued;
@@ -584,7 +639,8 @@ int bgm_causal_kernel_name(const bgm_causal* m, char* buf, int len) {
   if (use_tc(m) && zd > 8 && zd <= 12) zmax = 12;
   if (use_tc(m) && zd > 16 && zd <= 20) zmax = 20;
   const char* base = !use_tc(m) ? "causal_mh_kernel" : ((m->tc16 && zmax <= 12) ? "causal_mh_tc16_kernel" : "causal_mh_tc_kernel");
-  snprintf(buf, (size_t)len, "%s<%d>", base, zmax);
+  if (use_tc(m) && m->tc16 && zmax <= 12) snprintf(buf, (size_t)len, "%s<%d, %s>", base, zmax, m->tc16_l1 ? "true" : "false");
+  else snprintf(buf, (size_t)len, "%s<%d>", base, zmax);
   return 0;
 }
 

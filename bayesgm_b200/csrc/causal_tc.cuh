@@ -51,6 +51,10 @@ struct TcProgram {
   int fW4, fb4, hW4, hb4;                     // [8][2], [2]
   int f3_hi, f3_lo, fb3;                      // effect kernel: f third layer alone, [8][16][4] (cols 8.. zero)
   int image_floats;
+  // causal_mh_tc16_kernel<ZMAX, true> only (its own image): the first layers of f and h as ONE tensor-core product
+  // [z.., x, 0.., 1] (l1_k = 8 inputs, the ones column last) -> [f_h1 (64) | h_h1 (64)], biases in the row of the ones column,
+  // structural zeros where a net does not read an input: [l1_k/4][128][4] images.  l1_k == 0: not packed.
+  int l1_k, l1_hi, l1_lo;
 };
 
 __device__ __forceinline__ void wg_sync(int wg) {
@@ -647,7 +651,7 @@ __device__ __forceinline__ void act_store16(uint32_t (&r)[16], const float* __re
 
 constexpr int TC16_XCH_FLOATS = 2 * 2 * TC_ROWS * 4;   // [slot][half][row][4] exchange buffer (x2: partials, noise)
 
-template <int ZMAX>
+template <int ZMAX, bool L1>
 __global__ void __launch_bounds__(512, 1)
 causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restrict__ image,
                       const __grid_constant__ MhDev D) {
@@ -694,6 +698,14 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
   float* my_n = xn + ((slot * 2 + c) * TC_ROWS + r_in_tile) * 4;
   const float* n0 = xn + ((slot * 2 + 0) * TC_ROWS + r_in_tile) * 4;
   const float* n1 = xn + ((slot * 2 + 1) * TC_ROWS + r_in_tile) * 4;
+  // L1 (the image is 2.3 KB larger): compact noise buffer, group 0 as [slot][row][4], then only the zd - 4 values of
+  // group 1 that are used as [slot][row][zd - 4]
+  const int n1s = P.zd > 4 ? P.zd - 4 : 0;
+  if constexpr (L1) {
+    n0 = xn + (slot * TC_ROWS + r_in_tile) * 4;
+    n1 = xn + 2 * TC_ROWS * 4 + (slot * TC_ROWS + r_in_tile) * n1s;
+    my_n = const_cast<float*>(c == 0 ? n0 : n1);
+  }
 
   const int n = A.n, zd = P.zd;
   const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
@@ -814,9 +826,15 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
       } else {
         if (SHARE_NOISE && t > ta) {
           const float4 a4 = *reinterpret_cast<const float4*>(n0);
-          const float4 b4 = *reinterpret_cast<const float4*>(n1);
           en[0] = a4.x; en[1] = a4.y; en[2] = a4.z; en[3] = a4.w;
-          if (ZMAX > 4) { en[4] = b4.x; en[5] = b4.y; en[6] = b4.z; en[7] = b4.w; }
+          if constexpr (L1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (ZMAX > 4 && i < n1s) en[4 + i] = n1[i];
+          } else {
+            const float4 b4 = *reinterpret_cast<const float4*>(n1);
+            if (ZMAX > 4) { en[4] = b4.x; en[5] = b4.y; en[6] = b4.z; en[7] = b4.w; }
+          }
         }
 #pragma unroll
         for (int d = 0; d < ZMAX; ++d)
@@ -831,11 +849,59 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
       for (int d = 0; d < KINMAX; ++d)
         if (d == zd) in[d] = x_l;
 
-      // ---- f layer 1 (my 32 columns) -> A; stage F2 ----
-      {
-        float a1[32];
-        first_layer32<KINMAX>(wimg + P.fW1, wimg + P.fb1, P.fmask, zd + 1, in, c * 32, a1);
-        split_store32(a1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
+      float a1[32];   // h layer 1 (my 32 columns), kept in registers until f's second-layer MMAs have read A
+      if constexpr (L1) {
+        // ---- f and h layer 1 on the tensor cores: [z', x, 0.., 1] (8 inputs) -> [f_h1 | h_h1] (TMEM columns 64..191) ----
+        {
+          uint32_t w8[8];
+#pragma unroll
+          for (int j = 0; j < 7; ++j) {   // in[] is [z' (zd), x, 0..]: zd + 1 <= 7 entries in use
+            uint32_t hi, lo;
+            umma::split_tf32(in[j], hi, lo);
+            w8[j] = c == 0 ? hi : lo;
+          }
+          w8[7] = c == 0 ? 0x3f800000u : 0u;   // the ones column (row 7 of the images holds the biases)
+          umma::st8(trow + TC_A_HI + c * 16, w8);   // c = 0: hi at columns 0..7, c = 1: lo at columns 16..23
+        }
+        publish();
+        if (issuer_warp) {
+          if (umma::elect_one()) {
+            umma::fence_after_sync();
+            umma::issue_layer<128, 1>(tbase + TC_A_LO, tbase + TC_A_HI, tbase + TC_A_HI + 16,
+                                      wimg_s + 4u * (uint32_t)P.l1_hi, wimg_s + 4u * (uint32_t)P.l1_lo);
+            umma::mma_commit(bar);
+          }
+          __syncwarp();
+        }
+        stage_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {   // f_h1: LeakyReLU + split, back into the A slots (same columns)
+          uint32_t rf[16], lo[16];
+          umma::ld16(trow + TC_A_LO + c * 32 + h * 16, rf);
+          umma::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            float2 h2, l2;
+            umma::split_tf32_x2(leaky_x2(make_float2(__uint_as_float(rf[j]), __uint_as_float(rf[j + 1]))), h2, l2);
+            rf[j] = __float_as_uint(h2.x); rf[j + 1] = __float_as_uint(h2.y);
+            lo[j] = __float_as_uint(l2.x); lo[j + 1] = __float_as_uint(l2.y);
+          }
+          umma::st16(trow + TC_A_HI + c * 32 + h * 16, rf);
+          umma::st16(trow + TC_A_LO + c * 32 + h * 16, lo);
+        }
+        {   // h_h1 (before activation) leaves the D slot: f's second-layer product is about to overwrite it
+          uint32_t rh0[16], rh1[16];
+          umma::ld16(trow + TC_D + c * 32, rh0);
+          umma::ld16(trow + TC_D + c * 32 + 16, rh1);
+          umma::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { a1[j] = __uint_as_float(rh0[j]); a1[16 + j] = __uint_as_float(rh1[j]); }
+        }
+      } else {
+        // ---- f layer 1 (my 32 columns) -> A; stage F2 ----
+        float f1[32];
+        first_layer32<KINMAX>(wimg + P.fW1, wimg + P.fb1, P.fmask, zd + 1, in, c * 32, f1);
+        split_store32(f1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
       }
       publish();
       if (issuer_warp) {
@@ -848,8 +914,15 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
         __syncwarp();
       }
       {
-        float a1[32];   // h layer 1 while f's MMAs run
-        first_layer32<KINMAX>(wimg + P.hW1, wimg + P.hb1, P.hmask, zd + 1, in, c * 32, a1);
+        if constexpr (L1) {   // h layer 1 came out of the same product: only its LeakyReLU is left, while f's MMAs run
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const float2 a = leaky_x2(make_float2(a1[j], a1[j + 1]));
+            a1[j] = a.x; a1[j + 1] = a.y;
+          }
+        } else {              // h layer 1 while f's MMAs run
+          first_layer32<KINMAX>(wimg + P.hW1, wimg + P.hb1, P.hmask, zd + 1, in, c * 32, a1);
+        }
         stage_wait();
         // f_h2 columns [16c, 16c+16) -> A3 columns [16c ..) ; A3 = [f_h2 (32) | h_h2 (32)]
         uint32_t r[16];
@@ -970,7 +1043,13 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
                 if (c * 4 < zd) {
                   float e[4];
                   normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, (uint32_t)c, e);
-                  *reinterpret_cast<float4*>(my_n) = make_float4(e[0], e[1], e[2], e[3]);
+                  if (!L1 || c == 0) {
+                    *reinterpret_cast<float4*>(my_n) = make_float4(e[0], e[1], e[2], e[3]);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                      if (i < n1s) my_n[i] = e[i];
+                  }
                 }
               } else {
 #pragma unroll
