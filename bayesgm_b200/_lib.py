@@ -274,3 +274,19 @@ def ptr(t):
 def stream_ptr():
     import torch
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_MEM_CAP = {}
+
+
+def free_memory_estimate(torch):
+    """Bytes this process can still allocate on the current device, WITHOUT a driver call per use:
+    `cudaMemGetInfo` is an ioctl under the driver's global lock and was measured to block the calling thread for
+    10-90 ms at a time on a shared multi-GPU host (profiles/r02Y_jitter*.log), which made one predict() call in
+    three take 60-160 ms instead of 52.  The driver is asked once per device; afterwards the figure follows the
+    allocator's own counters (capacity seen at the first call minus what torch currently holds in live tensors)."""
+    dev = torch.cuda.current_device()
+    cap = _MEM_CAP.get(dev)
+    if cap is None:
+        cap = _MEM_CAP[dev] = torch.cuda.mem_get_info()[0] + torch.cuda.memory_reserved()
+    return max(cap - torch.cuda.memory_allocated(), 0)

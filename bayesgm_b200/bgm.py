@@ -561,7 +561,7 @@ class BGM(object):
         same_pattern = bool(np.all(miss == miss[0]))                               # :622-623
         miss_idx = np.where(miss[0])[0]
         bs = max(1, int(bs))
-        free = torch.cuda.mem_get_info()[0]
+        free = _lib.free_memory_estimate(torch)
         per_row = 4.0 * n_mcmc * xd * 3.2            # draws + sorted copy + temporaries
         rows = max(bs, int(min(12e9, 0.3 * free) // per_row) // bs * bs)
         q_lo, q_hi = alpha / 2.0, 1.0 - alpha / 2.0

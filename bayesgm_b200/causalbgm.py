@@ -519,7 +519,7 @@ class CausalBGM(object):
             out = torch.empty((n_keep, n), dtype=torch.float32, device='cuda')
             xv, n_x = None, 2
         else:
-            xv = torch.tensor(np.asarray(x_values, dtype=np.float32), device='cuda')
+            xv = self._dose_grid(x_values, torch)
             n_x = len(x_values)
             out = torch.zeros((n_x, n_keep), dtype=torch.float64, device='cuda')
         total = n_keep * n
@@ -547,7 +547,7 @@ class CausalBGM(object):
         _lib.call("bgm_causal_effect_index", _lib.ptr(z_samples), n_keep, n, zd, _lib.ptr(local), _lib.ptr(rowtot),
                   _lib.ptr(rowend), _lib.ptr(scratch), st)
         n_distinct = int(rowend[-1].item())                   # the one host sync of the memoised path
-        if 8.0 * n_distinct * n_x > min(32e9, 0.4 * torch.cuda.mem_get_info()[0]):
+        if 8.0 * n_distinct * n_x > min(32e9, 0.4 * _lib.free_memory_estimate(torch)):
             # the (mu, sigma) table of the distinct states would not fit comfortably: evaluate directly
             del local, rowtot, rowend, scratch
             return self._effect_device(z_samples, n_keep, n, x_values, sample_y, seed, row_offset, noise=noise,
@@ -564,6 +564,15 @@ class CausalBGM(object):
                   _lib.ptr(out) if binary else None, st)
         self.last_distinct_fraction = n_distinct / float(total)
         return out
+
+    def _dose_grid(self, x_values, torch):
+        """x_values on the device; the last grid is kept (a copy from pageable memory is a synchronous driver call)."""
+        xa = np.ascontiguousarray(np.asarray(x_values, dtype=np.float32))
+        key = xa.tobytes()
+        cached = getattr(self, '_xv_cache', None)
+        if cached is None or cached[0] != key:
+            cached = self._xv_cache = (key, torch.tensor(xa, device='cuda'))
+        return cached[1]
 
     def _workspace(self, name, numel, torch):
         """float32 device workspace of at least `numel` elements, kept on the model and grown by >= 1.3x."""
@@ -636,7 +645,7 @@ class CausalBGM(object):
             n_x_ = 2 if binary else len(x_values)
             # kept states + effect draws + the memoised path's index arrays and (worst case) heads
             per_row = float(n_mcmc) * (4.0 * (zd_ + 2) + 8.0 + 8.0 * n_x_)
-            budget = min(24e9, 0.3 * torch.cuda.mem_get_info()[0])
+            budget = min(24e9, 0.3 * _lib.free_memory_estimate(torch))
             step_rows = max(bs, int(budget // per_row) // bs * bs)
         acc_tail = []
         for start in range(0, n_test, step_rows):

@@ -976,7 +976,9 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
         first_layer32<KINMAX>(wimg + P.gW1, wimg + P.gb1, ~0ull, zd, in, c * 32, g1);
         stage_wait();
         // ---- heads: c = 0 finishes f_net (outcome model :809-810), c = 1 h_net (treatment model :803-807) ----
-        float my_loss;
+        // The 8 -> 2 head is taken now (g's first product overwrites the D slot); the loss itself (softplus, log,
+        // division: ~200 instructions of dependent math) waits for one of g's MMA stages, where the thread is idle.
+        float my_loss = 0.f, head_mu, head_raw;
         {
           uint32_t r8[8];
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -994,6 +996,11 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
             mu = fmaf(a, w2.x, mu);
             raw = fmaf(a, w2.y, raw);
           }
+          head_mu = mu;
+          head_raw = raw;
+        }
+        auto head_loss = [&]() {
+          const float mu = head_mu, raw = head_raw;
           if (c == 0) {
             const float s2y = P.s2y >= 0.f ? P.s2y : softplus_f(raw) + 1e-6f;
             const float dy = y_l - mu;
@@ -1005,13 +1012,55 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
             const float dx = x_l - mu;
             my_loss = (dx * dx) / (2.f * s2x) + logf(s2x) / 2.f;
           }
-        }
+        };
         // ---- g_net on the tensor cores ----
         split_store32(g1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
         float sig = 0.f;
+        auto g_issue = [&](int m) {
+          publish();
+          if (issuer_warp) {
+            if (umma::elect_one()) {
+              umma::fence_after_sync();
+              umma::issue_layer_k64<64>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO,
+                                        wimg_s + 4u * (uint32_t)P.w_hi[m], wimg_s + 4u * (uint32_t)P.w_lo[m]);
+              umma::mma_commit(bar);
+            }
+            __syncwarp();
+          }
+        };
+        // first g product: nothing to read back yet.  Under its wait (the stage with the fewest live registers):
+        // the noise of the next iteration and the loss of the f / h head.
+        g_issue(0);
+        if (!A.eps_dev && t + 1 < tb) {
+          if constexpr (SHARE_NOISE) {
+            if (c * 4 < zd) {
+              float e[4];
+              normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, (uint32_t)c, e);
+              if (!L1 || c == 0) {
+                *reinterpret_cast<float4*>(my_n) = make_float4(e[0], e[1], e[2], e[3]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (i < n1s) my_n[i] = e[i];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int g = 0; g < ZMAX / 4; ++g) {
+              if (g * 4 < zd) {
+                float e[4];
+                normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, g, e);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) en[g * 4 + i] = e[i];
+              }
+            }
+          }
+        }
+        head_loss();
+        stage_wait();
 #pragma unroll 1
-        for (int m = 0; m < n_mma; ++m) {
-          if (m > 0) {
+        for (int m = 1; m < n_mma; ++m) {
+          {
             uint32_t ra[16], rb[16];
             umma::ld16(trow + TC_D + c * 32, ra);
             umma::ld16(trow + TC_D + c * 32 + 16, rb);
@@ -1026,46 +1075,9 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
               act_block16<false>(rb, bias + 16, nullptr, sig, ah + 16, al + 16);
             }
           }
-          publish();
-          if (issuer_warp) {
-            if (umma::elect_one()) {
-              umma::fence_after_sync();
-              umma::issue_layer_k64<64>(tbase + TC_D, tbase + TC_A_HI, tbase + TC_A_LO,
-                                        wimg_s + 4u * (uint32_t)P.w_hi[m], wimg_s + 4u * (uint32_t)P.w_lo[m]);
-              umma::mma_commit(bar);
-            }
-            __syncwarp();
-          }
-          // independent work under the MMA waits: noise of the next iteration, this iteration's uniform
-          if (!A.eps_dev) {
-            if (m == 0 && t + 1 < tb) {
-              if constexpr (SHARE_NOISE) {
-                if (c * 4 < zd) {
-                  float e[4];
-                  normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, (uint32_t)c, e);
-                  if (!L1 || c == 0) {
-                    *reinterpret_cast<float4*>(my_n) = make_float4(e[0], e[1], e[2], e[3]);
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                      if (i < n1s) my_n[i] = e[i];
-                  }
-                }
-              } else {
-#pragma unroll
-                for (int g = 0; g < ZMAX / 4; ++g) {
-                  if (g * 4 < zd) {
-                    float e[4];
-                    normal4(A.seed, grow, (uint32_t)(t + 1), NOISE_PROPOSAL, g, e);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) en[g * 4 + i] = e[i];
-                  }
-                }
-              }
-            }
-            // the accept uniform: drawn by the c == 0 thread, handed over with the partials below
-            if (m == 1 && !init_pass && c == 0) u_acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT);
-          }
+          g_issue(m);
+          // the accept uniform under the second wait: drawn by the c == 0 thread, handed over with the partials below
+          if (m == 1 && !A.eps_dev && !init_pass && c == 0) u_acc = uniform1(A.seed, grow, (uint32_t)t, NOISE_ACCEPT);
           stage_wait();
         }
         // ---- my half of the covariate SSE (:800), then the row's two threads swap their partials ----
