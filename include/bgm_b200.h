@@ -84,7 +84,8 @@ int bgm_causal_set_sampler(bgm_causal* m, int kind);
 int bgm_causal_sampler_info(const bgm_causal* m, int* active_kind, int* tensor_available,
                             int* tensor_smem_bytes, long long* tensor_issued_macs_per_row);
 /* Name of the __global__ function the next bgm_causal_mh / bgm_causal_logpost launch runs (as it
- * appears in an ncu launch list), e.g. "causal_mh_tc16_kernel<8>". */
+ * appears in an ncu launch list), e.g. "causal_mh_tc16_kernel<8, true>" (second argument: first layers of f / h on
+ * the tensor cores as well, z_dim <= 6). */
 int bgm_causal_kernel_name(const bgm_causal* m, char* buf, int len);
 
 /* Covariate projection.  With mu_v = h M + b (M: H x v_dim, the last layer of g_net,
