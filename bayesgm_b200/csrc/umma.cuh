@@ -100,17 +100,19 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
-// Packed variant (two values per instruction; sm_100 FMUL2 / FFMA2): Veltkamp's split with the
-// factor 2^13 + 1 -- hi = v rounded to nearest at 24 - 13 = 11 significant bits, lo = v - hi exact.
-// 4 packed FMA-pipe instructions per PAIR instead of IADD3 + LOP3 + FADD per value; the kernels
-// are bound by issue slots, not by the FMA pipe.  Range: v * 8193 must not overflow, i.e. |v| < 4.1e34
-// (beyond that hi is NaN and the proposal is rejected); NaN / inf inputs propagate as NaN.
+// Packed variant (two values per instruction; sm_100 FFMA2), three instructions per PAIR:
+//   s  = rn(v + 8192 v)      one rounding of 8193 v: its error is at most half an 11-bit ulp of v
+//   hi = s - 8192 v          exact (both are multiples of 2^(e_v - 10)): v rounded to nearest at 11 significant bits
+//   lo = v - hi              exact
+// (Veltkamp's split with the factor 2^13 + 1 minus one operation: 8192 v is exact, so the c - (c - v) detour that
+// protects against the rounding of c - v is not needed.  The kernels are bound by issue slots, and the hi / lo split
+// runs once per activation.)  Range: 8193 |v| must not overflow, i.e. |v| < 4.1e34 (beyond that hi is NaN and the
+// proposal is rejected); NaN / inf inputs propagate as NaN.
 __device__ __forceinline__ void split_tf32_x2(float2 v, float2& hi, float2& lo) {
-  const float2 m1 = make_float2(-1.f, -1.f);
-  const float2 c = __fmul2_rn(v, make_float2(8193.f, 8193.f));
-  const float2 t = __ffma2_rn(v, m1, c);     // c - v
-  hi = __ffma2_rn(t, m1, c);                 // c - (c - v)
-  lo = __ffma2_rn(hi, m1, v);                // v - hi
+  const float2 k = make_float2(8192.f, 8192.f), mk = make_float2(-8192.f, -8192.f), m1 = make_float2(-1.f, -1.f);
+  const float2 s = __ffma2_rn(v, k, v);
+  hi = __ffma2_rn(v, mk, s);
+  lo = __ffma2_rn(hi, m1, v);
 }
 
 // ---- descriptors ----
