@@ -346,3 +346,43 @@ def test_memoised_effect_equals_direct_evaluation(binary, engine, n, n_keep):
         else:
             np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-9)   # float64 sums, atomic order only
     assert 0.2 < frac < 0.35
+
+
+def test_first_layer_product_variant_is_selected_and_agrees_with_the_fma_variant(monkeypatch):
+    """z_dim <= 6: the first layers of f_net / h_net run as one tensor-core product (causal_mh_tc16_kernel<8, true>,
+    DESIGN.md 4.1b); z_dim 7..8 and BGM_TC16_NO_L1 keep them on the FMA pipe.  Same Philox streams, same accept
+    rule: the two variants must produce the same chains up to rounding-level ties."""
+    params = causal_params(200, [1, 1, 1, 2])
+    nets = causal_nets(params)
+    data = causal_data(300, 200)
+    m1 = product_model(params, nets, 'tensor')
+    assert m1.sampler_info()['kernel'] == 'causal_mh_tc16_kernel<8, true>'
+    p8 = causal_params(200, [2, 2, 2, 2])
+    assert product_model(p8, causal_nets(p8), 'tensor').sampler_info()['kernel'] == 'causal_mh_tc16_kernel<8, false>'
+    s1, t1 = m1.metropolis_hastings_sampler(data, q_sd=0.5, burn_in=30, n_keep=30, seed=5, return_trace=True, verbose=0)
+    monkeypatch.setenv("BGM_TC16_NO_L1", "1")        # read when the device model is built
+    m0 = product_model(params, nets, 'tensor')
+    assert m0.sampler_info()['kernel'] == 'causal_mh_tc16_kernel<8, false>'
+    s0, t0 = m0.metropolis_hastings_sampler(data, q_sd=0.5, burn_in=30, n_keep=30, seed=5, return_trace=True, verbose=0)
+    same = np.all(t1['accept'] == t0['accept'], axis=0)
+    assert same.mean() >= 0.99, "chains that took a different decision: %d of %d" % ((~same).sum(), same.size)
+    np.testing.assert_array_equal(s1[:, same], s0[:, same])
+    lp_close(t1['lp_prop'][:, same], t0['lp_prop'][:, same])
+
+
+def test_predict_asks_the_driver_for_free_memory_once(monkeypatch):
+    """cudaMemGetInfo blocks for up to ~85 ms on a shared host (profiles/r02Y_predict_jitter_before.log): predict()
+    may call it when the process first sizes its buffers, never per call."""
+    import torch
+    params = causal_params(200, [1, 1, 1, 2])
+    nets = causal_nets(params)
+    data = causal_data(500, 200)
+    m = product_model(params, nets)
+    kw = dict(alpha=0.01, n_mcmc=20, burn_in=20, x_values=np.linspace(0, 3, 5), q_sd=1.0, sample_y=True, bs=500, verbose=0)
+    m.predict(data, **kw)
+    calls = []
+    real = torch.cuda.mem_get_info
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    m.predict(data, **kw)
+    m.predict(data, **kw)
+    assert len(calls) == 0
