@@ -933,10 +933,11 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 b = *reinterpret_cast<const float4*>(wimg + P.fb2 + c * 16 + i * 4);
-          fh2[i * 4 + 0] = leaky_mx(__uint_as_float(r[i * 4 + 0]) + b.x);
-          fh2[i * 4 + 1] = leaky_mx(__uint_as_float(r[i * 4 + 1]) + b.y);
-          fh2[i * 4 + 2] = leaky_mx(__uint_as_float(r[i * 4 + 2]) + b.z);
-          fh2[i * 4 + 3] = leaky_mx(__uint_as_float(r[i * 4 + 3]) + b.w);
+          const float2 a0 = leaky_x2(__fadd2_rn(make_float2(__uint_as_float(r[i * 4 + 0]), __uint_as_float(r[i * 4 + 1])),
+                                                make_float2(b.x, b.y)));
+          const float2 a1p = leaky_x2(__fadd2_rn(make_float2(__uint_as_float(r[i * 4 + 2]), __uint_as_float(r[i * 4 + 3])),
+                                                 make_float2(b.z, b.w)));
+          fh2[i * 4 + 0] = a0.x; fh2[i * 4 + 1] = a0.y; fh2[i * 4 + 2] = a1p.x; fh2[i * 4 + 3] = a1p.y;
         }
         split_store32(a1, trow + TC_A_HI + c * 32, trow + TC_A_LO + c * 32);
         publish();
@@ -957,7 +958,12 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
           // f_h2 -> A3 columns [16c..], h_h2 -> A3 columns [32 + 16c..]
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) umma::split_tf32(fh2[j], hi[j], lo[j]);
+          for (int j = 0; j < 16; j += 2) {
+            float2 h2, l2;
+            umma::split_tf32_x2(make_float2(fh2[j], fh2[j + 1]), h2, l2);
+            hi[j] = __float_as_uint(h2.x); hi[j + 1] = __float_as_uint(h2.y);
+            lo[j] = __float_as_uint(l2.x); lo[j + 1] = __float_as_uint(l2.y);
+          }
           umma::st16(trow + TC_A_HI + c * 16, hi);
           umma::st16(trow + TC_A_LO + c * 16, lo);
           act_store16(rh, wimg + P.hb2 + c * 16, trow + TC_A_HI + 32 + c * 16, trow + TC_A_LO + 32 + c * 16);
@@ -1083,6 +1089,7 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
         // ---- my half of the covariate SSE (:800), then the row's two threads swap their partials ----
         float sse = 0.f;
         {
+          float2 sse2 = make_float2(0.f, 0.f);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t r[16], tt[16];
@@ -1090,11 +1097,13 @@ causal_mh_tc16_kernel(const __grid_constant__ TcProgram P, const float* __restri
             umma::ld16(trow + TC_P + c * 32 + h * 16, tt);
             umma::wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float dd = __uint_as_float(r[j]) - __uint_as_float(tt[j]);
-              sse = fmaf(dd, dd, sse);
+            for (int j = 0; j < 16; j += 2) {   // two running sums (even / odd columns), packed
+              const float2 dd = __ffma2_rn(make_float2(__uint_as_float(tt[j]), __uint_as_float(tt[j + 1])), make_float2(-1.f, -1.f),
+                                           make_float2(__uint_as_float(r[j]), __uint_as_float(r[j + 1])));
+              sse2 = __ffma2_rn(dd, dd, sse2);
             }
           }
+          sse = sse2.x + sse2.y;
         }
         *reinterpret_cast<float4*>(my_x) = make_float4(my_loss, sig, sse, u_acc);
         tile_sync256(slot);
