@@ -103,6 +103,7 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 // Packed variant (two values per instruction; sm_100 FFMA2), three instructions per PAIR:
 //   s  = rn(v + 8192 v)      one rounding of 8193 v: its error is at most half an 11-bit ulp of v
 //   hi = s - 8192 v          exact (both are multiples of 2^(e_v - 10)): v rounded to nearest at 11 significant bits
+//                            (at 10 for mantissas within 2.4e-4 of 2, where 8193 v crosses a binade: still tf32-exact)
 //   lo = v - hi              exact
 // (Veltkamp's split with the factor 2^13 + 1 minus one operation: 8192 v is exact, so the c - (c - v) detour that
 // protects against the rounding of c - v is not needed.  The kernels are bound by issue slots, and the hi / lo split
