@@ -46,3 +46,47 @@ def test_egm_stream_matches_reference_call_order():
     np.testing.assert_array_equal(np.concatenate(got_idx), want_idx)
     np.testing.assert_array_equal(np.concatenate(got_z), want_z)
     np.testing.assert_array_equal(np.random.choice(n, n, replace=False), after)
+
+
+def test_free_memory_estimate_asks_the_driver_once():
+    """_lib.free_memory_estimate (the memory-budget checks of predict()): cudaMemGetInfo once per device, afterwards
+    capacity - live tensor bytes from the allocator's counters."""
+    from bayesgm_b200 import _lib
+
+    class FakeCuda(object):
+        def __init__(self):
+            self.calls, self.allocated, self.reserved, self.device = 0, 0, 0, 0
+
+        def current_device(self):
+            return self.device
+
+        def mem_get_info(self):
+            self.calls += 1
+            return (100 - self.reserved, 128)
+
+        def memory_reserved(self):
+            return self.reserved
+
+        def memory_allocated(self):
+            return self.allocated
+
+    class FakeTorch(object):
+        cuda = FakeCuda()
+
+    t = FakeTorch()
+    saved = dict(_lib._MEM_CAP)
+    _lib._MEM_CAP.clear()
+    try:
+        t.cuda.reserved, t.cuda.allocated = 30, 20
+        assert _lib.free_memory_estimate(t) == 100 - 20          # driver-free 70 + cached 30 = capacity 100
+        t.cuda.allocated = 90
+        assert _lib.free_memory_estimate(t) == 10
+        t.cuda.allocated = 500
+        assert _lib.free_memory_estimate(t) == 0
+        assert t.cuda.calls == 1
+        t.cuda.device = 1                                          # another device: asked once more
+        t.cuda.allocated = 0
+        assert _lib.free_memory_estimate(t) == 100 and t.cuda.calls == 2
+    finally:
+        _lib._MEM_CAP.clear()
+        _lib._MEM_CAP.update(saved)
